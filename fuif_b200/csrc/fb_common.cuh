@@ -1,0 +1,97 @@
+// Shared declarations of the fuif_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/fuif_b200.h"
+
+// ---- host-side objects behind the opaque C-ABI handles -------------------------------------------------------
+
+struct fb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    long long launches = 0;
+    int sm_count = 148;
+    // MANIAC decoder resources (fb_maniac.cu), created lazily
+    void *maniac_state = nullptr;
+};
+
+struct FbChan {
+    fb_plane_desc d;          // mirrors Channel (reference image/image.h:54-91)
+    int16_t *dev = nullptr;   // w*h samples in HBM, row-major, no padding; nullptr = not decoded (data.size()==0)
+};
+
+struct FbXform {
+    int id;
+    std::vector<int> p;
+};
+
+struct fb_image {
+    fb_ctx *ctx = nullptr;
+    fb_image_info info{};
+    std::vector<FbChan> ch;
+    std::vector<FbXform> tr;
+    std::vector<int64_t> group_off;
+    std::vector<int32_t> group_first;
+};
+
+#define FB_CUDA(ctx, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                       \
+            return FB_ERR_CUDA;                                                                     \
+        }                                                                                           \
+    } while (0)
+
+// plane memory (stream-ordered pool)
+int fb_plane_alloc(fb_ctx *ctx, size_t nsamples, int16_t **out);
+void fb_plane_free(fb_ctx *ctx, int16_t *p);
+
+// ---- transform launchers (fb_transforms.cu).  All enqueue on ctx->stream and bump ctx->launches. -------------
+
+// inverse Squeeze steps (reference transform/squeeze.h:81-132, 173-224). res may be nullptr (all-zero residual).
+int fb_launch_inv_hsqueeze(fb_ctx *ctx, const int16_t *avg, const int16_t *res, int16_t *out, int wa, int wr, int h);
+int fb_launch_inv_vsqueeze(fb_ctx *ctx, const int16_t *avg, const int16_t *res, int16_t *out, int w, int ha, int hr);
+// forward Squeeze steps (squeeze.h:135-170, 227-263)
+int fb_launch_fwd_hsqueeze(fb_ctx *ctx, const int16_t *in, int16_t *avg, int16_t *res, int w, int h);
+int fb_launch_fwd_vsqueeze(fb_ctx *ctx, const int16_t *in, int16_t *avg, int16_t *res, int w, int h);
+// YCoCg (ycocg.h:33-63 / 65-95), in place on three planes of n samples each
+int fb_launch_ycocg(fb_ctx *ctx, int16_t *c0, int16_t *c1, int16_t *c2, size_t n, int maxval, int inverse, int clamp_lo, int clamp_hi, int do_clamp);
+// YCbCr (ycbcr.h:33-63 / 65-95)
+int fb_launch_ycbcr(fb_ctx *ctx, int16_t *c0, int16_t *c1, int16_t *c2, size_t n, int minval, int maxval, int inverse);
+// v *= q / v /= q with int16 wrap (quantize.h:32-49 / 56-71)
+int fb_launch_quantize(fb_ctx *ctx, int16_t *p, size_t n, int q, int inverse);
+// final clamp of Image::undo_transforms (image.cpp:107-113)
+int fb_launch_clamp(fb_ctx *ctx, int16_t *p, size_t n, int lo, int hi);
+// 8x8 inverse DCT of one component: 64 coefficient planes (bw x bh each, planes[k] for coefficient k in the
+// reference's block order, nullptr = absent) -> (8bw x 8bh) samples (dct.h:249-296)
+int fb_launch_inv_dct(fb_ctx *ctx, const int16_t *const *planes64_dev, int16_t *out, int bw, int bh, float dc_offset);
+// forward: samples (w x h, edge replicated) -> 64 planes (dct.h:298-336)
+int fb_launch_fwd_dct(fb_ctx *ctx, const int16_t *in, int w, int h, int16_t *const *planes64_dev, int bw, int bh, float dc_offset);
+// per-plane min / max (Channel::actual_minmax, image.cpp:82-92): out2_dev[0]=min out2_dev[1]=max (int32)
+int fb_launch_minmax(fb_ctx *ctx, const int16_t *p, size_t n, int *out2_dev);
+// planar int16 -> interleaved 8/16-bit big-endian samples (write_PAM_file layout)
+int fb_launch_interleave(fb_ctx *ctx, const int16_t *const *planes_dev, int nch, size_t npix, int bytes_per_sample, void *dst);
+
+// ---- MANIAC decode (fb_maniac.cu) ---------------------------------------------------------------------------
+struct FbManiacJob {
+    const uint8_t *bytes_host;
+    size_t nbytes;
+    fb_image *img;            // channel list after meta_apply; planes get allocated + filled, ranges/q filled in
+    size_t body_pos;          // byte offset of the first channel group
+    size_t bytes_to_load;     // 0 = everything
+    int max_properties;
+    int cutoff, alpha;
+    const int64_t *group_index;   // optional
+    int n_groups;
+};
+int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs);
+void fb_maniac_release(fb_ctx *ctx);

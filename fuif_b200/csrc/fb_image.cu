@@ -1,0 +1,830 @@
+// Host side of the fuif_b200 C ABI: contexts, the device-resident Image, the container parser and the
+// transform-chain driver (which kernels run in which order on which planes).  No sample is touched on the
+// host: every plane lives in HBM and every transform is a kernel from fb_transforms.cu.
+#include "fb_common.cuh"
+
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+// ---------------------------------------------------------------------------------------------------------
+// context + plane memory
+// ---------------------------------------------------------------------------------------------------------
+
+extern "C" int fb_ctx_create(int device, void *stream, fb_ctx **out) {
+    if (!out) return FB_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        // fail loudly: there is no CPU fallback in this library
+        fprintf(stderr, "fuif_b200: no usable CUDA device %d (found %d)\n", device, ndev);
+        return FB_ERR_CUDA;
+    }
+    fb_ctx *ctx = new (std::nothrow) fb_ctx();
+    if (!ctx) return FB_ERR_NOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return FB_ERR_CUDA; }
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FB_ERR_CUDA; }
+        ctx->own_stream = true;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    // keep freed plane memory in the stream-ordered pool instead of returning it to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = ctx;
+    return FB_OK;
+}
+
+extern "C" void fb_ctx_destroy(fb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    fb_maniac_release(ctx);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *fb_last_error(fb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int fb_ctx_synchronize(fb_ctx *ctx) {
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FB_OK;
+}
+
+extern "C" long long fb_ctx_launch_count(fb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int fb_plane_alloc(fb_ctx *ctx, size_t nsamples, int16_t **out) {
+    *out = nullptr;
+    size_t bytes = std::max<size_t>(nsamples * sizeof(int16_t), 16);
+    bytes = (bytes + 255) & ~(size_t)255;
+    void *p = nullptr;
+    FB_CUDA(ctx, cudaMallocAsync(&p, bytes, ctx->stream));
+    *out = (int16_t *)p;
+    return FB_OK;
+}
+
+void fb_plane_free(fb_ctx *ctx, int16_t *p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Image helpers
+// ---------------------------------------------------------------------------------------------------------
+
+static void chan_defaults(fb_plane_desc &d) {       // Channel::Channel(), reference image/image.h:68
+    memset(&d, 0, sizeof(d));
+    d.q = 1;
+    d.component = -1;
+}
+
+static inline int s16(int x) { return (int)(int16_t)x; }
+
+static void chan_setzero(fb_plane_desc &d) {        // Channel::setzero, image/image.h:70-74
+    if (d.minval > 0) d.zero = d.minval;
+    else if (d.maxval < 0) d.zero = d.maxval;
+    else d.zero = 0;
+}
+
+static size_t chan_samples(const fb_plane_desc &d) { return (d.w > 0 && d.h > 0) ? (size_t)d.w * d.h : 0; }
+
+// Channel::resize() on an undecoded plane: w*h samples of `zero` (image/image.h:75-77)
+static int chan_materialize(fb_ctx *ctx, FbChan &c) {
+    if (c.dev) return FB_OK;
+    size_t n = chan_samples(c.d);
+    int rc = fb_plane_alloc(ctx, n, &c.dev);
+    if (rc) return rc;
+    if (n) {
+        if (c.d.zero == 0) FB_CUDA(ctx, cudaMemsetAsync(c.dev, 0, n * sizeof(int16_t), ctx->stream));
+        else {
+            // memset16 through the clamp kernel: fill with zero then clamp to [zero, zero]
+            FB_CUDA(ctx, cudaMemsetAsync(c.dev, 0, n * sizeof(int16_t), ctx->stream));
+            rc = fb_launch_clamp(ctx, c.dev, n, c.d.zero, c.d.zero);
+            if (rc) return rc;
+        }
+    }
+    c.d.decoded = 1;
+    return FB_OK;
+}
+
+extern "C" void fb_image_destroy(fb_image *img) {
+    if (!img) return;
+    cudaSetDevice(img->ctx->device);
+    for (auto &c : img->ch) fb_plane_free(img->ctx, c.dev);
+    delete img;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Squeeze bookkeeping (reference transform/squeeze.h:266-408)
+// ---------------------------------------------------------------------------------------------------------
+
+// default_squeeze_parameters, squeeze.h:266-321 (MAX_FIRST_PREVIEW_SIZE = 8, config.h:41)
+static void default_squeeze_parameters(std::vector<int> &p, const fb_image *img) {
+    p.clear();
+    const int nb = img->info.nb_channels, m = img->info.nb_meta_channels;
+    int w = img->ch[m].d.w, h = img->ch[m].d.h;
+    const bool wide = w > h;
+    if (nb > 2 && img->ch[m + 1].d.w == w && img->ch[m + 1].d.h == h) {
+        p.insert(p.end(), {3, m + 1, m + 2});       // horizontal chroma squeeze, residuals appended at the end
+        p.insert(p.end(), {2, m + 1, m + 2});       // vertical chroma squeeze
+    }
+    if (!wide && h > 8) { p.insert(p.end(), {0, m, m + nb - 1}); h = (h + 1) / 2; }
+    while (w > 8 || h > 8) {
+        if (w > 8) { p.insert(p.end(), {1, m, m + nb - 1}); w = (w + 1) / 2; }
+        if (h > 8) { p.insert(p.end(), {0, m, m + nb - 1}); h = (h + 1) / 2; }
+    }
+}
+
+// meta_squeeze, squeeze.h:323-360: channel-list surgery only
+static int meta_squeeze(fb_image *img, std::vector<int> &p) {
+    if (p.empty()) default_squeeze_parameters(p, img);
+    for (size_t i = 0; i + 2 < p.size(); i += 3) {
+        const bool horizontal = p[i] & 1, in_place = !(p[i] & 2);
+        const int beginc = p[i + 1], endc = p[i + 2];
+        const int offset = in_place ? endc + 1 : img->info.nb_meta_channels + img->info.nb_channels;
+        if (beginc < 0 || endc < beginc || endc >= (int)img->ch.size() || offset > (int)img->ch.size()) return FB_ERR_INVALID;
+        for (int c = beginc; c <= endc; c++) {
+            FbChan dummy;
+            chan_defaults(dummy.d);
+            fb_plane_desc &s = img->ch[c].d;
+            dummy.d.hcshift = s.hcshift; dummy.d.vcshift = s.vcshift; dummy.d.component = s.component;
+            if (horizontal) {
+                int w = s.w;
+                s.w = (w + 1) / 2; s.hshift++; s.hcshift++;
+                dummy.d.w = w - (w + 1) / 2; dummy.d.h = s.h;
+            } else {
+                int h = s.h;
+                s.h = (h + 1) / 2; s.vshift++; s.vcshift++;
+                dummy.d.h = h - (h + 1) / 2; dummy.d.w = s.w;
+            }
+            dummy.d.hshift = s.hshift; dummy.d.vshift = s.vshift;
+            img->ch.insert(img->ch.begin() + offset + c - beginc, dummy);
+        }
+    }
+    return FB_OK;
+}
+
+// squeeze(..., inverse=true), squeeze.h:367-388 with inv_hsqueeze/inv_vsqueeze (:81-132, :173-224) as kernels
+static int inv_squeeze(fb_image *img, const std::vector<int> &params) {
+    fb_ctx *ctx = img->ctx;
+    std::vector<int> p = params;
+    if (p.empty()) default_squeeze_parameters(p, img);
+    for (int i = (int)p.size() - 3; i >= 0; i -= 3) {
+        const bool horizontal = p[i] & 1, in_place = !(p[i] & 2);
+        const int beginc = p[i + 1], endc = p[i + 2];
+        const int offset = in_place ? endc + 1 : img->info.nb_meta_channels + img->info.nb_channels;
+        if (beginc < 0 || endc < beginc || offset + endc - beginc >= (int)img->ch.size()) {
+            ctx->err = "Invalid parameters for squeeze transform";
+            return FB_ERR_INVALID;
+        }
+        for (int c = beginc; c <= endc; c++) {
+            FbChan &a = img->ch[c];
+            FbChan &r = img->ch[offset + c - beginc];
+            // the averages must exist; a missing residual plane acts as zeros (squeeze.h:379-383)
+            int rc = chan_materialize(ctx, a);
+            if (rc) return rc;
+            FbChan out;
+            out.d = a.d;
+            if (horizontal) { out.d.w = a.d.w + r.d.w; out.d.hshift--; out.d.hcshift--; }
+            else { out.d.h = a.d.h + r.d.h; out.d.vshift--; out.d.vcshift--; }
+            chan_setzero(out.d);
+            out.d.decoded = 1;
+            rc = fb_plane_alloc(ctx, chan_samples(out.d), &out.dev);
+            if (rc) return rc;
+            if (horizontal) rc = fb_launch_inv_hsqueeze(ctx, a.dev, r.dev, out.dev, a.d.w, r.d.w, a.d.h);
+            else rc = fb_launch_inv_vsqueeze(ctx, a.dev, r.dev, out.dev, a.d.w, a.d.h, r.d.h);
+            if (rc) return rc;
+            fb_plane_free(ctx, a.dev);
+            a = out;
+        }
+        for (int c = 0; c <= endc - beginc; c++) fb_plane_free(ctx, img->ch[offset + c].dev);
+        img->ch.erase(img->ch.begin() + offset, img->ch.begin() + offset + (endc - beginc + 1));
+    }
+    return FB_OK;
+}
+
+// squeeze(..., inverse=false), squeeze.h:389-406 with fwd_hsqueeze/fwd_vsqueeze (:135-170, :227-263)
+static int fwd_squeeze(fb_image *img, const std::vector<int> &params) {
+    fb_ctx *ctx = img->ctx;
+    std::vector<int> p = params;
+    if (p.empty()) default_squeeze_parameters(p, img);
+    for (size_t i = 0; i + 2 < p.size(); i += 3) {
+        const bool horizontal = p[i] & 1, in_place = !(p[i] & 2);
+        const int beginc = p[i + 1], endc = p[i + 2];
+        const int offset = in_place ? endc + 1 : img->info.nb_meta_channels + img->info.nb_channels;
+        if (beginc < 0 || endc < beginc || endc >= (int)img->ch.size() || offset > (int)img->ch.size()) return FB_ERR_INVALID;
+        for (int c = beginc; c <= endc; c++) {
+            FbChan &in = img->ch[c];
+            int rc = chan_materialize(ctx, in);
+            if (rc) return rc;
+            FbChan avg, res;
+            avg.d = in.d;
+            chan_defaults(res.d);
+            if (horizontal) {
+                avg.d.w = (in.d.w + 1) / 2; avg.d.hshift++; avg.d.hcshift++;
+                res.d.w = in.d.w - avg.d.w; res.d.h = in.d.h;
+                res.d.hshift = in.d.hshift + 1; res.d.vshift = in.d.vshift;
+            } else {
+                avg.d.h = (in.d.h + 1) / 2; avg.d.vshift++; avg.d.vcshift++;
+                res.d.w = in.d.w; res.d.h = in.d.h - avg.d.h;
+                res.d.hshift = in.d.hshift; res.d.vshift = in.d.vshift + 1;
+            }
+            res.d.hcshift = in.d.hcshift; res.d.vcshift = in.d.vcshift;
+            res.d.minval = s16(avg.d.minval - avg.d.maxval); res.d.maxval = s16(avg.d.maxval - avg.d.minval);
+            res.d.q = 1; res.d.component = in.d.component;
+            chan_setzero(res.d); chan_setzero(avg.d);
+            avg.d.decoded = res.d.decoded = 1;
+            if ((rc = fb_plane_alloc(ctx, chan_samples(avg.d), &avg.dev))) return rc;
+            if ((rc = fb_plane_alloc(ctx, chan_samples(res.d), &res.dev))) return rc;
+            if (horizontal) rc = fb_launch_fwd_hsqueeze(ctx, in.dev, avg.dev, res.dev, in.d.w, in.d.h);
+            else rc = fb_launch_fwd_vsqueeze(ctx, in.dev, avg.dev, res.dev, in.d.w, in.d.h);
+            if (rc) return rc;
+            fb_plane_free(ctx, in.dev);
+            in = avg;
+            img->ch.insert(img->ch.begin() + offset + c - beginc, res);
+        }
+    }
+    return FB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// DCT bookkeeping (reference transform/dct.h:120-336)
+// ---------------------------------------------------------------------------------------------------------
+
+// The reference's coefficient scan (dct.h:120-130, "we use a variant"): index -> position in the 8x8 block
+// laid out in L-shaped shells max(r,c)=s that hold scan indices s*s .. s*s+2s; even shells run down column
+// s then left along row s, odd shells run right along row s then up column s; shell 1 is irregular.
+static const int *scan_of_block_index() {
+    static int zz[64];
+    static bool ready = false;
+    if (!ready) {
+        zz[0] = 0; zz[1] = 1; zz[8] = 2; zz[9] = 3;
+        for (int s = 2; s < 8; s++) {
+            int idx = s * s;
+            if (s % 2 == 0) {
+                for (int r = 0; r <= s; r++) zz[r * 8 + s] = idx++;
+                for (int c = s - 1; c >= 0; c--) zz[s * 8 + c] = idx++;
+            } else {
+                for (int c = 0; c <= s; c++) zz[s * 8 + c] = idx++;
+                for (int r = s - 1; r >= 0; r--) zz[r * 8 + s] = idx++;
+            }
+        }
+        ready = true;
+    }
+    return zz;
+}
+
+static int dct_cshift(int k) { return k == 0 ? 3 : (k < 4 ? 2 : (k < 16 ? 1 : 0)); }       // dct_cshifts, dct.h:159-171
+
+static void default_dct_parameters(std::vector<int> &p, const fb_image *img) {              // dct.h:209-213
+    p.clear();
+    p.push_back(0);
+    p.push_back(img->info.nb_channels - 1);
+}
+
+// meta_DCT, dct.h:215-246.  default_DCT_scanscript (:173-207) puts coefficient k of component c at position k*nb+c.
+static int meta_dct(fb_image *img, std::vector<int> &p) {
+    if (p.size() < 2) default_dct_parameters(p, img);
+    const int beginc = img->info.nb_meta_channels + p[0], endc = img->info.nb_meta_channels + p[1];
+    const int nb = endc - beginc + 1;
+    if (nb < 1 || beginc < 0 || endc >= (int)img->ch.size()) return FB_ERR_INVALID;
+    for (int c = beginc; c <= endc; c++) {
+        fb_plane_desc &d = img->ch[c].d;
+        d.w = (d.w + 7) / 8; d.h = (d.h + 7) / 8;
+        d.hshift += 3; d.vshift += 3; d.hcshift += 3; d.vcshift += 3;
+    }
+    for (int i = nb; i < 64 * nb; i++) {
+        FbChan dummy;
+        chan_defaults(dummy.d);
+        const fb_plane_desc &s = img->ch[beginc + i % nb].d;
+        const int coeff = i / nb;
+        dummy.d.w = s.w; dummy.d.h = s.h; dummy.d.hshift = s.hshift; dummy.d.vshift = s.vshift;
+        dummy.d.hcshift = dct_cshift(coeff) + s.hcshift - 3;
+        dummy.d.vcshift = dct_cshift(coeff) + s.vcshift - 3;
+        dummy.d.component = s.component;
+        img->ch.push_back(dummy);
+    }
+    return FB_OK;
+}
+
+// inv_DCT, dct.h:249-296
+static int inv_dct(fb_image *img, std::vector<int> &p) {
+    fb_ctx *ctx = img->ctx;
+    if (p.size() < 2) default_dct_parameters(p, img);
+    const int beginc = img->info.nb_meta_channels + p[0], endc = img->info.nb_meta_channels + p[1];
+    const int nb = endc - beginc + 1;
+    const int offset = (int)img->ch.size() - 63 * nb;
+    if (nb < 1 || beginc < 0 || offset <= endc) { ctx->err = "Invalid number of channels to apply inverse DCT."; return FB_ERR_INVALID; }
+    const int *zz = scan_of_block_index();
+    const float dc_offset = (float)((img->info.maxval + 1.0) * 4.0);
+    for (int c = beginc; c <= endc; c++) {
+        int bw = img->ch[c - beginc + offset].d.w, bh = img->ch[c - beginc + offset].d.h;
+        if (img->ch[c].d.w < bw) bw = img->ch[c].d.w;
+        if (img->ch[c].d.h < bh) bh = img->ch[c].d.h;
+        const int16_t *planes[64];
+        planes[0] = img->ch[c].dev;
+        bool ok = img->ch[c].dev == nullptr || (img->ch[c].d.w == bw && img->ch[c].d.h == bh);
+        for (int i = 1; i < 64; i++) {
+            const FbChan &s = img->ch[offset - nb + zz[i] * nb + (c - beginc)];
+            planes[i] = s.dev;
+            if (s.dev && (s.d.w != bw || s.d.h != bh)) ok = false;
+        }
+        if (!ok) { ctx->err = "inverse DCT: coefficient planes of unequal size are not supported"; return FB_ERR_UNSUPPORTED; }
+        FbChan out;
+        chan_defaults(out.d);
+        out.d.w = bw * 8; out.d.h = bh * 8;
+        out.d.component = img->ch[c].d.component;
+        out.d.hshift = img->ch[c].d.hshift - 3; out.d.vshift = img->ch[c].d.vshift - 3;
+        out.d.hcshift = img->ch[c].d.hcshift - 3; out.d.vcshift = img->ch[c].d.hcshift - 3;      // sic, dct.h:280
+        out.d.decoded = 1;
+        int rc = fb_plane_alloc(ctx, chan_samples(out.d), &out.dev);
+        if (rc) return rc;
+        if ((rc = fb_launch_inv_dct(ctx, planes, out.dev, bw, bh, dc_offset))) return rc;
+        fb_plane_free(ctx, img->ch[c].dev);
+        img->ch[c] = out;
+    }
+    for (int c = offset; c < offset + nb * 63; c++) fb_plane_free(ctx, img->ch[c].dev);
+    img->ch.erase(img->ch.begin() + offset, img->ch.begin() + offset + nb * 63);
+    return FB_OK;
+}
+
+// fwd_DCT, dct.h:298-336 (explicit parameters only: the reference dereferences an empty vector otherwise)
+static int fwd_dct(fb_image *img, std::vector<int> &p, int *applied) {
+    fb_ctx *ctx = img->ctx;
+    *applied = 0;
+    if (p.size() < 2) { ctx->err = "forward DCT needs explicit parameters"; return FB_ERR_INVALID; }
+    const int beginc = img->info.nb_meta_channels + p[0], endc = img->info.nb_meta_channels + p[1];
+    const int nb = endc - beginc + 1;
+    if (nb < 1 || beginc < 0 || endc >= (int)img->ch.size()) return FB_ERR_INVALID;
+    std::vector<FbChan> src(img->ch.begin() + beginc, img->ch.begin() + endc + 1);     // the reference's "Image tmp = input"
+    for (auto &s : src) { int rc = chan_materialize(ctx, s); if (rc) return rc; }
+    for (int c = beginc; c <= endc; c++) img->ch[c].dev = src[c - beginc].dev;
+    const int offset = (int)img->ch.size();
+    int rc = meta_dct(img, p);
+    if (rc) return rc;
+    const int *zz = scan_of_block_index();
+    const float dc_offset = (float)((img->info.maxval + 1.0) * 4.0);
+    // channels beginc .. end get fresh sample buffers (dct.h:316-318); channels between endc and offset are
+    // resized in place by the reference, i.e. they keep their samples
+    for (int c = beginc; c < offset + 63 * nb; c++) {
+        if (c > endc && c < offset) { if ((rc = chan_materialize(ctx, img->ch[c]))) return rc; continue; }
+        img->ch[c].dev = nullptr;
+        if ((rc = fb_plane_alloc(ctx, chan_samples(img->ch[c].d), &img->ch[c].dev))) return rc;
+        img->ch[c].d.decoded = 1;
+    }
+    for (int c = beginc; c <= endc; c++) {
+        int16_t *planes[64];
+        planes[0] = img->ch[c].dev;
+        for (int i = 1; i < 64; i++) planes[i] = img->ch[offset - nb + zz[i] * nb + (c - beginc)].dev;
+        const FbChan &s = src[c - beginc];
+        if ((rc = fb_launch_fwd_dct(ctx, s.dev, s.d.w, s.d.h, planes, img->ch[c].d.w, img->ch[c].d.h, dc_offset))) return rc;
+    }
+    for (auto &s : src) fb_plane_free(ctx, s.dev);
+    *applied = 1;
+    return FB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// colour transforms / quantisation drivers
+// ---------------------------------------------------------------------------------------------------------
+
+// YCoCg(input, inverse), ycocg.h:33-101.  fuse_clamp: fold the final clamp of undo_transforms into the kernel.
+static int do_ycocg(fb_image *img, bool inverse, bool fuse_clamp, int *applied) {
+    fb_ctx *ctx = img->ctx;
+    *applied = 0;
+    const int m = img->info.nb_meta_channels;
+    if (img->info.nb_channels < 3 || (int)img->ch.size() < m + 3) {
+        if (inverse) { ctx->err = "Invalid number of channels to apply inverse YCoCg."; return FB_ERR_INVALID; }
+        return FB_OK;       // forward: "not applied" (ycocg.h:67-70)
+    }
+    const int w = img->ch[m].d.w, h = img->ch[m].d.h;
+    for (int k = 1; k < 3; k++)
+        if (img->ch[m + k].d.w < w || img->ch[m + k].d.h < h) { ctx->err = "Invalid channel dimensions to apply YCoCg"; return FB_ERR_INVALID; }
+    for (int k = 1; k < 3; k++)
+        if (img->ch[m + k].d.w != w) { ctx->err = "YCoCg on planes of different width is not supported"; return FB_ERR_UNSUPPORTED; }
+    for (int k = 0; k < 3; k++) { int rc = chan_materialize(ctx, img->ch[m + k]); if (rc) return rc; }
+    int rc = fb_launch_ycocg(ctx, img->ch[m].dev, img->ch[m + 1].dev, img->ch[m + 2].dev, (size_t)w * h, img->info.maxval, inverse ? 1 : 0,
+                             img->info.minval, img->info.maxval, fuse_clamp ? 1 : 0);
+    if (rc) return rc;
+    *applied = 1;
+    return FB_OK;
+}
+
+// YCbCr(input, inverse), ycbcr.h:33-101: always channels 0..2
+static int do_ycbcr(fb_image *img, bool inverse, int *applied) {
+    fb_ctx *ctx = img->ctx;
+    *applied = 0;
+    if (img->ch.size() < 3) { ctx->err = "Invalid number of channels to apply YCbCr."; return FB_ERR_INVALID; }
+    const int w = img->ch[0].d.w, h = img->ch[0].d.h;
+    for (int k = 1; k < 3; k++)
+        if (img->ch[k].d.w < w || img->ch[k].d.h < h) { ctx->err = "Invalid channel dimensions to apply YCbCr"; return FB_ERR_INVALID; }
+    for (int k = 1; k < 3; k++)
+        if (img->ch[k].d.w != w) { ctx->err = "YCbCr on planes of different width is not supported"; return FB_ERR_UNSUPPORTED; }
+    for (int k = 0; k < 3; k++) { int rc = chan_materialize(ctx, img->ch[k]); if (rc) return rc; }
+    int rc = fb_launch_ycbcr(ctx, img->ch[0].dev, img->ch[1].dev, img->ch[2].dev, (size_t)w * h, img->info.minval, img->info.maxval, inverse ? 1 : 0);
+    if (rc) return rc;
+    *applied = 1;
+    return FB_OK;
+}
+
+// inv_quantize / fwd_quantize, quantize.h:32-49 / 56-71
+static int do_quantize(fb_image *img, bool inverse, const std::vector<int> &p) {
+    fb_ctx *ctx = img->ctx;
+    for (int c = img->info.nb_meta_channels; c < (int)img->ch.size(); c++) {
+        FbChan &ch = img->ch[c];
+        if (inverse) {
+            if (!ch.dev) continue;
+            const int q = ch.d.q;
+            if (q == 1) continue;
+            int rc = fb_launch_quantize(ctx, ch.dev, chan_samples(ch.d), q, 1);
+            if (rc) return rc;
+            ch.d.minval = s16(ch.d.minval * q); ch.d.maxval = s16(ch.d.maxval * q); ch.d.q = 1;
+        } else {
+            if (p.empty()) return FB_ERR_INVALID;
+            const int q = c < (int)p.size() ? p[c] : p.back();
+            if (q == 0) return FB_ERR_INVALID;
+            int rc = chan_materialize(ctx, ch);
+            if (rc) return rc;
+            if ((rc = fb_launch_quantize(ctx, ch.dev, chan_samples(ch.d), q, 0))) return rc;
+            ch.d.minval = s16(ch.d.minval / q); ch.d.maxval = s16(ch.d.maxval / q); ch.d.q = q;
+        }
+    }
+    return FB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Transform dispatch (reference transform/transform.cpp:48-81)
+// ---------------------------------------------------------------------------------------------------------
+
+static int transform_meta_apply(fb_image *img, FbXform &t) {
+    switch (t.id) {
+    case FB_TRANSFORM_YCBCR: case FB_TRANSFORM_YCOCG: case FB_TRANSFORM_QUANTIZE: return FB_OK;
+    case FB_TRANSFORM_SQUEEZE: return meta_squeeze(img, t.p);
+    case FB_TRANSFORM_DCT: return meta_dct(img, t.p);
+    default:
+        img->ctx->err = "transform " + std::to_string(t.id) + " is outside the hot path (SURVEY.md 8: out of scope)";
+        return FB_ERR_UNSUPPORTED;
+    }
+}
+
+extern "C" int fb_image_undo_transforms(fb_image *img, int keep) {
+    if (!img || keep < 0) return FB_ERR_INVALID;
+    fb_ctx *ctx = img->ctx;
+    cudaSetDevice(ctx->device);
+    bool clamped = false;
+    while ((int)img->tr.size() > keep) {
+        FbXform &t = img->tr.back();
+        int rc = FB_OK, applied = 1;
+        const bool last = img->tr.size() == 1 && keep == 0;
+        switch (t.id) {
+        case FB_TRANSFORM_YCBCR: rc = do_ycbcr(img, true, &applied); break;
+        case FB_TRANSFORM_YCOCG: {
+            // the final clamp (image.cpp:107-113) is folded into the YCoCg kernel when YCoCg is the last
+            // transform and covers every plane of the image
+            const bool fuse = last && (int)img->ch.size() == img->info.nb_meta_channels + 3 && img->info.nb_meta_channels == 0;
+            rc = do_ycocg(img, true, fuse, &applied);
+            if (!rc && fuse) clamped = true;
+            break;
+        }
+        case FB_TRANSFORM_QUANTIZE: rc = do_quantize(img, true, t.p); break;
+        case FB_TRANSFORM_SQUEEZE: rc = inv_squeeze(img, t.p); break;
+        case FB_TRANSFORM_DCT: rc = inv_dct(img, t.p); break;
+        default:
+            ctx->err = "cannot undo transform " + std::to_string(t.id) + " (outside the hot path)";
+            rc = FB_ERR_UNSUPPORTED;
+        }
+        if (rc) { img->info.error = 1; return rc; }
+        img->tr.pop_back();
+    }
+    if (!keep && !clamped) {
+        for (auto &c : img->ch) {
+            if (!c.dev) continue;
+            int rc = fb_launch_clamp(ctx, c.dev, chan_samples(c.d), img->info.minval, img->info.maxval);
+            if (rc) return rc;
+        }
+    }
+    img->info.nb_planes = (int)img->ch.size();
+    img->info.nb_transforms = (int)img->tr.size();
+    return FB_OK;
+}
+
+extern "C" int fb_image_do_transform(fb_image *img, int32_t id, const int32_t *params, int nparams, int *applied_out) {
+    if (!img || nparams < 0 || (nparams && !params)) return FB_ERR_INVALID;
+    cudaSetDevice(img->ctx->device);
+    FbXform t;
+    t.id = id;
+    t.p.assign(params, params + nparams);
+    int applied = 0, rc = FB_OK;
+    switch (id) {
+    case FB_TRANSFORM_YCBCR: rc = do_ycbcr(img, false, &applied); if (rc == FB_ERR_INVALID) { rc = FB_OK; applied = 0; } break;
+    case FB_TRANSFORM_YCOCG: rc = do_ycocg(img, false, false, &applied); if (rc == FB_ERR_INVALID) { rc = FB_OK; applied = 0; } break;
+    case FB_TRANSFORM_QUANTIZE: rc = do_quantize(img, false, t.p); applied = rc == FB_OK; break;
+    case FB_TRANSFORM_SQUEEZE: rc = fwd_squeeze(img, t.p); applied = rc == FB_OK; break;
+    case FB_TRANSFORM_DCT: rc = fwd_dct(img, t.p, &applied); break;
+    default:
+        img->ctx->err = "transform " + std::to_string(id) + " is outside the hot path";
+        rc = FB_ERR_UNSUPPORTED;
+    }
+    if (rc) return rc;
+    if (applied) {
+        if (id == FB_TRANSFORM_DCT) t.p.assign(params, params + nparams);
+        img->tr.push_back(t);
+    }
+    img->info.nb_planes = (int)img->ch.size();
+    img->info.nb_transforms = (int)img->tr.size();
+    if (applied_out) *applied_out = applied;
+    return FB_OK;
+}
+
+extern "C" int fb_image_recompute_minmax(fb_image *img) {
+    if (!img) return FB_ERR_INVALID;
+    fb_ctx *ctx = img->ctx;
+    cudaSetDevice(ctx->device);
+    const size_t n = img->ch.size();
+    if (!n) return FB_OK;
+    int *dev = nullptr;
+    FB_CUDA(ctx, cudaMallocAsync((void **)&dev, n * 2 * sizeof(int), ctx->stream));
+    for (size_t i = 0; i < n; i++) {
+        int rc = fb_launch_minmax(ctx, img->ch[i].dev, img->ch[i].dev ? chan_samples(img->ch[i].d) : 0, dev + 2 * i);
+        if (rc) return rc;
+    }
+    std::vector<int> host(n * 2);
+    FB_CUDA(ctx, cudaMemcpyAsync(host.data(), dev, n * 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(dev, ctx->stream);
+    for (size_t i = 0; i < n; i++) { img->ch[i].d.minval = s16(host[2 * i]); img->ch[i].d.maxval = s16(host[2 * i + 1]); }
+    return FB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// create / query / download
+// ---------------------------------------------------------------------------------------------------------
+
+extern "C" int fb_image_create(fb_ctx *ctx, const fb_image_info *info, const fb_plane_desc *desc, const int16_t *const *planes,
+                               const int32_t *tids, const int32_t *tnp, const int32_t *tparams, fb_image **out) {
+    if (!ctx || !info || !out || (info->nb_planes && !desc)) return FB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    fb_image *img = new (std::nothrow) fb_image();
+    if (!img) return FB_ERR_NOMEM;
+    img->ctx = ctx;
+    img->info = *info;
+    img->ch.resize(info->nb_planes);
+    for (int i = 0; i < info->nb_planes; i++) {
+        img->ch[i].d = desc[i];
+        const size_t n = chan_samples(desc[i]);
+        if (desc[i].decoded && planes && planes[i]) {
+            int rc = fb_plane_alloc(ctx, n, &img->ch[i].dev);
+            if (rc) { fb_image_destroy(img); return rc; }
+            if (n && cudaMemcpyAsync(img->ch[i].dev, planes[i], n * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+                ctx->err = "H2D plane copy failed";
+                fb_image_destroy(img);
+                return FB_ERR_CUDA;
+            }
+        } else {
+            img->ch[i].d.decoded = 0;
+        }
+    }
+    int k = 0;
+    for (int i = 0; i < info->nb_transforms; i++) {
+        FbXform t;
+        t.id = tids[i];
+        t.p.assign(tparams + k, tparams + k + tnp[i]);
+        k += tnp[i];
+        img->tr.push_back(t);
+    }
+    *out = img;
+    return FB_OK;
+}
+
+extern "C" int fb_image_get_info(fb_image *img, fb_image_info *info) {
+    if (!img || !info) return FB_ERR_INVALID;
+    img->info.nb_planes = (int)img->ch.size();
+    img->info.nb_transforms = (int)img->tr.size();
+    *info = img->info;
+    return FB_OK;
+}
+
+extern "C" int fb_image_get_plane(fb_image *img, int i, fb_plane_desc *desc) {
+    if (!img || !desc || i < 0 || i >= (int)img->ch.size()) return FB_ERR_INVALID;
+    *desc = img->ch[i].d;
+    desc->decoded = img->ch[i].dev ? 1 : 0;
+    return FB_OK;
+}
+
+extern "C" int fb_image_get_transform(fb_image *img, int i, int32_t *id, int32_t *params, int cap) {
+    if (!img || i < 0 || i >= (int)img->tr.size()) return -1;
+    if (id) *id = img->tr[i].id;
+    for (int k = 0; k < cap && k < (int)img->tr[i].p.size(); k++) params[k] = img->tr[i].p[k];
+    return (int)img->tr[i].p.size();
+}
+
+extern "C" void *fb_image_plane_device_ptr(fb_image *img, int i) {
+    if (!img || i < 0 || i >= (int)img->ch.size()) return nullptr;
+    return img->ch[i].dev;
+}
+
+extern "C" int fb_image_download_plane(fb_image *img, int i, int16_t *dst) {
+    if (!img || !dst || i < 0 || i >= (int)img->ch.size() || !img->ch[i].dev) return FB_ERR_INVALID;
+    fb_ctx *ctx = img->ctx;
+    cudaSetDevice(ctx->device);
+    const size_t n = chan_samples(img->ch[i].d);
+    if (n) FB_CUDA(ctx, cudaMemcpyAsync(dst, img->ch[i].dev, n * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FB_OK;
+}
+
+extern "C" int fb_image_download_interleaved(fb_image *img, int nch, int bps, void *dst) {
+    if (!img || !dst || nch < 1 || nch > 8 || nch > (int)img->ch.size() || (bps != 1 && bps != 2)) return FB_ERR_INVALID;
+    fb_ctx *ctx = img->ctx;
+    cudaSetDevice(ctx->device);
+    const int w = img->ch[0].d.w, h = img->ch[0].d.h;
+    const int16_t *planes[8];
+    for (int c = 0; c < nch; c++) {
+        if (!img->ch[c].dev || img->ch[c].d.w != w || img->ch[c].d.h != h) { ctx->err = "interleave: planes missing or of different size"; return FB_ERR_INVALID; }
+        planes[c] = img->ch[c].dev;
+    }
+    const size_t npix = (size_t)w * h, bytes = npix * nch * bps;
+    void *dev = nullptr;
+    FB_CUDA(ctx, cudaMallocAsync(&dev, std::max<size_t>(bytes, 16), ctx->stream));
+    int rc = fb_launch_interleave(ctx, planes, nch, npix, bps, dev);
+    if (rc) return rc;
+    FB_CUDA(ctx, cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(dev, ctx->stream);
+    return FB_OK;
+}
+
+extern "C" int fb_image_group_index(fb_image *img, int64_t *offsets, int32_t *first_channel, int cap) {
+    if (!img) return 0;
+    const int n = (int)img->group_off.size();
+    for (int i = 0; i < n && i < cap; i++) {
+        if (offsets) offsets[i] = img->group_off[i];
+        if (first_channel) first_channel[i] = img->group_first[i];
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Container parser: fuif_decode up to the first channel group (reference encoding/encoding.cpp:599-706)
+// ---------------------------------------------------------------------------------------------------------
+
+namespace {
+struct ByteReader {         // FileIO semantics (fileio.h:33-81): EOF only after a failed read
+    const uint8_t *p; size_t n, pos = 0; bool eof = false;
+    int get() { if (pos >= n) { eof = true; return -1; } return p[pos++]; }
+};
+int read_varint(ByteReader &io) {        // read_big_endian_varint, encoding.cpp:45-59
+    int result = 0, bytes_read = 0;
+    while (bytes_read++ < 10) {
+        int number = io.get();
+        if (number < 0) break;
+        if (number < 128) return result + number;
+        number -= 128;
+        result += number;
+        result = (int)((unsigned)result << 7);
+    }
+    return -1;
+}
+bool transform_has_parameters(int id) {  // Transform::has_parameters, transform/transform.h:85-102
+    return id == 3 || id == 4 || id == 6 || id == 7 || id == 8 || id == 9 || id == 10;
+}
+struct Header {
+    int w, h, bit_depth, nb_channels, colormodel, max_properties;
+    int responsive_offsets[5];
+    size_t after_offsets;
+};
+int parse_header(ByteReader &io, Header &hd) {
+    if (io.n < 4) return FB_ERR_INVALID;
+    bool multi = false;
+    if (!memcmp(io.p, "FUAF", 4)) multi = true;
+    else if (memcmp(io.p, "FUIF", 4)) return FB_ERR_INVALID;
+    io.pos = 4;
+    hd.nb_channels = read_varint(io) - '0';
+    hd.bit_depth = read_varint(io) - '&';
+    hd.w = read_varint(io) + 1;
+    hd.h = read_varint(io) + 1;
+    if (multi) {            // animation fields (encoding.cpp:614-623): frames remain a vertical filmstrip
+        int nb_frames = read_varint(io) + 2;
+        (void)read_varint(io);
+        int numerator = read_varint(io);
+        if (numerator) for (int i = 1; i < nb_frames; i++) (void)read_varint(io);
+        (void)read_varint(io);
+    }
+    hd.colormodel = read_varint(io);
+    hd.max_properties = read_varint(io);
+    if (io.eof || hd.nb_channels < 0 || hd.bit_depth < 1 || hd.bit_depth > 16 || hd.w < 1 || hd.h < 1 || hd.max_properties < 0) return FB_ERR_INVALID;
+    return FB_OK;
+}
+}  // namespace
+
+extern "C" int fb_peek_header(const uint8_t *bytes, size_t nbytes, fb_image_info *info) {
+    if (!bytes || !info) return FB_ERR_INVALID;
+    ByteReader io{bytes, nbytes};
+    Header hd;
+    int rc = parse_header(io, hd);
+    if (rc) return rc;
+    memset(info, 0, sizeof(*info));
+    info->w = hd.w; info->h = hd.h; info->minval = 0; info->maxval = (1 << hd.bit_depth) - 1;
+    info->nb_channels = info->real_nb_channels = hd.nb_channels;
+    info->colormodel = hd.colormodel;
+    return FB_OK;
+}
+
+// Parses header + transform list, builds the (empty) channel list via meta_apply and hands the rest to the
+// GPU MANIAC decoder.
+static int parse_container(fb_ctx *ctx, const uint8_t *bytes, size_t nbytes, const fb_decode_options *opts, const int64_t *gidx, int ngroups,
+                           fb_image **out, FbManiacJob &job) {
+    ByteReader io{bytes, nbytes};
+    Header hd;
+    int rc = parse_header(io, hd);
+    if (rc) { ctx->err = "not a FUIF file or corrupt header"; return rc; }
+    fb_image *img = new (std::nothrow) fb_image();
+    if (!img) return FB_ERR_NOMEM;
+    img->ctx = ctx;
+    // Image(w, h, (1<<bit_depth)-1, nb_channels, colormodel), encoding.cpp:637 / image.h:114-120
+    img->info.w = hd.w; img->info.h = hd.h; img->info.minval = 0; img->info.maxval = (1 << hd.bit_depth) - 1;
+    img->info.nb_channels = img->info.real_nb_channels = hd.nb_channels;
+    img->info.nb_meta_channels = 0; img->info.colormodel = hd.colormodel;
+    img->ch.resize(hd.nb_channels);
+    for (int i = 0; i < hd.nb_channels; i++) {
+        chan_defaults(img->ch[i].d);
+        img->ch[i].d.w = hd.w; img->ch[i].d.h = hd.h; img->ch[i].d.maxval = img->info.maxval; img->ch[i].d.component = i;
+    }
+    *out = img;
+    job.bytes_host = bytes; job.nbytes = nbytes; job.img = img; job.max_properties = hd.max_properties;
+    job.cutoff = opts ? opts->maniac_cutoff : 6; job.alpha = opts ? opts->maniac_alpha : 0x0d000000;
+    job.group_index = gidx; job.n_groups = ngroups; job.bytes_to_load = 0; job.body_pos = io.pos;
+    if (hd.nb_channels < 1) return FB_OK;
+
+    int rel = 0;
+    for (int s = 0; s < 5; s++) { hd.responsive_offsets[s] = read_varint(io) + rel; rel = hd.responsive_offsets[s]; }
+    rel = (int)io.pos;
+    for (int s = 0; s < 5; s++) hd.responsive_offsets[s] += rel;
+
+    const int nb_transforms = read_varint(io);
+    for (int i = 0; i < nb_transforms; i++) {
+        const int idp = read_varint(io);
+        if (idp < 0) { ctx->err = "truncated transform list"; return FB_ERR_INVALID; }
+        FbXform t;
+        t.id = idp & 0xf;
+        if (transform_has_parameters(t.id)) {
+            const int np = idp >> 4;
+            for (int j = 0; j < np; j++) t.p.push_back(read_varint(io));
+        }
+        if ((rc = transform_meta_apply(img, t))) return rc;
+        img->tr.push_back(t);
+    }
+    const int preview = opts ? opts->preview : -1;
+    if (preview > 4) return FB_ERR_INVALID;
+    if (preview >= 0) job.bytes_to_load = (size_t)hd.responsive_offsets[preview];
+    job.body_pos = io.pos;
+    img->info.nb_planes = (int)img->ch.size();
+    img->info.nb_transforms = (int)img->tr.size();
+    return FB_OK;
+}
+
+extern "C" int fb_decode_batch(fb_ctx *ctx, int n_images, const uint8_t *const *bytes, const size_t *nbytes, const fb_decode_options *opts,
+                               const int64_t *const *group_index, const int *n_groups, fb_image **out) {
+    if (!ctx || n_images < 0 || !bytes || !nbytes || !out) return FB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    std::vector<FbManiacJob> jobs(n_images);
+    for (int i = 0; i < n_images; i++) out[i] = nullptr;
+    int rc = FB_OK;
+    for (int i = 0; i < n_images && !rc; i++)
+        rc = parse_container(ctx, bytes[i], nbytes[i], opts, group_index ? group_index[i] : nullptr, n_groups ? n_groups[i] : 0, &out[i], jobs[i]);
+    if (!rc) rc = fb_maniac_decode(ctx, jobs);
+    if (rc) {
+        for (int i = 0; i < n_images; i++) { fb_image_destroy(out[i]); out[i] = nullptr; }
+        return rc;
+    }
+    return FB_OK;
+}
+
+extern "C" int fb_decode(fb_ctx *ctx, const uint8_t *bytes, size_t nbytes, const fb_decode_options *opts, const int64_t *group_index, int n_groups,
+                         fb_image **out) {
+    const int64_t *gi[1] = {group_index};
+    return fb_decode_batch(ctx, 1, &bytes, &nbytes, opts, group_index ? gi : nullptr, &n_groups, out);
+}
+
+extern "C" int fb_decode_to_pixels(fb_ctx *ctx, const uint8_t *bytes, size_t nbytes, const fb_decode_options *opts, const int64_t *group_index,
+                                   int n_groups, int bps, void *dst, size_t dst_bytes) {
+    fb_image *img = nullptr;
+    int rc = fb_decode(ctx, bytes, nbytes, opts, group_index, n_groups, &img);
+    if (rc) return rc;
+    rc = fb_image_undo_transforms(img, 0);
+    if (!rc) {
+        const int nch = img->info.nb_channels;
+        if ((int)img->ch.size() < nch || nch < 1) rc = FB_ERR_INVALID;
+        else if ((size_t)img->ch[0].d.w * img->ch[0].d.h * nch * bps > dst_bytes) { ctx->err = "destination buffer too small"; rc = FB_ERR_INVALID; }
+        else rc = fb_image_download_interleaved(img, nch, bps, dst);
+    }
+    fb_image_destroy(img);
+    return rc;
+}

@@ -1,0 +1,789 @@
+// MANIAC entropy decoding + context model on the GPU (sm_100a).
+//
+// What runs here is fuif_decode_channel (reference encoding/encoding.cpp:259-429) with everything it inlines:
+//   group header varints                      encoding.cpp:264-329
+//   init_properties / predictors / properties encoding/context_predict.h:67-120, 125-206
+//   precompute_references                     context_predict.h:233-289
+//   24-bit range decoder                      maniac/rac.h:35-114
+//   adaptive 12-bit chances                   maniac/chance.h:42-84, chance.cpp:31-65 (table built on the host)
+//   zero/sign/exponent/mantissa integer coder maniac/symbol.h:72-185, uniform coder :44-56
+//   MANIAC tree parse + leaf walk             maniac/compound.h:135-320
+//
+// Mapping.  The bitstream is strictly serial inside one channel group (adaptive chances + neighbour
+// context), so the unit of parallelism is a *stream*: one channel group when the caller supplies
+// the groups' byte offsets (group index), otherwise one whole image.  One warp decodes one stream: the serial
+// decode is executed warp-uniformly (no divergence), while the data-parallel pieces (reference-property
+// rows, leaf initialisation, constant fills) are spread over the 32 lanes.  Streams are handed out through
+// an atomic ticket so that a stream only ever waits for lower-numbered streams (row wavefront on the
+// planes it back-references), which are guaranteed to be running already.
+#include "fb_common.cuh"
+
+#include <string.h>
+
+#include <algorithm>
+
+namespace {
+
+constexpr int kMaxNodes = 65536;
+constexpr int kMaxProps = 64;
+constexpr int NB_NONREF = 13;           // context_predict.h:210
+constexpr int MAX_BIT_DEPTH = 15;       // config.h:5
+
+struct DChan {
+    int w, h, minval, maxval, zero, q, hshift, vshift;
+    int16_t *data;
+    int state;          // 0 untouched, 1 holds samples
+    int hdr_done;       // group header of this channel has been parsed (ranges valid)
+    int rows_done;      // rows published so far (wavefront)
+    long long group_off;    // byte offset of the group header if this channel starts a group, else -1
+};
+
+struct DImage {
+    const uint8_t *bytes;
+    unsigned long long nbytes, bytes_to_load;
+    DChan *ch;
+    int nch, max_properties;
+    int n_orig;         // channels the Image constructor created with zero-filled buffers (encoding.cpp:637)
+    int status;         // 0 ok, else FB_ERR_*
+};
+
+struct DStream {
+    int image, first_channel, end_channel, max_groups;     // channels [first_channel, end_channel) belong to this stream
+    unsigned long long offset;
+};
+
+struct TNode { short property; unsigned short child; int splitval; };   // PropertyDecisionNode, compound.h:41-51
+
+struct WarpScratch {    // per resident warp, in global memory
+    TNode *nodes;           // kMaxNodes
+    uint16_t *leaves;       // kMaxNodes/2 * 32
+    int *stack;             // tree-parse frames, 4 ints each, kMaxNodes/2+2 frames
+    int16_t *refs;          // maxw * 12
+};
+
+struct Params {
+    DImage *images;
+    DStream *streams;
+    int nstreams;
+    int *ticket;
+    const uint16_t *table;      // [4096][2] decode table (cutoff, alpha)
+    const uint16_t *meta_table; // [4096][2] tree-coder table (cut 2, alpha 0xFFFFFFFF/19)
+    WarpScratch *scratch;
+    int maxw;
+};
+
+__device__ __forceinline__ int s16(int x) { return (int)(short)x; }
+__device__ __forceinline__ int ilog2u(unsigned l) { return l == 0 ? 0 : 31 - __clz(l); }      // maniac/util.h:33-36
+
+// ---- byte reader with FileIO end-of-stream rules (fileio.h:33-81) ------------------------------------------
+struct Reader {
+    const uint8_t *p;
+    unsigned long long n, pos, btl;
+    bool eof;
+    __device__ __forceinline__ int get() {
+        if (pos >= n) { eof = true; return -1; }
+        return __ldg(p + pos++);
+    }
+    __device__ __forceinline__ bool stop() const { return eof || (btl && pos >= btl); }
+    __device__ int varint() {           // read_big_endian_varint, encoding.cpp:45-59
+        int result = 0, bytes_read = 0;
+        while (bytes_read++ < 10) {
+            int number = get();
+            if (number < 0) break;
+            if (number < 128) return result + number;
+            number -= 128;
+            result += number;
+            result = (int)((unsigned)result << 7);
+        }
+        return -1;
+    }
+};
+
+// ---- range decoder (maniac/rac.h) -----------------------------------------------------------------------------
+struct Rac {
+    Reader *io;
+    unsigned range, low;
+    bool ones;      // a read past the end turned `low` into all-ones garbage (rac.h:64-69): every bit reads as 1
+    __device__ __forceinline__ void byte_in() {
+        int c = io->get();
+        if (c < 0) ones = true;
+        low = (low << 8) | (unsigned)(c & 0xFF);
+    }
+    __device__ void init(Reader *r) {           // RacInput ctor, rac.h:97-104
+        io = r; range = 1u << 24; low = 0; ones = false;
+        byte_in(); byte_in(); byte_in();
+    }
+    __device__ __forceinline__ void input() {   // rac.h:70-81
+        if (range <= (1u << 16)) { range <<= 8; byte_in(); }
+        if (range <= (1u << 16)) { range <<= 8; byte_in(); }
+    }
+    __device__ __forceinline__ int get(unsigned chance) {       // rac.h:82-95
+        int bit;
+        if (ones || low >= range - chance) { low -= range - chance; range = chance; bit = 1; }
+        else { range -= chance; bit = 0; }
+        input();
+        return bit;
+    }
+    __device__ __forceinline__ int read12(int b12) {            // rac.h:42-52, 107 (64-bit product)
+        return get((unsigned)(((unsigned long long)range * (unsigned)b12 + 0x800) >> 12));
+    }
+    __device__ __forceinline__ int read_bit() { return get(range >> 1); }   // rac.h:111
+};
+
+// ---- symbol coder (maniac/symbol.h) -------------------------------------------------------------------------------
+// leaf layout: [0]=zero [1]=sign [2..15]=exp[14] [16..30]=mant[15] [31]=pad   (SymbolChance<.,15>, symbol.h:72-139)
+#define SC_ZERO 0
+#define SC_SIGN 1
+#define SC_EXP 2
+#define SC_MANT 16
+
+__device__ __forceinline__ uint16_t initial_chance(int idx, int zero_chance) {      // SymbolChance(zero_chance), symbol.h:115-138
+    if (idx == SC_ZERO) return (uint16_t)zero_chance;
+    if (idx == SC_SIGN) return 0x800;
+    if (idx >= SC_MANT) return idx == 31 ? 0 : 1024;
+    unsigned long long rp = 0x1000 - (unsigned long long)zero_chance;
+    for (int i = 0;; i++) {
+        if (rp < 0x100) rp = 0x100;
+        if (rp > 0xf00) rp = 0xf00;
+        if (i == idx - SC_EXP) return (uint16_t)(0x1000 - rp);
+        rp = (rp * rp + 0x800) >> 12;
+    }
+}
+
+__device__ __forceinline__ int sym_read(Rac &rac, const uint16_t *__restrict__ table, uint16_t *leaf, int idx) {    // compound.h:90-95
+    int ch = leaf[idx];
+    int bit = rac.read12(ch);
+    leaf[idx] = table[ch * 2 + bit];
+    return bit;
+}
+
+// reader<15>(coder, min, max), symbol.h:154-185
+__device__ int read_int(Rac &rac, const uint16_t *__restrict__ table, uint16_t *leaf, int mn, int mx) {
+    if (mn == mx) return mn;
+    int sign;
+    if (sym_read(rac, table, leaf, SC_ZERO)) return 0;
+    if (mn < 0) { if (mx > 0) sign = sym_read(rac, table, leaf, SC_SIGN); else sign = 0; } else sign = 1;
+    const int amax = sign ? mx : -mn;
+    const int emax = ilog2u((unsigned)amax);
+    int e = 0;
+    for (; e < emax; e++) if (sym_read(rac, table, leaf, SC_EXP + e)) break;
+    int have = 1 << e;
+    for (int pos = e; pos > 0;) {
+        pos--;
+        int minabs1 = have | (1 << pos);
+        if (minabs1 > amax) continue;
+        if (sym_read(rac, table, leaf, SC_MANT + pos)) have = minabs1;
+    }
+    return sign ? have : -have;
+}
+__device__ int read_int2(Rac &rac, const uint16_t *table, uint16_t *leaf, int mn, int mx) {     // symbol.h:232-236
+    if (mn > 0) return read_int(rac, table, leaf, 0, mx - mn) + mn;
+    if (mx < 0) return read_int(rac, table, leaf, mn - mx, 0) + mx;
+    return read_int(rac, table, leaf, mn, mx);
+}
+__device__ int uniform_read(Rac &rac, int mn, int len) {    // UniformSymbolCoder::read_int, symbol.h:44-56
+    while (len != 0) {
+        int med = len / 2;
+        if (rac.read_bit()) { mn = mn + med + 1; len = len - (med + 1); }
+        else len = med;
+    }
+    return mn;
+}
+
+// ---- context model (encoding/context_predict.h) ---------------------------------------------------------------------
+__device__ __forceinline__ int slog(int x16) {      // context_predict.h:54-61
+    int x = s16(x16);
+    if (x == 0) return 0;
+    if (x > 0) return 32 - __clz(x);
+    return -(32 - __clz(-x));
+}
+__device__ __forceinline__ int fooabs(int x16) { int x = s16(x16); return s16(x < 0 ? -x : x); }   // :63-65
+
+__device__ __forceinline__ int median3(int a, int b, int c) {       // util.h:9-23
+    if (a < b) { if (b < c) return b; return a < c ? c : a; }
+    if (a < c) return a;
+    return b < c ? c : b;
+}
+
+__device__ bool check_bit_depth(int minv, int maxv, int predictor) {    // encoding.cpp:61-72
+    int maxav = s16(abs(maxv));
+    if (-minv > maxav) maxav = s16(-minv);
+    if (predictor > 0 && maxv - minv > maxav) maxav = s16(maxv - minv);
+    if (predictor > 0 && abs(minv - maxv) > maxav) maxav = s16(abs(minv - maxv));
+    return ilog2u((unsigned)maxav) + 1 <= MAX_BIT_DEPTH;
+}
+
+__device__ __forceinline__ void spin_until_ge(const int *flag, int want) {
+    while (*(const volatile int *)flag < want) __nanosleep(200);
+    __threadfence();
+}
+
+// All lanes of the warp call this with identical arguments.
+__device__ void fill_plane(DChan &c, int value, int lane) {
+    const size_t n = (size_t)c.w * c.h;
+    for (size_t i = lane; i < n; i += 32) c.data[i] = (int16_t)value;
+    __syncwarp();
+    c.state = 1;
+}
+
+// init_properties, context_predict.h:67-120
+__device__ int init_properties(int (*pr)[2], DImage &img, int beginc, int endc, int *refchan, int &nrefchan) {
+    int n = 0, offset = 0;
+    nrefchan = 0;
+    for (int j = beginc - 1; j >= 0 && offset < img.max_properties; j--) {
+        spin_until_ge(&img.ch[j].hdr_done, 1);
+        const DChan &cj = img.ch[j];
+        if (cj.minval == cj.maxval) continue;
+        if (cj.hshift < 0) continue;
+        int minval = cj.minval; if (minval > 0) minval = 0;
+        int maxval = cj.maxval; if (maxval < 0) maxval = 0;
+        pr[n][0] = 0; pr[n][1] = fooabs(maxval > -minval ? maxval : minval); n++; offset++;
+        pr[n][0] = slog(minval); pr[n][1] = slog(maxval); n++; offset++;
+        refchan[nrefchan++] = j;
+    }
+    int minval = 0x7FFF, maxval = -0x7FFF, maxh = 0, maxw = 0;
+    for (int j = beginc; j <= endc; j++) {
+        const DChan &cj = img.ch[j];
+        if (cj.minval < minval) minval = cj.minval;
+        if (cj.maxval > maxval) maxval = cj.maxval;
+        if (cj.h > maxh) maxh = cj.h;
+        if (cj.w > maxw) maxw = cj.w;
+    }
+    if (minval > 0) minval = 0;
+    if (maxval < 0) maxval = 0;
+    int amax = max(fooabs(minval), fooabs(maxval));
+    pr[n][0] = 0; pr[n][1] = amax; n++;
+    pr[n][0] = 0; pr[n][1] = amax; n++;
+    pr[n][0] = slog(minval); pr[n][1] = slog(maxval); n++;
+    pr[n][0] = slog(minval); pr[n][1] = slog(maxval); n++;
+    pr[n][0] = 0; pr[n][1] = maxh - 1; n++;
+    pr[n][0] = 0; pr[n][1] = maxw - 1; n++;
+    pr[n][0] = minval + minval - maxval; pr[n][1] = maxval + maxval - minval; n++;
+    pr[n][0] = minval + minval - maxval; pr[n][1] = maxval + maxval - minval; n++;
+    for (int k = 0; k < 5; k++) { pr[n][0] = slog(minval - maxval); pr[n][1] = slog(maxval - minval); n++; }
+    return n;
+}
+
+// MetaPropertySymbolCoder::read_tree, compound.h:277-320, recursion unrolled on an explicit stack
+__device__ bool read_tree(Rac &rac, const uint16_t *__restrict__ mtable, int (*range)[2], int nprops, TNode *nodes, int &nnodes,
+                          int *stack, uint16_t (*coder)[32]) {
+    int sub[kMaxProps][2];
+    for (int i = 0; i < nprops; i++) { sub[i][0] = range[i][0]; sub[i][1] = range[i][1]; }
+    for (int k = 0; k < 3; k++)
+        for (int i = 0; i < 32; i++) coder[k][i] = initial_chance(i, 1024);     // SimpleSymbolCoder ctx(ZERO_CHANCE), symbol.h:219
+    nnodes = 1;
+    nodes[0].property = -1; nodes[0].child = 0; nodes[0].splitval = 0;
+    int sp = 0;
+    // frame = {pos, stage | p<<2, oldmin, oldmax}; splitval lives in the node
+    stack[0] = 0; stack[1] = 0; stack[2] = 0; stack[3] = 0;
+    sp = 1;
+    while (sp > 0) {
+        int *f = stack + 4 * (sp - 1);
+        const int pos = f[0], stage = f[1] & 3, p = f[1] >> 2;
+        if (stage == 0) {
+            int pp = read_int2(rac, mtable, coder[0], 0, nprops) - 1;
+            nodes[pos].property = (short)pp;
+            if (pp == -1) { sp--; continue; }
+            int oldmin = sub[pp][0], oldmax = sub[pp][1];
+            if (oldmin >= oldmax) return false;                                     // "Invalid tree", compound.h:285-288
+            int splitval = read_int2(rac, mtable, coder[2], oldmin, oldmax - 1);
+            nodes[pos].splitval = splitval;
+            if (nnodes + 2 > 65535) return false;
+            int child = nnodes;
+            nodes[pos].child = (unsigned short)child;
+            nodes[child].property = -1; nodes[child].child = 0; nodes[child].splitval = 0;
+            nodes[child + 1] = nodes[child];
+            nnodes += 2;
+            sub[pp][0] = splitval + 1;
+            f[1] = 1 | (pp << 2); f[2] = oldmin; f[3] = oldmax;
+            int *g = stack + 4 * sp;
+            g[0] = child; g[1] = 0; g[2] = 0; g[3] = 0;
+            sp++;
+        } else if (stage == 1) {
+            sub[p][0] = f[2];
+            sub[p][1] = nodes[pos].splitval;
+            f[1] = 2 | (p << 2);
+            int *g = stack + 4 * sp;
+            g[0] = nodes[pos].child + 1; g[1] = 0; g[2] = 0; g[3] = 0;
+            sp++;
+        } else {
+            sub[p][1] = f[3];
+            sp--;
+        }
+    }
+    return true;
+}
+
+// precompute_references, context_predict.h:233-289.  Lanes split x.  refs[x*nref + k] (int16 is enough)
+__device__ void precompute_references(const DChan &ch, int y, DImage &img, const int *refchan, int nrefchan, int16_t *refs, int nref, int lane) {
+    const int oy = y << ch.vshift;
+    for (int r = 0; r < nrefchan; r++) {
+        const DChan &cj = img.ch[refchan[r]];
+        int ry = oy >> cj.vshift;
+        if (ry >= cj.h) ry = cj.h - 1;
+        spin_until_ge(&cj.rows_done, ry + 1);
+        const int16_t *row = cj.data + (size_t)ry * cj.w;
+        const int offset = 2 * r;
+        if (ch.hshift == cj.hshift && ch.w <= cj.w) {
+            for (int x = lane; x < ch.w; x += 32) { int v = __ldcg(row + x); refs[x * nref + offset] = (int16_t)fooabs(v); refs[x * nref + offset + 1] = (int16_t)slog(v); }
+        } else if (ch.hshift < cj.hshift) {
+            // every source sample but the last is repeated `stepsize` times, the last one fills the rest of the row
+            const int stepsize = (1 << cj.hshift) >> ch.hshift;
+            for (int x = lane; x < ch.w; x += 32) {
+                int rx = stepsize > 0 ? x / stepsize : cj.w - 1;
+                if (rx > cj.w - 1) rx = cj.w - 1;
+                int v = __ldcg(row + rx);
+                refs[x * nref + offset] = (int16_t)fooabs(v); refs[x * nref + offset + 1] = (int16_t)slog(v);
+            }
+        } else {
+            for (int x = lane; x < ch.w; x += 32) {
+                int rx = (x << ch.hshift) >> cj.hshift;
+                if (rx >= cj.w) rx = cj.w - 1;
+                int v = __ldcg(row + rx);
+                refs[x * nref + offset] = (int16_t)fooabs(v); refs[x * nref + offset + 1] = (int16_t)slog(v);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// predict_and_compute_properties, context_predict.h:125-168
+__device__ __forceinline__ int predict_props(int *p, const DChan &ch, int x, int y, int predictor, int offset) {
+    const int16_t *d = ch.data;
+    const int w = ch.w;
+    int left = x ? d[(size_t)y * w + x - 1] : ch.zero;
+    int top = y ? d[(size_t)(y - 1) * w + x] : ch.zero;
+    int topleft = (x && y) ? d[(size_t)(y - 1) * w + x - 1] : left;
+    int topright = (x + 1 < w && y) ? d[(size_t)(y - 1) * w + x + 1] : top;
+    int leftleft = x > 1 ? d[(size_t)y * w + x - 2] : left;
+    int toptop = y > 1 ? d[(size_t)(y - 2) * w + x] : top;
+    p[offset + 0] = fooabs(top);
+    p[offset + 1] = fooabs(left);
+    p[offset + 2] = slog(top);
+    p[offset + 3] = slog(left);
+    p[offset + 4] = y;
+    p[offset + 5] = x;
+    p[offset + 6] = left + top - topleft;
+    p[offset + 7] = topleft + topright - top;
+    p[offset + 8] = slog(left - topleft);
+    p[offset + 9] = slog(topleft - top);
+    p[offset + 10] = slog(top - topright);
+    p[offset + 11] = slog(top - toptop);
+    p[offset + 12] = slog(left - leftleft);
+    switch (predictor) {
+    case 0: return ch.zero;
+    case 1: return s16((left + top) / 2);
+    case 2: return median3(s16(left + top - topleft), left, top);
+    case 3: return left;
+    case 4: return top;
+    case 5: return s16((left + topleft + top + topright) / 4);
+    case 6: { int g = left + top - topleft; return s16(g < ch.minval ? ch.minval : (g > ch.maxval ? ch.maxval : g)); }
+    default: return median3(s16(left + top - topleft), left, top);
+    }
+}
+
+__device__ __forceinline__ void publish_rows(DChan &c, int rows, int lane) {
+    __syncwarp();
+    __threadfence();
+    if (lane == 0) atomicExch(&c.rows_done, rows);
+}
+
+// corrupt_or_truncated, encoding.cpp:209-219.  returns true = "truncated, carry on", false = corruption
+__device__ bool corrupt_or_truncated(Reader &io, DChan &c, int lane) {
+    if (io.stop()) { fill_plane(c, 0, lane); return true; }
+    return false;
+}
+
+// fuif_decode_channel, encoding.cpp:259-429.  Returns false on a hard error. `beginc` is advanced to the group's last channel.
+__device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params &P, WarpScratch &ws, int lane, uint16_t (*coder)[32]) {
+    if (io.stop()) return true;
+    const long long header_pos = (long long)io.pos;
+    const int firstbyte = io.varint();
+    if (io.stop()) return true;
+    const int b0 = beginc;
+    const int endc = beginc + (firstbyte >> 4);
+    const bool compress = firstbyte & 1;
+    const int predictor = (firstbyte & 14) >> 1;
+    int global_minv = s16(1 - io.varint());
+    if (io.stop()) return true;
+    if (global_minv == 1) global_minv = s16(io.varint());
+    if (io.stop()) return true;
+    const int global_maxv = s16(global_minv + io.varint());
+    if (io.stop()) return true;
+    if (endc >= img.nch || endc < beginc) return false;
+    img.ch[b0].group_off = header_pos;
+
+    int firstrealc = beginc;
+    bool early = false, early_result = true;
+    for (int i = beginc; i <= endc; i++) {
+        DChan &ch = img.ch[i];
+        if (ch.w * ch.h <= 0) continue;
+        ch.minval = global_minv; ch.maxval = global_maxv;
+        if (endc > beginc && global_minv < global_maxv) {
+            ch.minval = s16(ch.minval + io.varint());
+            ch.maxval = s16(ch.minval + io.varint());
+        }
+        if (ch.minval == ch.maxval) { fill_plane(ch, ch.minval, lane); firstrealc++; }
+        if (ch.minval == 0 && ch.maxval == 0) continue;
+        ch.q = io.varint();
+        if (io.stop()) { early = true; early_result = corrupt_or_truncated(io, ch, lane); break; }
+        if (compress && !check_bit_depth(ch.minval, ch.maxval, predictor)) { early = true; early_result = false; break; }
+    }
+    // ranges of this group's channels are final from here on: let dependent streams read them
+    __syncwarp();
+    __threadfence();
+    for (int i = beginc; i <= endc; i++) {
+        DChan &ch = img.ch[i];
+        if (ch.w * ch.h <= 0 || ch.minval == ch.maxval) continue;      // the reference calls setzero() only on channels it decodes
+        if (ch.minval > 0) ch.zero = ch.minval; else if (ch.maxval < 0) ch.zero = ch.maxval; else ch.zero = 0;   // setzero, image.h:70-74
+    }
+    __threadfence();
+    for (int i = beginc; i <= endc; i++) atomicExch(&img.ch[i].hdr_done, 1);
+    if (early) return early_result;
+    if (firstrealc > endc) { beginc = endc; return true; }
+
+    int pr[kMaxProps][2];
+    int refchan[kMaxProps / 2], nrefchan = 0;
+    const int nprops = init_properties(pr, img, beginc, endc, refchan, nrefchan);
+    const int nref = nprops - NB_NONREF;
+
+    int predictability = 2048;
+    if (predictor == 0 && compress) {
+        int rounded = io.varint();
+        if (rounded < 1 || rounded > 127) return corrupt_or_truncated(io, img.ch[min(firstrealc, img.nch - 1)], lane);
+        predictability = rounded * 32;
+    }
+
+    Rac rac;
+    rac.init(&io);
+
+    if (!compress) {        // encoding.cpp:334-354
+        for (int i = beginc; i <= endc; i++) {
+            DChan &ch = img.ch[i];
+            if (ch.minval == ch.maxval) continue;
+            fill_plane(ch, i < img.n_orig ? 0 : ch.zero, lane);
+            for (int y = 0; y < ch.h; y++) {
+                if (io.stop()) break;
+                for (int x = 0; x < ch.w; x++) ch.data[(size_t)y * ch.w + x] = (int16_t)uniform_read(rac, ch.minval, ch.maxval - ch.minval);
+                publish_rows(ch, y + 1, lane);
+            }
+            if (io.stop()) break;
+        }
+        beginc = endc;
+        return true;
+    }
+
+    int nnodes = 0;
+    if (!read_tree(rac, P.meta_table, pr, nprops, ws.nodes, nnodes, ws.stack, coder)) return corrupt_or_truncated(io, img.ch[beginc], lane);
+
+    // FinalPropertySymbolCoder ctor, compound.h:213-225: leaf numbering in node order, all leaves start from zero_chance
+    const int nleaves = (nnodes + 1) / 2;
+    for (int i = 0, leafID = 0; i < nnodes; i++) if (ws.nodes[i].property == -1) ws.nodes[i].child = (unsigned short)leafID++;
+    for (int i = lane; i < nleaves * 32; i += 32) ws.leaves[i] = initial_chance(i & 31, predictability);
+    __syncwarp();
+
+    int props[kMaxProps];
+    for (int i = 0; i < kMaxProps; i++) props[i] = 0;
+
+    for (int i = beginc; i <= endc; i++) {
+        DChan &ch = img.ch[i];
+        if (ch.minval == ch.maxval) continue;
+        // channel.resize(w,h): buffers made by meta_apply start out as `zero`, the Image constructor's as 0
+        fill_plane(ch, i < img.n_orig ? 0 : ch.zero, lane);
+        if (nnodes == 1 && predictor == 0 && ch.zero == 0) {        // fast track, encoding.cpp:371-383
+            for (int y = 0; y < ch.h; y++) {
+                if (io.stop()) break;
+                for (int x = 0; x < ch.w; x++) ch.data[(size_t)y * ch.w + x] = (int16_t)read_int(rac, P.table, ws.leaves, ch.minval, ch.maxval);
+                publish_rows(ch, y + 1, lane);
+            }
+        } else {
+            for (int y = 0; y < ch.h; y++) {
+                if (io.stop()) break;
+                precompute_references(ch, y, img, refchan, nrefchan, ws.refs, nref, lane);
+                for (int x = 0; x < ch.w; x++) {
+                    for (int k = 0; k < nref; k++) props[k] = ws.refs[x * nref + k];
+                    const int guess = predict_props(props, ch, x, y, predictor, nref);
+                    const int mn = ch.minval - guess, mx = ch.maxval - guess;
+                    int diff;
+                    if (mn == mx) diff = mn;
+                    else {
+                        int pos = 0;                                    // find_leaf, compound.h:142-153
+                        while (ws.nodes[pos].property != -1) {
+                            const TNode nd = ws.nodes[pos];
+                            pos = props[nd.property] > nd.splitval ? nd.child : nd.child + 1;
+                        }
+                        diff = read_int(rac, P.table, ws.leaves + 32 * ws.nodes[pos].child, mn, mx);
+                    }
+                    ch.data[(size_t)y * ch.w + x] = (int16_t)(s16(diff) + guess);
+                }
+                publish_rows(ch, y + 1, lane);
+            }
+        }
+        if (io.stop()) break;
+    }
+    beginc = endc;
+    return true;
+}
+
+__global__ void __launch_bounds__(32) k_maniac_decode(Params P) {
+    __shared__ uint16_t s_table[4096 * 2];
+    __shared__ uint16_t s_coder[3][32];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 4096 * 2; i += 32) s_table[i] = P.table[i];
+    __syncwarp();
+    Params Q = P;
+    Q.table = s_table;
+    WarpScratch ws = P.scratch[blockIdx.x];
+    for (;;) {
+        int sid = 0;
+        if (lane == 0) sid = atomicAdd(P.ticket, 1);
+        sid = __shfl_sync(0xffffffffu, sid, 0);
+        if (sid >= P.nstreams) break;
+        const DStream st = P.streams[sid];
+        DImage &img = P.images[st.image];
+        Reader io;
+        io.p = img.bytes; io.n = img.nbytes; io.pos = st.offset; io.btl = img.bytes_to_load; io.eof = false;
+        int groups = 0;
+        // the channel loop of fuif_decode, encoding.cpp:708-718
+        for (int i = st.first_channel; i < img.nch; i++) {
+            if (st.max_groups >= 0 && groups >= st.max_groups) break;
+            if ((img.bytes_to_load == 0 || io.pos < img.bytes_to_load) && !io.eof) {
+                if (!img.ch[i].w || !img.ch[i].h) continue;
+                bool ok = decode_group(img, io, i, Q, ws, lane, s_coder);
+                groups++;
+                if (!ok) { img.status = FB_ERR_INVALID; break; }
+            } else break;
+        }
+        // whatever happened (truncation, corruption), nobody may wait forever on this stream's channels
+        for (int c = st.first_channel; c < st.end_channel && c < img.nch; c++) {
+            atomicExch(&img.ch[c].hdr_done, 1);
+            publish_rows(img.ch[c], img.ch[c].h, lane);
+        }
+        __syncwarp();
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+
+// build_table, maniac/chance.cpp:31-65
+void build_table(uint16_t *t /*[4096][2]*/, uint32_t factor, unsigned max_p) {
+    const int64_t one = 1LL << 32;
+    const int size = 4096;
+    memset(t, 0, sizeof(uint16_t) * size * 2);
+    unsigned last_p8 = 0, p8;
+    int64_t p = one / 2;
+    for (unsigned i = 0; i < (unsigned)size / 2; i++) {
+        p8 = (unsigned)((size * p + one / 2) >> 32);
+        if (p8 <= last_p8) p8 = last_p8 + 1;
+        if (last_p8 && last_p8 < (unsigned)size && p8 <= max_p) t[last_p8 * 2 + 1] = (uint16_t)p8;
+        p += ((one - p) * factor + one / 2) >> 32;
+        last_p8 = p8;
+    }
+    for (unsigned i = size - max_p; i <= max_p; i++) {
+        if (t[i * 2 + 1]) continue;
+        p = ((int64_t)i * one + size / 2) / size;
+        p += ((one - p) * factor + one / 2) >> 32;
+        p8 = (unsigned)((size * p + one / 2) >> 32);
+        if (p8 <= i) p8 = i + 1;
+        if (p8 > max_p) p8 = max_p;
+        t[i * 2 + 1] = (uint16_t)p8;
+    }
+    for (unsigned i = 1; i < (unsigned)size; i++) t[i * 2 + 0] = (uint16_t)(size - t[(size - i) * 2 + 1]);
+}
+
+struct ManiacState {
+    uint16_t *table_dev = nullptr, *meta_dev = nullptr;
+    int cutoff = -1, alpha = -1;
+    int nslots = 0, maxw = 0;
+    WarpScratch *scratch_dev = nullptr;
+    void *arena = nullptr;
+    int *ticket_dev = nullptr;
+};
+
+int ensure_state(fb_ctx *ctx, int cutoff, int alpha, int nslots, int maxw) {
+    ManiacState *st = (ManiacState *)ctx->maniac_state;
+    if (!st) { st = new ManiacState(); ctx->maniac_state = st; }
+    if (!st->table_dev) {
+        FB_CUDA(ctx, cudaMalloc((void **)&st->table_dev, 4096 * 2 * sizeof(uint16_t)));
+        FB_CUDA(ctx, cudaMalloc((void **)&st->meta_dev, 4096 * 2 * sizeof(uint16_t)));
+        FB_CUDA(ctx, cudaMalloc((void **)&st->ticket_dev, sizeof(int)));
+        std::vector<uint16_t> t(4096 * 2);
+        build_table(t.data(), 0xFFFFFFFFu / 19, 4096 - 2);      // SimpleBitChanceTable(cut=2, alpha=0xFFFFFFFF/19), chance.h:53
+        FB_CUDA(ctx, cudaMemcpy(st->meta_dev, t.data(), t.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
+    if (st->cutoff != cutoff || st->alpha != alpha) {
+        std::vector<uint16_t> t(4096 * 2);
+        build_table(t.data(), (uint32_t)alpha, (unsigned)(4096 - cutoff));
+        FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        FB_CUDA(ctx, cudaMemcpy(st->table_dev, t.data(), t.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        st->cutoff = cutoff; st->alpha = alpha;
+    }
+    if (nslots > st->nslots || maxw > st->maxw) {
+        FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (st->arena) cudaFree(st->arena);
+        if (st->scratch_dev) cudaFree(st->scratch_dev);
+        st->arena = nullptr; st->scratch_dev = nullptr;
+        nslots = std::max(nslots, st->nslots);
+        maxw = std::max(maxw, st->maxw);
+        const size_t nodes_b = sizeof(TNode) * kMaxNodes, leaves_b = sizeof(uint16_t) * 32 * (kMaxNodes / 2);
+        const size_t stack_b = sizeof(int) * 4 * (kMaxNodes / 2 + 2);
+        const size_t refs_b = ((sizeof(int16_t) * (size_t)maxw * 12) + 255) & ~(size_t)255;
+        const size_t per = nodes_b + leaves_b + stack_b + refs_b;
+        FB_CUDA(ctx, cudaMalloc(&st->arena, per * nslots));
+        std::vector<WarpScratch> ws(nslots);
+        for (int i = 0; i < nslots; i++) {
+            char *base = (char *)st->arena + per * i;
+            ws[i].nodes = (TNode *)base;
+            ws[i].leaves = (uint16_t *)(base + nodes_b);
+            ws[i].stack = (int *)(base + nodes_b + leaves_b);
+            ws[i].refs = (int16_t *)(base + nodes_b + leaves_b + stack_b);
+        }
+        FB_CUDA(ctx, cudaMalloc((void **)&st->scratch_dev, sizeof(WarpScratch) * nslots));
+        FB_CUDA(ctx, cudaMemcpy(st->scratch_dev, ws.data(), sizeof(WarpScratch) * nslots, cudaMemcpyHostToDevice));
+        st->nslots = nslots; st->maxw = maxw;
+    }
+    return FB_OK;
+}
+
+// host copy of read_big_endian_varint for walking the group index
+int host_varint(const uint8_t *p, size_t n, size_t &pos) {
+    int result = 0, k = 0;
+    while (k++ < 10) {
+        if (pos >= n) return -1;
+        int number = p[pos++];
+        if (number < 128) return result + number;
+        result += number - 128;
+        result = (int)((unsigned)result << 7);
+    }
+    return -1;
+}
+
+}  // namespace
+
+void fb_maniac_release(fb_ctx *ctx) {
+    ManiacState *st = (ManiacState *)ctx->maniac_state;
+    if (!st) return;
+    cudaFree(st->table_dev); cudaFree(st->meta_dev); cudaFree(st->ticket_dev); cudaFree(st->arena); cudaFree(st->scratch_dev);
+    delete st;
+    ctx->maniac_state = nullptr;
+}
+
+int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
+    const int nimg = (int)jobs.size();
+    if (!nimg) return FB_OK;
+    int cutoff = jobs[0].cutoff, alpha = jobs[0].alpha;
+    // ---- plane allocation + descriptors
+    std::vector<DImage> himg(nimg);
+    std::vector<std::vector<DChan>> hch(nimg);
+    std::vector<DStream> streams;
+    size_t total_bytes = 0, total_ch = 0;
+    int maxw = 8;
+    for (int b = 0; b < nimg; b++) {
+        if (jobs[b].cutoff != cutoff || jobs[b].alpha != alpha) { ctx->err = "batch with mixed maniac options"; return FB_ERR_INVALID; }
+        total_bytes += (jobs[b].nbytes + 255) & ~(size_t)255;
+        total_ch += jobs[b].img->ch.size();
+    }
+    uint8_t *bytes_dev = nullptr;
+    DChan *ch_dev = nullptr;
+    DImage *img_dev = nullptr;
+    DStream *streams_dev = nullptr;
+    FB_CUDA(ctx, cudaMallocAsync((void **)&bytes_dev, std::max<size_t>(total_bytes, 256), ctx->stream));
+    FB_CUDA(ctx, cudaMallocAsync((void **)&ch_dev, std::max<size_t>(total_ch, 1) * sizeof(DChan), ctx->stream));
+    FB_CUDA(ctx, cudaMallocAsync((void **)&img_dev, nimg * sizeof(DImage), ctx->stream));
+    size_t boff = 0, coff = 0;
+    for (int b = 0; b < nimg; b++) {
+        FbManiacJob &job = jobs[b];
+        fb_image *img = job.img;
+        FB_CUDA(ctx, cudaMemcpyAsync(bytes_dev + boff, job.bytes_host, job.nbytes, cudaMemcpyHostToDevice, ctx->stream));
+        himg[b].bytes = bytes_dev + boff;
+        himg[b].nbytes = job.nbytes;
+        himg[b].bytes_to_load = job.bytes_to_load;
+        himg[b].ch = ch_dev + coff;
+        himg[b].nch = (int)img->ch.size();
+        himg[b].max_properties = job.max_properties;
+        himg[b].n_orig = img->info.real_nb_channels;
+        himg[b].status = 0;
+        hch[b].resize(img->ch.size());
+        for (size_t i = 0; i < img->ch.size(); i++) {
+            FbChan &c = img->ch[i];
+            DChan &d = hch[b][i];
+            memset(&d, 0, sizeof(d));
+            d.w = c.d.w; d.h = c.d.h; d.minval = c.d.minval; d.maxval = c.d.maxval; d.zero = c.d.zero; d.q = c.d.q;
+            d.hshift = c.d.hshift; d.vshift = c.d.vshift; d.group_off = -1;
+            const size_t n = (c.d.w > 0 && c.d.h > 0) ? (size_t)c.d.w * c.d.h : 0;
+            if (n) { int rc = fb_plane_alloc(ctx, n, &c.dev); if (rc) return rc; }
+            d.data = c.dev;
+            if (!n) { d.hdr_done = 1; d.rows_done = 0x7fffffff; }     // empty channels are skipped by the channel loop
+            maxw = std::max(maxw, c.d.w);
+        }
+        if (!hch[b].empty())
+            FB_CUDA(ctx, cudaMemcpyAsync(ch_dev + coff, hch[b].data(), hch[b].size() * sizeof(DChan), cudaMemcpyHostToDevice, ctx->stream));
+        // ---- streams
+        if (himg[b].nch > 0) {
+            bool indexed = job.group_index && job.n_groups > 0;
+            if (indexed) {
+                // one stream per group: walk the channel list exactly like the loop of fuif_decode (encoding.cpp:708-718)
+                int i = 0;
+                std::vector<DStream> mine;
+                for (int g = 0; g < job.n_groups && indexed; g++) {
+                    while (i < himg[b].nch && (!img->ch[i].d.w || !img->ch[i].d.h)) i++;
+                    size_t pos = (size_t)job.group_index[g];
+                    if (i >= himg[b].nch || job.group_index[g] < (int64_t)job.body_pos || pos >= job.nbytes) { indexed = false; break; }
+                    if (job.bytes_to_load && pos >= job.bytes_to_load) break;
+                    int fb = host_varint(job.bytes_host, job.nbytes, pos);
+                    if (fb < 0) { indexed = false; break; }
+                    if (!mine.empty()) mine.back().end_channel = i;
+                    mine.push_back(DStream{b, i, himg[b].nch, 1, (unsigned long long)job.group_index[g]});
+                    i += (fb >> 4) + 1;
+                }
+                if (indexed && !mine.empty()) streams.insert(streams.end(), mine.begin(), mine.end());
+                else indexed = false;
+            }
+            if (!indexed) streams.push_back(DStream{b, 0, himg[b].nch, -1, (unsigned long long)job.body_pos});
+        }
+        boff += (job.nbytes + 255) & ~(size_t)255;
+        coff += img->ch.size();
+    }
+    FB_CUDA(ctx, cudaMemcpyAsync(img_dev, himg.data(), nimg * sizeof(DImage), cudaMemcpyHostToDevice, ctx->stream));
+    const int nstreams = (int)streams.size();
+    if (nstreams) {
+        // streams are ordered image-major, groups ascending: dependencies always point to lower stream ids
+        FB_CUDA(ctx, cudaMallocAsync((void **)&streams_dev, nstreams * sizeof(DStream), ctx->stream));
+        FB_CUDA(ctx, cudaMemcpyAsync(streams_dev, streams.data(), nstreams * sizeof(DStream), cudaMemcpyHostToDevice, ctx->stream));
+        const int nslots = std::min(nstreams, ctx->sm_count * 8);
+        int rc = ensure_state(ctx, cutoff, alpha, nslots, maxw);
+        if (rc) return rc;
+        ManiacState *st = (ManiacState *)ctx->maniac_state;
+        FB_CUDA(ctx, cudaMemsetAsync(st->ticket_dev, 0, sizeof(int), ctx->stream));
+        Params P;
+        P.images = img_dev; P.streams = streams_dev; P.nstreams = nstreams; P.ticket = st->ticket_dev;
+        P.table = st->table_dev; P.meta_table = st->meta_dev; P.scratch = st->scratch_dev; P.maxw = st->maxw;
+        k_maniac_decode<<<nslots, 32, 0, ctx->stream>>>(P);
+        ctx->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { ctx->err = std::string("maniac launch: ") + cudaGetErrorString(e); return FB_ERR_CUDA; }
+    }
+    // ---- read back channel descriptors (ranges, q, which planes hold data) and the per-image status
+    std::vector<DChan> back(total_ch);
+    if (total_ch) FB_CUDA(ctx, cudaMemcpyAsync(back.data(), ch_dev, total_ch * sizeof(DChan), cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(ctx, cudaMemcpyAsync(himg.data(), img_dev, nimg * sizeof(DImage), cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(bytes_dev, ctx->stream); cudaFreeAsync(ch_dev, ctx->stream); cudaFreeAsync(img_dev, ctx->stream);
+    if (streams_dev) cudaFreeAsync(streams_dev, ctx->stream);
+    coff = 0;
+    int rc = FB_OK;
+    for (int b = 0; b < nimg; b++) {
+        fb_image *img = jobs[b].img;
+        for (size_t i = 0; i < img->ch.size(); i++) {
+            const DChan &d = back[coff + i];
+            FbChan &c = img->ch[i];
+            c.d.minval = d.minval; c.d.maxval = d.maxval; c.d.zero = d.zero; c.d.q = d.q;
+            if (d.state) c.d.decoded = 1;
+            else { fb_plane_free(ctx, c.dev); c.dev = nullptr; c.d.decoded = 0; }
+            if (d.group_off >= 0) { img->group_off.push_back(d.group_off); img->group_first.push_back((int32_t)i); }
+        }
+        if (himg[b].status) { ctx->err = "corrupt FUIF stream (image " + std::to_string(b) + ")"; rc = FB_ERR_INVALID; }
+        coff += img->ch.size();
+    }
+    return rc;
+}

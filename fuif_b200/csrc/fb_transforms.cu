@@ -1,0 +1,432 @@
+// Transform-chain kernels of fuif_b200 (sm_100a).  Bit-exact with the reference's integer / double results.
+//
+// All sample arithmetic follows the C++ semantics of the reference with pixel_type == int16_t
+// (reference image/image.h:35): a value assigned to a pixel_type wraps to 16 bits at that point (s16()).
+// The DCT and YCbCr kernels use __dmul_rn/__dadd_rn/__fsub_rn so that nvcc can never contract a multiply
+// and an add into an FMA: the reference is built for baseline x86-64 and rounds after every operation.
+#include "fb_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ int s16(int x) { return (int)(short)x; }
+
+// smooth_tendency, reference transform/squeeze.h:61-77
+__device__ __forceinline__ int smooth_tendency(int B, int a, int n) {
+    int diff = 0;
+    if (B >= a && a >= n) {
+        diff = s16((4 * B - 3 * n - a + 6) / 12);
+        if (diff - (diff & 1) > 2 * (B - a)) diff = s16(2 * (B - a) + 1);
+        if (diff + (diff & 1) > 2 * (a - n)) diff = s16(2 * (a - n));
+    } else if (B <= a && a <= n) {
+        diff = s16((4 * B - 3 * n - a - 6) / 12);
+        if (diff + (diff & 1) < 2 * (B - a)) diff = s16(2 * (B - a) - 1);
+        if (diff - (diff & 1) < 2 * (a - n)) diff = s16(2 * (a - n));
+    }
+    return diff;
+}
+
+// One unsqueeze pair (squeeze.h:97-108): given previous reconstructed sample `prev`, current average, next
+// average and the stored residual, produce A and B.
+__device__ __forceinline__ void unsqueeze_pair(int prev, int avg, int next_avg, int res, int &A, int &B) {
+    int tendency = smooth_tendency(prev, avg, next_avg);
+    int diff = s16(res + tendency);
+    A = s16(((avg << 1) + diff + (diff > 0 ? -(diff & 1) : (diff & 1))) >> 1);
+    B = s16(A - diff);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// v1 unsqueeze kernels: one thread per chain (row for horizontal, column for vertical).
+// ---------------------------------------------------------------------------------------------------------
+
+// inv_hsqueeze, squeeze.h:81-132.  avg: wa x h, res: wr x h (nullptr = zeros), out: (wa+wr) x h
+__global__ void k_inv_hsqueeze_rows(const int16_t *__restrict__ avg, const int16_t *__restrict__ res, int16_t *__restrict__ out,
+                                    int wa, int wr, int h) {
+    int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= h) return;
+    const int wo = wa + wr;
+    const int16_t *a = avg + (size_t)y * wa;
+    const int16_t *r = res ? res + (size_t)y * wr : nullptr;
+    int16_t *o = out + (size_t)y * wo;
+    if (wr == 0) {          // nothing to merge: the reference ends up copying the averages
+        for (int x = 0; x < wa; x++) o[x] = a[x];
+        return;
+    }
+    int prev = a[0];
+    for (int x = 0; x < wr; x++) {
+        int av = a[x];
+        int nx = (x + 1 < wa) ? a[x + 1] : av;
+        int rs = r ? r[x] : 0;
+        int A, B;
+        unsqueeze_pair(x == 0 ? av : prev, av, nx, rs, A, B);
+        o[2 * x] = (int16_t)A;
+        o[2 * x + 1] = (int16_t)B;
+        prev = B;
+    }
+    if (wo & 1) o[wo - 1] = a[wa - 1];
+}
+
+// inv_vsqueeze, squeeze.h:173-224.  avg: w x ha, res: w x hr, out: w x (ha+hr)
+__global__ void k_inv_vsqueeze_cols(const int16_t *__restrict__ avg, const int16_t *__restrict__ res, int16_t *__restrict__ out,
+                                    int w, int ha, int hr) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    const int ho = ha + hr;
+    if (hr == 0) {
+        for (int y = 0; y < ha; y++) out[(size_t)y * w + x] = avg[(size_t)y * w + x];
+        return;
+    }
+    int prev = 0;
+    int av = avg[x];
+    for (int y = 0; y < hr; y++) {
+        int nx = (y + 1 < ha) ? avg[(size_t)(y + 1) * w + x] : av;
+        int rs = res ? res[(size_t)y * w + x] : 0;
+        int A, B;
+        unsqueeze_pair(y == 0 ? av : prev, av, nx, rs, A, B);
+        out[(size_t)(2 * y) * w + x] = (int16_t)A;
+        out[(size_t)(2 * y + 1) * w + x] = (int16_t)B;
+        prev = B;
+        av = nx;
+    }
+    if (ho & 1) out[(size_t)(ho - 1) * w + x] = avg[(size_t)(ha - 1) * w + x];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward squeeze: fully parallel, one thread per residual sample (squeeze.h:135-170, 227-263)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pair_avg(int A, int B) { return s16((A + B + (A > B)) >> 1); }
+
+__global__ void k_fwd_hsqueeze(const int16_t *__restrict__ in, int16_t *__restrict__ avg, int16_t *__restrict__ res, int w, int h) {
+    const int wa = (w + 1) / 2, wr = w - wa;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)wa * h) return;
+    int y = (int)(idx / wa), x = (int)(idx % wa);
+    const int16_t *row = in + (size_t)y * w;
+    if (x >= wr) {      // odd tail column: plain copy (squeeze.h:164-167)
+        avg[(size_t)y * wa + x] = row[2 * x];
+        return;
+    }
+    int A = row[2 * x], B = row[2 * x + 1];
+    int av = pair_avg(A, B);
+    avg[(size_t)y * wa + x] = (int16_t)av;
+    int diff = s16(A - B);
+    int nx = av;
+    if (x + 1 < wr) nx = pair_avg(row[2 * x + 2], row[2 * x + 3]);
+    else if (w & 1) nx = row[2 * x + 2];
+    int left = (x > 0) ? row[2 * x - 1] : av;
+    res[(size_t)y * wr + x] = (int16_t)s16(diff - smooth_tendency(left, av, nx));
+}
+
+__global__ void k_fwd_vsqueeze(const int16_t *__restrict__ in, int16_t *__restrict__ avg, int16_t *__restrict__ res, int w, int h) {
+    const int ha = (h + 1) / 2, hr = h - ha;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)w * ha) return;
+    int y = (int)(idx / w), x = (int)(idx % w);
+    if (y >= hr) {
+        avg[(size_t)y * w + x] = in[(size_t)(2 * y) * w + x];
+        return;
+    }
+    int A = in[(size_t)(2 * y) * w + x], B = in[(size_t)(2 * y + 1) * w + x];
+    int av = pair_avg(A, B);
+    avg[(size_t)y * w + x] = (int16_t)av;
+    int diff = s16(A - B);
+    int nx = av;
+    if (y + 1 < hr) nx = pair_avg(in[(size_t)(2 * y + 2) * w + x], in[(size_t)(2 * y + 3) * w + x]);
+    else if (h & 1) nx = in[(size_t)(2 * y + 2) * w + x];
+    int top = (y > 0) ? in[(size_t)(2 * y - 1) * w + x] : av;
+    res[(size_t)y * w + x] = (int16_t)s16(diff - smooth_tendency(top, av, nx));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// colour transforms, quantisation, clamp
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// inv_YCoCg (ycocg.h:51-56) optionally followed by the final clamp of undo_transforms (image.cpp:107-113)
+__global__ void k_ycocg(int16_t *__restrict__ c0, int16_t *__restrict__ c1, int16_t *__restrict__ c2, size_t n, int maxval, int inverse,
+                        int lo, int hi, int do_clamp) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (inverse) {
+        int Y = clampi(c0[i], 0, maxval);
+        int Co = c1[i], Cg = c2[i];
+        int G = clampi(Y - ((-Cg) >> 1), 0, maxval);
+        int B = clampi(Y + ((1 - Cg) >> 1) - (Co >> 1), 0, maxval);
+        int R = clampi(Co + B, 0, maxval);
+        if (do_clamp) { R = clampi(R, lo, hi); G = clampi(G, lo, hi); B = clampi(B, lo, hi); }
+        c0[i] = (int16_t)R; c1[i] = (int16_t)G; c2[i] = (int16_t)B;
+    } else {
+        int R = c0[i], G = c1[i], B = c2[i];
+        int Y = (((R + B) >> 1) + G) >> 1;
+        int Co = R - B;
+        int Cg = G - ((R + B) >> 1);
+        c0[i] = (int16_t)Y; c1[i] = (int16_t)Co; c2[i] = (int16_t)Cg;
+    }
+}
+
+__device__ __forceinline__ int16_t clamp_trunc(double x, int lo, int hi) {
+    // CLAMP(x, l, u) evaluated in double, then the truncating double -> pixel_type conversion (ycbcr.h:55-57)
+    double v = (x < (double)lo) ? (double)lo : ((x > (double)hi) ? (double)hi : x);
+    return (int16_t)__double2int_rz(v);
+}
+
+// inv_YCbCr / fwd_YCbCr (ycbcr.h:49-58 / 81-90): float loads, double arithmetic in source order, no FMA
+__global__ void k_ycbcr(int16_t *__restrict__ c0, int16_t *__restrict__ c1, int16_t *__restrict__ c2, size_t n, int minval, int maxval,
+                        int inverse) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float half = (float)((maxval + 1) / 2);
+    if (inverse) {
+        float yy = (float)c0[i];
+        float cb = __fsub_rn((float)c1[i], half);
+        float cr = __fsub_rn((float)c2[i], half);
+        double dy = (double)yy, dcb = (double)cb, dcr = (double)cr;
+        double r = __dadd_rn(__dadd_rn(dy, __dmul_rn(1.402, dcr)), 0.5);
+        double g = __dadd_rn(__dsub_rn(__dsub_rn(dy, __dmul_rn(0.344136, dcb)), __dmul_rn(0.714136, dcr)), 0.5);
+        double b = __dadd_rn(__dadd_rn(dy, __dmul_rn(1.772, dcb)), 0.5);
+        c0[i] = clamp_trunc(r, minval, maxval);
+        c1[i] = clamp_trunc(g, minval, maxval);
+        c2[i] = clamp_trunc(b, minval, maxval);
+    } else {
+        double r = (double)(float)c0[i], g = (double)(float)c1[i], b = (double)(float)c2[i];
+        double dh = (double)half;
+        double yy = __dadd_rn(__dadd_rn(__dmul_rn(0.299, r), __dmul_rn(0.587, g)), __dmul_rn(0.114, b));
+        double cb = __dadd_rn(__dsub_rn(__dsub_rn(dh, __dmul_rn(0.168736, r)), __dmul_rn(0.331264, g)), __dmul_rn(0.5, b));
+        double cr = __dsub_rn(__dsub_rn(__dadd_rn(dh, __dmul_rn(0.5, r)), __dmul_rn(0.418688, g)), __dmul_rn(0.081312, b));
+        c0[i] = clamp_trunc(yy, minval, maxval);
+        c1[i] = clamp_trunc(cb, minval, maxval);
+        c2[i] = clamp_trunc(cr, minval, maxval);
+    }
+}
+
+__global__ void k_quantize(int16_t *__restrict__ p, size_t n, int q, int inverse) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int v = p[i];
+    p[i] = (int16_t)(inverse ? v * q : v / q);      // quantize.h:42 / 63 (rounded_div == n/d, :54)
+}
+
+__global__ void k_clamp(int16_t *__restrict__ p, size_t n, int lo, int hi) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    p[i] = (int16_t)clampi(p[i], lo, hi);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 8x8 DCT in double (dct.h:60-107): out = 0.0; out += k*in, columns then rows
+// ---------------------------------------------------------------------------------------------------------
+// kDCTMatrix[8u+x] = 0.5*alpha(u)*cos((2x+1)u*pi/16) to 10 decimals (dct.h:60-77)
+#define C0 0.3535533906
+#define C1 0.4903926402
+#define C2 0.4619397663
+#define C3 0.4157348062
+#define C5 0.2777851165
+#define C6 0.1913417162
+#define C7 0.0975451610
+__constant__ double kDCT[64] = {
+    C0,  C0,  C0,  C0,  C0,  C0,  C0,  C0,
+    C1,  C3,  C5,  C7, -C7, -C5, -C3, -C1,
+    C2,  C6, -C6, -C2, -C2, -C6,  C6,  C2,
+    C3, -C7, -C1, -C5,  C5,  C1,  C7, -C3,
+    C0, -C0, -C0,  C0,  C0, -C0, -C0,  C0,
+    C5, -C1,  C7,  C3, -C3, -C7,  C1, -C5,
+    C6, -C2,  C2, -C6, -C6,  C2, -C2,  C6,
+    C7, -C5,  C3, -C1,  C1, -C3,  C5, -C7,
+};
+
+struct Planes64 { const int16_t *p[64]; };
+struct Planes64W { int16_t *p[64]; };
+
+__device__ __forceinline__ void dct_1d(const double *in, int stride, double *out, bool inverse) {
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+        double acc = 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            double k = inverse ? kDCT[8 * u + x] : kDCT[8 * x + u];
+            acc = __dadd_rn(acc, __dmul_rn(k, in[u * stride]));
+        }
+        out[x * stride] = acc;
+    }
+}
+
+// inv_DCT body (dct.h:281-291): thread per 8x8 block
+__global__ void k_inv_dct(Planes64 pl, int16_t *__restrict__ out, int bw, int bh, float dc_offset) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)bw * bh) return;
+    int by = (int)(idx / bw), bx = (int)(idx % bw);
+    double block[64], tmp[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        int v = pl.p[i] ? pl.p[i][idx] : 0;
+        block[i] = (i == 0) ? (double)__fadd_rn((float)v, dc_offset) : (double)v;
+    }
+#pragma unroll
+    for (int x = 0; x < 8; ++x) dct_1d(&block[x], 8, &tmp[x], true);
+#pragma unroll
+    for (int y = 0; y < 8; ++y) dct_1d(&tmp[8 * y], 1, &block[8 * y], true);
+    const int ow = bw * 8;
+#pragma unroll
+    for (int y = 0; y < 8; y++) {
+        int16_t v[8];
+#pragma unroll
+        for (int x = 0; x < 8; x++) v[x] = (int16_t)__double2int_rz(round(block[y * 8 + x]));
+        int4 pk;
+        pk.x = (uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
+        pk.y = (uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16);
+        pk.z = (uint16_t)v[4] | ((uint32_t)(uint16_t)v[5] << 16);
+        pk.w = (uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16);
+        *reinterpret_cast<int4 *>(out + (size_t)(by * 8 + y) * ow + bx * 8) = pk;
+    }
+}
+
+// fwd_DCT body (dct.h:322-332)
+__global__ void k_fwd_dct(const int16_t *__restrict__ in, int w, int h, Planes64W pl, int bw, int bh, float dc_offset) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)bw * bh) return;
+    int by = (int)(idx / bw), bx = (int)(idx % bw);
+    double block[64], tmp[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        int r = by * 8 + (i >> 3), c = bx * 8 + (i & 7);      // repeating_edge_value, image.h:86
+        r = r >= h ? h - 1 : r;
+        c = c >= w ? w - 1 : c;
+        block[i] = (double)in[(size_t)r * w + c];
+    }
+#pragma unroll
+    for (int x = 0; x < 8; ++x) dct_1d(&block[x], 8, &tmp[x], false);
+#pragma unroll
+    for (int y = 0; y < 8; ++y) dct_1d(&tmp[8 * y], 1, &block[8 * y], false);
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        double v = round(block[i]);
+        if (i == 0) v = __dsub_rn(v, (double)dc_offset);
+        pl.p[i][idx] = (int16_t)__double2int_rz(v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// min/max and interleave
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_minmax(const int16_t *__restrict__ p, size_t n, int *out2) {
+    int mn = 0x7FFF, mx = -0x7FFF;      // LARGEST_VAL / SMALLEST_VAL, image.h:36-37
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int v = p[i];
+        mn = min(mn, v);
+        mx = max(mx, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&out2[0], mn); atomicMax(&out2[1], mx); }
+}
+
+struct PlanesN { const int16_t *p[8]; };
+__global__ void k_interleave(PlanesN pl, int nch, size_t npix, int bps, uint8_t *__restrict__ dst) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    for (int c = 0; c < nch; c++) {
+        int v = pl.p[c][i];
+        if (bps == 1) dst[i * nch + c] = (uint8_t)(v & 0xFF);
+        else { dst[(i * nch + c) * 2] = (uint8_t)((v >> 8) & 0xFF); dst[(i * nch + c) * 2 + 1] = (uint8_t)(v & 0xFF); }
+    }
+}
+
+inline unsigned nblocks(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+#define FB_LAUNCH_CHECK(ctx)                                                                       \
+    do {                                                                                           \
+        (ctx)->launches++;                                                                         \
+        cudaError_t e__ = cudaGetLastError();                                                      \
+        if (e__ != cudaSuccess) { (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(e__); return FB_ERR_CUDA; } \
+    } while (0)
+
+int fb_launch_inv_hsqueeze(fb_ctx *ctx, const int16_t *avg, const int16_t *res, int16_t *out, int wa, int wr, int h) {
+    if (h <= 0 || wa <= 0) return FB_OK;
+    k_inv_hsqueeze_rows<<<nblocks(h, 64), 64, 0, ctx->stream>>>(avg, res, out, wa, wr, h);
+    FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}
+int fb_launch_inv_vsqueeze(fb_ctx *ctx, const int16_t *avg, const int16_t *res, int16_t *out, int w, int ha, int hr) {
+    if (w <= 0 || ha <= 0) return FB_OK;
+    k_inv_vsqueeze_cols<<<nblocks(w, 64), 64, 0, ctx->stream>>>(avg, res, out, w, ha, hr);
+    FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}
+int fb_launch_fwd_hsqueeze(fb_ctx *ctx, const int16_t *in, int16_t *avg, int16_t *res, int w, int h) {
+    size_t n = (size_t)((w + 1) / 2) * h;
+    if (!n) return FB_OK;
+    k_fwd_hsqueeze<<<nblocks(n, 256), 256, 0, ctx->stream>>>(in, avg, res, w, h);
+    FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}
+int fb_launch_fwd_vsqueeze(fb_ctx *ctx, const int16_t *in, int16_t *avg, int16_t *res, int w, int h) {
+    size_t n = (size_t)w * ((h + 1) / 2);
+    if (!n) return FB_OK;
+    k_fwd_vsqueeze<<<nblocks(n, 256), 256, 0, ctx->stream>>>(in, avg, res, w, h);
+    FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}
+int fb_launch_ycocg(fb_ctx *ctx, int16_t *c0, int16_t *c1, int16_t *c2, size_t n, int maxval, int inverse, int lo, int hi, int do_clamp) {
+    if (!n) return FB_OK;
+    k_ycocg<<<nblocks(n, 256), 256, 0, ctx->stream>>>(c0, c1, c2, n, maxval, inverse, lo, hi, do_clamp);
+    FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}
+int fb_launch_ycbcr(fb_ctx *ctx, int16_t *c0, int16_t *c1, int16_t *c2, size_t n, int minval, int maxval, int inverse) {
+    if (!n) return FB_OK;
+    k_ycbcr<<<nblocks(n, 256), 256, 0, ctx->stream>>>(c0, c1, c2, n, minval, maxval, inverse);
+    FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}
+int fb_launch_quantize(fb_ctx *ctx, int16_t *p, size_t n, int q, int inverse) {
+    if (!n) return FB_OK;
+    k_quantize<<<nblocks(n, 256), 256, 0, ctx->stream>>>(p, n, q, inverse);
+    FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}
+int fb_launch_clamp(fb_ctx *ctx, int16_t *p, size_t n, int lo, int hi) {
+    if (!n) return FB_OK;
+    k_clamp<<<nblocks(n, 256), 256, 0, ctx->stream>>>(p, n, lo, hi);
+    FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}
+int fb_launch_inv_dct(fb_ctx *ctx, const int16_t *const *planes64, int16_t *out, int bw, int bh, float dc_offset) {
+    size_t n = (size_t)bw * bh;
+    if (!n) return FB_OK;
+    Planes64 pl;
+    for (int i = 0; i < 64; i++) pl.p[i] = planes64[i];
+    k_inv_dct<<<nblocks(n, 64), 64, 0, ctx->stream>>>(pl, out, bw, bh, dc_offset);
+    FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}
+int fb_launch_fwd_dct(fb_ctx *ctx, const int16_t *in, int w, int h, int16_t *const *planes64, int bw, int bh, float dc_offset) {
+    size_t n = (size_t)bw * bh;
+    if (!n) return FB_OK;
+    Planes64W pl;
+    for (int i = 0; i < 64; i++) pl.p[i] = planes64[i];
+    k_fwd_dct<<<nblocks(n, 64), 64, 0, ctx->stream>>>(in, w, h, pl, bw, bh, dc_offset);
+    FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}
+int fb_launch_minmax(fb_ctx *ctx, const int16_t *p, size_t n, int *out2_dev) {
+    int init[2] = {0x7FFF, -0x7FFF};
+    FB_CUDA(ctx, cudaMemcpyAsync(out2_dev, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    if (!n) return FB_OK;
+    unsigned nb = nblocks(n, 256);
+    if (nb > 1184) nb = 1184;
+    k_minmax<<<nb, 256, 0, ctx->stream>>>(p, n, out2_dev);
+    FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}
+int fb_launch_interleave(fb_ctx *ctx, const int16_t *const *planes, int nch, size_t npix, int bps, void *dst) {
+    if (!npix) return FB_OK;
+    if (nch > 8) return FB_ERR_INVALID;
+    PlanesN pl;
+    for (int i = 0; i < 8; i++) pl.p[i] = i < nch ? planes[i] : nullptr;
+    k_interleave<<<nblocks(npix, 256), 256, 0, ctx->stream>>>(pl, nch, npix, bps, (uint8_t *)dst);
+    FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}

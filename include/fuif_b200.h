@@ -1,0 +1,160 @@
+/* fuif_b200 -- C ABI of the B200-native FUIF hot path.
+ *
+ * The reference (cloudinary/fuif) has no plugin / FFI layer: its boundary is the C++ API in
+ * encoding/encoding.h and image/image.h, called only from fuif.cpp and fuifplay.cpp.  This header is the
+ * extern "C" layer a maintainer binds underneath that API: plain pointers and sizes,
+ * int status codes (0 = ok), no C++ or torch types.  Each entry point names the reference interface it
+ * replaces (file:line under the reference tree).
+ *
+ * Model: an fb_image is the device-resident mirror of the reference's `Image` (image/image.h:98-129): a list
+ * of int16 planes in HBM (one per `Channel`, image/image.h:54-91, row-major, no padding) plus the transform
+ * stack.  A context owns one CUDA device + stream; one context per host thread / GPU.
+ */
+#ifndef FUIF_B200_H
+#define FUIF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FB_API __attribute__((visibility("default")))
+#else
+#define FB_API
+#endif
+
+#define FB_OK 0
+#define FB_ERR_INVALID 1      /* bad argument / malformed stream ("return false" in the reference)            */
+#define FB_ERR_CUDA 2         /* CUDA runtime error; fb_last_error() has the text                            */
+#define FB_ERR_UNSUPPORTED 3  /* transform outside the hot path (palette, 2dmatch, permute, approximate, ..) */
+#define FB_ERR_NOMEM 4
+
+/* transform ids, reference transform/transform.h:30-70 */
+#define FB_TRANSFORM_YCBCR 0
+#define FB_TRANSFORM_YCOCG 1
+#define FB_TRANSFORM_SUBSAMPLE 3
+#define FB_TRANSFORM_DCT 4
+#define FB_TRANSFORM_QUANTIZE 5
+#define FB_TRANSFORM_SQUEEZE 7
+
+typedef struct fb_ctx fb_ctx;
+typedef struct fb_image fb_image;
+
+/* Mirrors class Channel (reference image/image.h:54-91) without the sample buffer. */
+typedef struct fb_plane_desc {
+    int32_t w, h;
+    int32_t minval, maxval;
+    int32_t zero;
+    int32_t q;
+    int32_t hshift, vshift;
+    int32_t hcshift, vcshift;
+    int32_t component;
+    int32_t decoded;          /* 1 if the plane holds samples (data.size() != 0 in the reference) */
+} fb_plane_desc;
+
+/* Mirrors the scalar members of class Image (reference image/image.h:98-129). */
+typedef struct fb_image_info {
+    int32_t w, h;
+    int32_t minval, maxval;
+    int32_t nb_channels, real_nb_channels, nb_meta_channels;
+    int32_t colormodel;
+    int32_t nb_planes;        /* channel.size()   */
+    int32_t nb_transforms;    /* transform.size() */
+    int32_t error;            /* Image::error     */
+} fb_image_info;
+
+/* Mirrors struct fuif_options (reference encoding/encoding.h:32-59), decode-side members only. */
+typedef struct fb_decode_options {
+    int32_t preview;          /* -1 all, 0 LQIP, 1..4 = 1/16 .. 1/2 (encoding.h:34)                  */
+    int32_t maniac_cutoff;    /* 6          (encoding.h:40; not in the bitstream)         */
+    int32_t maniac_alpha;     /* 0x0d000000 (encoding.h:41)                                          */
+    int32_t reserved;
+} fb_decode_options;
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+
+/* device: CUDA ordinal.  stream: a cudaStream_t to enqueue all work on (0 = a private stream is created). */
+FB_API int fb_ctx_create(int device, void *stream, fb_ctx **out);
+FB_API void fb_ctx_destroy(fb_ctx *ctx);
+FB_API const char *fb_last_error(fb_ctx *ctx);
+/* Blocks until everything enqueued on the context's stream has finished. */
+FB_API int fb_ctx_synchronize(fb_ctx *ctx);
+/* Number of kernels this library has launched on the context so far (bench.py's gpu_launches). */
+FB_API long long fb_ctx_launch_count(fb_ctx *ctx);
+
+/* ---- fuif_decode --------------------------------------------------------------------------------------- */
+
+/* Replaces fuif_decode<BlobReader>() / fuif_decode_file() (reference encoding/encoding.cpp:599-720, 745-753):
+ * parses the container on the host, runs the MANIAC range decoder + context model on the GPU
+ * (fuif_decode_channel, encoding.cpp:259-429) and leaves the TRANSFORMED planes in HBM together with the
+ * transform stack, exactly the state the reference's Image is in after fuif_decode().
+ * bytes: the .fuif file in HOST memory.  group_index (may be NULL): n_groups byte offsets of the channel
+ * groups' headers (fb_image_group_index() of an earlier decode, or written by an encoder) -- with it the
+ * groups decode concurrently, without it they decode back to back as the format dictates.
+ * End-of-stream follows FileIO (reference fileio.h:33-81). */
+FB_API int fb_decode(fb_ctx *ctx, const uint8_t *bytes, size_t nbytes, const fb_decode_options *opts,
+              const int64_t *group_index, int n_groups, fb_image **out);
+
+/* Same for a batch: every (image, group) is an independent stream of one kernel launch. */
+FB_API int fb_decode_batch(fb_ctx *ctx, int n_images, const uint8_t *const *bytes, const size_t *nbytes,
+                    const fb_decode_options *opts, const int64_t *const *group_index, const int *n_groups,
+                    fb_image **out);
+
+/* Byte offsets of the channel-group headers found while decoding (one per group, in stream order) and the
+ * first channel of each group.  Returns the number of groups; copies at most cap entries. */
+FB_API int fb_image_group_index(fb_image *img, int64_t *offsets, int32_t *first_channel, int cap);
+
+/* ---- Image ----------------------------------------------------------------------------------------------- */
+
+/* Builds a device image from host planes (what read_PAM_file + do_transform leave behind, or the output of the
+ * reference's own fuif_decode): H2D copy of every plane.  planes[i] may be NULL for desc[i].decoded == 0.
+ * transforms: ids / parameter counts / flattened parameters of Image::transform (image/image.h:101). */
+FB_API int fb_image_create(fb_ctx *ctx, const fb_image_info *info, const fb_plane_desc *desc, const int16_t *const *planes,
+                    const int32_t *transform_ids, const int32_t *transform_nparams, const int32_t *transform_params,
+                    fb_image **out);
+FB_API void fb_image_destroy(fb_image *img);
+
+FB_API int fb_image_get_info(fb_image *img, fb_image_info *info);
+FB_API int fb_image_get_plane(fb_image *img, int i, fb_plane_desc *desc);
+/* Transform i of the stack: returns its parameter count; copies at most cap parameters. */
+FB_API int fb_image_get_transform(fb_image *img, int i, int32_t *id, int32_t *params, int cap);
+/* Device pointer of plane i (int16, w*h samples, row-major) or NULL if not decoded. Valid until the image is
+ * transformed or destroyed. */
+FB_API void *fb_image_plane_device_ptr(fb_image *img, int i);
+/* D2H copy of plane i into dst (w*h int16). Synchronises the stream. */
+FB_API int fb_image_download_plane(fb_image *img, int i, int16_t *dst);
+/* D2H copy of the first n_channels planes interleaved as 8- or 16-bit samples (the layout write_PAM_file
+ * emits, reference export/write_pam.h:29-168; 16-bit samples big-endian). dst holds w*h*n_channels samples. */
+FB_API int fb_image_download_interleaved(fb_image *img, int n_channels, int bytes_per_sample, void *dst);
+
+/* Replaces Image::undo_transforms(keep) (reference image/image.cpp:94-115): pops and inverts transforms until
+ * `keep` are left, then (keep == 0) clamps every sample to [minval, maxval].  Runs entirely on the GPU:
+ * Squeeze (transform/squeeze.h:363-388), Quantize (quantize.h:32-49), DCT (dct.h:249-296),
+ * YCbCr (ycbcr.h:33-63), YCoCg (ycocg.h:33-63). */
+FB_API int fb_image_undo_transforms(fb_image *img, int keep);
+
+/* Replaces Image::do_transform (reference image/image.cpp:117-122; forward direction of the same transforms).
+ * *applied = 1 if the transform was applied and pushed on the stack, 0 if it did not apply. */
+FB_API int fb_image_do_transform(fb_image *img, int32_t id, const int32_t *params, int nparams, int *applied);
+
+/* Replaces Image::recompute_minmax (image/image.h:127; Channel::actual_minmax, image.cpp:82-92). */
+FB_API int fb_image_recompute_minmax(fb_image *img);
+
+/* ---- one-call convenience: file bytes in host memory -> pixels in host memory ------------------------------ */
+
+/* fuif_decode + undo_transforms + interleave, the path `fuif -d in.fuif out.ppm` takes (reference
+ * fuif.cpp:206-239).  dst must hold w*h*nb_channels samples of bytes_per_sample bytes each; query the sizes
+ * with fb_peek_header() first. */
+FB_API int fb_decode_to_pixels(fb_ctx *ctx, const uint8_t *bytes, size_t nbytes, const fb_decode_options *opts,
+                        const int64_t *group_index, int n_groups, int bytes_per_sample, void *dst, size_t dst_bytes);
+
+/* Header-only parse (reference encoding.cpp:599-637, "identify"): fills w, h, maxval, nb_channels. */
+FB_API int fb_peek_header(const uint8_t *bytes, size_t nbytes, fb_image_info *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

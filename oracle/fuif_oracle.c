@@ -841,7 +841,9 @@ static void symchance_init(symchance *s, int zero_chance) {    /* symbol.h:115-1
 
 static inline int ilog2u(uint32_t l) { return l == 0 ? 0 : 31 - __builtin_clz(l); }   /* maniac/util.h:33-36 */
 
+static long long st_bits = 0, st_steps = 0, st_syms = 0, st_same = 0, st_zero = 0, st_unk1 = 0; static int st_last = -1;   /* FO_STATS instrumentation only */
 static inline int sym_read(rac_in *rac, const chance_table *t, symchance *s, int idx) {   /* compound.h:90-95 */
+    st_bits++;
     int bit = rac_read_12bit(rac, s->c[idx]);
     s->c[idx] = t->next[s->c[idx]][bit];
     return bit;
@@ -1186,11 +1188,17 @@ static int decode_channel_group(blob *io, dec_ctx *dc, int max_properties, int *
                     if (mn == mx) diff = mn;
                     else {
                         int pos = 0;                                   /* find_leaf, compound.h:142-153 */
+                        st_syms++;
                         while (t.n[pos].property != -1) {
+                            st_steps++;
                             if (props[t.n[pos].property] > t.n[pos].splitval) pos = t.n[pos].childID;
                             else pos = t.n[pos].childID + 1;
                         }
+                        if (pos == st_last) st_same++;
+                        st_last = pos;
+                        { int q = 0, d = 0; while (t.n[q].property != -1) { int pr_ = t.n[q].property - nref; if (pr_ == 1 || pr_ == 3 || pr_ == 6 || pr_ == 8 || pr_ == 12) break; d++; q = props[t.n[q].property] > t.n[q].splitval ? t.n[q].childID : t.n[q].childID + 1; } st_unk1 += d; }
                         diff = read_int(&rac, &dc->table, &leaf[t.n[pos].childID], mn, mx);
+                        if (diff == 0) st_zero++;
                     }
                     ch->data[(size_t)y * ch->w + x] = (int16_t)(S16(diff) + guess);
                 }
@@ -1198,6 +1206,11 @@ static int decode_channel_group(blob *io, dec_ctx *dc, int max_properties, int *
             free(refs);
         }
         if (STOP(io, btl)) break;
+    }
+    if (getenv("FO_STATS")) {
+        fprintf(stderr, "group %d-%d %dx%d pred %d nodes %d props %d syms %lld steps/sym %.2f bits/sym %.2f same %.2f zero %.2f knownprefix %.2f\n", *pbeginc, endc, img->ch[endc].w, img->ch[endc].h,
+                predictor, t.size, nprops, st_syms, st_syms ? (double)st_steps / st_syms : 0.0, st_syms ? (double)st_bits / st_syms : 0.0, st_syms ? (double)st_same / st_syms : 0.0, st_syms ? (double)st_zero / st_syms : 0.0, st_syms ? (double)st_unk1 / st_syms : 0.0);
+        st_bits = st_steps = st_syms = st_same = st_zero = st_unk1 = 0;
     }
     free(leaf); free(t.n);
     *pbeginc = endc;

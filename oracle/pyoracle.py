@@ -99,7 +99,11 @@ class PlaneImage:
 def read_fbpd(path: str) -> PlaneImage:
     """Reads a plane dump written by oracle/ref_driver.cpp."""
     with open(path, "rb") as f:
-        buf = f.read()
+        return parse_fbpd(f.read())
+
+
+def parse_fbpd(buf: bytes) -> PlaneImage:
+    buf = bytes(buf)
     end = buf.index(b"END\n") + 4
     lines = buf[:end].decode().strip().split("\n")
     assert lines[0] == "FBPD1"
@@ -160,11 +164,6 @@ class OracleImage:
             a = np.ascontiguousarray(pix[:, :, i].astype(np.int16))
             lib().fo_plane_set(img.h, i, a.ctypes.data, a.size)
         return img
-
-    @staticmethod
-    def from_plane_image(pi: PlaneImage) -> "OracleImage":
-        img = OracleImage(lib().fo_image_new(pi.w, pi.h, pi.maxval, 0, pi.colormodel))
-        raise NotImplementedError
 
     def clone(self) -> "OracleImage":
         return OracleImage(lib().fo_image_clone(self.h))

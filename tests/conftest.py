@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import pyoracle as po
+    po.build()
+    return po
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    """One fuif_b200 context on cuda:0 for the whole GPU session."""
+    from fuif_b200 import api
+    c = api.Context(0)
+    yield c
+    c.close()
