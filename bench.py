@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- decode Mpixels/s of the FUIF hot path on B200 (BASELINE.json's metric).
+
+A step = one full decode of the workload: fuif_decode (MANIAC range decoder + context model on the GPU) followed by
+Image::undo_transforms (inverse Squeeze / DCT / colour transforms on the GPU), bit-exact with the reference.
+
+  value  : whole-job Mpx/s with the compressed file already resident in HBM and the pixels left in HBM
+  e2e    : the same through the host-buffer C-ABI call fb_decode_to_pixels (pinned host bytes in, pinned host pixels
+           out, H2D / D2H inside the timed region)
+  roofline      : the inverse transform chain (undo_transforms) timed with CUDA events inside every timed step:
+                  algorithmic bytes (read every coefficient once + write every sample once = 4*W*H*C) / time
+  cpu_baseline  : the reference's own CPU decoder (oracle/_ref/ref_driver, else the C port) on this box's host cores
+  --impl reference : times the reference CPU decoder on the same workload and prints the same JSON line.
+
+Launch: python bench.py --gpus N --steps K --warmup W     (N>1 via torch.distributed.run, one rank per GPU)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--no-index", action="store_true", help="decode without the group-offset sidecar (one stream per image)")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU decoder on the same workload, one process per image."""
+    from fuif_b200 import workloads as wl
+    if rank != 0:
+        return
+    n_img = max(1, args.gpus)
+    imgs = [wl.prepare_image(args.workload, seed_offset=i, want_index=False) for i in range(n_img)]
+    mpix = sum(im["w"] * im["h"] for im in imgs) / 1e6
+    use_ref = wl.have_ref_driver()
+
+    def one_step():
+        t0 = time.perf_counter()
+        if use_ref:
+            procs = [subprocess.Popen([wl.REF_DRIVER, "time", im["fuif_path"], "1"], stdout=subprocess.PIPE, text=True) for im in imgs]
+            outs = [p.communicate()[0] for p in procs]
+            inner = max(json.loads(o.strip().splitlines()[-1])["total_s"] for o in outs)
+        else:
+            from oracle import pyoracle as po
+            res = [None] * n_img
+
+            def work(i):
+                t = time.perf_counter()
+                o = po.OracleImage.decode(imgs[i]["fuif"])
+                o.undo_transforms(0)
+                res[i] = time.perf_counter() - t
+            ths = [threading.Thread(target=work, args=(i,)) for i in range(n_img)]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+            inner = max(res)
+        return inner, time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        one_step()
+    times = [one_step()[0] for _ in range(args.steps)]
+    ms = 1e3 * sum(times) / len(times)
+    value = mpix / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "decode Mpixels/s (bit-exact)", "value": value, "unit": "Mpx/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
+        "data": "synthetic", "config": {"workload": f"{args.workload}: {wl.WORKLOADS[args.workload][7]}", "images": n_img},
+        "cpu_baseline": {"value": value, "unit": "Mpx/s", "cores": n_img, "kind": "reference" if use_ref else "port",
+                         "sample": f"{n_img} full decode(s) of the workload image per step, one single-threaded process per image"},
+        "e2e": {"value": value, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank, local_rank, world = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from fuif_b200 import api
+    from fuif_b200 import workloads as wl
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: fuif_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- workload: one image per GPU (weak scaling, no data-path collective: files are independent units)
+    spec = wl.WORKLOADS[args.workload]
+    n_per_gpu = spec[5]
+    imgs = [wl.prepare_image(args.workload, seed_offset=rank * n_per_gpu + i, want_index=not args.no_index) for i in range(n_per_gpu)]
+    w, h, c, maxval = spec[0], spec[1], spec[2], spec[3]
+    mpix_rank = n_per_gpu * w * h / 1e6
+    bps = 2 if maxval > 255 else 1
+
+    stream = torch.cuda.current_stream()
+    ctx = api.Context(local_rank, stream.cuda_stream)
+
+    # compressed files resident in HBM (value path) and in pinned host memory (e2e path)
+    dev_bytes = [torch.frombuffer(bytearray(im["fuif"]), dtype=torch.uint8).cuda() for im in imgs]
+    pin_bytes = [torch.frombuffer(bytearray(im["fuif"]), dtype=torch.uint8).pin_memory() for im in imgs]
+    pin_out = [torch.empty((h, w, c), dtype=(torch.int16 if bps == 2 else torch.uint8)).pin_memory() for _ in imgs]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def step_value(ev=None):
+        """decode + undo_transforms, inputs and outputs in HBM. ev: optional (start, mid, end) CUDA events."""
+        out = []
+        if ev:
+            ev[0].record(stream)
+        for im, db in zip(imgs, dev_bytes):
+            out.append(api.fuif_decode((db.data_ptr(), db.numel()), ctx=ctx, group_index=im["index"]))
+        if ev:
+            ev[1].record(stream)
+        for o in out:
+            o.undo_transforms(0)
+        if ev:
+            ev[2].record(stream)
+        return out
+
+    def step_e2e():
+        for im, pb, po_ in zip(imgs, pin_bytes, pin_out):
+            arr = np.frombuffer(memoryview(pb.numpy()), dtype=np.uint8)
+            api.decode_to_pixels(arr, ctx=ctx, group_index=im["index"], out=po_.numpy())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- bit-exactness of what is being timed (rank 0, against the input image: the workload is lossless for cfg1/2/4)
+    res = step_value()
+    torch.cuda.synchronize()
+    lossless = args.workload in ("cfg1", "cfg2", "cfg4", "mid")
+    exact = None
+    if lossless:
+        from fuif_b200.synth import synth_image
+        exact = bool(np.array_equal(res[0].pixels(), synth_image(w, h, c, maxval, spec[4] + rank * n_per_gpu)))
+        if not exact:
+            raise SystemExit("decoded pixels differ from the input image: refusing to report a number")
+    del res
+
+    for _ in range(max(0, args.warmup - 1)):
+        r = step_value(); del r
+    torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream, L2 flushed between steps
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    launches0 = ctx.launches
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()
+        r = step_value(evs[k])
+        del r
+    torch.cuda.synchronize()
+    launches = ctx.launches - launches0
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clk = clocks.stop()
+    dec_ms = [e[0].elapsed_time(e[1]) for e in evs]
+    chain_ms = [e[1].elapsed_time(e[2]) for e in evs]
+    step_ms = [e[0].elapsed_time(e[2]) for e in evs]
+    total_ms = sum(step_ms)
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = world * mpix_rank / (ms_per_step / 1e3)
+
+    # ---- e2e: host buffers through the C-ABI convenience call
+    for _ in range(min(args.warmup, 1)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * mpix_rank / (float(t.item()) / args.steps)
+    if lossless:
+        from fuif_b200.synth import synth_image
+        got = pin_out[0].numpy()
+        if bps == 2:
+            got = got.view(">u2")
+        assert np.array_equal(got.astype(np.int32), synth_image(w, h, c, maxval, spec[4] + rank * n_per_gpu)), "e2e pixels differ"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the transform chain, from the events inside the timed steps
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak = 6650.0; peak_src = "fallback 6.65 TB/s (B200_PROFILING.md)"
+    alg_bytes = 4.0 * w * h * c * n_per_gpu
+    chain_mean_ms = sum(chain_ms) / len(chain_ms)
+    achieved = alg_bytes / (chain_mean_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "inverse transform chain (Image::undo_transforms: unsqueeze levels + colour inverse + clamp)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes": alg_bytes, "ms": chain_mean_ms, "peak_source": peak_src}
+
+    # ---- reference CPU decoder on this box's host cores (1 core: it is single-threaded), one bounded sample
+    cpu = None
+    if world == 1 and not args.skip_cpu_baseline:
+        if wl.have_ref_driver():
+            tt = wl.reference_decode_seconds(imgs[0]["fuif_path"])
+            cpu = {"value": w * h / 1e6 / tt["total_s"], "unit": "Mpx/s", "cores": 1, "kind": "reference",
+                   "sample": "one full decode (fuif_decode_file + undo_transforms) of the first workload image by oracle/_ref/ref_driver",
+                   "entropy_s": tt["entropy_s"], "chain_s": tt["chain_s"]}
+        else:
+            from oracle import pyoracle as po
+            t0 = time.perf_counter()
+            o = po.OracleImage.decode(imgs[0]["fuif"]); t1 = time.perf_counter()
+            o.undo_transforms(0); t2 = time.perf_counter()
+            cpu = {"value": w * h / 1e6 / (t2 - t0), "unit": "Mpx/s", "cores": 1, "kind": "port",
+                   "sample": "one full decode of the first workload image by oracle/libfuif_oracle.so", "entropy_s": t1 - t0, "chain_s": t2 - t1}
+
+    line = {
+        "metric": "decode Mpixels/s (bit-exact)", "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {spec[7]}", "images_per_gpu": n_per_gpu, "width": w, "height": h, "channels": c,
+                   "group_index_sidecar": not args.no_index, "l2": "256 MiB buffer written between timed steps", "parallelism": f"one image per GPU x{world}",
+                   "bit_exact_checked": exact},
+        "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": int(sum(len(im["fuif"]) for im in imgs)),
+                "d2h_bytes_per_step": int(n_per_gpu * w * h * c * bps)},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "stages": {"entropy_ms": sum(dec_ms) / len(dec_ms), "transform_chain_ms": chain_mean_ms, "wall_s_timed_region": t_wall,
+                   "transform_chain_mpx_s": mpix_rank / (chain_mean_ms / 1e3)},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

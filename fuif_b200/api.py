@@ -76,9 +76,9 @@ def load_library():
     L.fb_ctx_synchronize.argtypes = [vp]
     L.fb_ctx_launch_count.argtypes = [vp]
     L.fb_ctx_launch_count.restype = C.c_longlong
-    L.fb_decode.argtypes = [vp, vp, C.c_size_t, C.POINTER(DecodeOptions), i64p, C.c_int, C.POINTER(vp)]
+    L.fb_decode.argtypes = [vp, vp, C.c_size_t, C.POINTER(DecodeOptions), i64p, i32p, C.c_int, C.POINTER(vp)]
     L.fb_decode_batch.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(DecodeOptions), C.POINTER(i64p),
-                                  C.POINTER(C.c_int), C.POINTER(vp)]
+                                  C.POINTER(i32p), C.POINTER(C.c_int), C.POINTER(vp)]
     L.fb_image_group_index.argtypes = [vp, i64p, i32p, C.c_int]
     L.fb_image_create.argtypes = [vp, C.POINTER(ImageInfo), C.POINTER(PlaneDesc), C.POINTER(vp), i32p, i32p, i32p, C.POINTER(vp)]
     L.fb_image_destroy.argtypes = [vp]
@@ -93,7 +93,7 @@ def load_library():
     L.fb_image_undo_transforms.argtypes = [vp, C.c_int]
     L.fb_image_do_transform.argtypes = [vp, C.c_int32, i32p, C.c_int, C.POINTER(C.c_int)]
     L.fb_image_recompute_minmax.argtypes = [vp]
-    L.fb_decode_to_pixels.argtypes = [vp, vp, C.c_size_t, C.POINTER(DecodeOptions), i64p, C.c_int, C.c_int, vp, C.c_size_t]
+    L.fb_decode_to_pixels.argtypes = [vp, vp, C.c_size_t, C.POINTER(DecodeOptions), i64p, i32p, C.c_int, C.c_int, vp, C.c_size_t]
     L.fb_peek_header.argtypes = [vp, C.c_size_t, C.POINTER(ImageInfo)]
     _lib = L
     return L
@@ -204,7 +204,8 @@ class Image:
 
     def close(self):
         if self.__dict__.get("_handle"):
-            self.ctx.lib.fb_image_destroy(self._handle)
+            if self.ctx.h:      # a closed context has already released the device
+                self.ctx.lib.fb_image_destroy(self._handle)
             self._handle = None
 
     # ---- construction ----------------------------------------------------------------------------------------
@@ -317,20 +318,29 @@ class Image:
 
 
 def _index_args(group_index):
+    """group_index: None, a list of byte offsets, or (offsets, first_channels) as Image.group_index() returns it."""
     if group_index is None or len(group_index) == 0:
-        return None, 0, None
+        return None, None, 0
+    first = None
+    if isinstance(group_index, tuple):
+        group_index, first = group_index
     arr = (C.c_int64 * len(group_index))(*group_index)
-    return arr, len(group_index), arr
+    farr = (C.c_int32 * len(first))(*first) if first is not None else None
+    return arr, farr, len(group_index)
 
 
 def fuif_decode(data: bytes, options: fuif_options = default_fuif_options, ctx: Context | None = None, group_index=None) -> Image:
     """fuif_decode (reference encoding/encoding.cpp:599-720): .fuif bytes -> Image holding the transformed planes."""
     ctx = ctx or default_context()
-    buf = np.frombuffer(data, dtype=np.uint8)
-    arr, n, _keep = _index_args(group_index)
+    arr, farr, n = _index_args(group_index)
     h = C.c_void_p()
     opts = options._c()
-    ctx.check(ctx.lib.fb_decode(ctx.h, buf.ctypes.data, buf.size, C.byref(opts), arr, n, C.byref(h)), "fb_decode")
+    if isinstance(data, tuple):         # (device pointer, nbytes): the file already lives in HBM
+        ptr, size = data
+    else:
+        buf = np.frombuffer(data, dtype=np.uint8)
+        ptr, size = buf.ctypes.data, buf.size
+    ctx.check(ctx.lib.fb_decode(ctx.h, ptr, size, C.byref(opts), arr, farr, n, C.byref(h)), "fb_decode")
     return Image(ctx, h)
 
 
@@ -360,7 +370,7 @@ def fuif_decode_batch(datas, options: fuif_options = default_fuif_options, ctx: 
                 keep.append(a)
                 gi_ptrs[i] = C.cast(a, C.POINTER(C.c_int64))
                 gi_n[i] = len(gi)
-    ctx.check(ctx.lib.fb_decode_batch(ctx.h, n, ptrs, sizes, C.byref(opts), gi_ptrs, gi_n, out), "fb_decode_batch")
+    ctx.check(ctx.lib.fb_decode_batch(ctx.h, n, ptrs, sizes, C.byref(opts), gi_ptrs, None, gi_n, out), "fb_decode_batch")
     return [Image(ctx, C.c_void_p(out[i])) for i in range(n)]
 
 
@@ -376,7 +386,7 @@ def decode_to_pixels(data: bytes, options: fuif_options = default_fuif_options, 
     bps = 2 if inf.maxval > 255 else 1
     if out is None:
         out = np.empty((inf.h, inf.w, inf.nb_channels), dtype=(">u2" if bps == 2 else np.uint8))
-    arr, n, _keep = _index_args(group_index)
+    arr, farr, n = _index_args(group_index)
     opts = options._c()
-    ctx.check(L.fb_decode_to_pixels(ctx.h, buf.ctypes.data, buf.size, C.byref(opts), arr, n, bps, out.ctypes.data, out.nbytes), "fb_decode_to_pixels")
+    ctx.check(L.fb_decode_to_pixels(ctx.h, buf.ctypes.data, buf.size, C.byref(opts), arr, farr, n, bps, out.ctypes.data, out.nbytes), "fb_decode_to_pixels")
     return out

@@ -83,7 +83,8 @@ int fb_launch_interleave(fb_ctx *ctx, const int16_t *const *planes_dev, int nch,
 
 // ---- MANIAC decode (fb_maniac.cu) ---------------------------------------------------------------------------
 struct FbManiacJob {
-    const uint8_t *bytes_host;
+    const uint8_t *bytes_host;    // whole file on the host, or (bytes_dev != nullptr) just its first header_len bytes
+    const uint8_t *bytes_dev;     // non-null: the file already lives in HBM
     size_t nbytes;
     fb_image *img;            // channel list after meta_apply; planes get allocated + filled, ranges/q filled in
     size_t body_pos;          // byte offset of the first channel group
@@ -91,6 +92,7 @@ struct FbManiacJob {
     int max_properties;
     int cutoff, alpha;
     const int64_t *group_index;   // optional
+    const int32_t *group_first;   // optional (required with bytes_dev)
     int n_groups;
 };
 int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs);

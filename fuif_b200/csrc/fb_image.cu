@@ -739,9 +739,22 @@ extern "C" int fb_peek_header(const uint8_t *bytes, size_t nbytes, fb_image_info
 
 // Parses header + transform list, builds the (empty) channel list via meta_apply and hands the rest to the
 // GPU MANIAC decoder.
-static int parse_container(fb_ctx *ctx, const uint8_t *bytes, size_t nbytes, const fb_decode_options *opts, const int64_t *gidx, int ngroups,
-                           fb_image **out, FbManiacJob &job) {
-    ByteReader io{bytes, nbytes};
+static int parse_container(fb_ctx *ctx, const uint8_t *bytes_in, size_t nbytes, const fb_decode_options *opts, const int64_t *gidx,
+                           const int32_t *gfirst, int ngroups, fb_image **out, FbManiacJob &job, std::vector<uint8_t> &header_copy) {
+    // host or device bytes?  For a device buffer only the header (first 4 KiB) is read back.
+    const uint8_t *bytes = bytes_in;
+    const uint8_t *bytes_dev = nullptr;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, bytes_in) == cudaSuccess && attr.type == cudaMemoryTypeDevice) {
+        header_copy.resize(std::min<size_t>(nbytes, 4096));
+        FB_CUDA(ctx, cudaMemcpyAsync(header_copy.data(), bytes_in, header_copy.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        bytes = header_copy.data();
+        bytes_dev = bytes_in;
+    } else {
+        cudaGetLastError();
+    }
+    ByteReader io{bytes, bytes_dev ? header_copy.size() : nbytes};
     Header hd;
     int rc = parse_header(io, hd);
     if (rc) { ctx->err = "not a FUIF file or corrupt header"; return rc; }
@@ -758,7 +771,8 @@ static int parse_container(fb_ctx *ctx, const uint8_t *bytes, size_t nbytes, con
         img->ch[i].d.w = hd.w; img->ch[i].d.h = hd.h; img->ch[i].d.maxval = img->info.maxval; img->ch[i].d.component = i;
     }
     *out = img;
-    job.bytes_host = bytes; job.nbytes = nbytes; job.img = img; job.max_properties = hd.max_properties;
+    job.bytes_host = bytes; job.bytes_dev = bytes_dev; job.nbytes = nbytes; job.img = img; job.max_properties = hd.max_properties;
+    job.group_first = gfirst;
     job.cutoff = opts ? opts->maniac_cutoff : 6; job.alpha = opts ? opts->maniac_alpha : 0x0d000000;
     job.group_index = gidx; job.n_groups = ngroups; job.bytes_to_load = 0; job.body_pos = io.pos;
     if (hd.nb_channels < 1) return FB_OK;
@@ -771,7 +785,7 @@ static int parse_container(fb_ctx *ctx, const uint8_t *bytes, size_t nbytes, con
     const int nb_transforms = read_varint(io);
     for (int i = 0; i < nb_transforms; i++) {
         const int idp = read_varint(io);
-        if (idp < 0) { ctx->err = "truncated transform list"; return FB_ERR_INVALID; }
+        if (idp < 0 || io.eof) { ctx->err = "truncated transform list (or header larger than 4 KiB in a device buffer)"; return FB_ERR_INVALID; }
         FbXform t;
         t.id = idp & 0xf;
         if (transform_has_parameters(t.id)) {
@@ -791,14 +805,16 @@ static int parse_container(fb_ctx *ctx, const uint8_t *bytes, size_t nbytes, con
 }
 
 extern "C" int fb_decode_batch(fb_ctx *ctx, int n_images, const uint8_t *const *bytes, const size_t *nbytes, const fb_decode_options *opts,
-                               const int64_t *const *group_index, const int *n_groups, fb_image **out) {
+                               const int64_t *const *group_index, const int32_t *const *group_first, const int *n_groups, fb_image **out) {
     if (!ctx || n_images < 0 || !bytes || !nbytes || !out) return FB_ERR_INVALID;
     cudaSetDevice(ctx->device);
     std::vector<FbManiacJob> jobs(n_images);
+    std::vector<std::vector<uint8_t>> headers(n_images);
     for (int i = 0; i < n_images; i++) out[i] = nullptr;
     int rc = FB_OK;
     for (int i = 0; i < n_images && !rc; i++)
-        rc = parse_container(ctx, bytes[i], nbytes[i], opts, group_index ? group_index[i] : nullptr, n_groups ? n_groups[i] : 0, &out[i], jobs[i]);
+        rc = parse_container(ctx, bytes[i], nbytes[i], opts, group_index ? group_index[i] : nullptr, group_first ? group_first[i] : nullptr,
+                             n_groups ? n_groups[i] : 0, &out[i], jobs[i], headers[i]);
     if (!rc) rc = fb_maniac_decode(ctx, jobs);
     if (rc) {
         for (int i = 0; i < n_images; i++) { fb_image_destroy(out[i]); out[i] = nullptr; }
@@ -807,16 +823,17 @@ extern "C" int fb_decode_batch(fb_ctx *ctx, int n_images, const uint8_t *const *
     return FB_OK;
 }
 
-extern "C" int fb_decode(fb_ctx *ctx, const uint8_t *bytes, size_t nbytes, const fb_decode_options *opts, const int64_t *group_index, int n_groups,
-                         fb_image **out) {
+extern "C" int fb_decode(fb_ctx *ctx, const uint8_t *bytes, size_t nbytes, const fb_decode_options *opts, const int64_t *group_index,
+                         const int32_t *group_first, int n_groups, fb_image **out) {
     const int64_t *gi[1] = {group_index};
-    return fb_decode_batch(ctx, 1, &bytes, &nbytes, opts, group_index ? gi : nullptr, &n_groups, out);
+    const int32_t *gf[1] = {group_first};
+    return fb_decode_batch(ctx, 1, &bytes, &nbytes, opts, group_index ? gi : nullptr, group_first ? gf : nullptr, &n_groups, out);
 }
 
 extern "C" int fb_decode_to_pixels(fb_ctx *ctx, const uint8_t *bytes, size_t nbytes, const fb_decode_options *opts, const int64_t *group_index,
-                                   int n_groups, int bps, void *dst, size_t dst_bytes) {
+                                   const int32_t *group_first, int n_groups, int bps, void *dst, size_t dst_bytes) {
     fb_image *img = nullptr;
-    int rc = fb_decode(ctx, bytes, nbytes, opts, group_index, n_groups, &img);
+    int rc = fb_decode(ctx, bytes, nbytes, opts, group_index, group_first, n_groups, &img);
     if (rc) return rc;
     rc = fb_image_undo_transforms(img, 0);
     if (!rc) {

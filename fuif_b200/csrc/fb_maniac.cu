@@ -680,7 +680,7 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
     int maxw = 8;
     for (int b = 0; b < nimg; b++) {
         if (jobs[b].cutoff != cutoff || jobs[b].alpha != alpha) { ctx->err = "batch with mixed maniac options"; return FB_ERR_INVALID; }
-        total_bytes += (jobs[b].nbytes + 255) & ~(size_t)255;
+        if (!jobs[b].bytes_dev) total_bytes += (jobs[b].nbytes + 255) & ~(size_t)255;
         total_ch += jobs[b].img->ch.size();
     }
     uint8_t *bytes_dev = nullptr;
@@ -694,8 +694,11 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
     for (int b = 0; b < nimg; b++) {
         FbManiacJob &job = jobs[b];
         fb_image *img = job.img;
-        FB_CUDA(ctx, cudaMemcpyAsync(bytes_dev + boff, job.bytes_host, job.nbytes, cudaMemcpyHostToDevice, ctx->stream));
-        himg[b].bytes = bytes_dev + boff;
+        if (job.bytes_dev) himg[b].bytes = job.bytes_dev;
+        else {
+            FB_CUDA(ctx, cudaMemcpyAsync(bytes_dev + boff, job.bytes_host, job.nbytes, cudaMemcpyHostToDevice, ctx->stream));
+            himg[b].bytes = bytes_dev + boff;
+        }
         himg[b].nbytes = job.nbytes;
         himg[b].bytes_to_load = job.bytes_to_load;
         himg[b].ch = ch_dev + coff;
@@ -730,18 +733,24 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
                     size_t pos = (size_t)job.group_index[g];
                     if (i >= himg[b].nch || job.group_index[g] < (int64_t)job.body_pos || pos >= job.nbytes) { indexed = false; break; }
                     if (job.bytes_to_load && pos >= job.bytes_to_load) break;
-                    int fb = host_varint(job.bytes_host, job.nbytes, pos);
-                    if (fb < 0) { indexed = false; break; }
+                    if (job.group_first) {
+                        i = job.group_first[g];
+                        if (i < 0 || i >= himg[b].nch || (!mine.empty() && i <= mine.back().first_channel)) { indexed = false; break; }
+                    } else {
+                        if (job.bytes_dev) { indexed = false; break; }      // cannot read group headers of a device buffer on the host
+                        int fb = host_varint(job.bytes_host, job.nbytes, pos);
+                        if (fb < 0) { indexed = false; break; }
+                    }
                     if (!mine.empty()) mine.back().end_channel = i;
                     mine.push_back(DStream{b, i, himg[b].nch, 1, (unsigned long long)job.group_index[g]});
-                    i += (fb >> 4) + 1;
+                    if (!job.group_first) { size_t p2 = (size_t)job.group_index[g]; int fb = host_varint(job.bytes_host, job.nbytes, p2); i += (fb >> 4) + 1; }
                 }
                 if (indexed && !mine.empty()) streams.insert(streams.end(), mine.begin(), mine.end());
                 else indexed = false;
             }
             if (!indexed) streams.push_back(DStream{b, 0, himg[b].nch, -1, (unsigned long long)job.body_pos});
         }
-        boff += (job.nbytes + 255) & ~(size_t)255;
+        if (!job.bytes_dev) boff += (job.nbytes + 255) & ~(size_t)255;
         coff += img->ch.size();
     }
     FB_CUDA(ctx, cudaMemcpyAsync(img_dev, himg.data(), nimg * sizeof(DImage), cudaMemcpyHostToDevice, ctx->stream));

@@ -91,17 +91,19 @@ FB_API long long fb_ctx_launch_count(fb_ctx *ctx);
  * parses the container on the host, runs the MANIAC range decoder + context model on the GPU
  * (fuif_decode_channel, encoding.cpp:259-429) and leaves the TRANSFORMED planes in HBM together with the
  * transform stack, exactly the state the reference's Image is in after fuif_decode().
- * bytes: the .fuif file in HOST memory.  group_index (may be NULL): n_groups byte offsets of the channel
- * groups' headers (fb_image_group_index() of an earlier decode, or written by an encoder) -- with it the
- * groups decode concurrently, without it they decode back to back as the format dictates.
+ * bytes: the .fuif file, in HOST memory or already in DEVICE memory (detected; a device buffer is not copied,
+ * only its first 4 KiB are read back for the header).  group_index (may be NULL): n_groups byte offsets of the
+ * channel groups' headers (fb_image_group_index() of an earlier decode, or written by an encoder) -- with it
+ * the groups decode concurrently, without it they decode back to back as the format dictates.
+ * group_first (may be NULL for host bytes): first channel of each group, as fb_image_group_index() returns it.
  * End-of-stream follows FileIO (reference fileio.h:33-81). */
 FB_API int fb_decode(fb_ctx *ctx, const uint8_t *bytes, size_t nbytes, const fb_decode_options *opts,
-              const int64_t *group_index, int n_groups, fb_image **out);
+              const int64_t *group_index, const int32_t *group_first, int n_groups, fb_image **out);
 
 /* Same for a batch: every (image, group) is an independent stream of one kernel launch. */
 FB_API int fb_decode_batch(fb_ctx *ctx, int n_images, const uint8_t *const *bytes, const size_t *nbytes,
-                    const fb_decode_options *opts, const int64_t *const *group_index, const int *n_groups,
-                    fb_image **out);
+                    const fb_decode_options *opts, const int64_t *const *group_index,
+                    const int32_t *const *group_first, const int *n_groups, fb_image **out);
 
 /* Byte offsets of the channel-group headers found while decoding (one per group, in stream order) and the
  * first channel of each group.  Returns the number of groups; copies at most cap entries. */
@@ -149,7 +151,8 @@ FB_API int fb_image_recompute_minmax(fb_image *img);
  * fuif.cpp:206-239).  dst must hold w*h*nb_channels samples of bytes_per_sample bytes each; query the sizes
  * with fb_peek_header() first. */
 FB_API int fb_decode_to_pixels(fb_ctx *ctx, const uint8_t *bytes, size_t nbytes, const fb_decode_options *opts,
-                        const int64_t *group_index, int n_groups, int bytes_per_sample, void *dst, size_t dst_bytes);
+                        const int64_t *group_index, const int32_t *group_first, int n_groups, int bytes_per_sample,
+                        void *dst, size_t dst_bytes);
 
 /* Header-only parse (reference encoding.cpp:599-637, "identify"): fills w, h, maxval, nb_channels. */
 FB_API int fb_peek_header(const uint8_t *bytes, size_t nbytes, fb_image_info *info);

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from tests.cases import CASES
-from tests.util import gpu_plane_image, load_golden, ordered, upload_plane_image
+from tests.util import default_squeeze_parameters, gpu_plane_image, load_golden, ordered, upload_plane_image
 from fuif_b200.synth import read_pnm, synth_image
 
 pytestmark = pytest.mark.gpu
@@ -51,6 +51,8 @@ def test_indexed_decode_matches_sequential(oracle, ctx, case):
     assert list(zip(offs, first)) == [(int(a), int(b)) for a, b in ooffs]
     par = api.fuif_decode(blob["fuif"], ctx=ctx, group_index=offs)
     po.compare_plane_images(gpu_plane_image(po, par), gpu_plane_image(po, seq), case[0] + " indexed")
+    par2 = api.fuif_decode(blob["fuif"], ctx=ctx, group_index=(offs, first))
+    po.compare_plane_images(gpu_plane_image(po, par2), gpu_plane_image(po, seq), case[0] + " indexed+first")
     po.compare_plane_images(gpu_plane_image(po, par), po.parse_fbpd(blob["s0"]), case[0] + " indexed vs golden")
 
 
@@ -129,7 +131,8 @@ def test_transform_chain_vs_oracle_random(oracle, ctx, shape):
     gi = api.Image.from_pixels(pix, maxval, ctx)
     if c >= 3:
         assert oi.do_transform(1) and gi.do_transform(api.Transform(1))
-    assert oi.do_transform(7) and gi.do_transform(api.Transform(7))
+    sq = default_squeeze_parameters(w, h, c)
+    assert oi.do_transform(7, sq) and gi.do_transform(api.Transform(7, sq))
     po.compare_plane_images(gpu_plane_image(po, gi), oi.to_plane_image(), f"fwd {shape}")
     gi.undo_transforms(0)
     oi.undo_transforms(0)
@@ -146,8 +149,9 @@ def test_dct_chain_vs_oracle_random(oracle, ctx, shape):
     pix = synth_image(w, h, c, maxval, seed=3 * w + h)
     oi = po.OracleImage.from_pixels(pix, maxval)
     gi = api.Image.from_pixels(pix, maxval, ctx)
-    q = [8] + [8, 12, 12] * 64
-    for tid, params in ((0, []), (4, [0, 2]), (5, q[:192]), (7, [])):
+    q = [8, 12, 12] * 64
+    sq = default_squeeze_parameters((w + 7) // 8, (h + 7) // 8, 3)
+    for tid, params in ((0, []), (4, [0, 2]), (5, q), (7, sq)):
         assert oi.do_transform(tid, params) and gi.do_transform(api.Transform(tid, params))
         po.compare_plane_images(gpu_plane_image(po, gi), oi.to_plane_image(), f"fwd {tid} {shape}")
     for keep in (3, 2, 1, 0):
@@ -168,7 +172,8 @@ def test_extreme_values_wrap_like_int16(oracle, ctx):
     oi = po.OracleImage.from_pixels(pix, 16383)
     gi = api.Image.from_pixels(pix, 16383, ctx)
     assert oi.do_transform(1) and gi.do_transform(api.Transform(1))
-    assert oi.do_transform(7) and gi.do_transform(api.Transform(7))
+    sq = default_squeeze_parameters(w, h, 3)
+    assert oi.do_transform(7, sq) and gi.do_transform(api.Transform(7, sq))
     pi = oi.to_plane_image()
     po.compare_plane_images(gpu_plane_image(po, gi), pi, "extreme fwd")
     # now corrupt the residuals with full-range noise and undo: garbage in, identical garbage out

@@ -32,3 +32,23 @@ def upload_plane_image(api, pi, ctx):
     planes = [api.Channel(p.w, p.h, p.minval, p.maxval, p.zero, p.q, p.hshift, p.vshift, p.hcshift, p.vcshift, p.component, p.data) for p in pi.planes]
     trs = [api.Transform(t, ps) for t, ps in pi.transforms]
     return api.Image.from_planes(pi.w, pi.h, pi.minval, pi.maxval, pi.nb_channels, pi.real_nb_channels, pi.nb_meta_channels, pi.colormodel, planes, trs, ctx)
+
+
+def default_squeeze_parameters(w, h, nb_channels, nb_meta=0, chroma_same_size=True):
+    """The schedule meta_squeeze fills in at decode time (reference transform/squeeze.h:266-321).  An Image that was
+    squeezed with empty parameters can only be un-squeezed in memory when the schedule is passed explicitly: the
+    reference derives defaults from the *current* channel sizes (squeeze.h:364-365), which have changed by then."""
+    p = []
+    if nb_channels > 2 and chroma_same_size:
+        p += [3, nb_meta + 1, nb_meta + 2, 2, nb_meta + 1, nb_meta + 2]
+    if not (w > h) and h > 8:
+        p += [0, nb_meta, nb_meta + nb_channels - 1]
+        h = (h + 1) // 2
+    while w > 8 or h > 8:
+        if w > 8:
+            p += [1, nb_meta, nb_meta + nb_channels - 1]
+            w = (w + 1) // 2
+        if h > 8:
+            p += [0, nb_meta, nb_meta + nb_channels - 1]
+            h = (h + 1) // 2
+    return p
