@@ -70,19 +70,43 @@ struct Params {
     const uint16_t *meta_table; // [4096][2] tree-coder table (cut 2, alpha 0xFFFFFFFF/19)
     WarpScratch *scratch;
     int maxw;
+    int node_cap;           // tree nodes that fit the block's shared-memory node cache
 };
 
 __device__ __forceinline__ int s16(int x) { return (int)(short)x; }
 __device__ __forceinline__ int ilog2u(unsigned l) { return l == 0 ? 0 : 31 - __clz(l); }      // maniac/util.h:33-36
 
+__device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // ---- byte reader with FileIO end-of-stream rules (fileio.h:33-81) ------------------------------------------
+// `pos` counts consumed bytes (what ftell() reports); `win` caches up to four upcoming bytes, MSB first.
 struct Reader {
     const uint8_t *p;
     unsigned long long n, pos, btl;
+    unsigned win;
+    int avail;
     bool eof;
+    __device__ __forceinline__ void seek(unsigned long long to) { pos = to; avail = 0; win = 0; }
+    __device__ __forceinline__ void refill() {
+        const unsigned long long addr = (unsigned long long)(p + pos);
+        const unsigned w = __ldg((const unsigned *)(addr & ~3ull));
+        const int skip = (int)(addr & 3ull);
+        win = __byte_perm(w, 0, 0x0123) << (8 * skip);
+        avail = 4 - skip;
+    }
     __device__ __forceinline__ int get() {
         if (pos >= n) { eof = true; return -1; }
-        return __ldg(p + pos++);
+        if (avail == 0) refill();
+        const int b = (int)(win >> 24);
+        win <<= 8;
+        avail--;
+        pos++;
+        return b;
     }
     __device__ __forceinline__ bool stop() const { return eof || (btl && pos >= btl); }
     __device__ int varint() {           // read_big_endian_varint, encoding.cpp:45-59
@@ -114,18 +138,21 @@ struct Rac {
         byte_in(); byte_in(); byte_in();
     }
     __device__ __forceinline__ void input() {   // rac.h:70-81
-        if (range <= (1u << 16)) { range <<= 8; byte_in(); }
-        if (range <= (1u << 16)) { range <<= 8; byte_in(); }
+        if (range <= (1u << 16)) {
+            range <<= 8; byte_in();
+            if (range <= (1u << 16)) { range <<= 8; byte_in(); }
+        }
     }
     __device__ __forceinline__ int get(unsigned chance) {       // rac.h:82-95
         int bit;
-        if (ones || low >= range - chance) { low -= range - chance; range = chance; bit = 1; }
-        else { range -= chance; bit = 0; }
+        const unsigned thr = range - chance;
+        if (ones || low >= thr) { low -= thr; range = chance; bit = 1; }
+        else { range = thr; bit = 0; }
         input();
         return bit;
     }
-    __device__ __forceinline__ int read12(int b12) {            // rac.h:42-52, 107 (64-bit product)
-        return get((unsigned)(((unsigned long long)range * (unsigned)b12 + 0x800) >> 12));
+    __device__ __forceinline__ int read12(unsigned b12) {       // rac.h:42-52, 107 (64-bit product)
+        return get((unsigned)(((unsigned long long)range * b12 + 0x800ull) >> 12));
     }
     __device__ __forceinline__ int read_bit() { return get(range >> 1); }   // rac.h:111
 };
@@ -150,6 +177,7 @@ __device__ __forceinline__ uint16_t initial_chance(int idx, int zero_chance) {  
     }
 }
 
+// Memory-resident variant (tree parse, fast track, uncompressed): chances read-modify-written in place.
 __device__ __forceinline__ int sym_read(Rac &rac, const uint16_t *__restrict__ table, uint16_t *leaf, int idx) {    // compound.h:90-95
     int ch = leaf[idx];
     int bit = rac.read12(ch);
@@ -190,6 +218,67 @@ __device__ int uniform_read(Rac &rac, int mn, int len) {    // UniformSymbolCode
     return mn;
 }
 
+// Register-resident variant for the hot loop: the 31 chances of the selected leaf live in sixteen 32-bit registers
+// (two chances per register) and every access below has a compile-time index once the loops are unrolled, so the
+// chance lookup is off the range coder's dependency chain and the table lookup for the update only feeds the
+// write-back.  Same bit sequence as reader<15> (symbol.h:154-185) / FinalCompoundSymbolBitCoder::read (compound.h:90-95).
+#define SYM_REG(IDX, BIT)                                                                                       \
+    do {                                                                                                        \
+        const unsigned w_ = L[(IDX) >> 1];                                                                      \
+        const unsigned ch_ = ((IDX)&1) ? (w_ >> 16) : (w_ & 0xffffu);                                           \
+        BIT = rac.read12(ch_);                                                                                  \
+        const unsigned nc_ = table[ch_ * 2 + BIT];                                                              \
+        L[(IDX) >> 1] = ((IDX)&1) ? ((w_ & 0xffffu) | (nc_ << 16)) : ((w_ & 0xffff0000u) | nc_);                \
+    } while (0)
+
+__device__ __forceinline__ int read_int_reg(Rac &rac, const uint16_t *__restrict__ table, uint4 *leafp, int mn, int mx) {
+    unsigned L[16];
+    {
+        const uint4 a = leafp[0], b = leafp[1], c = leafp[2], d = leafp[3];
+        L[0] = a.x; L[1] = a.y; L[2] = a.z; L[3] = a.w; L[4] = b.x; L[5] = b.y; L[6] = b.z; L[7] = b.w;
+        L[8] = c.x; L[9] = c.y; L[10] = c.z; L[11] = c.w; L[12] = d.x; L[13] = d.y; L[14] = d.z; L[15] = d.w;
+    }
+    int result;
+    int bit;
+    SYM_REG(SC_ZERO, bit);
+    if (bit) {
+        result = 0;
+    } else {
+        int sign;
+        if (mn < 0) {
+            if (mx > 0) { SYM_REG(SC_SIGN, bit); sign = bit; } else sign = 0;
+        } else sign = 1;
+        const int amax = sign ? mx : -mn;
+        const int emax = ilog2u((unsigned)amax);
+        int e = 0;
+        bool go = true;
+#pragma unroll
+        for (int k = 0; k < MAX_BIT_DEPTH - 1; k++) {
+            if (go && k < emax) {
+                SYM_REG(SC_EXP + k, bit);
+                if (bit) go = false; else e = k + 1;
+            }
+        }
+        int have = 1 << e;
+#pragma unroll
+        for (int pos = MAX_BIT_DEPTH - 2; pos >= 0; pos--) {
+            if (pos < e) {
+                const int minabs1 = have | (1 << pos);
+                if (minabs1 <= amax) {
+                    SYM_REG(SC_MANT + pos, bit);
+                    if (bit) have = minabs1;
+                }
+            }
+        }
+        result = sign ? have : -have;
+    }
+    leafp[0] = make_uint4(L[0], L[1], L[2], L[3]);
+    leafp[1] = make_uint4(L[4], L[5], L[6], L[7]);
+    leafp[2] = make_uint4(L[8], L[9], L[10], L[11]);
+    leafp[3] = make_uint4(L[12], L[13], L[14], L[15]);
+    return result;
+}
+
 // ---- context model (encoding/context_predict.h) ---------------------------------------------------------------------
 __device__ __forceinline__ int slog(int x16) {      // context_predict.h:54-61
     int x = s16(x16);
@@ -214,8 +303,7 @@ __device__ bool check_bit_depth(int minv, int maxv, int predictor) {    // encod
 }
 
 __device__ __forceinline__ void spin_until_ge(const int *flag, int want) {
-    while (*(const volatile int *)flag < want) __nanosleep(200);
-    __threadfence();
+    while (ld_acquire(flag) < want) __nanosleep(100);
 }
 
 // All lanes of the warp call this with identical arguments.
@@ -233,10 +321,11 @@ __device__ int init_properties(int (*pr)[2], DImage &img, int beginc, int endc, 
     for (int j = beginc - 1; j >= 0 && offset < img.max_properties; j--) {
         spin_until_ge(&img.ch[j].hdr_done, 1);
         const DChan &cj = img.ch[j];
-        if (cj.minval == cj.maxval) continue;
+        const int cmin = __ldcg(&cj.minval), cmax = __ldcg(&cj.maxval);
+        if (cmin == cmax) continue;
         if (cj.hshift < 0) continue;
-        int minval = cj.minval; if (minval > 0) minval = 0;
-        int maxval = cj.maxval; if (maxval < 0) maxval = 0;
+        int minval = cmin; if (minval > 0) minval = 0;
+        int maxval = cmax; if (maxval < 0) maxval = 0;
         pr[n][0] = 0; pr[n][1] = fooabs(maxval > -minval ? maxval : minval); n++; offset++;
         pr[n][0] = slog(minval); pr[n][1] = slog(maxval); n++; offset++;
         refchan[nrefchan++] = j;
@@ -314,62 +403,7 @@ __device__ bool read_tree(Rac &rac, const uint16_t *__restrict__ mtable, int (*r
     return true;
 }
 
-// precompute_references, context_predict.h:233-289.  Lanes split x.  refs[x*nref + k] (int16 is enough)
-__device__ void precompute_references(const DChan &ch, int y, DImage &img, const int *refchan, int nrefchan, int16_t *refs, int nref, int lane) {
-    const int oy = y << ch.vshift;
-    for (int r = 0; r < nrefchan; r++) {
-        const DChan &cj = img.ch[refchan[r]];
-        int ry = oy >> cj.vshift;
-        if (ry >= cj.h) ry = cj.h - 1;
-        spin_until_ge(&cj.rows_done, ry + 1);
-        const int16_t *row = cj.data + (size_t)ry * cj.w;
-        const int offset = 2 * r;
-        if (ch.hshift == cj.hshift && ch.w <= cj.w) {
-            for (int x = lane; x < ch.w; x += 32) { int v = __ldcg(row + x); refs[x * nref + offset] = (int16_t)fooabs(v); refs[x * nref + offset + 1] = (int16_t)slog(v); }
-        } else if (ch.hshift < cj.hshift) {
-            // every source sample but the last is repeated `stepsize` times, the last one fills the rest of the row
-            const int stepsize = (1 << cj.hshift) >> ch.hshift;
-            for (int x = lane; x < ch.w; x += 32) {
-                int rx = stepsize > 0 ? x / stepsize : cj.w - 1;
-                if (rx > cj.w - 1) rx = cj.w - 1;
-                int v = __ldcg(row + rx);
-                refs[x * nref + offset] = (int16_t)fooabs(v); refs[x * nref + offset + 1] = (int16_t)slog(v);
-            }
-        } else {
-            for (int x = lane; x < ch.w; x += 32) {
-                int rx = (x << ch.hshift) >> cj.hshift;
-                if (rx >= cj.w) rx = cj.w - 1;
-                int v = __ldcg(row + rx);
-                refs[x * nref + offset] = (int16_t)fooabs(v); refs[x * nref + offset + 1] = (int16_t)slog(v);
-            }
-        }
-    }
-    __syncwarp();
-}
-
-// predict_and_compute_properties, context_predict.h:125-168
-__device__ __forceinline__ int predict_props(int *p, const DChan &ch, int x, int y, int predictor, int offset) {
-    const int16_t *d = ch.data;
-    const int w = ch.w;
-    int left = x ? d[(size_t)y * w + x - 1] : ch.zero;
-    int top = y ? d[(size_t)(y - 1) * w + x] : ch.zero;
-    int topleft = (x && y) ? d[(size_t)(y - 1) * w + x - 1] : left;
-    int topright = (x + 1 < w && y) ? d[(size_t)(y - 1) * w + x + 1] : top;
-    int leftleft = x > 1 ? d[(size_t)y * w + x - 2] : left;
-    int toptop = y > 1 ? d[(size_t)(y - 2) * w + x] : top;
-    p[offset + 0] = fooabs(top);
-    p[offset + 1] = fooabs(left);
-    p[offset + 2] = slog(top);
-    p[offset + 3] = slog(left);
-    p[offset + 4] = y;
-    p[offset + 5] = x;
-    p[offset + 6] = left + top - topleft;
-    p[offset + 7] = topleft + topright - top;
-    p[offset + 8] = slog(left - topleft);
-    p[offset + 9] = slog(topleft - top);
-    p[offset + 10] = slog(top - topright);
-    p[offset + 11] = slog(top - toptop);
-    p[offset + 12] = slog(left - leftleft);
+__device__ __forceinline__ int predict(int predictor, int left, int top, int topleft, int topright, const DChan &ch) {     // context_predict.h:157-166
     switch (predictor) {
     case 0: return ch.zero;
     case 1: return s16((left + top) / 2);
@@ -384,8 +418,7 @@ __device__ __forceinline__ int predict_props(int *p, const DChan &ch, int x, int
 
 __device__ __forceinline__ void publish_rows(DChan &c, int rows, int lane) {
     __syncwarp();
-    __threadfence();
-    if (lane == 0) atomicExch(&c.rows_done, rows);
+    if (lane == 0) st_release(&c.rows_done, rows);
 }
 
 // corrupt_or_truncated, encoding.cpp:209-219.  returns true = "truncated, carry on", false = corruption
@@ -394,8 +427,131 @@ __device__ bool corrupt_or_truncated(Reader &io, DChan &c, int lane) {
     return false;
 }
 
+struct Smem {
+    uint16_t *table;        // [4096][2]
+    uint16_t (*coder)[32];  // 3 x 32 tree-coder chances
+    int16_t *crefs;         // [32][kRefStride] reference properties of the current 32-pixel chunk
+    uint4 *nodes;           // node cache: slot i+1 holds node i, so that sibling pairs are 16-byte aligned
+    int node_cap;           // nodes that fit
+};
+constexpr int kRefStride = 20;      // up to 18 reference properties + padding (one lane per property: 18 + 13 <= 32)
+
+// One row of a channel in the "slow track" (encoding.cpp:388-421), 32 pixels at a time.
+// Lane roles: lane k < nref holds reference property k, lane nref+j holds non-reference property j (0..12).
+__device__ __forceinline__ void decode_row(DImage &img, DChan &ch, int y, int predictor, const int *refchan, int nrefchan, int nref,
+                                           Rac &rac, const Smem &sm, const TNode *gnodes, bool nodes_in_smem, uint16_t *leaves, int lane) {
+    const int w = ch.w;
+    int16_t *row = ch.data + (size_t)y * w;
+    const int16_t *row1 = row - w, *row2 = row - 2 * w;
+    const int role = lane - nref;
+    const int zero = ch.zero, cmin = ch.minval, cmax = ch.maxval;
+    int left = zero, leftleft = zero;
+    // reference rows (precompute_references, context_predict.h:233-289): row pointer, width and x mapping per channel
+    for (int x0 = 0; x0 < w; x0 += 32) {
+        const int x = x0 + lane;
+        const bool in = x < w;
+        // --- chunk prologue (lanes = pixels): neighbours from the rows above, reference properties
+        int T1 = zero, TL = zero, TR = zero, TT = zero;
+        if (in) {
+            if (y) {
+                T1 = row1[x];
+                TL = x ? row1[x - 1] : zero;            // x == 0: topleft = left = zero (context_predict.h:128)
+                TR = (x + 1 < w) ? row1[x + 1] : T1;
+                TT = (y > 1) ? row2[x] : T1;
+            }
+            for (int r = 0; r < nrefchan; r++) {
+                const DChan &cj = img.ch[refchan[r]];
+                int ry = (y << ch.vshift) >> cj.vshift;
+                if (ry >= cj.h) ry = cj.h - 1;
+                int rx;
+                if (ch.hshift == cj.hshift && w <= cj.w) rx = x;
+                else if (ch.hshift < cj.hshift) {
+                    const int stepsize = (1 << cj.hshift) >> ch.hshift;     // all samples but the last are repeated stepsize times
+                    rx = stepsize > 0 ? x / stepsize : cj.w - 1;
+                    if (rx > cj.w - 1) rx = cj.w - 1;
+                } else {
+                    rx = (x << ch.hshift) >> cj.hshift;
+                    if (rx >= cj.w) rx = cj.w - 1;
+                }
+                const int v = __ldcg(cj.data + (size_t)ry * cj.w + rx);
+                sm.crefs[lane * kRefStride + 2 * r] = (int16_t)fooabs(v);
+                sm.crefs[lane * kRefStride + 2 * r + 1] = (int16_t)slog(v);
+            }
+        }
+        __syncwarp();
+        int outv = 0;
+        const int cnt = min(32, w - x0);
+        for (int i = 0; i < cnt; i++) {
+            const int xx = x0 + i;
+            const int top = y ? __shfl_sync(0xffffffffu, T1, i) : zero;
+            const int tl_ = __shfl_sync(0xffffffffu, TL, i);
+            const int topleft = (xx && y) ? tl_ : left;
+            const int topright = y ? __shfl_sync(0xffffffffu, TR, i) : top;
+            const int toptop = y ? __shfl_sync(0xffffffffu, TT, i) : top;
+            // properties (predict_and_compute_properties, context_predict.h:135-154), one per lane
+            int mine = 0;
+            if (role < 0) mine = sm.crefs[i * kRefStride + lane];
+            else {
+                switch (role) {
+                case 0: mine = fooabs(top); break;
+                case 1: mine = fooabs(left); break;
+                case 2: mine = slog(top); break;
+                case 3: mine = slog(left); break;
+                case 4: mine = y; break;
+                case 5: mine = xx; break;
+                case 6: mine = left + top - topleft; break;
+                case 7: mine = topleft + topright - top; break;
+                case 8: mine = slog(left - topleft); break;
+                case 9: mine = slog(topleft - top); break;
+                case 10: mine = slog(top - topright); break;
+                case 11: mine = slog(top - toptop); break;
+                case 12: mine = slog(left - leftleft); break;
+                default: break;
+                }
+            }
+            const int guess = predict(predictor, left, top, topleft, topright, ch);
+            const int mn = cmin - guess, mx = cmax - guess;
+            int diff;
+            if (mn == mx) diff = mn;
+            else {
+                // find_leaf (compound.h:142-153): node values are warp-uniform, the tested property comes from its lane
+                int leaf;
+                if (nodes_in_smem) {
+                    const uint2 *n2 = reinterpret_cast<const uint2 *>(sm.nodes);
+                    uint2 cur = n2[1];                                                 // node 0 lives in slot 1
+                    while ((short)(cur.x & 0xffff) != -1) {
+                        const unsigned child = cur.x >> 16;
+                        const uint4 pair = sm.nodes[(child + 1) >> 1];                 // slots child+1, child+2
+                        const int v = __shfl_sync(0xffffffffu, mine, (int)(short)(cur.x & 0xffff));
+                        cur = (v > (int)cur.y) ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
+                    }
+                    leaf = cur.x >> 16;
+                } else {
+                    const uint2 *n2 = reinterpret_cast<const uint2 *>(gnodes);
+                    uint2 cur = n2[0];
+                    while ((short)(cur.x & 0xffff) != -1) {
+                        const unsigned child = cur.x >> 16;
+                        const uint2 a = n2[child], b = n2[child + 1];
+                        const int v = __shfl_sync(0xffffffffu, mine, (int)(short)(cur.x & 0xffff));
+                        cur = (v > (int)cur.y) ? a : b;
+                    }
+                    leaf = cur.x >> 16;
+                }
+                diff = read_int_reg(rac, sm.table, reinterpret_cast<uint4 *>(leaves + 32 * leaf), mn, mx);
+            }
+            const int val = s16(s16(diff) + guess);
+            if (lane == i) outv = val;
+            leftleft = (xx >= 1) ? left : val;       // next pixel: x>1 ? value(x-2) : left  (context_predict.h:132)
+            left = val;
+            if (xx == 0) leftleft = val;             // pixel 1 sees leftleft = left = value(0)
+        }
+        if (in) row[x] = (int16_t)outv;
+        __syncwarp();
+    }
+}
+
 // fuif_decode_channel, encoding.cpp:259-429.  Returns false on a hard error. `beginc` is advanced to the group's last channel.
-__device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params &P, WarpScratch &ws, int lane, uint16_t (*coder)[32]) {
+__device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params &P, WarpScratch &ws, int lane, const Smem &sm) {
     if (io.stop()) return true;
     const long long header_pos = (long long)io.pos;
     const int firstbyte = io.varint();
@@ -429,16 +585,15 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
         if (io.stop()) { early = true; early_result = corrupt_or_truncated(io, ch, lane); break; }
         if (compress && !check_bit_depth(ch.minval, ch.maxval, predictor)) { early = true; early_result = false; break; }
     }
-    // ranges of this group's channels are final from here on: let dependent streams read them
-    __syncwarp();
-    __threadfence();
     for (int i = beginc; i <= endc; i++) {
         DChan &ch = img.ch[i];
         if (ch.w * ch.h <= 0 || ch.minval == ch.maxval) continue;      // the reference calls setzero() only on channels it decodes
         if (ch.minval > 0) ch.zero = ch.minval; else if (ch.maxval < 0) ch.zero = ch.maxval; else ch.zero = 0;   // setzero, image.h:70-74
     }
-    __threadfence();
-    for (int i = beginc; i <= endc; i++) atomicExch(&img.ch[i].hdr_done, 1);
+    // ranges of this group's channels are final from here on: let dependent streams read them
+    __syncwarp();
+    if (lane == 0) for (int i = beginc; i <= endc; i++) st_release(&img.ch[i].hdr_done, 1);
+    __syncwarp();
     if (early) return early_result;
     if (firstrealc > endc) { beginc = endc; return true; }
 
@@ -446,6 +601,7 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
     int refchan[kMaxProps / 2], nrefchan = 0;
     const int nprops = init_properties(pr, img, beginc, endc, refchan, nrefchan);
     const int nref = nprops - NB_NONREF;
+    if (nprops > 32) { img.status = FB_ERR_UNSUPPORTED; return false; }     // one lane per property (max_properties <= 18)
 
     int predictability = 2048;
     if (predictor == 0 && compress) {
@@ -474,16 +630,20 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
     }
 
     int nnodes = 0;
-    if (!read_tree(rac, P.meta_table, pr, nprops, ws.nodes, nnodes, ws.stack, coder)) return corrupt_or_truncated(io, img.ch[beginc], lane);
+    if (!read_tree(rac, P.meta_table, pr, nprops, ws.nodes, nnodes, ws.stack, sm.coder)) return corrupt_or_truncated(io, img.ch[beginc], lane);
 
     // FinalPropertySymbolCoder ctor, compound.h:213-225: leaf numbering in node order, all leaves start from zero_chance
     const int nleaves = (nnodes + 1) / 2;
     for (int i = 0, leafID = 0; i < nnodes; i++) if (ws.nodes[i].property == -1) ws.nodes[i].child = (unsigned short)leafID++;
-    for (int i = lane; i < nleaves * 32; i += 32) ws.leaves[i] = initial_chance(i & 31, predictability);
     __syncwarp();
-
-    int props[kMaxProps];
-    for (int i = 0; i < kMaxProps; i++) props[i] = 0;
+    for (int i = lane; i < nleaves * 32; i += 32) ws.leaves[i] = initial_chance(i & 31, predictability);
+    const bool nodes_in_smem = nnodes <= sm.node_cap;
+    if (nodes_in_smem) {
+        const uint2 *src = reinterpret_cast<const uint2 *>(ws.nodes);
+        uint2 *dst = reinterpret_cast<uint2 *>(sm.nodes);
+        for (int i = lane; i < nnodes; i += 32) dst[i + 1] = src[i];
+    }
+    __syncwarp();
 
     for (int i = beginc; i <= endc; i++) {
         DChan &ch = img.ch[i];
@@ -493,29 +653,28 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
         if (nnodes == 1 && predictor == 0 && ch.zero == 0) {        // fast track, encoding.cpp:371-383
             for (int y = 0; y < ch.h; y++) {
                 if (io.stop()) break;
-                for (int x = 0; x < ch.w; x++) ch.data[(size_t)y * ch.w + x] = (int16_t)read_int(rac, P.table, ws.leaves, ch.minval, ch.maxval);
+                int16_t *row = ch.data + (size_t)y * ch.w;
+                for (int x0 = 0; x0 < ch.w; x0 += 32) {
+                    int outv = 0;
+                    const int cnt = min(32, ch.w - x0);
+                    for (int k = 0; k < cnt; k++) {
+                        const int v = read_int_reg(rac, sm.table, reinterpret_cast<uint4 *>(ws.leaves), ch.minval, ch.maxval);
+                        if (lane == k) outv = v;
+                    }
+                    if (x0 + lane < ch.w) row[x0 + lane] = (int16_t)outv;
+                }
                 publish_rows(ch, y + 1, lane);
             }
         } else {
             for (int y = 0; y < ch.h; y++) {
                 if (io.stop()) break;
-                precompute_references(ch, y, img, refchan, nrefchan, ws.refs, nref, lane);
-                for (int x = 0; x < ch.w; x++) {
-                    for (int k = 0; k < nref; k++) props[k] = ws.refs[x * nref + k];
-                    const int guess = predict_props(props, ch, x, y, predictor, nref);
-                    const int mn = ch.minval - guess, mx = ch.maxval - guess;
-                    int diff;
-                    if (mn == mx) diff = mn;
-                    else {
-                        int pos = 0;                                    // find_leaf, compound.h:142-153
-                        while (ws.nodes[pos].property != -1) {
-                            const TNode nd = ws.nodes[pos];
-                            pos = props[nd.property] > nd.splitval ? nd.child : nd.child + 1;
-                        }
-                        diff = read_int(rac, P.table, ws.leaves + 32 * ws.nodes[pos].child, mn, mx);
-                    }
-                    ch.data[(size_t)y * ch.w + x] = (int16_t)(s16(diff) + guess);
+                for (int r = 0; r < nrefchan; r++) {       // row wavefront on the planes this row back-references
+                    const DChan &cj = img.ch[refchan[r]];
+                    int ry = (y << ch.vshift) >> cj.vshift;
+                    if (ry >= cj.h) ry = cj.h - 1;
+                    spin_until_ge(&cj.rows_done, ry + 1);
                 }
+                decode_row(img, ch, y, predictor, refchan, nrefchan, nref, rac, sm, ws.nodes, nodes_in_smem, ws.leaves, lane);
                 publish_rows(ch, y + 1, lane);
             }
         }
@@ -526,13 +685,16 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
 }
 
 __global__ void __launch_bounds__(32) k_maniac_decode(Params P) {
-    __shared__ uint16_t s_table[4096 * 2];
-    __shared__ uint16_t s_coder[3][32];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
-    for (int i = lane; i < 4096 * 2; i += 32) s_table[i] = P.table[i];
+    Smem sm;
+    sm.table = reinterpret_cast<uint16_t *>(smem_raw);                                    // 16 KiB
+    sm.coder = reinterpret_cast<uint16_t(*)[32]>(smem_raw + 16384);                       // 192 B
+    sm.crefs = reinterpret_cast<int16_t *>(smem_raw + 16384 + 256);                       // 32*20*2 = 1280 B
+    sm.nodes = reinterpret_cast<uint4 *>(smem_raw + 16384 + 256 + 1280);
+    sm.node_cap = P.node_cap;
+    for (int i = lane; i < 4096 * 2; i += 32) sm.table[i] = P.table[i];
     __syncwarp();
-    Params Q = P;
-    Q.table = s_table;
     WarpScratch ws = P.scratch[blockIdx.x];
     for (;;) {
         int sid = 0;
@@ -542,23 +704,26 @@ __global__ void __launch_bounds__(32) k_maniac_decode(Params P) {
         const DStream st = P.streams[sid];
         DImage &img = P.images[st.image];
         Reader io;
-        io.p = img.bytes; io.n = img.nbytes; io.pos = st.offset; io.btl = img.bytes_to_load; io.eof = false;
+        io.p = img.bytes; io.n = img.nbytes; io.btl = img.bytes_to_load; io.eof = false;
+        io.seek(st.offset);
         int groups = 0;
         // the channel loop of fuif_decode, encoding.cpp:708-718
         for (int i = st.first_channel; i < img.nch; i++) {
             if (st.max_groups >= 0 && groups >= st.max_groups) break;
             if ((img.bytes_to_load == 0 || io.pos < img.bytes_to_load) && !io.eof) {
                 if (!img.ch[i].w || !img.ch[i].h) continue;
-                bool ok = decode_group(img, io, i, Q, ws, lane, s_coder);
+                bool ok = decode_group(img, io, i, P, ws, lane, sm);
                 groups++;
-                if (!ok) { img.status = FB_ERR_INVALID; break; }
+                if (!ok) { if (!img.status) img.status = FB_ERR_INVALID; break; }
             } else break;
         }
         // whatever happened (truncation, corruption), nobody may wait forever on this stream's channels
-        for (int c = st.first_channel; c < st.end_channel && c < img.nch; c++) {
-            atomicExch(&img.ch[c].hdr_done, 1);
-            publish_rows(img.ch[c], img.ch[c].h, lane);
-        }
+        __syncwarp();
+        if (lane == 0)
+            for (int c = st.first_channel; c < st.end_channel && c < img.nch; c++) {
+                st_release(&img.ch[c].hdr_done, 1);
+                st_release(&img.ch[c].rows_done, 0x7fffffff);
+            }
         __syncwarp();
     }
 }
@@ -767,7 +932,18 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         Params P;
         P.images = img_dev; P.streams = streams_dev; P.nstreams = nstreams; P.ticket = st->ticket_dev;
         P.table = st->table_dev; P.meta_table = st->meta_dev; P.scratch = st->scratch_dev; P.maxw = st->maxw;
-        k_maniac_decode<<<nslots, 32, 0, ctx->stream>>>(P);
+        // shared memory per block (= per stream in flight): 16 KiB chance table + scratch + as much tree-node cache as the
+        // number of blocks per SM leaves room for
+        const int per_sm = (nslots + ctx->sm_count - 1) / ctx->sm_count;
+        size_t budget = (size_t)(220 * 1024) / per_sm;
+        budget = std::min<size_t>(budget, 200 * 1024);
+        const size_t fixed = 16384 + 256 + 1280;
+        if (budget < fixed + 4096) budget = fixed + 4096;
+        P.node_cap = (int)((budget - fixed) / sizeof(TNode)) - 2;
+        if (P.node_cap > kMaxNodes) P.node_cap = kMaxNodes;
+        const size_t smem_bytes = fixed + (size_t)(P.node_cap + 2) * sizeof(TNode);
+        FB_CUDA(ctx, cudaFuncSetAttribute(k_maniac_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        k_maniac_decode<<<nslots, 32, smem_bytes, ctx->stream>>>(P);
         ctx->launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { ctx->err = std::string("maniac launch: ") + cudaGetErrorString(e); return FB_ERR_CUDA; }
@@ -791,7 +967,8 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
             else { fb_plane_free(ctx, c.dev); c.dev = nullptr; c.d.decoded = 0; }
             if (d.group_off >= 0) { img->group_off.push_back(d.group_off); img->group_first.push_back((int32_t)i); }
         }
-        if (himg[b].status) { ctx->err = "corrupt FUIF stream (image " + std::to_string(b) + ")"; rc = FB_ERR_INVALID; }
+        if (himg[b].status == FB_ERR_UNSUPPORTED) { ctx->err = "max_properties > 18 is not supported by the GPU context model"; rc = FB_ERR_UNSUPPORTED; }
+        else if (himg[b].status) { ctx->err = "corrupt FUIF stream (image " + std::to_string(b) + ")"; rc = FB_ERR_INVALID; }
         coff += img->ch.size();
     }
     return rc;
