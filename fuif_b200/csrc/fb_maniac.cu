@@ -18,6 +18,7 @@
 // planes it back-references), which are guaranteed to be running already.
 #include "fb_common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -71,6 +72,7 @@ struct Params {
     WarpScratch *scratch;
     int maxw;
     int node_cap;           // tree nodes that fit the block's shared-memory node cache
+    int debug;              // FB_MANIAC_DEBUG=1: trace group headers from lane 0
 };
 
 __device__ __forceinline__ int s16(int x) { return (int)(short)x; }
@@ -178,10 +180,15 @@ __device__ __forceinline__ uint16_t initial_chance(int idx, int zero_chance) {  
 }
 
 // Memory-resident variant (tree parse, fast track, uncompressed): chances read-modify-written in place.
+// All lanes execute the decode redundantly and store identical values.  Nothing guarantees that the lanes run in
+// lockstep, so every read-modify-write of shared state is bracketed: everyone has read before anyone writes, and every
+// write has landed before the next read.
 __device__ __forceinline__ int sym_read(Rac &rac, const uint16_t *__restrict__ table, uint16_t *leaf, int idx) {    // compound.h:90-95
     int ch = leaf[idx];
+    __syncwarp();
     int bit = rac.read12(ch);
     leaf[idx] = table[ch * 2 + bit];
+    __syncwarp();
     return bit;
 }
 
@@ -238,6 +245,7 @@ __device__ __forceinline__ int read_int_reg(Rac &rac, const uint16_t *__restrict
         L[0] = a.x; L[1] = a.y; L[2] = a.z; L[3] = a.w; L[4] = b.x; L[5] = b.y; L[6] = b.z; L[7] = b.w;
         L[8] = c.x; L[9] = c.y; L[10] = c.z; L[11] = c.w; L[12] = d.x; L[13] = d.y; L[14] = d.z; L[15] = d.w;
     }
+    __syncwarp();       // every lane holds the leaf before any lane writes it back (lanes are redundant, not lockstep)
     int result;
     int bit;
     SYM_REG(SC_ZERO, bit);
@@ -276,6 +284,7 @@ __device__ __forceinline__ int read_int_reg(Rac &rac, const uint16_t *__restrict
     leafp[1] = make_uint4(L[4], L[5], L[6], L[7]);
     leafp[2] = make_uint4(L[8], L[9], L[10], L[11]);
     leafp[3] = make_uint4(L[12], L[13], L[14], L[15]);
+    __syncwarp();       // the updated chances are in place before the next symbol loads a leaf
     return result;
 }
 
@@ -433,6 +442,7 @@ struct Smem {
     int16_t *crefs;         // [32][kRefStride] reference properties of the current 32-pixel chunk
     uint4 *nodes;           // node cache: slot i+1 holds node i, so that sibling pairs are 16-byte aligned
     int node_cap;           // nodes that fit
+    int debug;
 };
 constexpr int kRefStride = 20;      // up to 18 reference properties + padding (one lane per property: 18 + 13 <= 32)
 
@@ -489,24 +499,24 @@ __device__ __forceinline__ void decode_row(DImage &img, DChan &ch, int y, int pr
             const int topright = y ? __shfl_sync(0xffffffffu, TR, i) : top;
             const int toptop = y ? __shfl_sync(0xffffffffu, TT, i) : top;
             // properties (predict_and_compute_properties, context_predict.h:135-154), one per lane
-            int mine = 0;
-            if (role < 0) mine = sm.crefs[i * kRefStride + lane];
-            else {
-                switch (role) {
-                case 0: mine = fooabs(top); break;
-                case 1: mine = fooabs(left); break;
-                case 2: mine = slog(top); break;
-                case 3: mine = slog(left); break;
-                case 4: mine = y; break;
-                case 5: mine = xx; break;
-                case 6: mine = left + top - topleft; break;
-                case 7: mine = topleft + topright - top; break;
-                case 8: mine = slog(left - topleft); break;
-                case 9: mine = slog(topleft - top); break;
-                case 10: mine = slog(top - topright); break;
-                case 11: mine = slog(top - toptop); break;
-                case 12: mine = slog(left - leftleft); break;
-                default: break;
+            // Every lane evaluates all thirteen expressions and keeps the one its role selects (selects, not branches:
+            // the lanes must stay converged because the leaf chances are read-modify-written in memory below).
+            const int q0 = fooabs(top), q1 = fooabs(left), q2 = slog(top), q3 = slog(left), q6 = left + top - topleft,
+                      q7 = topleft + topright - top, q8 = slog(left - topleft), q9 = slog(topleft - top), q10 = slog(top - topright),
+                      q11 = slog(top - toptop), q12 = slog(left - leftleft);
+            int mine = sm.crefs[i * kRefStride + (role < 0 ? lane : 0)];
+            mine = role == 0 ? q0 : mine;   mine = role == 1 ? q1 : mine;   mine = role == 2 ? q2 : mine;   mine = role == 3 ? q3 : mine;
+            mine = role == 4 ? y : mine;    mine = role == 5 ? xx : mine;   mine = role == 6 ? q6 : mine;   mine = role == 7 ? q7 : mine;
+            mine = role == 8 ? q8 : mine;   mine = role == 9 ? q9 : mine;   mine = role == 10 ? q10 : mine; mine = role == 11 ? q11 : mine;
+            mine = role == 12 ? q12 : mine;
+            __syncwarp();
+            if (sm.debug) {     // self-check of the lane-distributed property vector against a uniform recomputation
+                int exp13[13] = {fooabs(top), fooabs(left), slog(top), slog(left), y, xx, left + top - topleft, topleft + topright - top,
+                                 slog(left - topleft), slog(topleft - top), slog(top - topright), slog(top - toptop), slog(left - leftleft)};
+                for (int k = 0; k < nref + 13; k++) {
+                    const int got = __shfl_sync(0xffffffffu, mine, k);
+                    const int want = k < nref ? (int)sm.crefs[i * kRefStride + k] : exp13[k - nref];
+                    if (got != want && lane == 0) printf("[maniac] prop mismatch y %d x %d k %d got %d want %d (w %d nref %d)\n", y, xx, k, got, want, w, nref);
                 }
             }
             const int guess = predict(predictor, left, top, topleft, topright, ch);
@@ -538,6 +548,7 @@ __device__ __forceinline__ void decode_row(DImage &img, DChan &ch, int y, int pr
                     leaf = cur.x >> 16;
                 }
                 diff = read_int_reg(rac, sm.table, reinterpret_cast<uint4 *>(leaves + 32 * leaf), mn, mx);
+                if (sm.debug && lane == 0 && y < 2 && xx < 6) printf("[maniac]   y %d x %d leaf %d mn %d mx %d diff %d guess %d pos %llu\n", y, xx, leaf, mn, mx, diff, guess, rac.io->pos);
             }
             const int val = s16(s16(diff) + guess);
             if (lane == i) outv = val;
@@ -566,6 +577,7 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
     if (io.stop()) return true;
     const int global_maxv = s16(global_minv + io.varint());
     if (io.stop()) return true;
+    if (P.debug && lane == 0) printf("[maniac] group at %lld: ch %d-%d compress %d pred %d range %d..%d\n", header_pos, beginc, endc, (int)compress, predictor, global_minv, global_maxv);
     if (endc >= img.nch || endc < beginc) return false;
     img.ch[b0].group_off = header_pos;
 
@@ -638,6 +650,10 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
     __syncwarp();
     for (int i = lane; i < nleaves * 32; i += 32) ws.leaves[i] = initial_chance(i & 31, predictability);
     const bool nodes_in_smem = nnodes <= sm.node_cap;
+    if (P.debug && lane == 0) {
+        printf("[maniac]   tree %d nodes, nprops %d nref %d, zero_chance %d, pos %llu, %dx%d\n", nnodes, nprops, nref, predictability, io.pos, img.ch[beginc].w, img.ch[beginc].h);
+        for (int i = 0; i < nnodes && i < 8; i++) printf("[maniac]     node %d: prop %d child %d split %d\n", i, ws.nodes[i].property, ws.nodes[i].child, ws.nodes[i].splitval);
+    }
     if (nodes_in_smem) {
         const uint2 *src = reinterpret_cast<const uint2 *>(ws.nodes);
         uint2 *dst = reinterpret_cast<uint2 *>(sm.nodes);
@@ -693,6 +709,7 @@ __global__ void __launch_bounds__(32) k_maniac_decode(Params P) {
     sm.crefs = reinterpret_cast<int16_t *>(smem_raw + 16384 + 256);                       // 32*20*2 = 1280 B
     sm.nodes = reinterpret_cast<uint4 *>(smem_raw + 16384 + 256 + 1280);
     sm.node_cap = P.node_cap;
+    sm.debug = P.debug;
     for (int i = lane; i < 4096 * 2; i += 32) sm.table[i] = P.table[i];
     __syncwarp();
     WarpScratch ws = P.scratch[blockIdx.x];
@@ -932,6 +949,7 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         Params P;
         P.images = img_dev; P.streams = streams_dev; P.nstreams = nstreams; P.ticket = st->ticket_dev;
         P.table = st->table_dev; P.meta_table = st->meta_dev; P.scratch = st->scratch_dev; P.maxw = st->maxw;
+        P.debug = getenv("FB_MANIAC_DEBUG") ? 1 : 0;
         // shared memory per block (= per stream in flight): 16 KiB chance table + scratch + as much tree-node cache as the
         // number of blocks per SM leaves room for
         const int per_sm = (nslots + ctx->sm_count - 1) / ctx->sm_count;

@@ -1199,6 +1199,8 @@ static int decode_channel_group(blob *io, dec_ctx *dc, int max_properties, int *
                         { int q = 0, d = 0; while (t.n[q].property != -1) { int pr_ = t.n[q].property - nref; if (pr_ == 1 || pr_ == 3 || pr_ == 6 || pr_ == 8 || pr_ == 12) break; d++; q = props[t.n[q].property] > t.n[q].splitval ? t.n[q].childID : t.n[q].childID + 1; } st_unk1 += d; }
                         diff = read_int(&rac, &dc->table, &leaf[t.n[pos].childID], mn, mx);
                         if (diff == 0) st_zero++;
+                        if (getenv("FO_TRACE") && atoi(getenv("FO_TRACE")) == i && y < 2 && x < 6)
+                            fprintf(stderr, "[oracle]   y %d x %d leaf %d mn %d mx %d diff %d guess %d pos %zu\n", y, x, t.n[pos].childID, mn, mx, diff, guess, io->pos);
                     }
                     ch->data[(size_t)y * ch->w + x] = (int16_t)(S16(diff) + guess);
                 }
