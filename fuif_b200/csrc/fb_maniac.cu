@@ -71,7 +71,7 @@ struct Params {
     const uint16_t *meta_table; // [4096][2] tree-coder table (cut 2, alpha 0xFFFFFFFF/19)
     WarpScratch *scratch;
     int maxw;
-    int node_cap;           // tree nodes that fit the block's shared-memory node cache
+    int warp_smem;          // bytes of shared memory per warp (after the block's 16 KiB chance table)
     int debug;              // FB_MANIAC_DEBUG=1: trace group headers from lane 0
 };
 
@@ -127,15 +127,15 @@ struct Reader {
 
 // ---- range decoder (maniac/rac.h) -----------------------------------------------------------------------------
 struct Rac {
-    Reader *io;
+    Reader io;          // by value: the whole coder state lives in registers
     unsigned range, low;
     bool ones;      // a read past the end turned `low` into all-ones garbage (rac.h:64-69): every bit reads as 1
     __device__ __forceinline__ void byte_in() {
-        int c = io->get();
+        int c = io.get();
         if (c < 0) ones = true;
         low = (low << 8) | (unsigned)(c & 0xFF);
     }
-    __device__ void init(Reader *r) {           // RacInput ctor, rac.h:97-104
+    __device__ __forceinline__ void init(const Reader &r) {           // RacInput ctor, rac.h:97-104
         io = r; range = 1u << 24; low = 0; ones = false;
         byte_in(); byte_in(); byte_in();
     }
@@ -179,37 +179,54 @@ __device__ __forceinline__ uint16_t initial_chance(int idx, int zero_chance) {  
     }
 }
 
-// Memory-resident variant (tree parse, fast track, uncompressed): chances read-modify-written in place.
-// All lanes execute the decode redundantly and store identical values.  Nothing guarantees that the lanes run in
-// lockstep, so every read-modify-write of shared state is bracketed: everyone has read before anyone writes, and every
-// write has landed before the next read.
-__device__ __forceinline__ int sym_read(Rac &rac, const uint16_t *__restrict__ table, uint16_t *leaf, int idx) {    // compound.h:90-95
-    int ch = leaf[idx];
-    __syncwarp();
-    int bit = rac.read12(ch);
-    leaf[idx] = table[ch * 2 + bit];
-    __syncwarp();
-    return bit;
-}
+// The serial coder runs in ONE lane (lane 0): adaptive chances are read-modify-written in place (shared memory),
+// so there is exactly one reader/writer and no lockstep assumption between lanes.
+//
+// SymCtx implements FinalCompoundSymbolBitCoder::read (compound.h:90-95): decode with chance lp[idx], then
+// lp[idx] = table[chance][bit].  The table lookup of bit k is consumed one bit later (delayed store), so its
+// shared-memory latency overlaps the next bit's chance load instead of stalling the in-order warp.
+struct SymCtx {
+    const uint16_t *table;
+    uint16_t *lp;
+    int pi;
+    unsigned pv;
+    __device__ __forceinline__ void begin(const uint16_t *t, uint16_t *leaf) { table = t; lp = leaf; pi = -1; pv = 0; }
+    __device__ __forceinline__ int read(Rac &rac, int idx) {
+        const unsigned ch = lp[idx];
+        if (pi >= 0) lp[pi] = (uint16_t)pv;
+        const int bit = rac.read12(ch);
+        pv = table[ch * 2 + bit];
+        pi = idx;
+        return bit;
+    }
+    __device__ __forceinline__ void end() { if (pi >= 0) lp[pi] = (uint16_t)pv; pi = -1; }
+};
 
 // reader<15>(coder, min, max), symbol.h:154-185
-__device__ int read_int(Rac &rac, const uint16_t *__restrict__ table, uint16_t *leaf, int mn, int mx) {
+__device__ __forceinline__ int read_int(Rac &rac, const uint16_t *__restrict__ table, uint16_t *leaf, int mn, int mx) {
     if (mn == mx) return mn;
-    int sign;
-    if (sym_read(rac, table, leaf, SC_ZERO)) return 0;
-    if (mn < 0) { if (mx > 0) sign = sym_read(rac, table, leaf, SC_SIGN); else sign = 0; } else sign = 1;
-    const int amax = sign ? mx : -mn;
-    const int emax = ilog2u((unsigned)amax);
-    int e = 0;
-    for (; e < emax; e++) if (sym_read(rac, table, leaf, SC_EXP + e)) break;
-    int have = 1 << e;
-    for (int pos = e; pos > 0;) {
-        pos--;
-        int minabs1 = have | (1 << pos);
-        if (minabs1 > amax) continue;
-        if (sym_read(rac, table, leaf, SC_MANT + pos)) have = minabs1;
+    SymCtx c;
+    c.begin(table, leaf);
+    int result;
+    if (c.read(rac, SC_ZERO)) result = 0;
+    else {
+        int sign;
+        if (mn < 0) { if (mx > 0) sign = c.read(rac, SC_SIGN); else sign = 0; } else sign = 1;
+        const int amax = sign ? mx : -mn;
+        const int emax = ilog2u((unsigned)amax);
+        int e = 0;
+        for (; e < emax; e++) if (c.read(rac, SC_EXP + e)) break;
+        int have = 1 << e;
+        for (int pos = e; pos > 0;) {
+            pos--;
+            const int minabs1 = have | (1 << pos);
+            if (minabs1 > amax) continue;
+            if (c.read(rac, SC_MANT + pos)) have = minabs1;
+        }
+        result = sign ? have : -have;
     }
-    return sign ? have : -have;
+    c.end();
+    return result;
 }
 __device__ int read_int2(Rac &rac, const uint16_t *table, uint16_t *leaf, int mn, int mx) {     // symbol.h:232-236
     if (mn > 0) return read_int(rac, table, leaf, 0, mx - mn) + mn;
@@ -223,69 +240,6 @@ __device__ int uniform_read(Rac &rac, int mn, int len) {    // UniformSymbolCode
         else len = med;
     }
     return mn;
-}
-
-// Register-resident variant for the hot loop: the 31 chances of the selected leaf live in sixteen 32-bit registers
-// (two chances per register) and every access below has a compile-time index once the loops are unrolled, so the
-// chance lookup is off the range coder's dependency chain and the table lookup for the update only feeds the
-// write-back.  Same bit sequence as reader<15> (symbol.h:154-185) / FinalCompoundSymbolBitCoder::read (compound.h:90-95).
-#define SYM_REG(IDX, BIT)                                                                                       \
-    do {                                                                                                        \
-        const unsigned w_ = L[(IDX) >> 1];                                                                      \
-        const unsigned ch_ = ((IDX)&1) ? (w_ >> 16) : (w_ & 0xffffu);                                           \
-        BIT = rac.read12(ch_);                                                                                  \
-        const unsigned nc_ = table[ch_ * 2 + BIT];                                                              \
-        L[(IDX) >> 1] = ((IDX)&1) ? ((w_ & 0xffffu) | (nc_ << 16)) : ((w_ & 0xffff0000u) | nc_);                \
-    } while (0)
-
-__device__ __forceinline__ int read_int_reg(Rac &rac, const uint16_t *__restrict__ table, uint4 *leafp, int mn, int mx) {
-    unsigned L[16];
-    {
-        const uint4 a = leafp[0], b = leafp[1], c = leafp[2], d = leafp[3];
-        L[0] = a.x; L[1] = a.y; L[2] = a.z; L[3] = a.w; L[4] = b.x; L[5] = b.y; L[6] = b.z; L[7] = b.w;
-        L[8] = c.x; L[9] = c.y; L[10] = c.z; L[11] = c.w; L[12] = d.x; L[13] = d.y; L[14] = d.z; L[15] = d.w;
-    }
-    __syncwarp();       // every lane holds the leaf before any lane writes it back (lanes are redundant, not lockstep)
-    int result;
-    int bit;
-    SYM_REG(SC_ZERO, bit);
-    if (bit) {
-        result = 0;
-    } else {
-        int sign;
-        if (mn < 0) {
-            if (mx > 0) { SYM_REG(SC_SIGN, bit); sign = bit; } else sign = 0;
-        } else sign = 1;
-        const int amax = sign ? mx : -mn;
-        const int emax = ilog2u((unsigned)amax);
-        int e = 0;
-        bool go = true;
-#pragma unroll
-        for (int k = 0; k < MAX_BIT_DEPTH - 1; k++) {
-            if (go && k < emax) {
-                SYM_REG(SC_EXP + k, bit);
-                if (bit) go = false; else e = k + 1;
-            }
-        }
-        int have = 1 << e;
-#pragma unroll
-        for (int pos = MAX_BIT_DEPTH - 2; pos >= 0; pos--) {
-            if (pos < e) {
-                const int minabs1 = have | (1 << pos);
-                if (minabs1 <= amax) {
-                    SYM_REG(SC_MANT + pos, bit);
-                    if (bit) have = minabs1;
-                }
-            }
-        }
-        result = sign ? have : -have;
-    }
-    leafp[0] = make_uint4(L[0], L[1], L[2], L[3]);
-    leafp[1] = make_uint4(L[4], L[5], L[6], L[7]);
-    leafp[2] = make_uint4(L[8], L[9], L[10], L[11]);
-    leafp[3] = make_uint4(L[12], L[13], L[14], L[15]);
-    __syncwarp();       // the updated chances are in place before the next symbol loads a leaf
-    return result;
 }
 
 // ---- context model (encoding/context_predict.h) ---------------------------------------------------------------------
@@ -311,8 +265,11 @@ __device__ bool check_bit_depth(int minv, int maxv, int predictor) {    // encod
     return ilog2u((unsigned)maxav) + 1 <= MAX_BIT_DEPTH;
 }
 
+// Poll with relaxed loads that bypass L1 (no cache invalidation per poll); one acquire once the value is there.
 __device__ __forceinline__ void spin_until_ge(const int *flag, int want) {
-    while (ld_acquire(flag) < want) __nanosleep(100);
+    if (__ldcg(flag) >= want) { (void)ld_acquire(flag); return; }
+    while (__ldcg(flag) < want) __nanosleep(64);
+    (void)ld_acquire(flag);
 }
 
 // All lanes of the warp call this with identical arguments.
@@ -362,7 +319,7 @@ __device__ int init_properties(int (*pr)[2], DImage &img, int beginc, int endc, 
     return n;
 }
 
-// MetaPropertySymbolCoder::read_tree, compound.h:277-320, recursion unrolled on an explicit stack
+// MetaPropertySymbolCoder::read_tree, compound.h:277-320, recursion unrolled on an explicit stack.  Lane 0 only.
 __device__ bool read_tree(Rac &rac, const uint16_t *__restrict__ mtable, int (*range)[2], int nprops, TNode *nodes, int &nnodes,
                           int *stack, uint16_t (*coder)[32]) {
     int sub[kMaxProps][2];
@@ -412,15 +369,15 @@ __device__ bool read_tree(Rac &rac, const uint16_t *__restrict__ mtable, int (*r
     return true;
 }
 
-__device__ __forceinline__ int predict(int predictor, int left, int top, int topleft, int topright, const DChan &ch) {     // context_predict.h:157-166
+__device__ __forceinline__ int predict(int predictor, int left, int top, int topleft, int topright, int zero, int cmin, int cmax) {     // context_predict.h:157-166
     switch (predictor) {
-    case 0: return ch.zero;
+    case 0: return zero;
     case 1: return s16((left + top) / 2);
     case 2: return median3(s16(left + top - topleft), left, top);
     case 3: return left;
     case 4: return top;
     case 5: return s16((left + topleft + top + topright) / 4);
-    case 6: { int g = left + top - topleft; return s16(g < ch.minval ? ch.minval : (g > ch.maxval ? ch.maxval : g)); }
+    case 6: { int g = left + top - topleft; return s16(g < cmin ? cmin : (g > cmax ? cmax : g)); }
     default: return median3(s16(left + top - topleft), left, top);
     }
 }
@@ -431,137 +388,143 @@ __device__ __forceinline__ void publish_rows(DChan &c, int rows, int lane) {
 }
 
 // corrupt_or_truncated, encoding.cpp:209-219.  returns true = "truncated, carry on", false = corruption
-__device__ bool corrupt_or_truncated(Reader &io, DChan &c, int lane) {
-    if (io.stop()) { fill_plane(c, 0, lane); return true; }
+__device__ bool corrupt_or_truncated(bool stopped, DChan &c, int lane) {
+    if (stopped) { fill_plane(c, 0, lane); return true; }
     return false;
 }
 
+// Per-warp shared memory.
+constexpr int kPropStride = 37;     // 32 property slots (one per lane) + top, topleft, topright + padding; odd => conflict-free rows
 struct Smem {
-    uint16_t *table;        // [4096][2]
+    const uint16_t *table;  // [4096][2], shared by the warps of the block
     uint16_t (*coder)[32];  // 3 x 32 tree-coder chances
-    int16_t *crefs;         // [32][kRefStride] reference properties of the current 32-pixel chunk
-    uint4 *nodes;           // node cache: slot i+1 holds node i, so that sibling pairs are 16-byte aligned
-    int node_cap;           // nodes that fit
-    int debug;
+    int *cprop;             // [32][kPropStride]: per pixel of the current chunk: properties by lane, then top / topleft / topright
+    unsigned char *dyn;     // dynamic region: tree-node cache, then leaf chances (resident or direct-mapped cache)
+    int dyn_bytes;
 };
-constexpr int kRefStride = 20;      // up to 18 reference properties + padding (one lane per property: 18 + 13 <= 32)
+
+// Node cache entry (8 bytes): x = property << 16 | slot16 (uint4 index of the child pair) for inner nodes,
+// x = 0xFFFF0000 | leaf id for leaves (sign bit set);  y = split value.  Slot i+1 holds node i so that sibling pairs
+// (odd node index, next) share one 16-byte line.
+struct LeafStore {
+    uint16_t *lines;        // shared memory: nlines x 32 chances
+    int *tags;              // direct-mapped tags (nullptr when every leaf is resident)
+    int mask;               // nlines - 1
+    uint16_t *gleaves;      // global backing store
+};
+
+// Returns the shared-memory address of leaf `leaf`'s 32 chances; all lanes cooperate on a miss.
+__device__ __forceinline__ uint16_t *leaf_lookup(const LeafStore &ls, int leaf, int lane) {
+    if (!ls.tags) return ls.lines + 32 * leaf;
+    const int slot = leaf & ls.mask;
+    const int tag = ls.tags[slot];
+    uint16_t *line = ls.lines + 32 * slot;
+    if (tag != leaf) {
+        __syncwarp();       // lane 0's chance updates of the line being evicted are visible to the copying lanes
+        if (lane < 16) {
+            unsigned *s = reinterpret_cast<unsigned *>(line);
+            if (tag >= 0) reinterpret_cast<unsigned *>(ls.gleaves + 32 * (size_t)tag)[lane] = s[lane];
+            s[lane] = reinterpret_cast<const unsigned *>(ls.gleaves + 32 * (size_t)leaf)[lane];
+        }
+        if (lane == 0) ls.tags[slot] = leaf;
+        __syncwarp();
+    }
+    return line;
+}
 
 // One row of a channel in the "slow track" (encoding.cpp:388-421), 32 pixels at a time.
 // Lane roles: lane k < nref holds reference property k, lane nref+j holds non-reference property j (0..12).
+// Returns through `rac` (meaningful in lane 0 only).
 __device__ __forceinline__ void decode_row(DImage &img, DChan &ch, int y, int predictor, const int *refchan, int nrefchan, int nref,
-                                           Rac &rac, const Smem &sm, const TNode *gnodes, bool nodes_in_smem, uint16_t *leaves, int lane) {
+                                           Rac &rac, const Smem &sm, const uint2 *nodes2, const LeafStore &ls, int lane) {
     const int w = ch.w;
     int16_t *row = ch.data + (size_t)y * w;
     const int16_t *row1 = row - w, *row2 = row - 2 * w;
     const int role = lane - nref;
     const int zero = ch.zero, cmin = ch.minval, cmax = ch.maxval;
+    const int vshift = ch.vshift, hshift = ch.hshift;
     int left = zero, leftleft = zero;
-    // reference rows (precompute_references, context_predict.h:233-289): row pointer, width and x mapping per channel
     for (int x0 = 0; x0 < w; x0 += 32) {
         const int x = x0 + lane;
-        const bool in = x < w;
         // --- chunk prologue (lanes = pixels): neighbours from the rows above, reference properties
-        int T1 = zero, TL = zero, TR = zero, TT = zero;
-        if (in) {
+        //     (precompute_references, context_predict.h:233-289) and every property that does not depend on `left`
+        if (x < w) {
+            int T1 = zero, TL = zero, TR = zero, TT = zero;
             if (y) {
                 T1 = row1[x];
-                TL = x ? row1[x - 1] : zero;            // x == 0: topleft = left = zero (context_predict.h:128)
+                TL = x ? row1[x - 1] : zero;
                 TR = (x + 1 < w) ? row1[x + 1] : T1;
                 TT = (y > 1) ? row2[x] : T1;
             }
+            int *pp = sm.cprop + lane * kPropStride;
             for (int r = 0; r < nrefchan; r++) {
                 const DChan &cj = img.ch[refchan[r]];
-                int ry = (y << ch.vshift) >> cj.vshift;
+                int ry = (y << vshift) >> cj.vshift;
                 if (ry >= cj.h) ry = cj.h - 1;
                 int rx;
-                if (ch.hshift == cj.hshift && w <= cj.w) rx = x;
-                else if (ch.hshift < cj.hshift) {
-                    const int stepsize = (1 << cj.hshift) >> ch.hshift;     // all samples but the last are repeated stepsize times
+                if (hshift == cj.hshift && w <= cj.w) rx = x;
+                else if (hshift < cj.hshift) {
+                    const int stepsize = (1 << cj.hshift) >> hshift;     // all samples but the last are repeated stepsize times
                     rx = stepsize > 0 ? x / stepsize : cj.w - 1;
                     if (rx > cj.w - 1) rx = cj.w - 1;
                 } else {
-                    rx = (x << ch.hshift) >> cj.hshift;
+                    rx = (x << hshift) >> cj.hshift;
                     if (rx >= cj.w) rx = cj.w - 1;
                 }
                 const int v = __ldcg(cj.data + (size_t)ry * cj.w + rx);
-                sm.crefs[lane * kRefStride + 2 * r] = (int16_t)fooabs(v);
-                sm.crefs[lane * kRefStride + 2 * r + 1] = (int16_t)slog(v);
+                pp[2 * r] = fooabs(v);
+                pp[2 * r + 1] = slog(v);
             }
+            pp[nref + 0] = fooabs(T1);
+            pp[nref + 2] = slog(T1);
+            pp[nref + 4] = y;
+            pp[nref + 5] = x;
+            pp[nref + 10] = slog(T1 - TR);
+            pp[nref + 11] = slog(T1 - TT);
+            pp[32] = T1; pp[33] = TL; pp[34] = TR;
         }
         __syncwarp();
         int outv = 0;
         const int cnt = min(32, w - x0);
         for (int i = 0; i < cnt; i++) {
             const int xx = x0 + i;
-            const int top = y ? __shfl_sync(0xffffffffu, T1, i) : zero;
-            const int tl_ = __shfl_sync(0xffffffffu, TL, i);
-            const int topleft = (xx && y) ? tl_ : left;
-            const int topright = y ? __shfl_sync(0xffffffffu, TR, i) : top;
-            const int toptop = y ? __shfl_sync(0xffffffffu, TT, i) : top;
-            // properties (predict_and_compute_properties, context_predict.h:135-154), one per lane
-            // Every lane evaluates all thirteen expressions and keeps the one its role selects (selects, not branches:
-            // the lanes must stay converged because the leaf chances are read-modify-written in memory below).
-            const int q0 = fooabs(top), q1 = fooabs(left), q2 = slog(top), q3 = slog(left), q6 = left + top - topleft,
-                      q7 = topleft + topright - top, q8 = slog(left - topleft), q9 = slog(topleft - top), q10 = slog(top - topright),
-                      q11 = slog(top - toptop), q12 = slog(left - leftleft);
-            int mine = sm.crefs[i * kRefStride + (role < 0 ? lane : 0)];
-            mine = role == 0 ? q0 : mine;   mine = role == 1 ? q1 : mine;   mine = role == 2 ? q2 : mine;   mine = role == 3 ? q3 : mine;
-            mine = role == 4 ? y : mine;    mine = role == 5 ? xx : mine;   mine = role == 6 ? q6 : mine;   mine = role == 7 ? q7 : mine;
-            mine = role == 8 ? q8 : mine;   mine = role == 9 ? q9 : mine;   mine = role == 10 ? q10 : mine; mine = role == 11 ? q11 : mine;
-            mine = role == 12 ? q12 : mine;
-            __syncwarp();
-            if (sm.debug) {     // self-check of the lane-distributed property vector against a uniform recomputation
-                int exp13[13] = {fooabs(top), fooabs(left), slog(top), slog(left), y, xx, left + top - topleft, topleft + topright - top,
-                                 slog(left - topleft), slog(topleft - top), slog(top - topright), slog(top - toptop), slog(left - leftleft)};
-                for (int k = 0; k < nref + 13; k++) {
-                    const int got = __shfl_sync(0xffffffffu, mine, k);
-                    const int want = k < nref ? (int)sm.crefs[i * kRefStride + k] : exp13[k - nref];
-                    if (got != want && lane == 0) printf("[maniac] prop mismatch y %d x %d k %d got %d want %d (w %d nref %d)\n", y, xx, k, got, want, w, nref);
-                }
-            }
-            const int guess = predict(predictor, left, top, topleft, topright, ch);
+            const int *pp = sm.cprop + i * kPropStride;
+            int mine = pp[lane];
+            const int top = pp[32];
+            const int topleft = (xx && y) ? pp[33] : left;         // context_predict.h:128
+            const int topright = pp[34];
+            // the properties that depend on the pixel just decoded (predict_and_compute_properties, context_predict.h:135-154)
+            const int q1 = fooabs(left), q3 = slog(left), q6 = left + top - topleft, q7 = topleft + topright - top,
+                      q8 = slog(left - topleft), q9 = slog(topleft - top), q12 = slog(left - leftleft);
+            mine = role == 1 ? q1 : mine;   mine = role == 3 ? q3 : mine;   mine = role == 6 ? q6 : mine;   mine = role == 7 ? q7 : mine;
+            mine = role == 8 ? q8 : mine;   mine = role == 9 ? q9 : mine;   mine = role == 12 ? q12 : mine;
+            const int guess = predict(predictor, left, top, topleft, topright, zero, cmin, cmax);
             const int mn = cmin - guess, mx = cmax - guess;
-            int diff;
-            if (mn == mx) diff = mn;
-            else {
+            int diff = mn;
+            if (mn != mx) {
                 // find_leaf (compound.h:142-153): node values are warp-uniform, the tested property comes from its lane
-                int leaf;
-                if (nodes_in_smem) {
-                    const uint2 *n2 = reinterpret_cast<const uint2 *>(sm.nodes);
-                    uint2 cur = n2[1];                                                 // node 0 lives in slot 1
-                    while ((short)(cur.x & 0xffff) != -1) {
-                        const unsigned child = cur.x >> 16;
-                        const uint4 pair = sm.nodes[(child + 1) >> 1];                 // slots child+1, child+2
-                        const int v = __shfl_sync(0xffffffffu, mine, (int)(short)(cur.x & 0xffff));
-                        cur = (v > (int)cur.y) ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
-                    }
-                    leaf = cur.x >> 16;
-                } else {
-                    const uint2 *n2 = reinterpret_cast<const uint2 *>(gnodes);
-                    uint2 cur = n2[0];
-                    while ((short)(cur.x & 0xffff) != -1) {
-                        const unsigned child = cur.x >> 16;
-                        const uint2 a = n2[child], b = n2[child + 1];
-                        const int v = __shfl_sync(0xffffffffu, mine, (int)(short)(cur.x & 0xffff));
-                        cur = (v > (int)cur.y) ? a : b;
-                    }
-                    leaf = cur.x >> 16;
+                uint2 cur = nodes2[1];
+                while ((int)cur.x >= 0) {
+                    const uint4 pair = reinterpret_cast<const uint4 *>(nodes2)[cur.x & 0xffffu];
+                    const int v = __shfl_sync(0xffffffffu, mine, (int)(cur.x >> 16));
+                    cur = (v > (int)cur.y) ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
                 }
-                diff = read_int_reg(rac, sm.table, reinterpret_cast<uint4 *>(leaves + 32 * leaf), mn, mx);
-                if (sm.debug && lane == 0 && y < 2 && xx < 6) printf("[maniac]   y %d x %d leaf %d mn %d mx %d diff %d guess %d pos %llu\n", y, xx, leaf, mn, mx, diff, guess, rac.io->pos);
+                uint16_t *lp = leaf_lookup(ls, (int)(cur.x & 0xffffu), lane);
+                if (lane == 0) diff = read_int(rac, sm.table, lp, mn, mx);
+                diff = __shfl_sync(0xffffffffu, diff, 0);
             }
             const int val = s16(s16(diff) + guess);
-            if (lane == i) outv = val;
-            leftleft = (xx >= 1) ? left : val;       // next pixel: x>1 ? value(x-2) : left  (context_predict.h:132)
+            outv = (lane == i) ? val : outv;
+            leftleft = xx ? left : val;          // next pixel: x > 1 ? value(x-2) : left   (context_predict.h:132)
             left = val;
-            if (xx == 0) leftleft = val;             // pixel 1 sees leftleft = left = value(0)
         }
-        if (in) row[x] = (int16_t)outv;
+        if (x < w) row[x] = (int16_t)outv;
         __syncwarp();
     }
 }
 
 // fuif_decode_channel, encoding.cpp:259-429.  Returns false on a hard error. `beginc` is advanced to the group's last channel.
+// `io` is kept identical in all lanes on entry and on exit; in between only lane 0's copy (inside `rac`) advances.
 __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params &P, WarpScratch &ws, int lane, const Smem &sm) {
     if (io.stop()) return true;
     const long long header_pos = (long long)io.pos;
@@ -594,7 +557,7 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
         if (ch.minval == ch.maxval) { fill_plane(ch, ch.minval, lane); firstrealc++; }
         if (ch.minval == 0 && ch.maxval == 0) continue;
         ch.q = io.varint();
-        if (io.stop()) { early = true; early_result = corrupt_or_truncated(io, ch, lane); break; }
+        if (io.stop()) { early = true; early_result = corrupt_or_truncated(true, ch, lane); break; }
         if (compress && !check_bit_depth(ch.minval, ch.maxval, predictor)) { early = true; early_result = false; break; }
     }
     for (int i = beginc; i <= endc; i++) {
@@ -618,48 +581,92 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
     int predictability = 2048;
     if (predictor == 0 && compress) {
         int rounded = io.varint();
-        if (rounded < 1 || rounded > 127) return corrupt_or_truncated(io, img.ch[min(firstrealc, img.nch - 1)], lane);
+        if (rounded < 1 || rounded > 127) return corrupt_or_truncated(io.stop(), img.ch[min(firstrealc, img.nch - 1)], lane);
         predictability = rounded * 32;
     }
 
+    // ---- from here on the serial coder lives in lane 0 (rac.io is the byte position)
     Rac rac;
-    rac.init(&io);
+    rac.init(io);
+#define SYNC_IO()                                                                     \
+    do {                                                                              \
+        io = rac.io;                                                                  \
+        io.pos = __shfl_sync(0xffffffffu, io.pos, 0);                                 \
+        io.eof = __shfl_sync(0xffffffffu, (int)io.eof, 0) != 0;                       \
+        io.avail = 0;                                                                 \
+    } while (0)
+#define STOPPED() (__shfl_sync(0xffffffffu, (int)rac.io.stop(), 0) != 0)
 
     if (!compress) {        // encoding.cpp:334-354
         for (int i = beginc; i <= endc; i++) {
             DChan &ch = img.ch[i];
             if (ch.minval == ch.maxval) continue;
             fill_plane(ch, i < img.n_orig ? 0 : ch.zero, lane);
-            for (int y = 0; y < ch.h; y++) {
-                if (io.stop()) break;
-                for (int x = 0; x < ch.w; x++) ch.data[(size_t)y * ch.w + x] = (int16_t)uniform_read(rac, ch.minval, ch.maxval - ch.minval);
-                publish_rows(ch, y + 1, lane);
+            if (lane == 0) {
+                for (int y = 0; y < ch.h; y++) {
+                    if (rac.io.stop()) break;
+                    for (int x = 0; x < ch.w; x++) ch.data[(size_t)y * ch.w + x] = (int16_t)uniform_read(rac, ch.minval, ch.maxval - ch.minval);
+                    st_release(&ch.rows_done, y + 1);
+                }
             }
-            if (io.stop()) break;
+            __syncwarp();
+            if (STOPPED()) break;
         }
         beginc = endc;
+        SYNC_IO();
         return true;
     }
 
-    int nnodes = 0;
-    if (!read_tree(rac, P.meta_table, pr, nprops, ws.nodes, nnodes, ws.stack, sm.coder)) return corrupt_or_truncated(io, img.ch[beginc], lane);
+    int nnodes = 0, tree_ok = 1;
+    if (lane == 0) tree_ok = read_tree(rac, P.meta_table, pr, nprops, ws.nodes, nnodes, ws.stack, sm.coder) ? 1 : 0;
+    tree_ok = __shfl_sync(0xffffffffu, tree_ok, 0);
+    nnodes = __shfl_sync(0xffffffffu, nnodes, 0);
+    if (!tree_ok) { const bool st = STOPPED(); SYNC_IO(); return corrupt_or_truncated(st, img.ch[beginc], lane); }
 
     // FinalPropertySymbolCoder ctor, compound.h:213-225: leaf numbering in node order, all leaves start from zero_chance
     const int nleaves = (nnodes + 1) / 2;
-    for (int i = 0, leafID = 0; i < nnodes; i++) if (ws.nodes[i].property == -1) ws.nodes[i].child = (unsigned short)leafID++;
-    __syncwarp();
-    for (int i = lane; i < nleaves * 32; i += 32) ws.leaves[i] = initial_chance(i & 31, predictability);
-    const bool nodes_in_smem = nnodes <= sm.node_cap;
-    if (P.debug && lane == 0) {
-        printf("[maniac]   tree %d nodes, nprops %d nref %d, zero_chance %d, pos %llu, %dx%d\n", nnodes, nprops, nref, predictability, io.pos, img.ch[beginc].w, img.ch[beginc].h);
-        for (int i = 0; i < nnodes && i < 8; i++) printf("[maniac]     node %d: prop %d child %d split %d\n", i, ws.nodes[i].property, ws.nodes[i].child, ws.nodes[i].splitval);
+    // shared-memory plan for this group: node cache (if it fits), then leaf lines
+    int dyn_off = 0;
+    uint2 *snodes = nullptr;
+    const int node_bytes = ((nnodes + 2) * 8 + 15) & ~15;
+    if (node_bytes + 64 * 8 + 64 <= sm.dyn_bytes) { snodes = reinterpret_cast<uint2 *>(sm.dyn); dyn_off = node_bytes; }
+    LeafStore ls;
+    ls.gleaves = ws.leaves;
+    const int rem = sm.dyn_bytes - dyn_off;
+    if (nleaves * 64 <= rem) {                  // every leaf resident
+        ls.lines = reinterpret_cast<uint16_t *>(sm.dyn + dyn_off); ls.tags = nullptr; ls.mask = 0;
+        for (int i = lane; i < nleaves * 32; i += 32) ls.lines[i] = initial_chance(i & 31, predictability);
+    } else {                                    // direct-mapped cache over the global leaf array
+        int nlines = 1;
+        while (nlines * 2 * 68 <= rem) nlines *= 2;
+        ls.tags = reinterpret_cast<int *>(sm.dyn + dyn_off);
+        ls.lines = reinterpret_cast<uint16_t *>(sm.dyn + dyn_off + ((nlines * 4 + 15) & ~15));
+        ls.mask = nlines - 1;
+        for (int i = lane; i < nlines; i += 32) ls.tags[i] = -1;
+        for (int i = lane; i < nleaves * 32; i += 32) ws.leaves[i] = initial_chance(i & 31, predictability);
     }
-    if (nodes_in_smem) {
-        const uint2 *src = reinterpret_cast<const uint2 *>(ws.nodes);
-        uint2 *dst = reinterpret_cast<uint2 *>(sm.nodes);
-        for (int i = lane; i < nnodes; i += 32) dst[i + 1] = src[i];
+    // node cache: packed entries, see struct LeafStore comment
+    uint2 *gpacked = reinterpret_cast<uint2 *>(ws.stack);      // the parse stack is free again: reuse it for the packed nodes
+    if (lane == 0) {
+        int leafID = 0;
+        for (int i = 0; i < nnodes; i++) {
+            const TNode nd = ws.nodes[i];
+            uint2 e;
+            if (nd.property == -1) { e.x = 0xFFFF0000u | (unsigned)leafID++; e.y = 0; }
+            else { e.x = ((unsigned)nd.property << 16) | (unsigned)((nd.child + 1) >> 1); e.y = (unsigned)nd.splitval; }
+            gpacked[i + 1] = e;
+        }
     }
     __syncwarp();
+    const uint2 *nodes2 = gpacked;
+    if (snodes) {
+        for (int i = lane; i < nnodes; i += 32) snodes[i + 1] = gpacked[i + 1];
+        nodes2 = snodes;
+    }
+    __syncwarp();
+    if (P.debug && lane == 0)
+        printf("[maniac]   tree %d nodes, nprops %d nref %d, zero_chance %d, pos %llu, %dx%d, nodes %s, leaves %s\n", nnodes, nprops, nref, predictability,
+               rac.io.pos, img.ch[beginc].w, img.ch[beginc].h, snodes ? "smem" : "global", ls.tags ? "cached" : "resident");
 
     for (int i = beginc; i <= endc; i++) {
         DChan &ch = img.ch[i];
@@ -667,52 +674,52 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
         // channel.resize(w,h): buffers made by meta_apply start out as `zero`, the Image constructor's as 0
         fill_plane(ch, i < img.n_orig ? 0 : ch.zero, lane);
         if (nnodes == 1 && predictor == 0 && ch.zero == 0) {        // fast track, encoding.cpp:371-383
-            for (int y = 0; y < ch.h; y++) {
-                if (io.stop()) break;
-                int16_t *row = ch.data + (size_t)y * ch.w;
-                for (int x0 = 0; x0 < ch.w; x0 += 32) {
-                    int outv = 0;
-                    const int cnt = min(32, ch.w - x0);
-                    for (int k = 0; k < cnt; k++) {
-                        const int v = read_int_reg(rac, sm.table, reinterpret_cast<uint4 *>(ws.leaves), ch.minval, ch.maxval);
-                        if (lane == k) outv = v;
-                    }
-                    if (x0 + lane < ch.w) row[x0 + lane] = (int16_t)outv;
+            uint16_t *lp = leaf_lookup(ls, 0, lane);
+            if (lane == 0) {
+                for (int y = 0; y < ch.h; y++) {
+                    if (rac.io.stop()) break;
+                    int16_t *row = ch.data + (size_t)y * ch.w;
+                    for (int x = 0; x < ch.w; x++) row[x] = (int16_t)read_int(rac, sm.table, lp, ch.minval, ch.maxval);
+                    st_release(&ch.rows_done, y + 1);
                 }
-                publish_rows(ch, y + 1, lane);
             }
+            __syncwarp();
         } else {
             for (int y = 0; y < ch.h; y++) {
-                if (io.stop()) break;
+                if (STOPPED()) break;
                 for (int r = 0; r < nrefchan; r++) {       // row wavefront on the planes this row back-references
                     const DChan &cj = img.ch[refchan[r]];
                     int ry = (y << ch.vshift) >> cj.vshift;
                     if (ry >= cj.h) ry = cj.h - 1;
                     spin_until_ge(&cj.rows_done, ry + 1);
                 }
-                decode_row(img, ch, y, predictor, refchan, nrefchan, nref, rac, sm, ws.nodes, nodes_in_smem, ws.leaves, lane);
+                decode_row(img, ch, y, predictor, refchan, nrefchan, nref, rac, sm, nodes2, ls, lane);
                 publish_rows(ch, y + 1, lane);
             }
         }
-        if (io.stop()) break;
+        if (STOPPED()) break;
     }
     beginc = endc;
+    SYNC_IO();
     return true;
+#undef SYNC_IO
+#undef STOPPED
 }
 
-__global__ void __launch_bounds__(32) k_maniac_decode(Params P) {
+__global__ void k_maniac_decode(Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint16_t *s_table = reinterpret_cast<uint16_t *>(smem_raw);                      // 16 KiB, shared by the block's warps
+    for (int i = threadIdx.x; i < 4096 * 2; i += blockDim.x) s_table[i] = P.table[i];
+    __syncthreads();
+    unsigned char *mine = smem_raw + 16384 + (size_t)warp * P.warp_smem;
     Smem sm;
-    sm.table = reinterpret_cast<uint16_t *>(smem_raw);                                    // 16 KiB
-    sm.coder = reinterpret_cast<uint16_t(*)[32]>(smem_raw + 16384);                       // 192 B
-    sm.crefs = reinterpret_cast<int16_t *>(smem_raw + 16384 + 256);                       // 32*20*2 = 1280 B
-    sm.nodes = reinterpret_cast<uint4 *>(smem_raw + 16384 + 256 + 1280);
-    sm.node_cap = P.node_cap;
-    sm.debug = P.debug;
-    for (int i = lane; i < 4096 * 2; i += 32) sm.table[i] = P.table[i];
-    __syncwarp();
-    WarpScratch ws = P.scratch[blockIdx.x];
+    sm.table = s_table;
+    sm.coder = reinterpret_cast<uint16_t(*)[32]>(mine);                               // 192 B
+    sm.cprop = reinterpret_cast<int *>(mine + 256);                                   // 32*37*4 = 4736 B
+    sm.dyn = mine + 256 + 4736;
+    sm.dyn_bytes = P.warp_smem - 256 - 4736;
+    WarpScratch ws = P.scratch[blockIdx.x * (blockDim.x >> 5) + warp];
     for (;;) {
         int sid = 0;
         if (lane == 0) sid = atomicAdd(P.ticket, 1);
@@ -941,7 +948,7 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         // streams are ordered image-major, groups ascending: dependencies always point to lower stream ids
         FB_CUDA(ctx, cudaMallocAsync((void **)&streams_dev, nstreams * sizeof(DStream), ctx->stream));
         FB_CUDA(ctx, cudaMemcpyAsync(streams_dev, streams.data(), nstreams * sizeof(DStream), cudaMemcpyHostToDevice, ctx->stream));
-        const int nslots = std::min(nstreams, ctx->sm_count * 8);
+        const int nslots = std::min((nstreams + 7) / 8 * 8, ctx->sm_count * 16);      // scratch slots: one per resident warp
         int rc = ensure_state(ctx, cutoff, alpha, nslots, maxw);
         if (rc) return rc;
         ManiacState *st = (ManiacState *)ctx->maniac_state;
@@ -950,18 +957,19 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         P.images = img_dev; P.streams = streams_dev; P.nstreams = nstreams; P.ticket = st->ticket_dev;
         P.table = st->table_dev; P.meta_table = st->meta_dev; P.scratch = st->scratch_dev; P.maxw = st->maxw;
         P.debug = getenv("FB_MANIAC_DEBUG") ? 1 : 0;
-        // shared memory per block (= per stream in flight): 16 KiB chance table + scratch + as much tree-node cache as the
-        // number of blocks per SM leaves room for
-        const int per_sm = (nslots + ctx->sm_count - 1) / ctx->sm_count;
-        size_t budget = (size_t)(220 * 1024) / per_sm;
-        budget = std::min<size_t>(budget, 200 * 1024);
-        const size_t fixed = 16384 + 256 + 1280;
-        if (budget < fixed + 4096) budget = fixed + 4096;
-        P.node_cap = (int)((budget - fixed) / sizeof(TNode)) - 2;
-        if (P.node_cap > kMaxNodes) P.node_cap = kMaxNodes;
-        const size_t smem_bytes = fixed + (size_t)(P.node_cap + 2) * sizeof(TNode);
+        // Launch shape.  Few streams (one image): one warp per block and block per SM with ~200 KiB of shared memory, so
+        // that the whole MANIAC tree and most leaf chances of a stream stay on-chip.  Many streams (batches): up to 8
+        // warps share a block's 16 KiB chance table and up to two blocks share an SM.
+        const int per_sm = (nstreams + ctx->sm_count - 1) / ctx->sm_count;
+        const int wpb = std::max(1, std::min(8, per_sm));
+        const int blocks_per_sm = std::max(1, std::min(2, (per_sm + wpb - 1) / wpb));
+        const int nblocks = std::min((nstreams + wpb - 1) / wpb, ctx->sm_count * blocks_per_sm);
+        const size_t block_smem = blocks_per_sm == 1 ? 200 * 1024 : 105 * 1024;
+        const size_t warp_smem = ((block_smem - 16384) / wpb) & ~(size_t)15;
+        P.warp_smem = (int)warp_smem;
+        const size_t smem_bytes = 16384 + warp_smem * wpb;
         FB_CUDA(ctx, cudaFuncSetAttribute(k_maniac_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        k_maniac_decode<<<nslots, 32, smem_bytes, ctx->stream>>>(P);
+        k_maniac_decode<<<nblocks, 32 * wpb, smem_bytes, ctx->stream>>>(P);
         ctx->launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { ctx->err = std::string("maniac launch: ") + cudaGetErrorString(e); return FB_ERR_CUDA; }
