@@ -60,6 +60,9 @@ void fb_plane_free(fb_ctx *ctx, int16_t *p);
 // inverse Squeeze steps (reference transform/squeeze.h:81-132, 173-224). res may be nullptr (all-zero residual).
 int fb_launch_inv_hsqueeze(fb_ctx *ctx, const int16_t *avg, const int16_t *res, int16_t *out, int wa, int wr, int h);
 int fb_launch_inv_vsqueeze(fb_ctx *ctx, const int16_t *avg, const int16_t *res, int16_t *out, int w, int ha, int hr);
+// one squeeze step over up to four planes in one launch (tiled kernels with warm-up + in-block verification)
+int fb_launch_inv_squeeze_batch(fb_ctx *ctx, int horizontal, int n, const int16_t *const *avg, const int16_t *const *res, int16_t *const *out,
+                                const int *wa, const int *wr, const int *ha, const int *hr);
 // forward Squeeze steps (squeeze.h:135-170, 227-263)
 int fb_launch_fwd_hsqueeze(fb_ctx *ctx, const int16_t *in, int16_t *avg, int16_t *res, int w, int h);
 int fb_launch_fwd_vsqueeze(fb_ctx *ctx, const int16_t *in, int16_t *avg, int16_t *res, int w, int h);

@@ -184,25 +184,36 @@ static int inv_squeeze(fb_image *img, const std::vector<int> &params) {
             ctx->err = "Invalid parameters for squeeze transform";
             return FB_ERR_INVALID;
         }
-        for (int c = beginc; c <= endc; c++) {
-            FbChan &a = img->ch[c];
-            FbChan &r = img->ch[offset + c - beginc];
-            // the averages must exist; a missing residual plane acts as zeros (squeeze.h:379-383)
-            int rc = chan_materialize(ctx, a);
+        // all planes of the step go into one launch (in groups of four)
+        for (int c0 = beginc; c0 <= endc; c0 += 4) {
+            const int n = std::min(4, endc - c0 + 1);
+            const int16_t *avgp[4], *resp[4];
+            int16_t *outp[4];
+            int wa[4], wr[4], ha[4], hr[4];
+            FbChan outs[4];
+            for (int k = 0; k < n; k++) {
+                FbChan &a = img->ch[c0 + k];
+                FbChan &r = img->ch[offset + c0 + k - beginc];
+                // the averages must exist; a missing residual plane acts as zeros (squeeze.h:379-383)
+                int rc = chan_materialize(ctx, a);
+                if (rc) return rc;
+                FbChan &out = outs[k];
+                out.d = a.d;
+                if (horizontal) { out.d.w = a.d.w + r.d.w; out.d.hshift--; out.d.hcshift--; }
+                else { out.d.h = a.d.h + r.d.h; out.d.vshift--; out.d.vcshift--; }
+                chan_setzero(out.d);
+                out.d.decoded = 1;
+                rc = fb_plane_alloc(ctx, chan_samples(out.d), &out.dev);
+                if (rc) return rc;
+                avgp[k] = a.dev; resp[k] = r.dev; outp[k] = out.dev;
+                wa[k] = a.d.w; wr[k] = r.d.w; ha[k] = a.d.h; hr[k] = r.d.h;
+            }
+            int rc = fb_launch_inv_squeeze_batch(ctx, horizontal ? 1 : 0, n, avgp, resp, outp, wa, wr, ha, hr);
             if (rc) return rc;
-            FbChan out;
-            out.d = a.d;
-            if (horizontal) { out.d.w = a.d.w + r.d.w; out.d.hshift--; out.d.hcshift--; }
-            else { out.d.h = a.d.h + r.d.h; out.d.vshift--; out.d.vcshift--; }
-            chan_setzero(out.d);
-            out.d.decoded = 1;
-            rc = fb_plane_alloc(ctx, chan_samples(out.d), &out.dev);
-            if (rc) return rc;
-            if (horizontal) rc = fb_launch_inv_hsqueeze(ctx, a.dev, r.dev, out.dev, a.d.w, r.d.w, a.d.h);
-            else rc = fb_launch_inv_vsqueeze(ctx, a.dev, r.dev, out.dev, a.d.w, a.d.h, r.d.h);
-            if (rc) return rc;
-            fb_plane_free(ctx, a.dev);
-            a = out;
+            for (int k = 0; k < n; k++) {
+                fb_plane_free(ctx, img->ch[c0 + k].dev);
+                img->ch[c0 + k] = outs[k];
+            }
         }
         for (int c = 0; c <= endc - beginc; c++) fb_plane_free(ctx, img->ch[offset + c].dev);
         img->ch.erase(img->ch.begin() + offset, img->ch.begin() + offset + (endc - beginc + 1));

@@ -243,11 +243,10 @@ __device__ int uniform_read(Rac &rac, int mn, int len) {    // UniformSymbolCode
 }
 
 // ---- context model (encoding/context_predict.h) ---------------------------------------------------------------------
-__device__ __forceinline__ int slog(int x16) {      // context_predict.h:54-61
-    int x = s16(x16);
-    if (x == 0) return 0;
-    if (x > 0) return 32 - __clz(x);
-    return -(32 - __clz(-x));
+__device__ __forceinline__ int slog(int x16) {      // context_predict.h:54-61 (branch-free: 32 - clz(0) == 0)
+    const int x = s16(x16);
+    const int b = 32 - __clz(abs(x));
+    return x < 0 ? -b : b;
 }
 __device__ __forceinline__ int fooabs(int x16) { int x = s16(x16); return s16(x < 0 ? -x : x); }   // :63-65
 
@@ -435,8 +434,15 @@ __device__ __forceinline__ uint16_t *leaf_lookup(const LeafStore &ls, int leaf, 
 // One row of a channel in the "slow track" (encoding.cpp:388-421), 32 pixels at a time.
 // Lane roles: lane k < nref holds reference property k, lane nref+j holds non-reference property j (0..12).
 // Returns through `rac` (meaningful in lane 0 only).
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+template <bool NODES_SMEM, bool PRED0>
 __device__ __forceinline__ void decode_row(DImage &img, DChan &ch, int y, int predictor, const int *refchan, int nrefchan, int nref,
                                            Rac &rac, const Smem &sm, const uint2 *nodes2, const LeafStore &ls, int lane) {
+    const unsigned nodes_saddr = NODES_SMEM ? (unsigned)__cvta_generic_to_shared(nodes2) : 0u;
     const int w = ch.w;
     int16_t *row = ch.data + (size_t)y * w;
     const int16_t *row1 = row - w, *row2 = row - 2 * w;
@@ -498,14 +504,18 @@ __device__ __forceinline__ void decode_row(DImage &img, DChan &ch, int y, int pr
                       q8 = slog(left - topleft), q9 = slog(topleft - top), q12 = slog(left - leftleft);
             mine = role == 1 ? q1 : mine;   mine = role == 3 ? q3 : mine;   mine = role == 6 ? q6 : mine;   mine = role == 7 ? q7 : mine;
             mine = role == 8 ? q8 : mine;   mine = role == 9 ? q9 : mine;   mine = role == 12 ? q12 : mine;
-            const int guess = predict(predictor, left, top, topleft, topright, zero, cmin, cmax);
+            const int guess = PRED0 ? zero : predict(predictor, left, top, topleft, topright, zero, cmin, cmax);
             const int mn = cmin - guess, mx = cmax - guess;
             int diff = mn;
             if (mn != mx) {
                 // find_leaf (compound.h:142-153): node values are warp-uniform, the tested property comes from its lane
-                uint2 cur = nodes2[1];
+                uint2 cur;
+                if (NODES_SMEM) { const uint4 r0 = lds128(nodes_saddr); cur = make_uint2(r0.z, r0.w); }     // node 0 lives in slot 1
+                else cur = nodes2[1];
                 while ((int)cur.x >= 0) {
-                    const uint4 pair = reinterpret_cast<const uint4 *>(nodes2)[cur.x & 0xffffu];
+                    uint4 pair;
+                    if (NODES_SMEM) pair = lds128(nodes_saddr + ((cur.x & 0xffffu) << 4));
+                    else pair = reinterpret_cast<const uint4 *>(nodes2)[cur.x & 0xffffu];
                     const int v = __shfl_sync(0xffffffffu, mine, (int)(cur.x >> 16));
                     cur = (v > (int)cur.y) ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
                 }
@@ -693,7 +703,13 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
                     if (ry >= cj.h) ry = cj.h - 1;
                     spin_until_ge(&cj.rows_done, ry + 1);
                 }
-                decode_row(img, ch, y, predictor, refchan, nrefchan, nref, rac, sm, nodes2, ls, lane);
+                if (snodes) {
+                    if (predictor == 0) decode_row<true, true>(img, ch, y, predictor, refchan, nrefchan, nref, rac, sm, nodes2, ls, lane);
+                    else decode_row<true, false>(img, ch, y, predictor, refchan, nrefchan, nref, rac, sm, nodes2, ls, lane);
+                } else {
+                    if (predictor == 0) decode_row<false, true>(img, ch, y, predictor, refchan, nrefchan, nref, rac, sm, nodes2, ls, lane);
+                    else decode_row<false, false>(img, ch, y, predictor, refchan, nrefchan, nref, rac, sm, nodes2, ls, lane);
+                }
                 publish_rows(ch, y + 1, lane);
             }
         }

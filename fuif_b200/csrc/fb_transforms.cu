@@ -6,6 +6,8 @@
 // and an add into an FMA: the reference is built for baseline x86-64 and rounds after every operation.
 #include "fb_common.cuh"
 
+#include <algorithm>
+
 namespace {
 
 __device__ __forceinline__ int s16(int x) { return (int)(short)x; }
@@ -88,6 +90,207 @@ __global__ void k_inv_vsqueeze_cols(const int16_t *__restrict__ avg, const int16
         av = nx;
     }
     if (ho & 1) out[(size_t)(ho - 1) * w + x] = avg[(size_t)(ha - 1) * w + x];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Tiled unsqueeze kernels.
+//
+// The inverse is a serial recurrence along the squeeze axis: the tendency of pair x needs B of pair x-1
+// (squeeze.h:104, :208).  The carried state is ONE int16, and the recurrence forgets its start within a few pairs
+// (SURVEY F6), so every chain is cut into segments that start K pairs early from a guessed state ("warm-up").  A
+// segment is exact iff the state it reached at its first pair equals the true last B of the segment before it; that
+// is checked inside the block and, on a mismatch, the segment is recomputed from the true state (and its successors
+// re-checked) until every segment agrees with its predecessor.  Segment 0 starts at the true chain start, so by
+// induction the result is bit-exact regardless of how good the guess was.
+// ---------------------------------------------------------------------------------------------------------
+
+// unsqueeze_pair with the tendency in closed form.  With t1 = B-a, t2 = a-n, a1=|t1|, a2=|t2|:
+//   monotone (t1, t2 of one sign):  |tendency| = min((4*a1+3*a2+6)/12, 2*a1+1, 2*a2), sign = sign(t1+t2)
+// which is squeeze.h:63-75 with both clamps folded into a min (d-(d&1) > 2k  <=>  d >= 2k+2;  d+(d&1) > 2k  <=>  d >= 2k+1).
+// The closed form assumes no int16 wrap inside smooth_tendency, guaranteed for a1, a2 <= 16383; anything larger takes
+// the literal path.
+__device__ __forceinline__ void unsqueeze_pair_fast(int prev, int av, int nx, int rs, int &A, int &B) {
+    const int t1 = prev - av, t2 = av - nx;
+    const int a1 = abs(t1), a2 = abs(t2);
+    if ((a1 | a2) > 16383) { unsqueeze_pair(prev, av, nx, rs, A, B); return; }
+    const unsigned m = (unsigned)(4 * a1 + 3 * a2 + 6);
+    const int q = (int)(__umulhi(m, 0xAAAAAAABu) >> 3);        // m / 12
+    int d = min(min(q, 2 * a1 + 1), 2 * a2);
+    const bool mono = ((t1 ^ t2) >= 0) | (t1 == 0);
+    d = (t1 + t2) < 0 ? -d : d;
+    const int tendency = mono ? d : 0;
+    const int diff = s16(rs + tendency);
+    A = s16(av + ((diff - (diff >> 31)) >> 1));                 // (2a + diff -+ (diff&1)) >> 1  ==  a + trunc(diff/2)
+    B = s16(A - diff);
+}
+
+struct SqJob {
+    const int16_t *avg, *res;   // res == nullptr: all-zero residual
+    int16_t *out;
+    int wa, wr;                 // horizontal: widths of avg / res planes; vertical: wa = width, wr unused
+    int ha, hr;                 // horizontal: ha = rows; vertical: heights of avg / res planes
+    int blocks;                 // blocks assigned to this job
+};
+struct SqJobs { SqJob j[4]; int n; };
+
+constexpr int kSegP = 33;       // pairs per segment: odd => conflict-free shared-memory columns
+constexpr int kWarm = 12;       // warm-up pairs (the recurrence re-joins the exact chain within <= 7 pairs in practice)
+
+// Horizontal: a block owns R complete rows of one plane.  thread = (row, segment).
+__global__ void k_inv_hsqueeze_tiled(SqJobs jobs, int R, int threads_per_row) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    int b = blockIdx.x, ji = 0;
+    while (ji < jobs.n - 1 && b >= jobs.j[ji].blocks) { b -= jobs.j[ji].blocks; ji++; }
+    const SqJob J = jobs.j[ji];
+    const int wa = J.wa, wr = J.wr, wo = wa + wr, h = J.ha;
+    const int y0 = b * R;
+    const int rows = min(R, h - y0);
+    if (rows <= 0) return;
+    const int PA = wa + 2, PR = wr + 2;             // halfword pitches of the staged rows
+    int16_t *avgS = reinterpret_cast<int16_t *>(smraw);
+    int16_t *resS = avgS + R * PA;
+    unsigned *outS = reinterpret_cast<unsigned *>(smraw + (((size_t)R * (PA + PR) * 2 + 15) & ~(size_t)15));
+    int16_t *bfS = reinterpret_cast<int16_t *>(outS + (size_t)R * wr);      // [R][nseg] final B of every segment
+    const int nseg = (wr + kSegP - 1) / kSegP;
+    // ---- stage the rows (coalesced)
+    for (int r = 0; r < rows; r++) {
+        const int16_t *ga = J.avg + (size_t)(y0 + r) * wa;
+        for (int i = threadIdx.x; i < wa; i += blockDim.x) avgS[r * PA + i] = ga[i];
+        if (J.res) {
+            const int16_t *gr = J.res + (size_t)(y0 + r) * wr;
+            for (int i = threadIdx.x; i < wr; i += blockDim.x) resS[r * PR + i] = gr[i];
+        } else {
+            for (int i = threadIdx.x; i < wr; i += blockDim.x) resS[r * PR + i] = 0;
+        }
+    }
+    __syncthreads();
+    const int r = threadIdx.x / threads_per_row, sgm = threadIdx.x % threads_per_row;
+    const bool active = r < rows && sgm < nseg;
+    const int xs = sgm * kSegP, xe = min(xs + kSegP, wr);
+    int bw = 0, bf = 0;     // state assumed at xs (from the warm-up) / state after the last pair
+    const int16_t *a = avgS + r * PA, *rr = resS + r * PR;
+    unsigned *o = outS + (size_t)r * wr;
+    auto run = [&](int from, int prev_in, bool exact_start) {
+        int prev = prev_in;
+        int av = a[from];
+        for (int x = from; x < xe; x++) {
+            const int nx = (x + 1 < wa) ? a[x + 1] : av;
+            int A, B;
+            unsqueeze_pair_fast((x == 0 || (!exact_start && x == from)) ? av : prev, av, nx, rr[x], A, B);
+            if (x == xs) bw = (x == from && !exact_start) ? av : prev;   // state consumed by the first owned pair
+            if (x >= xs) o[x] = (unsigned)(uint16_t)A | ((unsigned)(uint16_t)B << 16);
+            prev = B;
+            av = nx;
+        }
+        bf = prev;
+    };
+    if (active) {
+        const int from = max(0, xs - kWarm);
+        run(from, 0, false);
+        if (from == 0) bw = 0x7fffffff;          // exact by construction
+        bfS[r * nseg + sgm] = (int16_t)bf;
+    }
+    __syncthreads();
+    // ---- verify / repair until every segment started from its predecessor's true final state
+    for (;;) {
+        bool bad = false;
+        int want = 0;
+        if (active && sgm > 0 && bw != 0x7fffffff) {
+            want = bfS[r * nseg + sgm - 1];
+            bad = (want != (int)(int16_t)bw);
+        }
+        if (!__syncthreads_or(bad)) break;
+        if (bad) {
+            bw = want;
+            // restart exactly at xs with the true state
+            int prev = want, av = a[xs];
+            for (int x = xs; x < xe; x++) {
+                const int nx = (x + 1 < wa) ? a[x + 1] : av;
+                int A, B;
+                unsqueeze_pair_fast(prev, av, nx, rr[x], A, B);
+                o[x] = (unsigned)(uint16_t)A | ((unsigned)(uint16_t)B << 16);
+                prev = B;
+                av = nx;
+            }
+            bfS[r * nseg + sgm] = (int16_t)prev;
+        }
+        __syncthreads();
+    }
+    // ---- store (coalesced); odd tail column is a copy of the last average (squeeze.h:129)
+    for (int q = 0; q < rows; q++) {
+        int16_t *go = J.out + (size_t)(y0 + q) * wo;
+        const unsigned *so = outS + (size_t)q * wr;
+        if ((((size_t)(y0 + q) * wo) & 1) == 0) {
+            unsigned *go32 = reinterpret_cast<unsigned *>(go);
+            for (int i = threadIdx.x; i < wr; i += blockDim.x) go32[i] = so[i];
+        } else {
+            for (int i = threadIdx.x; i < 2 * wr; i += blockDim.x) go[i] = (int16_t)((so[i >> 1] >> ((i & 1) * 16)) & 0xffff);
+        }
+        if ((wo & 1) && threadIdx.x == 0) go[wo - 1] = avgS[q * PA + wa - 1];
+    }
+}
+
+// Vertical: a block owns 32 complete columns of one plane.  thread = (column, segment along y); lanes = columns.
+__global__ void k_inv_vsqueeze_tiled(SqJobs jobs, int nseg, int segp) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    int16_t *bfS = reinterpret_cast<int16_t *>(smraw);          // [nseg][32]
+    int b = blockIdx.x, ji = 0;
+    while (ji < jobs.n - 1 && b >= jobs.j[ji].blocks) { b -= jobs.j[ji].blocks; ji++; }
+    const SqJob J = jobs.j[ji];
+    const int w = J.wa, ha = J.ha, hr = J.hr, ho = ha + hr;
+    const int x = b * 32 + (threadIdx.x & 31);
+    const int sgm = threadIdx.x >> 5;
+    const bool active = x < w && sgm < nseg && sgm * segp < hr;
+    const int ys = sgm * segp, ye = min(ys + segp, hr);
+    const int16_t *a = J.avg + x, *rr = J.res ? J.res + x : nullptr;
+    int16_t *o = J.out + x;
+    int bw = 0, bf = 0;
+    if (active) {
+        const int from = max(0, ys - kWarm);
+        int prev = 0;
+        int av = a[(size_t)from * w];
+        for (int y = from; y < ye; y++) {
+            const int nx = (y + 1 < ha) ? a[(size_t)(y + 1) * w] : av;
+            const int rs = rr ? rr[(size_t)y * w] : 0;
+            int A, B;
+            unsqueeze_pair_fast((y == from) ? av : prev, av, nx, rs, A, B);
+            if (y == ys) bw = (y == from) ? av : prev;
+            if (y >= ys) { o[(size_t)(2 * y) * w] = (int16_t)A; o[(size_t)(2 * y + 1) * w] = (int16_t)B; }
+            prev = B;
+            av = nx;
+        }
+        bf = prev;
+        if (from == 0) bw = 0x7fffffff;
+        bfS[sgm * 32 + (threadIdx.x & 31)] = (int16_t)bf;
+    }
+    __syncthreads();
+    for (;;) {
+        bool bad = false;
+        int want = 0;
+        if (active && sgm > 0 && bw != 0x7fffffff) {
+            want = bfS[(sgm - 1) * 32 + (threadIdx.x & 31)];
+            bad = (want != (int)(int16_t)bw);
+        }
+        if (!__syncthreads_or(bad)) break;
+        if (bad) {
+            bw = want;
+            int prev = want, av = a[(size_t)ys * w];
+            for (int y = ys; y < ye; y++) {
+                const int nx = (y + 1 < ha) ? a[(size_t)(y + 1) * w] : av;
+                const int rs = rr ? rr[(size_t)y * w] : 0;
+                int A, B;
+                unsqueeze_pair_fast(prev, av, nx, rs, A, B);
+                o[(size_t)(2 * y) * w] = (int16_t)A;
+                o[(size_t)(2 * y + 1) * w] = (int16_t)B;
+                prev = B;
+                av = nx;
+            }
+            bfS[sgm * 32 + (threadIdx.x & 31)] = (int16_t)prev;
+        }
+        __syncthreads();
+    }
+    // odd tail row: copy of the last average row (squeeze.h:217-222)
+    if ((ho & 1) && x < w && sgm == 0) o[(size_t)(ho - 1) * w] = a[(size_t)(ha - 1) * w];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -352,6 +555,71 @@ int fb_launch_inv_hsqueeze(fb_ctx *ctx, const int16_t *avg, const int16_t *res, 
 int fb_launch_inv_vsqueeze(fb_ctx *ctx, const int16_t *avg, const int16_t *res, int16_t *out, int w, int ha, int hr) {
     if (w <= 0 || ha <= 0) return FB_OK;
     k_inv_vsqueeze_cols<<<nblocks(w, 64), 64, 0, ctx->stream>>>(avg, res, out, w, ha, hr);
+    FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}
+// Batched launch: up to four planes of one squeeze step in one kernel.
+int fb_launch_inv_squeeze_batch(fb_ctx *ctx, int horizontal, int n, const int16_t *const *avg, const int16_t *const *res, int16_t *const *out,
+                                const int *wa, const int *wr, const int *ha, const int *hr) {
+    if (n <= 0) return FB_OK;
+    if (n > 4) return FB_ERR_INVALID;
+    SqJobs jobs;
+    jobs.n = 0;
+    int total = 0;
+    if (horizontal) {
+        int maxwr = 0, maxwa = 0;
+        for (int i = 0; i < n; i++) { maxwr = std::max(maxwr, wr[i]); maxwa = std::max(maxwa, wa[i]); }
+        const int nseg = std::max(1, (maxwr + kSegP - 1) / kSegP);
+        int tpr = nseg;                                     // threads per row
+        if (tpr > 1024) { ctx->err = "plane too wide for the tiled unsqueeze"; return FB_ERR_UNSUPPORTED; }
+        int R = std::max(1, 256 / tpr);
+        auto smem_for = [&](int r) { return (((size_t)r * (maxwa + 2 + maxwr + 2) * 2 + 15) & ~(size_t)15) + (size_t)r * maxwr * 4 + (size_t)r * nseg * 2 + 16; };
+        while (R > 1 && smem_for(R) > 100 * 1024) R--;
+        if (smem_for(R) > 200 * 1024) { ctx->err = "plane too wide for the tiled unsqueeze"; return FB_ERR_UNSUPPORTED; }
+        for (int i = 0; i < n; i++) {
+            if (ha[i] <= 0 || wa[i] <= 0) continue;
+            if (wr[i] == 0) {       // nothing to merge: the output is the average plane (see k_inv_hsqueeze_rows)
+                k_inv_hsqueeze_rows<<<nblocks(ha[i], 64), 64, 0, ctx->stream>>>(avg[i], res[i], out[i], wa[i], wr[i], ha[i]);
+                ctx->launches++;
+                continue;
+            }
+            SqJob &J = jobs.j[jobs.n++];
+            J.avg = avg[i]; J.res = res[i]; J.out = out[i]; J.wa = wa[i]; J.wr = wr[i]; J.ha = ha[i]; J.hr = 0;
+            J.blocks = (ha[i] + R - 1) / R;
+            total += J.blocks;
+        }
+        if (!jobs.n) return FB_OK;
+        const size_t smem = smem_for(R);
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            FB_CUDA(ctx, cudaFuncSetAttribute(k_inv_hsqueeze_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured = 200 * 1024;
+        }
+        int threads = R * tpr;
+        threads = (threads + 31) / 32 * 32;
+        k_inv_hsqueeze_tiled<<<total, threads, smem, ctx->stream>>>(jobs, R, tpr);
+    } else {
+        int maxhr = 0;
+        for (int i = 0; i < n; i++) maxhr = std::max(maxhr, hr[i]);
+        // segments along y: at most 32 per block (1024 threads), at least kSegP pairs each
+        int segp = kSegP;
+        while ((maxhr + segp - 1) / segp > 32) segp += kSegP;
+        const int nseg = std::max(1, (maxhr + segp - 1) / segp);
+        for (int i = 0; i < n; i++) {
+            if (ha[i] <= 0 || wa[i] <= 0) continue;
+            if (hr[i] == 0) {
+                k_inv_vsqueeze_cols<<<nblocks(wa[i], 64), 64, 0, ctx->stream>>>(avg[i], res[i], out[i], wa[i], ha[i], hr[i]);
+                ctx->launches++;
+                continue;
+            }
+            SqJob &J = jobs.j[jobs.n++];
+            J.avg = avg[i]; J.res = res[i]; J.out = out[i]; J.wa = wa[i]; J.wr = 0; J.ha = ha[i]; J.hr = hr[i];
+            J.blocks = (wa[i] + 31) / 32;
+            total += J.blocks;
+        }
+        if (!jobs.n) return FB_OK;
+        k_inv_vsqueeze_tiled<<<total, 32 * nseg, (size_t)nseg * 32 * 2 + 16, ctx->stream>>>(jobs, nseg, segp);
+    }
     FB_LAUNCH_CHECK(ctx);
     return FB_OK;
 }
