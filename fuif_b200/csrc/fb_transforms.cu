@@ -137,6 +137,10 @@ constexpr int kSegP = 33;       // pairs per segment: odd => conflict-free share
 constexpr int kWarm = 12;       // warm-up pairs (the recurrence re-joins the exact chain within <= 7 pairs in practice)
 
 // Horizontal: a block owns R complete rows of one plane.  thread = (row, segment).
+// Shared memory: staged averages [R][PA] (+1 sentinel = last average, so that "next average" needs no bounds test),
+// staged residuals [R][PR], output words (A | B<<16) [R][wr], final state per segment [R][nseg].
+__device__ __forceinline__ int sq_round8(int v) { return (v + 7) & ~7; }
+
 __global__ void k_inv_hsqueeze_tiled(SqJobs jobs, int R, int threads_per_row) {
     extern __shared__ __align__(16) unsigned char smraw[];
     int b = blockIdx.x, ji = 0;
@@ -146,48 +150,74 @@ __global__ void k_inv_hsqueeze_tiled(SqJobs jobs, int R, int threads_per_row) {
     const int y0 = b * R;
     const int rows = min(R, h - y0);
     if (rows <= 0) return;
-    const int PA = wa + 2, PR = wr + 2;             // halfword pitches of the staged rows
+    const int PA = sq_round8(wa) + 8, PR = sq_round8(wr) + 8;       // halfword pitches (16-byte multiples)
     int16_t *avgS = reinterpret_cast<int16_t *>(smraw);
     int16_t *resS = avgS + R * PA;
-    unsigned *outS = reinterpret_cast<unsigned *>(smraw + (((size_t)R * (PA + PR) * 2 + 15) & ~(size_t)15));
+    unsigned *outS = reinterpret_cast<unsigned *>(resS + R * PR);
     int16_t *bfS = reinterpret_cast<int16_t *>(outS + (size_t)R * wr);      // [R][nseg] final B of every segment
     const int nseg = (wr + kSegP - 1) / kSegP;
-    // ---- stage the rows (coalesced)
-    for (int r = 0; r < rows; r++) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    // ---- stage the rows: one warp per row at a time, 16-byte loads when the row is 16-byte aligned
+    for (int r = warp; r < rows; r += nwarps) {
         const int16_t *ga = J.avg + (size_t)(y0 + r) * wa;
-        for (int i = threadIdx.x; i < wa; i += blockDim.x) avgS[r * PA + i] = ga[i];
+        int16_t *sa = avgS + r * PA;
+        if ((wa & 7) == 0) {
+            for (int c = lane * 8; c < wa; c += 256) *reinterpret_cast<uint4 *>(sa + c) = *reinterpret_cast<const uint4 *>(ga + c);
+        } else {
+            for (int c = lane; c < wa; c += 32) sa[c] = ga[c];
+        }
+        int16_t *sr = resS + r * PR;
         if (J.res) {
             const int16_t *gr = J.res + (size_t)(y0 + r) * wr;
-            for (int i = threadIdx.x; i < wr; i += blockDim.x) resS[r * PR + i] = gr[i];
+            if ((wr & 7) == 0) {
+                for (int c = lane * 8; c < wr; c += 256) *reinterpret_cast<uint4 *>(sr + c) = *reinterpret_cast<const uint4 *>(gr + c);
+            } else {
+                for (int c = lane; c < wr; c += 32) sr[c] = gr[c];
+            }
         } else {
-            for (int i = threadIdx.x; i < wr; i += blockDim.x) resS[r * PR + i] = 0;
+            for (int c = lane; c < wr; c += 32) sr[c] = 0;
         }
     }
     __syncthreads();
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) avgS[r * PA + wa] = avgS[r * PA + wa - 1];     // sentinel
+    __syncthreads();
+
     const int r = threadIdx.x / threads_per_row, sgm = threadIdx.x % threads_per_row;
     const bool active = r < rows && sgm < nseg;
     const int xs = sgm * kSegP, xe = min(xs + kSegP, wr);
-    int bw = 0, bf = 0;     // state assumed at xs (from the warm-up) / state after the last pair
     const int16_t *a = avgS + r * PA, *rr = resS + r * PR;
     unsigned *o = outS + (size_t)r * wr;
-    auto run = [&](int from, int prev_in, bool exact_start) {
-        int prev = prev_in;
-        int av = a[from];
-        for (int x = from; x < xe; x++) {
-            const int nx = (x + 1 < wa) ? a[x + 1] : av;
+    int bw = 0x7fffffff;    // state the first owned pair consumed (0x7fffffff: the true chain start, exact by construction)
+    // main pass over [xs, xe) from a given state; used by the first pass and by repairs
+    auto owned = [&](int prev, bool first_is_chain_start) {
+        int av = a[xs];
+        if (first_is_chain_start) prev = av;            // x == 0: left = avg (squeeze.h:84-89)
+        for (int x = xs; x < xe; x++) {
+            const int nx = a[x + 1];
             int A, B;
-            unsqueeze_pair_fast((x == 0 || (!exact_start && x == from)) ? av : prev, av, nx, rr[x], A, B);
-            if (x == xs) bw = (x == from && !exact_start) ? av : prev;   // state consumed by the first owned pair
-            if (x >= xs) o[x] = (unsigned)(uint16_t)A | ((unsigned)(uint16_t)B << 16);
+            unsqueeze_pair_fast(prev, av, nx, rr[x], A, B);
+            o[x] = (unsigned)(uint16_t)A | ((unsigned)(uint16_t)B << 16);
             prev = B;
             av = nx;
         }
-        bf = prev;
+        return prev;
     };
     if (active) {
-        const int from = max(0, xs - kWarm);
-        run(from, 0, false);
-        if (from == 0) bw = 0x7fffffff;          // exact by construction
+        int bf;
+        if (xs == 0) bf = owned(0, true);
+        else {
+            const int from = xs - kWarm;                // xs >= kSegP > kWarm
+            int av = a[from], prev = av;                // guessed state
+            for (int x = from; x < xs; x++) {
+                const int nx = a[x + 1];
+                int A, B;
+                unsqueeze_pair_fast(prev, av, nx, rr[x], A, B);
+                prev = B;
+                av = nx;
+            }
+            bw = prev;
+            bf = owned(prev, false);
+        }
         bfS[r * nseg + sgm] = (int16_t)bf;
     }
     __syncthreads();
@@ -195,38 +225,30 @@ __global__ void k_inv_hsqueeze_tiled(SqJobs jobs, int R, int threads_per_row) {
     for (;;) {
         bool bad = false;
         int want = 0;
-        if (active && sgm > 0 && bw != 0x7fffffff) {
+        if (active && sgm > 0) {
             want = bfS[r * nseg + sgm - 1];
-            bad = (want != (int)(int16_t)bw);
+            bad = (want != bw);
         }
         if (!__syncthreads_or(bad)) break;
         if (bad) {
             bw = want;
-            // restart exactly at xs with the true state
-            int prev = want, av = a[xs];
-            for (int x = xs; x < xe; x++) {
-                const int nx = (x + 1 < wa) ? a[x + 1] : av;
-                int A, B;
-                unsqueeze_pair_fast(prev, av, nx, rr[x], A, B);
-                o[x] = (unsigned)(uint16_t)A | ((unsigned)(uint16_t)B << 16);
-                prev = B;
-                av = nx;
-            }
-            bfS[r * nseg + sgm] = (int16_t)prev;
+            bfS[r * nseg + sgm] = (int16_t)owned(want, false);
         }
         __syncthreads();
     }
     // ---- store (coalesced); odd tail column is a copy of the last average (squeeze.h:129)
-    for (int q = 0; q < rows; q++) {
-        int16_t *go = J.out + (size_t)(y0 + q) * wo;
-        const unsigned *so = outS + (size_t)q * wr;
-        if ((((size_t)(y0 + q) * wo) & 1) == 0) {
-            unsigned *go32 = reinterpret_cast<unsigned *>(go);
-            for (int i = threadIdx.x; i < wr; i += blockDim.x) go32[i] = so[i];
-        } else {
-            for (int i = threadIdx.x; i < 2 * wr; i += blockDim.x) go[i] = (int16_t)((so[i >> 1] >> ((i & 1) * 16)) & 0xffff);
+    if ((wo & 7) == 0) {        // rows are contiguous and 16-byte aligned in both memories
+        const uint4 *so = reinterpret_cast<const uint4 *>(outS);
+        uint4 *go = reinterpret_cast<uint4 *>(J.out + (size_t)y0 * wo);
+        const int n16 = rows * wr / 4;
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) go[i] = so[i];
+    } else {
+        for (int q = warp; q < rows; q += nwarps) {
+            int16_t *go = J.out + (size_t)(y0 + q) * wo;
+            const unsigned *so = outS + (size_t)q * wr;
+            for (int i = lane; i < 2 * wr; i += 32) go[i] = (int16_t)((so[i >> 1] >> ((i & 1) * 16)) & 0xffff);
+            if ((wo & 1) && lane == 0) go[wo - 1] = avgS[q * PA + wa - 1];
         }
-        if ((wo & 1) && threadIdx.x == 0) go[wo - 1] = avgS[q * PA + wa - 1];
     }
 }
 
@@ -244,48 +266,60 @@ __global__ void k_inv_vsqueeze_tiled(SqJobs jobs, int nseg, int segp) {
     const int ys = sgm * segp, ye = min(ys + segp, hr);
     const int16_t *a = J.avg + x, *rr = J.res ? J.res + x : nullptr;
     int16_t *o = J.out + x;
-    int bw = 0, bf = 0;
-    if (active) {
-        const int from = max(0, ys - kWarm);
-        int prev = 0;
-        int av = a[(size_t)from * w];
-        for (int y = from; y < ye; y++) {
-            const int nx = (y + 1 < ha) ? a[(size_t)(y + 1) * w] : av;
-            const int rs = rr ? rr[(size_t)y * w] : 0;
+    int bw = 0x7fffffff;
+    auto owned = [&](int prev, bool first_is_chain_start) {
+        int av = a[(size_t)ys * w];
+        if (first_is_chain_start) prev = av;
+        const int16_t *pa = a + (size_t)(ys + 1) * w;
+        const int16_t *pr = rr ? rr + (size_t)ys * w : nullptr;
+        int16_t *po = o + (size_t)(2 * ys) * w;
+#pragma unroll 4
+        for (int y = ys; y < ye; y++) {
+            const int nx = (y + 1 < ha) ? *pa : av;
+            const int rs = pr ? *pr : 0;
             int A, B;
-            unsqueeze_pair_fast((y == from) ? av : prev, av, nx, rs, A, B);
-            if (y == ys) bw = (y == from) ? av : prev;
-            if (y >= ys) { o[(size_t)(2 * y) * w] = (int16_t)A; o[(size_t)(2 * y + 1) * w] = (int16_t)B; }
+            unsqueeze_pair_fast(prev, av, nx, rs, A, B);
+            po[0] = (int16_t)A;
+            po[w] = (int16_t)B;
             prev = B;
             av = nx;
+            pa += w; po += 2 * (size_t)w;
+            if (pr) pr += w;
         }
-        bf = prev;
-        if (from == 0) bw = 0x7fffffff;
+        return prev;
+    };
+    if (active) {
+        int bf;
+        if (ys == 0) bf = owned(0, true);
+        else {
+            const int from = ys - kWarm;
+            int av = a[(size_t)from * w], prev = av;
+#pragma unroll 4
+            for (int y = from; y < ys; y++) {
+                const int nx = a[(size_t)(y + 1) * w];     // y + 1 <= ys < hr <= ha
+                const int rs = rr ? rr[(size_t)y * w] : 0;
+                int A, B;
+                unsqueeze_pair_fast(prev, av, nx, rs, A, B);
+                prev = B;
+                av = nx;
+            }
+            bw = prev;
+            bf = owned(prev, false);
+        }
         bfS[sgm * 32 + (threadIdx.x & 31)] = (int16_t)bf;
     }
     __syncthreads();
     for (;;) {
         bool bad = false;
         int want = 0;
-        if (active && sgm > 0 && bw != 0x7fffffff) {
+        if (active && sgm > 0) {
             want = bfS[(sgm - 1) * 32 + (threadIdx.x & 31)];
-            bad = (want != (int)(int16_t)bw);
+            bad = (want != bw);
         }
         if (!__syncthreads_or(bad)) break;
         if (bad) {
             bw = want;
-            int prev = want, av = a[(size_t)ys * w];
-            for (int y = ys; y < ye; y++) {
-                const int nx = (y + 1 < ha) ? a[(size_t)(y + 1) * w] : av;
-                const int rs = rr ? rr[(size_t)y * w] : 0;
-                int A, B;
-                unsqueeze_pair_fast(prev, av, nx, rs, A, B);
-                o[(size_t)(2 * y) * w] = (int16_t)A;
-                o[(size_t)(2 * y + 1) * w] = (int16_t)B;
-                prev = B;
-                av = nx;
-            }
-            bfS[sgm * 32 + (threadIdx.x & 31)] = (int16_t)prev;
+            bfS[sgm * 32 + (threadIdx.x & 31)] = (int16_t)owned(want, false);
         }
         __syncthreads();
     }
@@ -573,7 +607,7 @@ int fb_launch_inv_squeeze_batch(fb_ctx *ctx, int horizontal, int n, const int16_
         int tpr = nseg;                                     // threads per row
         if (tpr > 1024) { ctx->err = "plane too wide for the tiled unsqueeze"; return FB_ERR_UNSUPPORTED; }
         int R = std::max(1, 256 / tpr);
-        auto smem_for = [&](int r) { return (((size_t)r * (maxwa + 2 + maxwr + 2) * 2 + 15) & ~(size_t)15) + (size_t)r * maxwr * 4 + (size_t)r * nseg * 2 + 16; };
+        auto smem_for = [&](int r) { return (size_t)r * (((maxwa + 7) & ~7) + 8 + ((maxwr + 7) & ~7) + 8) * 2 + (size_t)r * maxwr * 4 + (size_t)r * nseg * 2 + 16; };
         while (R > 1 && smem_for(R) > 100 * 1024) R--;
         if (smem_for(R) > 200 * 1024) { ctx->err = "plane too wide for the tiled unsqueeze"; return FB_ERR_UNSUPPORTED; }
         for (int i = 0; i < n; i++) {
