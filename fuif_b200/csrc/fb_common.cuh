@@ -63,6 +63,14 @@ int fb_launch_inv_vsqueeze(fb_ctx *ctx, const int16_t *avg, const int16_t *res, 
 // one squeeze step over up to four planes in one launch (tiled kernels with warm-up + in-block verification)
 int fb_launch_inv_squeeze_batch(fb_ctx *ctx, int horizontal, int n, const int16_t *const *avg, const int16_t *const *res, int16_t *const *out,
                                 const int *wa, const int *wr, const int *ha, const int *hr);
+// a planned unsqueeze step on one plane (all buffers already allocated); ops are listed in execution order
+struct FbSqOp {
+    int step, horizontal;
+    const int16_t *avg, *res;
+    int16_t *out;
+    int wa, wr, ha, hr;
+};
+int fb_run_inv_squeeze_plan(fb_ctx *ctx, const std::vector<FbSqOp> &ops);
 // forward Squeeze steps (squeeze.h:135-170, 227-263)
 int fb_launch_fwd_hsqueeze(fb_ctx *ctx, const int16_t *in, int16_t *avg, int16_t *res, int w, int h);
 int fb_launch_fwd_vsqueeze(fb_ctx *ctx, const int16_t *in, int16_t *avg, int16_t *res, int w, int h);

@@ -176,49 +176,45 @@ static int inv_squeeze(fb_image *img, const std::vector<int> &params) {
     fb_ctx *ctx = img->ctx;
     std::vector<int> p = params;
     if (p.empty()) default_squeeze_parameters(p, img);
-    for (int i = (int)p.size() - 3; i >= 0; i -= 3) {
+    // Pass 1: channel-list surgery and allocation, exactly in the reference's order; the kernels are only planned.
+    std::vector<FbSqOp> ops;
+    std::vector<int16_t *> to_free;
+    int step = 0;
+    for (int i = (int)p.size() - 3; i >= 0; i -= 3, step++) {
         const bool horizontal = p[i] & 1, in_place = !(p[i] & 2);
         const int beginc = p[i + 1], endc = p[i + 2];
         const int offset = in_place ? endc + 1 : img->info.nb_meta_channels + img->info.nb_channels;
         if (beginc < 0 || endc < beginc || offset + endc - beginc >= (int)img->ch.size()) {
             ctx->err = "Invalid parameters for squeeze transform";
+            for (auto q : to_free) fb_plane_free(ctx, q);
             return FB_ERR_INVALID;
         }
-        // all planes of the step go into one launch (in groups of four)
-        for (int c0 = beginc; c0 <= endc; c0 += 4) {
-            const int n = std::min(4, endc - c0 + 1);
-            const int16_t *avgp[4], *resp[4];
-            int16_t *outp[4];
-            int wa[4], wr[4], ha[4], hr[4];
-            FbChan outs[4];
-            for (int k = 0; k < n; k++) {
-                FbChan &a = img->ch[c0 + k];
-                FbChan &r = img->ch[offset + c0 + k - beginc];
-                // the averages must exist; a missing residual plane acts as zeros (squeeze.h:379-383)
-                int rc = chan_materialize(ctx, a);
-                if (rc) return rc;
-                FbChan &out = outs[k];
-                out.d = a.d;
-                if (horizontal) { out.d.w = a.d.w + r.d.w; out.d.hshift--; out.d.hcshift--; }
-                else { out.d.h = a.d.h + r.d.h; out.d.vshift--; out.d.vcshift--; }
-                chan_setzero(out.d);
-                out.d.decoded = 1;
-                rc = fb_plane_alloc(ctx, chan_samples(out.d), &out.dev);
-                if (rc) return rc;
-                avgp[k] = a.dev; resp[k] = r.dev; outp[k] = out.dev;
-                wa[k] = a.d.w; wr[k] = r.d.w; ha[k] = a.d.h; hr[k] = r.d.h;
-            }
-            int rc = fb_launch_inv_squeeze_batch(ctx, horizontal ? 1 : 0, n, avgp, resp, outp, wa, wr, ha, hr);
+        for (int c = beginc; c <= endc; c++) {
+            FbChan &a = img->ch[c];
+            FbChan &r = img->ch[offset + c - beginc];
+            // the averages must exist; a missing residual plane acts as zeros (squeeze.h:379-383)
+            int rc = chan_materialize(ctx, a);
             if (rc) return rc;
-            for (int k = 0; k < n; k++) {
-                fb_plane_free(ctx, img->ch[c0 + k].dev);
-                img->ch[c0 + k] = outs[k];
-            }
+            FbChan out;
+            out.d = a.d;
+            if (horizontal) { out.d.w = a.d.w + r.d.w; out.d.hshift--; out.d.hcshift--; }
+            else { out.d.h = a.d.h + r.d.h; out.d.vshift--; out.d.vcshift--; }
+            chan_setzero(out.d);
+            out.d.decoded = 1;
+            rc = fb_plane_alloc(ctx, chan_samples(out.d), &out.dev);
+            if (rc) return rc;
+            ops.push_back(FbSqOp{step, horizontal ? 1 : 0, a.dev, r.dev, out.dev, a.d.w, r.d.w, a.d.h, r.d.h});
+            to_free.push_back(a.dev);
+            a = out;
         }
-        for (int c = 0; c <= endc - beginc; c++) fb_plane_free(ctx, img->ch[offset + c].dev);
+        for (int c = 0; c <= endc - beginc; c++) to_free.push_back(img->ch[offset + c].dev);
         img->ch.erase(img->ch.begin() + offset, img->ch.begin() + offset + (endc - beginc + 1));
     }
-    return FB_OK;
+    // Pass 2: run the plan (pyramid kernel for the coarse levels, one batched launch per remaining step).
+    int rc = fb_run_inv_squeeze_plan(ctx, ops);
+    // Pass 3: the consumed planes go back to the stream-ordered pool (after the kernels in stream order).
+    for (auto q : to_free) fb_plane_free(ctx, q);
+    return rc;
 }
 
 // squeeze(..., inverse=false), squeeze.h:389-406 with fwd_hsqueeze/fwd_vsqueeze (:135-170, :227-263)

@@ -141,7 +141,7 @@ constexpr int kWarm = 12;       // warm-up pairs (the recurrence re-joins the ex
 // staged residuals [R][PR], output words (A | B<<16) [R][wr], final state per segment [R][nseg].
 __device__ __forceinline__ int sq_round8(int v) { return (v + 7) & ~7; }
 
-__global__ void k_inv_hsqueeze_tiled(SqJobs jobs, int R, int threads_per_row) {
+__global__ void __launch_bounds__(1024) k_inv_hsqueeze_tiled(SqJobs jobs, int R, int threads_per_row) {
     extern __shared__ __align__(16) unsigned char smraw[];
     int b = blockIdx.x, ji = 0;
     while (ji < jobs.n - 1 && b >= jobs.j[ji].blocks) { b -= jobs.j[ji].blocks; ji++; }
@@ -253,7 +253,7 @@ __global__ void k_inv_hsqueeze_tiled(SqJobs jobs, int R, int threads_per_row) {
 }
 
 // Vertical: a block owns 32 complete columns of one plane.  thread = (column, segment along y); lanes = columns.
-__global__ void k_inv_vsqueeze_tiled(SqJobs jobs, int nseg, int segp) {
+__global__ void __launch_bounds__(1024) k_inv_vsqueeze_tiled(SqJobs jobs, int nseg, int segp) {
     extern __shared__ __align__(16) unsigned char smraw[];
     int16_t *bfS = reinterpret_cast<int16_t *>(smraw);          // [nseg][32]
     int b = blockIdx.x, ji = 0;
@@ -325,6 +325,127 @@ __global__ void k_inv_vsqueeze_tiled(SqJobs jobs, int nseg, int segp) {
     }
     // odd tail row: copy of the last average row (squeeze.h:217-222)
     if ((ho & 1) && x < w && sgm == 0) o[(size_t)(ho - 1) * w] = a[(size_t)(ha - 1) * w];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Pyramid kernel: the coarse levels of the unsqueeze chain in ONE launch.
+//
+// Every plane of the image has its own chain of unsqueeze steps (a step never mixes planes), so one block walks one
+// plane's chain level by level for as long as the level's planes fit in shared memory (output <= 64 Ki samples),
+// with a block-wide barrier between levels.  This replaces ~12 dependent launches of tiny grids, each of which would
+// cost a launch latency plus one serial chain latency.  Same segment / warm-up / verify scheme as the tiled kernels.
+// ---------------------------------------------------------------------------------------------------------
+struct PyrLevel {
+    const int16_t *avg, *res;
+    int16_t *out;
+    int wa, wr, ha, hr;         // horizontal: avg wa x ha, res wr x ha;  vertical: avg wa x ha, res wa x hr
+    int horizontal;
+};
+constexpr int kPyrMaxLevels = 56;
+struct PyrParams {
+    PyrLevel lv[kPyrMaxLevels];
+    int chain_start[9];
+    int nchains;
+};
+constexpr int kPyrSeg = 16, kPyrWarm = 8;
+constexpr int kPyrMaxOut = 65536;          // samples of a level's output plane
+
+// One segment of one chain, inputs staged in shared memory, outputs to global memory.
+// ch_stride / step strides let the same code run along x (horizontal) or y (vertical).
+__device__ __forceinline__ int pyr_segment(const int16_t *a, const int16_t *rr, int a_step, int r_step, int16_t *o, int o_step, int n_avg,
+                                           int from, int xs, int xe, int prev, bool chain_start, int &bw) {
+    int av = a[from * a_step];
+    if (chain_start) prev = av;
+    for (int x = from; x < xe; x++) {
+        const int nx = (x + 1 < n_avg) ? a[(x + 1) * a_step] : av;
+        int A, B;
+        if (x == xs) bw = prev;
+        unsqueeze_pair_fast(prev, av, nx, rr[x * r_step], A, B);
+        if (x >= xs) { o[(2 * x) * o_step] = (int16_t)A; o[(2 * x + 1) * o_step] = (int16_t)B; }
+        prev = B;
+        av = nx;
+    }
+    return prev;
+}
+
+__global__ void __launch_bounds__(1024) k_inv_squeeze_pyramid(PyrParams P) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int c = blockIdx.x;
+    const int l0 = P.chain_start[c], l1 = P.chain_start[c + 1];
+    int *bwS = reinterpret_cast<int *>(smraw);                  // [items] state assumed at the segment start
+    int *bfS = bwS + 4096;                                      // [items] state after the segment
+    int16_t *data = reinterpret_cast<int16_t *>(bfS + 4096);
+    for (int l = l0; l < l1; l++) {
+        const PyrLevel L = P.lv[l];
+        const bool H = L.horizontal != 0;
+        const int wa = L.wa, ha = L.ha;
+        const int wr = H ? L.wr : wa, hr = H ? ha : L.hr;           // residual plane dims
+        const int wo = H ? wa + wr : wa, ho = H ? ha : ha + hr;
+        // pitches in halfwords: for horizontal levels lanes are rows, so make the word pitch odd
+        int PA = (wa + 1) & ~1, PR = (wr + 1) & ~1;
+        if (H) { if (((PA >> 1) & 1) == 0) PA += 2; if (((PR >> 1) & 1) == 0) PR += 2; }
+        int16_t *avgS = data, *resS = data + (size_t)ha * PA;
+        for (int i = threadIdx.x; i < wa * ha; i += blockDim.x) { const int r = i / wa, q = i - r * wa; avgS[r * PA + q] = L.avg[i]; }
+        for (int i = threadIdx.x; i < wr * hr; i += blockDim.x) { const int r = i / wr, q = i - r * wr; resS[r * PR + q] = L.res ? L.res[i] : (int16_t)0; }
+        __syncthreads();
+        const int nchain = H ? ha : wa;                 // independent chains
+        const int npair = H ? wr : hr;                  // pairs along a chain
+        const int navg = H ? wa : ha;
+        const int nseg = (npair + kPyrSeg - 1) / kPyrSeg;
+        const int items = nchain * nseg;                // item = chain + nchain * seg  (lanes = chains)
+        auto run_item = [&](int item, bool repair, int state) {
+            const int chain = item % nchain, seg = item / nchain;
+            const int xs = seg * kPyrSeg, xe = min(xs + kPyrSeg, npair);
+            const int16_t *a = H ? avgS + chain * PA : avgS + chain;
+            const int16_t *rr = H ? resS + chain * PR : resS + chain;
+            int16_t *o = H ? L.out + (size_t)chain * wo : L.out + chain;
+            const int a_step = H ? 1 : PA, r_step = H ? 1 : PR, o_step = H ? 1 : wo;
+            int bw = 0x7fffffff, bf;
+            if (repair) bf = pyr_segment(a, rr, a_step, r_step, o, o_step, navg, xs, xs, xe, state, false, bw);
+            else if (xs < kPyrWarm + 1) { bf = pyr_segment(a, rr, a_step, r_step, o, o_step, navg, 0, xs, xe, 0, true, bw); if (xs == 0) bw = 0x7fffffff; else bw = 0x7ffffffe; }
+            else {
+                const int from = xs - kPyrWarm;
+                bf = pyr_segment(a, rr, a_step, r_step, o, o_step, navg, from, xs, xe, a[from * a_step], false, bw);
+            }
+            if (!repair) bwS[item] = bw;
+            bfS[item] = bf;
+        };
+        if (items <= 4096) {
+            for (int item = threadIdx.x; item < items; item += blockDim.x) run_item(item, false, 0);
+            __syncthreads();
+            for (;;) {
+                bool any = false;
+                for (int item = threadIdx.x; item < items; item += blockDim.x) {
+                    if (item < nchain) continue;                                // segment 0 starts at the true chain start
+                    const int bw = bwS[item];
+                    if (bw == 0x7ffffffe) continue;                             // ran from the chain start: exact
+                    const int want = bfS[item - nchain];
+                    if (want != bw) any = true;
+                }
+                if (!__syncthreads_or(any)) break;
+                for (int item = threadIdx.x; item < items; item += blockDim.x) {
+                    if (item < nchain) continue;
+                    const int bw = bwS[item];
+                    if (bw == 0x7ffffffe) continue;
+                    const int want = bfS[item - nchain];
+                    if (want != bw) { bwS[item] = want; run_item(item, true, want); }
+                }
+                __syncthreads();
+            }
+        } else {        // cannot happen for planes within kPyrMaxOut, kept as a safe serial path
+            for (int chain = threadIdx.x; chain < nchain; chain += blockDim.x) {
+                const int16_t *a = H ? avgS + chain * PA : avgS + chain;
+                const int16_t *rr = H ? resS + chain * PR : resS + chain;
+                int16_t *o = H ? L.out + (size_t)chain * wo : L.out + chain;
+                int bw;
+                pyr_segment(a, rr, H ? 1 : PA, H ? 1 : PR, o, H ? 1 : wo, navg, 0, 0, npair, 0, true, bw);
+            }
+        }
+        // odd tail: copy of the last average column / row (squeeze.h:129, :217-222)
+        if (H) { if (wo & 1) for (int r = threadIdx.x; r < ha; r += blockDim.x) L.out[(size_t)r * wo + wo - 1] = avgS[r * PA + wa - 1]; }
+        else { if (ho & 1) for (int q = threadIdx.x; q < wa; q += blockDim.x) L.out[(size_t)(ho - 1) * wo + q] = avgS[(ha - 1) * PA + q]; }
+        __syncthreads();        // the level's output (global memory) is complete and visible to the whole block
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -655,6 +776,78 @@ int fb_launch_inv_squeeze_batch(fb_ctx *ctx, int horizontal, int n, const int16_
         k_inv_vsqueeze_tiled<<<total, 32 * nseg, (size_t)nseg * 32 * 2 + 16, ctx->stream>>>(jobs, nseg, segp);
     }
     FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}
+// Executes a planned sequence of unsqueeze steps: coarse levels of every plane in one pyramid launch, the rest as one
+// batched launch per step.
+int fb_run_inv_squeeze_plan(fb_ctx *ctx, const std::vector<FbSqOp> &ops) {
+    const int n = (int)ops.size();
+    if (!n) return FB_OK;
+    // chains: op k continues the chain whose last op produced its `avg` plane
+    std::vector<int> chain(n, -1), prev(n, -1);
+    int nchains = 0;
+    for (int k = 0; k < n; k++) {
+        for (int q = k - 1; q >= 0; q--)
+            if (ops[q].out == ops[k].avg) { chain[k] = chain[q]; prev[k] = q; break; }
+        if (chain[k] < 0) chain[k] = nchains++;
+    }
+    // fused prefix of every chain
+    std::vector<char> fused(n, 0);
+    auto level_fits = [&](const FbSqOp &o) {
+        const long long wo = o.horizontal ? o.wa + o.wr : o.wa, ho = o.horizontal ? o.ha : o.ha + o.hr;
+        const long long npair = o.horizontal ? o.wr : o.hr, nchain = o.horizontal ? o.ha : o.wa;
+        if (npair <= 0 || wo * ho > kPyrMaxOut) return false;
+        if (nchain * ((npair + kPyrSeg - 1) / kPyrSeg) > 4096) return false;
+        return ((long long)(o.wa + 3) * o.ha + (long long)((o.horizontal ? o.wr : o.wa) + 3) * (o.horizontal ? o.ha : o.hr)) * 2 <= 150 * 1024;
+    };
+    PyrParams P;
+    P.nchains = 0;
+    int nlv = 0;
+    if (nchains <= 8) {
+        for (int cidx = 0; cidx < nchains; cidx++) {
+            const int start = nlv;
+            for (int k = 0; k < n; k++) {
+                if (chain[k] != cidx) continue;
+                if ((prev[k] >= 0 && !fused[prev[k]]) || !level_fits(ops[k]) || nlv >= kPyrMaxLevels) break;
+                PyrLevel &L = P.lv[nlv++];
+                L.avg = ops[k].avg; L.res = ops[k].res; L.out = ops[k].out;
+                L.wa = ops[k].wa; L.wr = ops[k].wr; L.ha = ops[k].ha; L.hr = ops[k].hr; L.horizontal = ops[k].horizontal;
+                fused[k] = 1;
+            }
+            if (nlv > start) { P.chain_start[P.nchains++] = start; }
+        }
+        P.chain_start[P.nchains] = nlv;
+    }
+    if (P.nchains > 0) {
+        const size_t smem = 2 * 4096 * sizeof(int) + 150 * 1024 + 64;
+        static bool configured = false;
+        if (!configured) {
+            FB_CUDA(ctx, cudaFuncSetAttribute(k_inv_squeeze_pyramid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        k_inv_squeeze_pyramid<<<P.nchains, 1024, smem, ctx->stream>>>(P);
+        FB_LAUNCH_CHECK(ctx);
+    }
+    // the remaining ops, one batched launch per squeeze step (up to four planes each)
+    int k = 0;
+    while (k < n) {
+        if (fused[k]) { k++; continue; }
+        const int16_t *avgp[4], *resp[4];
+        int16_t *outp[4];
+        int wa[4], wr[4], ha[4], hr[4], m = 0;
+        const int step = ops[k].step, horizontal = ops[k].horizontal;
+        int q = k;
+        while (q < n && ops[q].step == step && m < 4) {
+            if (!fused[q]) {
+                avgp[m] = ops[q].avg; resp[m] = ops[q].res; outp[m] = ops[q].out;
+                wa[m] = ops[q].wa; wr[m] = ops[q].wr; ha[m] = ops[q].ha; hr[m] = ops[q].hr; m++;
+            }
+            q++;
+        }
+        int rc = fb_launch_inv_squeeze_batch(ctx, horizontal, m, avgp, resp, outp, wa, wr, ha, hr);
+        if (rc) return rc;
+        k = q;
+    }
     return FB_OK;
 }
 int fb_launch_fwd_hsqueeze(fb_ctx *ctx, const int16_t *in, int16_t *avg, int16_t *res, int w, int h) {

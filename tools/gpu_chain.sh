@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q -k "transform or extreme or dct or undo or roundtrip or forward" > gpurun_out/pytest_chain.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_chain.log
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_chain.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_chain.log
 timeout 300 python tools/chain_bench.py cfg2 5 2>&1 | tail -2
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_inv|k_ycocg|k_clamp" -c 30 --csv --log-file gpurun_out/launches_chain_mid.csv python tools/decode_once.py mid --undo > /dev/null 2>&1
 python - <<'PY'
