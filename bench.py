@@ -168,7 +168,10 @@ def main():
     mpix_rank = n_per_gpu * w * h / 1e6
     bps = 2 if maxval > 255 else 1
 
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the library enqueues on it and the CUDA events below are recorded on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = api.Context(local_rank, stream.cuda_stream)
 
     # compressed files resident in HBM (value path) and in pinned host memory (e2e path)

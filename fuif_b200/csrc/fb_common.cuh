@@ -21,6 +21,16 @@ struct fb_ctx {
     int sm_count = 148;
     // MANIAC decoder resources (fb_maniac.cu), created lazily
     void *maniac_state = nullptr;
+    // FB_KERNEL_TIMING=1: a CUDA event after every launch, dumped by fb_ctx_synchronize (development aid)
+    bool timing = false;
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    void mark(const char *name) {
+        if (!timing) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, stream);
+        marks.emplace_back(name, e);
+    }
 };
 
 struct FbChan {

@@ -3,6 +3,7 @@
 // host: every plane lives in HBM and every transform is a kernel from fb_transforms.cu.
 #include "fb_common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -33,6 +34,7 @@ extern "C" int fb_ctx_create(int device, void *stream, fb_ctx **out) {
     }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    ctx->timing = getenv("FB_KERNEL_TIMING") != nullptr;
     // keep freed plane memory in the stream-ordered pool instead of returning it to the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -56,6 +58,15 @@ extern "C" const char *fb_last_error(fb_ctx *ctx) { return ctx ? ctx->err.c_str(
 
 extern "C" int fb_ctx_synchronize(fb_ctx *ctx) {
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->timing && ctx->marks.size() > 1) {
+        for (size_t i = 1; i < ctx->marks.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ctx->marks[i - 1].second, ctx->marks[i].second);
+            fprintf(stderr, "[timing] %-32s %8.1f us\n", ctx->marks[i].first.c_str(), ms * 1000.f);
+        }
+        for (auto &mk : ctx->marks) cudaEventDestroy(mk.second);
+        ctx->marks.clear();
+    }
     return FB_OK;
 }
 
@@ -486,6 +497,7 @@ extern "C" int fb_image_undo_transforms(fb_image *img, int keep) {
     fb_ctx *ctx = img->ctx;
     cudaSetDevice(ctx->device);
     bool clamped = false;
+    ctx->mark("undo_transforms begin");
     while ((int)img->tr.size() > keep) {
         FbXform &t = img->tr.back();
         int rc = FB_OK, applied = 1;

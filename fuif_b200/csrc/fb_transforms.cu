@@ -133,15 +133,15 @@ struct SqJob {
 };
 struct SqJobs { SqJob j[4]; int n; };
 
-constexpr int kSegP = 33;       // pairs per segment: odd => conflict-free shared-memory columns
-constexpr int kWarm = 12;       // warm-up pairs (the recurrence re-joins the exact chain within <= 7 pairs in practice)
+constexpr int kWarm = 8;        // warm-up pairs (the recurrence re-joins the exact chain within <= 7 pairs in practice;
+                                // a wrong guess only costs a repair round, never exactness)
 
 // Horizontal: a block owns R complete rows of one plane.  thread = (row, segment).
 // Shared memory: staged averages [R][PA] (+1 sentinel = last average, so that "next average" needs no bounds test),
 // staged residuals [R][PR], output words (A | B<<16) [R][wr], final state per segment [R][nseg].
 __device__ __forceinline__ int sq_round8(int v) { return (v + 7) & ~7; }
 
-__global__ void __launch_bounds__(1024) k_inv_hsqueeze_tiled(SqJobs jobs, int R, int threads_per_row) {
+__global__ void __launch_bounds__(1024) k_inv_hsqueeze_tiled(SqJobs jobs, int R, int threads_per_row, int kSegP) {
     extern __shared__ __align__(16) unsigned char smraw[];
     int b = blockIdx.x, ji = 0;
     while (ji < jobs.n - 1 && b >= jobs.j[ji].blocks) { b -= jobs.j[ji].blocks; ji++; }
@@ -270,21 +270,28 @@ __global__ void __launch_bounds__(1024) k_inv_vsqueeze_tiled(SqJobs jobs, int ns
     auto owned = [&](int prev, bool first_is_chain_start) {
         int av = a[(size_t)ys * w];
         if (first_is_chain_start) prev = av;
-        const int16_t *pa = a + (size_t)(ys + 1) * w;
-        const int16_t *pr = rr ? rr + (size_t)ys * w : nullptr;
-        int16_t *po = o + (size_t)(2 * ys) * w;
-#pragma unroll 4
-        for (int y = ys; y < ye; y++) {
-            const int nx = (y + 1 < ha) ? *pa : av;
-            const int rs = pr ? *pr : 0;
-            int A, B;
-            unsqueeze_pair_fast(prev, av, nx, rs, A, B);
-            po[0] = (int16_t)A;
-            po[w] = (int16_t)B;
-            prev = B;
-            av = nx;
-            pa += w; po += 2 * (size_t)w;
-            if (pr) pr += w;
+        // inputs of eight steps are fetched together (they do not depend on the chain), then consumed
+        for (int yb = ys; yb < ye; yb += 8) {
+            int nxv[8], rsv[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int y = yb + j;
+                nxv[j] = (y < ye && y + 1 < ha) ? a[(size_t)(y + 1) * w] : 0;
+                rsv[j] = (y < ye && rr) ? rr[(size_t)y * w] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int y = yb + j;
+                if (y < ye) {
+                    const int nx = (y + 1 < ha) ? nxv[j] : av;
+                    int A, B;
+                    unsqueeze_pair_fast(prev, av, nx, rsv[j], A, B);
+                    o[(size_t)(2 * y) * w] = (int16_t)A;
+                    o[(size_t)(2 * y + 1) * w] = (int16_t)B;
+                    prev = B;
+                    av = nx;
+                }
+            }
         }
         return prev;
     };
@@ -294,14 +301,18 @@ __global__ void __launch_bounds__(1024) k_inv_vsqueeze_tiled(SqJobs jobs, int ns
         else {
             const int from = ys - kWarm;
             int av = a[(size_t)from * w], prev = av;
-#pragma unroll 4
-            for (int y = from; y < ys; y++) {
-                const int nx = a[(size_t)(y + 1) * w];     // y + 1 <= ys < hr <= ha
-                const int rs = rr ? rr[(size_t)y * w] : 0;
+            int nxv[kWarm], rsv[kWarm];
+#pragma unroll
+            for (int j = 0; j < kWarm; j++) {
+                nxv[j] = a[(size_t)(from + j + 1) * w];     // from + j + 1 <= ys < hr <= ha
+                rsv[j] = rr ? rr[(size_t)(from + j) * w] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < kWarm; j++) {
                 int A, B;
-                unsqueeze_pair_fast(prev, av, nx, rs, A, B);
+                unsqueeze_pair_fast(prev, av, nxv[j], rsv[j], A, B);
                 prev = B;
-                av = nx;
+                av = nxv[j];
             }
             bw = prev;
             bf = owned(prev, false);
@@ -347,8 +358,8 @@ struct PyrParams {
     int chain_start[9];
     int nchains;
 };
-constexpr int kPyrSeg = 16, kPyrWarm = 8;
-constexpr int kPyrMaxOut = 65536;          // samples of a level's output plane
+constexpr int kPyrSeg = 8, kPyrWarm = 8;
+constexpr int kPyrMaxOut = 4096;           // samples of a level's output plane (one block = one SM works on it)
 
 // One segment of one chain, inputs staged in shared memory, outputs to global memory.
 // ch_stride / step strides let the same code run along x (horizontal) or y (vertical).
@@ -519,6 +530,31 @@ __global__ void k_ycocg(int16_t *__restrict__ c0, int16_t *__restrict__ c1, int1
         int Cg = G - ((R + B) >> 1);
         c0[i] = (int16_t)Y; c1[i] = (int16_t)Co; c2[i] = (int16_t)Cg;
     }
+}
+
+// 8 samples per thread, 128-bit loads / stores (n8 = number of 8-sample groups; planes are 256-byte aligned)
+__global__ void k_ycocg_inv_vec8(int16_t *__restrict__ c0, int16_t *__restrict__ c1, int16_t *__restrict__ c2, size_t n8, int maxval, int lo, int hi,
+                                 int do_clamp) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    uint4 a = reinterpret_cast<const uint4 *>(c0)[i], b = reinterpret_cast<const uint4 *>(c1)[i], c = reinterpret_cast<const uint4 *>(c2)[i];
+    unsigned *pa = &a.x, *pb = &b.x, *pc = &c.x;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        unsigned ra = 0, rb = 0, rc = 0;
+#pragma unroll
+        for (int hlf = 0; hlf < 2; hlf++) {
+            const int Yr = (int)(short)(pa[k] >> (16 * hlf)), Co = (int)(short)(pb[k] >> (16 * hlf)), Cg = (int)(short)(pc[k] >> (16 * hlf));
+            const int Y = clampi(Yr, 0, maxval);
+            int G = clampi(Y - ((-Cg) >> 1), 0, maxval);
+            int B = clampi(Y + ((1 - Cg) >> 1) - (Co >> 1), 0, maxval);
+            int R = clampi(Co + B, 0, maxval);
+            if (do_clamp) { R = clampi(R, lo, hi); G = clampi(G, lo, hi); B = clampi(B, lo, hi); }
+            ra |= (unsigned)(uint16_t)R << (16 * hlf); rb |= (unsigned)(uint16_t)G << (16 * hlf); rc |= (unsigned)(uint16_t)B << (16 * hlf);
+        }
+        pa[k] = ra; pb[k] = rb; pc[k] = rc;
+    }
+    reinterpret_cast<uint4 *>(c0)[i] = a; reinterpret_cast<uint4 *>(c1)[i] = b; reinterpret_cast<uint4 *>(c2)[i] = c;
 }
 
 __device__ __forceinline__ int16_t clamp_trunc(double x, int lo, int hi) {
@@ -697,6 +733,7 @@ inline unsigned nblocks(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
 #define FB_LAUNCH_CHECK(ctx)                                                                       \
     do {                                                                                           \
         (ctx)->launches++;                                                                         \
+        (ctx)->mark(__func__);                                                                     \
         cudaError_t e__ = cudaGetLastError();                                                      \
         if (e__ != cudaSuccess) { (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(e__); return FB_ERR_CUDA; } \
     } while (0)
@@ -724,6 +761,14 @@ int fb_launch_inv_squeeze_batch(fb_ctx *ctx, int horizontal, int n, const int16_
     if (horizontal) {
         int maxwr = 0, maxwa = 0;
         for (int i = 0; i < n; i++) { maxwr = std::max(maxwr, wr[i]); maxwa = std::max(maxwa, wa[i]); }
+        // segment length: short segments for small levels (latency bound: fewer serial steps per thread), long ones for
+        // big levels (throughput bound: less warm-up redundancy).  Odd => conflict-free shared-memory columns.
+        long long pairs_total = 0;
+        for (int i = 0; i < n; i++) pairs_total += (long long)wr[i] * ha[i];
+        int kSegP = 33;
+        if (pairs_total / 33 < 148LL * 1024) kSegP = 17;
+        if (pairs_total / 17 < 148LL * 1024) kSegP = 9;
+        while ((maxwr + kSegP - 1) / kSegP > 1024) kSegP += 8;
         const int nseg = std::max(1, (maxwr + kSegP - 1) / kSegP);
         int tpr = nseg;                                     // threads per row
         if (tpr > 1024) { ctx->err = "plane too wide for the tiled unsqueeze"; return FB_ERR_UNSUPPORTED; }
@@ -752,13 +797,17 @@ int fb_launch_inv_squeeze_batch(fb_ctx *ctx, int horizontal, int n, const int16_
         }
         int threads = R * tpr;
         threads = (threads + 31) / 32 * 32;
-        k_inv_hsqueeze_tiled<<<total, threads, smem, ctx->stream>>>(jobs, R, tpr);
+        k_inv_hsqueeze_tiled<<<total, threads, smem, ctx->stream>>>(jobs, R, tpr, kSegP);
     } else {
         int maxhr = 0;
         for (int i = 0; i < n; i++) maxhr = std::max(maxhr, hr[i]);
         // segments along y: at most 32 per block (1024 threads), at least kSegP pairs each
-        int segp = kSegP;
-        while ((maxhr + segp - 1) / segp > 32) segp += kSegP;
+        long long pairs_total = 0;
+        for (int i = 0; i < n; i++) pairs_total += (long long)wa[i] * hr[i];
+        int segp = 32;
+        if (pairs_total / 32 < 148LL * 1024) segp = 16;
+        if (pairs_total / 16 < 148LL * 1024) segp = 8;
+        while ((maxhr + segp - 1) / segp > 32) segp += 8;
         const int nseg = std::max(1, (maxhr + segp - 1) / segp);
         for (int i = 0; i < n; i++) {
             if (ha[i] <= 0 || wa[i] <= 0) continue;
@@ -866,7 +915,15 @@ int fb_launch_fwd_vsqueeze(fb_ctx *ctx, const int16_t *in, int16_t *avg, int16_t
 }
 int fb_launch_ycocg(fb_ctx *ctx, int16_t *c0, int16_t *c1, int16_t *c2, size_t n, int maxval, int inverse, int lo, int hi, int do_clamp) {
     if (!n) return FB_OK;
-    k_ycocg<<<nblocks(n, 256), 256, 0, ctx->stream>>>(c0, c1, c2, n, maxval, inverse, lo, hi, do_clamp);
+    const bool aligned = (((uintptr_t)c0 | (uintptr_t)c1 | (uintptr_t)c2) & 15) == 0;
+    if (inverse && aligned && n >= 8) {
+        const size_t n8 = n / 8;
+        k_ycocg_inv_vec8<<<nblocks(n8, 256), 256, 0, ctx->stream>>>(c0, c1, c2, n8, maxval, lo, hi, do_clamp);
+        const size_t done = n8 * 8;
+        if (done < n) k_ycocg<<<1, 32, 0, ctx->stream>>>(c0 + done, c1 + done, c2 + done, n - done, maxval, inverse, lo, hi, do_clamp);
+    } else {
+        k_ycocg<<<nblocks(n, 256), 256, 0, ctx->stream>>>(c0, c1, c2, n, maxval, inverse, lo, hi, do_clamp);
+    }
     FB_LAUNCH_CHECK(ctx);
     return FB_OK;
 }

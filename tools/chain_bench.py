@@ -9,7 +9,8 @@ name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 spec = wl.WORKLOADS[name]
 im = wl.prepare_image(name)
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
 ctx = api.Context(0, stream.cuda_stream)
 img = api.fuif_decode(im["fuif"], ctx=ctx, group_index=im["index"])
 inf = img.info()
