@@ -151,7 +151,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from fuif_b200 import api
+    from fuif_b200 import api, shard
     from fuif_b200 import workloads as wl
 
     if not torch.cuda.is_available():
@@ -163,7 +163,8 @@ def main():
     # ---- workload: one image per GPU (weak scaling, no data-path collective: files are independent units)
     spec = wl.WORKLOADS[args.workload]
     n_per_gpu = spec[5]
-    imgs = [wl.prepare_image(args.workload, seed_offset=rank * n_per_gpu + i, want_index=not args.no_index) for i in range(n_per_gpu)]
+    units = shard.units_for_rank(n_per_gpu, rank)
+    imgs = [wl.prepare_image(args.workload, seed_offset=u, want_index=not args.no_index) for u in units]
     w, h, c, maxval = spec[0], spec[1], spec[2], spec[3]
     mpix_rank = n_per_gpu * w * h / 1e6
     bps = 2 if maxval > 255 else 1
@@ -241,12 +242,9 @@ def main():
     dec_ms = [e[0].elapsed_time(e[1]) for e in evs]
     chain_ms = [e[1].elapsed_time(e[2]) for e in evs]
     step_ms = [e[0].elapsed_time(e[2]) for e in evs]
-    total_ms = sum(step_ms)
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
-    value = world * mpix_rank / (ms_per_step / 1e3)
+    total_ms, total_units = shard.reduce_step_time(sum(step_ms), len(units), device="cuda")
+    ms_per_step = total_ms / args.steps
+    value = total_units * (w * h / 1e6) / (ms_per_step / 1e3)
 
     # ---- e2e: host buffers through the C-ABI convenience call
     for _ in range(min(args.warmup, 1)):
@@ -257,10 +255,8 @@ def main():
         step_e2e()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * mpix_rank / (float(t.item()) / args.steps)
+    e2e_max, _ = shard.reduce_step_time(e2e_s * 1e3, len(units), device="cuda")
+    e2e_value = total_units * (w * h / 1e6) / (e2e_max / 1e3 / args.steps)
     if lossless:
         from fuif_b200.synth import synth_image
         got = pin_out[0].numpy()

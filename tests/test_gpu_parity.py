@@ -187,3 +187,22 @@ def test_extreme_values_wrap_like_int16(oracle, ctx):
     gi2.undo_transforms(0)
     oi.undo_transforms(0)
     po.compare_plane_images(gpu_plane_image(po, gi2), oi.to_plane_image(), "extreme inv")
+
+
+def test_cli_decodes_like_fuif_d(ctx, tmp_path):
+    """The C++ mirror API + CLI (`fuif_b200_cli -d in.fuif out.ppm`) against the reference's decoded pixels."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "fuif_b200", "fuif_b200_cli")
+    assert os.path.exists(cli), "run __graft_entry__.build()"
+    for name in ("sq128", "rgba14", "gray", "dct"):
+        blob = load_golden(name)
+        fin, fout = tmp_path / (name + ".fuif"), tmp_path / (name + ".pnm")
+        fin.write_bytes(blob["fuif"])
+        subprocess.run([cli, "-d", str(fin), str(fout)], check=True)
+        got, _ = read_pnm(str(fout))
+        final = ordered(blob, "s")[-1]
+        from oracle import pyoracle as po
+        ref = po.parse_fbpd(final)
+        want = np.stack([p.data.astype(np.int32) for p in ref.planes[:ref.nb_channels]], axis=-1)
+        assert np.array_equal(got, want), name
