@@ -96,11 +96,11 @@ class ClockSampler:
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU decoder on the same workload, one process per image."""
-    from fuif_b200 import workloads as wl
+    import bench_workloads as wl
     if rank != 0:
         return
-    n_img = max(1, args.gpus)
-    imgs = [wl.prepare_image(args.workload, seed_offset=i, want_index=False) for i in range(n_img)]
+    n_img = max(1, args.gpus) * wl.WORKLOADS[args.workload][5]
+    imgs = wl.prepare_images(args.workload, range(n_img), want_index=False)
     mpix = sum(im["w"] * im["h"] for im in imgs) / 1e6
     use_ref = wl.have_ref_driver()
 
@@ -152,7 +152,7 @@ def main():
     import torch
     import torch.distributed as dist
     from fuif_b200 import api, shard
-    from fuif_b200 import workloads as wl
+    import bench_workloads as wl
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: fuif_b200 has no CPU fallback")
@@ -164,7 +164,7 @@ def main():
     spec = wl.WORKLOADS[args.workload]
     n_per_gpu = spec[5]
     units = shard.units_for_rank(n_per_gpu, rank)
-    imgs = [wl.prepare_image(args.workload, seed_offset=u, want_index=not args.no_index) for u in units]
+    imgs = wl.prepare_images(args.workload, units, want_index=not args.no_index)
     w, h, c, maxval = spec[0], spec[1], spec[2], spec[3]
     mpix_rank = n_per_gpu * w * h / 1e6
     bps = 2 if maxval > 255 else 1
@@ -183,11 +183,13 @@ def main():
 
     def step_value(ev=None):
         """decode + undo_transforms, inputs and outputs in HBM. ev: optional (start, mid, end) CUDA events."""
-        out = []
         if ev:
             ev[0].record(stream)
-        for im, db in zip(imgs, dev_bytes):
-            out.append(api.fuif_decode((db.data_ptr(), db.numel()), ctx=ctx, group_index=im["index"]))
+        if len(imgs) == 1:
+            out = [api.fuif_decode((dev_bytes[0].data_ptr(), dev_bytes[0].numel()), ctx=ctx, group_index=imgs[0]["index"])]
+        else:       # a batch: every (image, group) is a stream of ONE launch
+            out = api.fuif_decode_batch([(db.data_ptr(), db.numel()) for db in dev_bytes], ctx=ctx,
+                                        group_indexes=None if args.no_index else [im["index"] for im in imgs])
         if ev:
             ev[1].record(stream)
         for o in out:
@@ -197,9 +199,16 @@ def main():
         return out
 
     def step_e2e():
-        for im, pb, po_ in zip(imgs, pin_bytes, pin_out):
-            arr = np.frombuffer(memoryview(pb.numpy()), dtype=np.uint8)
-            api.decode_to_pixels(arr, ctx=ctx, group_index=im["index"], out=po_.numpy())
+        if len(imgs) == 1:
+            arr = np.frombuffer(memoryview(pin_bytes[0].numpy()), dtype=np.uint8)
+            api.decode_to_pixels(arr, ctx=ctx, group_index=imgs[0]["index"], out=pin_out[0].numpy())
+            return
+        res_ = api.fuif_decode_batch([np.frombuffer(memoryview(pb.numpy()), dtype=np.uint8) for pb in pin_bytes], ctx=ctx,
+                                     group_indexes=None if args.no_index else [im["index"] for im in imgs])
+        for o in res_:
+            o.undo_transforms(0)
+        for o, po_ in zip(res_, pin_out):
+            ctx.check(ctx.lib.fb_image_download_interleaved(o._handle, c, bps, po_.numpy().ctypes.data), "fb_image_download_interleaved")
 
     def barrier():
         torch.cuda.synchronize()
@@ -211,10 +220,11 @@ def main():
     res = step_value()
     torch.cuda.synchronize()
     lossless = args.workload in ("cfg1", "cfg2", "cfg4", "mid")
+    spec_seed0 = spec[4] + units[0]
     exact = None
     if lossless:
         from fuif_b200.synth import synth_image
-        exact = bool(np.array_equal(res[0].pixels(), synth_image(w, h, c, maxval, spec[4] + rank * n_per_gpu)))
+        exact = bool(np.array_equal(res[0].pixels(), synth_image(w, h, c, maxval, spec_seed0)))
         if not exact:
             raise SystemExit("decoded pixels differ from the input image: refusing to report a number")
     del res
@@ -262,7 +272,7 @@ def main():
         got = pin_out[0].numpy()
         if bps == 2:
             got = got.view(">u2")
-        assert np.array_equal(got.astype(np.int32), synth_image(w, h, c, maxval, spec[4] + rank * n_per_gpu)), "e2e pixels differ"
+        assert np.array_equal(got.astype(np.int32), synth_image(w, h, c, maxval, spec_seed0)), "e2e pixels differ"
 
     if rank != 0:
         if world > 1:
@@ -286,8 +296,19 @@ def main():
     cpu = None
     if world == 1 and not args.skip_cpu_baseline:
         if wl.have_ref_driver():
-            tt = wl.reference_decode_seconds(imgs[0]["fuif_path"])
-            cpu = {"value": w * h / 1e6 / tt["total_s"], "unit": "Mpx/s", "cores": 1, "kind": "reference",
+            import tempfile
+            from fuif_b200.synth import read_pnm
+            with tempfile.TemporaryDirectory() as td:
+                pnm = os.path.join(td, "ref.pnm")
+                tt = wl.reference_decode_seconds(imgs[0]["fuif_path"], pnm)
+                ref_pix, _ = read_pnm(pnm)
+            got = pin_out[0].numpy()
+            if bps == 2:
+                got = got.view(">u2")
+            exact_vs_ref = bool(np.array_equal(got.astype(np.int32), ref_pix))      # the reference is the checker here
+            if not exact_vs_ref:
+                raise SystemExit("GPU pixels differ from the reference decoder's pixels: refusing to report a number")
+            cpu = {"value": w * h / 1e6 / tt["total_s"], "unit": "Mpx/s", "cores": 1, "kind": "reference", "gpu_pixels_equal_reference": exact_vs_ref,
                    "sample": "one full decode (fuif_decode_file + undo_transforms) of the first workload image by oracle/_ref/ref_driver",
                    "entropy_s": tt["entropy_s"], "chain_s": tt["chain_s"]}
         else:

@@ -1,0 +1,130 @@
+"""Benchmark / large-test workloads: the configurations BASELINE.json names, generated deterministically
+(fuif_b200.synth) and encoded ONCE into .fuif files that are cached on local disk.
+
+Benchmark infrastructure, not product code (it lives outside the fuif_b200 package on purpose).  The encoder is not part
+of the decode hot path that is being measured: files are produced by the reference's own encoder (the prebuilt
+oracle/_ref/ref_driver travels with the repository to the GPU box), which also makes the inputs independent of this
+repository's code.  The "group index" sidecar (byte offset of every channel group, 61 integers for a 4096x4096 image) is
+what an encoder knows for free when it writes the file; for reference-encoded files it is recovered ONCE by a sequential
+decode on the GPU (fb_image_group_index) -- or, in the GPU-less build container, by the CPU oracle -- and cached next to
+the file.
+"""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import time
+
+import numpy as np
+
+from fuif_b200.synth import synth_image, write_pnm
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+
+# name -> (w, h, channels, maxval, base seed, number of images, ref_driver encode options, description)
+WORKLOADS = {
+    "cfg1": (512, 512, 3, 255, 1234, 1, [], "single 512x512 RGB, lossless YCoCg+Squeeze"),
+    "cfg2": (4096, 4096, 3, 255, 7, 1, [], "4096x4096 8-bit RGB lossless YCoCg+Squeeze"),
+    "cfg3": (4096, 4096, 3, 255, 7, 1, ["-C", "1", "-J", "-q", "8,12", "-G", "1"], "4096x4096 lossy YCbCr+DCT+Quantize(+Squeeze of DC), one plane per group"),
+    "cfg4": (1920, 1080, 3, 255, 100, 64, [], "batch of 64 1920x1080 RGB lossless Squeeze images"),
+    "cfg5": (8192, 8192, 4, 16383, 9, 1, ["-q", "12,64"], "8192x8192 14-bit 4-channel, YCoCg+Squeeze+Quantize"),
+    "mid": (2048, 2048, 3, 255, 7, 1, [], "2048x2048 8-bit RGB lossless YCoCg+Squeeze (quick runs)"),
+}
+
+
+def cache_dir() -> str:
+    d = os.environ.get("FUIF_B200_CACHE", os.path.join(ROOT, ".bench_cache"))      # git-ignored; travels with gpurun snapshots
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def have_ref_driver() -> bool:
+    return os.path.exists(REF_DRIVER) and os.access(REF_DRIVER, os.X_OK)
+
+
+def _paths(name: str, seed: int):
+    base = os.path.join(cache_dir(), f"{name}_s{seed}")
+    return base + ".pnm", base + ".fuif", base + ".index.json"
+
+
+def prepare_image(name: str, seed_offset: int = 0, want_index: bool = True) -> dict:
+    """Returns {'fuif': bytes, 'w','h','c','maxval','pnm': path, 'fuif_path': path, 'index': (offsets, first) | None}."""
+    w, h, c, maxval, seed, _n, opts, _ = WORKLOADS[name]
+    seed += seed_offset
+    pnm, fuif, idx = _paths(name, seed)
+    if not os.path.exists(fuif):
+        if not have_ref_driver():
+            raise RuntimeError("oracle/_ref/ref_driver is missing: run __graft_entry__.build() where /root/reference exists "
+                               "(the benchmark inputs are encoded by the reference encoder)")
+        write_pnm(pnm, synth_image(w, h, c, maxval, seed), maxval)
+        tmp = fuif + f".tmp{os.getpid()}"
+        subprocess.run([REF_DRIVER, "encode", pnm, tmp, *opts], check=True, capture_output=True)
+        os.replace(tmp, fuif)
+        os.remove(pnm)      # the pixels are regenerated from the seed when a check needs them
+    with open(fuif, "rb") as f:
+        data = f.read()
+    out = {"fuif": data, "w": w, "h": h, "c": c, "maxval": maxval, "pnm": pnm, "fuif_path": fuif, "index": None}
+    if want_index:
+        if os.path.exists(idx):
+            with open(idx) as f:
+                j = json.load(f)
+        else:
+            t0 = time.perf_counter()
+            import torch
+            if torch.cuda.is_available():       # one sequential decode by the library itself
+                from fuif_b200 import api
+                seq = api.fuif_decode(data)
+                offs_, first_ = seq.group_index()
+                del seq
+                j = {"offsets": [int(a) for a in offs_], "first": [int(b) for b in first_], "source": "fb_image_group_index", "decode_s": time.perf_counter() - t0}
+            else:                               # build container without a GPU
+                from oracle import pyoracle as po
+                _img, offs = po.OracleImage.decode(data, want_offsets=True)
+                del _img
+                j = {"offsets": [int(a) for a, _ in offs], "first": [int(b) for _, b in offs], "source": "oracle", "decode_s": time.perf_counter() - t0}
+            with open(idx + f".tmp{os.getpid()}", "w") as f:
+                json.dump(j, f)
+            os.replace(idx + f".tmp{os.getpid()}", idx)
+        out["index"] = (j["offsets"], j["first"])
+    return out
+
+
+def prepare_images(name: str, seed_offsets, want_index: bool = True, workers: int = 32) -> list:
+    """Several images of a workload; the (CPU-only) encodes run in parallel processes, the index step stays serial."""
+    from concurrent.futures import ProcessPoolExecutor
+    seed_offsets = list(seed_offsets)
+    missing = [u for u in seed_offsets if not os.path.exists(_paths(name, WORKLOADS[name][4] + u)[1])]
+    if len(missing) > 1:
+        with ProcessPoolExecutor(max_workers=min(workers, len(missing))) as ex:
+            list(ex.map(_encode_only, [(name, u) for u in missing]))
+    if want_index:
+        need = [u for u in seed_offsets if not os.path.exists(_paths(name, WORKLOADS[name][4] + u)[2])]
+        import torch
+        if len(need) > 1 and torch.cuda.is_available():
+            # recover the group offsets of all files with ONE batched sequential decode (one stream per file)
+            from fuif_b200 import api
+            t0 = time.perf_counter()
+            datas = [open(_paths(name, WORKLOADS[name][4] + u)[1], "rb").read() for u in need]
+            for u, im in zip(need, api.fuif_decode_batch(datas)):
+                offs_, first_ = im.group_index()
+                idx = _paths(name, WORKLOADS[name][4] + u)[2]
+                with open(idx, "w") as f:
+                    json.dump({"offsets": [int(a) for a in offs_], "first": [int(b) for b in first_], "source": "fb_image_group_index (batch)",
+                               "decode_s": time.perf_counter() - t0}, f)
+    return [prepare_image(name, seed_offset=u, want_index=want_index) for u in seed_offsets]
+
+
+def _encode_only(args):
+    name, u = args
+    prepare_image(name, seed_offset=u, want_index=False)
+    return u
+
+
+def reference_decode_seconds(fuif_path: str, out_pnm: str | None = None) -> dict:
+    """One full decode by the unmodified reference (fuif_decode_file + undo_transforms), timed inside its process;
+    optionally leaves the decoded pixels in out_pnm (written after the timed part)."""
+    cmd = [REF_DRIVER, "time", fuif_path, "1"] + ([out_pnm] if out_pnm else [])
+    r = subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return json.loads(r.stdout.strip().splitlines()[-1])

@@ -354,23 +354,42 @@ def fuif_decode_batch(datas, options: fuif_options = default_fuif_options, ctx: 
     """Decodes several files in one kernel launch: every (image, channel group) is an independent stream."""
     ctx = ctx or default_context()
     n = len(datas)
-    bufs = [np.frombuffer(d, dtype=np.uint8) for d in datas]
-    ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
-    sizes = (C.c_size_t * n)(*[b.size for b in bufs])
+    bufs, plist, slist = [], [], []
+    for d in datas:
+        if isinstance(d, tuple):            # (device pointer, nbytes)
+            plist.append(d[0]); slist.append(d[1])
+        else:
+            b = np.frombuffer(d, dtype=np.uint8)
+            bufs.append(b); plist.append(b.ctypes.data); slist.append(b.size)
+    ptrs = (C.c_void_p * n)(*plist)
+    sizes = (C.c_size_t * n)(*slist)
     out = (C.c_void_p * n)()
     opts = options._c()
-    gi_ptrs = None
+    gi_ptrs = gf_ptrs = None
     gi_n = (C.c_int * n)()
     keep = []
     if group_indexes is not None:
         gi_ptrs = (C.POINTER(C.c_int64) * n)()
+        gf_ptrs = (C.POINTER(C.c_int32) * n)()
+        have_first = False
         for i, gi in enumerate(group_indexes):
-            if gi:
-                a = (C.c_int64 * len(gi))(*gi)
-                keep.append(a)
-                gi_ptrs[i] = C.cast(a, C.POINTER(C.c_int64))
-                gi_n[i] = len(gi)
-    ctx.check(ctx.lib.fb_decode_batch(ctx.h, n, ptrs, sizes, C.byref(opts), gi_ptrs, None, gi_n, out), "fb_decode_batch")
+            if not gi:
+                continue
+            first = None
+            if isinstance(gi, tuple):
+                gi, first = gi
+            a = (C.c_int64 * len(gi))(*gi)
+            keep.append(a)
+            gi_ptrs[i] = C.cast(a, C.POINTER(C.c_int64))
+            gi_n[i] = len(gi)
+            if first is not None:
+                f = (C.c_int32 * len(first))(*first)
+                keep.append(f)
+                gf_ptrs[i] = C.cast(f, C.POINTER(C.c_int32))
+                have_first = True
+        if not have_first:
+            gf_ptrs = None
+    ctx.check(ctx.lib.fb_decode_batch(ctx.h, n, ptrs, sizes, C.byref(opts), gi_ptrs, gf_ptrs, gi_n, out), "fb_decode_batch")
     return [Image(ctx, C.c_void_p(out[i])) for i in range(n)]
 
 

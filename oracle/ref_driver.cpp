@@ -22,7 +22,7 @@
 //   decode <in.fuif> <out.pam> [-R k]
 //   dump   <in.fuif> <prefix>  [-R k]     planes after decode and after each inverse transform
 //   fwd    <in.pam>  <prefix>  [same options as encode]   planes after each forward transform
-//   time   <in.fuif> [reps]               JSON timing of entropy stage / transform chain
+//   time   <in.fuif> [reps] [out.pam]     JSON timing of entropy stage / transform chain; optionally writes the pixels
 //
 // Plane dump format ("FBPD1"): text header, then raw little-endian int16 planes:
 //   FBPD1
@@ -209,6 +209,7 @@ int main(int argc, char **argv) {
             if (t1 - t0 < best_entropy) best_entropy = t1 - t0;
             if (t2 - t1 < best_chain) best_chain = t2 - t1;
             w = img.w; h = img.h;
+            if (r == reps - 1 && argc > 4) write_PAM_file(argv[4], img);
         }
         printf("{\"w\": %d, \"h\": %d, \"entropy_s\": %.6f, \"chain_s\": %.6f, \"total_s\": %.6f}\n", w, h, best_entropy, best_chain,
                best_entropy + best_chain);

@@ -3,7 +3,8 @@ on the host, then per iteration upload them, flush L2 and time the chain with CU
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from fuif_b200 import api, workloads as wl
+from fuif_b200 import api
+import bench_workloads as wl
 from fuif_b200.synth import synth_image
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5

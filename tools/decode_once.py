@@ -1,7 +1,8 @@
 """Decodes one workload image once on cuda:0 (profiling helper: run under ncu)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from fuif_b200 import api, workloads as wl
+from fuif_b200 import api
+import bench_workloads as wl
 name = sys.argv[1] if len(sys.argv) > 1 else "mid"
 undo = "--undo" in sys.argv
 noindex = "--no-index" in sys.argv

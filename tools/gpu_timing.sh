@@ -4,7 +4,8 @@ FB_KERNEL_TIMING=1 timeout 300 python - > gpurun_out/timing.log 2>&1 <<'PY'
 import sys, os
 sys.path.insert(0, '.')
 import numpy as np, torch
-from fuif_b200 import api, workloads as wl
+from fuif_b200 import api
+import bench_workloads as wl
 im = wl.prepare_image("cfg2")
 st = torch.cuda.Stream(); torch.cuda.set_stream(st); ctx = api.Context(0, st.cuda_stream)
 img = api.fuif_decode(im["fuif"], ctx=ctx, group_index=im["index"])
