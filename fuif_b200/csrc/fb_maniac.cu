@@ -183,23 +183,20 @@ __device__ __forceinline__ uint16_t initial_chance(int idx, int zero_chance) {  
 // so there is exactly one reader/writer and no lockstep assumption between lanes.
 //
 // SymCtx implements FinalCompoundSymbolBitCoder::read (compound.h:90-95): decode with chance lp[idx], then
-// lp[idx] = table[chance][bit].  The table lookup of bit k is consumed one bit later (delayed store), so its
-// shared-memory latency overlaps the next bit's chance load instead of stalling the in-order warp.
+// lp[idx] = table[chance][bit].  Both successors of the chance are fetched as one 32-bit word right after the chance
+// itself, so the table lookup overlaps the range arithmetic instead of following it.
 struct SymCtx {
-    const uint16_t *table;
+    const unsigned *tab32;      // newchance[4096][2] viewed as 4096 words: low half = successor after a 0, high half after a 1
     uint16_t *lp;
-    int pi;
-    unsigned pv;
-    __device__ __forceinline__ void begin(const uint16_t *t, uint16_t *leaf) { table = t; lp = leaf; pi = -1; pv = 0; }
+    __device__ __forceinline__ void begin(const uint16_t *t, uint16_t *leaf) { tab32 = reinterpret_cast<const unsigned *>(t); lp = leaf; }
     __device__ __forceinline__ int read(Rac &rac, int idx) {
         const unsigned ch = lp[idx];
-        if (pi >= 0) lp[pi] = (uint16_t)pv;
+        const unsigned both = tab32[ch];        // issued before the bit is known: off the coder's dependency chain
         const int bit = rac.read12(ch);
-        pv = table[ch * 2 + bit];
-        pi = idx;
+        lp[idx] = (uint16_t)(bit ? (both >> 16) : (both & 0xffffu));
         return bit;
     }
-    __device__ __forceinline__ void end() { if (pi >= 0) lp[pi] = (uint16_t)pv; pi = -1; }
+    __device__ __forceinline__ void end() {}
 };
 
 // reader<15>(coder, min, max), symbol.h:154-185
@@ -449,6 +446,11 @@ __device__ __forceinline__ void decode_row(DImage &img, DChan &ch, int y, int pr
     const int role = lane - nref;
     const int zero = ch.zero, cmin = ch.minval, cmax = ch.maxval;
     const int vshift = ch.vshift, hshift = ch.hshift;
+    // lane role -> operands / function of its left-dependent property (roles 1,3,6,7,8,9,12)
+    const bool is_ld = role == 1 || role == 3 || role == 6 || role == 7 || role == 8 || role == 9 || role == 12;
+    const bool selA1 = role == 6, selA2 = role == 7, selA3 = role == 9;
+    const bool selB1 = role == 6 || role == 8, selB2 = role == 7 || role == 9, selB3 = role == 12;
+    const bool mode_abs = role == 1, mode_id = role == 6 || role == 7;
     int left = zero, leftleft = zero;
     for (int x0 = 0; x0 < w; x0 += 32) {
         const int x = x0 + lane;
@@ -499,11 +501,22 @@ __device__ __forceinline__ void decode_row(DImage &img, DChan &ch, int y, int pr
             const int top = pp[32];
             const int topleft = (xx && y) ? pp[33] : left;         // context_predict.h:128
             const int topright = pp[34];
-            // the properties that depend on the pixel just decoded (predict_and_compute_properties, context_predict.h:135-154)
-            const int q1 = fooabs(left), q3 = slog(left), q6 = left + top - topleft, q7 = topleft + topright - top,
-                      q8 = slog(left - topleft), q9 = slog(topleft - top), q12 = slog(left - leftleft);
-            mine = role == 1 ? q1 : mine;   mine = role == 3 ? q3 : mine;   mine = role == 6 ? q6 : mine;   mine = role == 7 ? q7 : mine;
-            mine = role == 8 ? q8 : mine;   mine = role == 9 ? q9 : mine;   mine = role == 12 ? q12 : mine;
+            // The seven properties that depend on the pixel just decoded (context_predict.h:135-154) all have the form
+            // f(A - B): |left-0|, slog(left-0), (left+top)-topleft, (topleft+topright)-top, slog(left-topleft),
+            // slog(topleft-top), slog(left-leftleft).  Each lane evaluates only ITS expression: operands are picked with
+            // loop-invariant per-lane predicates, f with a per-lane mode.
+            {
+                const int u1 = left + top, u2 = topleft + topright;
+                int A = selA1 ? u1 : left;  A = selA2 ? u2 : A;      A = selA3 ? topleft : A;
+                int B = selB1 ? topleft : 0; B = selB2 ? top : B;     B = selB3 ? leftleft : B;
+                const int t = A - B;
+                const int t16 = s16(t), ab = abs(t16);
+                int sl = 32 - __clz(ab);
+                sl = t16 < 0 ? -sl : sl;
+                int r_ = mode_abs ? s16(ab) : sl;
+                r_ = mode_id ? t : r_;
+                mine = is_ld ? r_ : mine;
+            }
             const int guess = PRED0 ? zero : predict(predictor, left, top, topleft, topright, zero, cmin, cmax);
             const int mn = cmin - guess, mx = cmax - guess;
             int diff = mn;
