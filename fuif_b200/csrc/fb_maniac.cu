@@ -71,7 +71,8 @@ struct Params {
     const uint16_t *meta_table; // [4096][2] tree-coder table (cut 2, alpha 0xFFFFFFFF/19)
     WarpScratch *scratch;
     int maxw;
-    int warp_smem;          // bytes of shared memory per warp (after the block's 16 KiB chance table)
+    int warp_smem;          // bytes of shared memory per stream slot (after the block's 16 KiB chance table)
+    int helpers;            // walker warps per stream (0 or 2)
     int debug;              // FB_MANIAC_DEBUG=1: trace group headers from lane 0
 };
 
@@ -389,6 +390,7 @@ __device__ bool corrupt_or_truncated(bool stopped, DChan &c, int lane) {
     return false;
 }
 
+struct Mail;
 // Per-warp shared memory.
 constexpr int kPropStride = 37;     // 32 property slots (one per lane) + top, topleft, topright + padding; odd => conflict-free rows
 struct Smem {
@@ -397,6 +399,8 @@ struct Smem {
     int *cprop;             // [32][kPropStride]: per pixel of the current chunk: properties by lane, then top / topleft / topright
     unsigned char *dyn;     // dynamic region: tree-node cache, then leaf chances (resident or direct-mapped cache)
     int dyn_bytes;
+    struct Mail *mail;      // mailbox shared with the walker warps (nullptr: no walkers)
+    int nwalkers;
 };
 
 // Node cache entry (8 bytes): x = property << 16 | slot16 (uint4 index of the child pair) for inner nodes,
@@ -436,16 +440,161 @@ __device__ __forceinline__ uint4 lds128(unsigned addr) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
+// Chunk prologue (lanes = the 32 pixels x0..x0+31 of row y): neighbours from the rows above, reference properties
+// (precompute_references, context_predict.h:233-289) and every property that does not depend on `left`, written to
+// cprop[lane][...].  All lanes of the decoder warp call it.
+__device__ __forceinline__ void chunk_prologue(DImage &img, const DChan &ch, int y, int x0, const int *refchan, int nrefchan, int nref,
+                                               int *cprop, int lane) {
+    const int w = ch.w, zero = ch.zero;
+    const int x = x0 + lane;
+    if (x < w) {
+        const int16_t *row1 = ch.data + (size_t)(y - 1) * w, *row2 = row1 - w;
+        int T1 = zero, TL = zero, TR = zero, TT = zero;
+        if (y) {
+            T1 = row1[x];
+            TL = x ? row1[x - 1] : zero;
+            TR = (x + 1 < w) ? row1[x + 1] : T1;
+            TT = (y > 1) ? row2[x] : T1;
+        }
+        int *pp = cprop + lane * kPropStride;
+        for (int r = 0; r < nrefchan; r++) {
+            const DChan &cj = img.ch[refchan[r]];
+            int ry = (y << ch.vshift) >> cj.vshift;
+            if (ry >= cj.h) ry = cj.h - 1;
+            int rx;
+            if (ch.hshift == cj.hshift && w <= cj.w) rx = x;
+            else if (ch.hshift < cj.hshift) {
+                const int stepsize = (1 << cj.hshift) >> ch.hshift;     // all samples but the last are repeated stepsize times
+                rx = stepsize > 0 ? x / stepsize : cj.w - 1;
+                if (rx > cj.w - 1) rx = cj.w - 1;
+            } else {
+                rx = (x << ch.hshift) >> cj.hshift;
+                if (rx >= cj.w) rx = cj.w - 1;
+            }
+            const int v = __ldcg(cj.data + (size_t)ry * cj.w + rx);
+            pp[2 * r] = fooabs(v);
+            pp[2 * r + 1] = slog(v);
+        }
+        pp[nref + 0] = fooabs(T1);
+        pp[nref + 2] = slog(T1);
+        pp[nref + 4] = y;
+        pp[nref + 5] = x;
+        pp[nref + 10] = slog(T1 - TR);
+        pp[nref + 11] = slog(T1 - TT);
+        pp[32] = T1; pp[33] = TL; pp[34] = TR;
+    }
+}
+
+// ---- walker warps ------------------------------------------------------------------------------------------------
+// The tree walk of pixel x+1 depends on pixel x only through `left` (and on x-1 through `leftleft`).  While lane 0 of
+// the decoder warp is busy with the bits of pixel x, up to two walker warps evaluate the MANIAC tree of pixel x+1 for
+// EVERY value pixel x can take (one candidate per lane: cmin + lane, cmin + 32 + lane), and leave the leaf ids in shared
+// memory.  The decoder then needs one table lookup instead of property evaluation + tree walk on its serial chain.
+// Used when the group has predictor 0, a tree of more than one node cached in shared memory and a value range <= 64.
+struct Mail {
+    volatile int cmd_seq;       // bumped by the decoder for every command
+    int cmd;                    // 1 = row, 2 = exit
+    int y, w, zero, cmin, cmax, nref, nwalk;
+    unsigned nodes_saddr;
+    volatile int go;            // candidates of pixels <= go may be computed
+    volatile int done[2];       // walker k has published the candidates of pixels < done[k]
+    int cval[64];               // decoded values of the current row, ring indexed by x & 63
+    unsigned short cand[2][64]; // candidate leaf ids of pixel x in cand[x & 1]
+};
+constexpr int kMailBytes = 1024;
+
+__device__ void walker_main(Mail *mail, const int *cprop2 /* [2][32][kPropStride] */, int widx, int lane) {
+    int seen = 0;
+    for (;;) {
+        while (mail->cmd_seq == seen) __nanosleep(32);
+        seen = mail->cmd_seq;
+        __threadfence_block();
+        if (mail->cmd == 2) return;
+        const int y = mail->y, w = mail->w, cmin = mail->cmin, cmax = mail->cmax, nref = mail->nref;
+        if (widx >= mail->nwalk) continue;
+        const unsigned nodes_saddr = mail->nodes_saddr;
+        const int cl = cmin + 32 * widx + lane;         // this lane's candidate for `left`
+        const bool valid = cl <= cmax;
+        for (int j = 0; j < w; j++) {
+            while (mail->go < j) { }
+            __threadfence_block();
+            const int *pp = cprop2 + (((j >> 5) & 1) * 32 + (j & 31)) * kPropStride;
+            const int top = pp[32], topright = pp[34];
+            const int topleft = (j && y) ? pp[33] : cl;
+            const int leftleft = (j > 1) ? mail->cval[(j - 2) & 63] : cl;
+            const int q1 = fooabs(cl), q3 = slog(cl), q6 = cl + top - topleft, q7 = topleft + topright - top, q8 = slog(cl - topleft),
+                      q9 = slog(topleft - top), q12 = slog(cl - leftleft);
+            const uint4 r0 = lds128(nodes_saddr);
+            uint2 cur = make_uint2(r0.z, r0.w);
+            while ((int)cur.x >= 0) {
+                const uint4 pair = lds128(nodes_saddr + ((cur.x & 0xffffu) << 4));
+                const int p = (int)(cur.x >> 16), role = p - nref;
+                int v = pp[p];
+                v = role == 1 ? q1 : v;  v = role == 3 ? q3 : v;  v = role == 6 ? q6 : v;  v = role == 7 ? q7 : v;
+                v = role == 8 ? q8 : v;  v = role == 9 ? q9 : v;  v = role == 12 ? q12 : v;
+                cur = (v > (int)cur.y) ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
+            }
+            if (valid) mail->cand[j & 1][cl - cmin] = (unsigned short)(cur.x & 0xffffu);
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) mail->done[widx] = j + 1;
+        }
+    }
+}
+
+// One row with walker warps (PRED0, nodes in shared memory).  Same results as decode_row.
+__device__ __forceinline__ void decode_row_helped(DImage &img, DChan &ch, int y, const int *refchan, int nrefchan, int nref, Rac &rac,
+                                                  const Smem &sm, const LeafStore &ls, Mail *mail, int nwalk, int lane) {
+    const int w = ch.w;
+    int16_t *row = ch.data + (size_t)y * w;
+    const int zero = ch.zero, cmin = ch.minval, cmax = ch.maxval;
+    const int mn = cmin - zero, mx = cmax - zero;           // predictor 0: guess = zero
+    chunk_prologue(img, ch, y, 0, refchan, nrefchan, nref, sm.cprop, lane);
+    if (w > 32) chunk_prologue(img, ch, y, 32, refchan, nrefchan, nref, sm.cprop + 32 * kPropStride, lane);
+    __syncwarp();
+    if (lane == 0) {
+        mail->y = y; mail->w = w; mail->zero = zero; mail->cmin = cmin; mail->cmax = cmax; mail->nref = nref; mail->nwalk = nwalk;
+        mail->go = 0; mail->done[0] = 0; mail->done[1] = 0; mail->cmd = 1;
+        __threadfence_block();
+        mail->cmd_seq = mail->cmd_seq + 1;
+    }
+    int left = zero;
+    for (int x0 = 0; x0 < w; x0 += 32) {
+        if (x0 > 0 && x0 + 32 < w) {      // properties of the chunk after this one (its buffer is free: nobody reads chunk x0-32 any more)
+            chunk_prologue(img, ch, y, x0 + 32, refchan, nrefchan, nref, sm.cprop + (((x0 >> 5) + 1) & 1) * 32 * kPropStride, lane);
+            __syncwarp();
+        }
+        int outv = 0;
+        const int cnt = min(32, w - x0);
+        for (int i = 0; i < cnt; i++) {
+            const int xx = x0 + i;
+            if (lane == 0) { __threadfence_block(); mail->go = xx + 1; }        // candidates of pixel xx+1 may start (val(xx-1) is in cval)
+            const int k = (left - cmin) >> 5;
+            while (mail->done[k] < xx + 1) { }
+            __threadfence_block();
+            const int leaf = mail->cand[xx & 1][left - cmin];
+            uint16_t *lp = leaf_lookup(ls, leaf, lane);
+            int diff = mn;
+            if (lane == 0) diff = read_int(rac, sm.table, lp, mn, mx);
+            diff = __shfl_sync(0xffffffffu, diff, 0);
+            const int val = s16(s16(diff) + zero);
+            if (lane == 0) mail->cval[xx & 63] = val;
+            outv = (lane == i) ? val : outv;
+            left = val;
+        }
+        if (x0 + lane < w) row[x0 + lane] = (int16_t)outv;
+        __syncwarp();
+    }
+}
+
 template <bool NODES_SMEM, bool PRED0>
 __device__ __forceinline__ void decode_row(DImage &img, DChan &ch, int y, int predictor, const int *refchan, int nrefchan, int nref,
                                            Rac &rac, const Smem &sm, const uint2 *nodes2, const LeafStore &ls, int lane) {
     const unsigned nodes_saddr = NODES_SMEM ? (unsigned)__cvta_generic_to_shared(nodes2) : 0u;
     const int w = ch.w;
     int16_t *row = ch.data + (size_t)y * w;
-    const int16_t *row1 = row - w, *row2 = row - 2 * w;
     const int role = lane - nref;
     const int zero = ch.zero, cmin = ch.minval, cmax = ch.maxval;
-    const int vshift = ch.vshift, hshift = ch.hshift;
     // lane role -> operands / function of its left-dependent property (roles 1,3,6,7,8,9,12)
     const bool is_ld = role == 1 || role == 3 || role == 6 || role == 7 || role == 8 || role == 9 || role == 12;
     const bool selA1 = role == 6, selA2 = role == 7, selA3 = role == 9;
@@ -454,43 +603,7 @@ __device__ __forceinline__ void decode_row(DImage &img, DChan &ch, int y, int pr
     int left = zero, leftleft = zero;
     for (int x0 = 0; x0 < w; x0 += 32) {
         const int x = x0 + lane;
-        // --- chunk prologue (lanes = pixels): neighbours from the rows above, reference properties
-        //     (precompute_references, context_predict.h:233-289) and every property that does not depend on `left`
-        if (x < w) {
-            int T1 = zero, TL = zero, TR = zero, TT = zero;
-            if (y) {
-                T1 = row1[x];
-                TL = x ? row1[x - 1] : zero;
-                TR = (x + 1 < w) ? row1[x + 1] : T1;
-                TT = (y > 1) ? row2[x] : T1;
-            }
-            int *pp = sm.cprop + lane * kPropStride;
-            for (int r = 0; r < nrefchan; r++) {
-                const DChan &cj = img.ch[refchan[r]];
-                int ry = (y << vshift) >> cj.vshift;
-                if (ry >= cj.h) ry = cj.h - 1;
-                int rx;
-                if (hshift == cj.hshift && w <= cj.w) rx = x;
-                else if (hshift < cj.hshift) {
-                    const int stepsize = (1 << cj.hshift) >> hshift;     // all samples but the last are repeated stepsize times
-                    rx = stepsize > 0 ? x / stepsize : cj.w - 1;
-                    if (rx > cj.w - 1) rx = cj.w - 1;
-                } else {
-                    rx = (x << hshift) >> cj.hshift;
-                    if (rx >= cj.w) rx = cj.w - 1;
-                }
-                const int v = __ldcg(cj.data + (size_t)ry * cj.w + rx);
-                pp[2 * r] = fooabs(v);
-                pp[2 * r + 1] = slog(v);
-            }
-            pp[nref + 0] = fooabs(T1);
-            pp[nref + 2] = slog(T1);
-            pp[nref + 4] = y;
-            pp[nref + 5] = x;
-            pp[nref + 10] = slog(T1 - TR);
-            pp[nref + 11] = slog(T1 - TT);
-            pp[32] = T1; pp[33] = TL; pp[34] = TR;
-        }
+        chunk_prologue(img, ch, y, x0, refchan, nrefchan, nref, sm.cprop, lane);
         __syncwarp();
         int outv = 0;
         const int cnt = min(32, w - x0);
@@ -708,6 +821,10 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
             }
             __syncwarp();
         } else {
+            const int range = ch.maxval - ch.minval + 1;
+            const bool helped = sm.mail && snodes && predictor == 0 && nnodes > 1 && range <= 32 * sm.nwalkers && range >= 1;
+            const int nwalk = (range + 31) / 32;
+            if (helped && lane == 0) sm.mail->nodes_saddr = (unsigned)__cvta_generic_to_shared(snodes);
             for (int y = 0; y < ch.h; y++) {
                 if (STOPPED()) break;
                 for (int r = 0; r < nrefchan; r++) {       // row wavefront on the planes this row back-references
@@ -716,7 +833,8 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
                     if (ry >= cj.h) ry = cj.h - 1;
                     spin_until_ge(&cj.rows_done, ry + 1);
                 }
-                if (snodes) {
+                if (helped) decode_row_helped(img, ch, y, refchan, nrefchan, nref, rac, sm, ls, sm.mail, nwalk, lane);
+                else if (snodes) {
                     if (predictor == 0) decode_row<true, true>(img, ch, y, predictor, refchan, nrefchan, nref, rac, sm, nodes2, ls, lane);
                     else decode_row<true, false>(img, ch, y, predictor, refchan, nrefchan, nref, rac, sm, nodes2, ls, lane);
                 } else {
@@ -738,17 +856,28 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
 __global__ void k_maniac_decode(Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wps = 1 + P.helpers;                       // warps per stream: decoder + walkers
+    const int slot = warp / wps, wrole = warp % wps;
     uint16_t *s_table = reinterpret_cast<uint16_t *>(smem_raw);                      // 16 KiB, shared by the block's warps
     for (int i = threadIdx.x; i < 4096 * 2; i += blockDim.x) s_table[i] = P.table[i];
     __syncthreads();
-    unsigned char *mine = smem_raw + 16384 + (size_t)warp * P.warp_smem;
+    unsigned char *mine = smem_raw + 16384 + (size_t)slot * P.warp_smem;
     Smem sm;
     sm.table = s_table;
     sm.coder = reinterpret_cast<uint16_t(*)[32]>(mine);                               // 192 B
-    sm.cprop = reinterpret_cast<int *>(mine + 256);                                   // 32*37*4 = 4736 B
-    sm.dyn = mine + 256 + 4736;
-    sm.dyn_bytes = P.warp_smem - 256 - 4736;
-    WarpScratch ws = P.scratch[blockIdx.x * (blockDim.x >> 5) + warp];
+    const int cprop_bytes = P.helpers ? 2 * 4736 : 4736;         // chunk properties, double-buffered when walkers run ahead
+    const int mail_bytes = P.helpers ? kMailBytes : 0;
+    sm.cprop = reinterpret_cast<int *>(mine + 256);
+    sm.mail = P.helpers ? reinterpret_cast<Mail *>(mine + 256 + cprop_bytes) : nullptr;
+    sm.nwalkers = P.helpers;
+    sm.dyn = mine + 256 + cprop_bytes + mail_bytes;
+    sm.dyn_bytes = P.warp_smem - 256 - cprop_bytes - mail_bytes;
+    if (P.helpers) {
+        if (wrole == 0 && lane == 0) { sm.mail->cmd_seq = 0; sm.mail->cmd = 0; sm.mail->go = 0; sm.mail->done[0] = 0; sm.mail->done[1] = 0; }
+        __syncthreads();
+        if (wrole > 0) { walker_main(sm.mail, sm.cprop, wrole - 1, lane); return; }
+    }
+    WarpScratch ws = P.scratch[blockIdx.x * (blockDim.x >> 5) / wps + slot];
     for (;;) {
         int sid = 0;
         if (lane == 0) sid = atomicAdd(P.ticket, 1);
@@ -778,6 +907,11 @@ __global__ void k_maniac_decode(Params P) {
                 st_release(&img.ch[c].rows_done, 0x7fffffff);
             }
         __syncwarp();
+    }
+    if (P.helpers && lane == 0) {       // release the walkers
+        sm.mail->cmd = 2;
+        __threadfence_block();
+        sm.mail->cmd_seq = sm.mail->cmd_seq + 1;
     }
 }
 
@@ -990,7 +1124,9 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         // that the whole MANIAC tree and most leaf chances of a stream stay on-chip.  Many streams (batches): up to 8
         // warps share a block's 16 KiB chance table and up to two blocks share an SM.
         const int per_sm = (nstreams + ctx->sm_count - 1) / ctx->sm_count;
-        const int wpb = std::max(1, std::min(8, per_sm));
+        // one stream per SM: give it two walker warps as well (see walker_main)
+        P.helpers = (per_sm == 1 && !getenv("FB_MANIAC_NO_WALKERS")) ? 2 : 0;
+        const int wpb = std::max(1, std::min(8, per_sm));          // streams per block
         const int blocks_per_sm = std::max(1, std::min(2, (per_sm + wpb - 1) / wpb));
         const int nblocks = std::min((nstreams + wpb - 1) / wpb, ctx->sm_count * blocks_per_sm);
         const size_t block_smem = blocks_per_sm == 1 ? 200 * 1024 : 105 * 1024;
@@ -998,7 +1134,7 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         P.warp_smem = (int)warp_smem;
         const size_t smem_bytes = 16384 + warp_smem * wpb;
         FB_CUDA(ctx, cudaFuncSetAttribute(k_maniac_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        k_maniac_decode<<<nblocks, 32 * wpb, smem_bytes, ctx->stream>>>(P);
+        k_maniac_decode<<<nblocks, 32 * wpb * (1 + P.helpers), smem_bytes, ctx->stream>>>(P);
         ctx->launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { ctx->err = std::string("maniac launch: ") + cudaGetErrorString(e); return FB_ERR_CUDA; }
