@@ -72,7 +72,7 @@ struct Params {
     WarpScratch *scratch;
     int maxw;
     int warp_smem;          // bytes of shared memory per stream slot (after the block's 16 KiB chance table)
-    int helpers;            // walker warps per stream (0 or 2)
+    int helpers;            // walker warps per stream (0 or kMaxWalkers)
     int debug;              // FB_MANIAC_DEBUG=1: trace group headers from lane 0
 };
 
@@ -400,6 +400,7 @@ struct Smem {
     unsigned char *dyn;     // dynamic region: tree-node cache, then leaf chances (resident or direct-mapped cache)
     int dyn_bytes;
     struct Mail *mail;      // mailbox shared with the walker warps (nullptr: no walkers)
+    int *ldrows;            // [walkers][32][kLdRowStride] per-lane property values of the walkers
     int nwalkers;
 };
 
@@ -497,45 +498,59 @@ struct Mail {
     int y, w, zero, cmin, cmax, nref, nwalk;
     unsigned nodes_saddr;
     volatile int go;            // candidates of pixels <= go may be computed
-    volatile int done[2];       // walker k has published the candidates of pixels < done[k]
+    volatile int done[8];       // walker k has published the candidates of pixels < done[k]
     int cval[64];               // decoded values of the current row, ring indexed by x & 63
-    unsigned short cand[2][64]; // candidate leaf ids of pixel x in cand[x & 1]
+    unsigned short cand[2][256];// candidate leaf ids of pixel x in cand[x & 1]
 };
-constexpr int kMailBytes = 1024;
+constexpr int kMailBytes = 1536;
+constexpr int kMaxWalkers = 8;  // value ranges up to 256
 
-__device__ void walker_main(Mail *mail, const int *cprop2 /* [2][32][kPropStride] */, int widx, int lane) {
+#define COMPILER_FENCE() asm volatile("" ::: "memory")
+__device__ __forceinline__ int lds32(unsigned addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+constexpr int kLdRowStride = 9;     // words per walker lane: its 7 left-dependent property values (+ padding)
+
+// Shared-memory accesses of one warp are performed in program order and there is no cache between the warps of a block,
+// so the flag protocol below needs compiler barriers only (no MEMBAR per pixel).
+__device__ void walker_main(Mail *mail, const int *cprop2 /* [2][32][kPropStride] */, int *ldrows, int widx, int lane) {
     int seen = 0;
+    int *myrow = ldrows + (widx * 32 + lane) * kLdRowStride;
+    const unsigned ld_s = (unsigned)__cvta_generic_to_shared(myrow) - 64 * 4;      // biased: offsets 64.. address this row
     for (;;) {
         while (mail->cmd_seq == seen) __nanosleep(32);
         seen = mail->cmd_seq;
         __threadfence_block();
         if (mail->cmd == 2) return;
-        const int y = mail->y, w = mail->w, cmin = mail->cmin, cmax = mail->cmax, nref = mail->nref;
+        const int y = mail->y, w = mail->w, cmin = mail->cmin, cmax = mail->cmax;
         if (widx >= mail->nwalk) continue;
         const unsigned nodes_saddr = mail->nodes_saddr;
         const int cl = cmin + 32 * widx + lane;         // this lane's candidate for `left`
         const bool valid = cl <= cmax;
+        const int q1 = fooabs(cl), q3 = slog(cl);
         for (int j = 0; j < w; j++) {
             while (mail->go < j) { }
-            __threadfence_block();
+            COMPILER_FENCE();
             const int *pp = cprop2 + (((j >> 5) & 1) * 32 + (j & 31)) * kPropStride;
+            const unsigned pp_s = (unsigned)__cvta_generic_to_shared(pp);
             const int top = pp[32], topright = pp[34];
             const int topleft = (j && y) ? pp[33] : cl;
-            const int leftleft = (j > 1) ? mail->cval[(j - 2) & 63] : cl;
-            const int q1 = fooabs(cl), q3 = slog(cl), q6 = cl + top - topleft, q7 = topleft + topright - top, q8 = slog(cl - topleft),
-                      q9 = slog(topleft - top), q12 = slog(cl - leftleft);
+            const int leftleft = (j > 1) ? ((volatile int *)mail->cval)[(j - 2) & 63] : cl;
+            myrow[0] = q1; myrow[1] = q3; myrow[2] = cl + top - topleft; myrow[3] = topleft + topright - top;
+            myrow[4] = slog(cl - topleft); myrow[5] = slog(topleft - top); myrow[6] = slog(cl - leftleft);
+            COMPILER_FENCE();       // the asm loads below read these
             const uint4 r0 = lds128(nodes_saddr);
             uint2 cur = make_uint2(r0.z, r0.w);
             while ((int)cur.x >= 0) {
                 const uint4 pair = lds128(nodes_saddr + ((cur.x & 0xffffu) << 4));
-                const int p = (int)(cur.x >> 16), role = p - nref;
-                int v = pp[p];
-                v = role == 1 ? q1 : v;  v = role == 3 ? q3 : v;  v = role == 6 ? q6 : v;  v = role == 7 ? q7 : v;
-                v = role == 8 ? q8 : v;  v = role == 9 ? q9 : v;  v = role == 12 ? q12 : v;
+                const unsigned off = cur.x >> 16;       // < 64: word of the shared property row, >= 64: word of this lane's row
+                const int v = lds32((off >= 64u ? ld_s : pp_s) + off * 4);
                 cur = (v > (int)cur.y) ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
             }
-            if (valid) mail->cand[j & 1][cl - cmin] = (unsigned short)(cur.x & 0xffffu);
-            __threadfence_block();
+            if (valid) ((volatile unsigned short *)mail->cand[j & 1])[cl - cmin] = (unsigned short)(cur.x & 0xffffu);
+            COMPILER_FENCE();
             __syncwarp();
             if (lane == 0) mail->done[widx] = j + 1;
         }
@@ -554,7 +569,8 @@ __device__ __forceinline__ void decode_row_helped(DImage &img, DChan &ch, int y,
     __syncwarp();
     if (lane == 0) {
         mail->y = y; mail->w = w; mail->zero = zero; mail->cmin = cmin; mail->cmax = cmax; mail->nref = nref; mail->nwalk = nwalk;
-        mail->go = 0; mail->done[0] = 0; mail->done[1] = 0; mail->cmd = 1;
+        mail->go = 0; mail->cmd = 1;
+        for (int k = 0; k < kMaxWalkers; k++) mail->done[k] = 0;
         __threadfence_block();
         mail->cmd_seq = mail->cmd_seq + 1;
     }
@@ -568,17 +584,18 @@ __device__ __forceinline__ void decode_row_helped(DImage &img, DChan &ch, int y,
         const int cnt = min(32, w - x0);
         for (int i = 0; i < cnt; i++) {
             const int xx = x0 + i;
-            if (lane == 0) { __threadfence_block(); mail->go = xx + 1; }        // candidates of pixel xx+1 may start (val(xx-1) is in cval)
+            COMPILER_FENCE();
+            if (lane == 0) mail->go = xx + 1;                                    // candidates of pixel xx+1 may start (val(xx-1) is in cval)
             const int k = (left - cmin) >> 5;
             while (mail->done[k] < xx + 1) { }
-            __threadfence_block();
-            const int leaf = mail->cand[xx & 1][left - cmin];
+            COMPILER_FENCE();
+            const int leaf = ((volatile unsigned short *)mail->cand[xx & 1])[left - cmin];
             uint16_t *lp = leaf_lookup(ls, leaf, lane);
             int diff = mn;
             if (lane == 0) diff = read_int(rac, sm.table, lp, mn, mx);
             diff = __shfl_sync(0xffffffffu, diff, 0);
             const int val = s16(s16(diff) + zero);
-            if (lane == 0) mail->cval[xx & 63] = val;
+            if (lane == 0) ((volatile int *)mail->cval)[xx & 63] = val;
             outv = (lane == i) ? val : outv;
             left = val;
         }
@@ -795,9 +812,22 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
     }
     __syncwarp();
     const uint2 *nodes2 = gpacked;
+    // Groups that can use the walker warps keep a walker-friendly copy in shared memory: the property field becomes a word
+    // offset -- < 64: into the shared per-pixel property row, 64 + k: the k-th left-dependent value of the walker's lane.
+    const bool walker_nodes = sm.mail && snodes && predictor == 0 && nnodes > 1;
     if (snodes) {
-        for (int i = lane; i < nnodes; i += 32) snodes[i + 1] = gpacked[i + 1];
-        nodes2 = snodes;
+        for (int i = lane; i < nnodes; i += 32) {
+            uint2 e = gpacked[i + 1];
+            if (walker_nodes && (int)e.x >= 0) {
+                const int pidx = (int)(e.x >> 16), role = pidx - nref;
+                int off = pidx;
+                if (role == 1) off = 64; else if (role == 3) off = 65; else if (role == 6) off = 66; else if (role == 7) off = 67;
+                else if (role == 8) off = 68; else if (role == 9) off = 69; else if (role == 12) off = 70;
+                e.x = ((unsigned)off << 16) | (e.x & 0xffffu);
+            }
+            snodes[i + 1] = e;
+        }
+        if (!walker_nodes) nodes2 = snodes;     // the decoder's own walk reads the property index, i.e. the plain encoding
     }
     __syncwarp();
     if (P.debug && lane == 0)
@@ -822,9 +852,10 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
             __syncwarp();
         } else {
             const int range = ch.maxval - ch.minval + 1;
-            const bool helped = sm.mail && snodes && predictor == 0 && nnodes > 1 && range <= 32 * sm.nwalkers && range >= 1;
+            const bool helped = walker_nodes && range <= 32 * sm.nwalkers && range >= 1;
             const int nwalk = (range + 31) / 32;
             if (helped && lane == 0) sm.mail->nodes_saddr = (unsigned)__cvta_generic_to_shared(snodes);
+            const long long t_start = clock64();
             for (int y = 0; y < ch.h; y++) {
                 if (STOPPED()) break;
                 for (int r = 0; r < nrefchan; r++) {       // row wavefront on the planes this row back-references
@@ -834,7 +865,7 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
                     spin_until_ge(&cj.rows_done, ry + 1);
                 }
                 if (helped) decode_row_helped(img, ch, y, refchan, nrefchan, nref, rac, sm, ls, sm.mail, nwalk, lane);
-                else if (snodes) {
+                else if (snodes && !walker_nodes) {
                     if (predictor == 0) decode_row<true, true>(img, ch, y, predictor, refchan, nrefchan, nref, rac, sm, nodes2, ls, lane);
                     else decode_row<true, false>(img, ch, y, predictor, refchan, nrefchan, nref, rac, sm, nodes2, ls, lane);
                 } else {
@@ -843,6 +874,9 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
                 }
                 publish_rows(ch, y + 1, lane);
             }
+            if (P.debug && lane == 0)
+                printf("[maniac]   ch %d %dx%d range %d nodes %d helped %d walkers %d: %.0f cycles/symbol\n", i, ch.w, ch.h, range, nnodes, (int)helped, nwalk,
+                       (double)(clock64() - t_start) / ((double)ch.w * ch.h));
         }
         if (STOPPED()) break;
     }
@@ -866,16 +900,17 @@ __global__ void k_maniac_decode(Params P) {
     sm.table = s_table;
     sm.coder = reinterpret_cast<uint16_t(*)[32]>(mine);                               // 192 B
     const int cprop_bytes = P.helpers ? 2 * 4736 : 4736;         // chunk properties, double-buffered when walkers run ahead
-    const int mail_bytes = P.helpers ? kMailBytes : 0;
+    const int mail_bytes = P.helpers ? kMailBytes + kMaxWalkers * 32 * kLdRowStride * 4 : 0;
     sm.cprop = reinterpret_cast<int *>(mine + 256);
     sm.mail = P.helpers ? reinterpret_cast<Mail *>(mine + 256 + cprop_bytes) : nullptr;
+    sm.ldrows = P.helpers ? reinterpret_cast<int *>(mine + 256 + cprop_bytes + kMailBytes) : nullptr;
     sm.nwalkers = P.helpers;
     sm.dyn = mine + 256 + cprop_bytes + mail_bytes;
     sm.dyn_bytes = P.warp_smem - 256 - cprop_bytes - mail_bytes;
     if (P.helpers) {
-        if (wrole == 0 && lane == 0) { sm.mail->cmd_seq = 0; sm.mail->cmd = 0; sm.mail->go = 0; sm.mail->done[0] = 0; sm.mail->done[1] = 0; }
+        if (wrole == 0 && lane == 0) { sm.mail->cmd_seq = 0; sm.mail->cmd = 0; sm.mail->go = 0; }
         __syncthreads();
-        if (wrole > 0) { walker_main(sm.mail, sm.cprop, wrole - 1, lane); return; }
+        if (wrole > 0) { walker_main(sm.mail, sm.cprop, sm.ldrows, wrole - 1, lane); return; }
     }
     WarpScratch ws = P.scratch[blockIdx.x * (blockDim.x >> 5) / wps + slot];
     for (;;) {
@@ -1125,7 +1160,7 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         // warps share a block's 16 KiB chance table and up to two blocks share an SM.
         const int per_sm = (nstreams + ctx->sm_count - 1) / ctx->sm_count;
         // one stream per SM: give it two walker warps as well (see walker_main)
-        P.helpers = (per_sm == 1 && !getenv("FB_MANIAC_NO_WALKERS")) ? 2 : 0;
+        P.helpers = (per_sm == 1 && !getenv("FB_MANIAC_NO_WALKERS")) ? kMaxWalkers : 0;
         const int wpb = std::max(1, std::min(8, per_sm));          // streams per block
         const int blocks_per_sm = std::max(1, std::min(2, (per_sm + wpb - 1) / wpb));
         const int nblocks = std::min((nstreams + wpb - 1) / wpb, ctx->sm_count * blocks_per_sm);
