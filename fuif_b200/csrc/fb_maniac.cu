@@ -201,7 +201,8 @@ struct SymCtx {
 };
 
 // reader<15>(coder, min, max), symbol.h:154-185
-__device__ __forceinline__ int read_int(Rac &rac, const uint16_t *__restrict__ table, uint16_t *leaf, int mn, int mx) {
+// mant_base: index of bit_mant[0] in the leaf (16 in the full layout, 9 in the compact one, see LeafStore)
+__device__ __forceinline__ int read_int(Rac &rac, const uint16_t *__restrict__ table, uint16_t *leaf, int mn, int mx, int mant_base = SC_MANT) {
     if (mn == mx) return mn;
     SymCtx c;
     c.begin(table, leaf);
@@ -219,7 +220,7 @@ __device__ __forceinline__ int read_int(Rac &rac, const uint16_t *__restrict__ t
             pos--;
             const int minabs1 = have | (1 << pos);
             if (minabs1 > amax) continue;
-            if (c.read(rac, SC_MANT + pos)) have = minabs1;
+            if (c.read(rac, mant_base + pos)) have = minabs1;
         }
         result = sign ? have : -have;
     }
@@ -407,8 +408,12 @@ struct Smem {
 // Node cache entry (8 bytes): x = property << 16 | slot16 (uint4 index of the child pair) for inner nodes,
 // x = 0xFFFF0000 | leaf id for leaves (sign bit set);  y = split value.  Slot i+1 holds node i so that sibling pairs
 // (odd node index, next) share one 16-byte line.
+// Leaf layout: full = 32 chances (zero, sign, exp[14], mant[15], pad); compact = 16 chances (zero, sign, exp[7], mant[7]) when
+// no value of the group can need more than 7 exponent / mantissa bits (value range <= 255) -- twice as many leaves on-chip.
 struct LeafStore {
-    uint16_t *lines;        // shared memory: nlines x 32 chances
+    int shift;              // log2(chances per leaf): 5 or 4
+    int mant_base;          // 16 or 9
+    uint16_t *lines;        // shared memory: nlines x (1 << shift) chances
     int *tags;              // direct-mapped tags (nullptr when every leaf is resident)
     int mask;               // nlines - 1
     uint16_t *gleaves;      // global backing store
@@ -416,16 +421,17 @@ struct LeafStore {
 
 // Returns the shared-memory address of leaf `leaf`'s 32 chances; all lanes cooperate on a miss.
 __device__ __forceinline__ uint16_t *leaf_lookup(const LeafStore &ls, int leaf, int lane) {
-    if (!ls.tags) return ls.lines + 32 * leaf;
+    if (!ls.tags) return ls.lines + ((size_t)leaf << ls.shift);
     const int slot = leaf & ls.mask;
     const int tag = ls.tags[slot];
-    uint16_t *line = ls.lines + 32 * slot;
+    uint16_t *line = ls.lines + ((size_t)slot << ls.shift);
+    const int words = 1 << (ls.shift - 1);
     if (tag != leaf) {
         __syncwarp();       // lane 0's chance updates of the line being evicted are visible to the copying lanes
-        if (lane < 16) {
+        if (lane < words) {
             unsigned *s = reinterpret_cast<unsigned *>(line);
-            if (tag >= 0) reinterpret_cast<unsigned *>(ls.gleaves + 32 * (size_t)tag)[lane] = s[lane];
-            s[lane] = reinterpret_cast<const unsigned *>(ls.gleaves + 32 * (size_t)leaf)[lane];
+            if (tag >= 0) reinterpret_cast<unsigned *>(ls.gleaves + ((size_t)tag << ls.shift))[lane] = s[lane];
+            s[lane] = reinterpret_cast<const unsigned *>(ls.gleaves + ((size_t)leaf << ls.shift))[lane];
         }
         if (lane == 0) ls.tags[slot] = leaf;
         __syncwarp();
@@ -592,7 +598,7 @@ __device__ __forceinline__ void decode_row_helped(DImage &img, DChan &ch, int y,
             const int leaf = ((volatile unsigned short *)mail->cand[xx & 1])[left - cmin];
             uint16_t *lp = leaf_lookup(ls, leaf, lane);
             int diff = mn;
-            if (lane == 0) diff = read_int(rac, sm.table, lp, mn, mx);
+            if (lane == 0) diff = read_int(rac, sm.table, lp, mn, mx, ls.mant_base);
             diff = __shfl_sync(0xffffffffu, diff, 0);
             const int val = s16(s16(diff) + zero);
             if (lane == 0) ((volatile int *)mail->cval)[xx & 63] = val;
@@ -663,7 +669,7 @@ __device__ __forceinline__ void decode_row(DImage &img, DChan &ch, int y, int pr
                     cur = (v > (int)cur.y) ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
                 }
                 uint16_t *lp = leaf_lookup(ls, (int)(cur.x & 0xffffu), lane);
-                if (lane == 0) diff = read_int(rac, sm.table, lp, mn, mx);
+                if (lane == 0) diff = read_int(rac, sm.table, lp, mn, mx, ls.mant_base);
                 diff = __shfl_sync(0xffffffffu, diff, 0);
             }
             const int val = s16(s16(diff) + guess);
@@ -786,17 +792,30 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
     LeafStore ls;
     ls.gleaves = ws.leaves;
     const int rem = sm.dyn_bytes - dyn_off;
-    if (nleaves * 64 <= rem) {                  // every leaf resident
+    int group_range = 0;
+    for (int i = beginc; i <= endc; i++) group_range = max(group_range, img.ch[i].maxval - img.ch[i].minval + 1);
+    const bool compact = group_range <= 255;
+    ls.shift = compact ? 4 : 5;
+    ls.mant_base = compact ? 9 : SC_MANT;
+    const int lbytes = 2 << ls.shift;           // bytes per leaf
+    // initial chance of entry e of a leaf in the chosen layout
+    auto init_entry = [&](int e) -> uint16_t {
+        if (!compact) return initial_chance(e, predictability);
+        if (e < 2) return initial_chance(e, predictability);
+        if (e < 9) return initial_chance(SC_EXP + (e - 2), predictability);
+        return 1024;
+    };
+    if (nleaves * lbytes <= rem) {              // every leaf resident
         ls.lines = reinterpret_cast<uint16_t *>(sm.dyn + dyn_off); ls.tags = nullptr; ls.mask = 0;
-        for (int i = lane; i < nleaves * 32; i += 32) ls.lines[i] = initial_chance(i & 31, predictability);
+        for (int i = lane; i < (nleaves << ls.shift); i += 32) ls.lines[i] = init_entry(i & ((1 << ls.shift) - 1));
     } else {                                    // direct-mapped cache over the global leaf array
         int nlines = 1;
-        while (nlines * 2 * 68 <= rem) nlines *= 2;
+        while (nlines * 2 * (lbytes + 4) <= rem) nlines *= 2;
         ls.tags = reinterpret_cast<int *>(sm.dyn + dyn_off);
         ls.lines = reinterpret_cast<uint16_t *>(sm.dyn + dyn_off + ((nlines * 4 + 15) & ~15));
         ls.mask = nlines - 1;
         for (int i = lane; i < nlines; i += 32) ls.tags[i] = -1;
-        for (int i = lane; i < nleaves * 32; i += 32) ws.leaves[i] = initial_chance(i & 31, predictability);
+        for (int i = lane; i < (nleaves << ls.shift); i += 32) ws.leaves[i] = init_entry(i & ((1 << ls.shift) - 1));
     }
     // node cache: packed entries, see struct LeafStore comment
     uint2 *gpacked = reinterpret_cast<uint2 *>(ws.stack);      // the parse stack is free again: reuse it for the packed nodes
@@ -845,7 +864,7 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
                 for (int y = 0; y < ch.h; y++) {
                     if (rac.io.stop()) break;
                     int16_t *row = ch.data + (size_t)y * ch.w;
-                    for (int x = 0; x < ch.w; x++) row[x] = (int16_t)read_int(rac, sm.table, lp, ch.minval, ch.maxval);
+                    for (int x = 0; x < ch.w; x++) row[x] = (int16_t)read_int(rac, sm.table, lp, ch.minval, ch.maxval, ls.mant_base);
                     st_release(&ch.rows_done, y + 1);
                 }
             }
@@ -900,7 +919,7 @@ __global__ void k_maniac_decode(Params P) {
     sm.table = s_table;
     sm.coder = reinterpret_cast<uint16_t(*)[32]>(mine);                               // 192 B
     const int cprop_bytes = P.helpers ? 2 * 4736 : 4736;         // chunk properties, double-buffered when walkers run ahead
-    const int mail_bytes = P.helpers ? kMailBytes + kMaxWalkers * 32 * kLdRowStride * 4 : 0;
+    const int mail_bytes = P.helpers ? kMailBytes + P.helpers * 32 * kLdRowStride * 4 : 0;
     sm.cprop = reinterpret_cast<int *>(mine + 256);
     sm.mail = P.helpers ? reinterpret_cast<Mail *>(mine + 256 + cprop_bytes) : nullptr;
     sm.ldrows = P.helpers ? reinterpret_cast<int *>(mine + 256 + cprop_bytes + kMailBytes) : nullptr;
@@ -1141,12 +1160,26 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         coff += img->ch.size();
     }
     FB_CUDA(ctx, cudaMemcpyAsync(img_dev, himg.data(), nimg * sizeof(DImage), cudaMemcpyHostToDevice, ctx->stream));
+    if (nimg > 1) {
+        // group-major ticket order: the k-th stream of every image before any (k+1)-th stream.  A stream still only depends on
+        // lower tickets (earlier groups of its own image), and the large late groups of all images end up running together
+        // instead of trailing image by image.
+        std::vector<int> ord(streams.size());
+        std::vector<int> seen(nimg, 0);
+        for (size_t k = 0; k < streams.size(); k++) ord[k] = seen[streams[k].image]++;
+        std::vector<size_t> idx(streams.size());
+        for (size_t k = 0; k < idx.size(); k++) idx[k] = k;
+        std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return ord[a] < ord[b]; });
+        std::vector<DStream> sorted(streams.size());
+        for (size_t k = 0; k < idx.size(); k++) sorted[k] = streams[idx[k]];
+        streams.swap(sorted);
+    }
     const int nstreams = (int)streams.size();
     if (nstreams) {
         // streams are ordered image-major, groups ascending: dependencies always point to lower stream ids
         FB_CUDA(ctx, cudaMallocAsync((void **)&streams_dev, nstreams * sizeof(DStream), ctx->stream));
         FB_CUDA(ctx, cudaMemcpyAsync(streams_dev, streams.data(), nstreams * sizeof(DStream), cudaMemcpyHostToDevice, ctx->stream));
-        const int nslots = std::min((nstreams + 7) / 8 * 8, ctx->sm_count * 16);      // scratch slots: one per resident warp
+        const int nslots = std::min((nstreams + 3) / 4 * 4, ctx->sm_count * 4);        // scratch slots: one per stream in flight
         int rc = ensure_state(ctx, cutoff, alpha, nslots, maxw);
         if (rc) return rc;
         ManiacState *st = (ManiacState *)ctx->maniac_state;
@@ -1158,13 +1191,15 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         // Launch shape.  Few streams (one image): one warp per block and block per SM with ~200 KiB of shared memory, so
         // that the whole MANIAC tree and most leaf chances of a stream stay on-chip.  Many streams (batches): up to 8
         // warps share a block's 16 KiB chance table and up to two blocks share an SM.
+        // Launch shape.  A block serves `spb` streams at a time, each with one decoder warp and `helpers` walker warps, and
+        // owns one SM (~200 KiB of shared memory split between its streams: tree-node cache, leaf chances, per-chunk
+        // property rows).  Few streams (one image) => one stream per SM with 8 walkers (value ranges up to 256); batches =>
+        // up to four streams per SM with 3 walkers each (ranges up to 96; wider ranges fall back to the decoder's own walk).
         const int per_sm = (nstreams + ctx->sm_count - 1) / ctx->sm_count;
-        // one stream per SM: give it two walker warps as well (see walker_main)
-        P.helpers = (per_sm == 1 && !getenv("FB_MANIAC_NO_WALKERS")) ? kMaxWalkers : 0;
-        const int wpb = std::max(1, std::min(8, per_sm));          // streams per block
-        const int blocks_per_sm = std::max(1, std::min(2, (per_sm + wpb - 1) / wpb));
-        const int nblocks = std::min((nstreams + wpb - 1) / wpb, ctx->sm_count * blocks_per_sm);
-        const size_t block_smem = blocks_per_sm == 1 ? 200 * 1024 : 105 * 1024;
+        const int wpb = std::max(1, std::min(4, per_sm));          // streams per block
+        P.helpers = getenv("FB_MANIAC_NO_WALKERS") ? 0 : (wpb == 1 ? kMaxWalkers : (wpb == 2 ? 5 : 3));
+        const int nblocks = std::min((nstreams + wpb - 1) / wpb, ctx->sm_count);
+        const size_t block_smem = 200 * 1024;
         const size_t warp_smem = ((block_smem - 16384) / wpb) & ~(size_t)15;
         P.warp_smem = (int)warp_smem;
         const size_t smem_bytes = 16384 + warp_smem * wpb;

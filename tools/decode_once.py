@@ -12,8 +12,11 @@ for a in sys.argv:
         reps = int(a.split("=")[1])
 im = wl.prepare_image(name, want_index=not noindex)
 ctx = api.Context(0)
+import time
 for _ in range(reps):
+    t0 = time.perf_counter()
     img = api.fuif_decode(im["fuif"], ctx=ctx, group_index=im["index"])
+    print("fuif_decode wall %.3f s" % (time.perf_counter() - t0))
     if undo:
         img.undo_transforms(0)
     ctx.synchronize()
