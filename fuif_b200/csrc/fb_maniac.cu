@@ -1179,7 +1179,7 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         // streams are ordered image-major, groups ascending: dependencies always point to lower stream ids
         FB_CUDA(ctx, cudaMallocAsync((void **)&streams_dev, nstreams * sizeof(DStream), ctx->stream));
         FB_CUDA(ctx, cudaMemcpyAsync(streams_dev, streams.data(), nstreams * sizeof(DStream), cudaMemcpyHostToDevice, ctx->stream));
-        const int nslots = std::min((nstreams + 3) / 4 * 4, ctx->sm_count * 4);        // scratch slots: one per stream in flight
+        const int nslots = std::min((nstreams + 1) / 2 * 2, ctx->sm_count * 2);        // scratch slots: one per stream in flight
         int rc = ensure_state(ctx, cutoff, alpha, nslots, maxw);
         if (rc) return rc;
         ManiacState *st = (ManiacState *)ctx->maniac_state;
@@ -1194,10 +1194,10 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         // Launch shape.  A block serves `spb` streams at a time, each with one decoder warp and `helpers` walker warps, and
         // owns one SM (~200 KiB of shared memory split between its streams: tree-node cache, leaf chances, per-chunk
         // property rows).  Few streams (one image) => one stream per SM with 8 walkers (value ranges up to 256); batches =>
-        // up to four streams per SM with 3 walkers each (ranges up to 96; wider ranges fall back to the decoder's own walk).
+        // two streams per SM with 6 walkers each (ranges up to 192; wider ranges fall back to the decoder's own walk).
         const int per_sm = (nstreams + ctx->sm_count - 1) / ctx->sm_count;
-        const int wpb = std::max(1, std::min(4, per_sm));          // streams per block
-        P.helpers = getenv("FB_MANIAC_NO_WALKERS") ? 0 : (wpb == 1 ? kMaxWalkers : (wpb == 2 ? 5 : 3));
+        const int wpb = std::max(1, std::min(2, per_sm));          // streams per block
+        P.helpers = getenv("FB_MANIAC_NO_WALKERS") ? 0 : (wpb == 1 ? kMaxWalkers : 6);
         const int nblocks = std::min((nstreams + wpb - 1) / wpb, ctx->sm_count);
         const size_t block_smem = 200 * 1024;
         const size_t warp_smem = ((block_smem - 16384) / wpb) & ~(size_t)15;
