@@ -26,6 +26,7 @@ TRANSFORM_PALETTE = 6
 TRANSFORM_SQUEEZE = 7
 
 FB_OK = 0
+FB_OPT_SQUEEZE_MODE = 1
 
 
 class FuifError(RuntimeError):
@@ -52,7 +53,7 @@ ABI_SYMBOLS = [
     "fb_image_create", "fb_image_destroy", "fb_image_get_info", "fb_image_get_plane", "fb_image_get_transform",
     "fb_image_plane_device_ptr", "fb_image_download_plane", "fb_image_download_interleaved",
     "fb_image_undo_transforms", "fb_image_do_transform", "fb_image_recompute_minmax",
-    "fb_decode_to_pixels", "fb_peek_header",
+    "fb_decode_to_pixels", "fb_peek_header", "fb_ctx_set_option", "fb_ctx_fallback_count",
 ]
 
 _lib = None
@@ -76,6 +77,9 @@ def load_library():
     L.fb_ctx_synchronize.argtypes = [vp]
     L.fb_ctx_launch_count.argtypes = [vp]
     L.fb_ctx_launch_count.restype = C.c_longlong
+    L.fb_ctx_set_option.argtypes = [vp, C.c_int, C.c_int]
+    L.fb_ctx_fallback_count.argtypes = [vp]
+    L.fb_ctx_fallback_count.restype = C.c_longlong
     L.fb_decode.argtypes = [vp, vp, C.c_size_t, C.POINTER(DecodeOptions), i64p, i32p, C.c_int, C.POINTER(vp)]
     L.fb_decode_batch.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(DecodeOptions), C.POINTER(i64p),
                                   C.POINTER(i32p), C.POINTER(C.c_int), C.POINTER(vp)]
@@ -177,6 +181,15 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self.lib.fb_ctx_launch_count(self.h))
+
+    def set_squeeze_mode(self, mode: int) -> None:
+        """0 fused tile kernels (default), 1 one kernel per squeeze step, 2 fused + forced serial fallback (tests)."""
+        self.check(self.lib.fb_ctx_set_option(self.h, FB_OPT_SQUEEZE_MODE, mode), "fb_ctx_set_option")
+
+    @property
+    def fallbacks(self) -> int:
+        """Squeeze inverses whose speculative tile starts failed verification (recomputed serially; still exact)."""
+        return int(self.lib.fb_ctx_fallback_count(self.h))
 
 
 _default_ctx = None

@@ -21,6 +21,11 @@ struct fb_ctx {
     int sm_count = 148;
     // MANIAC decoder resources (fb_maniac.cu), created lazily
     void *maniac_state = nullptr;
+    // fused unsqueeze (fb_fused_squeeze.cuh): [0] verification flag of the current run, [1] number of runs whose
+    // verification failed and were recomputed by the serial fallback; fq_mode: 0 default, 1 per-level kernels,
+    // 2 force the fallback (tests)
+    int *fq_counters = nullptr;
+    int fq_mode = 0;
     // FB_KERNEL_TIMING=1: a CUDA event after every launch, dumped by fb_ctx_synchronize (development aid)
     bool timing = false;
     std::vector<std::pair<std::string, cudaEvent_t>> marks;
@@ -80,7 +85,14 @@ struct FbSqOp {
     int16_t *out;
     int wa, wr, ha, hr;
 };
-int fb_run_inv_squeeze_plan(fb_ctx *ctx, const std::vector<FbSqOp> &ops);
+// what follows the last step of the plan and may be fused into its final launch
+struct FbSqEpilogue {
+    int kind;                   // 0 none, 1 clamp every final plane, 2 inverse YCoCg on ycc[0..2] (+ clamp of every final plane)
+    int maxval, lo, hi, do_clamp;
+    const int16_t *ycc[3];
+};
+// *epilogue_done = 1 if the epilogue was applied by the plan's last launch
+int fb_run_inv_squeeze_plan(fb_ctx *ctx, const std::vector<FbSqOp> &ops, const FbSqEpilogue *ep, int *epilogue_done);
 // forward Squeeze steps (squeeze.h:135-170, 227-263)
 int fb_launch_fwd_hsqueeze(fb_ctx *ctx, const int16_t *in, int16_t *avg, int16_t *res, int w, int h);
 int fb_launch_fwd_vsqueeze(fb_ctx *ctx, const int16_t *in, int16_t *avg, int16_t *res, int w, int h);

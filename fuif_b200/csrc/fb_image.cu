@@ -50,6 +50,7 @@ extern "C" void fb_ctx_destroy(fb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     fb_maniac_release(ctx);
+    if (ctx->fq_counters) cudaFree(ctx->fq_counters);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -71,6 +72,21 @@ extern "C" int fb_ctx_synchronize(fb_ctx *ctx) {
 }
 
 extern "C" long long fb_ctx_launch_count(fb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int fb_ctx_set_option(fb_ctx *ctx, int option, int value) {
+    if (!ctx) return FB_ERR_INVALID;
+    if (option == FB_OPT_SQUEEZE_MODE && value >= 0 && value <= 2) { ctx->fq_mode = value; return FB_OK; }
+    return FB_ERR_INVALID;
+}
+
+extern "C" long long fb_ctx_fallback_count(fb_ctx *ctx) {
+    if (!ctx || !ctx->fq_counters) return 0;
+    int v[2] = {0, 0};
+    cudaSetDevice(ctx->device);
+    if (cudaMemcpyAsync(v, ctx->fq_counters, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    return v[1];
+}
 
 int fb_plane_alloc(fb_ctx *ctx, size_t nsamples, int16_t **out) {
     *out = nullptr;
@@ -183,7 +199,9 @@ static int meta_squeeze(fb_image *img, std::vector<int> &p) {
 }
 
 // squeeze(..., inverse=true), squeeze.h:367-388 with inv_hsqueeze/inv_vsqueeze (:81-132, :173-224) as kernels
-static int inv_squeeze(fb_image *img, const std::vector<int> &params) {
+// ep_kind: what undo_transforms will do right after this Squeeze (0 nothing fusable, 1 final clamp, 2 inverse YCoCg,
+// do_clamp: followed by the final clamp); *ep_done = 1 if the unsqueeze kernels already did it.
+static int inv_squeeze(fb_image *img, const std::vector<int> &params, int ep_kind, int do_clamp, int *ep_done) {
     fb_ctx *ctx = img->ctx;
     std::vector<int> p = params;
     if (p.empty()) default_squeeze_parameters(p, img);
@@ -221,8 +239,33 @@ static int inv_squeeze(fb_image *img, const std::vector<int> &params) {
         for (int c = 0; c <= endc - beginc; c++) to_free.push_back(img->ch[offset + c].dev);
         img->ch.erase(img->ch.begin() + offset, img->ch.begin() + offset + (endc - beginc + 1));
     }
-    // Pass 2: run the plan (pyramid kernel for the coarse levels, one batched launch per remaining step).
-    int rc = fb_run_inv_squeeze_plan(ctx, ops);
+    // Pass 2: run the plan (fused tile kernels; per-level kernels for shapes the planner refuses).
+    FbSqEpilogue ep{};
+    const int m = img->info.nb_meta_channels;
+    if (ep_kind) {
+        // every plane of the image must come out of this plan, otherwise the epilogue stays with the caller
+        bool all = true;
+        for (auto &c : img->ch) {
+            bool produced = false;
+            for (auto &o : ops) if (o.out == c.dev) produced = true;
+            if (!produced) all = false;
+        }
+        if (ep_kind == 2) {
+            bool okc = img->info.nb_channels >= 3 && (int)img->ch.size() >= m + 3;
+            if (okc) for (int k = 1; k < 3; k++) if (img->ch[m + k].d.w != img->ch[m].d.w || img->ch[m + k].d.h != img->ch[m].d.h) okc = false;
+            if (okc) {
+                ep.kind = 2;
+                for (int k = 0; k < 3; k++) ep.ycc[k] = img->ch[m + k].dev;
+                ep.do_clamp = (do_clamp && all) ? 1 : 0;
+                if (do_clamp && !all) ep.kind = 0;     // keep the order "YCoCg, then clamp of everything" simple: do not fuse
+            }
+        } else if (all) {
+            ep.kind = 1;
+            ep.do_clamp = 1;
+        }
+        ep.maxval = img->info.maxval; ep.lo = img->info.minval; ep.hi = img->info.maxval;
+    }
+    int rc = fb_run_inv_squeeze_plan(ctx, ops, ep.kind ? &ep : nullptr, ep_done);
     // Pass 3: the consumed planes go back to the stream-ordered pool (after the kernels in stream order).
     for (auto q : to_free) fb_plane_free(ctx, q);
     return rc;
@@ -513,7 +556,25 @@ extern "C" int fb_image_undo_transforms(fb_image *img, int keep) {
             break;
         }
         case FB_TRANSFORM_QUANTIZE: rc = do_quantize(img, true, t.p); break;
-        case FB_TRANSFORM_SQUEEZE: rc = inv_squeeze(img, t.p); break;
+        case FB_TRANSFORM_SQUEEZE: {
+            // look ahead: an inverse YCoCg and / or the final clamp right after the Squeeze ride on its last launch
+            const int nt = (int)img->tr.size();
+            int ep_kind = 0, do_clamp = 0, ep_done = 0;
+            if (nt >= 2 && nt - 2 >= keep && img->tr[nt - 2].id == FB_TRANSFORM_YCOCG && img->info.nb_meta_channels == 0) {
+                ep_kind = 2;
+                do_clamp = (nt == 2 && keep == 0) ? 1 : 0;
+            } else if (last) {
+                ep_kind = 1;
+                do_clamp = 1;
+            }
+            const std::vector<int> params = t.p;
+            rc = inv_squeeze(img, params, ep_kind, do_clamp, &ep_done);
+            if (!rc && ep_done) {
+                if (ep_kind == 2) img->tr.pop_back();      // the Squeeze; the YCoCg entry is popped below
+                if (do_clamp) clamped = true;
+            }
+            break;
+        }
         case FB_TRANSFORM_DCT: rc = inv_dct(img, t.p); break;
         default:
             ctx->err = "cannot undo transform " + std::to_string(t.id) + " (outside the hot path)";

@@ -5,6 +5,9 @@
 // The DCT and YCbCr kernels use __dmul_rn/__dadd_rn/__fsub_rn so that nvcc can never contract a multiply
 // and an add into an FMA: the reference is built for baseline x86-64 and rounds after every operation.
 #include "fb_common.cuh"
+#include "fb_fused_plan.h"
+
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -829,7 +832,7 @@ int fb_launch_inv_squeeze_batch(fb_ctx *ctx, int horizontal, int n, const int16_
 }
 // Executes a planned sequence of unsqueeze steps: coarse levels of every plane in one pyramid launch, the rest as one
 // batched launch per step.
-int fb_run_inv_squeeze_plan(fb_ctx *ctx, const std::vector<FbSqOp> &ops) {
+static int run_inv_squeeze_plan_per_level(fb_ctx *ctx, const std::vector<FbSqOp> &ops) {
     const int n = (int)ops.size();
     if (!n) return FB_OK;
     // chains: op k continues the chain whose last op produced its `avg` plane
@@ -897,6 +900,83 @@ int fb_run_inv_squeeze_plan(fb_ctx *ctx, const std::vector<FbSqOp> &ops) {
         if (rc) return rc;
         k = q;
     }
+    return FB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused path: the whole Squeeze inverse in a handful of tile-kernel launches (fb_fused_squeeze.cuh) + one
+// verification launch.  Tunables (development / profiling only): FB_SQUEEZE_MODE=perlevel|fused, FB_FQ_TILE=WxH,
+// FB_FQ_LEVELS, FB_FQ_COARSE, FB_FQ_THREADS, FB_FQ_FORCE_FALLBACK=1.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct FqTunables {
+    bool fused = true;
+    int force_fallback = 0;
+    fq::PlanOptions opt;
+    FqTunables() {
+        if (const char *m = getenv("FB_SQUEEZE_MODE")) fused = std::string(m) != "perlevel";
+        if (const char *t = getenv("FB_FQ_TILE")) { int a = 0, b = 0; if (sscanf(t, "%dx%d", &a, &b) == 2) { opt.tile_w = a; opt.tile_h = b; } }
+        if (const char *t = getenv("FB_FQ_LEVELS")) opt.levels_per_launch = atoi(t);
+        if (const char *t = getenv("FB_FQ_COARSE")) opt.coarse_dim = atoi(t);
+        if (const char *t = getenv("FB_FQ_THREADS")) opt.threads_per_gang = atoi(t);
+        if (const char *t = getenv("FB_FQ_FORCE_FALLBACK")) force_fallback = atoi(t);
+    }
+};
+const FqTunables &fq_tunables() { static FqTunables t; return t; }
+}  // namespace
+
+int fb_run_inv_squeeze_plan(fb_ctx *ctx, const std::vector<FbSqOp> &ops, const FbSqEpilogue *ep, int *epilogue_done) {
+    if (epilogue_done) *epilogue_done = 0;
+    if (ops.empty()) return FB_OK;
+    const FqTunables &tun = fq_tunables();
+    fq::Plan P;
+    if (tun.fused && ctx->fq_mode != 1) {
+        std::vector<fq::PlanOp> po(ops.size());
+        for (size_t i = 0; i < ops.size(); i++) {
+            po[i].step = ops[i].step; po[i].horizontal = ops[i].horizontal;
+            po[i].avg = ops[i].avg; po[i].res = ops[i].res; po[i].out = ops[i].out;
+            po[i].wa = ops[i].wa; po[i].wr = ops[i].wr; po[i].ha = ops[i].ha; po[i].hr = ops[i].hr;
+        }
+        fq::EpilogueSpec E;
+        if (ep) {
+            E.kind = ep->kind; E.maxval = ep->maxval; E.lo = ep->lo; E.hi = ep->hi; E.do_clamp = ep->do_clamp;
+            for (int j = 0; j < 3; j++) E.ycc[j] = ep->ycc[j];
+        }
+        P = fq::make_plan(po, E, tun.opt);
+        // an epilogue that cannot be fused is left to the caller; without it the plan is still good
+        if (P.ok && ep && ep->kind != fq::kEpNone && !P.epilogue_fused) { E = fq::EpilogueSpec(); P = fq::make_plan(po, E, tun.opt); }
+    }
+    if (!P.ok) return run_inv_squeeze_plan_per_level(ctx, ops);
+
+    static bool configured = false;
+    if (!configured) {
+        FB_CUDA(ctx, cudaFuncSetAttribute(fq::k_fq_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    if (!ctx->fq_counters) {
+        FB_CUDA(ctx, cudaMalloc((void **)&ctx->fq_counters, 4 * sizeof(int)));
+        FB_CUDA(ctx, cudaMemsetAsync(ctx->fq_counters, 0, 4 * sizeof(int), ctx->stream));
+    }
+    unsigned char *scratch = nullptr;
+    if (P.scratch_bytes) {
+        FB_CUDA(ctx, cudaMallocAsync((void **)&scratch, P.scratch_bytes, ctx->stream));
+        fq::relocate_scratch(P, scratch);
+    }
+    for (auto &L : P.launches) {
+        fq::k_fq_tiles<<<L.grid, L.threads, L.smem, ctx->stream>>>(L.task);
+        FB_LAUNCH_CHECK(ctx);
+    }
+    const int force = tun.force_fallback || ctx->fq_mode == 2;
+    if (P.need_verify || force) {
+        FB_CUDA(ctx, cudaMemsetAsync(ctx->fq_counters, 0, sizeof(int), ctx->stream));      // [0] = flag of this run
+        P.verify.flag = ctx->fq_counters;
+        P.verify.force = force;
+        void *args[] = {(void *)&P.verify};
+        FB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)fq::k_fq_verify_fallback, dim3(ctx->sm_count), dim3(256), args, 0, ctx->stream));
+        FB_LAUNCH_CHECK(ctx);
+    }
+    if (scratch) cudaFreeAsync(scratch, ctx->stream);
+    if (epilogue_done) *epilogue_done = P.epilogue_fused ? 1 : 0;
     return FB_OK;
 }
 int fb_launch_fwd_hsqueeze(fb_ctx *ctx, const int16_t *in, int16_t *avg, int16_t *res, int w, int h) {

@@ -85,6 +85,14 @@ FB_API int fb_ctx_synchronize(fb_ctx *ctx);
 /* Number of kernels this library has launched on the context so far (bench.py's gpu_launches). */
 FB_API long long fb_ctx_launch_count(fb_ctx *ctx);
 
+/* Diagnostics / testing knobs (no reference counterpart).  FB_OPT_SQUEEZE_MODE: 0 = fused tile kernels for the
+ * Squeeze inverse (default), 1 = one kernel per squeeze step, 2 = fused kernels + force the exact serial fallback. */
+#define FB_OPT_SQUEEZE_MODE 1
+FB_API int fb_ctx_set_option(fb_ctx *ctx, int option, int value);
+/* Number of Squeeze inverses on this context whose speculative tile starts failed verification and were therefore
+ * recomputed by the serial fallback kernel (results are bit-exact either way).  Synchronises the stream. */
+FB_API long long fb_ctx_fallback_count(fb_ctx *ctx);
+
 /* ---- fuif_decode --------------------------------------------------------------------------------------- */
 
 /* Replaces fuif_decode<BlobReader>() / fuif_decode_file() (reference encoding/encoding.cpp:599-720, 745-753):

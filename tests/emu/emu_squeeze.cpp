@@ -1,0 +1,82 @@
+// TEST INFRASTRUCTURE ONLY: runs the fused unsqueeze kernel source of the product (fb_fused_squeeze.cuh, planned by
+// fb_fused_plan.h) under the CPU execution-model emulator (cuemu.h), so that the CPU-only test tier can compare it with
+// the oracle.  Built by tests/emu_util.py with  g++ -DFB_EMULATE.
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "fb_fused_plan.h"
+
+extern "C" {
+
+// opdesc[nops][9] = step, horizontal, avg plane, res plane (-1: none), out plane, wa, wr, ha, hr
+// ep[8] = kind, maxval, lo, hi, do_clamp, Y plane, Co plane, Cg plane
+// opts[6] = tile_w, tile_h, levels_per_launch, coarse_dim, threads_per_gang, force_fallback
+// stats[8] (out) = plan ok, launches, fallback ran, checks, failed comparisons (before the fallback), epilogue fused, max smem, total CTAs
+int emu_run_plan(int nplanes, int16_t **planes, int nops, const int *opdesc, const int *ep, const int *opts, int *stats) {
+    (void)nplanes;
+    std::vector<fq::PlanOp> ops(nops);
+    for (int i = 0; i < nops; i++) {
+        const int *d = opdesc + 9 * i;
+        ops[i].step = d[0]; ops[i].horizontal = d[1];
+        ops[i].avg = planes[d[2]]; ops[i].res = d[3] >= 0 ? planes[d[3]] : nullptr; ops[i].out = planes[d[4]];
+        ops[i].wa = d[5]; ops[i].wr = d[6]; ops[i].ha = d[7]; ops[i].hr = d[8];
+    }
+    fq::EpilogueSpec E;
+    E.kind = ep[0]; E.maxval = ep[1]; E.lo = ep[2]; E.hi = ep[3]; E.do_clamp = ep[4];
+    for (int j = 0; j < 3; j++) E.ycc[j] = ep[5 + j] >= 0 ? planes[ep[5 + j]] : nullptr;
+    fq::PlanOptions O;
+    O.tile_w = opts[0]; O.tile_h = opts[1]; O.levels_per_launch = opts[2]; O.coarse_dim = opts[3]; O.threads_per_gang = opts[4];
+    fq::Plan P = fq::make_plan(ops, E, O);
+    memset(stats, 0, 8 * sizeof(int));
+    stats[0] = P.ok;
+    if (!P.ok) return 1;
+    std::vector<unsigned char> scratch(P.scratch_bytes + 256, 0xEE);
+    fq::relocate_scratch(P, scratch.data());
+    int flags[2] = {0, 0};
+    P.verify.flag = flags;
+    P.verify.force = opts[5];
+    stats[1] = (int)P.launches.size();
+    stats[5] = P.epilogue_fused;
+    for (auto &L : P.launches) {
+        const fq::Task T = L.task;
+        stats[6] = std::max(stats[6], (int)L.smem);
+        stats[7] += L.grid;
+        cuemu::launch((unsigned)L.grid, (unsigned)L.threads, L.smem, false, [&]() { fq::k_fq_tiles(T); });
+    }
+    stats[3] = P.verify.nchecks;
+    // count failed comparisons (diagnostics: the speculation failure rate), then run the real verify / fallback kernel
+    for (int ci = 0; ci < P.verify.nchecks; ci++) {
+        const fq::Check &C = P.verify.chk[ci];
+        for (int tile = 0; tile < C.ntx * C.nty; tile++) {
+            const int ti = tile / C.nty, tj = tile % C.nty;
+            const int along = C.horizontal ? ti : tj, across = C.horizontal ? tj : ti;
+            if (!along) continue;
+            for (int e = 0; e < C.est_cap; e++) {
+                const int v = C.est[(size_t)tile * C.est_cap + e];
+                if (v == fq::kNoCheck) continue;
+                if (C.act[(size_t)(along - 1) * C.dim_across + across * C.cell + e] != v) stats[4]++;
+            }
+        }
+    }
+    if (P.need_verify || P.verify.force) {
+        const fq::VerifyParams V = P.verify;
+        cuemu::launch(4, 64, 0, true, [&]() { fq::k_fq_verify_fallback(V); });
+    }
+    stats[2] = flags[0];
+    return 0;
+}
+
+// closed-form pair vs the reference's literal formulation on n random full-range inputs; returns mismatches
+int emu_check_pair(const int16_t *prev, const int16_t *av, const int16_t *nx, const int16_t *rs, int n) {
+    int bad = 0;
+    for (int i = 0; i < n; i++) {
+        int A, B, A2, B2;
+        fq::unsqueeze_pair(prev[i], av[i], nx[i], rs[i], A, B);
+        fq::unsqueeze_pair_literal(prev[i], av[i], nx[i], rs[i], A2, B2);
+        if (A != A2 || B != B2) bad++;
+    }
+    return bad;
+}
+}

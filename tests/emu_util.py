@@ -1,0 +1,68 @@
+"""TEST INFRASTRUCTURE ONLY: builds tests/emu/libfb_emu.so (the product's fused-kernel SOURCE compiled for the CPU
+execution-model emulator, tests/emu/cuemu.h) and mirrors, in Python, the channel-list surgery of the library's
+inv_squeeze (fuif_b200/csrc/fb_image.cu; reference transform/squeeze.h:367-388) so that a plan can be run on numpy planes."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+EMU_DIR = os.path.join(HERE, "emu")
+LIB = os.path.join(EMU_DIR, "libfb_emu.so")
+SRCS = [os.path.join(EMU_DIR, "emu_squeeze.cpp"), os.path.join(EMU_DIR, "cuemu.h"),
+        os.path.join(ROOT, "fuif_b200", "csrc", "fb_fused_squeeze.cuh"), os.path.join(ROOT, "fuif_b200", "csrc", "fb_fused_plan.h"),
+        os.path.join(ROOT, "fuif_b200", "csrc", "fb_port.h")]
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB) or any(os.path.getmtime(LIB) < os.path.getmtime(s) for s in SRCS):
+            subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-DFB_EMULATE", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas",
+                                   "-I", EMU_DIR, "-I", os.path.join(ROOT, "fuif_b200", "csrc"), SRCS[0], "-o", LIB])
+        L = C.CDLL(LIB)
+        L.emu_run_plan.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.emu_check_pair.argtypes = [C.c_void_p] * 4 + [C.c_int]
+        _lib = L
+    return _lib
+
+
+def plan_inverse_squeeze(dims, params, nb_meta, nb_channels):
+    """dims: [(w, h)] of the channel list after meta_squeeze.  Returns (ops, nplanes, final) where ops are
+    (step, horizontal, avg, res, out, wa, wr, ha, hr) over plane ids (ids >= len(dims) are new planes) and final is the
+    list of (plane id, w, h) of the channel list after the inverse."""
+    chans = [(i, w, h) for i, (w, h) in enumerate(dims)]
+    nplanes = len(dims)
+    ops = []
+    step = 0
+    for i in range(len(params) - 3, -1, -3):
+        horizontal, in_place = params[i] & 1, not (params[i] & 2)
+        beginc, endc = params[i + 1], params[i + 2]
+        offset = endc + 1 if in_place else nb_meta + nb_channels
+        for c in range(beginc, endc + 1):
+            a, r = chans[c], chans[offset + c - beginc]
+            if horizontal:
+                out = (nplanes, a[1] + r[1], a[2])
+            else:
+                out = (nplanes, a[1], a[2] + r[2])
+            nplanes += 1
+            ops.append((step, horizontal, a[0], r[0], out[0], a[1], r[1], a[2], r[2]))
+            chans[c] = out
+        del chans[offset:offset + endc - beginc + 1]
+        step += 1
+    return ops, nplanes, chans
+
+
+def run_plan(planes, ops, ep, opts):
+    """planes: list of contiguous int16 arrays (outputs preallocated).  Returns the stats list."""
+    L = lib()
+    ptrs = (C.c_void_p * len(planes))(*[p.ctypes.data for p in planes])
+    od = (C.c_int * (9 * len(ops)))(*[int(v) for o in ops for v in o])
+    e = (C.c_int * 8)(*ep)
+    o = (C.c_int * 6)(*opts)
+    st = (C.c_int * 8)()
+    L.emu_run_plan(len(planes), ptrs, len(ops), od, e, o, st)
+    return list(st)

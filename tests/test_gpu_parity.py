@@ -206,3 +206,66 @@ def test_cli_decodes_like_fuif_d(ctx, tmp_path):
         ref = po.parse_fbpd(final)
         want = np.stack([p.data.astype(np.int32) for p in ref.planes[:ref.nb_channels]], axis=-1)
         assert np.array_equal(got, want), name
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2], ids=["fused", "perlevel", "forced_fallback"])
+@pytest.mark.parametrize("shape", [(512, 384, 3, 255), (1000, 333, 3, 255), (257, 513, 4, 16383), (640, 480, 1, 255)])
+def test_unsqueeze_modes_vs_oracle(oracle, shape, mode):
+    """The fused tile kernels, the per-level kernels and the serial fallback kernel must all reproduce the oracle."""
+    from fuif_b200 import api
+    po = oracle
+    c2 = api.Context(0)
+    try:
+        c2.set_squeeze_mode(mode)
+        w, h, c, maxval = shape
+        pix = synth_image(w, h, c, maxval, seed=2 * w + h)
+        oi = po.OracleImage.from_pixels(pix, maxval)
+        if c >= 3:
+            assert oi.do_transform(1)
+        sq = default_squeeze_parameters(w, h, c)
+        assert oi.do_transform(7, sq)
+        gi = upload_plane_image(api, oi.to_plane_image(), c2)
+        gi.undo_transforms(0)
+        oi.undo_transforms(0)
+        po.compare_plane_images(gpu_plane_image(po, gi), oi.to_plane_image(), f"mode {mode} {shape}")
+        assert np.array_equal(gi.pixels(), pix)
+        if mode == 2:
+            assert c2.fallbacks >= 1
+        if mode == 0:
+            assert c2.fallbacks == 0, "speculative tile starts failed verification on a smooth image"
+        # keep = 1 (colour transform left in place): no epilogue
+        if c >= 3:
+            oi2 = po.OracleImage.from_pixels(pix, maxval)
+            assert oi2.do_transform(1) and oi2.do_transform(7, sq)
+            gi2 = upload_plane_image(api, oi2.to_plane_image(), c2)
+            gi2.undo_transforms(1)
+            oi2.undo_transforms(1)
+            po.compare_plane_images(gpu_plane_image(po, gi2), oi2.to_plane_image(), f"mode {mode} keep=1 {shape}")
+    finally:
+        c2.close()
+
+
+def test_fused_unsqueeze_full_range_garbage(oracle):
+    """Full-range noise in every coefficient plane: wraps everywhere, speculation may fail -> verified / repaired."""
+    from fuif_b200 import api
+    po = oracle
+    c2 = api.Context(0)
+    try:
+        rng = np.random.default_rng(11)
+        w, h = 640, 400
+        pix = synth_image(w, h, 3, 255, seed=1)
+        oi = po.OracleImage.from_pixels(pix, 255)
+        sq = default_squeeze_parameters(w, h, 3)
+        assert oi.do_transform(1) and oi.do_transform(7, sq)
+        pi = oi.to_plane_image()
+        L = po.lib()
+        for i, p in enumerate(pi.planes):
+            p.data = rng.integers(-32768, 32768, size=p.data.shape).astype(np.int16)
+            a = np.ascontiguousarray(p.data)
+            L.fo_plane_set(oi.h, i, a.ctypes.data, a.size)
+        gi = upload_plane_image(api, pi, c2)
+        gi.undo_transforms(0)
+        oi.undo_transforms(0)
+        po.compare_plane_images(gpu_plane_image(po, gi), oi.to_plane_image(), "garbage fused")
+    finally:
+        c2.close()
