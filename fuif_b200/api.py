@@ -27,6 +27,7 @@ TRANSFORM_SQUEEZE = 7
 
 FB_OK = 0
 FB_OPT_SQUEEZE_MODE = 1
+FB_OPT_KERNEL_TIMING = 2
 
 
 class FuifError(RuntimeError):
@@ -53,7 +54,7 @@ ABI_SYMBOLS = [
     "fb_image_create", "fb_image_destroy", "fb_image_get_info", "fb_image_get_plane", "fb_image_get_transform",
     "fb_image_plane_device_ptr", "fb_image_download_plane", "fb_image_download_interleaved",
     "fb_image_undo_transforms", "fb_image_do_transform", "fb_image_recompute_minmax",
-    "fb_decode_to_pixels", "fb_peek_header", "fb_ctx_set_option", "fb_ctx_fallback_count",
+    "fb_decode_to_pixels", "fb_peek_header", "fb_ctx_set_option", "fb_ctx_counter", "fb_ctx_timing_report",
 ]
 
 _lib = None
@@ -78,8 +79,10 @@ def load_library():
     L.fb_ctx_launch_count.argtypes = [vp]
     L.fb_ctx_launch_count.restype = C.c_longlong
     L.fb_ctx_set_option.argtypes = [vp, C.c_int, C.c_int]
-    L.fb_ctx_fallback_count.argtypes = [vp]
-    L.fb_ctx_fallback_count.restype = C.c_longlong
+    L.fb_ctx_counter.argtypes = [vp, C.c_int]
+    L.fb_ctx_counter.restype = C.c_longlong
+    L.fb_ctx_timing_report.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.fb_ctx_timing_report.restype = C.c_longlong
     L.fb_decode.argtypes = [vp, vp, C.c_size_t, C.POINTER(DecodeOptions), i64p, i32p, C.c_int, C.POINTER(vp)]
     L.fb_decode_batch.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(DecodeOptions), C.POINTER(i64p),
                                   C.POINTER(i32p), C.POINTER(C.c_int), C.POINTER(vp)]
@@ -183,13 +186,32 @@ class Context:
         return int(self.lib.fb_ctx_launch_count(self.h))
 
     def set_squeeze_mode(self, mode: int) -> None:
-        """0 fused tile kernels (default), 1 one kernel per squeeze step, 2 fused + forced serial fallback (tests)."""
+        """0 fused tile kernels (default), 1 one kernel per squeeze step, 2 fused + forced serial recompute, 3 fused +
+        forced repair of every tile of the last launch (tests)."""
         self.check(self.lib.fb_ctx_set_option(self.h, FB_OPT_SQUEEZE_MODE, mode), "fb_ctx_set_option")
 
     @property
     def fallbacks(self) -> int:
-        """Squeeze inverses whose speculative tile starts failed verification (recomputed serially; still exact)."""
-        return int(self.lib.fb_ctx_fallback_count(self.h))
+        """Squeeze inverses that failed verification in an early launch (recomputed serially; still exact)."""
+        return int(self.lib.fb_ctx_counter(self.h, 0))
+
+    @property
+    def repaired_tiles(self) -> int:
+        """Tiles of last launches whose speculative start failed verification (recomputed from exact states)."""
+        return int(self.lib.fb_ctx_counter(self.h, 1))
+
+    def enable_kernel_timing(self, on: bool = True) -> None:
+        self.check(self.lib.fb_ctx_set_option(self.h, FB_OPT_KERNEL_TIMING, 1 if on else 0), "fb_ctx_set_option")
+
+    def timing_report(self) -> list:
+        """[(kernel / launcher name, microseconds, algorithmic bytes)] since the last report (synchronises)."""
+        buf = C.create_string_buffer(1 << 20)
+        self.lib.fb_ctx_timing_report(self.h, buf, len(buf))
+        out = []
+        for ln in buf.value.decode().splitlines():
+            name, us, b = ln.split("\t")
+            out.append((name, float(us), float(b)))
+        return out
 
 
 _default_ctx = None

@@ -21,20 +21,22 @@ struct fb_ctx {
     int sm_count = 148;
     // MANIAC decoder resources (fb_maniac.cu), created lazily
     void *maniac_state = nullptr;
-    // fused unsqueeze (fb_fused_squeeze.cuh): [0] verification flag of the current run, [1] number of runs whose
-    // verification failed and were recomputed by the serial fallback; fq_mode: 0 default, 1 per-level kernels,
-    // 2 force the fallback (tests)
+    // fused unsqueeze (fb_fused_squeeze.cuh) device counters: [0] current run failed, [1] tiles to repair in the current
+    // run, [2] runs recomputed by the serial fallback so far, [3] tiles repaired so far; fq_mode: 0 default,
+    // 1 per-level kernels, 2 force the serial fallback, 3 force the repair of every tile of the last launch (tests)
     int *fq_counters = nullptr;
     int fq_mode = 0;
     // FB_KERNEL_TIMING=1: a CUDA event after every launch, dumped by fb_ctx_synchronize (development aid)
-    bool timing = false;
-    std::vector<std::pair<std::string, cudaEvent_t>> marks;
-    void mark(const char *name) {
+    bool timing = false, timing_stderr = false;
+    struct Mark { std::string name; cudaEvent_t ev; double bytes; };
+    std::vector<Mark> marks;
+    // bytes: algorithmic HBM bytes of the launch just enqueued (0 = not accounted)
+    void mark(const char *name, double bytes = 0) {
         if (!timing) return;
         cudaEvent_t e;
         cudaEventCreate(&e);
         cudaEventRecord(e, stream);
-        marks.emplace_back(name, e);
+        marks.push_back(Mark{name, e, bytes});
     }
 };
 

@@ -33,6 +33,7 @@ struct PlanOptions {
     int levels_per_launch = 4;          // steps fused per tiled launch
     int coarse_dim = 128;               // the first launch takes every step whose output is at most this wide and high
     int threads_per_gang = 128;
+    int warm_last = kWarm, warm_mid = kWarmMid;
     size_t max_smem = 200 * 1024;
 };
 
@@ -40,6 +41,7 @@ struct PlannedLaunch {
     Task task;
     int grid = 0, threads = 0;
     size_t smem = 0;
+    double bytes = 0;           // algorithmic HBM bytes: level-0 averages + residuals read once, final planes written once
 };
 
 struct Plan {
@@ -48,8 +50,11 @@ struct Plan {
     bool epilogue_fused = false;
     std::vector<PlannedLaunch> launches;
     bool need_verify = false;
-    VerifyParams verify;        // flag pointer left for the caller
-    size_t scratch_bytes = 0;   // est / act scratch; pointers in tasks / checks are offsets from nullptr until relocated
+    VerifyParams verify;        // counters pointer left for the caller
+    int verify_threads = 256;   // block size / shared memory of the cooperative verification launch (= the last launch's)
+    size_t verify_smem = 0;
+    size_t scratch_bytes = 0;   // est / act scratch; pointers in tasks / checks are offsets (+1) until relocated
+    size_t tile_bad_off = 0, bad_list_off = 0;
 };
 
 namespace detail {
@@ -65,8 +70,8 @@ inline bool same_geometry(const std::vector<int> &a, const std::vector<int> &b, 
 
 }  // namespace detail
 
-// Relocates the scratch offsets stored in a plan to a real allocation.
-inline void relocate_scratch(Plan &P, unsigned char *base) {
+// Relocates the scratch offsets stored in a plan to a real allocation and wires the counters.
+inline void relocate_scratch(Plan &P, unsigned char *base, int *counters) {
     auto fix_i = [&](int *&p) { if (p) p = reinterpret_cast<int *>(base + (reinterpret_cast<uintptr_t>(p) - 1)); };
     auto fix_s = [&](int16_t *&p) { if (p) p = reinterpret_cast<int16_t *>(base + (reinterpret_cast<uintptr_t>(p) - 1)); };
     for (auto &L : P.launches)
@@ -78,6 +83,13 @@ inline void relocate_scratch(Plan &P, unsigned char *base) {
         int16_t *a = const_cast<int16_t *>(P.verify.chk[i].act);
         fix_i(e); fix_s(a);
         P.verify.chk[i].est = e; P.verify.chk[i].act = a;
+    }
+    for (auto &L : P.launches) { L.task.counters = counters; L.task.tile_bad = nullptr; }
+    P.verify.counters = counters;
+    if (!P.launches.empty()) {
+        if (P.tile_bad_off) P.launches.back().task.tile_bad = base + (P.tile_bad_off - 1);
+        P.verify.bad_list = P.bad_list_off ? reinterpret_cast<int *>(base + (P.bad_list_off - 1)) : nullptr;
+        P.verify.top = P.launches.back().task;
     }
 }
 
@@ -186,7 +198,11 @@ inline Plan make_plan(const std::vector<PlanOp> &ops, const EpilogueSpec &ep, co
                 }
         }
         if (join) { std::vector<int> all; for (int gi = 0; gi < (int)gangs.size(); gi++) all.push_back(gi); tasks.push_back(all); }
-        else for (int gi = 0; gi < (int)gangs.size(); gi++) tasks.push_back({gi});
+        else
+            for (int gi = 0; gi < (int)gangs.size(); gi++) {
+                if (tasks.empty() || (int)tasks.back().size() >= kMaxGangs) tasks.emplace_back();
+                tasks.back().push_back(gi);
+            }
         if (last_range) P.epilogue_fused = join;
 
         for (auto &tk : tasks) {
@@ -194,18 +210,13 @@ inline Plan make_plan(const std::vector<PlanOp> &ops, const EpilogueSpec &ep, co
             Task &T = PL.task;
             memset(&T, 0, sizeof(T));
             T.ngangs = (int)tk.size();
-            const PlanOp &fin = ops[segs[gangs[tk[0]][0]].back()];
-            const int W = out_w(fin), H = out_h(fin);
+            T.joined = join ? 1 : 0;
             const bool single = ri == 0 && coarse_end > 0;
-            T.TW = single ? ((W + 15) & ~15) : opt.tile_w;
-            T.TH = single ? ((H + 15) & ~15) : opt.tile_h;
-            T.ntx = (W + T.TW - 1) / T.TW;
-            T.nty = (H + T.TH - 1) / T.TH;
             T.epilogue = join ? ep.kind : kEpNone;
             T.maxval = ep.maxval; T.lo = ep.lo; T.hi = ep.hi; T.do_clamp = join ? ep.do_clamp : 0;
             for (int j = 0; j < 3; j++) { T.ycc_gang[j] = -1; T.ycc_plane[j] = -1; }
-            int thread0 = 0;
-            size_t smem_hw = 0;     // halfwords
+            int thread0 = 0, block0 = 0;
+            size_t smem_hw = 0, smem_hw_max = 0;     // halfwords
             for (int gq = 0; gq < T.ngangs; gq++) {
                 Gang &G = T.g[gq];
                 const std::vector<int> &members = gangs[tk[gq]];
@@ -214,10 +225,18 @@ inline Plan make_plan(const std::vector<PlanOp> &ops, const EpilogueSpec &ep, co
                 G.nlev = (int)seg0.size();
                 if (G.nlev > kMaxLevels) return Plan();
                 G.w0 = ops[seg0[0]].wa; G.h0 = ops[seg0[0]].ha;
+                const int W = out_w(ops[seg0.back()]), H = out_h(ops[seg0.back()]);
                 G.W = W; G.H = H;
-                if (out_w(ops[seg0.back()]) != W || out_h(ops[seg0.back()]) != H) return Plan();
-                G.first_thread = thread0; G.nthreads = opt.threads_per_gang; G.bar_id = 1 + gq;
-                thread0 += G.nthreads;
+                G.TW = single ? ((W + 15) & ~15) : opt.tile_w;
+                G.TH = single ? ((H + 15) & ~15) : opt.tile_h;
+                G.ntx = (W + G.TW - 1) / G.TW;
+                G.nty = (H + G.TH - 1) / G.TH;
+                if (join && gq > 0 && (G.ntx != T.g[0].ntx || G.nty != T.g[0].nty || W != T.g[0].W || H != T.g[0].H)) return Plan();
+                G.bar_id = 1 + gq;
+                G.warm = last_range ? opt.warm_last : opt.warm_mid;
+                if (join) { G.first_thread = thread0; G.nthreads = opt.threads_per_gang; thread0 += G.nthreads; G.first_block = 0; }
+                else { G.first_thread = 0; G.nthreads = opt.threads_per_gang; thread0 = G.nthreads; G.first_block = block0; block0 += G.ntx * G.nty; smem_hw = 0; }
+                Gang &TT = G;       // tile grid of this gang
                 int nh_after = 0, nv_after = 0;
                 for (int k = G.nlev - 1; k >= 0; k--) {
                     Level &L = G.lv[k];
@@ -226,11 +245,11 @@ inline Plan make_plan(const std::vector<PlanOp> &ops, const EpilogueSpec &ep, co
                     L.wa = o.wa; L.ha = o.ha;
                     L.wr = o.horizontal ? o.wr : o.wa; L.hr = o.horizontal ? o.ha : o.hr;
                     L.wo = out_w(o); L.ho = out_h(o);
-                    if (T.ntx > 1 && (T.TW >> nh_after) < 2) return Plan();
-                    if (T.nty > 1 && (T.TH >> nv_after) < 2) return Plan();
-                    if (T.ntx > 1 && (T.TW % (1 << (nh_after + (o.horizontal ? 1 : 0))))) return Plan();
-                    if (T.nty > 1 && (T.TH % (1 << (nv_after + (o.horizontal ? 0 : 1))))) return Plan();
-                    L.tw = T.TW >> nh_after; L.th = T.TH >> nv_after;
+                    if (TT.ntx > 1 && (TT.TW >> nh_after) < 2) return Plan();
+                    if (TT.nty > 1 && (TT.TH >> nv_after) < 2) return Plan();
+                    if (TT.ntx > 1 && (TT.TW % (1 << (nh_after + (o.horizontal ? 1 : 0))))) return Plan();
+                    if (TT.nty > 1 && (TT.TH % (1 << (nv_after + (o.horizontal ? 0 : 1))))) return Plan();
+                    L.tw = TT.TW >> nh_after; L.th = TT.TH >> nv_after;
                     for (int pl = 0; pl < G.np; pl++) L.res[pl] = ops[segs[members[pl]][k]].res;
                     if (o.horizontal) nh_after++; else nv_after++;
                 }
@@ -244,14 +263,14 @@ inline Plan make_plan(const std::vector<PlanOp> &ops, const EpilogueSpec &ep, co
                 std::vector<int> out_w_(G.nlev, 0), out_h_(G.nlev, 0), res_w_(G.nlev, 0), res_h_(G.nlev, 0), est_n(G.nlev, 0);
                 int in_w = 0, in_h = 0;
                 std::vector<std::pair<int, int>> probes;
-                for (int i = 0; i < T.ntx; i++) probes.emplace_back(i, 0);
-                for (int j = 1; j < T.nty; j++) probes.emplace_back(0, j);
+                for (int i = 0; i < G.ntx; i++) probes.emplace_back(i, 0);
+                for (int j = 1; j < G.nty; j++) probes.emplace_back(0, j);
                 Geom gm[kMaxLevels];
                 Region inr;
                 for (auto &pr : probes) {
                     {
                         const int ti = pr.first, tj = pr.second;
-                        geometry(G, T.TW, T.TH, T.ntx, T.nty, ti, tj, gm, inr);
+                        geometry(G, ti, tj, G.warm, gm, inr);
                         in_w = std::max(in_w, ((inr.x1 - (inr.x0 & ~7)) + 7) & ~7);
                         in_h = std::max(in_h, inr.y1 - inr.y0);
                         for (int k = 0; k < G.nlev; k++) {
@@ -290,28 +309,37 @@ inline Plan make_plan(const std::vector<PlanOp> &ops, const EpilogueSpec &ep, co
                 // ---- verification scratch for the levels whose chains can start inside the plane
                 for (int k = 0; k < G.nlev; k++) {
                     Level &L = G.lv[k];
-                    const bool multi = L.horizontal ? T.ntx > 1 : T.nty > 1;
+                    const bool multi = L.horizontal ? G.ntx > 1 : G.nty > 1;
                     for (int pl = 0; pl < kGP; pl++) { L.est[pl] = nullptr; L.act[pl] = nullptr; }
                     if (!multi) continue;
                     for (int pl = 0; pl < G.np; pl++) {
-                        L.est[pl] = reinterpret_cast<int *>(salloc((size_t)T.ntx * T.nty * L.est_cap * sizeof(int)));
-                        const size_t nact = L.horizontal ? (size_t)T.ntx * L.ho : (size_t)T.nty * L.wo;
+                        L.est[pl] = reinterpret_cast<int *>(salloc((size_t)G.ntx * G.nty * L.est_cap * sizeof(int)));
+                        const size_t nact = L.horizontal ? (size_t)G.ntx * L.ho : (size_t)G.nty * L.wo;
                         L.act[pl] = reinterpret_cast<int16_t *>(salloc(nact * sizeof(int16_t)));
                         if (P.verify.nchecks >= kMaxChecks) return Plan();
                         Check &C = P.verify.chk[P.verify.nchecks++];
                         C.est = L.est[pl]; C.act = L.act[pl];
-                        C.horizontal = L.horizontal; C.ntx = T.ntx; C.nty = T.nty; C.est_cap = L.est_cap;
+                        C.horizontal = L.horizontal; C.ntx = G.ntx; C.nty = G.nty; C.est_cap = L.est_cap;
                         C.cell = L.horizontal ? L.th : L.tw;
                         C.dim_across = L.horizontal ? L.ho : L.wo;
+                        C.first_block = -1 - G.first_block;     // provisional: turned into first_block for the last launch below
                         P.need_verify = true;
                     }
                 }
+                smem_hw_max = std::max(smem_hw_max, smem_hw);
             }
             if (T.epilogue == kEpYCoCg && (T.ycc_gang[0] < 0 || T.ycc_gang[1] < 0 || T.ycc_gang[2] < 0)) return Plan();
-            T.geom_off = (int)(((smem_hw * 2) + 15) & ~(size_t)15);
+            T.geom_off = (int)(((smem_hw_max * 2) + 15) & ~(size_t)15);
             PL.smem = (size_t)T.geom_off + sizeof(Geom) * kMaxGangs * kMaxLevels + sizeof(Region) * kMaxGangs + 16;
             if (PL.smem > opt.max_smem) return Plan();
-            PL.grid = T.ntx * T.nty;
+            for (int gq = 0; gq < T.ngangs; gq++) {
+                const Gang &G = T.g[gq];
+                for (int pl = 0; pl < G.np; pl++) {
+                    PL.bytes += 2.0 * G.w0 * G.h0 + 2.0 * G.W * G.H;
+                    for (int k = 0; k < G.nlev; k++) if (G.lv[k].res[pl]) PL.bytes += 2.0 * G.lv[k].wr * G.lv[k].hr;
+                }
+            }
+            PL.grid = join ? T.g[0].ntx * T.g[0].nty : block0;
             PL.threads = thread0;
             P.launches.push_back(PL);
         }
@@ -329,7 +357,7 @@ inline Plan make_plan(const std::vector<PlanOp> &ops, const EpilogueSpec &ep, co
             so.horizontal = ops[k].horizontal; so.step = ops[k].step;
         }
         P.verify.force = 0;
-        P.verify.flag = nullptr;
+        P.verify.counters = nullptr;
         P.verify.epilogue = P.epilogue_fused ? ep.kind : kEpNone;
         P.verify.maxval = ep.maxval; P.verify.lo = ep.lo; P.verify.hi = ep.hi; P.verify.do_clamp = P.epilogue_fused ? ep.do_clamp : 0;
         P.verify.nother = 0;
@@ -347,6 +375,29 @@ inline Plan make_plan(const std::vector<PlanOp> &ops, const EpilogueSpec &ep, co
                     if (!is_ycc) { if (P.verify.nother >= 4) return Plan(); P.verify.other[P.verify.nother++] = o; }
                 }
         }
+    }
+    // ---- checks of the very last launch are repairable tile by tile
+    {
+        const PlannedLaunch &PL = P.launches.back();
+        std::vector<const int *> last_est;
+        for (int gi = 0; gi < PL.task.ngangs; gi++)
+            for (int k = 0; k < PL.task.g[gi].nlev; k++)
+                for (int pl = 0; pl < PL.task.g[gi].np; pl++) if (PL.task.g[gi].lv[k].est[pl]) last_est.push_back(PL.task.g[gi].lv[k].est[pl]);
+        bool any = false;
+        for (int i = 0; i < P.verify.nchecks; i++) {
+            Check &C = P.verify.chk[i];
+            const bool is_last = std::find(last_est.begin(), last_est.end(), C.est) != last_est.end();
+            C.first_block = is_last ? (-1 - C.first_block) : -1;
+            any = any || is_last;
+        }
+        P.verify.top_blocks = PL.grid;
+        P.verify.bad_cap = PL.grid;
+        if (any) {
+            P.tile_bad_off = salloc((size_t)PL.grid);
+            P.bad_list_off = salloc((size_t)PL.grid * sizeof(int));
+        } else P.verify.bad_cap = 0;
+        P.verify_threads = PL.threads;
+        P.verify_smem = PL.smem;
     }
     P.scratch_bytes = scratch;
     P.ok = true;

@@ -14,8 +14,12 @@
 // value it really produced ("act").  Ownership is a lattice: at the output of level k a tile owns the cell
 // [ti*tw_k, (ti+1)*tw_k) x [tj*th_k, (tj+1)*th_k) with tw_k = TW >> (horizontal steps after k).  By induction over
 // (level, tile index along the axis) all results are exact iff every est equals its act; k_fq_verify_fallback checks
-// that after the last fused launch and, if a single comparison fails, recomputes the whole run with plain serial
-// chains (exact by construction).  So the output is bit-exact no matter how good the guesses were.
+// that after the last fused launch.  A tile of the LAST launch whose est failed is recomputed there in "exact mode"
+// (no warm-up: its chains start from the recorded act values, exact by the same induction; if that changes any act the
+// tile had published, the run is treated as failed).  A failure in an earlier launch, whose output later launches have
+// consumed, makes the whole run be recomputed with plain serial chains (exact by construction).  So the output is
+// bit-exact no matter how good the guesses were; the warm-up length only sets how rarely the repairs happen
+// (failures drop ~7x per warm-up pair: ~1e-7 per chain start at 8 pairs).
 //
 // This header is compiled by nvcc (the product) and by g++ with -DFB_EMULATE (tests/emu: the CPU-only test tier runs
 // the very same kernel source under an execution-model emulator and compares it with the oracle).
@@ -24,7 +28,14 @@
 
 namespace fq {
 
-constexpr int kWarm = 8;            // warm-up pairs before the first pair whose output is used
+#ifndef FQ_WARM
+#define FQ_WARM 8
+#endif
+#ifndef FQ_WARM_MID
+#define FQ_WARM_MID 12
+#endif
+constexpr int kWarm = FQ_WARM;          // warm-up pairs of the last launch (failed tiles are repaired locally)
+constexpr int kWarmMid = FQ_WARM_MID;   // warm-up pairs of earlier launches (a failure there costs a full serial recompute)
 constexpr int kMaxLevels = 12;      // unsqueeze steps per gang in one launch
 constexpr int kGP = 2;              // planes per gang (identical geometry: processed by one thread for ILP)
 constexpr int kMaxGangs = 2;        // gangs per CTA (joined by the colour epilogue)
@@ -103,7 +114,10 @@ struct Gang {
     int np, nlev;
     int w0, h0;                 // level-0 average planes
     int W, H;                   // final planes
+    int TW, TH, ntx, nty;       // tile grid over the final planes
+    int first_block;            // separate gangs: first CTA of this gang's tile grid
     int first_thread, nthreads, bar_id;
+    int warm;                   // warm-up pairs of speculative chain starts
     int in_pitch;
     int in_off[kGP];
     const int16_t *in[kGP];
@@ -112,11 +126,14 @@ struct Gang {
 };
 struct Task {
     int ngangs;
-    int TW, TH, ntx, nty;       // tile grid over the final planes (all gangs share W, H)
+    int joined;                 // 1: every CTA runs all gangs on one tile (they share W, H and the tile grid; colour
+                                //    epilogue possible); 0: every gang has its own tile grid and CTAs (first_block)
     int epilogue;               // kEpNone / kEpClamp / kEpYCoCg
     int maxval, lo, hi, do_clamp;
     int ycc_gang[3], ycc_plane[3];      // kEpYCoCg: where Y, Co, Cg live
     int geom_off;               // byte offset of the geometry scratch in shared memory
+    int *counters;              // [0] run failed (serial fallback needed) [1] number of tiles to repair [2], [3] statistics
+    unsigned char *tile_bad;    // last launch: one flag per CTA, cleared by the CTA itself, set by the verification
     Gang g[kMaxGangs];
 };
 
@@ -129,9 +146,10 @@ struct Geom {                   // what one tile computes at one level (absolute
 struct Region { int x0, y0, x1, y1; };
 
 // Walks the levels backwards from the owned tile of the final planes; g[k] for k = 0..nlev-1, in = level-0 input.
-FB_HD void geometry(const Gang &G, int TW, int TH, int ntx, int nty, int ti, int tj, Geom *g, Region &in) {
-    int nx0 = ti * TW, nx1 = (ti == ntx - 1) ? G.W : (ti + 1) * TW;
-    int ny0 = tj * TH, ny1 = (tj == nty - 1) ? G.H : (tj + 1) * TH;
+// warm = 0 gives the exact-mode geometry (no halos: every chain starts at the first owned pair).
+FB_HD void geometry(const Gang &G, int ti, int tj, int warm, Geom *g, Region &in) {
+    int nx0 = ti * G.TW, nx1 = (ti == G.ntx - 1) ? G.W : (ti + 1) * G.TW;
+    int ny0 = tj * G.TH, ny1 = (tj == G.nty - 1) ? G.H : (tj + 1) * G.TH;
     int xe = nx0, ye = ny0;
     for (int k = G.nlev - 1; k >= 0; k--) {
         const Level &L = G.lv[k];
@@ -139,7 +157,7 @@ FB_HD void geometry(const Gang &G, int TW, int TH, int ntx, int nty, int ti, int
         if (L.horizontal) {
             q.p_store = nx0 >> 1;
             q.p_exact = xe >> 1;
-            q.p_start = imax(0, q.p_store - kWarm);
+            q.p_start = imax(0, q.p_store - warm);
             q.p_end = imin((nx1 + 1) >> 1, L.wr);
             q.tail = (nx1 == L.wo) && (L.wo & 1);
             q.x0 = 2 * q.p_store; q.x1 = nx1; q.y0 = ny0; q.y1 = ny1;
@@ -148,7 +166,7 @@ FB_HD void geometry(const Gang &G, int TW, int TH, int ntx, int nty, int ti, int
         } else {
             q.p_store = ny0 >> 1;
             q.p_exact = ye >> 1;
-            q.p_start = imax(0, q.p_store - kWarm);
+            q.p_start = imax(0, q.p_store - warm);
             q.p_end = imin((ny1 + 1) >> 1, L.hr);
             q.tail = (ny1 == L.ho) && (L.ho & 1);
             q.y0 = 2 * q.p_store; q.y1 = ny1; q.x0 = nx0; q.x1 = nx1;
@@ -193,8 +211,8 @@ FB_DEV void stage_region(int16_t *dst, int dpitch, const int16_t *src, int w, in
 
 // All chains of one level for the planes of a gang.  H: chains are rows, V: chains are columns.
 template <int NP, bool H>
-FB_DEV void run_level(const Task &T, const Gang &G, int k, const Geom &q, const Geom *qprev, const Region &in, int16_t *sm, int ti, int tj,
-                      int gtid) {
+FB_DEV void run_level(const Gang &G, int k, const Geom &q, const Geom *qprev, const Region &in, int16_t *sm, int ti, int tj,
+                      int gtid, bool exact, int *counters) {
     const Level &L = G.lv[k];
     // source of the averages: the staged level-0 planes or the previous level's output
     int aox, aoy, apitch;
@@ -206,12 +224,12 @@ FB_DEV void run_level(const Task &T, const Gang &G, int k, const Geom &q, const 
     // the very last pair of a chain without an odd tail has no next average: it uses its own (squeeze.h:93, :201)
     const bool self_next = (q.p_end == npair) && (navg == npair) && (q.p_end > q.p_exact);
     const int p_plain_end = self_next ? q.p_end - 1 : q.p_end;
-    const int last_tile_along = H ? (ti == T.ntx - 1) : (tj == T.nty - 1);
+    const int last_tile_along = H ? (ti == G.ntx - 1) : (tj == G.nty - 1);
     const int own_end_along = H ? (ti + 1) * L.tw : (tj + 1) * L.th;       // only used when !last_tile_along
     const int own_c0 = H ? tj * L.th : ti * L.tw;
-    const int own_c1 = H ? ((tj == T.nty - 1) ? L.ho : (tj + 1) * L.th) : ((ti == T.ntx - 1) ? L.wo : (ti + 1) * L.tw);
+    const int own_c1 = H ? ((tj == G.nty - 1) ? L.ho : (tj + 1) * L.th) : ((ti == G.ntx - 1) ? L.wo : (ti + 1) * L.tw);
     const int dim_across = H ? L.ho : L.wo;
-    const int tile_lin = ti * T.nty + tj;
+    const int tile_lin = ti * G.nty + tj;
     for (int c = q.c0 + gtid; c < q.c1; c += G.nthreads) {
         const int16_t *a[NP], *r[NP];
         int16_t *o[NP];
@@ -233,6 +251,10 @@ FB_DEV void run_level(const Task &T, const Gang &G, int k, const Geom &q, const 
         int prev[NP], av[NP], est[NP];
 #pragma unroll
         for (int pl = 0; pl < NP; pl++) { av[pl] = a[pl][q.p_start * a_step]; prev[pl] = av[pl]; est[pl] = kNoCheck; }
+        if (exact && q.p_start > 0) {       // repair: start from the value the owner of the previous pair produced
+#pragma unroll
+            for (int pl = 0; pl < NP; pl++) prev[pl] = L.act[pl][(size_t)((H ? ti : tj) - 1) * dim_across + c];
+        }
         auto pairs = [&](int from, int to, bool store, bool own_next) {
             for (int p = from; p < to; p++) {
 #pragma unroll
@@ -265,7 +287,7 @@ FB_DEV void run_level(const Task &T, const Gang &G, int k, const Geom &q, const 
             }
         }
         // verification records
-        if (c >= q.ce && L.est[0]) {
+        if (!exact && c >= q.ce && L.est[0]) {
 #pragma unroll
             for (int pl = 0; pl < NP; pl++) L.est[pl][(size_t)tile_lin * L.est_cap + (c - q.ce)] = est[pl];
         }
@@ -274,12 +296,14 @@ FB_DEV void run_level(const Task &T, const Gang &G, int k, const Geom &q, const 
 #pragma unroll
             for (int pl = 0; pl < NP; pl++) {
                 const int16_t v = H ? o[pl][own_end_along - 1] : o[pl][(own_end_along - 1) * opitch];
-                L.act[pl][(size_t)idx * dim_across + c] = v;
+                int16_t *slot = &L.act[pl][(size_t)idx * dim_across + c];
+                if (exact) { if (*slot != v) atomicOr(counters, 1); }      // a repair must not change what neighbours checked against
+                else *slot = v;
             }
         }
     }
     // unused est slots of this tile
-    if (L.est[0]) {
+    if (!exact && L.est[0]) {
         for (int e = (q.c1 - q.ce) + gtid; e < L.est_cap; e += G.nthreads) {
 #pragma unroll
             for (int pl = 0; pl < NP; pl++) L.est[pl][(size_t)tile_lin * L.est_cap + e] = kNoCheck;
@@ -288,7 +312,7 @@ FB_DEV void run_level(const Task &T, const Gang &G, int k, const Geom &q, const 
 }
 
 template <int NP>
-FB_DEV void run_gang(const Task &T, const Gang &G, const Geom *geo, const Region &in, int16_t *sm, int ti, int tj, int gtid) {
+FB_DEV void run_gang(const Gang &G, const Geom *geo, const Region &in, int16_t *sm, int ti, int tj, int gtid, bool exact, int *counters) {
     // stage the level-0 averages and every level's residuals
     for (int pl = 0; pl < NP; pl++) stage_region(sm + G.in_off[pl], G.in_pitch, G.in[pl], G.w0, in.x0, in.x1, in.y0, in.y1, gtid, G.nthreads);
     for (int k = 0; k < G.nlev; k++) {
@@ -301,17 +325,18 @@ FB_DEV void run_gang(const Task &T, const Gang &G, const Geom *geo, const Region
     }
     fb_bar_sync(G.bar_id, G.nthreads);
     for (int k = 0; k < G.nlev; k++) {
-        if (G.lv[k].horizontal) run_level<NP, true>(T, G, k, geo[k], k ? &geo[k - 1] : nullptr, in, sm, ti, tj, gtid);
-        else run_level<NP, false>(T, G, k, geo[k], k ? &geo[k - 1] : nullptr, in, sm, ti, tj, gtid);
+        if (G.lv[k].horizontal) run_level<NP, true>(G, k, geo[k], k ? &geo[k - 1] : nullptr, in, sm, ti, tj, gtid, exact, counters);
+        else run_level<NP, false>(G, k, geo[k], k ? &geo[k - 1] : nullptr, in, sm, ti, tj, gtid, exact, counters);
         fb_bar_sync(G.bar_id, G.nthreads);
     }
 }
 
 // Final planes of the tile: shared memory -> HBM with the colour inverse / clamp applied, 8 samples per thread-step.
-FB_DEV void epilogue(const Task &T, const Geom *geo0, const Geom *geo1, int16_t *sm, int ti, int tj) {
-    const int x0 = ti * T.TW, y0 = tj * T.TH;
-    const int W = T.g[0].W, H = T.g[0].H;
-    const int x1 = (ti == T.ntx - 1) ? W : x0 + T.TW, y1 = (tj == T.nty - 1) ? H : y0 + T.TH;
+FB_DEV void epilogue(const Task &T, int g_first, int g_last, int16_t *sm, int ti, int tj) {
+    const Gang &G0 = T.g[g_first];
+    const int x0 = ti * G0.TW, y0 = tj * G0.TH;
+    const int W = G0.W, H = G0.H;
+    const int x1 = (ti == G0.ntx - 1) ? W : x0 + G0.TW, y1 = (tj == G0.nty - 1) ? H : y0 + G0.TH;
     const int nchunk = (x1 - x0 + 7) >> 3, rows = y1 - y0, total = nchunk * rows;
     const int nthr = (int)blockDim.x;
     // units of work: the YCoCg triple (if any) and every other plane on its own
@@ -319,7 +344,7 @@ FB_DEV void epilogue(const Task &T, const Geom *geo0, const Geom *geo1, int16_t 
     int16_t *dstp[kMaxGangs * kGP];
     int pitch[kMaxGangs * kGP];
     int nfin = 0, ycc[3] = {-1, -1, -1};
-    for (int gi = 0; gi < T.ngangs; gi++) {
+    for (int gi = g_first; gi <= g_last; gi++) {
         const Gang &G = T.g[gi];
         const Level &L = G.lv[G.nlev - 1];
         for (int pl = 0; pl < G.np; pl++) {
@@ -332,7 +357,6 @@ FB_DEV void epilogue(const Task &T, const Geom *geo0, const Geom *geo1, int16_t 
             nfin++;
         }
     }
-    (void)geo0; (void)geo1;
     const bool vec = (W & 7) == 0;
     int r = (int)threadIdx.x / nchunk, c = (int)threadIdx.x - r * nchunk;
     const int dr = nthr / nchunk, dc = nthr - dr * nchunk;
@@ -402,25 +426,37 @@ FB_DEV void epilogue(const Task &T, const Geom *geo0, const Geom *geo1, int16_t 
     }
 }
 
-FB_KERNEL(512) k_fq_tiles(const FB_GRID_CONSTANT Task T) {
-    FB_DYN_SMEM(smraw);
+// One tile (CTA `block` of the launch): speculative (exact == false) or repair (exact == true) mode.
+FB_DEV void tile_body(const Task &T, int block, bool exact, unsigned char *smraw) {
     int16_t *sm = reinterpret_cast<int16_t *>(smraw);
     Geom *geo = reinterpret_cast<Geom *>(smraw + T.geom_off);                  // [kMaxGangs][kMaxLevels]
     Region *inr = reinterpret_cast<Region *>(geo + kMaxGangs * kMaxLevels);    // [kMaxGangs]
-    const int tile = (int)blockIdx.x;
-    const int ti = tile % T.ntx, tj = tile / T.ntx;
     const int tid = (int)threadIdx.x;
-    const int gi = (T.ngangs > 1 && tid >= T.g[1].first_thread) ? 1 : 0;
+    int gi, tile;
+    if (T.joined) {
+        gi = (T.ngangs > 1 && tid >= T.g[1].first_thread) ? 1 : 0;
+        tile = block;
+    } else {
+        gi = (T.ngangs > 1 && block >= T.g[1].first_block) ? 1 : 0;
+        tile = block - T.g[gi].first_block;
+    }
     const Gang &G = T.g[gi];
+    const int ti = tile % G.ntx, tj = tile / G.ntx;
     const int gtid = tid - G.first_thread;
-    if (gtid == 0) geometry(G, T.TW, T.TH, T.ntx, T.nty, ti, tj, geo + gi * kMaxLevels, inr[gi]);
+    if (gtid == 0) geometry(G, ti, tj, exact ? 0 : G.warm, geo + gi * kMaxLevels, inr[gi]);
+    if (tid == 0 && !exact && T.tile_bad) T.tile_bad[block] = 0;
     __syncthreads();
-    if (gtid < G.nthreads) {
-        if (G.np == 1) run_gang<1>(T, G, geo + gi * kMaxLevels, inr[gi], sm, ti, tj, gtid);
-        else run_gang<2>(T, G, geo + gi * kMaxLevels, inr[gi], sm, ti, tj, gtid);
+    if (gtid >= 0 && gtid < G.nthreads) {
+        if (G.np == 1) run_gang<1>(G, geo + gi * kMaxLevels, inr[gi], sm, ti, tj, gtid, exact, T.counters);
+        else run_gang<2>(G, geo + gi * kMaxLevels, inr[gi], sm, ti, tj, gtid, exact, T.counters);
     }
     __syncthreads();
-    epilogue(T, geo, geo + kMaxLevels, sm, ti, tj);
+    epilogue(T, T.joined ? 0 : gi, T.joined ? T.ngangs - 1 : gi, sm, ti, tj);
+}
+
+FB_KERNEL(512) k_fq_tiles(const FB_GRID_CONSTANT Task T) {
+    FB_DYN_SMEM(smraw);
+    tile_body(T, (int)blockIdx.x, false, smraw);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -430,6 +466,7 @@ struct Check {                  // one (level, plane) of a multi-tile launch
     const int *est;
     const int16_t *act;
     int horizontal, ntx, nty, est_cap, cell, dim_across;     // cell: lattice cell size across the axis
+    int first_block;            // >= 0: a check of the LAST launch (CTA id = first_block + tj*ntx + ti): repairable
 };
 struct SerialOp {               // one unsqueeze step on one plane, as the per-level kernels see it
     const int16_t *avg, *res;
@@ -439,13 +476,18 @@ struct SerialOp {               // one unsqueeze step on one plane, as the per-l
 constexpr int kMaxChecks = 96, kMaxSerialOps = 96;
 struct VerifyParams {
     int nchecks, nops;
-    int *flag;                  // flag[0]: zeroed before the run, != 0 afterwards: the fallback ran; flag[1]: running count
-    int force;                  // testing: behave as if a check had failed
+    int *counters;              // [0] run failed [1] tiles to repair (both zeroed before the run) [2] runs that fell back
+                                // to the serial recompute [3] tiles repaired (statistics, never reset)
+    int *bad_list;              // CTA ids of the last launch to repair
+    int bad_cap;
+    int force;                  // testing: 1 = behave as if an early check had failed, 2 = repair every tile of the last launch
     int epilogue, maxval, lo, hi, do_clamp;
     int16_t *ycc[3];            // kEpYCoCg: final Y/Co/Cg planes
     int16_t *other[4];          // planes that only get the clamp
     int nother;
     int W, H;
+    int top_blocks;             // grid of the last launch
+    Task top;                   // the last launch (for repairs)
     Check chk[kMaxChecks];
     SerialOp op[kMaxSerialOps];
 };
@@ -472,9 +514,11 @@ FB_DEV void serial_chain(const SerialOp &o, int chain) {
     if (navg > npair) out[(size_t)(navg + npair - 1) * os] = a[(size_t)(navg - 1) * as];
 }
 
-FB_KERNEL(256) k_fq_verify_fallback(const FB_GRID_CONSTANT VerifyParams P) {
+// Cooperative launch: blockDim = threads of the last fused launch, dynamic shared memory = its shared memory.
+FB_KERNEL(512) k_fq_verify_fallback(const FB_GRID_CONSTANT VerifyParams P) {
+    FB_DYN_SMEM(smraw);
     const int gthreads = (int)(gridDim.x * blockDim.x), gtid = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    int bad = P.force;
+    int bad = P.force == 1;
     for (int ci = 0; ci < P.nchecks; ci++) {
         const Check &C = P.chk[ci];
         const int per_tile = C.est_cap, ntiles = C.ntx * C.nty;
@@ -486,14 +530,40 @@ FB_KERNEL(256) k_fq_verify_fallback(const FB_GRID_CONSTANT VerifyParams P) {
             const int v = C.est[i];
             if (v == kNoCheck) continue;
             const int want = C.act[(size_t)(along - 1) * C.dim_across + across * C.cell + e];
-            if (want != v) bad = 1;
+            if (want != v) {
+                if (C.first_block < 0) bad = 1;
+                else {
+                    const int cta = C.first_block + tj * C.ntx + ti;
+                    if (P.top.tile_bad[cta] == 0) {         // benign race: duplicates are filtered by the exchange below
+                        P.top.tile_bad[cta] = 1;
+                        const int slot = atomicAdd(P.counters + 1, 1);
+                        if (slot < P.bad_cap) P.bad_list[slot] = cta; else bad = 1;
+                    }
+                }
+            }
         }
     }
-    if (bad) atomicOr(P.flag, 1);
+    if (P.force == 2) {
+        for (int i = gtid; i < P.top_blocks && i < P.bad_cap; i += gthreads) P.bad_list[i] = i;
+        if (gtid == 0) P.counters[1] = imin(P.top_blocks, P.bad_cap);
+    }
+    if (bad) atomicOr(P.counters, 1);
     fb_grid_sync();
-    if (*(volatile int *)P.flag == 0) return;
-    if (gtid == 0) atomicAdd(P.flag + 1, 1);        // statistics: runs that needed the fallback
-    // ---- exact recomputation, one grid barrier per squeeze step
+    int nbad = *(volatile int *)(P.counters + 1);
+    if (*(volatile int *)P.counters == 0 && nbad == 0) return;
+    // ---- local repair of tiles of the last launch (a tile may be listed twice after a lost race: harmless)
+    if (*(volatile int *)P.counters == 0) {
+        nbad = imin(nbad, P.bad_cap);
+        for (int i = (int)blockIdx.x; i < nbad; i += (int)gridDim.x) {
+            tile_body(P.top, P.bad_list[i], true, smraw);
+            __syncthreads();
+        }
+        if (gtid == 0) atomicAdd(P.counters + 3, nbad);
+        fb_grid_sync();
+        if (*(volatile int *)P.counters == 0) return;
+    }
+    if (gtid == 0) atomicAdd(P.counters + 2, 1);
+    // ---- exact recomputation of the whole run, one grid barrier per squeeze step
     int i0 = 0;
     while (i0 < P.nops) {
         int i1 = i0;

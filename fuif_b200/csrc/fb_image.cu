@@ -34,7 +34,8 @@ extern "C" int fb_ctx_create(int device, void *stream, fb_ctx **out) {
     }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-    ctx->timing = getenv("FB_KERNEL_TIMING") != nullptr;
+    ctx->timing_stderr = getenv("FB_KERNEL_TIMING") != nullptr;
+    ctx->timing = ctx->timing_stderr;
     // keep freed plane memory in the stream-ordered pool instead of returning it to the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -59,13 +60,13 @@ extern "C" const char *fb_last_error(fb_ctx *ctx) { return ctx ? ctx->err.c_str(
 
 extern "C" int fb_ctx_synchronize(fb_ctx *ctx) {
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->timing && ctx->marks.size() > 1) {
+    if (ctx->timing_stderr && ctx->marks.size() > 1) {
         for (size_t i = 1; i < ctx->marks.size(); i++) {
             float ms = 0;
-            cudaEventElapsedTime(&ms, ctx->marks[i - 1].second, ctx->marks[i].second);
-            fprintf(stderr, "[timing] %-32s %8.1f us\n", ctx->marks[i].first.c_str(), ms * 1000.f);
+            cudaEventElapsedTime(&ms, ctx->marks[i - 1].ev, ctx->marks[i].ev);
+            fprintf(stderr, "[timing] %-32s %8.1f us\n", ctx->marks[i].name.c_str(), ms * 1000.f);
         }
-        for (auto &mk : ctx->marks) cudaEventDestroy(mk.second);
+        for (auto &mk : ctx->marks) cudaEventDestroy(mk.ev);
         ctx->marks.clear();
     }
     return FB_OK;
@@ -75,17 +76,41 @@ extern "C" long long fb_ctx_launch_count(fb_ctx *ctx) { return ctx ? ctx->launch
 
 extern "C" int fb_ctx_set_option(fb_ctx *ctx, int option, int value) {
     if (!ctx) return FB_ERR_INVALID;
-    if (option == FB_OPT_SQUEEZE_MODE && value >= 0 && value <= 2) { ctx->fq_mode = value; return FB_OK; }
+    if (option == FB_OPT_SQUEEZE_MODE && value >= 0 && value <= 3) { ctx->fq_mode = value; return FB_OK; }
+    if (option == FB_OPT_KERNEL_TIMING) { ctx->timing = value != 0 || ctx->timing_stderr; return FB_OK; }
     return FB_ERR_INVALID;
 }
 
-extern "C" long long fb_ctx_fallback_count(fb_ctx *ctx) {
-    if (!ctx || !ctx->fq_counters) return 0;
-    int v[2] = {0, 0};
+extern "C" long long fb_ctx_counter(fb_ctx *ctx, int which) {
+    if (!ctx || which < 0 || which > 1) return -1;
+    if (!ctx->fq_counters) return 0;
+    int v[4] = {0, 0, 0, 0};
     cudaSetDevice(ctx->device);
     if (cudaMemcpyAsync(v, ctx->fq_counters, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
-    return v[1];
+    return v[2 + which];
+}
+
+extern "C" long long fb_ctx_timing_report(fb_ctx *ctx, char *buf, size_t cap) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    std::string out;
+    for (size_t i = 1; i < ctx->marks.size(); i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->marks[i - 1].ev, ctx->marks[i].ev);
+        char line[256];
+        snprintf(line, sizeof(line), "%s\t%.3f\t%.0f\n", ctx->marks[i].name.c_str(), ms * 1000.0, ctx->marks[i].bytes);
+        out += line;
+    }
+    for (auto &mk : ctx->marks) cudaEventDestroy(mk.ev);
+    ctx->marks.clear();
+    if (buf && cap) {
+        const size_t n = std::min(cap - 1, out.size());
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return (long long)out.size();
 }
 
 int fb_plane_alloc(fb_ctx *ctx, size_t nsamples, int16_t **out) {

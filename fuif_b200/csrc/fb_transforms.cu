@@ -951,29 +951,36 @@ int fb_run_inv_squeeze_plan(fb_ctx *ctx, const std::vector<FbSqOp> &ops, const F
     static bool configured = false;
     if (!configured) {
         FB_CUDA(ctx, cudaFuncSetAttribute(fq::k_fq_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        FB_CUDA(ctx, cudaFuncSetAttribute(fq::k_fq_verify_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
     if (!ctx->fq_counters) {
         FB_CUDA(ctx, cudaMalloc((void **)&ctx->fq_counters, 4 * sizeof(int)));
         FB_CUDA(ctx, cudaMemsetAsync(ctx->fq_counters, 0, 4 * sizeof(int), ctx->stream));
     }
+    const int force = tun.force_fallback ? tun.force_fallback : (ctx->fq_mode == 2 ? 1 : (ctx->fq_mode == 3 ? 2 : 0));
+    const bool verify = P.need_verify || force;
     unsigned char *scratch = nullptr;
-    if (P.scratch_bytes) {
-        FB_CUDA(ctx, cudaMallocAsync((void **)&scratch, P.scratch_bytes, ctx->stream));
-        fq::relocate_scratch(P, scratch);
-    }
-    for (auto &L : P.launches) {
+    if (P.scratch_bytes) FB_CUDA(ctx, cudaMallocAsync((void **)&scratch, P.scratch_bytes, ctx->stream));
+    fq::relocate_scratch(P, scratch, ctx->fq_counters);
+    if (verify) FB_CUDA(ctx, cudaMemsetAsync(ctx->fq_counters, 0, 2 * sizeof(int), ctx->stream));     // [0] failed, [1] tiles to repair
+    for (size_t li = 0; li < P.launches.size(); li++) {
+        auto &L = P.launches[li];
         fq::k_fq_tiles<<<L.grid, L.threads, L.smem, ctx->stream>>>(L.task);
-        FB_LAUNCH_CHECK(ctx);
+        ctx->launches++;
+        ctx->mark(li + 1 == P.launches.size() ? "k_fq_tiles(last)" : "k_fq_tiles", L.bytes);
+        cudaError_t e__ = cudaGetLastError();
+        if (e__ != cudaSuccess) { ctx->err = std::string("k_fq_tiles launch: ") + cudaGetErrorString(e__); return FB_ERR_CUDA; }
     }
-    const int force = tun.force_fallback || ctx->fq_mode == 2;
-    if (P.need_verify || force) {
-        FB_CUDA(ctx, cudaMemsetAsync(ctx->fq_counters, 0, sizeof(int), ctx->stream));      // [0] = flag of this run
-        P.verify.flag = ctx->fq_counters;
+    if (verify) {
         P.verify.force = force;
+        if (force == 2 && !P.verify.bad_list) P.verify.force = 0;      // nothing speculative in this run
         void *args[] = {(void *)&P.verify};
-        FB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)fq::k_fq_verify_fallback, dim3(ctx->sm_count), dim3(256), args, 0, ctx->stream));
-        FB_LAUNCH_CHECK(ctx);
+        // one CTA per SM is always co-resident (<= 200 KiB of shared memory, <= 512 threads)
+        FB_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)fq::k_fq_verify_fallback, dim3(ctx->sm_count), dim3(P.verify_threads), args,
+                                                 P.verify_smem, ctx->stream));
+        ctx->launches++;
+        ctx->mark("k_fq_verify_fallback", 0);
     }
     if (scratch) cudaFreeAsync(scratch, ctx->stream);
     if (epilogue_done) *epilogue_done = P.epilogue_fused ? 1 : 0;

@@ -85,13 +85,23 @@ FB_API int fb_ctx_synchronize(fb_ctx *ctx);
 /* Number of kernels this library has launched on the context so far (bench.py's gpu_launches). */
 FB_API long long fb_ctx_launch_count(fb_ctx *ctx);
 
-/* Diagnostics / testing knobs (no reference counterpart).  FB_OPT_SQUEEZE_MODE: 0 = fused tile kernels for the
- * Squeeze inverse (default), 1 = one kernel per squeeze step, 2 = fused kernels + force the exact serial fallback. */
+/* Diagnostics / testing knobs (no reference counterpart).
+ * FB_OPT_SQUEEZE_MODE: 0 = fused tile kernels for the Squeeze inverse (default), 1 = one kernel per squeeze step,
+ *   2 = fused kernels + force the exact serial recompute, 3 = fused kernels + force the repair of every tile of the
+ *   last launch.  FB_OPT_KERNEL_TIMING: 1 = record a CUDA event after every launch (fb_ctx_timing_report). */
 #define FB_OPT_SQUEEZE_MODE 1
+#define FB_OPT_KERNEL_TIMING 2
 FB_API int fb_ctx_set_option(fb_ctx *ctx, int option, int value);
-/* Number of Squeeze inverses on this context whose speculative tile starts failed verification and were therefore
- * recomputed by the serial fallback kernel (results are bit-exact either way).  Synchronises the stream. */
-FB_API long long fb_ctx_fallback_count(fb_ctx *ctx);
+/* The fused Squeeze inverse starts tiles speculatively and verifies them (results are bit-exact either way).
+ * which = 0: Squeeze inverses so far that failed verification in an early launch and were recomputed serially;
+ * which = 1: tiles of last launches so far that failed verification and were recomputed from exact states.
+ * Synchronises the stream. */
+#define FB_COUNTER_SERIAL_FALLBACKS 0
+#define FB_COUNTER_REPAIRED_TILES 1
+FB_API long long fb_ctx_counter(fb_ctx *ctx, int which);
+/* With FB_OPT_KERNEL_TIMING: synchronises, then writes one line "name<TAB>microseconds<TAB>algorithmic bytes" per
+ * launch recorded since the last report (NUL-terminated, truncated to cap) and returns the untruncated length. */
+FB_API long long fb_ctx_timing_report(fb_ctx *ctx, char *buf, size_t cap);
 
 /* ---- fuif_decode --------------------------------------------------------------------------------------- */
 

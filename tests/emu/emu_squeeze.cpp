@@ -12,8 +12,8 @@ extern "C" {
 
 // opdesc[nops][9] = step, horizontal, avg plane, res plane (-1: none), out plane, wa, wr, ha, hr
 // ep[8] = kind, maxval, lo, hi, do_clamp, Y plane, Co plane, Cg plane
-// opts[6] = tile_w, tile_h, levels_per_launch, coarse_dim, threads_per_gang, force_fallback
-// stats[8] (out) = plan ok, launches, fallback ran, checks, failed comparisons (before the fallback), epilogue fused, max smem, total CTAs
+// opts[8] = tile_w, tile_h, levels_per_launch, coarse_dim, threads_per_gang, force (1 serial fallback, 2 repair all), warm_last, warm_mid
+// stats[9] (out) = plan ok, launches, serial fallback ran, checks, failed comparisons, epilogue fused, max smem, total CTAs, tiles repaired
 int emu_run_plan(int nplanes, int16_t **planes, int nops, const int *opdesc, const int *ep, const int *opts, int *stats) {
     (void)nplanes;
     std::vector<fq::PlanOp> ops(nops);
@@ -28,14 +28,15 @@ int emu_run_plan(int nplanes, int16_t **planes, int nops, const int *opdesc, con
     for (int j = 0; j < 3; j++) E.ycc[j] = ep[5 + j] >= 0 ? planes[ep[5 + j]] : nullptr;
     fq::PlanOptions O;
     O.tile_w = opts[0]; O.tile_h = opts[1]; O.levels_per_launch = opts[2]; O.coarse_dim = opts[3]; O.threads_per_gang = opts[4];
+    if (opts[6] > 0) O.warm_last = opts[6];
+    if (opts[7] > 0) O.warm_mid = opts[7];
     fq::Plan P = fq::make_plan(ops, E, O);
-    memset(stats, 0, 8 * sizeof(int));
+    memset(stats, 0, 9 * sizeof(int));
     stats[0] = P.ok;
     if (!P.ok) return 1;
     std::vector<unsigned char> scratch(P.scratch_bytes + 256, 0xEE);
-    fq::relocate_scratch(P, scratch.data());
-    int flags[2] = {0, 0};
-    P.verify.flag = flags;
+    int counters[4] = {0, 0, 0, 0};
+    fq::relocate_scratch(P, scratch.data(), counters);
     P.verify.force = opts[5];
     stats[1] = (int)P.launches.size();
     stats[5] = P.epilogue_fused;
@@ -62,9 +63,10 @@ int emu_run_plan(int nplanes, int16_t **planes, int nops, const int *opdesc, con
     }
     if (P.need_verify || P.verify.force) {
         const fq::VerifyParams V = P.verify;
-        cuemu::launch(4, 64, 0, true, [&]() { fq::k_fq_verify_fallback(V); });
+        cuemu::launch(3, (unsigned)P.verify_threads, P.verify_smem, true, [&]() { fq::k_fq_verify_fallback(V); });
     }
-    stats[2] = flags[0];
+    stats[2] = counters[2];
+    stats[8] = counters[3];
     return 0;
 }
 

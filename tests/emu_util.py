@@ -62,7 +62,7 @@ def run_plan(planes, ops, ep, opts):
     ptrs = (C.c_void_p * len(planes))(*[p.ctypes.data for p in planes])
     od = (C.c_int * (9 * len(ops)))(*[int(v) for o in ops for v in o])
     e = (C.c_int * 8)(*ep)
-    o = (C.c_int * 6)(*opts)
-    st = (C.c_int * 8)()
+    o = (C.c_int * 8)(*(list(opts) + [0] * (8 - len(opts))))
+    st = (C.c_int * 9)()
     L.emu_run_plan(len(planes), ptrs, len(ops), od, e, o, st)
     return list(st)

@@ -114,3 +114,29 @@ def test_keep_colour_transform_no_epilogue(oracle):
     pix = synth_image(100, 60, 3, 255, seed=9)
     params = default_squeeze_parameters(100, 60, 3)
     run_case(oracle, pix, 255, params, [32, 32, 4, 16, 64, 0], keep_colour=True)
+
+
+@pytest.mark.parametrize("shape", [(200, 120, 3), (131, 77, 3), (260, 40, 4), (64, 48, 1)])
+def test_repair_every_tile_of_last_launch(oracle, shape):
+    """force = 2: every tile of the last launch is recomputed in exact mode (chains start from the recorded act values)."""
+    w, h, nch = shape
+    maxval = 255 if nch != 4 else 16383
+    pix = synth_image(w, h, nch, maxval, seed=w)
+    params = default_squeeze_parameters(w, h, nch)
+    st = run_case(oracle, pix, maxval, params, [32, 32, 4, 16, 64, 2], ycocg=nch >= 3)
+    assert st[8] > 0 and st[2] == 0, st
+
+
+def test_short_warmup_failures_are_repaired_locally(oracle):
+    """warm-up of 2 pairs in the last launch: many speculative starts fail; the tiles are repaired, no serial fallback."""
+    pix = synth_image(256, 192, 3, 255, seed=21, noise=0.1)
+    params = default_squeeze_parameters(256, 192, 3)
+    st = run_case(oracle, pix, 255, params, [32, 32, 4, 32, 64, 0, 2, 12])
+    assert st[4] > 0 and st[8] > 0 and st[2] == 0, st
+
+
+def test_short_warmup_in_an_early_launch_takes_the_serial_fallback(oracle):
+    pix = synth_image(256, 192, 3, 255, seed=22, noise=0.1)
+    params = default_squeeze_parameters(256, 192, 3)
+    st = run_case(oracle, pix, 255, params, [32, 32, 2, 16, 64, 0, 8, 1], keep_colour=True)
+    assert st[4] > 0 and st[2] == 1, st

@@ -208,7 +208,7 @@ def test_cli_decodes_like_fuif_d(ctx, tmp_path):
         assert np.array_equal(got, want), name
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2], ids=["fused", "perlevel", "forced_fallback"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3], ids=["fused", "perlevel", "forced_fallback", "forced_repair"])
 @pytest.mark.parametrize("shape", [(512, 384, 3, 255), (1000, 333, 3, 255), (257, 513, 4, 16383), (640, 480, 1, 255)])
 def test_unsqueeze_modes_vs_oracle(oracle, shape, mode):
     """The fused tile kernels, the per-level kernels and the serial fallback kernel must all reproduce the oracle."""
@@ -231,6 +231,8 @@ def test_unsqueeze_modes_vs_oracle(oracle, shape, mode):
         assert np.array_equal(gi.pixels(), pix)
         if mode == 2:
             assert c2.fallbacks >= 1
+        if mode == 3:
+            assert c2.repaired_tiles >= 1 and c2.fallbacks == 0
         if mode == 0:
             assert c2.fallbacks == 0, "speculative tile starts failed verification on a smooth image"
         # keep = 1 (colour transform left in place): no epilogue
