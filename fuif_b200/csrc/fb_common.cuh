@@ -21,9 +21,9 @@ struct fb_ctx {
     int sm_count = 148;
     // MANIAC decoder resources (fb_maniac.cu), created lazily
     void *maniac_state = nullptr;
-    // fused unsqueeze (fb_fused_squeeze.cuh) device counters: [0] current run failed, [1] tiles to repair in the current
-    // run, [2] runs recomputed by the serial fallback so far, [3] tiles repaired so far; fq_mode: 0 default,
-    // 1 per-level kernels, 2 force the serial fallback, 3 force the repair of every tile of the last launch (tests)
+    // fused unsqueeze (fb_fused_squeeze.cuh) device counters, 8 ints laid out as fq::VerifyParams::counters says;
+    // fq_mode: 0 default, 1 per-level kernels, 2 force the serial fallback, 3 force the repair of every tile of the
+    // last launch (tests)
     int *fq_counters = nullptr;
     int fq_mode = 0;
     // FB_KERNEL_TIMING=1: a CUDA event after every launch, dumped by fb_ctx_synchronize (development aid)

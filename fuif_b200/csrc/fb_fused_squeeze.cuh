@@ -132,7 +132,7 @@ struct Task {
     int maxval, lo, hi, do_clamp;
     int ycc_gang[3], ycc_plane[3];      // kEpYCoCg: where Y, Co, Cg live
     int geom_off;               // byte offset of the geometry scratch in shared memory
-    int *counters;              // [0] run failed (serial fallback needed) [1] number of tiles to repair [2], [3] statistics
+    int *counters;              // see VerifyParams::counters
     unsigned char *tile_bad;    // last launch: one flag per CTA, cleared by the CTA itself, set by the verification
     Gang g[kMaxGangs];
 };
@@ -297,7 +297,7 @@ FB_DEV void run_level(const Gang &G, int k, const Geom &q, const Geom *qprev, co
             for (int pl = 0; pl < NP; pl++) {
                 const int16_t v = H ? o[pl][own_end_along - 1] : o[pl][(own_end_along - 1) * opitch];
                 int16_t *slot = &L.act[pl][(size_t)idx * dim_across + c];
-                if (exact) { if (*slot != v) atomicOr(counters, 1); }      // a repair must not change what neighbours checked against
+                if (exact) { if (*slot != v) atomicOr(counters + 2, 1); }  // a repair must not change what neighbours checked against
                 else *slot = v;
             }
         }
@@ -476,8 +476,9 @@ struct SerialOp {               // one unsqueeze step on one plane, as the per-l
 constexpr int kMaxChecks = 96, kMaxSerialOps = 96;
 struct VerifyParams {
     int nchecks, nops;
-    int *counters;              // [0] run failed [1] tiles to repair (both zeroed before the run) [2] runs that fell back
-                                // to the serial recompute [3] tiles repaired (statistics, never reset)
+    int *counters;              // zeroed before every run: [0] a check of an early launch failed [1] tiles of the last launch
+                                // to repair [2] a repair changed a published act;  statistics, never reset: [4] runs that
+                                // were recomputed serially [5] tiles repaired
     int *bad_list;              // CTA ids of the last launch to repair
     int bad_cap;
     int force;                  // testing: 1 = behave as if an early check had failed, 2 = repair every tile of the last launch
@@ -549,20 +550,21 @@ FB_KERNEL(512) k_fq_verify_fallback(const FB_GRID_CONSTANT VerifyParams P) {
     }
     if (bad) atomicOr(P.counters, 1);
     fb_grid_sync();
-    int nbad = *(volatile int *)(P.counters + 1);
-    if (*(volatile int *)P.counters == 0 && nbad == 0) return;
+    // counters[0] and [1] are stable from here on (repairs report through [2])
+    const int failed_early = *(volatile int *)P.counters;
+    const int nbad = imin(*(volatile int *)(P.counters + 1), P.bad_cap);
+    if (!failed_early && nbad == 0) return;
     // ---- local repair of tiles of the last launch (a tile may be listed twice after a lost race: harmless)
-    if (*(volatile int *)P.counters == 0) {
-        nbad = imin(nbad, P.bad_cap);
+    if (!failed_early) {
         for (int i = (int)blockIdx.x; i < nbad; i += (int)gridDim.x) {
             tile_body(P.top, P.bad_list[i], true, smraw);
             __syncthreads();
         }
-        if (gtid == 0) atomicAdd(P.counters + 3, nbad);
+        if (gtid == 0) atomicAdd(P.counters + 5, nbad);
         fb_grid_sync();
-        if (*(volatile int *)P.counters == 0) return;
+        if (*(volatile int *)(P.counters + 2) == 0) return;
     }
-    if (gtid == 0) atomicAdd(P.counters + 2, 1);
+    if (gtid == 0) atomicAdd(P.counters + 4, 1);
     // ---- exact recomputation of the whole run, one grid barrier per squeeze step
     int i0 = 0;
     while (i0 < P.nops) {

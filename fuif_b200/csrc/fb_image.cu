@@ -84,11 +84,11 @@ extern "C" int fb_ctx_set_option(fb_ctx *ctx, int option, int value) {
 extern "C" long long fb_ctx_counter(fb_ctx *ctx, int which) {
     if (!ctx || which < 0 || which > 1) return -1;
     if (!ctx->fq_counters) return 0;
-    int v[4] = {0, 0, 0, 0};
+    int v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaSetDevice(ctx->device);
     if (cudaMemcpyAsync(v, ctx->fq_counters, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
-    return v[2 + which];
+    return v[4 + which];
 }
 
 extern "C" long long fb_ctx_timing_report(fb_ctx *ctx, char *buf, size_t cap) {

@@ -955,15 +955,15 @@ int fb_run_inv_squeeze_plan(fb_ctx *ctx, const std::vector<FbSqOp> &ops, const F
         configured = true;
     }
     if (!ctx->fq_counters) {
-        FB_CUDA(ctx, cudaMalloc((void **)&ctx->fq_counters, 4 * sizeof(int)));
-        FB_CUDA(ctx, cudaMemsetAsync(ctx->fq_counters, 0, 4 * sizeof(int), ctx->stream));
+        FB_CUDA(ctx, cudaMalloc((void **)&ctx->fq_counters, 8 * sizeof(int)));
+        FB_CUDA(ctx, cudaMemsetAsync(ctx->fq_counters, 0, 8 * sizeof(int), ctx->stream));
     }
     const int force = tun.force_fallback ? tun.force_fallback : (ctx->fq_mode == 2 ? 1 : (ctx->fq_mode == 3 ? 2 : 0));
     const bool verify = P.need_verify || force;
     unsigned char *scratch = nullptr;
     if (P.scratch_bytes) FB_CUDA(ctx, cudaMallocAsync((void **)&scratch, P.scratch_bytes, ctx->stream));
     fq::relocate_scratch(P, scratch, ctx->fq_counters);
-    if (verify) FB_CUDA(ctx, cudaMemsetAsync(ctx->fq_counters, 0, 2 * sizeof(int), ctx->stream));     // [0] failed, [1] tiles to repair
+    if (verify) FB_CUDA(ctx, cudaMemsetAsync(ctx->fq_counters, 0, 4 * sizeof(int), ctx->stream));     // per-run part, see fq::VerifyParams
     for (size_t li = 0; li < P.launches.size(); li++) {
         auto &L = P.launches[li];
         fq::k_fq_tiles<<<L.grid, L.threads, L.smem, ctx->stream>>>(L.task);

@@ -35,7 +35,7 @@ int emu_run_plan(int nplanes, int16_t **planes, int nops, const int *opdesc, con
     stats[0] = P.ok;
     if (!P.ok) return 1;
     std::vector<unsigned char> scratch(P.scratch_bytes + 256, 0xEE);
-    int counters[4] = {0, 0, 0, 0};
+    int counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     fq::relocate_scratch(P, scratch.data(), counters);
     P.verify.force = opts[5];
     stats[1] = (int)P.launches.size();
@@ -65,8 +65,8 @@ int emu_run_plan(int nplanes, int16_t **planes, int nops, const int *opdesc, con
         const fq::VerifyParams V = P.verify;
         cuemu::launch(3, (unsigned)P.verify_threads, P.verify_smem, true, [&]() { fq::k_fq_verify_fallback(V); });
     }
-    stats[2] = counters[2];
-    stats[8] = counters[3];
+    stats[2] = counters[4];
+    stats[8] = counters[5];
     return 0;
 }
 
