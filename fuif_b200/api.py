@@ -186,8 +186,8 @@ class Context:
         return int(self.lib.fb_ctx_launch_count(self.h))
 
     def set_squeeze_mode(self, mode: int) -> None:
-        """0 fused tile kernels (default), 1 one kernel per squeeze step, 2 fused + forced serial recompute, 3 fused +
-        forced repair of every tile of the last launch (tests)."""
+        """0 direct per-step kernels (default), 1 tiled per-step kernels only, 4 fused tile kernels, 2 fused + forced serial
+        recompute, 3 fused + forced repair of every tile of the last launch (tests)."""
         self.check(self.lib.fb_ctx_set_option(self.h, FB_OPT_SQUEEZE_MODE, mode), "fb_ctx_set_option")
 
     @property

@@ -22,8 +22,8 @@ struct fb_ctx {
     // MANIAC decoder resources (fb_maniac.cu), created lazily
     void *maniac_state = nullptr;
     // fused unsqueeze (fb_fused_squeeze.cuh) device counters, 8 ints laid out as fq::VerifyParams::counters says;
-    // fq_mode: 0 default, 1 per-level kernels, 2 force the serial fallback, 3 force the repair of every tile of the
-    // last launch (tests)
+    // fq_mode (FB_OPT_SQUEEZE_MODE): 0 default (direct per-step kernels), 1 tiled per-step kernels only, 2 fused tile
+    // kernels + forced serial fallback, 3 fused + forced repair of every tile of the last launch, 4 fused
     int *fq_counters = nullptr;
     int fq_mode = 0;
     // FB_KERNEL_TIMING=1: a CUDA event after every launch, dumped by fb_ctx_synchronize (development aid)
@@ -92,8 +92,9 @@ struct FbSqEpilogue {
     int kind;                   // 0 none, 1 clamp every final plane, 2 inverse YCoCg on ycc[0..2] (+ clamp of every final plane)
     int maxval, lo, hi, do_clamp;
     const int16_t *ycc[3];
+    int16_t *rout;              // kind 2: a spare W x H plane for R when the epilogue cannot work in place
 };
-// *epilogue_done = 1 if the epilogue was applied by the plan's last launch
+// *epilogue_done = 0: not applied; 1: applied in place; 2: applied with R written to ep->rout (G, B in ycc[1], ycc[2])
 int fb_run_inv_squeeze_plan(fb_ctx *ctx, const std::vector<FbSqOp> &ops, const FbSqEpilogue *ep, int *epilogue_done);
 // forward Squeeze steps (squeeze.h:135-170, 227-263)
 int fb_launch_fwd_hsqueeze(fb_ctx *ctx, const int16_t *in, int16_t *avg, int16_t *res, int w, int h);

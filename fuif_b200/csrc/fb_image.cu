@@ -76,7 +76,7 @@ extern "C" long long fb_ctx_launch_count(fb_ctx *ctx) { return ctx ? ctx->launch
 
 extern "C" int fb_ctx_set_option(fb_ctx *ctx, int option, int value) {
     if (!ctx) return FB_ERR_INVALID;
-    if (option == FB_OPT_SQUEEZE_MODE && value >= 0 && value <= 3) { ctx->fq_mode = value; return FB_OK; }
+    if (option == FB_OPT_SQUEEZE_MODE && value >= 0 && value <= 4) { ctx->fq_mode = value; return FB_OK; }
     if (option == FB_OPT_KERNEL_TIMING) { ctx->timing = value != 0 || ctx->timing_stderr; return FB_OK; }
     return FB_ERR_INVALID;
 }
@@ -290,7 +290,17 @@ static int inv_squeeze(fb_image *img, const std::vector<int> &params, int ep_kin
         }
         ep.maxval = img->info.maxval; ep.lo = img->info.minval; ep.hi = img->info.maxval;
     }
-    int rc = fb_run_inv_squeeze_plan(ctx, ops, ep.kind ? &ep : nullptr, ep_done);
+    if (ep.kind == 2) {
+        int rc0 = fb_plane_alloc(ctx, chan_samples(img->ch[m].d), &ep.rout);
+        if (rc0) return rc0;
+    }
+    int done = 0;
+    int rc = fb_run_inv_squeeze_plan(ctx, ops, ep.kind ? &ep : nullptr, &done);
+    if (ep.rout) {
+        if (!rc && done == 2) { to_free.push_back(img->ch[m].dev); img->ch[m].dev = ep.rout; }
+        else to_free.push_back(ep.rout);
+    }
+    if (ep_done) *ep_done = done ? 1 : 0;
     // Pass 3: the consumed planes go back to the stream-ordered pool (after the kernels in stream order).
     for (auto q : to_free) fb_plane_free(ctx, q);
     return rc;

@@ -6,6 +6,7 @@
 // and an add into an FMA: the reference is built for baseline x86-64 and rounds after every operation.
 #include "fb_common.cuh"
 #include "fb_fused_plan.h"
+#include "fb_direct_plan.h"
 
 #include <stdlib.h>
 
@@ -832,8 +833,11 @@ int fb_launch_inv_squeeze_batch(fb_ctx *ctx, int horizontal, int n, const int16_
 }
 // Executes a planned sequence of unsqueeze steps: coarse levels of every plane in one pyramid launch, the rest as one
 // batched launch per step.
-static int run_inv_squeeze_plan_per_level(fb_ctx *ctx, const std::vector<FbSqOp> &ops) {
+// use_direct: steps whose planes are eligible run on the direct kernels (fb_direct_squeeze.cuh), which can also carry
+// the epilogue (inverse YCoCg on the step that produces Co and Cg, final clamp on every plane's last step).
+static int run_inv_squeeze_plan_per_level(fb_ctx *ctx, const std::vector<FbSqOp> &ops, bool use_direct, const FbSqEpilogue *ep, int *epilogue_done) {
     const int n = (int)ops.size();
+    if (epilogue_done) *epilogue_done = 0;
     if (!n) return FB_OK;
     // chains: op k continues the chain whose last op produced its `avg` plane
     std::vector<int> chain(n, -1), prev(n, -1);
@@ -880,41 +884,120 @@ static int run_inv_squeeze_plan_per_level(fb_ctx *ctx, const std::vector<FbSqOp>
         k_inv_squeeze_pyramid<<<P.nchains, 1024, smem, ctx->stream>>>(P);
         FB_LAUNCH_CHECK(ctx);
     }
-    // the remaining ops, one batched launch per squeeze step (up to four planes each)
+    // ---- can the epilogue ride on the direct kernels?  Every final plane's last op must be direct-eligible (and not
+    // part of the pyramid launch); for YCoCg the very last step must be the horizontal step producing Co and Cg.
+    auto as_step_op = [&](const FbSqOp &o) {
+        dq::StepOp so;
+        so.avg = o.avg; so.res = o.res; so.out = o.out; so.wa = o.wa; so.wr = o.wr; so.ha = o.ha; so.hr = o.hr; so.clamp = 0;
+        return so;
+    };
+    std::vector<char> is_final(n, 1), clamp_op(n, 0);
+    for (int k = 0; k < n; k++)
+        for (int q = k + 1; q < n; q++) if (ops[q].avg == ops[k].out) is_final[k] = 0;
+    bool ep_ok = use_direct && ep && ep->kind != 0;
+    int ico = -1, icg = -1;
+    if (ep_ok) {
+        const int last_step = ops[n - 1].step;
+        for (int k = 0; k < n && ep_ok; k++) {
+            if (!is_final[k]) continue;
+            const bool elig = !fused[k] && (ops[k].horizontal ? dq::h_eligible(as_step_op(ops[k])) : dq::v_eligible(as_step_op(ops[k])));
+            if (ep->kind == 2 && ops[k].out == ep->ycc[0]) { if (ops[k].step == last_step) ep_ok = false; continue; }   // Y: consumed by the epilogue, never clamped
+            if (ep->kind == 2 && (ops[k].out == ep->ycc[1] || ops[k].out == ep->ycc[2])) {
+                if (!elig || !ops[k].horizontal || ops[k].step != last_step) ep_ok = false;
+                (ops[k].out == ep->ycc[1] ? ico : icg) = k;
+                continue;
+            }
+            if (ep->do_clamp) { if (!elig) ep_ok = false; clamp_op[k] = 1; }
+        }
+        if (ep->kind == 2) {
+            if (ico < 0 || icg < 0 || !ep->rout) ep_ok = false;
+            else if (ops[ico].wa != ops[icg].wa || ops[ico].ha != ops[icg].ha) ep_ok = false;
+            bool have_y = false;
+            for (int k = 0; k < n; k++) if (is_final[k] && ops[k].out == ep->ycc[0]) have_y = true;
+            if (!have_y) ep_ok = false;
+        }
+    }
+    if (!ep_ok) std::fill(clamp_op.begin(), clamp_op.end(), 0);
+    static bool direct_configured = false;
+    // ---- the remaining ops, step by step: direct kernels where eligible, the tiled kernels for the rest
     int k = 0;
+    bool ep_applied = false;
     while (k < n) {
         if (fused[k]) { k++; continue; }
-        const int16_t *avgp[4], *resp[4];
-        int16_t *outp[4];
-        int wa[4], wr[4], ha[4], hr[4], m = 0;
         const int step = ops[k].step, horizontal = ops[k].horizontal;
+        std::vector<int> idx;
         int q = k;
-        while (q < n && ops[q].step == step && m < 4) {
-            if (!fused[q]) {
-                avgp[m] = ops[q].avg; resp[m] = ops[q].res; outp[m] = ops[q].out;
-                wa[m] = ops[q].wa; wr[m] = ops[q].wr; ha[m] = ops[q].ha; hr[m] = ops[q].hr; m++;
+        while (q < n && ops[q].step == step) { if (!fused[q]) idx.push_back(q); q++; }
+        std::vector<int> rest = idx;
+        if (use_direct) {
+            std::vector<dq::StepOp> sops;
+            for (int i : idx) { dq::StepOp so = as_step_op(ops[i]); so.clamp = clamp_op[i]; sops.push_back(so); }
+            dq::StepEpilogue E;
+            if (ep_ok && ep->kind == 2 && step == ops[n - 1].step) {
+                E.enabled = 1; E.yin = ep->ycc[0]; E.rout = ep->rout; E.co_out = ep->ycc[1]; E.cg_out = ep->ycc[2];
+                E.maxval = ep->maxval; E.lo = ep->lo; E.hi = ep->hi; E.do_clamp = ep->do_clamp;
             }
-            q++;
+            dq::StepPlan SP = dq::plan_step(sops, horizontal != 0, E, ep ? ep->lo : 0, ep ? ep->hi : 0, ctx->sm_count);
+            if (E.enabled && !SP.epilogue_done) { ctx->err = "internal: YCoCg epilogue planned but not placed"; return FB_ERR_INVALID; }
+            if (!direct_configured) {
+                FB_CUDA(ctx, cudaFuncSetAttribute(dq::k_inv_hsq_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                FB_CUDA(ctx, cudaFuncSetAttribute(dq::k_inv_vsq_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                direct_configured = true;
+            }
+            if (SP.hj.n) {
+                dq::k_inv_hsq_direct<<<SP.h_grid, SP.h_threads, SP.h_smem, ctx->stream>>>(SP.hj);
+                ctx->launches++;
+                ctx->mark(SP.epilogue_done ? "k_inv_hsq_direct(ycocg)" : "k_inv_hsq_direct", SP.bytes);
+            }
+            if (SP.vj.n) {
+                dq::k_inv_vsq_direct<<<SP.v_grid, SP.v_threads, SP.v_smem, ctx->stream>>>(SP.vj);
+                ctx->launches++;
+                ctx->mark("k_inv_vsq_direct", SP.bytes);
+            }
+            cudaError_t e__ = cudaGetLastError();
+            if (e__ != cudaSuccess) { ctx->err = std::string("direct unsqueeze launch: ") + cudaGetErrorString(e__); return FB_ERR_CUDA; }
+            if (SP.epilogue_done) ep_applied = true;
+            rest.clear();
+            for (int i : SP.leftover) {
+                if (clamp_op[idx[i]]) { ctx->err = "internal: clamp planned on an op the direct kernels refused"; return FB_ERR_INVALID; }
+                rest.push_back(idx[i]);
+            }
         }
-        int rc = fb_launch_inv_squeeze_batch(ctx, horizontal, m, avgp, resp, outp, wa, wr, ha, hr);
-        if (rc) return rc;
+        for (size_t r0 = 0; r0 < rest.size(); r0 += 4) {
+            const int16_t *avgp[4], *resp[4];
+            int16_t *outp[4];
+            int wa[4], wr[4], ha[4], hr[4], m = 0;
+            for (size_t r = r0; r < rest.size() && m < 4; r++, m++) {
+                const FbSqOp &o = ops[rest[r]];
+                avgp[m] = o.avg; resp[m] = o.res; outp[m] = o.out; wa[m] = o.wa; wr[m] = o.wr; ha[m] = o.ha; hr[m] = o.hr;
+            }
+            int rc = fb_launch_inv_squeeze_batch(ctx, horizontal, m, avgp, resp, outp, wa, wr, ha, hr);
+            if (rc) return rc;
+        }
         k = q;
+    }
+    if (ep_ok && epilogue_done) {
+        if (ep->kind == 2) *epilogue_done = ep_applied ? 2 : 0;
+        else *epilogue_done = 1;
+        if (ep->kind == 2 && !ep_applied) { ctx->err = "internal: YCoCg epilogue not applied"; return FB_ERR_INVALID; }
     }
     return FB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Fused path: the whole Squeeze inverse in a handful of tile-kernel launches (fb_fused_squeeze.cuh) + one
-// verification launch.  Tunables (development / profiling only): FB_SQUEEZE_MODE=perlevel|fused, FB_FQ_TILE=WxH,
-// FB_FQ_LEVELS, FB_FQ_COARSE, FB_FQ_THREADS, FB_FQ_FORCE_FALLBACK=1.
+// Entry point of the Squeeze inverse.  Default: one launch per squeeze step on the direct kernels
+// (fb_direct_squeeze.cuh), pyramid kernel for the coarse levels, tiled kernels for ineligible planes.  Optional
+// (FB_OPT_SQUEEZE_MODE >= 2 / FB_SQUEEZE_MODE=fused): the multi-level fused tile kernels (fb_fused_squeeze.cuh) + one
+// verification launch; tunables for that path: FB_FQ_TILE=WxH, FB_FQ_LEVELS, FB_FQ_COARSE, FB_FQ_THREADS,
+// FB_FQ_FORCE_FALLBACK.
 // ---------------------------------------------------------------------------------------------------------
 namespace {
 struct FqTunables {
-    bool fused = true;
+    int mode = 0;               // 0 direct per-step kernels (default), 1 tiled per-step kernels only, 4 fused tile kernels
     int force_fallback = 0;
     fq::PlanOptions opt;
     FqTunables() {
-        if (const char *m = getenv("FB_SQUEEZE_MODE")) fused = std::string(m) != "perlevel";
+        if (const char *m = getenv("FB_SQUEEZE_MODE")) mode = std::string(m) == "perlevel" ? 1 : (std::string(m) == "fused" ? 4 : 0);
         if (const char *t = getenv("FB_FQ_TILE")) { int a = 0, b = 0; if (sscanf(t, "%dx%d", &a, &b) == 2) { opt.tile_w = a; opt.tile_h = b; } }
         if (const char *t = getenv("FB_FQ_LEVELS")) opt.levels_per_launch = atoi(t);
         if (const char *t = getenv("FB_FQ_COARSE")) opt.coarse_dim = atoi(t);
@@ -930,7 +1013,8 @@ int fb_run_inv_squeeze_plan(fb_ctx *ctx, const std::vector<FbSqOp> &ops, const F
     if (ops.empty()) return FB_OK;
     const FqTunables &tun = fq_tunables();
     fq::Plan P;
-    if (tun.fused && ctx->fq_mode != 1) {
+    const int mode = ctx->fq_mode ? ctx->fq_mode : tun.mode;
+    if (mode >= 2) {
         std::vector<fq::PlanOp> po(ops.size());
         for (size_t i = 0; i < ops.size(); i++) {
             po[i].step = ops[i].step; po[i].horizontal = ops[i].horizontal;
@@ -946,7 +1030,7 @@ int fb_run_inv_squeeze_plan(fb_ctx *ctx, const std::vector<FbSqOp> &ops, const F
         // an epilogue that cannot be fused is left to the caller; without it the plan is still good
         if (P.ok && ep && ep->kind != fq::kEpNone && !P.epilogue_fused) { E = fq::EpilogueSpec(); P = fq::make_plan(po, E, tun.opt); }
     }
-    if (!P.ok) return run_inv_squeeze_plan_per_level(ctx, ops);
+    if (!P.ok) return run_inv_squeeze_plan_per_level(ctx, ops, mode != 1, mode != 1 ? ep : nullptr, epilogue_done);
 
     static bool configured = false;
     if (!configured) {
@@ -958,7 +1042,7 @@ int fb_run_inv_squeeze_plan(fb_ctx *ctx, const std::vector<FbSqOp> &ops, const F
         FB_CUDA(ctx, cudaMalloc((void **)&ctx->fq_counters, 8 * sizeof(int)));
         FB_CUDA(ctx, cudaMemsetAsync(ctx->fq_counters, 0, 8 * sizeof(int), ctx->stream));
     }
-    const int force = tun.force_fallback ? tun.force_fallback : (ctx->fq_mode == 2 ? 1 : (ctx->fq_mode == 3 ? 2 : 0));
+    const int force = tun.force_fallback ? tun.force_fallback : (mode == 2 ? 1 : (mode == 3 ? 2 : 0));
     const bool verify = P.need_verify || force;
     unsigned char *scratch = nullptr;
     if (P.scratch_bytes) FB_CUDA(ctx, cudaMallocAsync((void **)&scratch, P.scratch_bytes, ctx->stream));

@@ -86,13 +86,15 @@ FB_API int fb_ctx_synchronize(fb_ctx *ctx);
 FB_API long long fb_ctx_launch_count(fb_ctx *ctx);
 
 /* Diagnostics / testing knobs (no reference counterpart).
- * FB_OPT_SQUEEZE_MODE: 0 = fused tile kernels for the Squeeze inverse (default), 1 = one kernel per squeeze step,
- *   2 = fused kernels + force the exact serial recompute, 3 = fused kernels + force the repair of every tile of the
- *   last launch.  FB_OPT_KERNEL_TIMING: 1 = record a CUDA event after every launch (fb_ctx_timing_report). */
+ * FB_OPT_SQUEEZE_MODE: which kernels undo a Squeeze -- 0 = one launch per squeeze step on the direct (register
+ *   resident, 128-bit access) kernels with the inverse YCoCg / clamp riding on the last step (default), 1 = the tiled
+ *   per-step kernels only, 4 = multi-level fused tile kernels, 2 = fused + force the exact serial recompute,
+ *   3 = fused + force the repair of every tile of the last launch.
+ * FB_OPT_KERNEL_TIMING: 1 = record a CUDA event after every launch (fb_ctx_timing_report). */
 #define FB_OPT_SQUEEZE_MODE 1
 #define FB_OPT_KERNEL_TIMING 2
 FB_API int fb_ctx_set_option(fb_ctx *ctx, int option, int value);
-/* The fused Squeeze inverse starts tiles speculatively and verifies them (results are bit-exact either way).
+/* The fused Squeeze inverse (mode >= 2) starts tiles speculatively and verifies them (results are bit-exact either way).
  * which = 0: Squeeze inverses so far that failed verification in an early launch and were recomputed serially;
  * which = 1: tiles of last launches so far that failed verification and were recomputed from exact states.
  * Synchronises the stream. */

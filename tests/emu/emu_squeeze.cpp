@@ -82,3 +82,66 @@ int emu_check_pair(const int16_t *prev, const int16_t *av, const int16_t *nx, co
     return bad;
 }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// direct per-step kernels (fb_direct_squeeze.cuh + fb_direct_plan.h)
+// ---------------------------------------------------------------------------------------------------------
+#include "fb_direct_plan.h"
+
+extern "C" {
+// opdesc[nops][10] = step, horizontal, avg plane, res plane (-1), out plane, wa, wr, ha, hr, clamp
+// ep[9] = enabled, Y plane, R-out plane, Co-out plane, Cg-out plane, maxval, lo, hi, do_clamp
+// stats[4] (out) = direct launches, ops handled by the direct kernels, ops left to the serial code, epilogue done
+int emu_run_direct(int nplanes, int16_t **planes, int nops, const int *opdesc, const int *ep, int lo, int hi, int *stats) {
+    (void)nplanes;
+    memset(stats, 0, 4 * sizeof(int));
+    int i0 = 0;
+    while (i0 < nops) {
+        int i1 = i0;
+        while (i1 < nops && opdesc[10 * i1] == opdesc[10 * i0]) i1++;
+        const bool horizontal = opdesc[10 * i0 + 1] != 0;
+        std::vector<dq::StepOp> ops;
+        for (int i = i0; i < i1; i++) {
+            const int *d = opdesc + 10 * i;
+            dq::StepOp o;
+            o.avg = planes[d[2]]; o.res = d[3] >= 0 ? planes[d[3]] : nullptr; o.out = planes[d[4]];
+            o.wa = d[5]; o.wr = d[6]; o.ha = d[7]; o.hr = d[8]; o.clamp = d[9];
+            ops.push_back(o);
+        }
+        dq::StepEpilogue E;
+        if (ep[0] && i1 == nops) {
+            E.enabled = 1; E.yin = planes[ep[1]]; E.rout = planes[ep[2]]; E.co_out = planes[ep[3]]; E.cg_out = planes[ep[4]];
+            E.maxval = ep[5]; E.lo = ep[6]; E.hi = ep[7]; E.do_clamp = ep[8];
+        }
+        dq::StepPlan P = dq::plan_step(ops, horizontal, E, lo, hi, 4);
+        if (P.hj.n) {
+            const dq::HJobs J = P.hj;
+            cuemu::launch((unsigned)P.h_grid, (unsigned)P.h_threads, P.h_smem, false, [&]() { dq::k_inv_hsq_direct(J); });
+            stats[0]++;
+            for (int j = 0; j < J.n; j++) stats[1] += J.j[j].np;
+        }
+        if (P.vj.n) {
+            const dq::VJobs J = P.vj;
+            cuemu::launch((unsigned)P.v_grid, (unsigned)P.v_threads, P.v_smem, false, [&]() { dq::k_inv_vsq_direct(J); });
+            stats[0]++;
+            stats[1] += J.n;
+        }
+        for (int k : P.leftover) {
+            const dq::StepOp &o = ops[k];
+            fq::SerialOp so;
+            so.avg = o.avg; so.res = o.res; so.out = o.out; so.wa = o.wa; so.wr = o.wr; so.ha = o.ha; so.hr = o.hr;
+            so.horizontal = horizontal; so.step = 0;
+            const int nchain = horizontal ? o.ha : o.wa;
+            for (int c = 0; c < nchain; c++) fq::serial_chain(so, c);
+            if (o.clamp) {
+                const size_t nn = (size_t)(horizontal ? o.wa + o.wr : o.wa) * (horizontal ? o.ha : o.ha + o.hr);
+                for (size_t q = 0; q < nn; q++) o.out[q] = (int16_t)fq::clampi(o.out[q], lo, hi);
+            }
+            stats[2]++;
+        }
+        if (P.epilogue_done) stats[3] = 1;
+        i0 = i1;
+    }
+    return 0;
+}
+}

@@ -13,7 +13,8 @@ EMU_DIR = os.path.join(HERE, "emu")
 LIB = os.path.join(EMU_DIR, "libfb_emu.so")
 SRCS = [os.path.join(EMU_DIR, "emu_squeeze.cpp"), os.path.join(EMU_DIR, "cuemu.h"),
         os.path.join(ROOT, "fuif_b200", "csrc", "fb_fused_squeeze.cuh"), os.path.join(ROOT, "fuif_b200", "csrc", "fb_fused_plan.h"),
-        os.path.join(ROOT, "fuif_b200", "csrc", "fb_port.h")]
+        os.path.join(ROOT, "fuif_b200", "csrc", "fb_port.h"), os.path.join(ROOT, "fuif_b200", "csrc", "fb_direct_squeeze.cuh"),
+        os.path.join(ROOT, "fuif_b200", "csrc", "fb_direct_plan.h")]
 _lib = None
 
 
@@ -26,6 +27,7 @@ def lib():
         L = C.CDLL(LIB)
         L.emu_run_plan.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.emu_check_pair.argtypes = [C.c_void_p] * 4 + [C.c_int]
+        L.emu_run_direct.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -65,4 +67,15 @@ def run_plan(planes, ops, ep, opts):
     o = (C.c_int * 8)(*(list(opts) + [0] * (8 - len(opts))))
     st = (C.c_int * 9)()
     L.emu_run_plan(len(planes), ptrs, len(ops), od, e, o, st)
+    return list(st)
+
+
+def run_direct(planes, ops10, ep9, lo, hi):
+    """ops10: (step, horizontal, avg, res, out, wa, wr, ha, hr, clamp).  Returns [launches, direct ops, serial ops, epilogue done]."""
+    L = lib()
+    ptrs = (C.c_void_p * len(planes))(*[p.ctypes.data for p in planes])
+    od = (C.c_int * (10 * len(ops10)))(*[int(v) for o in ops10 for v in o])
+    e = (C.c_int * 9)(*ep9)
+    st = (C.c_int * 4)()
+    L.emu_run_direct(len(planes), ptrs, len(ops10), od, e, lo, hi, st)
     return list(st)

@@ -208,8 +208,8 @@ def test_cli_decodes_like_fuif_d(ctx, tmp_path):
         assert np.array_equal(got, want), name
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3], ids=["fused", "perlevel", "forced_fallback", "forced_repair"])
-@pytest.mark.parametrize("shape", [(512, 384, 3, 255), (1000, 333, 3, 255), (257, 513, 4, 16383), (640, 480, 1, 255)])
+@pytest.mark.parametrize("mode", [0, 1, 4, 2, 3], ids=["direct", "tiled", "fused", "fused_forced_fallback", "fused_forced_repair"])
+@pytest.mark.parametrize("shape", [(512, 384, 3, 255), (1000, 333, 3, 255), (257, 513, 4, 16383), (640, 480, 1, 255), (1024, 768, 4, 16383)])
 def test_unsqueeze_modes_vs_oracle(oracle, shape, mode):
     """The fused tile kernels, the per-level kernels and the serial fallback kernel must all reproduce the oracle."""
     from fuif_b200 import api
@@ -233,7 +233,7 @@ def test_unsqueeze_modes_vs_oracle(oracle, shape, mode):
             assert c2.fallbacks >= 1
         if mode == 3:
             assert c2.repaired_tiles >= 1 and c2.fallbacks == 0
-        if mode == 0:
+        if mode == 4:
             assert c2.fallbacks == 0, "speculative tile starts failed verification on a smooth image"
         # keep = 1 (colour transform left in place): no epilogue
         if c >= 3:
@@ -265,9 +265,11 @@ def test_fused_unsqueeze_full_range_garbage(oracle):
             p.data = rng.integers(-32768, 32768, size=p.data.shape).astype(np.int16)
             a = np.ascontiguousarray(p.data)
             L.fo_plane_set(oi.h, i, a.ctypes.data, a.size)
-        gi = upload_plane_image(api, pi, c2)
-        gi.undo_transforms(0)
         oi.undo_transforms(0)
-        po.compare_plane_images(gpu_plane_image(po, gi), oi.to_plane_image(), "garbage fused")
+        for mode in (0, 4):
+            c2.set_squeeze_mode(mode)
+            gi = upload_plane_image(api, pi, c2)
+            gi.undo_transforms(0)
+            po.compare_plane_images(gpu_plane_image(po, gi), oi.to_plane_image(), f"garbage mode {mode}")
     finally:
         c2.close()
