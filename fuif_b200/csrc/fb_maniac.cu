@@ -18,6 +18,7 @@
 // planes it back-references), which are guaranteed to be running already.
 #include "fb_common.cuh"
 
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -72,8 +73,10 @@ struct Params {
     WarpScratch *scratch;
     int maxw;
     int warp_smem;          // bytes of shared memory per stream slot (after the block's 16 KiB chance table)
-    int helpers;            // walker warps per stream (0 or kMaxWalkers)
+    int helpers;            // extra warps per stream (0, 7 or 15); every fourth one stays idle, the others are walkers
     int debug;              // FB_MANIAC_DEBUG=1: trace group headers from lane 0
+    int walker_sleep;       // ns a walker sleeps between polls of the decoder's progress
+    int walkers_used;       // tuning: use at most this many walkers
 };
 
 __device__ __forceinline__ int s16(int x) { return (int)(short)x; }
@@ -401,6 +404,7 @@ struct Smem {
     unsigned char *dyn;     // dynamic region: tree-node cache, then leaf chances (resident or direct-mapped cache)
     int dyn_bytes;
     struct Mail *mail;      // mailbox shared with the walker warps (nullptr: no walkers)
+    int walker_sleep;
     int *ldrows;            // [walkers][32][kLdRowStride] per-lane property values of the walkers
     int nwalkers;
 };
@@ -464,23 +468,34 @@ __device__ __forceinline__ void chunk_prologue(DImage &img, const DChan &ch, int
             TT = (y > 1) ? row2[x] : T1;
         }
         int *pp = cprop + lane * kPropStride;
-        for (int r = 0; r < nrefchan; r++) {
-            const DChan &cj = img.ch[refchan[r]];
-            int ry = (y << ch.vshift) >> cj.vshift;
-            if (ry >= cj.h) ry = cj.h - 1;
-            int rx;
-            if (ch.hshift == cj.hshift && w <= cj.w) rx = x;
-            else if (ch.hshift < cj.hshift) {
-                const int stepsize = (1 << cj.hshift) >> ch.hshift;     // all samples but the last are repeated stepsize times
-                rx = stepsize > 0 ? x / stepsize : cj.w - 1;
-                if (rx > cj.w - 1) rx = cj.w - 1;
-            } else {
-                rx = (x << ch.hshift) >> cj.hshift;
-                if (rx >= cj.w) rx = cj.w - 1;
+        // every load first (one memory latency for all of them), then the arithmetic
+        int rv[16];
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            rv[r] = 0;
+            if (r < nrefchan) {
+                const DChan &cj = img.ch[refchan[r]];
+                int ry = (y << ch.vshift) >> cj.vshift;
+                if (ry >= cj.h) ry = cj.h - 1;
+                int rx;
+                if (ch.hshift == cj.hshift && w <= cj.w) rx = x;
+                else if (ch.hshift < cj.hshift) {
+                    const int stepsize = (1 << cj.hshift) >> ch.hshift;     // all samples but the last are repeated stepsize times
+                    rx = stepsize > 0 ? x / stepsize : cj.w - 1;
+                    if (rx > cj.w - 1) rx = cj.w - 1;
+                } else {
+                    rx = (x << ch.hshift) >> cj.hshift;
+                    if (rx >= cj.w) rx = cj.w - 1;
+                }
+                rv[r] = __ldcg(cj.data + (size_t)ry * cj.w + rx);
             }
-            const int v = __ldcg(cj.data + (size_t)ry * cj.w + rx);
-            pp[2 * r] = fooabs(v);
-            pp[2 * r + 1] = slog(v);
+        }
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            if (r < nrefchan) {
+                pp[2 * r] = fooabs(rv[r]);
+                pp[2 * r + 1] = slog(rv[r]);
+            }
         }
         pp[nref + 0] = fooabs(T1);
         pp[nref + 2] = slog(T1);
@@ -492,24 +507,60 @@ __device__ __forceinline__ void chunk_prologue(DImage &img, const DChan &ch, int
     }
 }
 
-// ---- walker warps ------------------------------------------------------------------------------------------------
-// The tree walk of pixel x+1 depends on pixel x only through `left` (and on x-1 through `leftleft`).  While lane 0 of
-// the decoder warp is busy with the bits of pixel x, up to two walker warps evaluate the MANIAC tree of pixel x+1 for
-// EVERY value pixel x can take (one candidate per lane: cmin + lane, cmin + 32 + lane), and leave the leaf ids in shared
-// memory.  The decoder then needs one table lookup instead of property evaluation + tree walk on its serial chain.
-// Used when the group has predictor 0, a tree of more than one node cached in shared memory and a value range <= 64.
+// ---- run-ahead walker warps ---------------------------------------------------------------------------------------
+// The leaf of pixel x+1 depends on pixel x only through `left` (and on pixel x-1 only through `leftleft`, property 12).
+// Walker warps evaluate the MANIAC tree of upcoming pixels for EVERY value `left` can take (one candidate per lane; a
+// "unit" = one pixel x one block of 32 candidates) and leave the result -- a leaf id, or the inner node at which the walk
+// met a test of property 12 -- in a ring in shared memory.  Nothing a walker needs depends on a pixel of the current row
+// that is still to be decoded, so the walkers run up to K pixels AHEAD of the decoder and the tree walk is a
+// throughput problem spread over many warps instead of a latency on the decoder's serial chain.  The decoder (one lane)
+// then needs one shared-memory lookup per pixel; the rare walks that stopped at property 12 it finishes itself.
+// Used when the group has predictor 0, a value range <= 256 and a tree whose inner nodes fit in shared memory.
+//
+// Compact inner-node array (8 bytes per INNER node, leaves are not stored):
+//   x = splitval << 8 | off      off < 64: word of the shared per-pixel property row, 64 + k: k-th left-dependent value
+//   y = ref(child taken when value > splitval) | ref(other child) << 16,   ref = 0x8000 | leaf id, or inner-node index
+// Handshake words carry a 16-bit tag = (y & 1) << 15 | (x + 1) in their upper half, so a stale entry of the previous
+// row (or of a pixel K / 64 positions back) can never be taken for the one that is awaited.  Walker (r, b) owns candidate
+// block b of the pixels x = r mod g; K is a multiple of g, so a ring slot + block is only ever written by ONE warp, in order.
+constexpr int kCandSlotsMax = 16;   // ring slots: the walkers run up to K <= 16 pixels ahead of the decoder
+constexpr int kMaxCand = 256;       // value ranges up to 256
+constexpr int kMaxWalkers = 12;
+constexpr int kOffLeftLeft = 70;    // `off` of property 12 (slog(left - leftleft)): the only one that needs pixel x-2
+// Everything the decoder's pixel loop needs, handed from lane 0 to ALL lanes through shared memory.  The loop is executed by
+// the 32 lanes redundantly on identical values: its operands then provably come from uniform shared-memory loads, so the
+// compiler emits plain branches for it (no convergence-barrier bookkeeping per decision, which costs more than the
+// arithmetic when a single lane runs under `if (lane == 0)`).  Stores of the redundant lanes hit the same address with
+// the same value.
+struct RowState {
+    int w, y, zero, cmin, mn, mx, emax_pos, emax_neg;
+    unsigned mant_off, tagrow, kslots, inner_s, lines_s, line_shift, cached, mask, tags_s, tab_s, cprop_s;
+    unsigned range, low, ones, pos, n;
+    const uint8_t *p;
+    uint16_t *gleaves;
+    // for the chunk prologues and the row store
+    DImage *img;
+    DChan *ch;
+    int *cprop;
+    int refchan[16], nrefchan, nref;
+};
+
 struct Mail {
     volatile int cmd_seq;       // bumped by the decoder for every command
     int cmd;                    // 1 = row, 2 = exit
-    int y, w, zero, cmin, cmax, nref, nwalk;
-    unsigned nodes_saddr;
-    volatile int go;            // candidates of pixels <= go may be computed
-    volatile int done[8];       // walker k has published the candidates of pixels < done[k]
-    int cval[64];               // decoded values of the current row, ring indexed by x & 63
-    unsigned short cand[2][256];// candidate leaf ids of pixel x in cand[x & 1]
+    int y, w, cmin, nb, g, K;   // nb candidate blocks per pixel, g pixels in flight, K = ring slots (a multiple of g)
+    unsigned inner_saddr, tagrow;
+    volatile int ack[kMaxWalkers];              // last command each walker has read
+    volatile int done[kMaxWalkers];             // last command each walker has finished
+    volatile unsigned cval[64];                 // tag << 16 | decoded value & 0xffff, ring indexed by x & 63
+    volatile unsigned cand[kCandSlotsMax][kMaxCand];    // tag << 16 | result, slot x % K, column left - cmin
+    int dpriv[8];
+    RowState row;
 };
-constexpr int kMailBytes = 1536;
-constexpr int kMaxWalkers = 8;  // value ranges up to 256
+constexpr int kMailBytes = 17408;
+// block configuration: shared address of stream slot 0's mailbox, log2(warps per stream), bytes per stream slot
+__shared__ unsigned s_cfg[4];
+static_assert(sizeof(Mail) <= kMailBytes, "Mail layout");
 
 #define COMPILER_FENCE() asm volatile("" ::: "memory")
 __device__ __forceinline__ int lds32(unsigned addr) {
@@ -517,97 +568,299 @@ __device__ __forceinline__ int lds32(unsigned addr) {
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ unsigned lds32v(unsigned addr) {     // polled words
+    unsigned v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(unsigned addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned lds16(unsigned addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts16(unsigned addr, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ void sts32v(unsigned addr, unsigned v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 constexpr int kLdRowStride = 9;     // words per walker lane: its 7 left-dependent property values (+ padding)
 
 // Shared-memory accesses of one warp are performed in program order and there is no cache between the warps of a block,
-// so the flag protocol below needs compiler barriers only (no MEMBAR per pixel).
-__device__ void walker_main(Mail *mail, const int *cprop2 /* [2][32][kPropStride] */, int *ldrows, int widx, int lane) {
+// so the tag protocol needs compiler barriers only (no MEMBAR per pixel).
+__device__ void walker_main(Mail *mail, const int *cprop2 /* [2][32][kPropStride] */, int *ldrows, int widx, int lane, int sleep_ns) {
     int seen = 0;
     int *myrow = ldrows + (widx * 32 + lane) * kLdRowStride;
     const unsigned ld_s = (unsigned)__cvta_generic_to_shared(myrow) - 64 * 4;      // biased: offsets 64.. address this row
+    const unsigned cval_s = (unsigned)__cvta_generic_to_shared((const void *)mail->cval);
+    const unsigned cand_s = (unsigned)__cvta_generic_to_shared((const void *)mail->cand);
     for (;;) {
         while (mail->cmd_seq == seen) __nanosleep(32);
         seen = mail->cmd_seq;
         __threadfence_block();
         if (mail->cmd == 2) return;
-        const int y = mail->y, w = mail->w, cmin = mail->cmin, cmax = mail->cmax;
-        if (widx >= mail->nwalk) continue;
-        const unsigned nodes_saddr = mail->nodes_saddr;
-        const int cl = cmin + 32 * widx + lane;         // this lane's candidate for `left`
-        const bool valid = cl <= cmax;
-        const int q1 = fooabs(cl), q3 = slog(cl);
-        for (int j = 0; j < w; j++) {
-            while (mail->go < j) { }
+        const int y = mail->y, w = mail->w, cmin = mail->cmin, nb = mail->nb, g = mail->g, K = mail->K;
+        const unsigned inner = mail->inner_saddr, tagrow = mail->tagrow;
+        COMPILER_FENCE();
+        __syncwarp();
+        if (lane == 0) mail->ack[widx] = seen;      // the command's fields may be overwritten from here on
+        const int r = widx / nb, b = widx - r * nb;
+        if (r >= g) { if (lane == 0) mail->done[widx] = seen; continue; }
+        const int cl = cmin + 32 * b + lane;        // this lane's candidate for `left`
+        int slot = r;                               // r < g <= K
+        for (int j = r; j < w; j += g) {
+            if (j >= K) {                            // the ring slot is free once pixel j - K has been decoded
+                const unsigned want = tagrow | (unsigned)(j - K + 1);
+                const unsigned fa = cval_s + (unsigned)((j - K) & 63) * 4u;
+                while ((lds32v(fa) >> 16) != want) __nanosleep(sleep_ns);
+                __threadfence_block();      // acquire: the property rows read below were written before that value was posted
+            }
             COMPILER_FENCE();
             const int *pp = cprop2 + (((j >> 5) & 1) * 32 + (j & 31)) * kPropStride;
             const unsigned pp_s = (unsigned)__cvta_generic_to_shared(pp);
             const int top = pp[32], topright = pp[34];
             const int topleft = (j && y) ? pp[33] : cl;
-            const int leftleft = (j > 1) ? ((volatile int *)mail->cval)[(j - 2) & 63] : cl;
-            myrow[0] = q1; myrow[1] = q3; myrow[2] = cl + top - topleft; myrow[3] = topleft + topright - top;
-            myrow[4] = slog(cl - topleft); myrow[5] = slog(topleft - top); myrow[6] = slog(cl - leftleft);
+            myrow[0] = fooabs(cl); myrow[1] = slog(cl); myrow[2] = cl + top - topleft; myrow[3] = topleft + topright - top;
+            myrow[4] = slog(cl - topleft); myrow[5] = slog(topleft - top); myrow[6] = 0;   // x <= 1: leftleft = left
             COMPILER_FENCE();       // the asm loads below read these
-            const uint4 r0 = lds128(nodes_saddr);
-            uint2 cur = make_uint2(r0.z, r0.w);
-            while ((int)cur.x >= 0) {
-                const uint4 pair = lds128(nodes_saddr + ((cur.x & 0xffffu) << 4));
-                const unsigned off = cur.x >> 16;       // < 64: word of the shared property row, >= 64: word of this lane's row
-                const int v = lds32((off >= 64u ? ld_s : pp_s) + off * 4);
-                cur = (v > (int)cur.y) ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
+            const bool stop12 = j > 1;
+            unsigned ref = 0, result;
+            for (;;) {
+                const uint2 n = lds64(inner + ref * 8u);
+                const unsigned off = n.x & 0xffu;
+                if (stop12 && off == (unsigned)kOffLeftLeft) { result = 0x8000u | ref; break; }
+                const int v = lds32((off >= 64u ? ld_s : pp_s) + off * 4u);
+                const unsigned c = (v > ((int)n.x >> 8)) ? (n.y & 0xffffu) : (n.y >> 16);
+                if (c & 0x8000u) { result = c & 0x7fffu; break; }
+                ref = c;
             }
-            if (valid) ((volatile unsigned short *)mail->cand[j & 1])[cl - cmin] = (unsigned short)(cur.x & 0xffffu);
-            COMPILER_FENCE();
-            __syncwarp();
-            if (lane == 0) mail->done[widx] = j + 1;
+            sts32v(cand_s + (unsigned)(slot * kMaxCand + 32 * b + lane) * 4u, ((tagrow | (unsigned)(j + 1)) << 16) | result);
+            slot += g;
+            if (slot >= K) slot -= K;
         }
+        __syncwarp();
+        if (lane == 0) mail->done[widx] = seen;
     }
 }
 
-// One row with walker warps (PRED0, nodes in shared memory).  Same results as decode_row.
-__device__ __forceinline__ void decode_row_helped(DImage &img, DChan &ch, int y, const int *refchan, int nrefchan, int nref, Rac &rac,
-                                                  const Smem &sm, const LeafStore &ls, Mail *mail, int nwalk, int lane) {
-    const int w = ch.w;
+// ---- lean single-lane coder for the run-ahead path ------------------------------------------------------------------
+// Same arithmetic as Rac / read_int above, written without data-dependent branches inside a binary decision (the
+// renormalisation is predicated), with shared-memory addresses and the leaf's first eight chances held in registers.
+struct FRac {
+    unsigned range, low, ones;
+    const uint8_t *p;
+    unsigned pos, n;            // byte offsets (helped groups require a file < 2 GiB)
+};
+// input(), rac.h:70-81 (the rare part of a decision: about one in ten).  After the first read past the end `low` is all
+// ones for good (rac.h:64-69 ORs a sign-extended EOS into a 64-bit `low`): every later decision reads 1, and `low` is
+// topped up again here before it could ever drop below a threshold (the thresholds between two calls sum to < 2^24).
+__device__ __forceinline__ void fr_input(FRac &r) {
+#pragma unroll 1
+    for (int k = 0; k < 2 && r.range <= 0x10000u; k++) {
+        unsigned c = 0xffu;
+        if (r.pos < r.n) c = __ldg(r.p + r.pos); else r.ones = 1u;
+        r.pos++;
+        r.low = (r.low << 8) | c;
+        r.range <<= 8;
+    }
+    if (r.ones) r.low = 0xffffffffu;
+}
+// one binary decision with chance `ch` (FinalCompoundSymbolBitCoder::read, compound.h:90-95 + RacInput::get, rac.h:82-95);
+// the adapted chance goes back to shared memory at `slot`
+__device__ __forceinline__ unsigned fr_step(FRac &r, unsigned ch, unsigned slot, unsigned tab_s) {
+    const unsigned both = (unsigned)lds32(tab_s + ch * 4u);
+    const unsigned chance = (unsigned)(((unsigned long long)r.range * ch + 0x800ull) >> 12);
+    const unsigned thr = r.range - chance;
+    const bool b = r.low >= thr;
+    r.low = b ? r.low - thr : r.low;
+    r.range = b ? chance : thr;
+    sts16(slot, both >> (b ? 16 : 0));
+    if (r.range <= 0x10000u) fr_input(r);
+    return (unsigned)b;
+}
+struct SymConsts { int mn, mx, emax_pos, emax_neg; unsigned mant_off; };      // mant_off: byte offset of bit_mant[0] in a leaf
+// reader<15>(coder, min, max), symbol.h:154-185.  SIGN_MODE 0: the sign is coded (min < 0 < max), 1: always positive, 2: always negative
+template <int SIGN_MODE>
+__device__ __forceinline__ int fread_int(FRac &r, unsigned leaf_s, unsigned tab_s, const SymConsts &K) {
+    const uint4 L = lds128(leaf_s);             // zero, sign, exp[0..5]
+    if (fr_step(r, L.x & 0xffffu, leaf_s, tab_s)) return 0;
+    unsigned sign;
+    if (SIGN_MODE == 0) sign = fr_step(r, L.x >> 16, leaf_s + 2u, tab_s);
+    else sign = SIGN_MODE == 1 ? 1u : 0u;
+    const int amax = sign ? K.mx : -K.mn;
+    const int emax = sign ? K.emax_pos : K.emax_neg;
+    int e;
+    {
+        const unsigned ew[3] = {L.y, L.z, L.w};
+        e = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            if (k >= emax) goto exp_done;
+            if (fr_step(r, (k & 1) ? (ew[k >> 1] >> 16) : (ew[k >> 1] & 0xffffu), leaf_s + 4u + 2u * k, tab_s)) goto exp_done;
+            e = k + 1;
+        }
+        for (; e < emax; e++)
+            if (fr_step(r, lds16(leaf_s + 4u + 2u * e), leaf_s + 4u + 2u * e, tab_s)) break;
+    }
+exp_done:;
+    int have = 1 << e;
+    const unsigned mb = leaf_s + K.mant_off;
+    for (int pos = e; pos > 0;) {
+        pos--;
+        const int minabs1 = have | (1 << pos);
+        if (minabs1 > amax) continue;
+        if (fr_step(r, lds16(mb + 2u * pos), mb + 2u * pos, tab_s)) have = minabs1;
+    }
+    return sign ? have : -have;
+}
+
+__device__ __forceinline__ uint4 ldg128(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
+__device__ __forceinline__ void sts128(unsigned addr, const uint4 &v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// shared-memory address of a leaf's chances: resident array, or a direct-mapped write-back cache over the global array
+__device__ __forceinline__ unsigned leaf_addr_uniform(const RowState &R, unsigned leaf) {
+    if (!R.cached) return R.lines_s + (leaf << R.line_shift);
+    const unsigned slot = leaf & R.mask;
+    const unsigned ta = R.tags_s + slot * 4u;
+    const int tag = lds32(ta);
+    const unsigned line = R.lines_s + (slot << R.line_shift);
+    if (tag != (int)leaf) {
+        const unsigned n4 = 1u << (R.line_shift - 4);      // 16-byte pieces per leaf
+        if (tag >= 0) {
+            uint4 *old = reinterpret_cast<uint4 *>(R.gleaves + ((size_t)tag << (R.line_shift - 1)));
+            for (unsigned q = 0; q < n4; q++) old[q] = lds128(line + 16u * q);
+        }
+        const uint4 *src = reinterpret_cast<const uint4 *>(R.gleaves + ((size_t)leaf << (R.line_shift - 1)));
+        for (unsigned q = 0; q < n4; q++) sts128(line + 16u * q, ldg128(src + q));
+        sts32v(ta, leaf);
+    }
+    return line;
+}
+
+// the rest of a walk that a walker left at inner node `ref` (a test of property 12), with the real left / leftleft
+__device__ __forceinline__ unsigned finish_walk(unsigned inner, unsigned ref, unsigned pp_s, int left, int leftleft, int x, int y) {
+    const int top = lds32(pp_s + 32 * 4), topright = lds32(pp_s + 34 * 4);
+    const int topleft = (x && y) ? lds32(pp_s + 33 * 4) : left;
+    const int p0 = fooabs(left), p1 = slog(left), p2 = left + top - topleft, p3 = topleft + topright - top;
+    const int p4 = slog(left - topleft), p5 = slog(topleft - top), p6 = slog(left - leftleft);
+    for (;;) {
+        const uint2 n = lds64(inner + ref * 8u);
+        const unsigned off = n.x & 0xffu;
+        int v;
+        if (off < 64u) v = lds32(pp_s + off * 4u);
+        else { const unsigned k = off - 64u; v = k == 0 ? p0 : k == 1 ? p1 : k == 2 ? p2 : k == 3 ? p3 : k == 4 ? p4 : k == 5 ? p5 : p6; }
+        const unsigned c = (v > ((int)n.x >> 8)) ? (n.y & 0xffffu) : (n.y >> 16);
+        if (c & 0x8000u) return c & 0x7fffu;
+        ref = c;
+    }
+}
+
+// The pixel loop of one row, a function of its own with NO arguments: everything comes out of shared memory, found through
+// the block's configuration words, so that the compiler analyses the loop in isolation and sees only uniform operands.
+template <int SIGN_MODE>
+__device__ __noinline__ void row_ahead_loop() {
+    const int lane = threadIdx.x & 31;
+    const unsigned warp = __reduce_max_sync(0xffffffffu, threadIdx.x >> 5);
+    const unsigned mail_s = s_cfg[0] + (warp >> s_cfg[1]) * s_cfg[2];
+    RowState R;
+    {
+        const unsigned rs = mail_s + (unsigned)offsetof(Mail, row);
+        unsigned *dst = reinterpret_cast<unsigned *>(&R);
+#pragma unroll
+        for (int k = 0; k < (int)(sizeof(RowState) / 4); k++) dst[k] = (unsigned)lds32(rs + 4u * k);
+    }
+    const unsigned cval_s = mail_s + (unsigned)offsetof(Mail, cval), cand_s = mail_s + (unsigned)offsetof(Mail, cand);
+    const unsigned tab_s = R.tab_s, cprop_s = R.cprop_s;
+    SymConsts K;
+    K.mn = R.mn; K.mx = R.mx; K.emax_pos = R.emax_pos; K.emax_neg = R.emax_neg; K.mant_off = R.mant_off;
+    FRac fr;
+    fr.range = R.range; fr.low = R.low; fr.ones = R.ones; fr.p = R.p; fr.pos = R.pos; fr.n = R.n;
+    const int w = R.w, zero = R.zero, cmin = R.cmin, y = R.y;
+    DImage &img = *R.img;
+    DChan &ch = *R.ch;
     int16_t *row = ch.data + (size_t)y * w;
-    const int zero = ch.zero, cmin = ch.minval, cmax = ch.maxval;
-    const int mn = cmin - zero, mx = cmax - zero;           // predictor 0: guess = zero
+    int left = zero, leftleft = zero;
+    unsigned slot = 0;
+    for (int x0 = 0; x0 < w; x0 += 32) {
+        if (x0 > 0 && x0 + 32 < w) {      // properties of the chunk after this one (the walks of chunk x0-32 that matter are over)
+            chunk_prologue(img, ch, y, x0 + 32, R.refchan, R.nrefchan, R.nref, R.cprop + (((x0 >> 5) + 1) & 1) * 32 * kPropStride, lane);
+            __syncwarp();
+        }
+        const int cnt = min(32, w - x0);
+        for (int i = 0; i < cnt; i++) {         // all lanes, identical values
+            const int xx = x0 + i;
+            const unsigned want = R.tagrow | (unsigned)(xx + 1);
+            const unsigned ca = cand_s + (slot * kMaxCand + (unsigned)(left - cmin)) * 4u;
+            slot = slot + 1u == R.kslots ? 0u : slot + 1u;
+            unsigned e;
+            do { e = lds32v(ca); } while ((e >> 16) != want);
+            unsigned res = e & 0xffffu;
+            if (res & 0x8000u)
+                res = finish_walk(R.inner_s, res & 0x7fffu, cprop_s + (unsigned)((((xx >> 5) & 1) * 32 + (xx & 31)) * kPropStride) * 4u, left, leftleft, xx, y);
+            const unsigned leaf_s = leaf_addr_uniform(R, res);
+            const int diff = fread_int<SIGN_MODE>(fr, leaf_s, tab_s, K);
+            const int val = s16(s16(diff) + zero);
+            sts32v(cval_s + (unsigned)(xx & 63) * 4u, (want << 16) | ((unsigned)val & 0xffffu));
+            leftleft = xx ? left : val;          // next pixel: x > 1 ? value(x-2) : left   (context_predict.h:132)
+            left = val;
+        }
+        __syncwarp();
+        if (x0 + lane < w) row[x0 + lane] = (int16_t)(lds32v(cval_s + (unsigned)((x0 + lane) & 63) * 4u) & 0xffffu);
+        __syncwarp();
+    }
+    // the coder's state goes back the way it came
+    const unsigned rs = mail_s + (unsigned)offsetof(Mail, row);
+    sts32v(rs + (unsigned)offsetof(RowState, range), fr.range);
+    sts32v(rs + (unsigned)offsetof(RowState, low), fr.low);
+    sts32v(rs + (unsigned)offsetof(RowState, ones), fr.ones);
+    sts32v(rs + (unsigned)offsetof(RowState, pos), fr.pos);
+    __syncwarp();
+}
+
+// One row with run-ahead walkers (predictor 0).  Same results as decode_row.
+__device__ __forceinline__ void decode_row_ahead(int sign_mode, DImage &img, DChan &ch, int y, const int *refchan, int nrefchan, int nref, Rac &rac,
+                                                 const Smem &sm, const LeafStore &ls, unsigned inner_s, int nb, int lane) {
+    Mail *mail = sm.mail;
+    const int w = ch.w;
     chunk_prologue(img, ch, y, 0, refchan, nrefchan, nref, sm.cprop, lane);
     if (w > 32) chunk_prologue(img, ch, y, 32, refchan, nrefchan, nref, sm.cprop + 32 * kPropStride, lane);
+    // every walker has read the previous command
+    if (lane < sm.nwalkers) { const int cur = mail->cmd_seq; while (mail->ack[lane] != cur) { } }
     __syncwarp();
     if (lane == 0) {
-        mail->y = y; mail->w = w; mail->zero = zero; mail->cmin = cmin; mail->cmax = cmax; mail->nref = nref; mail->nwalk = nwalk;
-        mail->go = 0; mail->cmd = 1;
-        for (int k = 0; k < kMaxWalkers; k++) mail->done[k] = 0;
+        const int zero = ch.zero, cmin = ch.minval, cmax = ch.maxval;
+        const int g = max(1, sm.nwalkers / nb), kslots = g * ((8 + g - 1) / g);
+        RowState &S = mail->row;
+        S.w = w; S.y = y; S.zero = zero; S.cmin = cmin;
+        S.mn = cmin - zero; S.mx = cmax - zero;                 // predictor 0: guess = zero
+        S.emax_pos = ilog2u((unsigned)max(S.mx, 0)); S.emax_neg = ilog2u((unsigned)max(-S.mn, 0));
+        S.mant_off = 2u * (unsigned)ls.mant_base;
+        S.tagrow = (unsigned)(y & 1) << 15; S.kslots = (unsigned)kslots; S.inner_s = inner_s;
+        S.lines_s = (unsigned)__cvta_generic_to_shared(ls.lines); S.line_shift = (unsigned)ls.shift + 1u;
+        S.tab_s = (unsigned)__cvta_generic_to_shared(sm.table); S.cprop_s = (unsigned)__cvta_generic_to_shared(sm.cprop);
+        S.cached = ls.tags ? 1u : 0u; S.mask = (unsigned)ls.mask; S.tags_s = ls.tags ? (unsigned)__cvta_generic_to_shared(ls.tags) : 0u;
+        S.range = rac.range; S.low = rac.ones ? 0xffffffffu : rac.low; S.ones = rac.ones ? 1u : 0u;
+        S.pos = (unsigned)rac.io.pos; S.n = (unsigned)rac.io.n; S.p = rac.io.p; S.gleaves = ls.gleaves;
+        S.img = &img; S.ch = &ch; S.cprop = sm.cprop; S.nrefchan = nrefchan; S.nref = nref;
+        for (int k = 0; k < 16; k++) S.refchan[k] = k < nrefchan ? refchan[k] : 0;
+        mail->y = y; mail->w = w; mail->cmin = cmin; mail->nb = nb; mail->g = g; mail->K = kslots;
+        mail->inner_saddr = inner_s; mail->tagrow = S.tagrow; mail->cmd = 1;
         __threadfence_block();
         mail->cmd_seq = mail->cmd_seq + 1;
     }
-    int left = zero;
-    for (int x0 = 0; x0 < w; x0 += 32) {
-        if (x0 > 0 && x0 + 32 < w) {      // properties of the chunk after this one (its buffer is free: nobody reads chunk x0-32 any more)
-            chunk_prologue(img, ch, y, x0 + 32, refchan, nrefchan, nref, sm.cprop + (((x0 >> 5) + 1) & 1) * 32 * kPropStride, lane);
-            __syncwarp();
-        }
-        int outv = 0;
-        const int cnt = min(32, w - x0);
-        for (int i = 0; i < cnt; i++) {
-            const int xx = x0 + i;
-            COMPILER_FENCE();
-            if (lane == 0) mail->go = xx + 1;                                    // candidates of pixel xx+1 may start (val(xx-1) is in cval)
-            const int k = (left - cmin) >> 5;
-            while (mail->done[k] < xx + 1) { }
-            COMPILER_FENCE();
-            const int leaf = ((volatile unsigned short *)mail->cand[xx & 1])[left - cmin];
-            uint16_t *lp = leaf_lookup(ls, leaf, lane);
-            int diff = mn;
-            if (lane == 0) diff = read_int(rac, sm.table, lp, mn, mx, ls.mant_base);
-            diff = __shfl_sync(0xffffffffu, diff, 0);
-            const int val = s16(s16(diff) + zero);
-            if (lane == 0) ((volatile int *)mail->cval)[xx & 63] = val;
-            outv = (lane == i) ? val : outv;
-            left = val;
-        }
-        if (x0 + lane < w) row[x0 + lane] = (int16_t)outv;
-        __syncwarp();
+    __syncwarp();
+    if (sign_mode == 0) row_ahead_loop<0>();
+    else if (sign_mode == 1) row_ahead_loop<1>();
+    else row_ahead_loop<2>();
+    if (lane == 0) {
+        const RowState &S = mail->row;
+        const unsigned ones = *(volatile const unsigned *)&S.ones;
+        rac.range = *(volatile const unsigned *)&S.range; rac.low = *(volatile const unsigned *)&S.low; rac.ones = ones != 0u;
+        rac.io.pos = *(volatile const unsigned *)&S.pos; rac.io.eof = rac.io.eof || (ones != 0u); rac.io.avail = 0; rac.io.win = 0;
     }
+    __syncwarp();
 }
 
 template <bool NODES_SMEM, bool PRED0>
@@ -784,16 +1037,28 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
 
     // FinalPropertySymbolCoder ctor, compound.h:213-225: leaf numbering in node order, all leaves start from zero_chance
     const int nleaves = (nnodes + 1) / 2;
+    int group_range = 0, group_maxw = 0;
+    for (int i = beginc; i <= endc; i++) { group_range = max(group_range, img.ch[i].maxval - img.ch[i].minval + 1); group_maxw = max(group_maxw, img.ch[i].w); }
+    // Run-ahead walkers (see walker_main): predictor 0, value range <= 256 with one walker per block of 32 candidates, the
+    // compact inner-node array in shared memory (+ room for some leaves), 24-bit split values, 15-bit x tags, 32-bit offsets.
+    const int ninner = nnodes / 2;
+    const int inner_bytes = (ninner * 8 + 15) & ~15;
+    bool ahead = sm.mail && predictor == 0 && nnodes > 1 && group_range >= 1 && (group_range + 31) / 32 <= sm.nwalkers && group_range <= kMaxCand &&
+                 inner_bytes + 16384 <= sm.dyn_bytes && group_maxw <= 32766 && img.nbytes < 0x7fff0000ull;
+    if (ahead) {
+        bool wide = false;
+        for (int i = lane; i < nnodes; i += 32) { const int sv = ws.nodes[i].splitval; wide = wide || sv < -(1 << 23) || sv >= (1 << 23); }
+        if (__any_sync(0xffffffffu, wide)) ahead = false;
+    }
     // shared-memory plan for this group: node cache (if it fits), then leaf lines
     int dyn_off = 0;
     uint2 *snodes = nullptr;
     const int node_bytes = ((nnodes + 2) * 8 + 15) & ~15;
-    if (node_bytes + 64 * 8 + 64 <= sm.dyn_bytes) { snodes = reinterpret_cast<uint2 *>(sm.dyn); dyn_off = node_bytes; }
+    if (ahead) dyn_off = inner_bytes;
+    else if (node_bytes + 64 * 8 + 64 <= sm.dyn_bytes) { snodes = reinterpret_cast<uint2 *>(sm.dyn); dyn_off = node_bytes; }
     LeafStore ls;
     ls.gleaves = ws.leaves;
     const int rem = sm.dyn_bytes - dyn_off;
-    int group_range = 0;
-    for (int i = beginc; i <= endc; i++) group_range = max(group_range, img.ch[i].maxval - img.ch[i].minval + 1);
     const bool compact = group_range <= 255;
     ls.shift = compact ? 4 : 5;
     ls.mant_base = compact ? 9 : SC_MANT;
@@ -817,41 +1082,59 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
         for (int i = lane; i < nlines; i += 32) ls.tags[i] = -1;
         for (int i = lane; i < (nleaves << ls.shift); i += 32) ws.leaves[i] = init_entry(i & ((1 << ls.shift) - 1));
     }
-    // node cache: packed entries, see struct LeafStore comment
     uint2 *gpacked = reinterpret_cast<uint2 *>(ws.stack);      // the parse stack is free again: reuse it for the packed nodes
-    if (lane == 0) {
-        int leafID = 0;
-        for (int i = 0; i < nnodes; i++) {
-            const TNode nd = ws.nodes[i];
-            uint2 e;
-            if (nd.property == -1) { e.x = 0xFFFF0000u | (unsigned)leafID++; e.y = 0; }
-            else { e.x = ((unsigned)nd.property << 16) | (unsigned)((nd.child + 1) >> 1); e.y = (unsigned)nd.splitval; }
-            gpacked[i + 1] = e;
-        }
-    }
-    __syncwarp();
     const uint2 *nodes2 = gpacked;
-    // Groups that can use the walker warps keep a walker-friendly copy in shared memory: the property field becomes a word
-    // offset -- < 64: into the shared per-pixel property row, 64 + k: the k-th left-dependent value of the walker's lane.
-    const bool walker_nodes = sm.mail && snodes && predictor == 0 && nnodes > 1;
-    if (snodes) {
-        for (int i = lane; i < nnodes; i += 32) {
-            uint2 e = gpacked[i + 1];
-            if (walker_nodes && (int)e.x >= 0) {
-                const int pidx = (int)(e.x >> 16), role = pidx - nref;
-                int off = pidx;
-                if (role == 1) off = 64; else if (role == 3) off = 65; else if (role == 6) off = 66; else if (role == 7) off = 67;
-                else if (role == 8) off = 68; else if (role == 9) off = 69; else if (role == 12) off = 70;
-                e.x = ((unsigned)off << 16) | (e.x & 0xffffu);
-            }
-            snodes[i + 1] = e;
+    unsigned inner_s = 0;
+    if (ahead) {
+        // compact inner-node array (layout: see walker_main).  idx[i] = 0x8000 | leaf id (node order, compound.h:213-225) or inner index
+        int *idx = ws.stack;
+        int leaf_base = 0, inner_base = 0;
+        for (int i0 = 0; i0 < nnodes; i0 += 32) {
+            const int i = i0 + lane;
+            const bool valid = i < nnodes;
+            const bool isleaf = valid && ws.nodes[i].property == -1;
+            const unsigned lm = __ballot_sync(0xffffffffu, isleaf), vm = __ballot_sync(0xffffffffu, valid);
+            const unsigned im = vm & ~lm, lt = (1u << lane) - 1u;
+            if (valid) idx[i] = isleaf ? (0x8000 | (leaf_base + __popc(lm & lt))) : (inner_base + __popc(im & lt));
+            leaf_base += __popc(lm); inner_base += __popc(im);
         }
-        if (!walker_nodes) nodes2 = snodes;     // the decoder's own walk reads the property index, i.e. the plain encoding
+        __syncwarp();
+        uint2 *sinner = reinterpret_cast<uint2 *>(sm.dyn);
+        for (int i = lane; i < nnodes; i += 32) {
+            const TNode nd = ws.nodes[i];
+            if (nd.property == -1) continue;
+            const int pidx = nd.property, role = pidx - nref;
+            int off = pidx;
+            if (role == 1) off = 64; else if (role == 3) off = 65; else if (role == 6) off = 66; else if (role == 7) off = 67;
+            else if (role == 8) off = 68; else if (role == 9) off = 69; else if (role == 12) off = kOffLeftLeft;
+            uint2 e;
+            e.x = ((unsigned)nd.splitval << 8) | (unsigned)off;
+            e.y = (unsigned)idx[nd.child] | ((unsigned)idx[nd.child + 1] << 16);
+            sinner[idx[i]] = e;
+        }
+        inner_s = (unsigned)__cvta_generic_to_shared(sinner);
+    } else {
+        // node cache: packed entries, see struct LeafStore comment
+        if (lane == 0) {
+            int leafID = 0;
+            for (int i = 0; i < nnodes; i++) {
+                const TNode nd = ws.nodes[i];
+                uint2 e;
+                if (nd.property == -1) { e.x = 0xFFFF0000u | (unsigned)leafID++; e.y = 0; }
+                else { e.x = ((unsigned)nd.property << 16) | (unsigned)((nd.child + 1) >> 1); e.y = (unsigned)nd.splitval; }
+                gpacked[i + 1] = e;
+            }
+        }
+        __syncwarp();
+        if (snodes) {
+            for (int i = lane; i < nnodes; i += 32) snodes[i + 1] = gpacked[i + 1];
+            nodes2 = snodes;
+        }
     }
     __syncwarp();
     if (P.debug && lane == 0)
         printf("[maniac]   tree %d nodes, nprops %d nref %d, zero_chance %d, pos %llu, %dx%d, nodes %s, leaves %s\n", nnodes, nprops, nref, predictability,
-               rac.io.pos, img.ch[beginc].w, img.ch[beginc].h, snodes ? "smem" : "global", ls.tags ? "cached" : "resident");
+               rac.io.pos, img.ch[beginc].w, img.ch[beginc].h, ahead ? "run-ahead walkers" : (snodes ? "smem" : "global"), ls.tags ? "cached" : "resident");
 
     for (int i = beginc; i <= endc; i++) {
         DChan &ch = img.ch[i];
@@ -871,9 +1154,14 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
             __syncwarp();
         } else {
             const int range = ch.maxval - ch.minval + 1;
-            const bool helped = walker_nodes && range <= 32 * sm.nwalkers && range >= 1;
+            const bool helped = ahead;
             const int nwalk = (range + 31) / 32;
-            if (helped && lane == 0) sm.mail->nodes_saddr = (unsigned)__cvta_generic_to_shared(snodes);
+            const int sign_mode = (ch.minval - ch.zero < 0) ? ((ch.maxval - ch.zero > 0) ? 0 : 2) : 1;
+            if (helped) {       // handshake rings start out with tag 0 (never awaited); the walkers are idle here
+                for (int k = lane; k < 64; k += 32) sm.mail->cval[k] = 0;
+                for (int k = lane; k < kCandSlotsMax * kMaxCand; k += 32) (&sm.mail->cand[0][0])[k] = 0;
+                __syncwarp();
+            }
             const long long t_start = clock64();
             for (int y = 0; y < ch.h; y++) {
                 if (STOPPED()) break;
@@ -883,8 +1171,9 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
                     if (ry >= cj.h) ry = cj.h - 1;
                     spin_until_ge(&cj.rows_done, ry + 1);
                 }
-                if (helped) decode_row_helped(img, ch, y, refchan, nrefchan, nref, rac, sm, ls, sm.mail, nwalk, lane);
-                else if (snodes && !walker_nodes) {
+                if (helped) {
+                    decode_row_ahead(sign_mode, img, ch, y, refchan, nrefchan, nref, rac, sm, ls, inner_s, nwalk, lane);
+                } else if (snodes) {
                     if (predictor == 0) decode_row<true, true>(img, ch, y, predictor, refchan, nrefchan, nref, rac, sm, nodes2, ls, lane);
                     else decode_row<true, false>(img, ch, y, predictor, refchan, nrefchan, nref, rac, sm, nodes2, ls, lane);
                 } else {
@@ -893,9 +1182,15 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
                 }
                 publish_rows(ch, y + 1, lane);
             }
-            if (P.debug && lane == 0)
+            if (helped) {       // stragglers (walks of candidate blocks nobody needed) must be over before the tree or the rings change
+                if (lane < sm.nwalkers) { const int cur = sm.mail->cmd_seq; while (sm.mail->done[lane] != cur) { } }
+                __syncwarp();
+            }
+            if (P.debug && lane == 0) {
+                const double ns = (double)ch.w * ch.h;
                 printf("[maniac]   ch %d %dx%d range %d nodes %d helped %d walkers %d: %.0f cycles/symbol\n", i, ch.w, ch.h, range, nnodes, (int)helped, nwalk,
-                       (double)(clock64() - t_start) / ((double)ch.w * ch.h));
+                       (double)(clock64() - t_start) / ns);
+            }
         }
         if (STOPPED()) break;
     }
@@ -906,30 +1201,42 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
 #undef STOPPED
 }
 
-__global__ void k_maniac_decode(Params P) {
+__global__ void __launch_bounds__(512, 1) k_maniac_decode(Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the warp index goes through a warp reduction so that the compiler knows it (and every shared-memory address derived
+    // from it) is uniform across the warp: see RowState
+    const int lane = threadIdx.x & 31, warp = (int)__reduce_max_sync(0xffffffffu, threadIdx.x >> 5);
     const int wps = 1 + P.helpers;                       // warps per stream: decoder + walkers
     const int slot = warp / wps, wrole = warp % wps;
     uint16_t *s_table = reinterpret_cast<uint16_t *>(smem_raw);                      // 16 KiB, shared by the block's warps
     for (int i = threadIdx.x; i < 4096 * 2; i += blockDim.x) s_table[i] = P.table[i];
+    if (threadIdx.x == 0) {
+        s_cfg[0] = (unsigned)__cvta_generic_to_shared(smem_raw) + 16384u + 256u + (P.helpers ? 2u * 4736u : 4736u);
+        s_cfg[1] = P.helpers == 15 ? 4u : (P.helpers == 7 ? 3u : 0u);
+        s_cfg[2] = (unsigned)P.warp_smem;
+    }
     __syncthreads();
     unsigned char *mine = smem_raw + 16384 + (size_t)slot * P.warp_smem;
     Smem sm;
     sm.table = s_table;
     sm.coder = reinterpret_cast<uint16_t(*)[32]>(mine);                               // 192 B
     const int cprop_bytes = P.helpers ? 2 * 4736 : 4736;         // chunk properties, double-buffered when walkers run ahead
-    const int mail_bytes = P.helpers ? kMailBytes + P.helpers * 32 * kLdRowStride * 4 : 0;
+    const int nwalkers = P.helpers - P.helpers / 4;
+    const int mail_bytes = P.helpers ? kMailBytes + nwalkers * 32 * kLdRowStride * 4 : 0;
     sm.cprop = reinterpret_cast<int *>(mine + 256);
     sm.mail = P.helpers ? reinterpret_cast<Mail *>(mine + 256 + cprop_bytes) : nullptr;
     sm.ldrows = P.helpers ? reinterpret_cast<int *>(mine + 256 + cprop_bytes + kMailBytes) : nullptr;
-    sm.nwalkers = P.helpers;
+    sm.nwalkers = min(nwalkers, P.walkers_used);
     sm.dyn = mine + 256 + cprop_bytes + mail_bytes;
     sm.dyn_bytes = P.warp_smem - 256 - cprop_bytes - mail_bytes;
     if (P.helpers) {
-        if (wrole == 0 && lane == 0) { sm.mail->cmd_seq = 0; sm.mail->cmd = 0; sm.mail->go = 0; }
+        if (wrole == 0 && lane == 0) {
+            sm.mail->cmd_seq = 0; sm.mail->cmd = 0;
+            for (int k = 0; k < kMaxWalkers; k++) { sm.mail->ack[k] = 0; sm.mail->done[k] = 0; }
+        }
         __syncthreads();
-        if (wrole > 0) { walker_main(sm.mail, sm.cprop, sm.ldrows, wrole - 1, lane); return; }
+        // warps 4, 8, 12 of a stream stay idle: the decoder warp keeps its scheduler (warp id mod 4) to itself
+        if (wrole > 0) { if (wrole & 3) walker_main(sm.mail, sm.cprop, sm.ldrows, wrole - 1 - (wrole >> 2), lane, P.walker_sleep); return; }
     }
     WarpScratch ws = P.scratch[blockIdx.x * (blockDim.x >> 5) / wps + slot];
     for (;;) {
@@ -1187,7 +1494,9 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         Params P;
         P.images = img_dev; P.streams = streams_dev; P.nstreams = nstreams; P.ticket = st->ticket_dev;
         P.table = st->table_dev; P.meta_table = st->meta_dev; P.scratch = st->scratch_dev; P.maxw = st->maxw;
-        P.debug = getenv("FB_MANIAC_DEBUG") ? 1 : 0;
+        P.walker_sleep = getenv("FB_MANIAC_WSLEEP") ? atoi(getenv("FB_MANIAC_WSLEEP")) : 100;
+        P.walkers_used = getenv("FB_MANIAC_WUSED") ? atoi(getenv("FB_MANIAC_WUSED")) : 64;
+        P.debug = getenv("FB_MANIAC_DEBUG") ? std::max(1, atoi(getenv("FB_MANIAC_DEBUG"))) : 0;
         // Launch shape.  Few streams (one image): one warp per block and block per SM with ~200 KiB of shared memory, so
         // that the whole MANIAC tree and most leaf chances of a stream stay on-chip.  Many streams (batches): up to 8
         // warps share a block's 16 KiB chance table and up to two blocks share an SM.
@@ -1197,9 +1506,9 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         // two streams per SM with 6 walkers each (ranges up to 192; wider ranges fall back to the decoder's own walk).
         const int per_sm = (nstreams + ctx->sm_count - 1) / ctx->sm_count;
         const int wpb = std::max(1, std::min(2, per_sm));          // streams per block
-        P.helpers = getenv("FB_MANIAC_NO_WALKERS") ? 0 : (wpb == 1 ? kMaxWalkers : 6);
+        P.helpers = getenv("FB_MANIAC_NO_WALKERS") ? 0 : (wpb == 1 ? 15 : 7);     // 16 / 8 warps per stream: decoder, 12 / 6 walkers, idle warps
         const int nblocks = std::min((nstreams + wpb - 1) / wpb, ctx->sm_count);
-        const size_t block_smem = 200 * 1024;
+        const size_t block_smem = 226 * 1024;
         const size_t warp_smem = ((block_smem - 16384) / wpb) & ~(size_t)15;
         P.warp_smem = (int)warp_smem;
         const size_t smem_bytes = 16384 + warp_smem * wpb;
