@@ -77,6 +77,7 @@ struct Params {
     int debug;              // FB_MANIAC_DEBUG=1: trace group headers from lane 0
     int walker_sleep;       // ns a walker sleeps between polls of the decoder's progress
     int walkers_used;       // tuning: use at most this many walkers
+    int prefetch;           // walkers prefetch leaf lines
 };
 
 __device__ __forceinline__ int s16(int x) { return (int)(short)x; }
@@ -404,7 +405,7 @@ struct Smem {
     unsigned char *dyn;     // dynamic region: tree-node cache, then leaf chances (resident or direct-mapped cache)
     int dyn_bytes;
     struct Mail *mail;      // mailbox shared with the walker warps (nullptr: no walkers)
-    int walker_sleep;
+    int walker_sleep, prefetch;
     int *ldrows;            // [walkers][32][kLdRowStride] per-lane property values of the walkers
     int nwalkers;
 };
@@ -419,7 +420,8 @@ struct LeafStore {
     int mant_base;          // 16 or 9
     uint16_t *lines;        // shared memory: nlines x (1 << shift) chances
     int *tags;              // direct-mapped tags (nullptr when every leaf is resident)
-    int mask;               // nlines - 1
+    int mask;               // nlines - 1 (power-of-two line count: leaf & mask), or
+    int nlines;             // any line count for the run-ahead path (leaf % nlines); 0 = use mask
     uint16_t *gleaves;      // global backing store
 };
 
@@ -523,7 +525,7 @@ __device__ __forceinline__ void chunk_prologue(DImage &img, const DChan &ch, int
 // Handshake words carry a 16-bit tag = (y & 1) << 15 | (x + 1) in their upper half, so a stale entry of the previous
 // row (or of a pixel K / 64 positions back) can never be taken for the one that is awaited.  Walker (r, b) owns candidate
 // block b of the pixels x = r mod g; K is a multiple of g, so a ring slot + block is only ever written by ONE warp, in order.
-constexpr int kCandSlotsMax = 16;   // ring slots: the walkers run up to K <= 16 pixels ahead of the decoder
+constexpr int kCandSlotsMax = 9;    // ring slots: the walkers run up to K <= 9 pixels ahead of the decoder
 constexpr int kMaxCand = 256;       // value ranges up to 256
 constexpr int kMaxWalkers = 12;
 constexpr int kOffLeftLeft = 70;    // `off` of property 12 (slog(left - leftleft)): the only one that needs pixel x-2
@@ -534,7 +536,7 @@ constexpr int kOffLeftLeft = 70;    // `off` of property 12 (slog(left - leftlef
 // the same value.
 struct RowState {
     int w, y, zero, cmin, mn, mx, emax_pos, emax_neg;
-    unsigned mant_off, tagrow, kslots, inner_s, lines_s, line_shift, cached, mask, tags_s, tab_s, cprop_s;
+    unsigned mant_off, tagrow, kslots, inner_s, lines_s, line_shift, cached, mask, nlines, inv_nlines, tags_s, tab_s, cprop_s;
     unsigned range, low, ones, pos, n;
     const uint8_t *p;
     uint16_t *gleaves;
@@ -550,14 +552,19 @@ struct Mail {
     int cmd;                    // 1 = row, 2 = exit
     int y, w, cmin, nb, g, K;   // nb candidate blocks per pixel, g pixels in flight, K = ring slots (a multiple of g)
     unsigned inner_saddr, tagrow;
+    const uint16_t *pf_leaves;  // non-null: leaf chances live in global memory behind a cache: walkers prefetch the lines they find
+    int pf_shift;
     volatile int ack[kMaxWalkers];              // last command each walker has read
     volatile int done[kMaxWalkers];             // last command each walker has finished
     volatile unsigned cval[64];                 // tag << 16 | decoded value & 0xffff, ring indexed by x & 63
-    volatile unsigned cand[kCandSlotsMax][kMaxCand];    // tag << 16 | result, slot x % K, column left - cmin
+    // slot x % K, column left - cmin:  x = tag << 16 | T & 0xffff,  y = kind << 30 | B << 15 | A
+    //   kind 0: leaf A;  kind 1: the walk forked at a test of property 12: leaf A if leftleft <= T, else leaf B;
+    //   kind 2: the walk met a second test of property 12: the decoder finishes it from inner node A
+    volatile uint2 cand[kCandSlotsMax][kMaxCand];
     int dpriv[8];
     RowState row;
 };
-constexpr int kMailBytes = 17408;
+constexpr int kMailBytes = 19968;
 // block configuration: shared address of stream slot 0's mailbox, log2(warps per stream), bytes per stream slot
 __shared__ unsigned s_cfg[4];
 static_assert(sizeof(Mail) <= kMailBytes, "Mail layout");
@@ -585,6 +592,12 @@ __device__ __forceinline__ unsigned lds16(unsigned addr) {
 }
 __device__ __forceinline__ void sts16(unsigned addr, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory"); }
 __device__ __forceinline__ void sts32v(unsigned addr, unsigned v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint2 lds64v(unsigned addr) {
+    uint2 v;
+    asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64v(unsigned addr, unsigned x, unsigned y) { asm volatile("st.volatile.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(x), "r"(y) : "memory"); }
 constexpr int kLdRowStride = 9;     // words per walker lane: its 7 left-dependent property values (+ padding)
 
 // Shared-memory accesses of one warp are performed in program order and there is no cache between the warps of a block,
@@ -602,6 +615,8 @@ __device__ void walker_main(Mail *mail, const int *cprop2 /* [2][32][kPropStride
         if (mail->cmd == 2) return;
         const int y = mail->y, w = mail->w, cmin = mail->cmin, nb = mail->nb, g = mail->g, K = mail->K;
         const unsigned inner = mail->inner_saddr, tagrow = mail->tagrow;
+        const uint16_t *pf_leaves = mail->pf_leaves;
+        const int pf_shift = mail->pf_shift;
         COMPILER_FENCE();
         __syncwarp();
         if (lane == 0) mail->ack[widx] = seen;      // the command's fields may be overwritten from here on
@@ -624,18 +639,45 @@ __device__ void walker_main(Mail *mail, const int *cprop2 /* [2][32][kPropStride
             myrow[0] = fooabs(cl); myrow[1] = slog(cl); myrow[2] = cl + top - topleft; myrow[3] = topleft + topright - top;
             myrow[4] = slog(cl - topleft); myrow[5] = slog(topleft - top); myrow[6] = 0;   // x <= 1: leftleft = left
             COMPILER_FENCE();       // the asm loads below read these
+            // Property 12 = slog(left - leftleft) needs pixel j-2, which is not decoded yet.  slog is monotone, so a test
+            // "slog(cl - leftleft) > s" is "leftleft <= T" for a threshold T this lane can compute: the walk FORKS there, follows
+            // both children to their leaves and leaves (A, B, T) for the decoder.  A second such test on either path is rare;
+            // then the decoder finishes the walk itself from the first one.
             const bool stop12 = j > 1;
-            unsigned ref = 0, result;
+            unsigned ref = 0, phase = 0, leafA = 0, pendB = 0, forkref = 0, ry;
+            int T = 0;
             for (;;) {
                 const uint2 n = lds64(inner + ref * 8u);
                 const unsigned off = n.x & 0xffu;
-                if (stop12 && off == (unsigned)kOffLeftLeft) { result = 0x8000u | ref; break; }
-                const int v = lds32((off >= 64u ? ld_s : pp_s) + off * 4u);
-                const unsigned c = (v > ((int)n.x >> 8)) ? (n.y & 0xffffu) : (n.y >> 16);
-                if (c & 0x8000u) { result = c & 0x7fffu; break; }
+                unsigned c;
+                if (stop12 && off == (unsigned)kOffLeftLeft) {
+                    if (phase != 0u) { ry = (2u << 30) | forkref; break; }
+                    const int sv = (int)n.x >> 8;
+                    int dmin;       // slog(d) > sv  <=>  d >= dmin   (|d| <= 255 here)
+                    if (sv >= 0) dmin = sv >= 9 ? 512 : (1 << sv);
+                    else { const int t = -(sv + 1); dmin = t >= 9 ? -511 : -((1 << t) - 1); }
+                    T = cl - dmin;
+                    forkref = ref; phase = 1u; pendB = n.y >> 16;
+                    c = n.y & 0xffffu;
+                } else {
+                    const int v = lds32((off >= 64u ? ld_s : pp_s) + off * 4u);
+                    c = (v > ((int)n.x >> 8)) ? (n.y & 0xffffu) : (n.y >> 16);
+                }
+                if (c & 0x8000u) {
+                    if (phase == 0u) { ry = c & 0x7fffu; break; }
+                    if (phase == 1u) {
+                        leafA = c & 0x7fffu; phase = 2u; c = pendB;
+                        if (c & 0x8000u) { ry = (1u << 30) | ((c & 0x7fffu) << 15) | leafA; break; }
+                    } else { ry = (1u << 30) | ((c & 0x7fffu) << 15) | leafA; break; }
+                }
                 ref = c;
             }
-            sts32v(cand_s + (unsigned)(slot * kMaxCand + 32 * b + lane) * 4u, ((tagrow | (unsigned)(j + 1)) << 16) | result);
+            sts64v(cand_s + (unsigned)(slot * kMaxCand + 32 * b + lane) * 8u, ((tagrow | (unsigned)(j + 1)) << 16) | ((unsigned)T & 0xffffu), ry);
+            if (pf_leaves && (ry >> 30) < 2u) {     // pull the chances of the leaves this candidate leads to into L1 (a load whose
+                unsigned dummy;                       // result nobody waits for), ahead of the decoder's cache miss
+                asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(dummy) : "l"(pf_leaves + ((size_t)(ry & 0x7fffu) << pf_shift)));
+                if (ry >> 30) asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(dummy) : "l"(pf_leaves + ((size_t)((ry >> 15) & 0x7fffu) << pf_shift)));
+            }
             slot += g;
             if (slot >= K) slot -= K;
         }
@@ -722,7 +764,7 @@ __device__ __forceinline__ void sts128(unsigned addr, const uint4 &v) {
 // shared-memory address of a leaf's chances: resident array, or a direct-mapped write-back cache over the global array
 __device__ __forceinline__ unsigned leaf_addr_uniform(const RowState &R, unsigned leaf) {
     if (!R.cached) return R.lines_s + (leaf << R.line_shift);
-    const unsigned slot = leaf & R.mask;
+    const unsigned slot = R.nlines ? leaf - __umulhi(leaf, R.inv_nlines) * R.nlines : (leaf & R.mask);
     const unsigned ta = R.tags_s + slot * 4u;
     const int tag = lds32(ta);
     const unsigned line = R.lines_s + (slot << R.line_shift);
@@ -792,13 +834,15 @@ __device__ __noinline__ void row_ahead_loop() {
         for (int i = 0; i < cnt; i++) {         // all lanes, identical values
             const int xx = x0 + i;
             const unsigned want = R.tagrow | (unsigned)(xx + 1);
-            const unsigned ca = cand_s + (slot * kMaxCand + (unsigned)(left - cmin)) * 4u;
+            const unsigned ca = cand_s + (slot * kMaxCand + (unsigned)(left - cmin)) * 8u;
             slot = slot + 1u == R.kslots ? 0u : slot + 1u;
-            unsigned e;
-            do { e = lds32v(ca); } while ((e >> 16) != want);
-            unsigned res = e & 0xffffu;
-            if (res & 0x8000u)
-                res = finish_walk(R.inner_s, res & 0x7fffu, cprop_s + (unsigned)((((xx >> 5) & 1) * 32 + (xx & 31)) * kPropStride) * 4u, left, leftleft, xx, y);
+            uint2 e;
+            do { e = lds64v(ca); } while ((e.x >> 16) != want);
+            unsigned res = e.y & 0x7fffu;
+            const unsigned kind = e.y >> 30;
+            if (kind == 1u) res = leftleft <= (int)(short)(e.x & 0xffffu) ? res : ((e.y >> 15) & 0x7fffu);
+            else if (kind == 2u)
+                res = finish_walk(R.inner_s, res, cprop_s + (unsigned)((((xx >> 5) & 1) * 32 + (xx & 31)) * kPropStride) * 4u, left, leftleft, xx, y);
             const unsigned leaf_s = leaf_addr_uniform(R, res);
             const int diff = fread_int<SIGN_MODE>(fr, leaf_s, tab_s, K);
             const int val = s16(s16(diff) + zero);
@@ -831,7 +875,7 @@ __device__ __forceinline__ void decode_row_ahead(int sign_mode, DImage &img, DCh
     __syncwarp();
     if (lane == 0) {
         const int zero = ch.zero, cmin = ch.minval, cmax = ch.maxval;
-        const int g = max(1, sm.nwalkers / nb), kslots = g * ((8 + g - 1) / g);
+        const int g = max(1, min(8, sm.nwalkers / nb)), kslots = g >= 5 ? g : g * ((8 + g - 1) / g);
         RowState &S = mail->row;
         S.w = w; S.y = y; S.zero = zero; S.cmin = cmin;
         S.mn = cmin - zero; S.mx = cmax - zero;                 // predictor 0: guess = zero
@@ -840,13 +884,14 @@ __device__ __forceinline__ void decode_row_ahead(int sign_mode, DImage &img, DCh
         S.tagrow = (unsigned)(y & 1) << 15; S.kslots = (unsigned)kslots; S.inner_s = inner_s;
         S.lines_s = (unsigned)__cvta_generic_to_shared(ls.lines); S.line_shift = (unsigned)ls.shift + 1u;
         S.tab_s = (unsigned)__cvta_generic_to_shared(sm.table); S.cprop_s = (unsigned)__cvta_generic_to_shared(sm.cprop);
-        S.cached = ls.tags ? 1u : 0u; S.mask = (unsigned)ls.mask; S.tags_s = ls.tags ? (unsigned)__cvta_generic_to_shared(ls.tags) : 0u;
+        S.cached = ls.tags ? 1u : 0u; S.mask = (unsigned)ls.mask; S.nlines = (unsigned)ls.nlines; S.inv_nlines = ls.nlines ? 0xffffffffu / (unsigned)ls.nlines + 1u : 0u; S.tags_s = ls.tags ? (unsigned)__cvta_generic_to_shared(ls.tags) : 0u;
         S.range = rac.range; S.low = rac.ones ? 0xffffffffu : rac.low; S.ones = rac.ones ? 1u : 0u;
         S.pos = (unsigned)rac.io.pos; S.n = (unsigned)rac.io.n; S.p = rac.io.p; S.gleaves = ls.gleaves;
         S.img = &img; S.ch = &ch; S.cprop = sm.cprop; S.nrefchan = nrefchan; S.nref = nref;
         for (int k = 0; k < 16; k++) S.refchan[k] = k < nrefchan ? refchan[k] : 0;
         mail->y = y; mail->w = w; mail->cmin = cmin; mail->nb = nb; mail->g = g; mail->K = kslots;
         mail->inner_saddr = inner_s; mail->tagrow = S.tagrow; mail->cmd = 1;
+        mail->pf_leaves = (ls.tags && sm.prefetch) ? ls.gleaves : nullptr; mail->pf_shift = ls.shift;
         __threadfence_block();
         mail->cmd_seq = mail->cmd_seq + 1;
     }
@@ -1037,14 +1082,17 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
 
     // FinalPropertySymbolCoder ctor, compound.h:213-225: leaf numbering in node order, all leaves start from zero_chance
     const int nleaves = (nnodes + 1) / 2;
-    int group_range = 0, group_maxw = 0;
-    for (int i = beginc; i <= endc; i++) { group_range = max(group_range, img.ch[i].maxval - img.ch[i].minval + 1); group_maxw = max(group_maxw, img.ch[i].w); }
+    int group_range = 0, group_maxw = 0, group_lo = 0, group_hi = 0;
+    for (int i = beginc; i <= endc; i++) {
+        group_range = max(group_range, img.ch[i].maxval - img.ch[i].minval + 1); group_maxw = max(group_maxw, img.ch[i].w);
+        group_lo = min(group_lo, img.ch[i].minval); group_hi = max(group_hi, img.ch[i].maxval);
+    }
     // Run-ahead walkers (see walker_main): predictor 0, value range <= 256 with one walker per block of 32 candidates, the
     // compact inner-node array in shared memory (+ room for some leaves), 24-bit split values, 15-bit x tags, 32-bit offsets.
     const int ninner = nnodes / 2;
     const int inner_bytes = (ninner * 8 + 15) & ~15;
     bool ahead = sm.mail && predictor == 0 && nnodes > 1 && group_range >= 1 && (group_range + 31) / 32 <= sm.nwalkers && group_range <= kMaxCand &&
-                 inner_bytes + 16384 <= sm.dyn_bytes && group_maxw <= 32766 && img.nbytes < 0x7fff0000ull;
+                 inner_bytes + 16384 <= sm.dyn_bytes && group_maxw <= 32766 && img.nbytes < 0x7fff0000ull && group_lo >= -32000 && group_hi <= 32000;
     if (ahead) {
         bool wide = false;
         for (int i = lane; i < nnodes; i += 32) { const int sv = ws.nodes[i].splitval; wide = wide || sv < -(1 << 23) || sv >= (1 << 23); }
@@ -1071,11 +1119,13 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
         return 1024;
     };
     if (nleaves * lbytes <= rem) {              // every leaf resident
-        ls.lines = reinterpret_cast<uint16_t *>(sm.dyn + dyn_off); ls.tags = nullptr; ls.mask = 0;
+        ls.lines = reinterpret_cast<uint16_t *>(sm.dyn + dyn_off); ls.tags = nullptr; ls.mask = 0; ls.nlines = 0;
         for (int i = lane; i < (nleaves << ls.shift); i += 32) ls.lines[i] = init_entry(i & ((1 << ls.shift) - 1));
     } else {                                    // direct-mapped cache over the global leaf array
         int nlines = 1;
         while (nlines * 2 * (lbytes + 4) <= rem) nlines *= 2;
+        ls.nlines = 0;
+        if (ahead) { nlines = (rem - 16) / (lbytes + 4); ls.nlines = nlines; }     // leaf % nlines: no power-of-two rounding
         ls.tags = reinterpret_cast<int *>(sm.dyn + dyn_off);
         ls.lines = reinterpret_cast<uint16_t *>(sm.dyn + dyn_off + ((nlines * 4 + 15) & ~15));
         ls.mask = nlines - 1;
@@ -1159,7 +1209,7 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
             const int sign_mode = (ch.minval - ch.zero < 0) ? ((ch.maxval - ch.zero > 0) ? 0 : 2) : 1;
             if (helped) {       // handshake rings start out with tag 0 (never awaited); the walkers are idle here
                 for (int k = lane; k < 64; k += 32) sm.mail->cval[k] = 0;
-                for (int k = lane; k < kCandSlotsMax * kMaxCand; k += 32) (&sm.mail->cand[0][0])[k] = 0;
+                for (int k = lane; k < kCandSlotsMax * kMaxCand; k += 32) { (&sm.mail->cand[0][0])[k].x = 0; (&sm.mail->cand[0][0])[k].y = 0; }
                 __syncwarp();
             }
             const long long t_start = clock64();
@@ -1227,6 +1277,7 @@ __global__ void __launch_bounds__(512, 1) k_maniac_decode(Params P) {
     sm.mail = P.helpers ? reinterpret_cast<Mail *>(mine + 256 + cprop_bytes) : nullptr;
     sm.ldrows = P.helpers ? reinterpret_cast<int *>(mine + 256 + cprop_bytes + kMailBytes) : nullptr;
     sm.nwalkers = min(nwalkers, P.walkers_used);
+    sm.prefetch = P.prefetch;
     sm.dyn = mine + 256 + cprop_bytes + mail_bytes;
     sm.dyn_bytes = P.warp_smem - 256 - cprop_bytes - mail_bytes;
     if (P.helpers) {
@@ -1496,6 +1547,7 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         P.table = st->table_dev; P.meta_table = st->meta_dev; P.scratch = st->scratch_dev; P.maxw = st->maxw;
         P.walker_sleep = getenv("FB_MANIAC_WSLEEP") ? atoi(getenv("FB_MANIAC_WSLEEP")) : 100;
         P.walkers_used = getenv("FB_MANIAC_WUSED") ? atoi(getenv("FB_MANIAC_WUSED")) : 64;
+        P.prefetch = getenv("FB_MANIAC_NO_PREFETCH") ? 0 : 1;
         P.debug = getenv("FB_MANIAC_DEBUG") ? std::max(1, atoi(getenv("FB_MANIAC_DEBUG"))) : 0;
         // Launch shape.  Few streams (one image): one warp per block and block per SM with ~200 KiB of shared memory, so
         // that the whole MANIAC tree and most leaf chances of a stream stay on-chip.  Many streams (batches): up to 8
