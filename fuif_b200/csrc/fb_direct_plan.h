@@ -3,6 +3,7 @@
 // into jobs, segment lengths and block shapes.  Pure C++ so that the CPU-only test tier drives the same code.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -100,6 +101,8 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
         int S = 32;
         if (groups_total / 32 < (long long)sm_count * 128) S = 16;
         if (groups_total / 16 < (long long)sm_count * 128) S = 8;
+        static const int env_s = getenv("FB_DQ_VS") ? atoi(getenv("FB_DQ_VS")) : 0, env_t = getenv("FB_DQ_VT") ? atoi(getenv("FB_DQ_VT")) : 128;
+        if (env_s > 0) S = env_s;
         for (int i = 0; i < n && P.vj.n < 4; i++) {
             const StepOp &a = ops[i];
             if (!v_eligible(a)) continue;
@@ -107,7 +110,7 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
             int s = S;
             while ((a.ha + s - 1) / s > 256) s += 8;
             J.avg = a.avg; J.res = a.res; J.out = a.out; J.w = a.wa; J.ha = a.ha; J.S = s; J.nseg = (a.ha + s - 1) / s;
-            int cb = 128 / J.nseg;
+            int cb = env_t / J.nseg;
             if (cb < 2) cb = 2;
             if (cb > 8) cb = 8;
             while (cb > 1 && cb * J.nseg > 512) cb--;

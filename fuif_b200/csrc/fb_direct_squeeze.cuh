@@ -213,37 +213,60 @@ FB_KERNEL(512) k_inv_hsq_direct(const FB_GRID_CONSTANT HJobs jobs) {
 // ---------------------------------------------------------------------------------------------------------
 
 // Pairs [q_from, q1) of 8 adjacent columns, from state prev[8]; rows of pairs >= q_store are written.
-FB_DEV void v_run(const VJob &J, int x, int q_from, int q_store, int q1, bool chain_start, int *prev, int *bw) {
-    const int w = J.w;
-    uint4 cur = ld16(J.avg + (size_t)q_from * w + x);
-    if (chain_start) {
-        prev[0] = lo16(cur.x); prev[1] = hi16(cur.x); prev[2] = lo16(cur.y); prev[3] = hi16(cur.y);
-        prev[4] = lo16(cur.z); prev[5] = hi16(cur.z); prev[6] = lo16(cur.w); prev[7] = hi16(cur.w);
+// The input rows of the next kVDepth pairs are requested while the current kVDepth pairs are computed (the loads do not
+// depend on the chain), so a thread keeps 2 * kVDepth 16-byte loads in flight.
+constexpr int kVDepth = 4;
+FB_DEV void v_pair8(const VJob &J, int x, int q, bool store, const uint4 &cur, const uint4 &nxt, const uint4 &rs, int *prev) {
+    const uint32_t aw[4] = {cur.x, cur.y, cur.z, cur.w}, nw[4] = {nxt.x, nxt.y, nxt.z, nxt.w}, rw[4] = {rs.x, rs.y, rs.z, rs.w};
+    uint32_t oa[4], ob[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int A0, B0, A1, B1;
+        fq::unsqueeze_pair(prev[2 * k], lo16(aw[k]), lo16(nw[k]), lo16(rw[k]), A0, B0);
+        fq::unsqueeze_pair(prev[2 * k + 1], hi16(aw[k]), hi16(nw[k]), hi16(rw[k]), A1, B1);
+        prev[2 * k] = B0; prev[2 * k + 1] = B1;
+        oa[k] = pack16(A0, A1); ob[k] = pack16(B0, B1);
+        if (J.do_clamp) { oa[k] = clamp_word(oa[k], J.lo, J.hi); ob[k] = clamp_word(ob[k], J.lo, J.hi); }
     }
-    for (int q = q_from; q < q1; q++) {
-        const uint4 nxt = (q + 1 < J.ha) ? ld16(J.avg + (size_t)(q + 1) * w + x) : cur;     // last pair: own average (squeeze.h:201)
-        const uint4 rs = J.res ? ld16(J.res + (size_t)q * w + x) : zero4();
-        if (q == q_store) {
+    if (store) {
+        uint4 v;
+        v.x = oa[0]; v.y = oa[1]; v.z = oa[2]; v.w = oa[3]; st16(J.out + (size_t)(2 * q) * J.w + x, v);
+        v.x = ob[0]; v.y = ob[1]; v.z = ob[2]; v.w = ob[3]; st16(J.out + (size_t)(2 * q + 1) * J.w + x, v);
+    }
+}
+FB_DEV void v_run(const VJob &J, int x, int q_from, int q_store, int q1, bool chain_start, int *prev, int *bw) {
+    const int w = J.w, last = J.ha - 1;
+    uint4 A[kVDepth + 1], R[kVDepth];
 #pragma unroll
-            for (int i = 0; i < 8; i++) bw[i] = prev[i];
-        }
-        const uint32_t aw[4] = {cur.x, cur.y, cur.z, cur.w}, nw[4] = {nxt.x, nxt.y, nxt.z, nxt.w}, rw[4] = {rs.x, rs.y, rs.z, rs.w};
-        uint32_t oa[4], ob[4];
+    for (int i = 0; i <= kVDepth; i++) A[i] = ld16(J.avg + (size_t)imin(q_from + i, last) * w + x);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int A0, B0, A1, B1;
-            fq::unsqueeze_pair(prev[2 * k], lo16(aw[k]), lo16(nw[k]), lo16(rw[k]), A0, B0);
-            fq::unsqueeze_pair(prev[2 * k + 1], hi16(aw[k]), hi16(nw[k]), hi16(rw[k]), A1, B1);
-            prev[2 * k] = B0; prev[2 * k + 1] = B1;
-            oa[k] = pack16(A0, A1); ob[k] = pack16(B0, B1);
-            if (J.do_clamp) { oa[k] = clamp_word(oa[k], J.lo, J.hi); ob[k] = clamp_word(ob[k], J.lo, J.hi); }
+    for (int i = 0; i < kVDepth; i++) R[i] = J.res ? ld16(J.res + (size_t)imin(q_from + i, last) * w + x) : zero4();
+    if (chain_start) {
+        prev[0] = lo16(A[0].x); prev[1] = hi16(A[0].x); prev[2] = lo16(A[0].y); prev[3] = hi16(A[0].y);
+        prev[4] = lo16(A[0].z); prev[5] = hi16(A[0].z); prev[6] = lo16(A[0].w); prev[7] = hi16(A[0].w);
+    }
+    for (int q0 = q_from; q0 < q1; q0 += kVDepth) {
+        uint4 An[kVDepth], Rn[kVDepth];
+#pragma unroll
+        for (int i = 0; i < kVDepth; i++) {     // rows of the next round (addresses clamped into the plane: unused rows are harmless)
+            An[i] = ld16(J.avg + (size_t)imin(q0 + kVDepth + 1 + i, last) * w + x);
+            Rn[i] = J.res ? ld16(J.res + (size_t)imin(q0 + kVDepth + i, last) * w + x) : zero4();
         }
-        if (q >= q_store) {
-            uint4 v;
-            v.x = oa[0]; v.y = oa[1]; v.z = oa[2]; v.w = oa[3]; st16(J.out + (size_t)(2 * q) * w + x, v);
-            v.x = ob[0]; v.y = ob[1]; v.z = ob[2]; v.w = ob[3]; st16(J.out + (size_t)(2 * q + 1) * w + x, v);
+#pragma unroll
+        for (int i = 0; i < kVDepth; i++) {
+            const int q = q0 + i;
+            if (q < q1) {
+                if (q == q_store) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) bw[k] = prev[k];
+                }
+                // last pair of the column: next average = own (squeeze.h:201); A[i+1] then holds a clamped re-read of row ha-1 = A[i]
+                v_pair8(J, x, q, q >= q_store, A[i], A[i + 1], R[i], prev);
+            }
         }
-        cur = nxt;
+        A[0] = A[kVDepth];
+#pragma unroll
+        for (int i = 0; i < kVDepth; i++) { A[i + 1] = An[i]; R[i] = Rn[i]; }
     }
 }
 

@@ -894,13 +894,16 @@ static int run_inv_squeeze_plan_per_level(fb_ctx *ctx, const std::vector<FbSqOp>
     std::vector<char> is_final(n, 1), clamp_op(n, 0);
     for (int k = 0; k < n; k++)
         for (int q = k + 1; q < n; q++) if (ops[q].avg == ops[k].out) is_final[k] = 0;
+    // Measured on B200 (profiles/): the direct kernel wins every horizontal step, the tiled kernel (lanes = adjacent
+    // columns, warps = segments) every vertical one; FB_SQUEEZE_DIRECT_V=1 sends vertical steps to the direct kernel too.
+    static const bool direct_v = getenv("FB_SQUEEZE_DIRECT_V") != nullptr;
     bool ep_ok = use_direct && ep && ep->kind != 0;
     int ico = -1, icg = -1;
     if (ep_ok) {
         const int last_step = ops[n - 1].step;
         for (int k = 0; k < n && ep_ok; k++) {
             if (!is_final[k]) continue;
-            const bool elig = !fused[k] && (ops[k].horizontal ? dq::h_eligible(as_step_op(ops[k])) : dq::v_eligible(as_step_op(ops[k])));
+            const bool elig = !fused[k] && (ops[k].horizontal ? dq::h_eligible(as_step_op(ops[k])) : (direct_v && dq::v_eligible(as_step_op(ops[k]))));
             if (ep->kind == 2 && ops[k].out == ep->ycc[0]) { if (ops[k].step == last_step) ep_ok = false; continue; }   // Y: consumed by the epilogue, never clamped
             if (ep->kind == 2 && (ops[k].out == ep->ycc[1] || ops[k].out == ep->ycc[2])) {
                 if (!elig || !ops[k].horizontal || ops[k].step != last_step) ep_ok = false;
@@ -929,7 +932,7 @@ static int run_inv_squeeze_plan_per_level(fb_ctx *ctx, const std::vector<FbSqOp>
         int q = k;
         while (q < n && ops[q].step == step) { if (!fused[q]) idx.push_back(q); q++; }
         std::vector<int> rest = idx;
-        if (use_direct) {
+        if (use_direct && (horizontal || direct_v)) {
             std::vector<dq::StepOp> sops;
             for (int i : idx) { dq::StepOp so = as_step_op(ops[i]); so.clamp = clamp_op[i]; sops.push_back(so); }
             dq::StepEpilogue E;
