@@ -51,9 +51,12 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
     if (horizontal) {
         long long pairs_total = 0;
         for (auto &o : ops) pairs_total += (long long)o.wa * o.ha;
-        int S = 32;
-        if (pairs_total / 32 < (long long)sm_count * 1024) S = 16;
+        // 16 pairs per segment (+ 8 warm-up pairs): measured best on B200 at every level size (8, 24, 32, 64, 128 tried);
+        // more, shorter segments beat less warm-up work because the kernel lives on the number of chains in flight
+        int S = 16;
         if (pairs_total / 16 < (long long)sm_count * 256) S = 8;
+        static const int env_hs = getenv("FB_DQ_HS") ? atoi(getenv("FB_DQ_HS")) : 0;
+        if (env_hs > 0 && S == 16) S = env_hs;
         // the YCoCg pair first
         int ico = -1, icg = -1;
         if (ep.enabled)

@@ -769,13 +769,17 @@ __device__ __forceinline__ unsigned leaf_addr_uniform(const RowState &R, unsigne
     const int tag = lds32(ta);
     const unsigned line = R.lines_s + (slot << R.line_shift);
     if (tag != (int)leaf) {
-        const unsigned n4 = 1u << (R.line_shift - 4);      // 16-byte pieces per leaf
+        // write the evicted leaf back and fetch the new one: 32 bytes (compact leaves) or 64
+        const bool big = R.line_shift == 6u;
         if (tag >= 0) {
             uint4 *old = reinterpret_cast<uint4 *>(R.gleaves + ((size_t)tag << (R.line_shift - 1)));
-            for (unsigned q = 0; q < n4; q++) old[q] = lds128(line + 16u * q);
+            old[0] = lds128(line); old[1] = lds128(line + 16u);
+            if (big) { old[2] = lds128(line + 32u); old[3] = lds128(line + 48u); }
         }
         const uint4 *src = reinterpret_cast<const uint4 *>(R.gleaves + ((size_t)leaf << (R.line_shift - 1)));
-        for (unsigned q = 0; q < n4; q++) sts128(line + 16u * q, ldg128(src + q));
+        const uint4 v0 = ldg128(src), v1 = ldg128(src + 1);
+        sts128(line, v0); sts128(line + 16u, v1);
+        if (big) { const uint4 v2 = ldg128(src + 2), v3 = ldg128(src + 3); sts128(line + 32u, v2); sts128(line + 48u, v3); }
         sts32v(ta, leaf);
     }
     return line;
@@ -1257,7 +1261,14 @@ __global__ void __launch_bounds__(512, 1) k_maniac_decode(Params P) {
     // from it) is uniform across the warp: see RowState
     const int lane = threadIdx.x & 31, warp = (int)__reduce_max_sync(0xffffffffu, threadIdx.x >> 5);
     const int wps = 1 + P.helpers;                       // warps per stream: decoder + walkers
-    const int slot = warp / wps, wrole = warp % wps;
+    const int slot = warp / wps;
+    // Role of this warp inside its stream.  Warps are bound to schedulers by (warp id mod 4): the decoder of stream slot s sits
+    // on scheduler s mod 4 and the other warps of its stream on that scheduler stay idle, so every decoder has an issue
+    // port to itself (two streams per SM: schedulers 0 and 1).
+    const int drole = slot & 3;
+    const int wraw = warp % wps;
+    // 0 = decoder, -1 = idle, k > 0 = walker k-1 (walkers numbered in warp order, skipping the warps of the decoder's scheduler)
+    const int wrole = wraw == drole ? 0 : ((wraw & 3) == drole ? -1 : 1 + wraw - (wraw + 3 - drole) / 4);
     uint16_t *s_table = reinterpret_cast<uint16_t *>(smem_raw);                      // 16 KiB, shared by the block's warps
     for (int i = threadIdx.x; i < 4096 * 2; i += blockDim.x) s_table[i] = P.table[i];
     if (threadIdx.x == 0) {
@@ -1287,7 +1298,7 @@ __global__ void __launch_bounds__(512, 1) k_maniac_decode(Params P) {
         }
         __syncthreads();
         // warps 4, 8, 12 of a stream stay idle: the decoder warp keeps its scheduler (warp id mod 4) to itself
-        if (wrole > 0) { if (wrole & 3) walker_main(sm.mail, sm.cprop, sm.ldrows, wrole - 1 - (wrole >> 2), lane, P.walker_sleep); return; }
+        if (wrole != 0) { if (wrole > 0) walker_main(sm.mail, sm.cprop, sm.ldrows, wrole - 1, lane, P.walker_sleep); return; }
     }
     WarpScratch ws = P.scratch[blockIdx.x * (blockDim.x >> 5) / wps + slot];
     for (;;) {
