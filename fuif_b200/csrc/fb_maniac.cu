@@ -554,6 +554,11 @@ struct Mail {
     unsigned inner_saddr, tagrow;
     const uint16_t *pf_leaves;  // non-null: leaf chances live in global memory behind a cache: walkers prefetch the lines they find
     int pf_shift;
+    int prol_widx;              // the walker warp that computes the chunk prologues (property rows) of chunks >= 2
+    // Monotone progress counters of the current channel (never reset inside a channel, so a walker that is still busy with
+    // a candidate block nobody needed when the next row begins can never wait for something that was overwritten):
+    volatile int progress;      // pixels decoded so far (row-major): pixel (y, x) is done when progress > y * w + x
+    volatile int prol_ready;    // property rows of chunk (y, c) are in place when prol_ready >= y * nchunks + c
     volatile int ack[kMaxWalkers];              // last command each walker has read
     volatile int done[kMaxWalkers];             // last command each walker has finished
     volatile unsigned cval[64];                 // tag << 16 | decoded value & 0xffff, ring indexed by x & 63
@@ -620,17 +625,39 @@ __device__ void walker_main(Mail *mail, const int *cprop2 /* [2][32][kPropStride
         COMPILER_FENCE();
         __syncwarp();
         if (lane == 0) mail->ack[widx] = seen;      // the command's fields may be overwritten from here on
+        if (widx == mail->prol_widx) {
+            // This warp keeps the per-pixel property rows ahead of everybody: chunk c (pixels 32c ..) goes into buffer c & 1
+            // as soon as the decoder has begun chunk c-1 (every walk of chunk c-2 that matters is over by then).
+            const RowState &S = mail->row;
+            DImage &img = *S.img;
+            DChan &ch = *S.ch;
+            int *cprop = S.cprop;
+            const int nrefchan = S.nrefchan, nref = S.nref;
+            int refchan[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) refchan[k] = S.refchan[k];
+            const int nchunks = (w + 31) >> 5;
+            for (int c = 2; c < nchunks; c++) {
+                while (mail->progress < y * w + 32 * (c - 1)) __nanosleep(sleep_ns);      // the decoder has begun chunk c-1
+                __threadfence_block();
+                chunk_prologue(img, ch, y, 32 * c, refchan, nrefchan, nref, cprop + (c & 1) * 32 * kPropStride, lane);
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) mail->prol_ready = y * nchunks + c;
+            }
+            __syncwarp();
+            if (lane == 0) mail->done[widx] = seen;
+            continue;
+        }
         const int r = widx / nb, b = widx - r * nb;
         if (r >= g) { if (lane == 0) mail->done[widx] = seen; continue; }
         const int cl = cmin + 32 * b + lane;        // this lane's candidate for `left`
+        const int nchunks_w = (w + 31) >> 5;
         int slot = r;                               // r < g <= K
         for (int j = r; j < w; j += g) {
-            if (j >= K) {                            // the ring slot is free once pixel j - K has been decoded
-                const unsigned want = tagrow | (unsigned)(j - K + 1);
-                const unsigned fa = cval_s + (unsigned)((j - K) & 63) * 4u;
-                while ((lds32v(fa) >> 16) != want) __nanosleep(sleep_ns);
-                __threadfence_block();      // acquire: the property rows read below were written before that value was posted
-            }
+            if (j >= K) while (mail->progress <= y * w + j - K) __nanosleep(sleep_ns);     // the ring slot is free once pixel j - K has been decoded
+            while (mail->prol_ready < y * nchunks_w + (j >> 5)) { }
+            __threadfence_block();          // acquire: the property rows read below were written before prol_ready was posted
             COMPILER_FENCE();
             const int *pp = cprop2 + (((j >> 5) & 1) * 32 + (j & 31)) * kPropStride;
             const unsigned pp_s = (unsigned)__cvta_generic_to_shared(pp);
@@ -724,8 +751,7 @@ __device__ __forceinline__ unsigned fr_step(FRac &r, unsigned ch, unsigned slot,
 struct SymConsts { int mn, mx, emax_pos, emax_neg; unsigned mant_off; };      // mant_off: byte offset of bit_mant[0] in a leaf
 // reader<15>(coder, min, max), symbol.h:154-185.  SIGN_MODE 0: the sign is coded (min < 0 < max), 1: always positive, 2: always negative
 template <int SIGN_MODE>
-__device__ __forceinline__ int fread_int(FRac &r, unsigned leaf_s, unsigned tab_s, const SymConsts &K) {
-    const uint4 L = lds128(leaf_s);             // zero, sign, exp[0..5]
+__device__ __forceinline__ int fread_int(FRac &r, unsigned leaf_s, const uint4 &L /* zero, sign, exp[0..5] of the leaf */, unsigned tab_s, const SymConsts &K) {
     if (fr_step(r, L.x & 0xffffu, leaf_s, tab_s)) return 0;
     unsigned sign;
     if (SIGN_MODE == 0) sign = fr_step(r, L.x >> 16, leaf_s + 2u, tab_s);
@@ -748,12 +774,30 @@ __device__ __forceinline__ int fread_int(FRac &r, unsigned leaf_s, unsigned tab_
 exp_done:;
     int have = 1 << e;
     const unsigned mb = leaf_s + K.mant_off;
-    for (int pos = e; pos > 0;) {
-        pos--;
-        const int minabs1 = have | (1 << pos);
-        if (minabs1 > amax) continue;
-        if (fr_step(r, lds16(mb + 2u * pos), mb + 2u * pos, tab_s)) have = minabs1;
+    // mantissa, top position first (symbol.h:174-182): a jump on e into a fall-through sequence with static positions
+#define FB_MSTEP(p)                                                                                        \
+    {                                                                                                      \
+        const int minabs1 = have | (1 << (p));                                                             \
+        if (minabs1 <= amax && fr_step(r, lds16(mb + 2u * (p)), mb + 2u * (p), tab_s)) have = minabs1;     \
     }
+    switch (e) {
+    case 14: FB_MSTEP(13)
+    case 13: FB_MSTEP(12)
+    case 12: FB_MSTEP(11)
+    case 11: FB_MSTEP(10)
+    case 10: FB_MSTEP(9)
+    case 9: FB_MSTEP(8)
+    case 8: FB_MSTEP(7)
+    case 7: FB_MSTEP(6)
+    case 6: FB_MSTEP(5)
+    case 5: FB_MSTEP(4)
+    case 4: FB_MSTEP(3)
+    case 3: FB_MSTEP(2)
+    case 2: FB_MSTEP(1)
+    case 1: FB_MSTEP(0)
+    default: break;
+    }
+#undef FB_MSTEP
     return sign ? have : -have;
 }
 
@@ -761,19 +805,21 @@ __device__ __forceinline__ uint4 ldg128(const void *p) { return *reinterpret_cas
 __device__ __forceinline__ void sts128(unsigned addr, const uint4 &v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-// shared-memory address of a leaf's chances: resident array, or a direct-mapped write-back cache over the global array
-__device__ __forceinline__ unsigned leaf_addr_uniform(const RowState &R, unsigned leaf) {
-    if (!R.cached) return R.lines_s + (leaf << R.line_shift);
+// shared-memory address of a leaf's chances (resident array, or a direct-mapped write-back cache over the global array) and its
+// first eight chances; with the cache, the chances are loaded together with the tag and loaded again only after a miss
+__device__ __forceinline__ unsigned leaf_addr_uniform(const RowState &R, unsigned leaf, uint4 &L) {
+    if (!R.cached) { const unsigned a = R.lines_s + (leaf << R.line_shift); L = lds128(a); return a; }
     const unsigned slot = R.nlines ? leaf - __umulhi(leaf, R.inv_nlines) * R.nlines : (leaf & R.mask);
     const unsigned ta = R.tags_s + slot * 4u;
-    const int tag = lds32(ta);
     const unsigned line = R.lines_s + (slot << R.line_shift);
+    const int tag = lds32(ta);
+    L = lds128(line);
     if (tag != (int)leaf) {
         // write the evicted leaf back and fetch the new one: 32 bytes (compact leaves) or 64
         const bool big = R.line_shift == 6u;
         if (tag >= 0) {
             uint4 *old = reinterpret_cast<uint4 *>(R.gleaves + ((size_t)tag << (R.line_shift - 1)));
-            old[0] = lds128(line); old[1] = lds128(line + 16u);
+            old[0] = L; old[1] = lds128(line + 16u);
             if (big) { old[2] = lds128(line + 32u); old[3] = lds128(line + 48u); }
         }
         const uint4 *src = reinterpret_cast<const uint4 *>(R.gleaves + ((size_t)leaf << (R.line_shift - 1)));
@@ -781,6 +827,7 @@ __device__ __forceinline__ unsigned leaf_addr_uniform(const RowState &R, unsigne
         sts128(line, v0); sts128(line + 16u, v1);
         if (big) { const uint4 v2 = ldg128(src + 2), v3 = ldg128(src + 3); sts128(line + 32u, v2); sts128(line + 48u, v3); }
         sts32v(ta, leaf);
+        L = lds128(line);       // (not `L = v0`: a value that comes out of a generic load counts as divergent for the compiler, see RowState)
     }
     return line;
 }
@@ -818,22 +865,18 @@ __device__ __noinline__ void row_ahead_loop() {
         for (int k = 0; k < (int)(sizeof(RowState) / 4); k++) dst[k] = (unsigned)lds32(rs + 4u * k);
     }
     const unsigned cval_s = mail_s + (unsigned)offsetof(Mail, cval), cand_s = mail_s + (unsigned)offsetof(Mail, cand);
+    const unsigned prol_s = mail_s + (unsigned)offsetof(Mail, prol_ready), prog_s = mail_s + (unsigned)offsetof(Mail, progress);
     const unsigned tab_s = R.tab_s, cprop_s = R.cprop_s;
     SymConsts K;
     K.mn = R.mn; K.mx = R.mx; K.emax_pos = R.emax_pos; K.emax_neg = R.emax_neg; K.mant_off = R.mant_off;
     FRac fr;
     fr.range = R.range; fr.low = R.low; fr.ones = R.ones; fr.p = R.p; fr.pos = R.pos; fr.n = R.n;
     const int w = R.w, zero = R.zero, cmin = R.cmin, y = R.y;
-    DImage &img = *R.img;
-    DChan &ch = *R.ch;
-    int16_t *row = ch.data + (size_t)y * w;
+    int16_t *row = R.ch->data + (size_t)y * w;
+    const int rowbase = y * w;
     int left = zero, leftleft = zero;
     unsigned slot = 0;
     for (int x0 = 0; x0 < w; x0 += 32) {
-        if (x0 > 0 && x0 + 32 < w) {      // properties of the chunk after this one (the walks of chunk x0-32 that matter are over)
-            chunk_prologue(img, ch, y, x0 + 32, R.refchan, R.nrefchan, R.nref, R.cprop + (((x0 >> 5) + 1) & 1) * 32 * kPropStride, lane);
-            __syncwarp();
-        }
         const int cnt = min(32, w - x0);
         for (int i = 0; i < cnt; i++) {         // all lanes, identical values
             const int xx = x0 + i;
@@ -845,12 +888,16 @@ __device__ __noinline__ void row_ahead_loop() {
             unsigned res = e.y & 0x7fffu;
             const unsigned kind = e.y >> 30;
             if (kind == 1u) res = leftleft <= (int)(short)(e.x & 0xffffu) ? res : ((e.y >> 15) & 0x7fffu);
-            else if (kind == 2u)
+            else if (kind == 2u) {
+                while ((int)lds32v(prol_s) < y * ((w + 31) >> 5) + (xx >> 5)) { }
                 res = finish_walk(R.inner_s, res, cprop_s + (unsigned)((((xx >> 5) & 1) * 32 + (xx & 31)) * kPropStride) * 4u, left, leftleft, xx, y);
-            const unsigned leaf_s = leaf_addr_uniform(R, res);
-            const int diff = fread_int<SIGN_MODE>(fr, leaf_s, tab_s, K);
+            }
+            uint4 L;
+            const unsigned leaf_s = leaf_addr_uniform(R, res, L);
+            const int diff = fread_int<SIGN_MODE>(fr, leaf_s, L, tab_s, K);
             const int val = s16(s16(diff) + zero);
             sts32v(cval_s + (unsigned)(xx & 63) * 4u, (want << 16) | ((unsigned)val & 0xffffu));
+            sts32v(prog_s, (unsigned)(rowbase + xx + 1));
             leftleft = xx ? left : val;          // next pixel: x > 1 ? value(x-2) : left   (context_predict.h:132)
             left = val;
         }
@@ -879,7 +926,7 @@ __device__ __forceinline__ void decode_row_ahead(int sign_mode, DImage &img, DCh
     __syncwarp();
     if (lane == 0) {
         const int zero = ch.zero, cmin = ch.minval, cmax = ch.maxval;
-        const int g = max(1, min(8, sm.nwalkers / nb)), kslots = g >= 5 ? g : g * ((8 + g - 1) / g);
+        const int g = max(1, min(8, (sm.nwalkers - 1) / nb)), kslots = g >= 5 ? g : g * ((8 + g - 1) / g);
         RowState &S = mail->row;
         S.w = w; S.y = y; S.zero = zero; S.cmin = cmin;
         S.mn = cmin - zero; S.mx = cmax - zero;                 // predictor 0: guess = zero
@@ -896,6 +943,7 @@ __device__ __forceinline__ void decode_row_ahead(int sign_mode, DImage &img, DCh
         mail->y = y; mail->w = w; mail->cmin = cmin; mail->nb = nb; mail->g = g; mail->K = kslots;
         mail->inner_saddr = inner_s; mail->tagrow = S.tagrow; mail->cmd = 1;
         mail->pf_leaves = (ls.tags && sm.prefetch) ? ls.gleaves : nullptr; mail->pf_shift = ls.shift;
+        mail->prol_widx = sm.nwalkers - 1; mail->prol_ready = y * ((w + 31) >> 5) + 1;       // chunks 0 and 1 were computed above
         __threadfence_block();
         mail->cmd_seq = mail->cmd_seq + 1;
     }
@@ -1095,7 +1143,7 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
     // compact inner-node array in shared memory (+ room for some leaves), 24-bit split values, 15-bit x tags, 32-bit offsets.
     const int ninner = nnodes / 2;
     const int inner_bytes = (ninner * 8 + 15) & ~15;
-    bool ahead = sm.mail && predictor == 0 && nnodes > 1 && group_range >= 1 && (group_range + 31) / 32 <= sm.nwalkers && group_range <= kMaxCand &&
+    bool ahead = sm.mail && predictor == 0 && nnodes > 1 && group_range >= 1 && (group_range + 31) / 32 <= sm.nwalkers - 1 && group_range <= kMaxCand &&
                  inner_bytes + 16384 <= sm.dyn_bytes && group_maxw <= 32766 && img.nbytes < 0x7fff0000ull && group_lo >= -32000 && group_hi <= 32000;
     if (ahead) {
         bool wide = false;
@@ -1212,6 +1260,7 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
             const int nwalk = (range + 31) / 32;
             const int sign_mode = (ch.minval - ch.zero < 0) ? ((ch.maxval - ch.zero > 0) ? 0 : 2) : 1;
             if (helped) {       // handshake rings start out with tag 0 (never awaited); the walkers are idle here
+                if (lane == 0) { sm.mail->progress = 0; sm.mail->prol_ready = 0; }
                 for (int k = lane; k < 64; k += 32) sm.mail->cval[k] = 0;
                 for (int k = lane; k < kCandSlotsMax * kMaxCand; k += 32) { (&sm.mail->cand[0][0])[k].x = 0; (&sm.mail->cand[0][0])[k].y = 0; }
                 __syncwarp();
