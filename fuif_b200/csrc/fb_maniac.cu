@@ -11,11 +11,13 @@
 //
 // Mapping.  The bitstream is strictly serial inside one channel group (adaptive chances + neighbour
 // context), so the unit of parallelism is a *stream*: one channel group when the caller supplies
-// the groups' byte offsets (group index), otherwise one whole image.  One warp decodes one stream: the serial
-// decode is executed warp-uniformly (no divergence), while the data-parallel pieces (reference-property
-// rows, leaf initialisation, constant fills) are spread over the 32 lanes.  Streams are handed out through
-// an atomic ticket so that a stream only ever waits for lower-numbered streams (row wavefront on the
-// planes it back-references), which are guaranteed to be running already.
+// the groups' byte offsets (group index), otherwise one whole image.  A stream gets one SM-resident team of warps:
+// a decoder warp that runs the serial coder (its pixel loop is executed redundantly by all lanes on warp-uniform
+// values, see RowState), walker warps that evaluate the MANIAC tree of upcoming pixels for every candidate value of
+// `left` several pixels ahead of the decoder, and a warp that keeps the per-pixel property rows ahead of both
+// (see walker_main).  Groups the walkers cannot serve fall back to decode_row (one warp, lane k owns property k).
+// Streams are handed out through an atomic ticket so that a stream only ever waits for lower-numbered streams (row
+// wavefront on the planes it back-references), which are guaranteed to be running already.
 #include "fb_common.cuh"
 
 #include <stddef.h>
