@@ -1279,3 +1279,538 @@ fo_image *fo_decode(const uint8_t *bytes, size_t n, int preview, int maniac_cuto
     if (ngroups) *ngroups = gcount;
     return img;
 }
+
+/* ================================================================================================ */
+/* ENCODER (test infrastructure for the encode-side rows of SURVEY 8a: a20, a22, a24)                */
+/*   fuif_encode                 encoding/encoding.cpp:455-573                                       */
+/*   fuif_encode_channels        encoding/encoding.cpp:74-207 (learn pass + real pass)               */
+/*   PropertySymbolCoder         maniac/compound_enc.h:243-518 (tree learning, simplify)             */
+/*   CompoundSymbolBitCoder      maniac/compound_enc.h:76-136 (virtual chances, cost estimates)      */
+/*   MetaPropertySymbolCoder     maniac/compound_enc.h:523-552 (write_tree)                          */
+/*   writer<>, UniformSymbolCoder maniac/symbol_enc.h:28-109                                         */
+/*   RacOutput                   maniac/rac_enc.h:28-100                                             */
+/*   Log4kTable                  maniac/chance.cpp:67-91                                             */
+/*   BlobIO                      fileio.h:148-272 (including its bytes_used = seek_pos + 1 quirk)    */
+/* ================================================================================================ */
+
+#define CONTEXT_TREE_SPLIT_THRESHOLD (5461 * 8 * 2)     /* config.h */
+#define CONTEXT_TREE_MIN_SUBTREE_SIZE 10                /* config.h */
+
+/* ---- BlobIO (fileio.h:148-272) ---- */
+typedef struct { uint8_t *data; size_t cap, used, pos; } oblob;
+static void ob_grow(oblob *b, size_t need) {
+    if (need < b->cap) return;
+    size_t ns = need < 4096 ? 4096 : need;
+    if (ns < b->cap * 3 / 2) ns = b->cap * 3 / 2;
+    b->data = (uint8_t *)realloc(b->data, ns);
+    memset(b->data + b->cap, 0, ns - b->cap);       /* the reference leaves this memory uninitialised */
+    b->cap = ns;
+}
+static void ob_putc(oblob *b, int c) {              /* BlobIO::fputc: bytes_used runs ONE byte ahead of the last byte written */
+    ob_grow(b, b->pos + 1);
+    b->data[b->pos++] = (uint8_t)c;
+    if (b->used < b->pos) b->used = b->pos + 1;
+}
+static void ob_varint(oblob *b, size_t number, int done) {      /* write_big_endian_varint, encoding.cpp:30-41 */
+    if (number < 128) ob_putc(b, (int)(done ? number : number + 128));
+    else { size_t lsb = number & 127; ob_varint(b, number >> 7, 0); ob_varint(b, lsb, done); }
+}
+
+/* ---- RacOutput24 (rac_enc.h:28-100); out == NULL is RacDummy ---- */
+typedef struct { oblob *out; uint64_t range, low; int delayed_byte, delayed_count; } rac_out;
+static void racout_init(rac_out *r, oblob *out) { r->out = out; r->range = 1u << 24; r->low = 0; r->delayed_byte = -1; r->delayed_count = 0; }
+static void racout_output(rac_out *r) {
+    while (r->range <= (1u << 16)) {
+        int byte = (int)(r->low >> 16);
+        if (r->delayed_byte < 0) r->delayed_byte = byte;
+        else if (((r->low + r->range) >> 8) < (1u << 16)) {
+            ob_putc(r->out, r->delayed_byte);
+            while (r->delayed_count) { ob_putc(r->out, 0xFF); r->delayed_count--; }
+            r->delayed_byte = byte;
+        } else if ((r->low >> 8) >= (1u << 16)) {
+            ob_putc(r->out, r->delayed_byte + 1);
+            while (r->delayed_count) { ob_putc(r->out, 0); r->delayed_count--; }
+            r->delayed_byte = byte & 0xFF;
+        } else r->delayed_count++;
+        r->low = (r->low & ((1u << 16) - 1)) << 8;
+        r->range <<= 8;
+    }
+}
+static void racout_put(rac_out *r, uint64_t chance, int bit) {
+    if (!r->out) return;
+    if (bit) { r->low += r->range - chance; r->range = chance; } else r->range -= chance;
+    racout_output(r);
+}
+static void racout_write_12bit(rac_out *r, int b12, int bit) { if (r->out) racout_put(r, (r->range * (uint64_t)b12 + 0x800) >> 12, bit); }
+static void racout_write_bit(rac_out *r, int bit) { if (r->out) racout_put(r, r->range >> 1, bit); }
+static void racout_flush(rac_out *r) {
+    if (!r->out) return;
+    r->low += (1u << 16) - 1;
+    for (int k = 0; k < 4; k++) { r->range = (1u << 16) - 1; racout_output(r); }
+}
+
+/* ---- Log4kTable (chance.cpp:67-91) ---- */
+static uint16_t log4k_data[4097];
+static int log4k_ready = 0;
+static uint32_t log4kf(int x, uint32_t base) {
+    int bits = 8 * (int)sizeof(int) - __builtin_clz((unsigned)x);
+    uint64_t y = ((uint64_t)x) << (32 - bits);
+    uint32_t res = base * (uint32_t)(13 - bits);
+    uint32_t add = base;
+    while ((add > 1) && ((y & 0x7FFFFFFF) != 0)) {
+        y = (((uint64_t)y) * y + 0x40000000) >> 31;
+        add >>= 1;
+        if ((y >> 32) != 0) { res -= add; y >>= 1; }
+    }
+    return res;
+}
+static void log4k_init(void) {
+    if (log4k_ready) return;
+    log4k_data[0] = 0;
+    for (int i = 1; i <= 4096; i++) log4k_data[i] = (uint16_t)((log4kf(i, (uint32_t)((65535UL << 16) / 12)) + (1 << 15)) >> 16);
+    log4k_ready = 1;
+}
+static inline void chance_estim(uint16_t chance, int bit, uint64_t *total) { *total += log4k_data[bit ? chance : 4096 - chance]; }   /* chance.h:80-82 */
+
+/* ---- generic writer<15>(coder,min,max,value), symbol_enc.h:58-109; put(ctx, bit, index into symchance.c) ---- */
+typedef void (*bit_sink)(void *ctx, int bit, int idx);
+static void write_int_generic(bit_sink put, void *ctx, int min, int max, int value) {
+    if (min == max) return;
+    if (value == 0) { put(ctx, 1, SC_ZERO); return; }
+    put(ctx, 0, SC_ZERO);
+    int sign = (value > 0 ? 1 : 0);
+    if (max > 0 && min < 0) put(ctx, sign, SC_SIGN);
+    const int a = abs(value);
+    const int e = ilog2u((uint32_t)a);
+    int amax = sign ? abs(max) : abs(min);
+    int emax = ilog2u((uint32_t)amax);
+    int i = 0;
+    while (i < emax) {
+        if ((1 << (i + 1)) > amax) break;
+        put(ctx, i == e, SC_EXP + i);
+        if (i == e) break;
+        i++;
+    }
+    int have = (1 << e);
+    for (int pos = e; pos > 0;) {
+        int bit = 1;
+        --pos;
+        int minabs1 = have | (1 << pos);
+        if (minabs1 > amax) bit = 0;
+        else { bit = (a >> pos) & 1; put(ctx, bit, SC_MANT + pos); }
+        have |= (bit << pos);
+    }
+}
+static void write_int2_generic(bit_sink put, void *ctx, int min, int max, int value) {      /* symbol.h:223-227 */
+    if (min > 0) write_int_generic(put, ctx, 0, max - min, value - min);
+    else if (max < 0) write_int_generic(put, ctx, min - max, 0, value - max);
+    else write_int_generic(put, ctx, min, max, value);
+}
+
+/* SimpleSymbolBitCoder::write (symbol_enc.h:167-172) and FinalCompoundSymbolBitCoder::write (compound_enc.h:62-67) */
+typedef struct { rac_out *rac; const chance_table *t; symchance *s; } simple_ctx;
+static void simple_put(void *vc, int bit, int idx) {
+    simple_ctx *c = (simple_ctx *)vc;
+    racout_write_12bit(c->rac, c->s->c[idx], bit);
+    c->s->c[idx] = c->t->next[c->s->c[idx]][bit];
+}
+static void uniform_write(rac_out *rac, int min, int max, int val) {        /* UniformSymbolCoder::write_int, symbol_enc.h:28-47 */
+    if (min != 0) { max -= min; val -= min; }
+    if (max == 0) return;
+    int med = max / 2;
+    if (val > med) { racout_write_bit(rac, 1); uniform_write(rac, med + 1, max, val); }
+    else { racout_write_bit(rac, 0); uniform_write(rac, 0, med, val); }
+}
+
+/* ---- leaf of the learning pass: CompoundSymbolChances, compound_enc.h:29-59 ---- */
+typedef struct {
+    symchance real;
+    symchance *virt;            /* [nprop][2]: first (selected when property > splitval), second */
+    uint64_t realSize;
+    uint64_t *virtSize;
+    int64_t *virtPropSum;
+    int32_t count;
+    int16_t best_property;
+} lleaf;
+static void lleaf_init(lleaf *l, int nprop, int zero_chance) {
+    symchance_init(&l->real, zero_chance);
+    l->virt = (symchance *)malloc(sizeof(symchance) * 2 * (size_t)(nprop > 0 ? nprop : 1));
+    for (int i = 0; i < 2 * nprop; i++) symchance_init(&l->virt[i], zero_chance);
+    l->virtSize = (uint64_t *)calloc((size_t)(nprop > 0 ? nprop : 1), sizeof(uint64_t));
+    l->virtPropSum = (int64_t *)calloc((size_t)(nprop > 0 ? nprop : 1), sizeof(int64_t));
+    l->realSize = 0; l->count = 0; l->best_property = -1;
+}
+static void lleaf_copy(lleaf *d, const lleaf *s, int nprop) {
+    d->real = s->real;
+    d->virt = (symchance *)malloc(sizeof(symchance) * 2 * (size_t)(nprop > 0 ? nprop : 1));
+    memcpy(d->virt, s->virt, sizeof(symchance) * 2 * (size_t)nprop);
+    d->virtSize = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(nprop > 0 ? nprop : 1));
+    memcpy(d->virtSize, s->virtSize, sizeof(uint64_t) * (size_t)nprop);
+    d->virtPropSum = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nprop > 0 ? nprop : 1));
+    memcpy(d->virtPropSum, s->virtPropSum, sizeof(int64_t) * (size_t)nprop);
+    d->realSize = s->realSize; d->count = s->count; d->best_property = s->best_property;
+}
+static void lleaf_free(lleaf *l) { free(l->virt); free(l->virtSize); free(l->virtPropSum); }
+static void lleaf_reset_counters(lleaf *l, int nprop) {     /* resetCounters, compound_enc.h:40-46 */
+    l->best_property = -1; l->realSize = 0; l->count = 0;
+    for (int i = 0; i < nprop; i++) { l->virtPropSum[i] = 0; l->virtSize[i] = 0; }
+}
+
+/* ---- PropertySymbolCoder (learning), compound_enc.h:243-518 ---- */
+typedef struct {
+    const chance_table *table;
+    int nprop;
+    int (*range)[2];
+    lleaf *leaf; int nleaf, capleaf;
+    tree *t;
+    unsigned char *selection;
+    int split_threshold;
+    int (*cur)[2];              /* scratch: current_ranges */
+} learner;
+static inline int div_down(int64_t sum, int32_t count) {   /* compound_enc.h:256-260 */
+    if (sum >= 0) return (int)(sum / count);
+    return (int)-((-sum + count - 1) / count);
+}
+static inline int compute_splitval(const lleaf *ch, int p, int (*crange)[2]) {   /* compound_enc.h:261-284 */
+    if (crange[p][0] < 0 && crange[p][1] > 0) return 0;
+    int splitval = div_down(ch->virtPropSum[p], ch->count);
+    if (splitval >= crange[p][1]) splitval = crange[p][1] - 1;
+    return splitval;
+}
+/* find_leaf, compound_enc.h:307-366; returns the index of the leaf the symbol is coded with */
+static int learner_find_leaf(learner *L, const int *props) {
+    tree *t = L->t;
+    int pos = 0;
+    for (int i = 0; i < L->nprop; i++) { L->cur[i][0] = L->range[i][0]; L->cur[i][1] = L->range[i][1]; }
+    while (t->n[pos].property != -1) {
+        const int p = t->n[pos].property;
+        if (props[p] > t->n[pos].splitval) { L->cur[p][0] = t->n[pos].splitval + 1; pos = t->n[pos].childID; }
+        else { L->cur[p][1] = t->n[pos].splitval; pos = t->n[pos].childID + 1; }
+    }
+    int li = t->n[pos].childID;
+    lleaf *result = &L->leaf[li];
+    /* set_selection_and_update_property_sums, compound_enc.h:368-378 */
+    result->count++;
+    for (int i = 0; i < L->nprop; i++) {
+        result->virtPropSum[i] += props[i];
+        int splitval = compute_splitval(result, i, L->cur);
+        L->selection[i] = (unsigned char)(props[i] > splitval);
+    }
+    const int bp = result->best_property;
+    if (bp != -1 && result->realSize > result->virtSize[bp] + (uint64_t)L->split_threshold && L->nleaf < 0xFFFF && t->size < 0xFFFF &&
+        L->cur[bp][0] < L->cur[bp][1]) {
+        const int p = bp;
+        const int splitval = compute_splitval(result, p, L->cur);
+        const int new_inner = t->size;
+        const tnode copy = t->n[pos];
+        int a = tree_push(t); t->n[a] = copy;
+        int b = tree_push(t); t->n[b] = copy;
+        t->n[pos].splitval = splitval;
+        t->n[pos].property = (int16_t)p;
+        const int new_leaf = L->nleaf;
+        lleaf_reset_counters(result, L->nprop);
+        if (L->nleaf == L->capleaf) {
+            L->capleaf = L->capleaf ? L->capleaf * 2 : 16;
+            L->leaf = (lleaf *)realloc(L->leaf, sizeof(lleaf) * (size_t)L->capleaf);
+            result = &L->leaf[li];
+        }
+        lleaf_copy(&L->leaf[L->nleaf], result, L->nprop);
+        L->nleaf++;
+        const int old_leaf = t->n[pos].childID;
+        t->n[pos].childID = (uint16_t)new_inner;
+        t->n[new_inner].childID = (uint16_t)old_leaf;
+        t->n[new_inner + 1].childID = (uint16_t)new_leaf;
+        return props[p] > t->n[pos].splitval ? old_leaf : new_leaf;
+    }
+    return li;
+}
+/* CompoundSymbolBitCoder::write with RacDummy = updateChances, compound_enc.h:91-109 */
+typedef struct { learner *L; lleaf *leaf; } learn_ctx;
+static void learn_put(void *vc, int bit, int idx) {
+    learn_ctx *c = (learn_ctx *)vc;
+    lleaf *ch = c->leaf;
+    const chance_table *t = c->L->table;
+    chance_estim(ch->real.c[idx], bit, &ch->realSize);
+    ch->real.c[idx] = t->next[ch->real.c[idx]][bit];
+    int best_property = -1;
+    uint64_t best_size = ch->realSize;
+    for (int j = 0; j < c->L->nprop; j++) {
+        symchance *v = &ch->virt[2 * j + (c->L->selection[j] ? 0 : 1)];
+        chance_estim(v->c[idx], bit, &ch->virtSize[j]);
+        v->c[idx] = t->next[v->c[idx]][bit];
+        if (ch->virtSize[j] < best_size) { best_size = ch->virtSize[j]; best_property = j; }
+    }
+    ch->best_property = (int16_t)best_property;
+}
+/* simplify, compound_enc.h:430-496 */
+static void kill_children(tree *t, int pos) {
+    if (t->n[pos].property == -1) t->n[pos].property = 0; else kill_children(t, t->n[pos].childID);
+    if (t->n[pos + 1].property == -1) t->n[pos + 1].property = 0; else kill_children(t, t->n[pos + 1].childID);
+}
+static long long simplify_subtree(learner *L, int pos, int min_size) {
+    tree *t = L->t;
+    if (t->n[pos].property == -1) {
+        if (L->leaf[t->n[pos].childID].count == 0) return -100;
+        return L->leaf[t->n[pos].childID].count;
+    }
+    long long subtree_size = 0;
+    subtree_size += simplify_subtree(L, t->n[pos].childID, min_size);
+    subtree_size += simplify_subtree(L, t->n[pos].childID + 1, min_size);
+    if (subtree_size < min_size) { t->n[pos].property = -1; kill_children(t, t->n[pos].childID); }
+    return subtree_size;
+}
+
+/* MetaPropertySymbolCoder::write_subtree, compound_enc.h:523-546 */
+typedef struct { rac_out *rac; const chance_table *t; symchance coder[3]; int nprop; } meta_out;
+static void write_subtree(meta_out *m, const tree *t, int pos, int (*sub)[2]) {
+    const tnode *n = &t->n[pos];
+    const int p = n->property;
+    simple_ctx c0 = {m->rac, m->t, &m->coder[0]};
+    write_int2_generic(simple_put, &c0, 0, m->nprop, p + 1);
+    if (p != -1) {
+        const int oldmin = sub[p][0], oldmax = sub[p][1];
+        simple_ctx c2 = {m->rac, m->t, &m->coder[2]};
+        write_int2_generic(simple_put, &c2, oldmin, oldmax - 1, n->splitval);
+        sub[p][0] = n->splitval + 1;
+        write_subtree(m, t, n->childID, sub);
+        sub[p][0] = oldmin;
+        sub[p][1] = n->splitval;
+        write_subtree(m, t, n->childID + 1, sub);
+        sub[p][1] = oldmax;
+    }
+}
+
+/* fuif_encode_channels<learn, compress>, encoding.cpp:74-207.  out == NULL: DummyIO / RacDummy (the learn pass). */
+static int encode_channels(oblob *out, tree *t, const fo_enc_options *opt, const chance_table *table, int predictor, int beginc, int endc,
+                           fo_image *img, size_t *header_pos, int learn, int compress) {
+    oblob dummy = {0};
+    oblob *io = out ? out : &dummy;
+    ob_varint(io, (size_t)(((endc - beginc) << 4) + (predictor << 1) + (compress ? 1 : 0)), 1);
+    int global_minv = LARGEST_VAL, global_maxv = SMALLEST_VAL;
+    for (int i = beginc; i <= endc; i++) {
+        const fo_channel *ch = &img->ch[i];
+        if (ch->w * ch->h <= 0) continue;
+        if (ch->minval < global_minv) global_minv = ch->minval;
+        if (ch->maxval > global_maxv) global_maxv = ch->maxval;
+    }
+    if (global_minv <= 0) ob_varint(io, (size_t)(1 - global_minv), 1);
+    else { ob_varint(io, 0, 1); ob_varint(io, (size_t)global_minv, 1); }
+    ob_varint(io, (size_t)(global_maxv - global_minv), 1);
+    int firstrealc = beginc;
+    for (int i = beginc; i <= endc; i++) {
+        fo_channel *ch = &img->ch[i];
+        if (ch->w * ch->h <= 0) continue;
+        const int minv = ch->minval, maxv = ch->maxval;
+        if (endc > beginc && global_minv < global_maxv) { ob_varint(io, (size_t)(minv - global_minv), 1); ob_varint(io, (size_t)(maxv - minv), 1); }
+        if (minv == maxv) firstrealc++;
+        if (!check_bit_depth(minv, maxv, predictor)) { free(dummy.data); return 0; }
+        if (minv == 0 && maxv == 0) continue;
+        ob_varint(io, (size_t)ch->q, 1);
+        ch_setzero(ch);
+    }
+    *header_pos = out ? io->pos : (size_t)-1;
+    if (firstrealc > endc) { free(dummy.data); return 1; }
+
+    int pr[64][2];
+    const int nprops = init_properties(pr, img, beginc, endc, opt->max_properties);
+    const int nref = nprops - NB_NONREF;
+    int predictability = 2048;
+    {
+        const fo_channel *ch = &img->ch[firstrealc];
+        if (predictor == 0 && compress) {
+            uint64_t zeroes = 0, pixels = (uint64_t)(ch->h * ch->w);
+            for (size_t k = 0; k < (size_t)ch->w * ch->h; k++) if (ch->data[k] == 0) zeroes++;
+            int rounded = (int)(zeroes * 128 / pixels);
+            if (rounded < 1) rounded = 1;
+            if (rounded > 127) rounded = 127;
+            ob_varint(io, (size_t)rounded, 1);
+            predictability = rounded * 32;
+        }
+    }
+    rac_out rac;
+    racout_init(&rac, out);
+    if (!compress) {
+        for (int i = beginc; i <= endc; i++) {
+            const fo_channel *ch = &img->ch[i];
+            for (size_t k = 0; k < (size_t)ch->w * ch->h; k++) uniform_write(&rac, ch->minval, ch->maxval, ch->data[k]);
+        }
+    } else {
+        learner L;
+        memset(&L, 0, sizeof(L));
+        symchance *fleaf = NULL;
+        if (!learn) {
+            static chance_table meta_table;
+            static int meta_ready = 0;
+            if (!meta_ready) { build_table(&meta_table, 0xFFFFFFFFu / 19, 4096 - 2); meta_ready = 1; }
+            meta_out m;
+            m.rac = &rac; m.t = &meta_table; m.nprop = nprops;
+            for (int k = 0; k < 3; k++) symchance_init(&m.coder[k], 1024);
+            int sub[64][2];
+            for (int k = 0; k < nprops; k++) { sub[k][0] = pr[k][0]; sub[k][1] = pr[k][1]; }
+            write_subtree(&m, t, 0, sub);
+            /* FinalPropertySymbolCoder ctor, compound.h:213-225 */
+            const int nleaves = (t->size + 1) / 2;
+            fleaf = (symchance *)malloc(sizeof(symchance) * (size_t)nleaves);
+            for (int k = 0; k < nleaves; k++) symchance_init(&fleaf[k], predictability);
+            for (int k = 0, leafID = 0; k < t->size; k++) if (t->n[k].property == -1) t->n[k].childID = (uint16_t)leafID++;
+        } else {
+            L.table = table; L.nprop = nprops; L.range = pr; L.t = t; L.split_threshold = CONTEXT_TREE_SPLIT_THRESHOLD;
+            L.capleaf = 16; L.leaf = (lleaf *)malloc(sizeof(lleaf) * 16); L.nleaf = 1;
+            lleaf_init(&L.leaf[0], nprops, predictability);
+            L.selection = (unsigned char *)calloc((size_t)(nprops > 0 ? nprops : 1), 1);
+            L.cur = (int (*)[2])malloc(sizeof(int[2]) * 64);
+        }
+        int props[64];
+        memset(props, 0, sizeof(props));
+        for (int i = beginc; i <= endc; i++) {
+            const fo_channel *ch = &img->ch[i];
+            const int minv = ch->minval, maxv = ch->maxval;
+            if (minv == maxv) continue;
+            int rowslearned = 0;
+            int *refs = (int *)calloc((size_t)(nref > 0 ? nref : 1) * (size_t)(ch->w > 0 ? ch->w : 1), sizeof(int));
+            for (int y = 0; y < ch->h; y++) {
+                if (learn) { if ((float)++rowslearned > opt->nb_repeats * (float)ch->h) break; }
+                if (learn) y = rand() % ch->h;
+                precompute_references(ch, y, img, beginc, opt->max_properties, refs, nref);
+                for (int x = 0; x < ch->w; x++) {
+                    for (int k = 0; k < nref; k++) props[k] = refs[x * nref + k];
+                    const int guess = predict_props(props, ch, x, y, predictor, nref);
+                    const int diff = S16(ch->data[(size_t)y * ch->w + x] - guess);
+                    const int mn = minv - guess, mx = maxv - guess;
+                    if (learn) {                    /* PropertySymbolCoder::write_int looks for (and may split) the leaf even when min == max */
+                        const int li = learner_find_leaf(&L, props);
+                        learn_ctx c = {&L, &L.leaf[li]};
+                        write_int_generic(learn_put, &c, mn, mx, diff);
+                    } else if (mn != mx) {          /* FinalPropertySymbolCoder::write_int, compound_enc.h:217-223 */
+                        int pos = 0;
+                        while (t->n[pos].property != -1) pos = props[t->n[pos].property] > t->n[pos].splitval ? t->n[pos].childID : t->n[pos].childID + 1;
+                        simple_ctx c = {&rac, table, &fleaf[t->n[pos].childID]};
+                        write_int_generic(simple_put, &c, mn, mx, diff);
+                    }
+                }
+                if (learn) y = 0;
+            }
+            free(refs);
+        }
+        if (learn) {
+            simplify_subtree(&L, 0, CONTEXT_TREE_MIN_SUBTREE_SIZE);
+            for (int k = 0; k < L.nleaf; k++) lleaf_free(&L.leaf[k]);
+            free(L.leaf); free(L.selection); free(L.cur);
+        }
+        free(fleaf);
+    }
+    racout_flush(&rac);
+    free(dummy.data);
+    return 1;
+}
+
+/* Image::recompute_downscales, image/image.cpp:124-136 */
+static void recompute_downscales(const fo_image *img, int *ds) {
+    ds[0] = img->nb_meta_channels + img->nb_channels - 1;
+    for (int s = 1; s < 6; s++) {
+        ds[s] = img->nch - 1;
+        for (int k = ds[s - 1]; k < img->nch; k++) {
+            const int rs = 32 >> s;
+            if ((1 << img->ch[k].hcshift) < rs || (1 << img->ch[k].vcshift) < rs) break;
+            if ((1 << img->ch[k].hcshift) == rs && (1 << img->ch[k].vcshift) == rs) ds[s] = k;
+        }
+    }
+}
+
+/* fuif_prepare_encode + fuif_encode, encoding.cpp:737-743, 455-573.  Returns a malloc'ed buffer. */
+uint8_t *fo_encode(fo_image *img, const fo_enc_options *opt, size_t *nbytes) {
+    *nbytes = 0;
+    if (img->error) return NULL;
+    log4k_init();
+    srand(1);       /* the reference process calls rand() (encoding.cpp:185) from its initial state */
+    fo_recompute_minmax(img);
+    int downscales[6];
+    recompute_downscales(img, downscales);
+    chance_table *table = (chance_table *)malloc(sizeof(chance_table));
+    build_table(table, (uint32_t)opt->maniac_alpha, (unsigned)(4096 - opt->maniac_cutoff));
+
+    oblob real = {0};       /* FileIO: plain appends (no bytes_used quirk): only `pos` bytes are output */
+    const char *magic = "FUIF";
+    for (int k = 0; k < 4; k++) ob_putc(&real, magic[k]);
+    int nb_channels = img->real_nb_channels;
+    ob_varint(&real, (size_t)(nb_channels + '0'), 1);
+    int bit_depth = 1, maxval = 1;
+    while (maxval < img->maxval) { bit_depth++; maxval = maxval * 2 + 1; }
+    ob_varint(&real, (size_t)(bit_depth + '&'), 1);
+    ob_varint(&real, (size_t)(img->w - 1), 1);
+    ob_varint(&real, (size_t)(img->h - 1), 1);
+    ob_varint(&real, (size_t)img->colormodel, 1);
+    ob_varint(&real, (size_t)opt->max_properties, 1);
+    oblob io = {0};
+    int ok = 1;
+    if (nb_channels >= 1) {
+        ob_varint(&io, (size_t)img->ntr, 1);
+        for (int i = 0; i < img->ntr; i++) {
+            const int id = img->tr[i].id;
+            const int has_params = (id == FO_SUBSAMPLE || id == FO_PALETTE || id == FO_SQUEEZE || id == FO_DCT || id == 8 || id == 9 || id == 10);
+            const int np = has_params ? img->tr[i].np : 0;
+            ob_varint(&io, (size_t)((np << 4) + id), 1);
+            for (int j = 0; j < np; j++) ob_varint(&io, (size_t)img->tr[i].p[j], 1);
+        }
+        nb_channels = img->nch;
+        long long responsive_offsets[5] = {-1, -1, -1, -1, -1};
+        for (int i = 0; i < nb_channels && ok; i++) {
+            if (!img->ch[i].w || !img->ch[i].h) continue;
+            int predictor = 0;
+            if (opt->npred > i) predictor = opt->predictor[i]; else if (opt->npred > 0) predictor = opt->predictor[opt->npred - 1];
+            int j = i;
+            tree t = {0};
+            tree_push(&t);          /* Tree(): one leaf */
+            size_t header_pos = 0;
+            if (!opt->compress) {
+                ok = encode_channels(&io, &t, opt, table, predictor, i, j, img, &header_pos, 0, 0);
+                free(t.n);
+                continue;
+            }
+            for (int s = 1; s < 5; s++) if (j > downscales[s] && j < downscales[s + 1]) j = downscales[s + 1];
+            for (int k = i + 1; k <= j; k++) if (img->ch[i].w != img->ch[k].w || img->ch[i].h != img->ch[k].h) { j = k - 1; break; }
+            if (opt->max_group > 0 && j > i + opt->max_group - 1) j = i + opt->max_group - 1;
+            ok = encode_channels(NULL, &t, opt, table, predictor, i, j, img, &header_pos, 1, 1);
+            if (!ok) { free(t.n); break; }
+            const size_t before = io.pos;
+            ok = encode_channels(&io, &t, opt, table, predictor, i, j, img, &header_pos, 0, 1);
+            if (!ok) { free(t.n); break; }
+            size_t after = io.pos;
+            float bits = (float)(after - header_pos) * 8.0f, pixels = 0.0f, ubits = 0.0f;
+            for (int k = i; k <= j; k++) {
+                float chpixels = (float)(img->ch[k].w * img->ch[k].h);
+                float ubpp = (float)(ilog2u((uint32_t)(img->ch[k].maxval - img->ch[k].minval)) + 1);
+                pixels += chpixels;
+                if (img->ch[k].maxval > img->ch[k].minval) ubits += chpixels * ubpp;
+            }
+            if (ubits > 0.0f) ubits += 16;
+            (void)pixels;
+            if (bits >= ubits) {
+                io.pos = before;
+                ok = encode_channels(&io, &t, opt, table, predictor, i, j, img, &header_pos, 0, 0);
+                after = io.pos;
+            }
+            for (int s = 0; s < 5; s++) if (downscales[s] >= i && downscales[s] <= j) responsive_offsets[s] = (long long)after;
+            free(t.n);
+            i = j;
+        }
+        long long relative_offset = 0;
+        for (int s = 0; s < 5; s++) {
+            if (responsive_offsets[s] < 0) responsive_offsets[s] = (long long)io.pos;
+            long long offset = responsive_offsets[s] - relative_offset;
+            ob_varint(&real, (size_t)offset, 1);        /* TRUNCATION_OFFSET_RESOLUTION == 1 */
+            relative_offset = responsive_offsets[s];
+        }
+    }
+    free(table);
+    if (!ok) { free(real.data); free(io.data); return NULL; }
+    /* realio gets every byte of the blob up to bytes_used (one past the last byte written, see ob_putc) */
+    const size_t n = real.pos + io.used;
+    uint8_t *outb = (uint8_t *)malloc(n ? n : 1);
+    memcpy(outb, real.data, real.pos);
+    if (io.used) memcpy(outb + real.pos, io.data, io.used);
+    free(real.data); free(io.data);
+    *nbytes = n;
+    return outb;
+}
+void fo_free(void *p) { free(p); }

@@ -74,4 +74,21 @@ void fo_recompute_minmax(fo_image *img);
 #ifdef __cplusplus
 }
 #endif
+
+/* ---- encoder (test infrastructure for the encode-side rows; reference encoding/encoding.cpp:455-573, 74-207) ----
+ * fuif_prepare_encode + fuif_encode of `img` (transformed planes + transform list) with the reference's two-pass MANIAC
+ * tree learning.  Mutates channel ranges / zero like the reference does.  Returns a malloc'ed buffer (fo_free). */
+typedef struct {
+    float nb_repeats;           /* 0.5 */
+    int max_properties;         /* 12 */
+    int maniac_cutoff;          /* 6 */
+    int maniac_alpha;           /* 0x0d000000 */
+    int compress;               /* 1 */
+    int max_group;              /* -1 */
+    int npred;
+    const int *predictor;
+} fo_enc_options;
+uint8_t *fo_encode(fo_image *img, const fo_enc_options *opt, size_t *nbytes);
+void fo_free(void *p);
+
 #endif

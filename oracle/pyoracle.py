@@ -33,6 +33,12 @@ def have_ref() -> bool:
     return os.path.exists(REF_DRIVER) and os.access(REF_DRIVER, os.X_OK)
 
 
+class EncOptions(C.Structure):
+    """fo_enc_options (oracle/fuif_oracle.h) = the encode half of fuif_options, reference encoding/encoding.h:32-59."""
+    _fields_ = [("nb_repeats", C.c_float), ("max_properties", C.c_int), ("maniac_cutoff", C.c_int), ("maniac_alpha", C.c_int),
+                ("compress", C.c_int), ("max_group", C.c_int), ("npred", C.c_int), ("predictor", C.POINTER(C.c_int))]
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -57,6 +63,9 @@ def lib():
         L.fo_undo_transforms.argtypes = [C.c_void_p, C.c_int]
         L.fo_do_transform.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int]
         L.fo_recompute_minmax.argtypes = [C.c_void_p]
+        L.fo_encode.restype = C.c_void_p
+        L.fo_encode.argtypes = [C.c_void_p, C.POINTER(EncOptions), C.POINTER(C.c_size_t)]
+        L.fo_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -178,6 +187,20 @@ class OracleImage:
 
     def recompute_minmax(self) -> None:
         lib().fo_recompute_minmax(self.h)
+
+    def encode(self, predictor=(), nb_repeats: float = 0.5, max_properties: int = 12, cutoff: int = 6, alpha: int = 0x0d000000,
+               compress: bool = True, max_group: int = -1) -> bytes:
+        """fuif_prepare_encode + fuif_encode of the (already transformed) image, reference encoding/encoding.cpp:737-743, 455-573."""
+        pred = (C.c_int * max(1, len(predictor)))(*predictor)
+        opt = EncOptions(nb_repeats, max_properties, cutoff, alpha, 1 if compress else 0, max_group, len(predictor), pred)
+        n = C.c_size_t(0)
+        ptr = lib().fo_encode(self.h, C.byref(opt), C.byref(n))
+        if not ptr:
+            raise RuntimeError("oracle fo_encode failed")
+        try:
+            return C.string_at(ptr, n.value)
+        finally:
+            lib().fo_free(ptr)
 
     def to_plane_image(self) -> PlaneImage:
         L = lib()
