@@ -75,9 +75,11 @@ def prepare_image(name: str, seed_offset: int = 0, want_index: bool = True) -> d
             import torch
             if torch.cuda.is_available():       # one sequential decode by the library itself
                 from fuif_b200 import api
-                seq = api.fuif_decode(data)
+                ictx = api.Context(torch.cuda.current_device())      # this rank's GPU (N ranks must not all queue on device 0)
+                seq = api.fuif_decode(data, ctx=ictx)
                 offs_, first_ = seq.group_index()
                 del seq
+                ictx.close()
                 j = {"offsets": [int(a) for a in offs_], "first": [int(b) for b in first_], "source": "fb_image_group_index", "decode_s": time.perf_counter() - t0}
             else:                               # build container without a GPU
                 from oracle import pyoracle as po
@@ -107,7 +109,8 @@ def prepare_images(name: str, seed_offsets, want_index: bool = True, workers: in
             from fuif_b200 import api
             t0 = time.perf_counter()
             datas = [open(_paths(name, WORKLOADS[name][4] + u)[1], "rb").read() for u in need]
-            for u, im in zip(need, api.fuif_decode_batch(datas)):
+            ictx = api.Context(torch.cuda.current_device())
+            for u, im in zip(need, api.fuif_decode_batch(datas, ctx=ictx)):
                 offs_, first_ = im.group_index()
                 idx = _paths(name, WORKLOADS[name][4] + u)[2]
                 with open(idx, "w") as f:
