@@ -64,3 +64,42 @@ def test_encoder_matches_reference_file(oracle, case):
     back.undo_transforms(0)
     if not any(a == "-q" for a in opts):
         assert np.array_equal(back.pixels(), pix)
+
+
+# Direct comparison with the unmodified reference where it is available (the build container): option combinations the
+# golden cases do not cover -- several channels per group (-G), more / fewer learning iterations (-I), fewer reference
+# properties (-E), other predictors, a 10-bit image.
+LIVE = [
+    ("g3", 90, 70, 3, 255, 21, ["-G", "3"]),
+    ("gall", 64, 40, 3, 255, 22, ["-S", "0", "-G", "8"]),
+    ("i2", 72, 56, 3, 255, 23, ["-I", "2"]),
+    ("i0", 48, 48, 3, 255, 24, ["-I", "0"]),
+    ("e4", 100, 60, 3, 255, 25, ["-E", "4"]),
+    ("p6", 66, 50, 3, 255, 26, ["-P", "6630"]),
+    ("bits10", 80, 64, 3, 1023, 27, []),
+    ("gray16", 50, 70, 1, 16383, 28, ["-G", "2"]),
+]
+
+
+@pytest.mark.parametrize("case", LIVE, ids=[c[0] for c in LIVE])
+def test_encoder_matches_live_reference(oracle, case, tmp_path):
+    po = oracle
+    if not po.have_ref():
+        pytest.skip("oracle/_ref/ref_driver not built (needs /root/reference)")
+    from fuif_b200.synth import synth_image, write_pnm
+    name, w, h, c, maxval, seed, opts = case
+    pix = synth_image(w, h, c, maxval, seed)
+    pnm, out = str(tmp_path / "in.pnm"), str(tmp_path / "x.fuif")
+    write_pnm(pnm, pix, maxval)
+    po.ref_run("encode", pnm, out, *opts)
+    ref = open(out, "rb").read()
+    final = po.OracleImage.decode(ref).to_plane_image()         # only its transform list is used
+    oi = po.OracleImage.from_pixels(pix, maxval)
+    oi.recompute_minmax()
+    for tid, params in final.transforms:
+        assert oi.do_transform(tid, params if tid in (4, 5) else [])
+    o = _options(opts, c, final.transforms)
+    mine = oi.encode(predictor=o["predictor"], nb_repeats=o["nb_repeats"], max_properties=o["max_properties"], compress=o["compress"],
+                     max_group=o["max_group"])
+    assert len(mine) == len(ref), (len(mine), len(ref))
+    assert mine[:-1] == ref[:-1]
