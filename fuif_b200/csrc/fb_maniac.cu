@@ -18,7 +18,16 @@
 // (see walker_main).  Groups the walkers cannot serve fall back to decode_row (one warp, lane k owns property k).
 // Streams are handed out through an atomic ticket so that a stream only ever waits for lower-numbered streams (row
 // wavefront on the planes it back-references), which are guaranteed to be running already.
+// The device part of this file is also compiled, unchanged, for the CPU execution-model emulator of the test tier
+// (tests/emu/emu_maniac.cpp, -DFB_EMULATE): the few places where CUDA-only constructs need a stand-in are marked FB_EMULATE.
+#ifdef FB_EMULATE
+#include "maniac_emu_shim.h"
+#define FB_SPIN() fb_emu_yield()
+#else
 #include "fb_common.cuh"
+#define FB_SPIN()
+#define FB_DYN_SMEM_DECL(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
 
 #include <stddef.h>
 #include <stdlib.h>
@@ -85,12 +94,17 @@ struct Params {
 __device__ __forceinline__ int s16(int x) { return (int)(short)x; }
 __device__ __forceinline__ int ilog2u(unsigned l) { return l == 0 ? 0 : 31 - __clz(l); }      // maniac/util.h:33-36
 
+#ifdef FB_EMULATE
+__device__ __forceinline__ void st_release(int *p, int v) { *(volatile int *)p = v; }
+__device__ __forceinline__ int ld_acquire(const int *p) { return *(const volatile int *)p; }
+#else
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ int ld_acquire(const int *p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+#endif
 
 // ---- byte reader with FileIO end-of-stream rules (fileio.h:33-81) ------------------------------------------
 // `pos` counts consumed bytes (what ftell() reports); `win` caches up to four upcoming bytes, MSB first.
@@ -450,11 +464,15 @@ __device__ __forceinline__ uint16_t *leaf_lookup(const LeafStore &ls, int leaf, 
 // One row of a channel in the "slow track" (encoding.cpp:388-421), 32 pixels at a time.
 // Lane roles: lane k < nref holds reference property k, lane nref+j holds non-reference property j (0..12).
 // Returns through `rac` (meaningful in lane 0 only).
+#ifdef FB_EMULATE
+__device__ __forceinline__ uint4 lds128(unsigned addr) { uint4 v; memcpy(&v, fb_emu_smem(addr), 16); return v; }
+#else
 __device__ __forceinline__ uint4 lds128(unsigned addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
+#endif
 // Chunk prologue (lanes = the 32 pixels x0..x0+31 of row y): neighbours from the rows above, reference properties
 // (precompute_references, context_predict.h:233-289) and every property that does not depend on `left`, written to
 // cprop[lane][...].  All lanes of the decoder warp call it.
@@ -577,6 +595,16 @@ __shared__ unsigned s_cfg[4];
 static_assert(sizeof(Mail) <= kMailBytes, "Mail layout");
 
 #define COMPILER_FENCE() asm volatile("" ::: "memory")
+#ifdef FB_EMULATE
+__device__ __forceinline__ int lds32(unsigned addr) { int v; memcpy(&v, fb_emu_smem(addr), 4); return v; }
+__device__ __forceinline__ unsigned lds32v(unsigned addr) { fb_emu_yield(); unsigned v; memcpy(&v, fb_emu_smem(addr), 4); return v; }   // polled words
+__device__ __forceinline__ uint2 lds64(unsigned addr) { uint2 v; memcpy(&v, fb_emu_smem(addr), 8); return v; }
+__device__ __forceinline__ unsigned lds16(unsigned addr) { unsigned short v; memcpy(&v, fb_emu_smem(addr), 2); return v; }
+__device__ __forceinline__ void sts16(unsigned addr, unsigned v) { const unsigned short h = (unsigned short)v; memcpy(fb_emu_smem(addr), &h, 2); }
+__device__ __forceinline__ void sts32v(unsigned addr, unsigned v) { memcpy(fb_emu_smem(addr), &v, 4); }
+__device__ __forceinline__ uint2 lds64v(unsigned addr) { fb_emu_yield(); uint2 v; memcpy(&v, fb_emu_smem(addr), 8); return v; }
+__device__ __forceinline__ void sts64v(unsigned addr, unsigned x, unsigned y) { const uint2 v = {x, y}; memcpy(fb_emu_smem(addr), &v, 8); }
+#else
 __device__ __forceinline__ int lds32(unsigned addr) {
     int v;
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -605,6 +633,7 @@ __device__ __forceinline__ uint2 lds64v(unsigned addr) {
     return v;
 }
 __device__ __forceinline__ void sts64v(unsigned addr, unsigned x, unsigned y) { asm volatile("st.volatile.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(x), "r"(y) : "memory"); }
+#endif
 constexpr int kLdRowStride = 9;     // words per walker lane: its 7 left-dependent property values (+ padding)
 
 // Shared-memory accesses of one warp are performed in program order and there is no cache between the warps of a block,
@@ -658,7 +687,7 @@ __device__ void walker_main(Mail *mail, const int *cprop2 /* [2][32][kPropStride
         int slot = r;                               // r < g <= K
         for (int j = r; j < w; j += g) {
             if (j >= K) while (mail->progress <= y * w + j - K) __nanosleep(sleep_ns);     // the ring slot is free once pixel j - K has been decoded
-            while (mail->prol_ready < y * nchunks_w + (j >> 5)) { }
+            while (mail->prol_ready < y * nchunks_w + (j >> 5)) { FB_SPIN(); }
             __threadfence_block();          // acquire: the property rows read below were written before prol_ready was posted
             COMPILER_FENCE();
             const int *pp = cprop2 + (((j >> 5) & 1) * 32 + (j & 31)) * kPropStride;
@@ -703,9 +732,11 @@ __device__ void walker_main(Mail *mail, const int *cprop2 /* [2][32][kPropStride
             }
             sts64v(cand_s + (unsigned)(slot * kMaxCand + 32 * b + lane) * 8u, ((tagrow | (unsigned)(j + 1)) << 16) | ((unsigned)T & 0xffffu), ry);
             if (pf_leaves && (ry >> 30) < 2u) {     // pull the chances of the leaves this candidate leads to into L1 (a load whose
+#ifndef FB_EMULATE
                 unsigned dummy;                       // result nobody waits for), ahead of the decoder's cache miss
                 asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(dummy) : "l"(pf_leaves + ((size_t)(ry & 0x7fffu) << pf_shift)));
                 if (ry >> 30) asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(dummy) : "l"(pf_leaves + ((size_t)((ry >> 15) & 0x7fffu) << pf_shift)));
+#endif
             }
             slot += g;
             if (slot >= K) slot -= K;
@@ -804,9 +835,13 @@ exp_done:;
 }
 
 __device__ __forceinline__ uint4 ldg128(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
+#ifdef FB_EMULATE
+__device__ __forceinline__ void sts128(unsigned addr, const uint4 &v) { memcpy(fb_emu_smem(addr), &v, 16); }
+#else
 __device__ __forceinline__ void sts128(unsigned addr, const uint4 &v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+#endif
 // shared-memory address of a leaf's chances (resident array, or a direct-mapped write-back cache over the global array) and its
 // first eight chances; with the cache, the chances are loaded together with the tag and loaded again only after a miss
 __device__ __forceinline__ unsigned leaf_addr_uniform(const RowState &R, unsigned leaf, uint4 &L) {
@@ -880,6 +915,9 @@ __device__ __noinline__ void row_ahead_loop() {
     unsigned slot = 0;
     for (int x0 = 0; x0 < w; x0 += 32) {
         const int cnt = min(32, w - x0);
+#ifdef FB_EMULATE
+        if (lane == 0)      // no SIMT lockstep in the emulator: the redundant lanes would see each other's chance updates
+#endif
         for (int i = 0; i < cnt; i++) {         // all lanes, identical values
             const int xx = x0 + i;
             const unsigned want = R.tagrow | (unsigned)(xx + 1);
@@ -894,6 +932,9 @@ __device__ __noinline__ void row_ahead_loop() {
                 while ((int)lds32v(prol_s) < y * ((w + 31) >> 5) + (xx >> 5)) { }
                 res = finish_walk(R.inner_s, res, cprop_s + (unsigned)((((xx >> 5) & 1) * 32 + (xx & 31)) * kPropStride) * 4u, left, leftleft, xx, y);
             }
+#ifdef FB_EMU_TRACE
+            if (getenv("FB_EMU_TRACE") && atoi(getenv("FB_EMU_TRACE")) == w * 1000 + R.ch->h) printf("[ahead] y %d x %d left %d leftleft %d kind %u leaf %u T %d\n", y, xx, left, leftleft, kind, res, (int)(short)(e.x & 0xffffu));
+#endif
             uint4 L;
             const unsigned leaf_s = leaf_addr_uniform(R, res, L);
             const int diff = fread_int<SIGN_MODE>(fr, leaf_s, L, tab_s, K);
@@ -909,10 +950,15 @@ __device__ __noinline__ void row_ahead_loop() {
     }
     // the coder's state goes back the way it came
     const unsigned rs = mail_s + (unsigned)offsetof(Mail, row);
+#ifdef FB_EMULATE
+    if (lane == 0)      // (only lane 0 ran the loop there)
+#endif
+    {
     sts32v(rs + (unsigned)offsetof(RowState, range), fr.range);
     sts32v(rs + (unsigned)offsetof(RowState, low), fr.low);
     sts32v(rs + (unsigned)offsetof(RowState, ones), fr.ones);
     sts32v(rs + (unsigned)offsetof(RowState, pos), fr.pos);
+    }
     __syncwarp();
 }
 
@@ -924,7 +970,7 @@ __device__ __forceinline__ void decode_row_ahead(int sign_mode, DImage &img, DCh
     chunk_prologue(img, ch, y, 0, refchan, nrefchan, nref, sm.cprop, lane);
     if (w > 32) chunk_prologue(img, ch, y, 32, refchan, nrefchan, nref, sm.cprop + 32 * kPropStride, lane);
     // every walker has read the previous command
-    if (lane < sm.nwalkers) { const int cur = mail->cmd_seq; while (mail->ack[lane] != cur) { } }
+    if (lane < sm.nwalkers) { const int cur = mail->cmd_seq; while (mail->ack[lane] != cur) { FB_SPIN(); } }
     __syncwarp();
     if (lane == 0) {
         const int zero = ch.zero, cmin = ch.minval, cmax = ch.maxval;
@@ -1020,6 +1066,9 @@ __device__ __forceinline__ void decode_row(DImage &img, DChan &ch, int y, int pr
                     const int v = __shfl_sync(0xffffffffu, mine, (int)(cur.x >> 16));
                     cur = (v > (int)cur.y) ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
                 }
+#ifdef FB_EMU_TRACE
+                if (lane == 0 && getenv("FB_EMU_TRACE") && atoi(getenv("FB_EMU_TRACE")) == w * 1000 + ch.h) printf("[plain] y %d x %d left %d leftleft %d leaf %u\n", y, xx, left, leftleft, cur.x & 0xffffu);
+#endif
                 uint16_t *lp = leaf_lookup(ls, (int)(cur.x & 0xffffu), lane);
                 if (lane == 0) diff = read_int(rac, sm.table, lp, mn, mx, ls.mant_base);
                 diff = __shfl_sync(0xffffffffu, diff, 0);
@@ -1288,7 +1337,7 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
                 publish_rows(ch, y + 1, lane);
             }
             if (helped) {       // stragglers (walks of candidate blocks nobody needed) must be over before the tree or the rings change
-                if (lane < sm.nwalkers) { const int cur = sm.mail->cmd_seq; while (sm.mail->done[lane] != cur) { } }
+                if (lane < sm.nwalkers) { const int cur = sm.mail->cmd_seq; while (sm.mail->done[lane] != cur) { FB_SPIN(); } }
                 __syncwarp();
             }
             if (P.debug && lane == 0) {
@@ -1307,7 +1356,7 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
 }
 
 __global__ void __launch_bounds__(512, 1) k_maniac_decode(Params P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FB_DYN_SMEM_DECL(smem_raw);
     // the warp index goes through a warp reduction so that the compiler knows it (and every shared-memory address derived
     // from it) is uniform across the warp: see RowState
     const int lane = threadIdx.x & 31, warp = (int)__reduce_max_sync(0xffffffffu, threadIdx.x >> 5);
@@ -1417,6 +1466,9 @@ void build_table(uint16_t *t /*[4096][2]*/, uint32_t factor, unsigned max_p) {
     for (unsigned i = 1; i < (unsigned)size; i++) t[i * 2 + 0] = (uint16_t)(size - t[(size - i) * 2 + 1]);
 }
 
+#ifdef FB_EMULATE
+}  // namespace  (the emulator harness, which includes this file, takes it from here)
+#else
 struct ManiacState {
     uint16_t *table_dev = nullptr, *meta_dev = nullptr;
     int cutoff = -1, alpha = -1;
@@ -1657,3 +1709,4 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
     }
     return rc;
 }
+#endif  // FB_EMULATE
