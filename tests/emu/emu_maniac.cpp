@@ -8,7 +8,7 @@
 
 extern "C" {
 
-// chdesc[nch][4] = w, h, hshift, vshift;  planes[nch] = w*h int16 each (outputs);  chout[nch][5] = minval, maxval, zero, q, holds samples
+// chdesc[nch][5] = w, h, hshift, vshift, q after meta_apply (what the library's host half takes from its channel list);  planes[nch] = w*h int16 each (outputs);  chout[nch][5] = minval, maxval, zero, q, holds samples
 // ngroups > 0: one stream per channel group (group_off / group_first), else one stream for the whole file
 // shape: 0 = one stream per block with 15 extra warps (single image), 1 = two streams per block with 7 extra warps each (batches)
 // returns the image status (0 = ok)
@@ -22,7 +22,7 @@ int emu_maniac_decode(const uint8_t *bytes, size_t nbytes, size_t body_pos, int 
     for (int i = 0; i < nch; i++) {
         DChan &d = ch[(size_t)i];
         memset(&d, 0, sizeof(d));
-        d.w = chdesc[4 * i]; d.h = chdesc[4 * i + 1]; d.hshift = chdesc[4 * i + 2]; d.vshift = chdesc[4 * i + 3];
+        d.w = chdesc[5 * i]; d.h = chdesc[5 * i + 1]; d.hshift = chdesc[5 * i + 2]; d.vshift = chdesc[5 * i + 3]; d.q = chdesc[5 * i + 4];
         d.group_off = -1;
         d.data = planes[i];
         if (!(d.w > 0 && d.h > 0)) { d.hdr_done = 1; d.rows_done = 0x7fffffff; }

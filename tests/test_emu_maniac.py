@@ -56,11 +56,11 @@ def emu_decode(po, data, indexed=True, shape=0, nblocks=1, smem_kib=226):
     (nbch, _bd, _w, _h, _cm, max_properties), _ = _varints(data, 4, 6)
     nbch -= ord('0')
     nch = len(pi.planes)
-    desc = (C.c_int * (4 * nch))()
+    desc = (C.c_int * (5 * nch))()
     planes = []
     ptrs = (C.c_void_p * nch)()
     for i, p in enumerate(pi.planes):
-        desc[4 * i:4 * i + 4] = [p.w, p.h, p.hshift, p.vshift]
+        desc[5 * i:5 * i + 5] = [p.w, p.h, p.hshift, p.vshift, p.q]     # (q of an all-zero plane is never in the stream: the channel list's q stays)
         a = np.full((max(p.h, 0), max(p.w, 0)), -12345, dtype=np.int16)
         planes.append(a)
         ptrs[i] = a.ctypes.data if a.size else None
@@ -88,7 +88,7 @@ def _check(po, data, **kw):
         assert np.array_equal(g[0], p.data), f"plane {i} ({p.w}x{p.h}) differs"
 
 
-SMALL = ["odd", "tiny", "one", "gray", "nosq", "pred", "e0", "unc", "tall", "wide"]
+SMALL = ["odd", "tiny", "one", "gray", "nosq", "pred", "e0", "unc", "tall", "wide", "dct", "dctodd", "lossyq", "rgba14", "sq128"]
 
 
 @pytest.mark.parametrize("name", SMALL)
@@ -101,7 +101,7 @@ def test_kernel_source_decodes_golden_sequential(oracle, name):
     _check(oracle, bytes(load_golden(name)["fuif"]), indexed=False)
 
 
-@pytest.mark.parametrize("name", ["odd", "nosq"])
+@pytest.mark.parametrize("name", ["odd", "nosq", "dct", "sq128"])
 def test_batch_launch_shape_and_two_blocks(oracle, name):
     """two streams per block with 5 walkers each, two co-resident blocks (streams wait for planes decoded by the other block)"""
     _check(oracle, bytes(load_golden(name)["fuif"]), indexed=True, shape=1, nblocks=2)
