@@ -11,10 +11,11 @@ extern "C" {
 // chdesc[nch][5] = w, h, hshift, vshift, q after meta_apply (what the library's host half takes from its channel list);  planes[nch] = w*h int16 each (outputs);  chout[nch][5] = minval, maxval, zero, q, holds samples
 // ngroups > 0: one stream per channel group (group_off / group_first), else one stream for the whole file
 // shape: 0 = one stream per block with 15 extra warps (single image), 1 = two streams per block with 7 extra warps each (batches)
+// bytes_to_load: 0 = everything, else the responsive truncation point (-R k)
 // returns the image status (0 = ok)
 int emu_maniac_decode(const uint8_t *bytes, size_t nbytes, size_t body_pos, int max_properties, int n_orig, int nch, const int *chdesc,
                       int16_t **planes, int *chout, int ngroups, const long long *group_off, const int *group_first, int shape, int nblocks,
-                      int cutoff, int alpha, int smem_kib, int debug) {
+                      int cutoff, int alpha, int smem_kib, int debug, size_t bytes_to_load) {
     std::vector<uint8_t> file(nbytes + 16, 0);
     memcpy(file.data(), bytes, nbytes);
     std::vector<DChan> ch((size_t)nch);
@@ -29,7 +30,7 @@ int emu_maniac_decode(const uint8_t *bytes, size_t nbytes, size_t body_pos, int 
         maxw = std::max(maxw, d.w);
     }
     DImage img;
-    img.bytes = file.data(); img.nbytes = nbytes; img.bytes_to_load = 0; img.ch = ch.data(); img.nch = nch;
+    img.bytes = file.data(); img.nbytes = nbytes; img.bytes_to_load = bytes_to_load; img.ch = ch.data(); img.nch = nch;
     img.max_properties = max_properties; img.n_orig = n_orig; img.status = 0;
     std::vector<DStream> streams;
     if (ngroups > 0) {

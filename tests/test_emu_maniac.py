@@ -30,7 +30,7 @@ def lib():
         L = C.CDLL(LIB)
         L.emu_maniac_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int,
-                                        C.c_int, C.c_int]
+                                        C.c_int, C.c_int, C.c_size_t]
         _lib = L
     return _lib
 
@@ -49,11 +49,17 @@ def _varints(data, pos, n):
     return out, pos
 
 
-def emu_decode(po, data, indexed=True, shape=0, nblocks=1, smem_kib=226):
+def emu_decode(po, data, indexed=True, shape=0, nblocks=1, smem_kib=226, preview=-1):
     """Returns (status, [(plane array or None, minval, maxval, zero, q)]) for the channel list of the file."""
-    ref, offs = po.OracleImage.decode(data, want_offsets=True)
+    full, offs = po.OracleImage.decode(data, want_offsets=True)
+    ref = full if preview < 0 else po.OracleImage.decode(data, preview=preview)
     pi = ref.to_plane_image()
-    (nbch, _bd, _w, _h, _cm, max_properties), _ = _varints(data, 4, 6)
+    (nbch, _bd, _w, _h, _cm, max_properties), pos = _varints(data, 4, 6)
+    btl = 0
+    if preview >= 0:        # responsive truncation points, encoding.cpp:641-650
+        rel, pos = _varints(data, pos, 5)
+        btl = sum(rel[:preview + 1]) + pos
+        offs = [o for o in offs if o[0] < btl]      # what the library's host half does with a group index
     nbch -= ord('0')
     nch = len(pi.planes)
     desc = (C.c_int * (5 * nch))()
@@ -69,14 +75,14 @@ def emu_decode(po, data, indexed=True, shape=0, nblocks=1, smem_kib=226):
     goff = (C.c_longlong * max(1, ng))(*[o for o, _ in offs][:ng])
     gfirst = (C.c_int * max(1, ng))(*[f for _, f in offs][:ng])
     st = lib().emu_maniac_decode(data, len(data), offs[0][0], max_properties, nbch, nch, desc, ptrs, chout, ng, goff, gfirst, shape, nblocks, 6, 0x0d000000,
-                                 smem_kib, 0)
+                                 smem_kib, 0, btl)
     out = []
     for i in range(nch):
         out.append((planes[i] if chout[5 * i + 4] else None, chout[5 * i], chout[5 * i + 1], chout[5 * i + 2], chout[5 * i + 3]))
     return st, out, pi
 
 
-def _check(po, data, **kw):
+def _check(po, data, meta=True, **kw):
     st, got, pi = emu_decode(po, data, **kw)
     assert st == 0
     for i, (p, g) in enumerate(zip(pi.planes, got)):
@@ -84,7 +90,8 @@ def _check(po, data, **kw):
             assert g[0] is None, f"plane {i} decoded by the kernel but not by the oracle"
             continue
         assert g[0] is not None, f"plane {i} missing"
-        assert (g[1], g[2], g[4]) == (p.minval, p.maxval, p.q), f"plane {i} range / q: {(g[1], g[2], g[4])} vs {(p.minval, p.maxval, p.q)}"
+        if meta:
+            assert (g[1], g[2], g[4]) == (p.minval, p.maxval, p.q), f"plane {i} range / q: {(g[1], g[2], g[4])} vs {(p.minval, p.maxval, p.q)}"
         assert np.array_equal(g[0], p.data), f"plane {i} ({p.w}x{p.h}) differs"
 
 
@@ -110,3 +117,12 @@ def test_batch_launch_shape_and_two_blocks(oracle, name):
 def test_leaf_cache_path(oracle):
     """a shared-memory budget too small for the leaves of the larger groups: direct-mapped write-back leaf cache"""
     _check(oracle, bytes(load_golden("sq128")["fuif"]), indexed=True, smem_kib=72)
+
+
+@pytest.mark.parametrize("name", ["odd", "gray", "sq128", "dct"])
+@pytest.mark.parametrize("preview", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("indexed", [True, False], ids=["indexed", "sequential"])
+def test_responsive_truncation(oracle, name, preview, indexed):
+    """-R k: the stream stops at a responsive offset (encoding.cpp:704-716): planes beyond it stay undecoded, a plane cut in
+    the middle keeps its initial fill"""
+    _check(oracle, bytes(load_golden(name)["fuif"]), meta=False, indexed=indexed, preview=preview)
