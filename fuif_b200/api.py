@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 
 import numpy as np
 
@@ -47,6 +47,11 @@ class DecodeOptions(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("preview", "maniac_cutoff", "maniac_alpha", "reserved")]
 
 
+class EncodeOptions(C.Structure):
+    _fields_ = [("nb_repeats", C.c_float), ("max_properties", C.c_int32), ("maniac_cutoff", C.c_int32), ("maniac_alpha", C.c_int32),
+                ("compress", C.c_int32), ("max_group", C.c_int32), ("n_predictors", C.c_int32), ("predictor", C.POINTER(C.c_int32))]
+
+
 # every symbol include/fuif_b200.h declares (tests/test_abi.py checks that the library exports all of them)
 ABI_SYMBOLS = [
     "fb_ctx_create", "fb_ctx_destroy", "fb_last_error", "fb_ctx_synchronize", "fb_ctx_launch_count",
@@ -55,6 +60,7 @@ ABI_SYMBOLS = [
     "fb_image_plane_device_ptr", "fb_image_download_plane", "fb_image_download_interleaved",
     "fb_image_undo_transforms", "fb_image_do_transform", "fb_image_recompute_minmax",
     "fb_decode_to_pixels", "fb_peek_header", "fb_ctx_set_option", "fb_ctx_counter", "fb_ctx_timing_report",
+    "fb_encode", "fb_free",
 ]
 
 _lib = None
@@ -102,16 +108,24 @@ def load_library():
     L.fb_image_recompute_minmax.argtypes = [vp]
     L.fb_decode_to_pixels.argtypes = [vp, vp, C.c_size_t, C.POINTER(DecodeOptions), i64p, i32p, C.c_int, C.c_int, vp, C.c_size_t]
     L.fb_peek_header.argtypes = [vp, C.c_size_t, C.POINTER(ImageInfo)]
+    L.fb_encode.argtypes = [vp, vp, C.POINTER(EncodeOptions), C.POINTER(vp), C.POINTER(C.c_size_t), i64p, i32p, C.c_int, C.POINTER(C.c_int)]
+    L.fb_free.argtypes = [vp]
+    L.fb_free.restype = None
     _lib = L
     return L
 
 
 @dataclass
 class fuif_options:
-    """Decode-side members of struct fuif_options (reference encoding/encoding.h:32-59)."""
+    """struct fuif_options (reference encoding/encoding.h:32-59); the encode-side members are read by fuif_encode only."""
     preview: int = -1
     maniac_cutoff: int = 6
     maniac_alpha: int = 0x0d000000
+    nb_repeats: float = 0.5
+    max_properties: int = 12
+    compress: bool = True
+    max_group: int = -1
+    predictor: list = field(default_factory=list)
 
     def _c(self) -> DecodeOptions:
         return DecodeOptions(self.preview, self.maniac_cutoff, self.maniac_alpha, 0)
@@ -377,6 +391,36 @@ def fuif_decode(data: bytes, options: fuif_options = default_fuif_options, ctx: 
         ptr, size = buf.ctypes.data, buf.size
     ctx.check(ctx.lib.fb_decode(ctx.h, ptr, size, C.byref(opts), arr, farr, n, C.byref(h)), "fb_decode")
     return Image(ctx, h)
+
+
+def fuif_encode(image: "Image", options: fuif_options = default_fuif_options, want_index: bool = False):
+    """fuif_prepare_encode + fuif_encode (reference encoding/encoding.cpp:737-743, 455-573): the .fuif bytes of an image whose
+    forward transforms have been applied; with want_index also (offsets, first channels) of the channel groups, the sidecar
+    index fuif_decode() takes."""
+    ctx = image.ctx
+    pred = (C.c_int32 * max(1, len(options.predictor)))(*options.predictor)
+    eo = EncodeOptions(options.nb_repeats, options.max_properties, options.maniac_cutoff, options.maniac_alpha, 1 if options.compress else 0,
+                       options.max_group, len(options.predictor), pred)
+    out = C.c_void_p()
+    n = C.c_size_t()
+    cap = 4096
+    offs = (C.c_int64 * cap)()
+    first = (C.c_int32 * cap)()
+    ng = C.c_int()
+    ctx.check(ctx.lib.fb_encode(ctx.h, image._handle, C.byref(eo), C.byref(out), C.byref(n), offs, first, cap, C.byref(ng)), "fb_encode")
+    try:
+        data = C.string_at(out, n.value)
+    finally:
+        ctx.lib.fb_free(out)
+    if want_index:
+        return data, (list(offs[:ng.value]), list(first[:ng.value]))
+    return data
+
+
+def fuif_encode_file(filename: str, image: "Image", options: fuif_options = default_fuif_options) -> None:
+    """fuif_encode_file (reference encoding/encoding.cpp:722-735)."""
+    with open(filename, "wb") as f:
+        f.write(fuif_encode(image, options))
 
 
 def fuif_decode_file(filename: str, options: fuif_options = default_fuif_options, ctx: Context | None = None, group_index=None) -> Image:

@@ -21,7 +21,9 @@
 // at its own offset.
 //
 // STATUS (round 1): validated against the oracle encoder (itself byte-exact against the reference's files) under the CPU
-// execution-model emulator, tests/test_emu_maniac_enc.py; not yet run on a GPU, and not yet reachable through the C ABI.
+// execution-model emulator together with the host side (fb_encode_host.h), tests/test_emu_maniac_enc.py: whole files are
+// identical.  fb_encode() below is the C-ABI entry; it was written after the round's GPU time had run out, so its first run
+// on a GPU is the round-end test tier (tests/test_zz_gpu_encode.py).
 #ifdef FB_EMULATE
 #include "maniac_emu_shim.h"
 #else
@@ -66,6 +68,7 @@ struct EGroup {
     // output
     unsigned char *out; unsigned out_cap;
     unsigned out_len, header_len;       // header_len: bytes before the entropy-coded part (header_pos - before, encoding.cpp)
+    unsigned attempt_len;               // length of the compressed form if it was rolled back (its tail stays in `out`), else 0
     int status;                         // 0 ok, 1 output buffer too small, 2 leaf pool exhausted, 3 bit depth
     int nnodes;
 };
@@ -382,6 +385,7 @@ __device__ void learn_symbol(const EParams &P, EGroup &g, const GroupCtx &G, int
             leaf = &g.leaves[li];
         }
     }
+    __syncwarp();       // everybody has compared the leaf's sizes before they change
     // the decisions: each touches a different chance, so there is no order among them; lane p adapts property p's virtual
     // chance and adds its cost, lane 31 does the same for the real chances
     unsigned char dec[40];
@@ -644,7 +648,7 @@ __global__ void __launch_bounds__(32) k_maniac_encode(EParams P) {
     EGroup &g = P.groups[gi];
     Sink s;
     s.p = g.out; s.cap = g.out_cap; s.len = 0; s.overflow = 0;
-    if (lane == 0) { g.status = 0; g.nnodes = 1; g.nodes[0].property = -1; g.nodes[0].child = 0; g.nodes[0].splitval = 0; g.header_len = 0; }
+    if (lane == 0) { g.status = 0; g.attempt_len = 0; g.nnodes = 1; g.nodes[0].property = -1; g.nodes[0].child = 0; g.nodes[0].splitval = 0; g.header_len = 0; }
     __syncwarp();
     bool ok = true;
     if (!g.compress) ok = encode_channels(P, g, s, false, false, lane);
@@ -663,6 +667,7 @@ __global__ void __launch_bounds__(32) k_maniac_encode(EParams P) {
             }
             if (ubits > 0.0f) ubits += 16;
             if (bits >= ubits) {
+                if (lane == 0) g.attempt_len = after;
                 s.len = 0; s.overflow = 0;
                 ok = encode_channels(P, g, s, false, false, lane);
             }
@@ -675,3 +680,172 @@ __global__ void __launch_bounds__(32) k_maniac_encode(EParams P) {
 }
 
 }  // namespace fbenc
+
+#ifndef FB_EMULATE
+// ---------------------------------------------------------------------------------------------------------------------------
+// C ABI: fb_encode = fuif_prepare_encode + fuif_encode (reference encoding/encoding.cpp:737-743, 455-573)
+// ---------------------------------------------------------------------------------------------------------------------------
+#include <new>
+
+#include "fb_encode_host.h"
+
+namespace {
+struct DevBuf {         // frees on scope exit
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 16); }
+};
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+}  // namespace
+
+extern "C" void fb_free(void *p) { free(p); }
+
+extern "C" int fb_encode(fb_ctx *ctx, fb_image *img, const fb_encode_options *opts, uint8_t **bytes_out, size_t *nbytes_out, int64_t *group_index,
+                         int32_t *group_first, int cap_groups, int *n_groups_out) {
+    using namespace fbenc;
+    namespace H = fbenc_host;
+    if (!ctx || !img || !bytes_out || !nbytes_out || img->ctx != ctx) return FB_ERR_INVALID;
+    *bytes_out = nullptr; *nbytes_out = 0;
+    if (n_groups_out) *n_groups_out = 0;
+    if (img->info.error) { ctx->err = "fb_encode: image carries an error"; return FB_ERR_INVALID; }
+    cudaSetDevice(ctx->device);
+    H::Options o;
+    if (opts) {
+        o.nb_repeats = opts->nb_repeats; o.max_properties = opts->max_properties; o.maniac_cutoff = opts->maniac_cutoff; o.maniac_alpha = opts->maniac_alpha;
+        o.compress = opts->compress != 0; o.max_group = opts->max_group;
+        if (opts->n_predictors > 0 && opts->predictor) o.predictor.assign(opts->predictor, opts->predictor + opts->n_predictors);
+    }
+    if (o.max_properties < 0 || o.max_properties > 18) { ctx->err = "fb_encode: max_properties > 18 is not supported (one lane per property)"; return FB_ERR_UNSUPPORTED; }
+    if (!(o.nb_repeats >= 0.0f) || o.nb_repeats > 64.0f) { ctx->err = "fb_encode: nb_repeats out of range"; return FB_ERR_INVALID; }
+    // fuif_prepare_encode: tight ranges (the downscale positions are computed by plan_groups / assemble)
+    int rc = fb_image_recompute_minmax(img);
+    if (rc) return rc;
+    const int nch = (int)img->ch.size();
+    std::vector<H::Plane> planes((size_t)nch);
+    std::vector<EChan> ech((size_t)nch);
+    for (int i = 0; i < nch; i++) {
+        fb_plane_desc &d = img->ch[(size_t)i].d;
+        const bool has = d.w > 0 && d.h > 0;
+        if (has && !img->ch[(size_t)i].dev) { ctx->err = "fb_encode: a plane has no samples"; return FB_ERR_INVALID; }
+        if (has && (long long)d.w * d.h > 0x7fffffffLL) { ctx->err = "fb_encode: plane too large"; return FB_ERR_UNSUPPORTED; }
+        H::Plane &p = planes[(size_t)i];
+        p.w = d.w; p.h = d.h; p.minval = d.minval; p.maxval = d.maxval; p.zero = d.zero; p.q = d.q; p.hshift = d.hshift; p.vshift = d.vshift;
+        p.hcshift = d.hcshift; p.vcshift = d.vcshift;
+        if (has && !(p.minval == 0 && p.maxval == 0)) { H::chan_setzero(p); d.zero = p.zero; }      // encoding.cpp:118 (zero is `mutable` there)
+        EChan &e = ech[(size_t)i];
+        e.w = p.w; e.h = p.h; e.minval = p.minval; e.maxval = p.maxval; e.zero = p.zero; e.q = p.q; e.hshift = p.hshift; e.vshift = p.vshift;
+        e.data = img->ch[(size_t)i].dev;
+    }
+    H::ImageInfo info;
+    info.w = img->info.w; info.h = img->info.h; info.maxval = img->info.maxval; info.colormodel = img->info.colormodel;
+    info.real_nb_channels = img->info.real_nb_channels; info.nb_channels = img->info.nb_channels; info.nb_meta_channels = img->info.nb_meta_channels;
+    std::vector<H::Transform> tr;
+    for (const FbXform &t : img->tr) tr.push_back(H::Transform{t.id, t.p});
+    long long nrand = 0;
+    std::vector<H::Group> groups;
+    if (info.real_nb_channels >= 1) groups = H::plan_groups(planes, info, o, &nrand);
+    const int ng = (int)groups.size();
+    std::vector<H::GroupBytes> gb((size_t)ng);
+    std::vector<std::vector<unsigned char>> host_bytes((size_t)ng);
+    if (ng) {
+        // tables
+        std::vector<uint16_t> table(4096 * 2), meta(4096 * 2), log4k(4097);
+        H::build_chance_table(table.data(), (uint32_t)o.maniac_alpha, (unsigned)(4096 - o.maniac_cutoff));
+        H::build_chance_table(meta.data(), 0xFFFFFFFFu / 19, 4096 - 2);
+        H::build_log4k(log4k.data());
+        std::vector<int> rnd((size_t)nrand + 1);
+        H::glibc_rand(rnd.data(), nrand);
+        // working memory of every group, carved from one allocation per kind
+        std::vector<EGroup> eg((size_t)ng);
+        std::vector<size_t> leaf_off((size_t)ng), out_off((size_t)ng);
+        size_t leaf_total = 0, out_total = 0;
+        for (int g = 0; g < ng; g++) {
+            const H::Group &G = groups[(size_t)g];
+            long long cap = G.learned + 1;          // a split needs a learned symbol
+            if (cap > kMaxNodes / 2) cap = kMaxNodes / 2;
+            if (cap < 2) cap = 2;
+            leaf_off[(size_t)g] = leaf_total; leaf_total += (size_t)cap;
+            long long tree_bytes = 24 * G.learned;
+            if (tree_bytes > (512 << 10)) tree_bytes = 512 << 10;
+            const size_t ocap = align_up((size_t)(4 * G.pixels + tree_bytes + 4096), 256);
+            if (ocap > 0xfffffff0u) { ctx->err = "fb_encode: group too large"; return FB_ERR_UNSUPPORTED; }
+            out_off[(size_t)g] = out_total; out_total += ocap;
+            EGroup &E = eg[(size_t)g];
+            memset(&E, 0, sizeof(E));
+            E.beginc = G.beginc; E.endc = G.endc; E.predictor = G.predictor; E.compress = o.compress ? 1 : 0; E.rand_off = G.rand_off;
+            E.leaf_cap = (int)cap; E.out_cap = (unsigned)ocap;
+        }
+        const size_t stack_ints = (size_t)8 * (kMaxNodes / 2 + 2);
+        DevBuf d_ch, d_groups, d_nodes, d_leaves, d_fleaves, d_stack, d_scr, d_out, d_tables, d_rnd;
+        const size_t tables_bytes = (4096 * 2 * 2 + 4104) * sizeof(uint16_t);
+        if (d_ch.alloc(sizeof(EChan) * (size_t)nch) != cudaSuccess || d_groups.alloc(sizeof(EGroup) * (size_t)ng) != cudaSuccess ||
+            d_nodes.alloc(sizeof(TNode) * kMaxNodes * (size_t)ng) != cudaSuccess || d_leaves.alloc(sizeof(LLeaf) * leaf_total) != cudaSuccess ||
+            d_fleaves.alloc(sizeof(uint16_t) * 32 * (kMaxNodes / 2) * (size_t)ng) != cudaSuccess || d_stack.alloc(sizeof(int) * stack_ints * (size_t)ng) != cudaSuccess ||
+            d_scr.alloc(sizeof(long long) * 160 * (size_t)ng) != cudaSuccess || d_out.alloc(out_total) != cudaSuccess || d_tables.alloc(tables_bytes) != cudaSuccess ||
+            d_rnd.alloc(sizeof(int) * rnd.size()) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->err = "fb_encode: out of device memory";
+            return FB_ERR_NOMEM;
+        }
+        for (int g = 0; g < ng; g++) {
+            EGroup &E = eg[(size_t)g];
+            E.nodes = (TNode *)d_nodes.p + (size_t)kMaxNodes * g;
+            E.leaves = (LLeaf *)d_leaves.p + leaf_off[(size_t)g];
+            E.fleaves = (uint16_t *)d_fleaves.p + (size_t)32 * (kMaxNodes / 2) * g;
+            E.stack = (int *)d_stack.p + stack_ints * g;
+            E.scr = (long long *)d_scr.p + (size_t)160 * g;
+            E.out = (unsigned char *)d_out.p + out_off[(size_t)g];
+        }
+        uint16_t *dt = (uint16_t *)d_tables.p;
+        FB_CUDA(ctx, cudaMemcpyAsync(d_ch.p, ech.data(), sizeof(EChan) * (size_t)nch, cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(ctx, cudaMemcpyAsync(d_groups.p, eg.data(), sizeof(EGroup) * (size_t)ng, cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(ctx, cudaMemcpyAsync(dt, table.data(), 8192 * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(ctx, cudaMemcpyAsync(dt + 8192, meta.data(), 8192 * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(ctx, cudaMemcpyAsync(dt + 16384, log4k.data(), 4097 * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(ctx, cudaMemcpyAsync(d_rnd.p, rnd.data(), sizeof(int) * rnd.size(), cudaMemcpyHostToDevice, ctx->stream));
+        // the tail a rolled-back attempt leaves must read as written, and unwritten bytes as zero
+        FB_CUDA(ctx, cudaMemsetAsync(d_out.p, 0, out_total, ctx->stream));
+        EParams P;
+        P.ch = (const EChan *)d_ch.p; P.nch = nch; P.groups = (EGroup *)d_groups.p; P.ngroups = ng; P.max_properties = o.max_properties;
+        P.nb_repeats = o.nb_repeats; P.table = dt; P.meta_table = dt + 8192; P.log4k = dt + 16384; P.rnd = (const int *)d_rnd.p; P.nrnd = nrand;
+        {   // the kernel's frame (property tables, decision lists) is larger than the default per-thread stack
+            cudaFuncAttributes fa;
+            size_t lim = 0;
+            FB_CUDA(ctx, cudaFuncGetAttributes(&fa, k_maniac_encode));
+            FB_CUDA(ctx, cudaDeviceGetLimit(&lim, cudaLimitStackSize));
+            if (lim < fa.localSizeBytes + 512) FB_CUDA(ctx, cudaDeviceSetLimit(cudaLimitStackSize, fa.localSizeBytes + 512));
+        }
+        k_maniac_encode<<<ng, 32, 0, ctx->stream>>>(P);
+        FB_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+        ctx->mark("k_maniac_encode");
+        FB_CUDA(ctx, cudaMemcpyAsync(eg.data(), d_groups.p, sizeof(EGroup) * (size_t)ng, cudaMemcpyDeviceToHost, ctx->stream));
+        FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int g = 0; g < ng; g++) {
+            const EGroup &E = eg[(size_t)g];
+            if (E.status == 3) { ctx->err = "fb_encode: sample range needs more than 15 bits (check_bit_depth, encoding.cpp:61-72)"; return FB_ERR_INVALID; }
+            if (E.status) { ctx->err = E.status == 1 ? "fb_encode: group output buffer too small" : "fb_encode: leaf pool exhausted"; return FB_ERR_UNSUPPORTED; }
+            if (E.attempt_len > E.out_cap) { ctx->err = "fb_encode: rolled-back attempt exceeds the output buffer"; return FB_ERR_UNSUPPORTED; }
+            const unsigned n = E.attempt_len > E.out_len ? E.attempt_len : E.out_len;
+            host_bytes[(size_t)g].resize(n ? n : 1);
+            if (n) FB_CUDA(ctx, cudaMemcpyAsync(host_bytes[(size_t)g].data(), E.out, n, cudaMemcpyDeviceToHost, ctx->stream));
+            gb[(size_t)g].bytes = host_bytes[(size_t)g].data();
+            gb[(size_t)g].out_len = E.out_len;
+            gb[(size_t)g].attempt_len = E.attempt_len;
+        }
+        FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    std::vector<int64_t> offs;
+    std::vector<uint8_t> file = H::assemble(info, tr, planes, o, groups, gb, &offs);
+    uint8_t *outp = (uint8_t *)malloc(file.size() ? file.size() : 1);
+    if (!outp) return FB_ERR_NOMEM;
+    if (!file.empty()) memcpy(outp, file.data(), file.size());
+    *bytes_out = outp; *nbytes_out = file.size();
+    if (n_groups_out) *n_groups_out = ng;
+    for (int g = 0; g < ng && g < cap_groups; g++) {
+        if (group_index) group_index[g] = offs[(size_t)g];
+        if (group_first) group_first[g] = groups[(size_t)g].beginc;
+    }
+    return FB_OK;
+}
+#endif  // !FB_EMULATE

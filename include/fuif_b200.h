@@ -165,6 +165,32 @@ FB_API int fb_image_do_transform(fb_image *img, int32_t id, const int32_t *param
 /* Replaces Image::recompute_minmax (image/image.h:127; Channel::actual_minmax, image.cpp:82-92). */
 FB_API int fb_image_recompute_minmax(fb_image *img);
 
+/* ---- fuif_encode --------------------------------------------------------------------------------------- */
+
+/* Mirrors struct fuif_options (reference encoding/encoding.h:32-59), encode-side members. */
+typedef struct fb_encode_options {
+    float nb_repeats;         /* 0.5: share of each plane's rows the tree is learned from (encoding.h:36)  */
+    int32_t max_properties;   /* 12; at most 18 here                                  (encoding.h:38)      */
+    int32_t maniac_cutoff;    /* 6                                                                         */
+    int32_t maniac_alpha;     /* 0x0d000000                                                                */
+    int32_t compress;         /* 1; 0 = plain binary coding of every sample           (encoding.h:41)      */
+    int32_t max_group;        /* -1 = as many same-size channels per group as the format allows            */
+    int32_t n_predictors;     /* per-channel predictor ids, the last one repeating    (encoding.h:44)      */
+    const int32_t *predictor;
+} fb_encode_options;
+
+/* Replaces fuif_prepare_encode() + fuif_encode<BlobIO>() / fuif_encode_file() (reference encoding/encoding.cpp:737-743,
+ * 455-573) on an image whose forward transforms have been applied (fb_image_do_transform): tightens the plane ranges,
+ * then learns and writes every channel group on the GPU (fuif_encode_channels, encoding.cpp:74-207: MANIAC tree
+ * learning, pruning, tree + sample coding; one warp per group, the groups concurrently) and assembles the container
+ * on the host.  The file is the reference encoder's byte for byte, including the row order its learning pass draws
+ * from libc rand() in a fresh process.  *bytes is malloc'ed: release it with fb_free().
+ * group_index / group_first (may be NULL; at most cap entries are written, *n_groups gets the count): the sidecar
+ * index fb_decode() takes -- the encoder knows it for free.  opts == NULL: the reference defaults. */
+FB_API int fb_encode(fb_ctx *ctx, fb_image *img, const fb_encode_options *opts, uint8_t **bytes, size_t *nbytes,
+              int64_t *group_index, int32_t *group_first, int cap, int *n_groups);
+FB_API void fb_free(void *p);
+
 /* ---- one-call convenience: file bytes in host memory -> pixels in host memory ------------------------------ */
 
 /* fuif_decode + undo_transforms + interleave, the path `fuif -d in.fuif out.ppm` takes (reference

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(HERE)
 EMU_DIR = os.path.join(HERE, "emu")
 LIB = os.path.join(EMU_DIR, "libfb_emu_maniac_enc.so")
 SRCS = [os.path.join(EMU_DIR, "emu_maniac_enc.cpp"), os.path.join(EMU_DIR, "cuemu.h"), os.path.join(EMU_DIR, "maniac_emu_shim.h"),
-        os.path.join(ROOT, "fuif_b200", "csrc", "fb_maniac_enc.cu")]
+        os.path.join(ROOT, "fuif_b200", "csrc", "fb_maniac_enc.cu"), os.path.join(ROOT, "fuif_b200", "csrc", "fb_encode_host.h")]
 _lib = None
 
 
@@ -33,6 +33,11 @@ def lib():
         L = C.CDLL(LIB)
         L.emu_maniac_encode.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_void_p), C.c_uint,
                                         C.POINTER(C.c_int), C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]
+        L.emu_fuif_encode.restype = C.c_longlong
+        L.emu_fuif_encode.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.c_float, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_longlong,
+                                      C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
+        L.emu_glibc_rand.argtypes = [C.c_void_p, C.c_longlong]
         _lib = L
     return _lib
 
@@ -180,3 +185,94 @@ def test_encode_kernel_matches_oracle_encoder(oracle, case):
     mine_file = ref[:offs[0][0]] + b"".join(bytes(outs[gi][:glen[3 * gi]]) for gi in range(ng))
     back = po.OracleImage.decode(mine_file + b"\0")
     po.compare_plane_images(back.to_plane_image(), dec.to_plane_image(), name + " decode of the kernel's output")
+
+
+ENC_CASES = list(CASES)
+
+
+def test_rand_restatement_matches_libc():
+    """the product tabulates libc rand() itself (glibc TYPE_3, seed 1): the learning pass visits the reference's rows"""
+    n = 5000
+    mine = np.zeros(n, dtype=np.int32)
+    lib().emu_glibc_rand(mine.ctypes.data, n)
+    assert np.array_equal(mine, libc_rand(n))
+
+
+@pytest.mark.parametrize("case", ENC_CASES, ids=lambda c: c[0])
+def test_encode_file_matches_oracle_encoder(oracle, case):
+    """fb_encode() end to end with the kernel emulated: the product's host side (group planning, rand() table, chance and
+    cost tables, container assembly with BlobIO's quirks) around the kernel must give the oracle encoder's file, every byte,
+    and the group index it returns must be the one a decode finds."""
+    po = oracle
+    name, w, h, c, maxval, seed, opts = case
+    blob = load_golden(name)
+    final = po.parse_fbpd(ordered(blob, "f")[-1])
+    with tempfile.NamedTemporaryFile(suffix=".pnm", delete=False) as f:
+        f.write(blob["pnm"])
+        path = f.name
+    try:
+        pix, _ = read_pnm(path)
+    finally:
+        os.remove(path)
+    oi = po.OracleImage.from_pixels(pix, maxval)
+    oi.recompute_minmax()
+    for tid, params in final.transforms:
+        assert oi.do_transform(tid, params if tid in (4, 5) else [])
+    _check_file(po, oi, _options(opts, c, final.transforms))
+
+
+def _check_file(po, oi, o):
+    oi.recompute_minmax()                       # fuif_prepare_encode
+    pi = oi.to_plane_image()                    # zero not yet set by an encode: the host side has to do it
+    ref = oi.encode(predictor=o["predictor"], nb_repeats=o["nb_repeats"], max_properties=o["max_properties"], compress=o["compress"], max_group=o["max_group"])
+    _dec, offs = po.OracleImage.decode(ref, want_offsets=True)
+    nch = len(pi.planes)
+    desc = (C.c_int * (10 * nch))()
+    ptrs = (C.c_void_p * nch)()
+    keep = []
+    for i, p in enumerate(pi.planes):
+        desc[10 * i:10 * i + 10] = [p.w, p.h, p.minval, p.maxval, p.zero, p.q, p.hshift, p.vshift, p.hcshift, p.vcshift]
+        a = np.ascontiguousarray(p.data.astype(np.int16)) if p.data is not None else np.zeros(1, dtype=np.int16)
+        keep.append(a)
+        ptrs[i] = a.ctypes.data
+    info = (C.c_int * 7)(pi.w, pi.h, pi.maxval, pi.colormodel, pi.real_nb_channels, pi.nb_channels, pi.nb_meta_channels)
+    flat = []
+    for tid, params in pi.transforms:
+        flat += [tid, len(params)] + list(params)
+    tdesc = (C.c_int * max(1, len(flat)))(*flat)
+    pred = (C.c_int * max(1, len(o["predictor"])))(*o["predictor"])
+    cap = len(ref) + 4096
+    out = np.zeros(cap, dtype=np.uint8)
+    goffs = (C.c_longlong * 512)()
+    gfirst = (C.c_int * 512)()
+    ng = C.c_int()
+    n = lib().emu_fuif_encode(nch, desc, ptrs, info, len(pi.transforms), tdesc, o["nb_repeats"], o["max_properties"], 6, 0x0d000000, 1 if o["compress"] else 0,
+                              o["max_group"], len(o["predictor"]), pred, out.ctypes.data, cap, goffs, gfirst, 512, C.byref(ng))
+    assert n >= 0, f"status {-n}"
+    mine = bytes(out[:n])
+    assert len(mine) == len(ref), f"{len(mine)} bytes vs {len(ref)}"
+    assert mine == ref, f"first difference at byte {next(i for i in range(len(ref)) if mine[i] != ref[i])}"
+    assert [(int(goffs[g]), int(gfirst[g])) for g in range(ng.value)] == [(int(a), int(b)) for a, b in offs]
+    return ref, offs
+
+
+@pytest.mark.parametrize("kind", ["noise", "noise_sq", "flat", "noise16"])
+def test_encode_file_entropy_extremes(oracle, kind):
+    """noise: the compressed form of a group is no smaller than the plain one, so the reference rolls back and the tail of
+    the abandoned attempt stays in its blob; flat: constant planes, groups without entropy-coded data"""
+    po = oracle
+    rng = np.random.default_rng(5)
+    maxval = 65535 >> 2 if kind == "noise16" else 255
+    w, h, c = (37, 29, 3) if kind != "noise16" else (24, 20, 1)
+    pix = np.full((h, w, c), 77, dtype=np.int32) if kind == "flat" else rng.integers(0, maxval + 1, size=(h, w, c)).astype(np.int32)
+    oi = po.OracleImage.from_pixels(pix, maxval)
+    oi.recompute_minmax()
+    o = {"nb_repeats": 0.5, "max_properties": 12, "compress": True, "max_group": -1, "predictor": [2] * c + [0]}
+    if kind in ("noise_sq", "flat"):
+        assert oi.do_transform(1, [])
+        assert oi.do_transform(7, [])
+        o["max_group"] = 1
+    ref, offs = _check_file(po, oi, o)
+    plain = [(_varint(ref, off)[0] & 1) == 0 for off, _ in offs]
+    if kind.startswith("noise"):
+        assert any(plain), "expected at least one rolled-back group"
