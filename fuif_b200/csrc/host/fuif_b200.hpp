@@ -1,11 +1,13 @@
 // fuif_b200.hpp -- C++ host side of the drop-in boundary.
 //
-// Source-compatible mirror of the reference's codec API for the decode / transform hot path:
+// Source-compatible mirror of the reference's codec API for the decode / encode / transform hot path:
 //   Channel, Image            reference image/image.h:54-129
 //   Transform                 reference transform/transform.h:77-106
 //   fuif_options              reference encoding/encoding.h:32-59
 //   fuif_decode<IO>, fuif_decode_file, Image::undo_transforms, Image::do_transform
 //                             reference encoding/encoding.h:68-71, image/image.h:125-126
+//   fuif_prepare_encode, fuif_encode<IO>, fuif_encode_file
+//                             reference encoding/encoding.h:61-66
 // Same names, same argument meaning, same "return false + message on stderr" error behaviour, so a caller written
 // against the reference (fuif.cpp:206-239, fuifplay.cpp:86-88) compiles against this header unchanged.  Every method
 // that touches samples forwards to the extern "C" library (include/fuif_b200.h); there is no CPU implementation here.
@@ -67,12 +69,16 @@ public:
     Transform(const Transform &o) : ID(o.ID), parameters(o.parameters) {}
 };
 
-struct fuif_options {           // reference encoding/encoding.h:32-59 (decode-side members)
+struct fuif_options {           // reference encoding/encoding.h:32-59 (without debug / heatmap / max_dist)
     int preview = -1;
     bool identify = false;
+    float nb_repeats = 0.5f;
     int max_properties = 12;
     int maniac_cutoff = 6;
     int maniac_alpha = 0x0d000000;
+    bool compress = true;
+    int max_group = -1;
+    std::vector<int> predictor;
 };
 static const fuif_options default_fuif_options{};
 
@@ -230,6 +236,65 @@ inline bool fuif_decode_file(const char *filename, Image &image, fuif_options op
     if (f != stdin) fclose(f);
     BlobReader io(bytes.data(), bytes.size());
     return fuif_decode(io, image, options);
+}
+
+// fuif_prepare_encode (reference encoding/encoding.cpp:737-743): tight ranges.  fuif_encode() does this on the device copy
+// anyway; calling it keeps code written against the reference unchanged and refreshes the host-side ranges.
+inline void fuif_prepare_encode(Image &image, fuif_options &) {
+    fb_image *dev = image.upload();
+    if (!dev) { image.error = true; return; }
+    if (fb_image_recompute_minmax(dev) == FB_OK) {
+        for (size_t i = 0; i < image.channel.size(); i++) {
+            fb_plane_desc d;
+            if (fb_image_get_plane(dev, (int)i, &d) == FB_OK) { image.channel[i].minval = (pixel_type)d.minval; image.channel[i].maxval = (pixel_type)d.maxval; }
+        }
+    }
+    fb_image_destroy(dev);
+}
+
+// fuif_encode<IO> (reference encoding/encoding.cpp:455-573): IO is anything with fputc(int) (FileIO / BlobIO of fileio.h).
+// The channel groups are learned and coded on the GPU; the bytes are the reference encoder's.
+template <typename IO>
+bool fuif_encode(IO &realio, const Image &image, fuif_options &options) {
+    if (image.error) return false;
+    fb_ctx *ctx = default_context();
+    if (!ctx) return false;
+    fb_image *dev = image.upload();
+    if (!dev) return false;
+    std::vector<int32_t> pred(options.predictor.begin(), options.predictor.end());
+    fb_encode_options o{options.nb_repeats, options.max_properties, options.maniac_cutoff, options.maniac_alpha, options.compress ? 1 : 0, options.max_group,
+                        (int32_t)pred.size(), pred.empty() ? nullptr : pred.data()};
+    uint8_t *bytes = nullptr;
+    size_t n = 0;
+    const int rc = fb_encode(ctx, dev, &o, &bytes, &n, nullptr, nullptr, 0, nullptr);
+    if (rc == FB_OK)        // Channel::zero is `mutable` in the reference and set by the encoder (encoding.cpp:118)
+        for (size_t i = 0; i < image.channel.size(); i++) {
+            fb_plane_desc d;
+            if (fb_image_get_plane(dev, (int)i, &d) == FB_OK) image.channel[i].zero = (pixel_type)d.zero;
+        }
+    fb_image_destroy(dev);
+    if (rc != FB_OK) { fprintf(stderr, "Could not encode: %s\n", fb_last_error(ctx)); return false; }
+    for (size_t i = 0; i < n; i++) realio.fputc(bytes[i]);
+    fb_free(bytes);
+    return true;
+}
+
+// FileIO's writing half (reference fileio.h:33-81)
+class FileWriter {
+    FILE *f;
+public:
+    explicit FileWriter(FILE *fil) : f(fil) {}
+    int fputc(int c) { return ::fputc(c, f); }
+};
+
+// fuif_encode_file (reference encoding/encoding.cpp:722-735); "-" is stdout
+inline bool fuif_encode_file(const char *filename, const Image &image, fuif_options &options) {
+    FILE *f = !strcmp(filename, "-") ? stdout : fopen(filename, "wb");
+    if (!f) return false;
+    FileWriter io(f);
+    const bool ok = fuif_encode(io, image, options);
+    if (f != stdout) fclose(f);
+    return ok;
 }
 
 }  // namespace fuif_b200
