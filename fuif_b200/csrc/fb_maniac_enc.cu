@@ -63,8 +63,6 @@ struct EGroup {
     LLeaf *leaves; int leaf_cap;
     uint16_t *fleaves;          // (kMaxNodes / 2) x 32: leaves of the real pass
     int *stack;                 // 8 * (kMaxNodes / 2 + 2) ints: explicit stacks of write_tree / simplify / kill_children
-    long long *scr;             // 5 x 32: per-lane values of the current symbol, exchanged through memory (one barrier
-                                // instead of a shuffle per tree level): property, range lo, range hi, split value, virtual cost
     // output
     unsigned char *out; unsigned out_cap;
     unsigned out_len, header_len;       // header_len: bytes before the entropy-coded part (header_pos - before, encoding.cpp)
@@ -81,6 +79,10 @@ struct EParams {
     const uint16_t *log4k;                  // [4097], chance.cpp:67-91
     const int *rnd; long long nrnd;         // libc rand() sequence from its initial state
 };
+
+// 5 x 32: per-lane values of the current symbol, exchanged through shared memory (one warp barrier instead of a shuffle per
+// tree level): property, range lo, range hi, split value, virtual cost.  One warp per block, so one copy per block.
+__shared__ long long s_scr[160];
 
 __device__ __forceinline__ int s16(int x) { return (int)(short)x; }
 __device__ __forceinline__ int ilog2u(unsigned l) { return l == 0 ? 0 : 31 - __clz((int)l); }
@@ -322,7 +324,7 @@ __device__ void leaf_init(LLeaf &l, int zero_chance, int lane) {
 // virtual chances (compound_enc.h:307-366, 91-109).  All lanes call it with their own property value.
 __device__ void learn_symbol(const EParams &P, EGroup &g, const GroupCtx &G, int &nnodes, int &nleaves, int myprop, int mn, int mx, int value, int lane) {
     TNode *nodes = g.nodes;
-    long long *prop = g.scr, *slo = g.scr + 32, *shi = g.scr + 64, *ssp = g.scr + 96, *ssz = g.scr + 128;
+    long long *prop = s_scr, *slo = s_scr + 32, *shi = s_scr + 64, *ssp = s_scr + 96, *ssz = s_scr + 128;
     prop[lane] = myprop;
     __syncwarp();
     // every lane walks the tree (same path); lane p narrows the range of property p on the way
@@ -612,11 +614,11 @@ __device__ bool encode_channels(const EParams &P, EGroup &g, Sink &s, bool learn
                     learn_symbol(P, g, G, nnodes, nleaves, myprop, mn, mx, diff, lane);
                     if (g.status) return false;
                 } else if (mn != mx) {
-                    g.scr[lane] = myprop;
+                    s_scr[lane] = myprop;
                     __syncwarp();
                     if (lane == 0) {
                         int pos = 0;
-                        while (nodes[pos].property != -1) pos = (int)g.scr[nodes[pos].property] > nodes[pos].splitval ? nodes[pos].child : nodes[pos].child + 1;
+                        while (nodes[pos].property != -1) pos = (int)s_scr[nodes[pos].property] > nodes[pos].splitval ? nodes[pos].child : nodes[pos].child + 1;
                         const int nd = symbol_decisions(mn, mx, diff, dec);
                         code_decisions(rac, s, P.table, g.fleaves + (size_t)nodes[pos].child * 32, dec, nd);
                     }
@@ -776,12 +778,12 @@ extern "C" int fb_encode(fb_ctx *ctx, fb_image *img, const fb_encode_options *op
             E.leaf_cap = (int)cap; E.out_cap = (unsigned)ocap;
         }
         const size_t stack_ints = (size_t)8 * (kMaxNodes / 2 + 2);
-        DevBuf d_ch, d_groups, d_nodes, d_leaves, d_fleaves, d_stack, d_scr, d_out, d_tables, d_rnd;
+        DevBuf d_ch, d_groups, d_nodes, d_leaves, d_fleaves, d_stack, d_out, d_tables, d_rnd;
         const size_t tables_bytes = (4096 * 2 * 2 + 4104) * sizeof(uint16_t);
         if (d_ch.alloc(sizeof(EChan) * (size_t)nch) != cudaSuccess || d_groups.alloc(sizeof(EGroup) * (size_t)ng) != cudaSuccess ||
             d_nodes.alloc(sizeof(TNode) * kMaxNodes * (size_t)ng) != cudaSuccess || d_leaves.alloc(sizeof(LLeaf) * leaf_total) != cudaSuccess ||
             d_fleaves.alloc(sizeof(uint16_t) * 32 * (kMaxNodes / 2) * (size_t)ng) != cudaSuccess || d_stack.alloc(sizeof(int) * stack_ints * (size_t)ng) != cudaSuccess ||
-            d_scr.alloc(sizeof(long long) * 160 * (size_t)ng) != cudaSuccess || d_out.alloc(out_total) != cudaSuccess || d_tables.alloc(tables_bytes) != cudaSuccess ||
+            d_out.alloc(out_total) != cudaSuccess || d_tables.alloc(tables_bytes) != cudaSuccess ||
             d_rnd.alloc(sizeof(int) * rnd.size()) != cudaSuccess) {
             cudaGetLastError();
             ctx->err = "fb_encode: out of device memory";
@@ -793,7 +795,6 @@ extern "C" int fb_encode(fb_ctx *ctx, fb_image *img, const fb_encode_options *op
             E.leaves = (LLeaf *)d_leaves.p + leaf_off[(size_t)g];
             E.fleaves = (uint16_t *)d_fleaves.p + (size_t)32 * (kMaxNodes / 2) * g;
             E.stack = (int *)d_stack.p + stack_ints * g;
-            E.scr = (long long *)d_scr.p + (size_t)160 * g;
             E.out = (unsigned char *)d_out.p + out_off[(size_t)g];
         }
         uint16_t *dt = (uint16_t *)d_tables.p;

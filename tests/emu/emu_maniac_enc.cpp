@@ -26,7 +26,6 @@ int emu_maniac_encode(int nch, const int *chdesc, int16_t **planes, int ngroups,
     std::vector<std::vector<LLeaf>> leaves((size_t)ngroups);
     std::vector<std::vector<uint16_t>> fleaves((size_t)ngroups);
     std::vector<std::vector<int>> stacks((size_t)ngroups);
-    std::vector<std::vector<long long>> scr((size_t)ngroups);
     for (int g = 0; g < ngroups; g++) {
         EGroup &G = groups[(size_t)g];
         memset(&G, 0, sizeof(G));
@@ -37,8 +36,7 @@ int emu_maniac_encode(int nch, const int *chdesc, int16_t **planes, int ngroups,
         fleaves[(size_t)g].resize((size_t)(kMaxNodes / 2) * 32);
         stacks[(size_t)g].resize((size_t)8 * (kMaxNodes / 2 + 2));
         G.nodes = nodes[(size_t)g].data(); G.leaves = leaves[(size_t)g].data(); G.leaf_cap = leaf_cap;
-        scr[(size_t)g].resize(5 * 32);
-        G.fleaves = fleaves[(size_t)g].data(); G.stack = stacks[(size_t)g].data(); G.scr = scr[(size_t)g].data();
+        G.fleaves = fleaves[(size_t)g].data(); G.stack = stacks[(size_t)g].data();
         G.out = out[g]; G.out_cap = out_cap;
     }
     EParams P;
@@ -103,7 +101,6 @@ long long emu_fuif_encode(int nch, const int *chdesc, int16_t **planes_in, const
     std::vector<std::vector<LLeaf>> leaves((size_t)ng);
     std::vector<std::vector<uint16_t>> fleaves((size_t)ng);
     std::vector<std::vector<int>> stacks((size_t)ng);
-    std::vector<std::vector<long long>> scr((size_t)ng);
     std::vector<std::vector<unsigned char>> outs((size_t)ng);
     for (int g = 0; g < ng; g++) {
         const H::Group &G = groups[(size_t)g];
@@ -116,10 +113,10 @@ long long emu_fuif_encode(int nch, const int *chdesc, int16_t **planes_in, const
         memset(&E, 0, sizeof(E));
         E.beginc = G.beginc; E.endc = G.endc; E.predictor = G.predictor; E.compress = o.compress ? 1 : 0; E.rand_off = G.rand_off;
         nodes[(size_t)g].resize(kMaxNodes); leaves[(size_t)g].resize((size_t)cap); fleaves[(size_t)g].resize((size_t)(kMaxNodes / 2) * 32);
-        stacks[(size_t)g].resize((size_t)8 * (kMaxNodes / 2 + 2)); scr[(size_t)g].resize(160);
+        stacks[(size_t)g].resize((size_t)8 * (kMaxNodes / 2 + 2));
         outs[(size_t)g].assign((size_t)(4 * G.pixels + tree_bytes + 4096), 0);
         E.nodes = nodes[(size_t)g].data(); E.leaves = leaves[(size_t)g].data(); E.leaf_cap = (int)cap; E.fleaves = fleaves[(size_t)g].data();
-        E.stack = stacks[(size_t)g].data(); E.scr = scr[(size_t)g].data(); E.out = outs[(size_t)g].data(); E.out_cap = (unsigned)outs[(size_t)g].size();
+        E.stack = stacks[(size_t)g].data(); E.out = outs[(size_t)g].data(); E.out_cap = (unsigned)outs[(size_t)g].size();
     }
     EParams P;
     P.ch = ch.data(); P.nch = nch; P.groups = eg.data(); P.ngroups = ng; P.max_properties = max_properties; P.nb_repeats = nb_repeats;
