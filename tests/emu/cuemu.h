@@ -126,9 +126,18 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, bool cooper
                 makecontext(&f.uc, (void (*)())fibre_entry, 0);
             }
         }
+        // CUEMU_ORDER=reverse|shuffle changes the order in which the fibres get their turns: a kernel whose results depend on
+        // which thread of a barrier interval runs first has a race that the default order hides
+        static const char *order_env = getenv("CUEMU_ORDER");
+        const bool reverse = order_env && order_env[0] == 'r', shuffle = order_env && order_env[0] == 's';
+        unsigned long long lcg = 0x9E3779B97F4A7C15ull;
         size_t remaining = s.fibres.size();
         while (remaining) {
-            for (size_t i = 0; i < s.fibres.size(); i++) {
+            const size_t nf = s.fibres.size();
+            lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+            const size_t rot = shuffle ? (size_t)(lcg >> 33) % nf : 0;
+            for (size_t k = 0; k < nf; k++) {
+                const size_t i = reverse ? nf - 1 - k : (k + rot) % nf;
                 Fibre &f = s.fibres[i];
                 if (f.done) continue;
                 s.current = (int)i;

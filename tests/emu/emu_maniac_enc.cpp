@@ -114,6 +114,11 @@ long long emu_fuif_encode(int nch, const int *chdesc, int16_t **planes_in, const
         E.beginc = G.beginc; E.endc = G.endc; E.predictor = G.predictor; E.compress = o.compress ? 1 : 0; E.rand_off = G.rand_off;
         nodes[(size_t)g].resize(kMaxNodes); leaves[(size_t)g].resize((size_t)cap); fleaves[(size_t)g].resize((size_t)(kMaxNodes / 2) * 32);
         stacks[(size_t)g].resize((size_t)8 * (kMaxNodes / 2 + 2));
+        // cudaMalloc does not clear memory: the kernel must not depend on zeroed working buffers (the output buffer is cleared by fb_encode)
+        memset((void *)nodes[(size_t)g].data(), 0xCD, nodes[(size_t)g].size() * sizeof(TNode));
+        memset((void *)leaves[(size_t)g].data(), 0xCD, leaves[(size_t)g].size() * sizeof(LLeaf));
+        memset((void *)fleaves[(size_t)g].data(), 0xCD, fleaves[(size_t)g].size() * sizeof(uint16_t));
+        memset((void *)stacks[(size_t)g].data(), 0xCD, stacks[(size_t)g].size() * sizeof(int));
         outs[(size_t)g].assign((size_t)(4 * G.pixels + tree_bytes + 4096), 0);
         E.nodes = nodes[(size_t)g].data(); E.leaves = leaves[(size_t)g].data(); E.leaf_cap = (int)cap; E.fleaves = fleaves[(size_t)g].data();
         E.stack = stacks[(size_t)g].data(); E.out = outs[(size_t)g].data(); E.out_cap = (unsigned)outs[(size_t)g].size();

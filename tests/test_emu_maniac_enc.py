@@ -5,6 +5,7 @@ plain form when the reference rolls back -- must be identical."""
 import ctypes as C
 import os
 import subprocess
+import sys
 import tempfile
 
 import numpy as np
@@ -276,3 +277,14 @@ def test_encode_file_entropy_extremes(oracle, kind):
     plain = [(_varint(ref, off)[0] & 1) == 0 for off, _ in offs]
     if kind.startswith("noise"):
         assert any(plain), "expected at least one rolled-back group"
+
+
+@pytest.mark.parametrize("order", ["reverse", "shuffle"])
+def test_encode_is_independent_of_lane_order(order):
+    """The emulator gives the lanes of a warp their turns in lane order by default, which would hide a race between lanes inside
+    one barrier interval (on hardware they run together).  Same files with the order reversed / rotated at random."""
+    env = dict(os.environ, CUEMU_ORDER=order)
+    lib()       # built by now, so the child does not race another build
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "file_matches and (odd or dct or pred or unc) or extremes"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-1000:]
