@@ -45,10 +45,12 @@ struct EChan {                  // a plane as the encoder sees it (ranges tight:
     const int16_t *data;
 };
 struct TNode { short property; unsigned short child; int splitval; };   // PropertyDecisionNode, compound.h:41-51
-// leaf of the learning pass: CompoundSymbolChances, compound_enc.h:29-59 (virt[p][0] is used while property p > its running split value)
+// leaf of the learning pass: CompoundSymbolChances, compound_enc.h:29-59.  virt[s][i][p] is chance i of property p's virtual
+// context s (s = 0 while property p > its running split value): property-minor, so that the 32 lanes of a decision touch
+// at most two 64-byte runs instead of 32 cache lines
 struct LLeaf {
     uint16_t real[32];
-    uint16_t virt[32][2][32];
+    uint16_t virt[2][32][32];
     unsigned long long realSize;
     unsigned long long virtSize[32];
     long long virtPropSum[32];
@@ -83,6 +85,10 @@ struct EParams {
 // 5 x 32: per-lane values of the current symbol, exchanged through shared memory (one warp barrier instead of a shuffle per
 // tree level): property, range lo, range hi, split value, virtual cost.  One warp per block, so one copy per block.
 __shared__ long long s_scr[160];
+// the chance successor table of the sample coder and the cost table, copied in at kernel start: every decision of every lane
+// looks both up at a data-dependent index
+__shared__ uint16_t s_table[4096 * 2];
+__shared__ uint16_t s_log4k[4104];
 
 __device__ __forceinline__ int s16(int x) { return (int)(short)x; }
 __device__ __forceinline__ int ilog2u(unsigned l) { return l == 0 ? 0 : 31 - __clz((int)l); }
@@ -315,7 +321,7 @@ __device__ __forceinline__ int compute_splitval(long long sum, int count, int lo
 }
 __device__ void leaf_init(LLeaf &l, int zero_chance, int lane) {
     l.real[lane] = initial_chance(lane, zero_chance);
-    for (int p = 0; p < 32; p++) { l.virt[p][0][lane] = initial_chance(lane, zero_chance); l.virt[p][1][lane] = l.virt[p][0][lane]; }
+    for (int i = 0; i < 32; i++) { l.virt[0][i][lane] = initial_chance(i, zero_chance); l.virt[1][i][lane] = l.virt[0][i][lane]; }
     l.virtSize[lane] = 0; l.virtPropSum[lane] = 0;
     if (lane == 0) { l.realSize = 0; l.count = 0; l.best = -1; }
     __syncwarp();
@@ -395,13 +401,13 @@ __device__ void learn_symbol(const EParams &P, EGroup &g, const GroupCtx &G, int
     if (nd == 0) { __syncwarp(); return; }
     unsigned long long mysz = ~0ull;
     if (lane < G.nprops) {
-        uint16_t *vc = leaf->virt[lane][sel ? 0 : 1];
+        uint16_t (*vc)[32] = leaf->virt[sel ? 0 : 1];
         unsigned long long sz = leaf->virtSize[lane];
         for (int k = 0; k < nd; k++) {
             const int idx = dec[k] >> 1, bit = dec[k] & 1;
-            const unsigned c = vc[idx];
-            sz += P.log4k[bit ? c : 4096 - c];
-            vc[idx] = P.table[c * 2 + bit];
+            const unsigned c = vc[idx][lane];
+            sz += s_log4k[bit ? c : 4096 - c];
+            vc[idx][lane] = s_table[c * 2 + bit];
         }
         leaf->virtSize[lane] = sz;
         mysz = sz;
@@ -410,8 +416,8 @@ __device__ void learn_symbol(const EParams &P, EGroup &g, const GroupCtx &G, int
         for (int k = 0; k < nd; k++) {
             const int idx = dec[k] >> 1, bit = dec[k] & 1;
             const unsigned c = leaf->real[idx];
-            sz += P.log4k[bit ? c : 4096 - c];
-            leaf->real[idx] = P.table[c * 2 + bit];
+            sz += s_log4k[bit ? c : 4096 - c];
+            leaf->real[idx] = s_table[c * 2 + bit];
         }
         leaf->realSize = sz;
     }
@@ -620,7 +626,7 @@ __device__ bool encode_channels(const EParams &P, EGroup &g, Sink &s, bool learn
                         int pos = 0;
                         while (nodes[pos].property != -1) pos = (int)s_scr[nodes[pos].property] > nodes[pos].splitval ? nodes[pos].child : nodes[pos].child + 1;
                         const int nd = symbol_decisions(mn, mx, diff, dec);
-                        code_decisions(rac, s, P.table, g.fleaves + (size_t)nodes[pos].child * 32, dec, nd);
+                        code_decisions(rac, s, s_table, g.fleaves + (size_t)nodes[pos].child * 32, dec, nd);
                     }
                     __syncwarp();
                 }
@@ -650,6 +656,8 @@ __global__ void __launch_bounds__(32) k_maniac_encode(EParams P) {
     EGroup &g = P.groups[gi];
     Sink s;
     s.p = g.out; s.cap = g.out_cap; s.len = 0; s.overflow = 0;
+    for (int k = lane; k < 4096 * 2; k += 32) s_table[k] = P.table[k];
+    for (int k = lane; k < 4097; k += 32) s_log4k[k] = P.log4k[k];
     if (lane == 0) { g.status = 0; g.attempt_len = 0; g.nnodes = 1; g.nodes[0].property = -1; g.nodes[0].child = 0; g.nodes[0].splitval = 0; g.header_len = 0; }
     __syncwarp();
     bool ok = true;
