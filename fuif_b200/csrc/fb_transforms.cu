@@ -938,7 +938,9 @@ static int run_inv_squeeze_plan_per_level(fb_ctx *ctx, const std::vector<FbSqOp>
             dq::StepEpilogue E;
             if (ep_ok && ep->kind == 2 && step == ops[n - 1].step) {
                 E.enabled = 1; E.yin = ep->ycc[0]; E.rout = ep->rout; E.co_out = ep->ycc[1]; E.cg_out = ep->ycc[2];
-                E.maxval = ep->maxval; E.lo = ep->lo; E.hi = ep->hi; E.do_clamp = ep->do_clamp;
+                E.maxval = ep->maxval; E.lo = ep->lo; E.hi = ep->hi;
+                // inv_YCoCg leaves R, G, B in [0, maxval] (ycocg.h:51-56): a final clamp to a range that contains it is the identity
+                E.do_clamp = (ep->do_clamp && !(ep->lo <= 0 && ep->hi >= ep->maxval)) ? 1 : 0;
             }
             dq::StepPlan SP = dq::plan_step(sops, horizontal != 0, E, ep ? ep->lo : 0, ep ? ep->hi : 0, ctx->sm_count);
             if (E.enabled && !SP.epilogue_done) { ctx->err = "internal: YCoCg epilogue planned but not placed"; return FB_ERR_INVALID; }
