@@ -59,16 +59,19 @@ FB_DEV uint4 ld16(const int16_t *p) { return *reinterpret_cast<const uint4 *>(p)
 FB_DEV void st16(int16_t *p, const uint4 &v) { *reinterpret_cast<uint4 *>(p) = v; }
 FB_DEV uint4 zero4() { uint4 z; z.x = 0; z.y = 0; z.z = 0; z.w = 0; return z; }
 
+// CLAMP(x, 0, hi) for hi >= 0 as max-then-min: two instructions where the conditional form costs three.  The two forms differ
+// only for hi < 0, and the planner does not fuse the colour epilogue for such an image (fb_transforms.cu).
+FB_DEV int clamp0(int x, int hi) { return fq::imin(fq::imax(x, 0), hi); }
 // inv_YCoCg (+ clamp) on two samples packed in words, ycocg.h:51-56
 FB_DEV void ycocg_word(uint32_t wy, uint32_t wo, uint32_t wg, int maxval, int lo, int hi, int do_clamp, uint32_t &r, uint32_t &g, uint32_t &b) {
     r = 0; g = 0; b = 0;
 #pragma unroll
     for (int hlf = 0; hlf < 2; hlf++) {
         const int Yr = (int)(short)(wy >> (16 * hlf)), Co = (int)(short)(wo >> (16 * hlf)), Cg = (int)(short)(wg >> (16 * hlf));
-        const int Y = clampi(Yr, 0, maxval);
-        int G_ = clampi(Y - ((-Cg) >> 1), 0, maxval);
-        int B_ = clampi(Y + ((1 - Cg) >> 1) - (Co >> 1), 0, maxval);
-        int R_ = clampi(Co + B_, 0, maxval);
+        const int Y = clamp0(Yr, maxval);
+        int G_ = clamp0(Y - ((-Cg) >> 1), maxval);
+        int B_ = clamp0(Y + ((1 - Cg) >> 1) - (Co >> 1), maxval);
+        int R_ = clamp0(Co + B_, maxval);
         if (do_clamp) { R_ = clampi(R_, lo, hi); G_ = clampi(G_, lo, hi); B_ = clampi(B_, lo, hi); }
         r |= (uint32_t)(uint16_t)R_ << (16 * hlf); g |= (uint32_t)(uint16_t)G_ << (16 * hlf); b |= (uint32_t)(uint16_t)B_ << (16 * hlf);
     }

@@ -897,7 +897,7 @@ static int run_inv_squeeze_plan_per_level(fb_ctx *ctx, const std::vector<FbSqOp>
     // Measured on B200 (profiles/): the direct kernel wins every horizontal step, the tiled kernel (lanes = adjacent
     // columns, warps = segments) every vertical one; FB_SQUEEZE_DIRECT_V=1 sends vertical steps to the direct kernel too.
     static const bool direct_v = getenv("FB_SQUEEZE_DIRECT_V") != nullptr;
-    bool ep_ok = use_direct && ep && ep->kind != 0;
+    bool ep_ok = use_direct && ep && ep->kind != 0 && !(ep->kind == 2 && ep->maxval < 0);     // dq::clamp0 wants maxval >= 0
     int ico = -1, icg = -1;
     if (ep_ok) {
         const int last_step = ops[n - 1].step;
