@@ -288,3 +288,33 @@ def test_encode_is_independent_of_lane_order(order):
     p = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-p", "no:cacheprovider",
                         "-k", "file_matches and (odd or dct or pred or unc) or extremes"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-1000:]
+
+
+@pytest.mark.parametrize("variant", ["repeats2", "repeats01", "props2", "props18", "group3", "pred3", "pred0_nosq", "gray16"])
+def test_encode_file_option_variants(oracle, variant):
+    """encode options the golden cases leave out: more / fewer learning iterations (rand() offsets of later groups shift),
+    fewer / more back-reference properties (18 = the most one warp holds), several channels per group, the remaining predictors"""
+    po = oracle
+    rng = np.random.default_rng(21)
+    w, h, c, maxval = 41, 30, 3, 255
+    if variant == "gray16":
+        c, maxval = 1, 4095
+    yy, xx = np.mgrid[0:h, 0:w]
+    pix = np.stack([np.clip((maxval * (0.5 + 0.4 * np.sin(xx / (5.0 + k)) * np.cos(yy / (7.0 + k))) + rng.normal(0, maxval * 0.02, (h, w))), 0, maxval)
+                    for k in range(c)], axis=-1).astype(np.int32)
+    oi = po.OracleImage.from_pixels(pix, maxval)
+    oi.recompute_minmax()
+    o = {"nb_repeats": 0.5, "max_properties": 12, "compress": True, "max_group": 1, "predictor": [2] * c + [0]}
+    squeeze = True
+    if variant == "repeats2": o["nb_repeats"] = 2.0
+    elif variant == "repeats01": o["nb_repeats"] = 0.1
+    elif variant == "props2": o["max_properties"] = 2
+    elif variant == "props18": o["max_properties"] = 18
+    elif variant == "group3": o["max_group"] = 3
+    elif variant == "pred3": o["predictor"] = [3, 3, 3, 3]
+    elif variant == "pred0_nosq": o["predictor"] = [0]; squeeze = False; o["max_group"] = -1
+    if c >= 3:
+        assert oi.do_transform(1, [])
+    if squeeze:
+        assert oi.do_transform(7, [])
+    _check_file(po, oi, o)
