@@ -21,7 +21,7 @@ def aligned_plane(shape, fill=None):
     return a
 
 
-def run_case(po, pix, maxval, params, garbage=None, colour=True):
+def run_case(po, pix, maxval, params, garbage=None, colour=True, ep_clamp=1):
     h, w, nch = pix.shape
     img = po.OracleImage.from_pixels(pix, maxval)
     if colour and nch >= 3:
@@ -57,7 +57,7 @@ def run_case(po, pix, maxval, params, garbage=None, colour=True):
     if use_ycocg:
         planes.append(aligned_plane((h, w), 0x7777))
         rplane = len(planes) - 1
-        ep = [1, final_ids[0], rplane, final_ids[1], final_ids[2], maxval, 0, maxval, 1]
+        ep = [1, final_ids[0], rplane, final_ids[1], final_ids[2], maxval, 0, maxval, ep_clamp]
     st = emu_util.run_direct(planes, ops10, ep, 0, maxval)
     got = [planes[i].copy() for i in final_ids]
     if use_ycocg:
@@ -98,3 +98,12 @@ def test_direct_unsqueeze_full_range_garbage(oracle):
 def test_direct_unsqueeze_noise(oracle):
     pix = np.random.default_rng(5).integers(0, 256, size=(160, 640, 3)).astype(np.int32)
     run_case(oracle, pix, 255, default_squeeze_parameters(640, 160, 3))
+
+
+@pytest.mark.parametrize("garbage", [None, (9, 32767)])
+def test_colour_epilogue_without_final_clamp(oracle, garbage):
+    """The library leaves the per-pixel final clamp out of the colour epilogue when the clamp range contains [0, maxval]
+    (fb_transforms.cu): inverse YCoCg already leaves R, G, B there, so the pixels must not change -- also for garbage input."""
+    pix = synth_image(256, 128, 3, 255, seed=4)
+    st = run_case(oracle, pix, 255, default_squeeze_parameters(256, 128, 3), garbage=garbage, ep_clamp=0)
+    assert st[3] == 1, st
