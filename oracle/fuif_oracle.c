@@ -189,6 +189,20 @@ int fo_plane_set_range(fo_image *img, int i, int minval, int maxval, int q) {
     return 0;
 }
 
+/* test plumbing: give plane i new dimensions / shifts (zero-filled), and push a transform without applying it -- the state
+ * an Image is in when its channels were produced elsewhere (e.g. chroma planes of a JPEG) */
+int fo_plane_reshape(fo_image *img, int i, int w, int h, int hshift, int vshift, int hcshift, int vcshift, int component) {
+    if (i < 0 || i >= img->nch) return -1;
+    fo_channel *c = &img->ch[i];
+    c->w = w; c->h = h; c->hshift = hshift; c->vshift = vshift; c->hcshift = hcshift; c->vcshift = vcshift; c->component = component;
+    ch_fill(c, 0);
+    return 0;
+}
+int fo_push_transform(fo_image *img, int id, const int *params, int np) {
+    img_push_transform(img, id, params, np);
+    return 0;
+}
+
 void fo_recompute_minmax(fo_image *img) {       /* Channel::actual_minmax, image/image.cpp:82-92 */
     for (int i = 0; i < img->nch; i++) {
         int mn = LARGEST_VAL, mx = SMALLEST_VAL;
@@ -671,6 +685,82 @@ static int fwd_dct(fo_image *img, const int *p, int np) {
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* ChromaSubsample, transform/subsample.h (inverse + meta; the reference has no forward, :130-133)    */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* check_subsample_parameters, subsample.h:33-69: one abbreviated parameter expands to (first, last, ratio_h, ratio_v) */
+static int subsample_parameters(const int *p, int np, int *out) {
+    int n = 0;
+    if (np == 1 && p[0] >= 0 && p[0] <= 3) {
+        static const int abbrev[4][2] = {{2, 2}, {2, 1}, {1, 2}, {4, 1}};   /* 4:2:0, 4:2:2, 4:4:0, 4:1:1 */
+        out[0] = 1; out[1] = 2; out[2] = abbrev[p[0]][0]; out[3] = abbrev[p[0]][1];
+        return 4;
+    }
+    for (int i = 0; i < np && i < 64; i++) out[n++] = p[i];
+    if (n % 4) return 0;            /* "invalid parameters": cleared */
+    return n;
+}
+
+/* inv_subsample, subsample.h:73-128 */
+static int inv_subsample(fo_image *img, const int *p0, int np0) {
+    int p[64];
+    const int np = subsample_parameters(p0, np0, p);
+    for (int i = 0; i < np; i += 4) {
+        const int c1 = p[i], c2 = p[i + 1], srh = p[i + 2], srv = p[i + 3];
+        for (int c = c1; c <= c2; c++) {
+            fo_channel *in = &img->ch[c];
+            const int ow = in->w, oh = in->h;
+            if (ow >= img->ch[img->nb_meta_channels].w && oh >= img->ch[img->nb_meta_channels].h) continue;   /* LQIP / 1:16 decodes */
+            fo_channel out;
+            ch_make(&out, ow * srh, oh * srv, in->minval, in->maxval, 1, 0, 0, 0, 0);
+            if (srv <= 2 && srh <= 2) {
+                if (srh == 2) {
+                    for (int y = 0; y < oh; y++) for (int x = 0; x < ow; x++) {
+                        ch_set(&out, y * srv, x * srh, (3 * ch_get(in, y, x) + ch_get(in, y, x ? x - 1 : 0) + 1) >> 2);
+                        ch_set(&out, y * srv, x * srh + 1, (3 * ch_get(in, y, x) + ch_get(in, y, x + 1 < ow ? x + 1 : x) + 2) >> 2);
+                    }
+                } else {
+                    for (int y = 0; y < oh; y++) for (int x = 0; x < ow; x++) ch_set(&out, y * srv, x, ch_get(in, y, x));
+                }
+                if (srv == 2) {
+                    fo_channel orig = out;
+                    orig.data = (int16_t *)malloc((out.n + 1) * sizeof(int16_t));
+                    memcpy(orig.data, out.data, out.n * sizeof(int16_t));
+                    for (int y = 0; y < oh; y++) for (int x = 0; x < ow * srh; x++) {
+                        ch_set(&out, y * srv, x, (3 * ch_get(&orig, y * srv, x) + ch_get(&orig, y ? (y - 1) * srv : 0, x) + 1) >> 2);
+                        ch_set(&out, y * srv + 1, x, (3 * ch_get(&orig, y * srv, x) + ch_get(&orig, y + 1 < oh ? (y + 1) * srv : y * srv, x) + 2) >> 2);
+                    }
+                    free(orig.data);
+                }
+            } else {
+                for (int y = 0; y < oh * srv; y++) for (int x = 0; x < ow * srh; x++) ch_set(&out, y, x, ch_get(in, y / srv, x / srh));
+            }
+            free(in->data);
+            *in = out;
+        }
+    }
+    return 1;
+}
+
+/* meta_subsample, subsample.h:135-157 (the reference asserts ratios of 1 or 2 here) */
+static int meta_subsample(fo_image *img, const int *p0, int np0) {
+    int p[64];
+    const int np = subsample_parameters(p0, np0, p);
+    for (int i = 0; i < np; i += 4) {
+        const int c1 = p[i], c2 = p[i + 1], srh = p[i + 2], srv = p[i + 3];
+        if ((srh != 1 && srh != 2) || (srv != 1 && srv != 2)) return 0;
+        if (c1 < 0 || c2 >= img->nch) return 0;
+        for (int c = c1; c <= c2; c++) {
+            img->ch[c].w = (img->ch[c].w + srh - 1) / srh;
+            img->ch[c].h = (img->ch[c].h + srv - 1) / srv;
+            img->ch[c].hshift += srh == 1 ? 0 : 1;
+            img->ch[c].vshift += srv == 1 ? 0 : 1;
+        }
+    }
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* Transform dispatch (transform/transform.cpp:48-81) and Image::undo_transforms / do_transform       */
 /* ------------------------------------------------------------------------------------------------ */
 
@@ -686,7 +776,14 @@ static int transform_apply(fo_image *img, fo_transform *t, int inverse) {
             t->p = (int *)realloc(t->p, 2 * sizeof(int)); t->np = 2; t->p[0] = 0; t->p[1] = img->nb_channels - 1;
         }
         return inverse ? inv_dct(img, t->p) : fwd_dct(img, t->p, t->np);
-    default: return 0;       /* subsample / palette / 2dmatch / permute / approximate: out of scope */
+    case FO_SUBSAMPLE:
+        if (!inverse) return 0;     /* fwd_subsample is a stub in the reference (subsample.h:130-133) */
+        for (int i = 0; i + 3 < t->np || (t->np == 1 && i == 0); i += 4) {     /* channels must exist */
+            if (t->np == 1) { if (img->nch < 3) return 0; break; }
+            if (t->p[i] < 0 || t->p[i + 1] >= img->nch) return 0;
+        }
+        return inv_subsample(img, t->p, t->np);
+    default: return 0;       /* palette / 2dmatch / permute / approximate: out of scope */
     }
 }
 
@@ -704,6 +801,7 @@ static int transform_meta_apply(fo_image *img, fo_transform *t) {
     case FO_DCT:
         if (t->np < 2) { t->p = (int *)realloc(t->p, 2 * sizeof(int)); t->np = 2; t->p[0] = 0; t->p[1] = img->nb_channels - 1; }
         return meta_dct(img, t->p);
+    case FO_SUBSAMPLE: return meta_subsample(img, t->p, t->np);
     default: return 0;
     }
 }

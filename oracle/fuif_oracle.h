@@ -54,6 +54,8 @@ int fo_transform_info(const fo_image *img, int i, int *id, int *params, int maxp
 /* overwrite plane i (n must equal w*h of the plane, or 0 to mark it undecoded) */
 int fo_plane_set(fo_image *img, int i, const int16_t *data, size_t n);
 int fo_plane_set_range(fo_image *img, int i, int minval, int maxval, int q);
+int fo_plane_reshape(fo_image *img, int i, int w, int h, int hshift, int vshift, int hcshift, int vcshift, int component);
+int fo_push_transform(fo_image *img, int id, const int *params, int np);
 
 /* fuif_decode over a memory blob (reference encoding/encoding.cpp:599-720) with the end-of-stream rules of
  * FileIO (fileio.h:33-81), the IO class fuif_decode_file uses.

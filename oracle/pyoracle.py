@@ -58,6 +58,8 @@ def lib():
         L.fo_transform_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
         L.fo_plane_set.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.fo_plane_set_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.fo_plane_reshape.argtypes = [C.c_void_p] + [C.c_int] * 8
+        L.fo_push_transform.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int]
         L.fo_decode.restype = C.c_void_p
         L.fo_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
         L.fo_undo_transforms.argtypes = [C.c_void_p, C.c_int]
@@ -172,6 +174,23 @@ class OracleImage:
         for i in range(c):
             a = np.ascontiguousarray(pix[:, :, i].astype(np.int16))
             lib().fo_plane_set(img.h, i, a.ctypes.data, a.size)
+        return img
+
+    @staticmethod
+    def from_plane_image(pi: "PlaneImage") -> "OracleImage":
+        """An Image whose planes and transform stack are given as they are (nothing is applied): the state after fuif_decode,
+        or of an importer that delivers already-transformed planes.  The plane count must be nb_channels."""
+        assert len(pi.planes) == pi.nb_channels and pi.nb_meta_channels == 0
+        img = OracleImage(lib().fo_image_new(pi.w, pi.h, pi.maxval, pi.nb_channels, pi.colormodel))
+        for i, p in enumerate(pi.planes):
+            lib().fo_plane_reshape(img.h, i, p.w, p.h, p.hshift, p.vshift, p.hcshift, p.vcshift, p.component)
+            if p.data is not None:
+                a = np.ascontiguousarray(p.data.astype(np.int16))
+                lib().fo_plane_set(img.h, i, a.ctypes.data, a.size)
+            lib().fo_plane_set_range(img.h, i, p.minval, p.maxval, p.q)
+        for tid, params in pi.transforms:
+            arr = (C.c_int * max(1, len(params)))(*params)
+            lib().fo_push_transform(img.h, tid, arr, len(params))
         return img
 
     def clone(self) -> "OracleImage":

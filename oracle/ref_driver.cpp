@@ -23,6 +23,10 @@
 //   dump   <in.fuif> <prefix>  [-R k]     planes after decode and after each inverse transform
 //   fwd    <in.pam>  <prefix>  [same options as encode]   planes after each forward transform
 //   time   <in.fuif> [reps] [out.pam]     JSON timing of entropy stage / transform chain; optionally writes the pixels
+//   subsample <in.pam> <prefix> <p0[,p1,...]> [-F]   chroma planes decimated by this driver (the reference has no forward
+//                                         subsampling), TRANSFORM_ChromaSubsample pushed with these parameters; dumps
+//                                         <prefix>.b.fbpd, then the reference's inv_subsample -> <prefix>.a.fbpd;
+//                                         -F: also encodes the subsampled image to <prefix>.fuif first
 //
 // Plane dump format ("FBPD1"): text header, then raw little-endian int16 planes:
 //   FBPD1
@@ -154,7 +158,7 @@ static double now_s() {
 
 int main(int argc, char **argv) {
     if (argc < 3) {
-        fprintf(stderr, "usage: %s encode|decode|dump|fwd|time ...\n", argv[0]);
+        fprintf(stderr, "usage: %s encode|decode|dump|fwd|time|subsample ...\n", argv[0]);
         return 2;
     }
     std::string cmd = argv[1];
@@ -193,6 +197,54 @@ int main(int argc, char **argv) {
             if (img.error) return 1;
             write_dump(prefix + ".s" + std::to_string(step++) + ".fbpd", img);
         }
+        return 0;
+    }
+    if (cmd == "subsample") {
+        if (argc < 5) return 2;
+        Image img = read_PAM_file(argv[2]);
+        if (!img.w) { fprintf(stderr, "cannot read %s\n", argv[2]); return 1; }
+        std::string prefix = argv[3];
+        std::vector<int> params;
+        for (char *tok = strtok(argv[4], ","); tok; tok = strtok(nullptr, ",")) params.push_back(atoi(tok));
+        std::vector<int> full = params;
+        if (full.size() == 1) {     // the abbreviations of check_subsample_parameters (subsample.h:33-69), spelled out for the decimation below
+            static const int ab[4][2] = {{2, 2}, {2, 1}, {1, 2}, {4, 1}};
+            int k = full[0];
+            if (k < 0 || k > 3) return 2;
+            full = {1, 2, ab[k][0], ab[k][1]};
+        }
+        if (full.size() % 4) return 2;
+        for (size_t i = 0; i < full.size(); i += 4)
+            for (int c = full[i]; c <= full[i + 1]; c++) {
+                if (c < 0 || c >= (int)img.channel.size()) return 2;
+                const Channel &in = img.channel[c];
+                const int srh = full[i + 2], srv = full[i + 3];
+                Channel out((in.w + srh - 1) / srh, (in.h + srv - 1) / srv, in.minval, in.maxval, in.q, in.hshift + (srh == 1 ? 0 : 1), in.vshift + (srv == 1 ? 0 : 1),
+                            in.hcshift, in.vcshift);
+                out.component = in.component;
+                for (int y = 0; y < out.h; y++)
+                    for (int x = 0; x < out.w; x++) {       // box average over the cell (edge cells are smaller)
+                        int sum = 0, n = 0;
+                        for (int dy = 0; dy < srv; dy++) for (int dx = 0; dx < srh; dx++)
+                            if (y * srv + dy < in.h && x * srh + dx < in.w) { sum += in.value(y * srv + dy, x * srh + dx); n++; }
+                        out.value(y, x) = (pixel_type)((sum + n / 2) / n);
+                    }
+                img.channel[c] = out;
+            }
+        Transform t(TRANSFORM_ChromaSubsample);
+        t.parameters = params;
+        img.transform.push_back(t);
+        bool want_file = false;
+        for (int i = 5; i < argc; i++) if (!strcmp(argv[i], "-F")) want_file = true;
+        if (want_file) {
+            fuif_options options = default_fuif_options;
+            fuif_prepare_encode(img, options);
+            if (!fuif_encode_file((prefix + ".fuif").c_str(), img, options)) return 1;
+        }
+        write_dump(prefix + ".b.fbpd", img);
+        img.undo_transforms((int)img.transform.size() - 1);
+        if (img.error) return 1;
+        write_dump(prefix + ".a.fbpd", img);
         return 0;
     }
     if (cmd == "time") {

@@ -23,3 +23,18 @@ CASES = [
     ("one", 1, 1, 3, 255, 14, []),
     ("sq128", 128, 96, 3, 255, 15, []),
 ]
+
+# ChromaSubsample (reference transform/subsample.h): name, w, h, channels, maxval, seed, transform parameters, also as a file?
+# One abbreviated parameter = 4:2:0 / 4:2:2 / 4:4:0 / 4:1:1; four = (first channel, last channel, ratio_h, ratio_v).
+# Odd sizes make the upscaled planes larger than the image; 4:1:1 and 3x3 take the box-filter branch (no file: the
+# bitstream's meta step only allows ratios 1 and 2).
+SUBSAMPLE_CASES = [
+    ("420", 64, 48, 3, 255, 31, [0], True),
+    ("420odd", 37, 29, 3, 255, 32, [0], True),
+    ("422", 50, 21, 3, 255, 33, [1], True),
+    ("440", 33, 40, 3, 255, 34, [2], True),
+    ("411", 64, 20, 3, 255, 35, [3], False),
+    ("box3", 31, 17, 3, 1023, 36, [1, 2, 3, 3], False),
+    ("one_chan", 40, 30, 4, 16383, 37, [2, 2, 2, 2], True),
+    ("tiny", 2, 3, 3, 255, 38, [0], True),
+]
