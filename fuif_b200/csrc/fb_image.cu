@@ -556,6 +556,69 @@ static int do_quantize(fb_image *img, bool inverse, const std::vector<int> &p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// ChromaSubsample (reference transform/subsample.h): inverse + meta; the reference has no forward (:130-133)
+// ---------------------------------------------------------------------------------------------------------
+
+// check_subsample_parameters, subsample.h:33-69: one abbreviated parameter = 4:2:0 / 4:2:2 / 4:4:0 / 4:1:1; a list that is not
+// a multiple of four is "invalid" and cleared (the transform then does nothing)
+static std::vector<int> subsample_parameters(const std::vector<int> &p) {
+    if (p.size() == 1 && p[0] >= 0 && p[0] <= 3) {
+        static const int ab[4][2] = {{2, 2}, {2, 1}, {1, 2}, {4, 1}};
+        return {1, 2, ab[p[0]][0], ab[p[0]][1]};
+    }
+    if (p.size() % 4) return {};
+    return p;
+}
+
+// inv_subsample, subsample.h:73-128.  The upscaled plane is a fresh Channel(w*srh, h*srv, minval, maxval): shifts, q and
+// component go back to their defaults, and its size can exceed the image's (odd dimensions), exactly as in the reference.
+static int inv_subsample(fb_image *img, const std::vector<int> &params) {
+    fb_ctx *ctx = img->ctx;
+    const std::vector<int> p = subsample_parameters(params);
+    const int nch = (int)img->ch.size();
+    for (size_t i = 0; i + 3 < p.size(); i += 4) {
+        const int c1 = p[i], c2 = p[i + 1], srh = p[i + 2], srv = p[i + 3];
+        if (c1 < 0 || c2 >= nch || srh < 1 || srv < 1 || srh > 64 || srv > 64) { ctx->err = "inv_subsample: bad parameters"; return FB_ERR_INVALID; }
+        for (int c = c1; c <= c2; c++) {
+            FbChan &in = img->ch[c];
+            const FbChan &ref = img->ch[img->info.nb_meta_channels];
+            if (in.d.w >= ref.d.w && in.d.h >= ref.d.h) continue;       // LQIP / 1:16 decodes: already as large as the first channel
+            if ((long long)in.d.w * srh * (long long)in.d.h * srv > 0x7fffffffLL) { ctx->err = "inv_subsample: plane too large"; return FB_ERR_UNSUPPORTED; }
+            int rc = chan_materialize(ctx, in);         // reads of an undecoded plane give `zero` (image.h:82)
+            if (rc) return rc;
+            FbChan out;
+            chan_defaults(out.d);
+            out.d.w = in.d.w * srh; out.d.h = in.d.h * srv; out.d.minval = in.d.minval; out.d.maxval = in.d.maxval;
+            chan_setzero(out.d);
+            out.d.decoded = 1;
+            rc = fb_plane_alloc(ctx, chan_samples(out.d), &out.dev);
+            if (rc) return rc;
+            rc = fb_launch_inv_subsample(ctx, in.dev, out.dev, in.d.w, in.d.h, srh, srv);
+            if (rc) { fb_plane_free(ctx, out.dev); return rc; }
+            fb_plane_free(ctx, in.dev);         // stream-ordered: released after the kernel above
+            in = out;
+        }
+    }
+    return FB_OK;
+}
+
+// meta_subsample, subsample.h:135-157 (the reference asserts ratios of 1 or 2 here)
+static int meta_subsample(fb_image *img, const std::vector<int> &params) {
+    const std::vector<int> p = subsample_parameters(params);
+    const int nch = (int)img->ch.size();
+    for (size_t i = 0; i + 3 < p.size(); i += 4) {
+        const int c1 = p[i], c2 = p[i + 1], srh = p[i + 2], srv = p[i + 3];
+        if ((srh != 1 && srh != 2) || (srv != 1 && srv != 2) || c1 < 0 || c2 >= nch) { img->ctx->err = "meta_subsample: bad parameters"; return FB_ERR_INVALID; }
+        for (int c = c1; c <= c2; c++) {
+            fb_plane_desc &d = img->ch[c].d;
+            d.w = (d.w + srh - 1) / srh; d.h = (d.h + srv - 1) / srv;
+            d.hshift += srh == 1 ? 0 : 1; d.vshift += srv == 1 ? 0 : 1;
+        }
+    }
+    return FB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Transform dispatch (reference transform/transform.cpp:48-81)
 // ---------------------------------------------------------------------------------------------------------
 
@@ -564,6 +627,7 @@ static int transform_meta_apply(fb_image *img, FbXform &t) {
     case FB_TRANSFORM_YCBCR: case FB_TRANSFORM_YCOCG: case FB_TRANSFORM_QUANTIZE: return FB_OK;
     case FB_TRANSFORM_SQUEEZE: return meta_squeeze(img, t.p);
     case FB_TRANSFORM_DCT: return meta_dct(img, t.p);
+    case FB_TRANSFORM_SUBSAMPLE: return meta_subsample(img, t.p);
     default:
         img->ctx->err = "transform " + std::to_string(t.id) + " is outside the hot path (SURVEY.md 8: out of scope)";
         return FB_ERR_UNSUPPORTED;
@@ -611,6 +675,7 @@ extern "C" int fb_image_undo_transforms(fb_image *img, int keep) {
             break;
         }
         case FB_TRANSFORM_DCT: rc = inv_dct(img, t.p); break;
+        case FB_TRANSFORM_SUBSAMPLE: rc = inv_subsample(img, t.p); break;
         default:
             ctx->err = "cannot undo transform " + std::to_string(t.id) + " (outside the hot path)";
             rc = FB_ERR_UNSUPPORTED;
@@ -643,6 +708,7 @@ extern "C" int fb_image_do_transform(fb_image *img, int32_t id, const int32_t *p
     case FB_TRANSFORM_QUANTIZE: rc = do_quantize(img, false, t.p); applied = rc == FB_OK; break;
     case FB_TRANSFORM_SQUEEZE: rc = fwd_squeeze(img, t.p); applied = rc == FB_OK; break;
     case FB_TRANSFORM_DCT: rc = fwd_dct(img, t.p, &applied); break;
+    case FB_TRANSFORM_SUBSAMPLE: applied = 0; break;       // fwd_subsample is a stub in the reference: "return false"
     default:
         img->ctx->err = "transform " + std::to_string(id) + " is outside the hot path";
         rc = FB_ERR_UNSUPPORTED;

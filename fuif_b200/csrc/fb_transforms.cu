@@ -7,6 +7,7 @@
 #include "fb_common.cuh"
 #include "fb_fused_plan.h"
 #include "fb_direct_plan.h"
+#include "fb_subsample.cuh"
 
 #include <stdlib.h>
 
@@ -1147,6 +1148,16 @@ int fb_launch_minmax(fb_ctx *ctx, const int16_t *p, size_t n, int *out2_dev) {
     if (nb > 1184) nb = 1184;
     k_minmax<<<nb, 256, 0, ctx->stream>>>(p, n, out2_dev);
     FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}
+int fb_launch_inv_subsample(fb_ctx *ctx, const int16_t *in, int16_t *out, int ow, int oh, int srh, int srv) {
+    const size_t n = (size_t)ow * srh * (size_t)oh * srv;
+    if (!n) return FB_OK;
+    sb::k_inv_subsample<<<nblocks(n, 256), 256, 0, ctx->stream>>>(in, out, ow, oh, srh, srv);
+    ctx->launches++;
+    ctx->mark("k_inv_subsample", 2.0 * ((double)ow * oh + (double)n));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e); return FB_ERR_CUDA; }
     return FB_OK;
 }
 int fb_launch_interleave(fb_ctx *ctx, const int16_t *const *planes, int nch, size_t npix, int bps, void *dst) {

@@ -155,7 +155,7 @@ FB_API int fb_image_download_interleaved(fb_image *img, int n_channels, int byte
 /* Replaces Image::undo_transforms(keep) (reference image/image.cpp:94-115): pops and inverts transforms until
  * `keep` are left, then (keep == 0) clamps every sample to [minval, maxval].  Runs entirely on the GPU:
  * Squeeze (transform/squeeze.h:363-388), Quantize (quantize.h:32-49), DCT (dct.h:249-296),
- * YCbCr (ycbcr.h:33-63), YCoCg (ycocg.h:33-63). */
+ * YCbCr (ycbcr.h:33-63), YCoCg (ycocg.h:33-63), ChromaSubsample (subsample.h:73-128). */
 FB_API int fb_image_undo_transforms(fb_image *img, int keep);
 
 /* Replaces Image::do_transform (reference image/image.cpp:117-122; forward direction of the same transforms).

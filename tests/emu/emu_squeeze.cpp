@@ -7,8 +7,16 @@
 #include <vector>
 
 #include "fb_fused_plan.h"
+#include "fb_subsample.cuh"
 
 extern "C" {
+
+// the chroma upscaling kernel on one plane: in (ow x oh) -> out (ow*srh x oh*srv)
+void emu_inv_subsample(const int16_t *in, int16_t *out, int ow, int oh, int srh, int srv) {
+    const size_t n = (size_t)ow * srh * (size_t)oh * srv;
+    if (!n) return;
+    cuemu::launch((unsigned)((n + 255) / 256), 256, 0, false, [&]() { sb::k_inv_subsample(in, out, ow, oh, srh, srv); });
+}
 
 // opdesc[nops][9] = step, horizontal, avg plane, res plane (-1: none), out plane, wa, wr, ha, hr
 // ep[8] = kind, maxval, lo, hi, do_clamp, Y plane, Co plane, Cg plane

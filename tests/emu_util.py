@@ -14,7 +14,7 @@ LIB = os.path.join(EMU_DIR, "libfb_emu.so")
 SRCS = [os.path.join(EMU_DIR, "emu_squeeze.cpp"), os.path.join(EMU_DIR, "cuemu.h"),
         os.path.join(ROOT, "fuif_b200", "csrc", "fb_fused_squeeze.cuh"), os.path.join(ROOT, "fuif_b200", "csrc", "fb_fused_plan.h"),
         os.path.join(ROOT, "fuif_b200", "csrc", "fb_port.h"), os.path.join(ROOT, "fuif_b200", "csrc", "fb_direct_squeeze.cuh"),
-        os.path.join(ROOT, "fuif_b200", "csrc", "fb_direct_plan.h")]
+        os.path.join(ROOT, "fuif_b200", "csrc", "fb_direct_plan.h"), os.path.join(ROOT, "fuif_b200", "csrc", "fb_subsample.cuh")]
 _lib = None
 
 
@@ -28,6 +28,8 @@ def lib():
         L.emu_run_plan.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.emu_check_pair.argtypes = [C.c_void_p] * 4 + [C.c_int]
         L.emu_run_direct.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.emu_inv_subsample.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.emu_inv_subsample.restype = None
         _lib = L
     return _lib
 
