@@ -761,6 +761,81 @@ static int meta_subsample(fo_image *img, const int *p0, int np0) {
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Approximate, transform/approximate.h: channel = quotient, extra channel at the end = remainder    */
+/* ------------------------------------------------------------------------------------------------ */
+
+static int approx_q(const int *p, int np, int c, int beginc) {      /* approximate.h:37: the last divisor repeats */
+    return c + 2 - beginc < np ? p[c + 2 - beginc] : p[np - 1];
+}
+
+/* meta_approximate, approximate.h:64-80: one copy of every approximated channel with a non-zero parameter goes to the end */
+static int meta_approximate(fo_image *img, const int *p, int np) {
+    if (np < 3) return 0;
+    const int nb = p[1] - p[0] + 1;
+    if (nb < 1 || p[0] < 0 || p[1] >= img->nch) return 0;
+    for (int c = p[0]; c <= p[1]; c++) {
+        if (!approx_q(p, np, c, p[0])) continue;
+        fo_channel d = img->ch[c];
+        d.data = (int16_t *)malloc(d.n * sizeof(int16_t) + 2);
+        if (d.n) memcpy(d.data, img->ch[c].data, d.n * sizeof(int16_t));
+        img_insert(img, img->nch, &d);
+    }
+    return 1;
+}
+
+/* fwd_approximate, approximate.h:83-113: floor division by q+1, remainder in [0, q] */
+static int fwd_approximate(fo_image *img, const int *p, int np) {
+    const int offset = img->nch;
+    if (!meta_approximate(img, p, np)) { img->error = 1; return 1; }    /* the reference sets image.error and still returns true */
+    const int beginc = p[0], endc = p[1];
+    int i = 0;
+    for (int c = beginc; c <= endc; c++) {
+        const int q = approx_q(p, np, c, beginc) + 1;
+        if (q == 1) continue;
+        fo_channel *ch = &img->ch[c], *chr = &img->ch[offset + i];
+        i++;
+        for (size_t k = 0; k < ch->n; k++) {
+            const int v = ch->data[k];
+            int quotient = S16(v / q), r = S16(v % q);
+            if (r < 0) { quotient = S16(quotient - 1); r = S16(r + q); }
+            ch->data[k] = (int16_t)quotient;
+            chr->data[k] = (int16_t)r;
+        }
+        ch->minval = S16(ch->minval / q);
+        ch->maxval = S16(ch->maxval / q);
+        chr->minval = 0;
+        chr->maxval = S16(q - 1);
+        chr->q = ch->q;
+    }
+    return 1;
+}
+
+/* inv_approximate, approximate.h:32-62 */
+static int inv_approximate(fo_image *img, const int *p, int np) {
+    if (np < 3) return 0;               /* the reference would read past its parameter vector */
+    const int beginc = p[0], endc = p[1];
+    int offset = img->nch - (endc - beginc + 1);
+    for (int c = beginc; c <= endc; c++) if (!approx_q(p, np, c, beginc)) offset++;
+    if (beginc < 0 || endc >= img->nch || offset < 0 || offset > img->nch) return 0;
+    int i = 0;
+    for (int c = beginc; c <= endc; c++) {
+        const int q = approx_q(p, np, c, beginc) + 1;
+        if (q == 1) continue;
+        fo_channel *ch = &img->ch[c];
+        const fo_channel *chr = &img->ch[offset + i];
+        i++;
+        if (chr->n) ch->q = chr->q;
+        for (int y = 0; y < ch->h; y++) for (int x = 0; x < ch->w; x++) {
+            int v = S16(ch_get(ch, y, x) * q);
+            v = S16(v + (chr->n ? ch_get(chr, y, x) : 0));
+            ch_set(ch, y, x, v);
+        }
+    }
+    img_erase(img, offset, img->nch);
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* Transform dispatch (transform/transform.cpp:48-81) and Image::undo_transforms / do_transform       */
 /* ------------------------------------------------------------------------------------------------ */
 
@@ -783,7 +858,8 @@ static int transform_apply(fo_image *img, fo_transform *t, int inverse) {
             if (t->p[i] < 0 || t->p[i + 1] >= img->nch) return 0;
         }
         return inv_subsample(img, t->p, t->np);
-    default: return 0;       /* palette / 2dmatch / permute / approximate: out of scope */
+    case 10: return inverse ? inv_approximate(img, t->p, t->np) : fwd_approximate(img, t->p, t->np);
+    default: return 0;       /* palette / 2dmatch / permute: out of scope */
     }
 }
 
@@ -802,6 +878,7 @@ static int transform_meta_apply(fo_image *img, fo_transform *t) {
         if (t->np < 2) { t->p = (int *)realloc(t->p, 2 * sizeof(int)); t->np = 2; t->p[0] = 0; t->p[1] = img->nb_channels - 1; }
         return meta_dct(img, t->p);
     case FO_SUBSAMPLE: return meta_subsample(img, t->p, t->np);
+    case 10: return meta_approximate(img, t->p, t->np);
     default: return 0;
     }
 }

@@ -18,7 +18,7 @@
 //   fuif_decode_file           encoding/encoding.cpp:745
 //
 // Sub-commands:
-//   encode <in.pam> <out.fuif> [-C 0|1|2] [-J] [-S 0|1] [-q luma,chroma] [-E n] [-I f] [-G n] [-P digits]
+//   encode <in.pam> <out.fuif> [-C 0|1|2] [-J] [-S 0|1] [-q luma,chroma] [-E n] [-I f] [-G n] [-P digits] [-A k,q]
 //   decode <in.fuif> <out.pam> [-R k]
 //   dump   <in.fuif> <prefix>  [-R k]     planes after decode and after each inverse transform
 //   fwd    <in.pam>  <prefix>  [same options as encode]   planes after each forward transform
@@ -72,6 +72,7 @@ struct EncOpts {
     bool dct = false;
     bool squeeze = true;
     int qluma = 0, qchroma = 0;  // 0 = lossless
+    int approx_k = 0, approx_q = 0;     // -A k,q: TRANSFORM_APPROXIMATE on the last k channels with divisor q+1 (fuif.cpp:504-510)
     fuif_options options = default_fuif_options;
 };
 
@@ -87,6 +88,7 @@ static bool parse_enc_opts(int argc, char **argv, int start, EncOpts &o) {
         else if (a == "-I") o.options.nb_repeats = atof(need());
         else if (a == "-G") o.options.max_group = atoi(need());
         else if (a == "-U") o.options.compress = false;
+        else if (a == "-A") { if (sscanf(need(), "%d,%d", &o.approx_k, &o.approx_q) != 2) return false; }
         else if (a == "-P") { const char *s = need(); while (*s) { if (*s >= '0' && *s <= '9') o.options.predictor.push_back(*s - '0'); s++; } }
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return false; }
     }
@@ -136,6 +138,14 @@ static bool build_chain(Image &img, EncOpts &o, const std::string *dump_prefix) 
             quantize.parameters.push_back(q);
         }
         if (!img.do_transform(quantize)) return false;
+        dump();
+    }
+    if (o.approx_k > 0) {
+        Transform approximate(TRANSFORM_APPROXIMATE);
+        approximate.parameters.push_back((int)img.channel.size() - o.approx_k);
+        approximate.parameters.push_back((int)img.channel.size() - 1);
+        approximate.parameters.push_back(o.approx_q);
+        if (!img.do_transform(approximate)) return false;
         dump();
     }
     if (has_dct && o.squeeze) {

@@ -38,3 +38,13 @@ SUBSAMPLE_CASES = [
     ("one_chan", 40, 30, 4, 16383, 37, [2, 2, 2, 2], True),
     ("tiny", 2, 3, 3, 255, 38, [0], True),
 ]
+
+# Approximate (reference transform/approximate.h; ref_driver option -A k,q = the last k channels divided by q+1, remainders
+# appended as extra channels, as fuif.cpp:504-510 does).  Same tuple layout as CASES.
+APPROX_CASES = [
+    ("approx", 64, 48, 3, 255, 41, ["-A", "2,3"]),
+    ("approx_q", 50, 40, 3, 255, 42, ["-q", "12,64", "-A", "3,1"]),
+    ("approx_nosq", 40, 30, 3, 255, 43, ["-S", "0", "-A", "3,7"]),
+    ("approx_noop", 33, 31, 1, 255, 44, ["-S", "0", "-A", "1,0"]),
+    ("approx14", 48, 36, 4, 16383, 45, ["-A", "4,99"]),
+]

@@ -16,14 +16,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from fuif_b200.synth import synth_image, write_pnm  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402
-from tests.cases import CASES  # noqa: E402
+from tests.cases import APPROX_CASES, CASES  # noqa: E402
 
 
 def main():
     po.build()
     assert po.have_ref(), "oracle/_ref/ref_driver missing (needs /root/reference)"
     out_dir = os.path.dirname(os.path.abspath(__file__))
-    for name, w, h, c, maxval, seed, opts in CASES:
+    which = APPROX_CASES if "approx" in sys.argv[1:] else CASES      # python make_golden.py [approx]
+    for name, w, h, c, maxval, seed, opts in which:
         with tempfile.TemporaryDirectory() as td:
             pnm = os.path.join(td, "in.pnm")
             fuif = os.path.join(td, "x.fuif")
