@@ -619,6 +619,91 @@ static int meta_subsample(fb_image *img, const std::vector<int> &params) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Approximate (reference transform/approximate.h): parameters = first channel, last channel, divisor - 1 per channel (the
+// last one repeats; 0 = leave the channel alone).  Channel numbers are absolute (meta channels included), as in the reference.
+// ---------------------------------------------------------------------------------------------------------
+
+static int approx_param(const std::vector<int> &p, int c, int beginc) {      // approximate.h:37
+    const size_t k = (size_t)(c + 2 - beginc);
+    return k < p.size() ? p[k] : p.back();
+}
+
+// meta_approximate, approximate.h:64-80: a copy of every approximated channel (geometry, range, q) goes to the end of the list
+static int meta_approximate(fb_image *img, const std::vector<int> &p) {
+    if (p.size() < 3) { img->ctx->err = "Approximate: incorrect number of parameters"; return FB_ERR_INVALID; }
+    const int nb = p[1] - p[0] + 1;
+    if (nb < 1 || p[0] < 0 || p[1] >= (int)img->ch.size()) { img->ctx->err = "Approximate: incorrect parameters"; return FB_ERR_INVALID; }
+    for (int c = p[0]; c <= p[1]; c++) {
+        if (!approx_param(p, c, p[0])) continue;
+        FbChan r;
+        r.d = img->ch[c].d;
+        r.d.decoded = 0;
+        r.dev = nullptr;
+        img->ch.push_back(r);
+    }
+    return FB_OK;
+}
+
+// fwd_approximate, approximate.h:83-113
+static int fwd_approximate(fb_image *img, const std::vector<int> &p) {
+    fb_ctx *ctx = img->ctx;
+    const int offset = (int)img->ch.size();
+    int rc = meta_approximate(img, p);
+    if (rc) return rc;
+    int i = 0;
+    for (int c = p[0]; c <= p[1]; c++) {
+        const int q = approx_param(p, c, p[0]) + 1;
+        if (q == 1) continue;
+        if (q < 1) { ctx->err = "Approximate: negative divisor"; return FB_ERR_INVALID; }
+        FbChan &ch = img->ch[c], &chr = img->ch[offset + i];
+        i++;
+        if ((rc = chan_materialize(ctx, ch))) return rc;
+        if ((rc = fb_plane_alloc(ctx, chan_samples(ch.d), &chr.dev))) return rc;
+        chr.d.decoded = 1;
+        if ((rc = fb_launch_approximate(ctx, ch.dev, chr.dev, chan_samples(ch.d), q, 0))) return rc;
+        ch.d.minval = s16(ch.d.minval / q); ch.d.maxval = s16(ch.d.maxval / q);
+        chr.d.minval = 0; chr.d.maxval = s16(q - 1);
+        chr.d.q = ch.d.q;       // the quantisation factor travels with the remainder in case the quotient becomes all zero
+    }
+    return FB_OK;
+}
+
+// inv_approximate, approximate.h:32-62
+static int inv_approximate(fb_image *img, const std::vector<int> &p) {
+    fb_ctx *ctx = img->ctx;
+    if (p.size() < 3) { ctx->err = "Approximate: incorrect number of parameters"; return FB_ERR_INVALID; }
+    const int beginc = p[0], endc = p[1], nch = (int)img->ch.size();
+    int offset = nch - (endc - beginc + 1);
+    for (int c = beginc; c <= endc; c++) if (beginc <= endc && !approx_param(p, c, beginc)) offset++;
+    if (beginc < 0 || endc >= nch || endc < beginc || offset <= endc || offset > nch) { ctx->err = "Approximate: incorrect parameters"; return FB_ERR_INVALID; }
+    int i = 0;
+    for (int c = beginc; c <= endc; c++) {
+        const int q = approx_param(p, c, beginc) + 1;
+        if (q == 1) continue;
+        if (offset + i >= nch) { ctx->err = "Approximate: remainder channel missing"; return FB_ERR_INVALID; }
+        FbChan &ch = img->ch[c];
+        const FbChan &chr = img->ch[offset + i];
+        i++;
+        if (chr.dev) ch.d.q = chr.d.q;
+        const size_t n = chan_samples(ch.d);
+        if (ch.dev) {
+            if (chr.dev && chan_samples(chr.d) != n) { ctx->err = "Approximate: remainder channel of a different size"; return FB_ERR_INVALID; }
+            int rc = fb_launch_approximate(ctx, ch.dev, chr.dev, n, q, 1);
+            if (rc) return rc;
+        } else {
+            // an undecoded channel has no samples: every ch.value(y, x) of the reference's loop is the channel's `zero`
+            // (image.h:84 returns a reference to it), which is therefore multiplied w*h times
+            int z = ch.d.zero;
+            for (size_t k = 0; k < n && z != 0; k++) z = s16(z * q);
+            ch.d.zero = z;
+        }
+    }
+    for (int c = offset; c < nch; c++) if (img->ch[c].dev) fb_plane_free(ctx, img->ch[c].dev);
+    img->ch.erase(img->ch.begin() + offset, img->ch.end());
+    return FB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Transform dispatch (reference transform/transform.cpp:48-81)
 // ---------------------------------------------------------------------------------------------------------
 
@@ -628,6 +713,7 @@ static int transform_meta_apply(fb_image *img, FbXform &t) {
     case FB_TRANSFORM_SQUEEZE: return meta_squeeze(img, t.p);
     case FB_TRANSFORM_DCT: return meta_dct(img, t.p);
     case FB_TRANSFORM_SUBSAMPLE: return meta_subsample(img, t.p);
+    case FB_TRANSFORM_APPROXIMATE: return meta_approximate(img, t.p);
     default:
         img->ctx->err = "transform " + std::to_string(t.id) + " is outside the hot path (SURVEY.md 8: out of scope)";
         return FB_ERR_UNSUPPORTED;
@@ -676,6 +762,7 @@ extern "C" int fb_image_undo_transforms(fb_image *img, int keep) {
         }
         case FB_TRANSFORM_DCT: rc = inv_dct(img, t.p); break;
         case FB_TRANSFORM_SUBSAMPLE: rc = inv_subsample(img, t.p); break;
+        case FB_TRANSFORM_APPROXIMATE: rc = inv_approximate(img, t.p); break;
         default:
             ctx->err = "cannot undo transform " + std::to_string(t.id) + " (outside the hot path)";
             rc = FB_ERR_UNSUPPORTED;
@@ -708,6 +795,7 @@ extern "C" int fb_image_do_transform(fb_image *img, int32_t id, const int32_t *p
     case FB_TRANSFORM_QUANTIZE: rc = do_quantize(img, false, t.p); applied = rc == FB_OK; break;
     case FB_TRANSFORM_SQUEEZE: rc = fwd_squeeze(img, t.p); applied = rc == FB_OK; break;
     case FB_TRANSFORM_DCT: rc = fwd_dct(img, t.p, &applied); break;
+    case FB_TRANSFORM_APPROXIMATE: rc = fwd_approximate(img, t.p); applied = rc == FB_OK; break;
     case FB_TRANSFORM_SUBSAMPLE: applied = 0; break;       // fwd_subsample is a stub in the reference: "return false"
     default:
         img->ctx->err = "transform " + std::to_string(id) + " is outside the hot path";

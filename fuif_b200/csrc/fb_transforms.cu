@@ -8,6 +8,7 @@
 #include "fb_fused_plan.h"
 #include "fb_direct_plan.h"
 #include "fb_subsample.cuh"
+#include "fb_approx.cuh"
 
 #include <stdlib.h>
 
@@ -1148,6 +1149,16 @@ int fb_launch_minmax(fb_ctx *ctx, const int16_t *p, size_t n, int *out2_dev) {
     if (nb > 1184) nb = 1184;
     k_minmax<<<nb, 256, 0, ctx->stream>>>(p, n, out2_dev);
     FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}
+int fb_launch_approximate(fb_ctx *ctx, int16_t *ch, int16_t *chr, size_t n, int q, int inverse) {
+    if (!n) return FB_OK;
+    if (inverse) ap::k_approx_inv<<<nblocks(n, 256), 256, 0, ctx->stream>>>(ch, chr, n, q);
+    else ap::k_approx_fwd<<<nblocks(n, 256), 256, 0, ctx->stream>>>(ch, chr, n, q);
+    ctx->launches++;
+    ctx->mark(inverse ? "k_approx_inv" : "k_approx_fwd", 2.0 * (double)n * (chr ? 3 : 2));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e); return FB_ERR_CUDA; }
     return FB_OK;
 }
 int fb_launch_inv_subsample(fb_ctx *ctx, const int16_t *in, int16_t *out, int ow, int oh, int srh, int srv) {

@@ -8,8 +8,17 @@
 
 #include "fb_fused_plan.h"
 #include "fb_subsample.cuh"
+#include "fb_approx.cuh"
 
 extern "C" {
+
+// the Approximate kernels on one channel (+ its remainder channel; chr may be NULL for the inverse)
+void emu_approximate(int16_t *ch, int16_t *chr, long long n, int q, int inverse) {
+    if (n <= 0) return;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    if (inverse) cuemu::launch(nb, 256, 0, false, [&]() { ap::k_approx_inv(ch, chr, (size_t)n, q); });
+    else cuemu::launch(nb, 256, 0, false, [&]() { ap::k_approx_fwd(ch, chr, (size_t)n, q); });
+}
 
 // the chroma upscaling kernel on one plane: in (ow x oh) -> out (ow*srh x oh*srv)
 void emu_inv_subsample(const int16_t *in, int16_t *out, int ow, int oh, int srh, int srv) {
