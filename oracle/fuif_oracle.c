@@ -761,6 +761,94 @@ static int meta_subsample(fo_image *img, const int *p0, int np0) {
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Palette, transform/palette.h: channels begin..end become one index channel + a palette meta-channel */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* meta_palette, palette.h:70-89 */
+static int meta_palette(fo_image *img, const int *p, int np) {
+    if (np != 3) return 0;
+    const int begin_c = img->nb_meta_channels + p[0], end_c = img->nb_meta_channels + p[1];
+    if (p[0] < 0 || begin_c > end_c || end_c >= img->nch) return 0;
+    const int nb = end_c - begin_c + 1, nb_colors = p[2];
+    img->nb_meta_channels++;
+    img->nb_channels -= nb - 1;
+    img_erase(img, begin_c + 1, end_c + 1);
+    fo_channel pch;
+    ch_make(&pch, nb_colors, nb, 0, 1, 1, 0, 0, 0, 0);
+    pch.hshift = -1;
+    img_insert(img, 0, &pch);
+    return 1;
+}
+
+/* fwd_palette, palette.h:92-143: the colours in use, in lexicographic order (std::set of vectors); false when there are too many */
+static int palette_cmp_nb;
+static int palette_cmp(const void *a, const void *b) {
+    const int16_t *x = (const int16_t *)a, *y = (const int16_t *)b;
+    for (int i = 0; i < palette_cmp_nb; i++) if (x[i] != y[i]) return x[i] < y[i] ? -1 : 1;
+    return 0;
+}
+static int fwd_palette(fo_image *img, int *p, int np) {
+    if (np != 3) return 0;
+    const int begin_c = img->nb_meta_channels + p[0], end_c = img->nb_meta_channels + p[1];
+    if (p[0] < 0 || begin_c > end_c || end_c >= img->nch) return 0;
+    const int nb = end_c - begin_c + 1;
+    const int w = img->ch[begin_c].w, h = img->ch[begin_c].h;
+    const size_t n = (size_t)w * h;
+    int16_t *cols = (int16_t *)malloc((n + 1) * (size_t)nb * sizeof(int16_t));
+    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++)
+        for (int c = 0; c < nb; c++) cols[((size_t)y * w + x) * nb + c] = (int16_t)ch_get(&img->ch[begin_c + c], y, x);
+    palette_cmp_nb = nb;
+    qsort(cols, n, (size_t)nb * sizeof(int16_t), palette_cmp);
+    size_t count = 0;
+    for (size_t k = 0; k < n; k++)
+        if (!count || palette_cmp(cols + (count - 1) * nb, cols + k * nb)) { memmove(cols + count * nb, cols + k * nb, (size_t)nb * sizeof(int16_t)); count++; }
+    if ((long long)count > (long long)p[2]) { free(cols); return 0; }      /* too many colours */
+    p[2] = (int)count;
+    fo_channel pch;
+    ch_make(&pch, (int)count, nb, 0, 1, 1, 0, 0, 0, 0);
+    pch.hshift = -1;
+    for (size_t k = 0; k < count; k++) for (int c = 0; c < nb; c++) ch_set(&pch, c, (int)k, cols[k * nb + c]);
+    int16_t key[64];
+    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+        for (int c = 0; c < nb && c < 64; c++) key[c] = (int16_t)ch_get(&img->ch[begin_c + c], y, x);
+        size_t lo = 0, hi = count;         /* position of the colour in the sorted palette */
+        while (lo < hi) { size_t mid = (lo + hi) / 2; if (palette_cmp(cols + mid * nb, key) < 0) lo = mid + 1; else hi = mid; }
+        ch_set(&img->ch[begin_c], y, x, (int)lo);
+    }
+    free(cols);
+    img->nb_meta_channels++;
+    img->nb_channels -= nb - 1;
+    img_erase(img, begin_c + 1, end_c + 1);
+    img_insert(img, 0, &pch);
+    return 1;
+}
+
+/* inv_palette, palette.h:32-68 */
+static int inv_palette(fo_image *img, const int *p, int np) {
+    if (img->nb_meta_channels < 1 || np != 3) return 0;
+    const int nb = img->ch[0].h;
+    const int c0 = img->nb_meta_channels + p[0];
+    if (p[0] < 0 || c0 >= img->nch) return 0;
+    const int w = img->ch[c0].w, h = img->ch[c0].h;
+    for (int i = 1; i < nb; i++) {
+        fo_channel d;
+        ch_make(&d, w, h, 0, 1, 1, 0, 0, 0, 0);
+        img_insert(img, c0 + 1, &d);
+        img->ch[c0 + i].component = p[0] + i;       /* as written in the reference: the channel at c0+i, whichever it is by now */
+    }
+    const fo_channel *pal = &img->ch[0];
+    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+        int index = ch_get(&img->ch[c0], y, x);
+        index = CLAMPI(index, 0, pal->w - 1);
+        for (int c = 0; c < nb; c++) ch_set(&img->ch[c0 + c], y, x, ch_get(pal, c, index));
+    }
+    img->nb_channels += nb - 1;
+    img->nb_meta_channels--;
+    img_erase(img, 0, 1);
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* Approximate, transform/approximate.h: channel = quotient, extra channel at the end = remainder    */
 /* ------------------------------------------------------------------------------------------------ */
 
@@ -858,6 +946,7 @@ static int transform_apply(fo_image *img, fo_transform *t, int inverse) {
             if (t->p[i] < 0 || t->p[i + 1] >= img->nch) return 0;
         }
         return inv_subsample(img, t->p, t->np);
+    case FO_PALETTE: return inverse ? inv_palette(img, t->p, t->np) : fwd_palette(img, t->p, t->np);
     case 10: return inverse ? inv_approximate(img, t->p, t->np) : fwd_approximate(img, t->p, t->np);
     default: return 0;       /* palette / 2dmatch / permute: out of scope */
     }
@@ -879,6 +968,7 @@ static int transform_meta_apply(fo_image *img, fo_transform *t) {
         return meta_dct(img, t->p);
     case FO_SUBSAMPLE: return meta_subsample(img, t->p, t->np);
     case 10: return meta_approximate(img, t->p, t->np);
+    case FO_PALETTE: return meta_palette(img, t->p, t->np);
     default: return 0;
     }
 }

@@ -48,3 +48,13 @@ APPROX_CASES = [
     ("approx_noop", 33, 31, 1, 255, 44, ["-S", "0", "-A", "1,0"]),
     ("approx14", 48, 36, 4, 16383, 45, ["-A", "4,99"]),
 ]
+
+# Palette (reference transform/palette.h; ref_driver option -L n = one palette over all channels with at most n colours, after
+# the colour transform, as fuif.cpp:398-407 does).  The input of these cases is the synthetic image reduced to four levels per
+# channel (tests/golden/make_golden.py), so that it has few colours.  Same tuple layout as CASES.
+PALETTE_CASES = [
+    ("pal", 48, 40, 3, 255, 51, ["-L", "512"]),
+    ("pal_nosq", 37, 29, 3, 255, 52, ["-S", "0", "-L", "1000"]),
+    ("pal4", 40, 30, 4, 255, 53, ["-L", "4000"]),
+    ("pal_c0", 33, 27, 3, 255, 54, ["-C", "0", "-S", "0", "-L", "300"]),
+]

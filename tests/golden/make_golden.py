@@ -16,19 +16,22 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from fuif_b200.synth import synth_image, write_pnm  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402
-from tests.cases import APPROX_CASES, CASES  # noqa: E402
+from tests.cases import APPROX_CASES, CASES, PALETTE_CASES  # noqa: E402
 
 
 def main():
     po.build()
     assert po.have_ref(), "oracle/_ref/ref_driver missing (needs /root/reference)"
     out_dir = os.path.dirname(os.path.abspath(__file__))
-    which = APPROX_CASES if "approx" in sys.argv[1:] else CASES      # python make_golden.py [approx]
+    which = APPROX_CASES if "approx" in sys.argv[1:] else PALETTE_CASES if "palette" in sys.argv[1:] else CASES      # python make_golden.py [approx|palette]
     for name, w, h, c, maxval, seed, opts in which:
         with tempfile.TemporaryDirectory() as td:
             pnm = os.path.join(td, "in.pnm")
             fuif = os.path.join(td, "x.fuif")
-            write_pnm(pnm, synth_image(w, h, c, maxval, seed), maxval)
+            pix = synth_image(w, h, c, maxval, seed)
+            if name.startswith("pal"):
+                pix = (pix // 64) * 64 + 17         # four levels per channel: few colours
+            write_pnm(pnm, pix, maxval)
             po.ref_run("encode", pnm, fuif, *opts)
             po.ref_run("dump", fuif, os.path.join(td, "d"))
             po.ref_run("fwd", pnm, os.path.join(td, "d"), *opts)

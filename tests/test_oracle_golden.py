@@ -2,9 +2,9 @@
 import numpy as np
 import pytest
 
-from tests.cases import APPROX_CASES, CASES
+from tests.cases import APPROX_CASES, CASES, PALETTE_CASES
 
-ALL_CASES = CASES + APPROX_CASES
+ALL_CASES = CASES + APPROX_CASES + PALETTE_CASES
 from tests.util import load_golden, ordered
 from fuif_b200.synth import read_pnm  # noqa: F401
 
@@ -43,12 +43,12 @@ def test_forward_chain(oracle, case):
     po.compare_plane_images(oi.to_plane_image(), steps[0], name + " f0")
     k = 1
     for tid, params in steps[-1].transforms:
-        assert oi.do_transform(tid, params if tid in (4, 5, 10) else [])
+        assert oi.do_transform(tid, params if tid in (4, 5, 6, 10) else [])
         po.compare_plane_images(oi.to_plane_image(), steps[k], f"{name} f{k}")
         k += 1
 
 
-@pytest.mark.parametrize("case", [c for c in ALL_CASES if c[0] in ("odd", "sq128", "rgba14", "dct", "gray", "approx", "approx_q", "approx14")], ids=lambda c: c[0])
+@pytest.mark.parametrize("case", [c for c in ALL_CASES if c[0] in ("odd", "sq128", "rgba14", "dct", "gray", "approx", "approx_q", "approx14", "pal", "pal4")], ids=lambda c: c[0])
 @pytest.mark.parametrize("preview", [0, 1, 2, 3, 4])
 def test_responsive_decode(oracle, case, preview):
     """-R k partial decodes (encoding.cpp:704-716, squeeze.h:379-383)."""
