@@ -112,6 +112,8 @@ int fb_launch_clamp(fb_ctx *ctx, int16_t *p, size_t n, int lo, int hi);
 int fb_launch_inv_dct(fb_ctx *ctx, const int16_t *const *planes64_dev, int16_t *out, int bw, int bh, float dc_offset);
 // forward: samples (w x h, edge replicated) -> 64 planes (dct.h:298-336)
 int fb_launch_fwd_dct(fb_ctx *ctx, const int16_t *in, int w, int h, int16_t *const *planes64_dev, int bw, int bh, float dc_offset);
+// inv_palette (palette.h:32-68): out_planes[0] holds the indices and receives row 0 of the palette, planes 1..nb-1 the other rows
+int fb_launch_palette_inv(fb_ctx *ctx, int16_t *const *out_planes, int nb, const int16_t *palette, int ncolors, size_t n);
 // Approximate (approximate.h:32-113): inverse ch = ch*q + chr (chr may be nullptr), forward ch, chr = floor-div / remainder
 int fb_launch_approximate(fb_ctx *ctx, int16_t *ch, int16_t *chr, size_t n, int q, int inverse);
 // chroma upscaling of one plane (ow x oh -> ow*srh x oh*srv), subsample.h:73-128

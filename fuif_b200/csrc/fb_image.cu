@@ -619,6 +619,67 @@ static int meta_subsample(fb_image *img, const std::vector<int> &params) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Palette (reference transform/palette.h): parameters = first channel, last channel (relative to the meta channels), colours.
+// Inverse and decode-time meta step; fwd_palette (collecting the set of colours in use, :92-143) is not offered here.
+// ---------------------------------------------------------------------------------------------------------
+
+// meta_palette, palette.h:70-89: channels first+1..last disappear, a palette meta-channel (colours x channels, hshift -1) leads the list
+static int meta_palette(fb_image *img, const std::vector<int> &p) {
+    if (p.size() != 3) { img->ctx->err = "Palette: incorrect parameters"; return FB_ERR_INVALID; }
+    const int begin_c = img->info.nb_meta_channels + p[0], end_c = img->info.nb_meta_channels + p[1];
+    if (p[0] < 0 || begin_c > end_c || end_c >= (int)img->ch.size() || p[2] < 0) { img->ctx->err = "Palette: incorrect parameters"; return FB_ERR_INVALID; }
+    const int nb = end_c - begin_c + 1;
+    img->info.nb_meta_channels++;
+    img->info.nb_channels -= nb - 1;
+    for (int c = begin_c + 1; c <= end_c; c++) if (img->ch[c].dev) fb_plane_free(img->ctx, img->ch[c].dev);
+    img->ch.erase(img->ch.begin() + begin_c + 1, img->ch.begin() + end_c + 1);
+    FbChan pch;
+    chan_defaults(pch.d);
+    pch.d.w = p[2]; pch.d.h = nb; pch.d.minval = 0; pch.d.maxval = 1; pch.d.hshift = -1;
+    chan_setzero(pch.d);
+    img->ch.insert(img->ch.begin(), pch);
+    return FB_OK;
+}
+
+// inv_palette, palette.h:32-68
+static int inv_palette(fb_image *img, const std::vector<int> &p) {
+    fb_ctx *ctx = img->ctx;
+    if (img->info.nb_meta_channels < 1) { ctx->err = "Palette transform without palette"; return FB_ERR_INVALID; }
+    if (p.size() != 3) { ctx->err = "Palette: incorrect parameters"; return FB_ERR_INVALID; }
+    const int nb = img->ch[0].d.h;
+    const int c0 = img->info.nb_meta_channels + p[0];
+    if (p[0] < 0 || c0 >= (int)img->ch.size()) { ctx->err = "Palette: incorrect parameters"; return FB_ERR_INVALID; }
+    if (nb < 1 || nb > 8 || img->ch[0].d.w < 1) { ctx->err = "Palette: more than 8 channels or an empty palette"; return FB_ERR_UNSUPPORTED; }
+    if (!img->ch[c0].dev && chan_samples(img->ch[c0].d)) {
+        // the reference then reads AND writes the channel's `zero` once per pixel (image.h:84): not reproduced
+        ctx->err = "Palette: the index channel was not decoded";
+        return FB_ERR_UNSUPPORTED;
+    }
+    const int w = img->ch[c0].d.w, h = img->ch[c0].d.h;
+    for (int i = 1; i < nb; i++) {
+        FbChan d;
+        chan_defaults(d.d);
+        d.d.w = w; d.d.h = h; d.d.minval = 0; d.d.maxval = 1;
+        chan_setzero(d.d);
+        d.d.decoded = 1;
+        int rc = fb_plane_alloc(ctx, chan_samples(d.d), &d.dev);
+        if (rc) return rc;
+        img->ch.insert(img->ch.begin() + c0 + 1, d);
+        img->ch[c0 + i].d.component = p[0] + i;         // as written in the reference: the channel at c0+i, whichever it is by now
+    }
+    int rc = chan_materialize(ctx, img->ch[0]);         // an undecoded palette reads as `zero` everywhere
+    if (rc) return rc;
+    int16_t *outs[8];
+    for (int c = 0; c < nb; c++) outs[c] = img->ch[c0 + c].dev;
+    if ((rc = fb_launch_palette_inv(ctx, outs, nb, img->ch[0].dev, img->ch[0].d.w, chan_samples(img->ch[c0].d)))) return rc;
+    img->info.nb_channels += nb - 1;
+    img->info.nb_meta_channels--;
+    fb_plane_free(ctx, img->ch[0].dev);
+    img->ch.erase(img->ch.begin());
+    return FB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Approximate (reference transform/approximate.h): parameters = first channel, last channel, divisor - 1 per channel (the
 // last one repeats; 0 = leave the channel alone).  Channel numbers are absolute (meta channels included), as in the reference.
 // ---------------------------------------------------------------------------------------------------------
@@ -714,6 +775,7 @@ static int transform_meta_apply(fb_image *img, FbXform &t) {
     case FB_TRANSFORM_DCT: return meta_dct(img, t.p);
     case FB_TRANSFORM_SUBSAMPLE: return meta_subsample(img, t.p);
     case FB_TRANSFORM_APPROXIMATE: return meta_approximate(img, t.p);
+    case FB_TRANSFORM_PALETTE: return meta_palette(img, t.p);
     default:
         img->ctx->err = "transform " + std::to_string(t.id) + " is outside the hot path (SURVEY.md 8: out of scope)";
         return FB_ERR_UNSUPPORTED;
@@ -763,6 +825,7 @@ extern "C" int fb_image_undo_transforms(fb_image *img, int keep) {
         case FB_TRANSFORM_DCT: rc = inv_dct(img, t.p); break;
         case FB_TRANSFORM_SUBSAMPLE: rc = inv_subsample(img, t.p); break;
         case FB_TRANSFORM_APPROXIMATE: rc = inv_approximate(img, t.p); break;
+        case FB_TRANSFORM_PALETTE: rc = inv_palette(img, t.p); break;
         default:
             ctx->err = "cannot undo transform " + std::to_string(t.id) + " (outside the hot path)";
             rc = FB_ERR_UNSUPPORTED;

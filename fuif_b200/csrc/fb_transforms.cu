@@ -9,6 +9,7 @@
 #include "fb_direct_plan.h"
 #include "fb_subsample.cuh"
 #include "fb_approx.cuh"
+#include "fb_palette.cuh"
 
 #include <stdlib.h>
 
@@ -1149,6 +1150,18 @@ int fb_launch_minmax(fb_ctx *ctx, const int16_t *p, size_t n, int *out2_dev) {
     if (nb > 1184) nb = 1184;
     k_minmax<<<nb, 256, 0, ctx->stream>>>(p, n, out2_dev);
     FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}
+int fb_launch_palette_inv(fb_ctx *ctx, int16_t *const *out_planes, int nb, const int16_t *palette, int ncolors, size_t n) {
+    if (!n) return FB_OK;
+    if (nb < 1 || nb > pl::kMaxPlanes || ncolors < 1) return FB_ERR_UNSUPPORTED;
+    pl::Planes P;
+    for (int c = 0; c < pl::kMaxPlanes; c++) P.p[c] = c < nb ? out_planes[c] : nullptr;
+    pl::k_palette_inv<<<nblocks(n, 256), 256, 0, ctx->stream>>>(P, palette, n, ncolors, nb);
+    ctx->launches++;
+    ctx->mark("k_palette_inv", 2.0 * (double)n * (1 + nb));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e); return FB_ERR_CUDA; }
     return FB_OK;
 }
 int fb_launch_approximate(fb_ctx *ctx, int16_t *ch, int16_t *chr, size_t n, int q, int inverse) {

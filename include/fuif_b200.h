@@ -29,7 +29,7 @@ extern "C" {
 #define FB_OK 0
 #define FB_ERR_INVALID 1      /* bad argument / malformed stream ("return false" in the reference)            */
 #define FB_ERR_CUDA 2         /* CUDA runtime error; fb_last_error() has the text                            */
-#define FB_ERR_UNSUPPORTED 3  /* transform outside the hot path (palette, 2dmatch, permute)              */
+#define FB_ERR_UNSUPPORTED 3  /* outside the hot path (2dmatch, permute, building a palette)            */
 #define FB_ERR_NOMEM 4
 
 /* transform ids, reference transform/transform.h:30-70 */
@@ -38,6 +38,7 @@ extern "C" {
 #define FB_TRANSFORM_SUBSAMPLE 3
 #define FB_TRANSFORM_DCT 4
 #define FB_TRANSFORM_QUANTIZE 5
+#define FB_TRANSFORM_PALETTE 6
 #define FB_TRANSFORM_SQUEEZE 7
 #define FB_TRANSFORM_APPROXIMATE 10
 
@@ -156,7 +157,8 @@ FB_API int fb_image_download_interleaved(fb_image *img, int n_channels, int byte
 /* Replaces Image::undo_transforms(keep) (reference image/image.cpp:94-115): pops and inverts transforms until
  * `keep` are left, then (keep == 0) clamps every sample to [minval, maxval].  Runs entirely on the GPU:
  * Squeeze (transform/squeeze.h:363-388), Quantize (quantize.h:32-49), DCT (dct.h:249-296),
- * YCbCr (ycbcr.h:33-63), YCoCg (ycocg.h:33-63), ChromaSubsample (subsample.h:73-128), Approximate (approximate.h:32-62). */
+ * YCbCr (ycbcr.h:33-63), YCoCg (ycocg.h:33-63), ChromaSubsample (subsample.h:73-128), Approximate (approximate.h:32-62),
+ * Palette (palette.h:32-68; inverse and decode-time meta step only: building a palette is left to the caller). */
 FB_API int fb_image_undo_transforms(fb_image *img, int keep);
 
 /* Replaces Image::do_transform (reference image/image.cpp:117-122; forward direction of the same transforms).

@@ -9,8 +9,17 @@
 #include "fb_fused_plan.h"
 #include "fb_subsample.cuh"
 #include "fb_approx.cuh"
+#include "fb_palette.cuh"
 
 extern "C" {
+
+// the palette gather: planes[0] holds the indices (and receives row 0 of the palette), planes[1..nb-1] the other rows
+void emu_palette_inv(int16_t **planes, int nb, const int16_t *palette, int ncolors, long long n) {
+    if (n <= 0) return;
+    pl::Planes P;
+    for (int c = 0; c < pl::kMaxPlanes; c++) P.p[c] = c < nb ? planes[c] : nullptr;
+    cuemu::launch((unsigned)((n + 255) / 256), 256, 0, false, [&]() { pl::k_palette_inv(P, palette, (size_t)n, ncolors, nb); });
+}
 
 // the Approximate kernels on one channel (+ its remainder channel; chr may be NULL for the inverse)
 void emu_approximate(int16_t *ch, int16_t *chr, long long n, int q, int inverse) {

@@ -103,6 +103,14 @@ def test_kernel_source_decodes_golden_indexed(oracle, name):
     _check(oracle, bytes(load_golden(name)["fuif"]), indexed=True)
 
 
+@pytest.mark.parametrize("name", ["approx", "approx_nosq", "approx14", "pal", "pal_nosq", "pal4", "pal_c0"])
+@pytest.mark.parametrize("indexed", [True, False], ids=["indexed", "sequential"])
+def test_kernel_source_decodes_meta_and_remainder_channels(oracle, name, indexed):
+    """files whose channel list starts with a palette meta-channel (hshift -1: never a back-reference, context_predict.h:73)
+    or ends with Approximate's remainder channels"""
+    _check(oracle, bytes(load_golden(name)["fuif"]), indexed=indexed)
+
+
 @pytest.mark.parametrize("name", ["odd", "gray", "unc", "tiny"])
 def test_kernel_source_decodes_golden_sequential(oracle, name):
     _check(oracle, bytes(load_golden(name)["fuif"]), indexed=False)
