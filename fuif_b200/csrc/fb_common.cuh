@@ -114,6 +114,9 @@ int fb_launch_inv_dct(fb_ctx *ctx, const int16_t *const *planes64_dev, int16_t *
 int fb_launch_fwd_dct(fb_ctx *ctx, const int16_t *in, int w, int h, int16_t *const *planes64_dev, int bw, int bh, float dc_offset);
 // inv_palette (palette.h:32-68): out_planes[0] holds the indices and receives row 0 of the palette, planes 1..nb-1 the other rows
 int fb_launch_palette_inv(fb_ctx *ctx, int16_t *const *out_planes, int nb, const int16_t *palette, int ncolors, size_t n);
+// fwd_palette (palette.h:92-143) in two steps: distinct colours (hash set on the device, sorted on the host), then indices
+int fb_palette_collect(fb_ctx *ctx, int16_t *const *planes, int nb, size_t n, int limit, std::vector<unsigned long long> &sorted, int *too_many);
+int fb_launch_palette_index(fb_ctx *ctx, int16_t *const *planes, int nb, size_t n, const unsigned long long *sorted_dev, int count);
 // Approximate (approximate.h:32-113): inverse ch = ch*q + chr (chr may be nullptr), forward ch, chr = floor-div / remainder
 int fb_launch_approximate(fb_ctx *ctx, int16_t *ch, int16_t *chr, size_t n, int q, int inverse);
 // chroma upscaling of one plane (ow x oh -> ow*srh x oh*srv), subsample.h:73-128

@@ -620,8 +620,10 @@ static int meta_subsample(fb_image *img, const std::vector<int> &params) {
 
 // ---------------------------------------------------------------------------------------------------------
 // Palette (reference transform/palette.h): parameters = first channel, last channel (relative to the meta channels), colours.
-// Inverse and decode-time meta step; fwd_palette (collecting the set of colours in use, :92-143) is not offered here.
+// Forward (up to four channels), inverse and decode-time meta step.
 // ---------------------------------------------------------------------------------------------------------
+
+static int pl_unpack(unsigned long long k, int c) { return (int)((k >> (16 * (3 - c))) & 0xffffu) - 32768; }     // pl::unpack_colour, fb_palette.cuh
 
 // meta_palette, palette.h:70-89: channels first+1..last disappear, a palette meta-channel (colours x channels, hshift -1) leads the list
 static int meta_palette(fb_image *img, const std::vector<int> &p) {
@@ -638,6 +640,61 @@ static int meta_palette(fb_image *img, const std::vector<int> &p) {
     pch.d.w = p[2]; pch.d.h = nb; pch.d.minval = 0; pch.d.maxval = 1; pch.d.hshift = -1;
     chan_setzero(pch.d);
     img->ch.insert(img->ch.begin(), pch);
+    return FB_OK;
+}
+
+// fwd_palette, palette.h:92-143.  *applied = 0 (and nothing changes) when the channels use more than p[2] colours; otherwise
+// p[2] becomes the number of colours found, as in the reference.
+static int fwd_palette(fb_image *img, std::vector<int> &p, int *applied) {
+    fb_ctx *ctx = img->ctx;
+    *applied = 0;
+    if (p.size() != 3) { ctx->err = "Palette: incorrect parameters"; return FB_ERR_INVALID; }
+    const int begin_c = img->info.nb_meta_channels + p[0], end_c = img->info.nb_meta_channels + p[1];
+    if (p[0] < 0 || begin_c > end_c || end_c >= (int)img->ch.size()) { ctx->err = "Palette: incorrect parameters"; return FB_ERR_INVALID; }
+    const int nb = end_c - begin_c + 1;
+    if (nb > 4) { ctx->err = "Palette over more than four channels"; return FB_ERR_UNSUPPORTED; }
+    const int w = img->ch[begin_c].d.w, h = img->ch[begin_c].d.h;
+    int16_t *planes[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int c = 0; c < nb; c++) {
+        FbChan &ch = img->ch[begin_c + c];
+        if (ch.d.w != w || ch.d.h != h) { ctx->err = "Palette over channels of different sizes"; return FB_ERR_UNSUPPORTED; }
+        int rc = chan_materialize(ctx, ch);
+        if (rc) return rc;
+        planes[c] = ch.dev;
+    }
+    const size_t n = chan_samples(img->ch[begin_c].d);
+    std::vector<unsigned long long> sorted;
+    int too_many = 0;
+    int rc = fb_palette_collect(ctx, planes, nb, n, p[2], sorted, &too_many);
+    if (rc) return rc;
+    if (too_many) return FB_OK;
+    const int count = (int)sorted.size();
+    p[2] = count;
+    // the palette meta-channel: `count` columns, one row per channel, hshift -1
+    FbChan pch;
+    chan_defaults(pch.d);
+    pch.d.w = count; pch.d.h = nb; pch.d.minval = 0; pch.d.maxval = 1; pch.d.hshift = -1;
+    chan_setzero(pch.d);
+    pch.d.decoded = 1;
+    std::vector<int16_t> pal((size_t)count * nb + 1);
+    for (int k = 0; k < count; k++) for (int c = 0; c < nb; c++) pal[(size_t)c * count + k] = (int16_t)pl_unpack(sorted[(size_t)k], c);
+    if ((rc = fb_plane_alloc(ctx, chan_samples(pch.d), &pch.dev))) return rc;
+    unsigned long long *sorted_dev = nullptr;
+    FB_CUDA(ctx, cudaMallocAsync((void **)&sorted_dev, (sorted.size() + 1) * sizeof(unsigned long long), ctx->stream));
+    if (count) {
+        FB_CUDA(ctx, cudaMemcpyAsync(pch.dev, pal.data(), (size_t)count * nb * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(ctx, cudaMemcpyAsync(sorted_dev, sorted.data(), sorted.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = fb_launch_palette_index(ctx, planes, nb, n, sorted_dev, count);
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // pal / sorted are host vectors about to go out of scope
+    cudaFreeAsync(sorted_dev, ctx->stream);
+    if (rc) return rc;
+    img->info.nb_meta_channels++;
+    img->info.nb_channels -= nb - 1;
+    for (int c = begin_c + 1; c <= end_c; c++) if (img->ch[c].dev) fb_plane_free(ctx, img->ch[c].dev);
+    img->ch.erase(img->ch.begin() + begin_c + 1, img->ch.begin() + end_c + 1);
+    img->ch.insert(img->ch.begin(), pch);
+    *applied = 1;
     return FB_OK;
 }
 
@@ -859,6 +916,7 @@ extern "C" int fb_image_do_transform(fb_image *img, int32_t id, const int32_t *p
     case FB_TRANSFORM_SQUEEZE: rc = fwd_squeeze(img, t.p); applied = rc == FB_OK; break;
     case FB_TRANSFORM_DCT: rc = fwd_dct(img, t.p, &applied); break;
     case FB_TRANSFORM_APPROXIMATE: rc = fwd_approximate(img, t.p); applied = rc == FB_OK; break;
+    case FB_TRANSFORM_PALETTE: rc = fwd_palette(img, t.p, &applied); break;
     case FB_TRANSFORM_SUBSAMPLE: applied = 0; break;       // fwd_subsample is a stub in the reference: "return false"
     default:
         img->ctx->err = "transform " + std::to_string(id) + " is outside the hot path";

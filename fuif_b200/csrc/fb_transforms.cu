@@ -1164,6 +1164,59 @@ int fb_launch_palette_inv(fb_ctx *ctx, int16_t *const *out_planes, int nb, const
     if (e != cudaSuccess) { ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e); return FB_ERR_CUDA; }
     return FB_OK;
 }
+// fwd_palette, step 1: the distinct colours of nb planes.  Returns the sorted keys (pl::pack_colour order = the reference's
+// std::set order) in `sorted`, or *too_many = 1 when there are more than `limit`.
+int fb_palette_collect(fb_ctx *ctx, int16_t *const *planes, int nb, size_t n, int limit, std::vector<unsigned long long> &sorted, int *too_many) {
+    *too_many = 0;
+    sorted.clear();
+    if (nb < 1 || nb > 4) return FB_ERR_UNSUPPORTED;
+    if (limit < 0) limit = 0;
+    size_t cap = 4096;
+    while (cap < (size_t)limit * 4 + 4096) cap <<= 1;
+    unsigned long long *table = nullptr;
+    int *ctr = nullptr;
+    FB_CUDA(ctx, cudaMallocAsync((void **)&table, cap * sizeof(unsigned long long), ctx->stream));
+    FB_CUDA(ctx, cudaMallocAsync((void **)&ctr, 4 * sizeof(int), ctx->stream));
+    FB_CUDA(ctx, cudaMemsetAsync(table, 0xFF, cap * sizeof(unsigned long long), ctx->stream));
+    FB_CUDA(ctx, cudaMemsetAsync(ctr, 0, 4 * sizeof(int), ctx->stream));
+    if (n) {
+        pl::Planes P;
+        for (int c = 0; c < pl::kMaxPlanes; c++) P.p[c] = c < nb ? planes[c] : nullptr;
+        pl::Collect C;
+        C.table = table; C.cap_mask = (unsigned)(cap - 1); C.limit = limit; C.count = ctr; C.has_allones = ctr + 1; C.overflow = ctr + 2;
+        pl::k_palette_collect<<<nblocks(n, 256), 256, 0, ctx->stream>>>(P, n, nb, C);
+        ctx->launches++;
+        ctx->mark("k_palette_collect", 2.0 * (double)n * nb);
+        FB_CUDA(ctx, cudaGetLastError());
+    }
+    int h[4];
+    FB_CUDA(ctx, cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h[2] || h[0] > limit) *too_many = 1;
+    else {
+        std::vector<unsigned long long> t(cap);
+        FB_CUDA(ctx, cudaMemcpyAsync(t.data(), table, cap * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (unsigned long long k : t) if (k != pl::kEmptySlot) sorted.push_back(k);
+        if (h[1]) sorted.push_back(pl::kEmptySlot);
+        std::sort(sorted.begin(), sorted.end());
+    }
+    cudaFreeAsync(table, ctx->stream);
+    cudaFreeAsync(ctr, ctx->stream);
+    return FB_OK;
+}
+// fwd_palette, step 2: plane 0 <- position of every sample's colour in `sorted_dev` (count keys in HBM)
+int fb_launch_palette_index(fb_ctx *ctx, int16_t *const *planes, int nb, size_t n, const unsigned long long *sorted_dev, int count) {
+    if (!n) return FB_OK;
+    pl::Planes P;
+    for (int c = 0; c < pl::kMaxPlanes; c++) P.p[c] = c < nb ? planes[c] : nullptr;
+    pl::k_palette_index<<<nblocks(n, 256), 256, 0, ctx->stream>>>(P, n, nb, sorted_dev, count);
+    ctx->launches++;
+    ctx->mark("k_palette_index", 2.0 * (double)n * (nb + 1));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e); return FB_ERR_CUDA; }
+    return FB_OK;
+}
 int fb_launch_approximate(fb_ctx *ctx, int16_t *ch, int16_t *chr, size_t n, int q, int inverse) {
     if (!n) return FB_OK;
     if (inverse) ap::k_approx_inv<<<nblocks(n, 256), 256, 0, ctx->stream>>>(ch, chr, n, q);

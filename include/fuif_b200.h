@@ -29,7 +29,7 @@ extern "C" {
 #define FB_OK 0
 #define FB_ERR_INVALID 1      /* bad argument / malformed stream ("return false" in the reference)            */
 #define FB_ERR_CUDA 2         /* CUDA runtime error; fb_last_error() has the text                            */
-#define FB_ERR_UNSUPPORTED 3  /* outside the hot path (2dmatch, permute, building a palette)            */
+#define FB_ERR_UNSUPPORTED 3  /* outside the hot path (2dmatch, permute, palettes over > 4 channels)    */
 #define FB_ERR_NOMEM 4
 
 /* transform ids, reference transform/transform.h:30-70 */
@@ -158,11 +158,13 @@ FB_API int fb_image_download_interleaved(fb_image *img, int n_channels, int byte
  * `keep` are left, then (keep == 0) clamps every sample to [minval, maxval].  Runs entirely on the GPU:
  * Squeeze (transform/squeeze.h:363-388), Quantize (quantize.h:32-49), DCT (dct.h:249-296),
  * YCbCr (ycbcr.h:33-63), YCoCg (ycocg.h:33-63), ChromaSubsample (subsample.h:73-128), Approximate (approximate.h:32-62),
- * Palette (palette.h:32-68; inverse and decode-time meta step only: building a palette is left to the caller). */
+ * Palette (palette.h:32-68). */
 FB_API int fb_image_undo_transforms(fb_image *img, int keep);
 
 /* Replaces Image::do_transform (reference image/image.cpp:117-122; forward direction of the same transforms).
- * *applied = 1 if the transform was applied and pushed on the stack, 0 if it did not apply. */
+ * *applied = 1 if the transform was applied and pushed on the stack, 0 if it did not apply (e.g. a Palette over channels
+ * that use more colours than its third parameter allows, palette.h:109).  Palette records the number of colours it found
+ * in that parameter, as the reference does. */
 FB_API int fb_image_do_transform(fb_image *img, int32_t id, const int32_t *params, int nparams, int *applied);
 
 /* Replaces Image::recompute_minmax (image/image.h:127; Channel::actual_minmax, image.cpp:82-92). */

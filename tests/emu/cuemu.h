@@ -167,6 +167,8 @@ inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)
 template <class T> inline T __ldg(const T *p) { return *p; }
 inline int atomicOr(int *p, int v) { int o = *p; *p = o | v; return o; }
 inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; return o; }
+inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long cmp, unsigned long long v) { unsigned long long o = *p; if (o == cmp) *p = v; return o; }
+inline int atomicExch(int *p, int v) { int o = *p; *p = v; return o; }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 using std::max;
 using std::min;

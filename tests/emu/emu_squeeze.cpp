@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "fb_fused_plan.h"
@@ -19,6 +20,29 @@ void emu_palette_inv(int16_t **planes, int nb, const int16_t *palette, int ncolo
     pl::Planes P;
     for (int c = 0; c < pl::kMaxPlanes; c++) P.p[c] = c < nb ? planes[c] : nullptr;
     cuemu::launch((unsigned)((n + 255) / 256), 256, 0, false, [&]() { pl::k_palette_inv(P, palette, (size_t)n, ncolors, nb); });
+}
+
+// fwd_palette as the library runs it: hash-set collect kernel, sort of the keys, index kernel.  planes[0..nb-1] hold the
+// channels; on success planes[0] holds the indices and palette[c * count + k] the colours.  Returns the number of colours
+// or -1 when there are more than `limit`.  table_cap (a power of two) lets a test force collisions / a full table.
+int emu_palette_fwd(int16_t **planes, int nb, long long n, int limit, int16_t *palette, int table_cap) {
+    std::vector<unsigned long long> table((size_t)table_cap, pl::kEmptySlot);
+    int ctr[4] = {0, 0, 0, 0};
+    pl::Planes P;
+    for (int c = 0; c < pl::kMaxPlanes; c++) P.p[c] = c < nb ? planes[c] : nullptr;
+    pl::Collect C;
+    C.table = table.data(); C.cap_mask = (unsigned)(table_cap - 1); C.limit = limit; C.count = ctr; C.has_allones = ctr + 1; C.overflow = ctr + 2;
+    const unsigned nblk = (unsigned)((n + 255) / 256);
+    if (n > 0) cuemu::launch(nblk, 256, 0, false, [&]() { pl::k_palette_collect(P, (size_t)n, nb, C); });
+    if (ctr[2] || ctr[0] > limit) return -1;
+    std::vector<unsigned long long> sorted;
+    for (unsigned long long k : table) if (k != pl::kEmptySlot) sorted.push_back(k);
+    if (ctr[1]) sorted.push_back(pl::kEmptySlot);
+    std::sort(sorted.begin(), sorted.end());
+    const int count = (int)sorted.size();
+    for (int k = 0; k < count; k++) for (int c = 0; c < nb; c++) palette[(size_t)c * count + k] = (int16_t)pl::unpack_colour(sorted[(size_t)k], c);
+    if (n > 0) cuemu::launch(nblk, 256, 0, false, [&]() { pl::k_palette_index(P, (size_t)n, nb, sorted.data(), count); });
+    return count;
 }
 
 // the Approximate kernels on one channel (+ its remainder channel; chr may be NULL for the inverse)

@@ -35,6 +35,7 @@ def lib():
         L.emu_approximate.restype = None
         L.emu_palette_inv.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_longlong]
         L.emu_palette_inv.restype = None
+        L.emu_palette_fwd.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_int]
         _lib = L
     return _lib
 

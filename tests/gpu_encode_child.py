@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 from fuif_b200 import api  # noqa: E402
 from fuif_b200.synth import read_pnm, synth_image  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402
-from tests.cases import APPROX_CASES, CASES  # noqa: E402
+from tests.cases import APPROX_CASES, CASES, PALETTE_CASES  # noqa: E402
 from tests.test_oracle_encoder import _options  # noqa: E402
 from tests.util import gpu_plane_image, load_golden, ordered  # noqa: E402
 
@@ -79,7 +79,7 @@ def main(names):
                 o = {"nb_repeats": 0.5, "max_properties": 12, "compress": True, "max_group": -1, "predictor": [2, 2, 2, 0]}
                 res = check(name, pix, 255, [], o, ctx)
             else:
-                case = next(c for c in CASES + APPROX_CASES if c[0] == name)
+                case = next(c for c in CASES + APPROX_CASES + PALETTE_CASES if c[0] == name)
                 _n, w, h, c, maxval, seed, opts = case
                 blob = load_golden(name)
                 final = po.parse_fbpd(ordered(blob, "f")[-1])
@@ -90,7 +90,7 @@ def main(names):
                     pix, _ = read_pnm(path)
                 finally:
                     os.remove(path)
-                trs = [(tid, params if tid in (4, 5, 10) else []) for tid, params in final.transforms]
+                trs = [(tid, params if tid in (4, 5, 6, 10) else []) for tid, params in final.transforms]
                 res = check(name, pix, maxval, trs, _options(opts, c, final.transforms), ctx, golden_file=bytes(blob["fuif"]))
         except Exception as e:      # noqa: BLE001 -- reported to the parent, which fails the case
             res = {"case": name, "ok": False, "why": f"{type(e).__name__}: {e}"[:400]}

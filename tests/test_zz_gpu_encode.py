@@ -16,7 +16,7 @@ from tests.cases import CASES
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-NAMES = [c[0] for c in CASES] + ["approx", "approx_nosq", "noise", "synth256", "synth512", "synth1000x333"]
+NAMES = [c[0] for c in CASES] + ["approx", "approx_nosq", "pal", "pal_nosq", "noise", "synth256", "synth512", "synth1000x333"]
 _results = None
 
 
