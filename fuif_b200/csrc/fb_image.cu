@@ -737,6 +737,43 @@ static int inv_palette(fb_image *img, const std::vector<int> &p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Permute (reference transform/permute.h) with explicit parameters: pure channel-list bookkeeping, the planes stay where
+// they are in HBM.  The reference's other mode (permutation stored in a meta-channel) cannot round-trip there -- fwd_permute
+// leaves the parameters in the Transform, so the decoder's meta_permute takes the explicit branch -- and is not offered.
+// ---------------------------------------------------------------------------------------------------------
+
+// meta_permute, permute.h:57-83: channel i of the list goes to position parameters[i]
+static int meta_permute(fb_image *img, const std::vector<int> &p) {
+    const int m = img->info.nb_meta_channels, nb = (int)img->ch.size() - m, np = (int)p.size();
+    if (np == 0) { img->ctx->err = "Permute through a meta-channel is not supported"; return FB_ERR_UNSUPPORTED; }
+    if (np > nb) { img->ctx->err = "Permute: incorrect number of parameters"; return FB_ERR_INVALID; }
+    for (int i = 0; i < np; i++) {
+        if (p[i] < 0 || p[i] >= np) { img->ctx->err = "Permute: invalid permutation"; return FB_ERR_INVALID; }
+        for (int j = 0; j < i; j++) if (p[i] == p[j]) { img->ctx->err = "Permute: invalid permutation"; return FB_ERR_INVALID; }
+    }
+    const std::vector<FbChan> old(img->ch.begin() + m, img->ch.begin() + m + np);
+    for (int i = 0; i < np; i++) img->ch[m + p[i]] = old[i];
+    return FB_OK;
+}
+// fwd_permute, permute.h:85-124: a leading -1 selects the explicit mode and is dropped from the stored parameters
+static int fwd_permute(fb_image *img, std::vector<int> &p) {
+    if (p.size() < 3) { img->ctx->err = "Permute: not enough parameters"; return FB_ERR_INVALID; }
+    if (p[0] != -1) { img->ctx->err = "Permute through a meta-channel is not supported"; return FB_ERR_UNSUPPORTED; }
+    p.erase(p.begin());
+    return meta_permute(img, p);
+}
+// inv_permute, permute.h:31-55: position i gets back the channel that sits at parameters[i]
+static int inv_permute(fb_image *img, const std::vector<int> &p) {
+    const int m = img->info.nb_meta_channels, np = (int)p.size();
+    if (np == 0) { img->ctx->err = "Permute through a meta-channel is not supported"; return FB_ERR_UNSUPPORTED; }
+    if (np > (int)img->ch.size() - m) { img->ctx->err = "Permute: incorrect number of parameters"; return FB_ERR_INVALID; }
+    for (int i = 0; i < np; i++) if (p[i] < 0 || p[i] >= np) { img->ctx->err = "Permute: invalid permutation"; return FB_ERR_INVALID; }
+    const std::vector<FbChan> old(img->ch.begin() + m, img->ch.begin() + m + np);
+    for (int i = 0; i < np; i++) img->ch[m + i] = old[p[i]];
+    return FB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Approximate (reference transform/approximate.h): parameters = first channel, last channel, divisor - 1 per channel (the
 // last one repeats; 0 = leave the channel alone).  Channel numbers are absolute (meta channels included), as in the reference.
 // ---------------------------------------------------------------------------------------------------------
@@ -833,6 +870,7 @@ static int transform_meta_apply(fb_image *img, FbXform &t) {
     case FB_TRANSFORM_SUBSAMPLE: return meta_subsample(img, t.p);
     case FB_TRANSFORM_APPROXIMATE: return meta_approximate(img, t.p);
     case FB_TRANSFORM_PALETTE: return meta_palette(img, t.p);
+    case FB_TRANSFORM_PERMUTE: return meta_permute(img, t.p);
     default:
         img->ctx->err = "transform " + std::to_string(t.id) + " is outside the hot path (SURVEY.md 8: out of scope)";
         return FB_ERR_UNSUPPORTED;
@@ -883,6 +921,7 @@ extern "C" int fb_image_undo_transforms(fb_image *img, int keep) {
         case FB_TRANSFORM_SUBSAMPLE: rc = inv_subsample(img, t.p); break;
         case FB_TRANSFORM_APPROXIMATE: rc = inv_approximate(img, t.p); break;
         case FB_TRANSFORM_PALETTE: rc = inv_palette(img, t.p); break;
+        case FB_TRANSFORM_PERMUTE: rc = inv_permute(img, t.p); break;
         default:
             ctx->err = "cannot undo transform " + std::to_string(t.id) + " (outside the hot path)";
             rc = FB_ERR_UNSUPPORTED;
@@ -917,6 +956,7 @@ extern "C" int fb_image_do_transform(fb_image *img, int32_t id, const int32_t *p
     case FB_TRANSFORM_DCT: rc = fwd_dct(img, t.p, &applied); break;
     case FB_TRANSFORM_APPROXIMATE: rc = fwd_approximate(img, t.p); applied = rc == FB_OK; break;
     case FB_TRANSFORM_PALETTE: rc = fwd_palette(img, t.p, &applied); break;
+    case FB_TRANSFORM_PERMUTE: rc = fwd_permute(img, t.p); applied = rc == FB_OK; break;
     case FB_TRANSFORM_SUBSAMPLE: applied = 0; break;       // fwd_subsample is a stub in the reference: "return false"
     default:
         img->ctx->err = "transform " + std::to_string(id) + " is outside the hot path";

@@ -849,6 +849,46 @@ static int inv_palette(fo_image *img, const int *p, int np) {
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Permute, transform/permute.h, with explicit parameters.  (Its meta-channel mode cannot round-trip in */
+/* the reference: fwd_permute leaves the parameters in the Transform, so the decoder's meta_permute      */
+/* takes the explicit branch while the encoder added a meta-channel.  It is not restated.)               */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* meta_permute, permute.h:57-83, explicit branch: channel i of the list goes to position parameters[i] */
+static int meta_permute(fo_image *img, const int *p, int np) {
+    const int nb = img->nch - img->nb_meta_channels, m = img->nb_meta_channels;
+    if (np <= 0 || np > nb) return 0;
+    for (int i = 0; i < np; i++) {
+        if (p[i] < 0 || p[i] >= np) return 0;
+        for (int j = 0; j < i; j++) if (p[i] == p[j]) return 0;
+    }
+    fo_channel *old = (fo_channel *)malloc(sizeof(fo_channel) * (size_t)np);
+    memcpy(old, &img->ch[m], sizeof(fo_channel) * (size_t)np);
+    for (int i = 0; i < np; i++) img->ch[m + p[i]] = old[i];
+    free(old);
+    return 1;
+}
+/* fwd_permute, permute.h:85-124: a leading -1 selects the explicit mode and is dropped from the stored parameters */
+static int fwd_permute(fo_image *img, fo_transform *t) {
+    if (t->np < 3 || t->p[0] != -1) return 0;
+    memmove(t->p, t->p + 1, sizeof(int) * (size_t)(t->np - 1));
+    t->np--;
+    if (!meta_permute(img, t->p, t->np)) { img->error = 1; }       /* the reference flags the image and still reports success */
+    return 1;
+}
+/* inv_permute, permute.h:31-55, explicit branch: position i gets back the channel that sits at parameters[i] */
+static int inv_permute(fo_image *img, const int *p, int np) {
+    const int m = img->nb_meta_channels;
+    if (np <= 0 || np > img->nch - m) return 0;
+    fo_channel *old = (fo_channel *)malloc(sizeof(fo_channel) * (size_t)np);
+    for (int i = 0; i < np; i++) { if (p[i] < 0 || p[i] >= np) { free(old); return 0; } }
+    memcpy(old, &img->ch[m], sizeof(fo_channel) * (size_t)np);
+    for (int i = 0; i < np; i++) img->ch[m + i] = old[p[i]];
+    free(old);
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* Approximate, transform/approximate.h: channel = quotient, extra channel at the end = remainder    */
 /* ------------------------------------------------------------------------------------------------ */
 
@@ -947,8 +987,9 @@ static int transform_apply(fo_image *img, fo_transform *t, int inverse) {
         }
         return inv_subsample(img, t->p, t->np);
     case FO_PALETTE: return inverse ? inv_palette(img, t->p, t->np) : fwd_palette(img, t->p, t->np);
+    case 9: return inverse ? inv_permute(img, t->p, t->np) : fwd_permute(img, t);
     case 10: return inverse ? inv_approximate(img, t->p, t->np) : fwd_approximate(img, t->p, t->np);
-    default: return 0;       /* palette / 2dmatch / permute: out of scope */
+    default: return 0;       /* 2dmatch: out of scope */
     }
 }
 
@@ -969,6 +1010,7 @@ static int transform_meta_apply(fo_image *img, fo_transform *t) {
     case FO_SUBSAMPLE: return meta_subsample(img, t->p, t->np);
     case 10: return meta_approximate(img, t->p, t->np);
     case FO_PALETTE: return meta_palette(img, t->p, t->np);
+    case 9: return meta_permute(img, t->p, t->np);
     default: return 0;
     }
 }

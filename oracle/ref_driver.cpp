@@ -18,7 +18,7 @@
 //   fuif_decode_file           encoding/encoding.cpp:745
 //
 // Sub-commands:
-//   encode <in.pam> <out.fuif> [-C 0|1|2] [-J] [-S 0|1] [-q luma,chroma] [-E n] [-I f] [-G n] [-P digits] [-A k,q] [-L colours]
+//   encode <in.pam> <out.fuif> [-C 0|1|2] [-J] [-S 0|1] [-q luma,chroma] [-E n] [-I f] [-G n] [-P digits] [-A k,q] [-L colours] [-M perm]
 //   decode <in.fuif> <out.pam> [-R k]
 //   dump   <in.fuif> <prefix>  [-R k]     planes after decode and after each inverse transform
 //   fwd    <in.pam>  <prefix>  [same options as encode]   planes after each forward transform
@@ -72,6 +72,7 @@ struct EncOpts {
     bool dct = false;
     bool squeeze = true;
     int qluma = 0, qchroma = 0;  // 0 = lossless
+    std::vector<int> permutation;   // -M a,b,c: TRANSFORM_PERMUTE with explicit parameters (-1 is prepended: fwd_permute's "no meta-channel" mode, permute.h:90-93)
     int palette_colors = 0;  // -L n: all-channel TRANSFORM_PALETTE with at most n colours after the colour transform (fuif.cpp:398-407)
     int approx_k = 0, approx_q = 0;     // -A k,q: TRANSFORM_APPROXIMATE on the last k channels with divisor q+1 (fuif.cpp:504-510)
     fuif_options options = default_fuif_options;
@@ -90,6 +91,7 @@ static bool parse_enc_opts(int argc, char **argv, int start, EncOpts &o) {
         else if (a == "-G") o.options.max_group = atoi(need());
         else if (a == "-U") o.options.compress = false;
         else if (a == "-L") o.palette_colors = atoi(need());
+        else if (a == "-M") { const char *v = need(); char *dup = strdup(v); for (char *tok = strtok(dup, ","); tok; tok = strtok(nullptr, ",")) o.permutation.push_back(atoi(tok)); free(dup); }
         else if (a == "-A") { if (sscanf(need(), "%d,%d", &o.approx_k, &o.approx_q) != 2) return false; }
         else if (a == "-P") { const char *s = need(); while (*s) { if (*s >= '0' && *s <= '9') o.options.predictor.push_back(*s - '0'); s++; } }
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return false; }
@@ -109,6 +111,13 @@ static bool build_chain(Image &img, EncOpts &o, const std::string *dump_prefix) 
     dump();
     if (o.colorspace == 2) { if (img.do_transform(Transform(TRANSFORM_YCoCg))) dump(); }
     else if (o.colorspace == 1) { if (img.do_transform(Transform(TRANSFORM_YCbCr))) dump(); }
+    if (!o.permutation.empty()) {
+        Transform reorder(TRANSFORM_PERMUTE);
+        reorder.parameters.push_back(-1);
+        for (int c : o.permutation) reorder.parameters.push_back(c);
+        if (!img.do_transform(reorder)) return false;
+        dump();
+    }
     if (o.palette_colors > 0 && img.nb_channels > 1) {
         Transform maybe_palette(TRANSFORM_PALETTE);
         maybe_palette.parameters.push_back(0);

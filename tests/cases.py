@@ -58,3 +58,11 @@ PALETTE_CASES = [
     ("pal4", 40, 30, 4, 255, 53, ["-L", "4000"]),
     ("pal_c0", 33, 27, 3, 255, 54, ["-C", "0", "-S", "0", "-L", "300"]),
 ]
+
+# Permute with explicit parameters (reference transform/permute.h; ref_driver option -M a,b,c before the palette / squeeze
+# steps).  Same tuple layout as CASES.
+PERMUTE_CASES = [
+    ("perm", 40, 30, 3, 255, 61, ["-M", "2,0,1"]),
+    ("perm_nosq", 33, 21, 4, 255, 62, ["-S", "0", "-M", "1,0,3,2"]),
+    ("perm2", 36, 28, 3, 255, 63, ["-C", "0", "-M", "1,0"]),
+]

@@ -16,14 +16,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from fuif_b200.synth import synth_image, write_pnm  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402
-from tests.cases import APPROX_CASES, CASES, PALETTE_CASES  # noqa: E402
+from tests.cases import APPROX_CASES, CASES, PALETTE_CASES, PERMUTE_CASES  # noqa: E402
 
 
 def main():
     po.build()
     assert po.have_ref(), "oracle/_ref/ref_driver missing (needs /root/reference)"
     out_dir = os.path.dirname(os.path.abspath(__file__))
-    which = APPROX_CASES if "approx" in sys.argv[1:] else PALETTE_CASES if "palette" in sys.argv[1:] else CASES      # python make_golden.py [approx|palette]
+    which = APPROX_CASES if "approx" in sys.argv[1:] else PALETTE_CASES if "palette" in sys.argv[1:] else PERMUTE_CASES if "permute" in sys.argv[1:] else CASES    # python make_golden.py [approx|palette|permute]
     for name, w, h, c, maxval, seed, opts in which:
         with tempfile.TemporaryDirectory() as td:
             pnm = os.path.join(td, "in.pnm")

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from fuif_b200.synth import read_pnm
-from tests.cases import APPROX_CASES, CASES, PALETTE_CASES
+from tests.cases import APPROX_CASES, CASES, PALETTE_CASES, PERMUTE_CASES
 from tests.test_oracle_encoder import _options
 from tests.util import load_golden, ordered
 
@@ -138,7 +138,7 @@ def test_encode_kernel_matches_oracle_encoder(oracle, case):
     oi = po.OracleImage.from_pixels(pix, maxval)
     oi.recompute_minmax()
     for tid, params in final.transforms:
-        assert oi.do_transform(tid, params if tid in (4, 5, 6, 10) else [])
+        assert oi.do_transform(tid, [-1] + list(params) if tid == 9 else (params if tid in (4, 5, 6, 10) else []))
     o = _options(opts, c, final.transforms)
     ref = oi.encode(predictor=o["predictor"], nb_repeats=o["nb_repeats"], max_properties=o["max_properties"], compress=o["compress"], max_group=o["max_group"])
     assert ref[:-1] == bytes(blob["fuif"])[:-1]
@@ -188,7 +188,7 @@ def test_encode_kernel_matches_oracle_encoder(oracle, case):
     po.compare_plane_images(back.to_plane_image(), dec.to_plane_image(), name + " decode of the kernel's output")
 
 
-ENC_CASES = list(CASES) + list(APPROX_CASES) + list(PALETTE_CASES)
+ENC_CASES = list(CASES) + list(APPROX_CASES) + list(PALETTE_CASES) + list(PERMUTE_CASES)
 
 
 def test_rand_restatement_matches_libc():
@@ -218,7 +218,7 @@ def test_encode_file_matches_oracle_encoder(oracle, case):
     oi = po.OracleImage.from_pixels(pix, maxval)
     oi.recompute_minmax()
     for tid, params in final.transforms:
-        assert oi.do_transform(tid, params if tid in (4, 5, 6, 10) else [])
+        assert oi.do_transform(tid, [-1] + list(params) if tid == 9 else (params if tid in (4, 5, 6, 10) else []))
     _check_file(po, oi, _options(opts, c, final.transforms))
 
 

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from fuif_b200.synth import read_pnm
-from tests.cases import APPROX_CASES, CASES, PALETTE_CASES
+from tests.cases import APPROX_CASES, CASES, PALETTE_CASES, PERMUTE_CASES
 from tests.util import load_golden, ordered
 
 
@@ -26,7 +26,7 @@ def _options(opts, nb_channels, transforms):
         elif a == "-U": o["compress"] = False
         elif a == "-P": o["predictor"] = [int(ch) for ch in next(it) if ch.isdigit()]
         elif a == "-J": dct = True
-        elif a in ("-C", "-S", "-q", "-A", "-L"): next(it)
+        elif a in ("-C", "-S", "-q", "-A", "-L", "-M"): next(it)
     if not dct and any(t == 7 for t, _ in transforms) and o["max_group"] < 0:
         o["max_group"] = 1                      # build_chain: one channel per group after a Squeeze
     if not o["predictor"]:                          # build_chain: 3 for meta channels, 2 for the image's channels, then 0
@@ -36,7 +36,7 @@ def _options(opts, nb_channels, transforms):
     return o
 
 
-@pytest.mark.parametrize("case", CASES + APPROX_CASES + PALETTE_CASES, ids=[c[0] for c in CASES + APPROX_CASES + PALETTE_CASES])
+@pytest.mark.parametrize("case", CASES + APPROX_CASES + PALETTE_CASES + PERMUTE_CASES, ids=[c[0] for c in CASES + APPROX_CASES + PALETTE_CASES + PERMUTE_CASES])
 def test_encoder_matches_reference_file(oracle, case):
     po = oracle
     name, w, h, c, maxval, seed, opts = case
@@ -52,7 +52,7 @@ def test_encoder_matches_reference_file(oracle, case):
     oi = po.OracleImage.from_pixels(pix, maxval)
     oi.recompute_minmax()
     for tid, params in final.transforms:
-        assert oi.do_transform(tid, params if tid in (4, 5, 6, 10) else [])
+        assert oi.do_transform(tid, [-1] + list(params) if tid == 9 else (params if tid in (4, 5, 6, 10) else []))
     o = _options(opts, c, final.transforms)
     mine = oi.encode(predictor=o["predictor"], nb_repeats=o["nb_repeats"], max_properties=o["max_properties"], compress=o["compress"],
                      max_group=o["max_group"])
@@ -99,7 +99,7 @@ def test_encoder_matches_live_reference(oracle, case, tmp_path):
     oi = po.OracleImage.from_pixels(pix, maxval)
     oi.recompute_minmax()
     for tid, params in final.transforms:
-        assert oi.do_transform(tid, params if tid in (4, 5, 6, 10) else [])
+        assert oi.do_transform(tid, [-1] + list(params) if tid == 9 else (params if tid in (4, 5, 6, 10) else []))
     o = _options(opts, c, final.transforms)
     mine = oi.encode(predictor=o["predictor"], nb_repeats=o["nb_repeats"], max_properties=o["max_properties"], compress=o["compress"],
                      max_group=o["max_group"])

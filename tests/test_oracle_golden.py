@@ -2,9 +2,9 @@
 import numpy as np
 import pytest
 
-from tests.cases import APPROX_CASES, CASES, PALETTE_CASES
+from tests.cases import APPROX_CASES, CASES, PALETTE_CASES, PERMUTE_CASES
 
-ALL_CASES = CASES + APPROX_CASES + PALETTE_CASES
+ALL_CASES = CASES + APPROX_CASES + PALETTE_CASES + PERMUTE_CASES
 from tests.util import load_golden, ordered
 from fuif_b200.synth import read_pnm  # noqa: F401
 
@@ -43,7 +43,7 @@ def test_forward_chain(oracle, case):
     po.compare_plane_images(oi.to_plane_image(), steps[0], name + " f0")
     k = 1
     for tid, params in steps[-1].transforms:
-        assert oi.do_transform(tid, params if tid in (4, 5, 6, 10) else [])
+        assert oi.do_transform(tid, [-1] + list(params) if tid == 9 else (params if tid in (4, 5, 6, 10) else []))
         po.compare_plane_images(oi.to_plane_image(), steps[k], f"{name} f{k}")
         k += 1
 

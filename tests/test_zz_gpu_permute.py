@@ -1,0 +1,57 @@
+"""GPU: files with a Permute transform (explicit parameters, reference transform/permute.h) through the C ABI against golden
+vectors made by the unmodified reference.  Permute is channel-list bookkeeping: what is checked is that decode, every inverse
+step and the forward chain see the same channel order as the reference."""
+import os
+import tempfile
+
+import pytest
+
+from fuif_b200.synth import read_pnm
+from tests.cases import PERMUTE_CASES
+from tests.util import gpu_plane_image, load_golden, ordered
+
+pytestmark = [pytest.mark.gpu,
+              # Not strict: a pass is reported as XPASS.  Written after the round's GPU budget was spent; the marker goes away with the first recorded hardware run.
+              pytest.mark.xfail(strict=False, reason="Permute has not run on hardware yet")]
+
+
+@pytest.mark.parametrize("case", PERMUTE_CASES, ids=lambda c: c[0])
+def test_decode_and_undo_vs_golden(oracle, ctx, case):
+    from fuif_b200 import api
+    po = oracle
+    blob = load_golden(case[0])
+    steps = [po.parse_fbpd(b) for b in ordered(blob, "s")]
+    img = api.fuif_decode(blob["fuif"], ctx=ctx)
+    po.compare_plane_images(gpu_plane_image(po, img), steps[0], case[0] + " s0")
+    ntr = len(steps[0].transforms)
+    for k, ref in enumerate(steps[1:]):
+        img.undo_transforms(ntr - 1 - k)
+        po.compare_plane_images(gpu_plane_image(po, img), ref, f"{case[0]} s{k + 1}")
+
+
+@pytest.mark.parametrize("case", PERMUTE_CASES, ids=lambda c: c[0])
+def test_forward_chain_vs_golden(oracle, ctx, case):
+    from fuif_b200 import api
+    po = oracle
+    name, w, h, c, maxval, seed, opts = case
+    blob = load_golden(name)
+    steps = [po.parse_fbpd(b) for b in ordered(blob, "f")]
+    with tempfile.NamedTemporaryFile(suffix=".pnm", delete=False) as f:
+        f.write(blob["pnm"])
+        path = f.name
+    try:
+        pix, _ = read_pnm(path)
+    finally:
+        os.remove(path)
+    img = api.Image.from_pixels(pix, maxval, ctx)
+    img.recompute_minmax()
+    k = 1
+    for tid, params in steps[-1].transforms:
+        par = [-1] + list(params) if tid == 9 else (list(params) if tid in (4, 5, 6, 10) else [])
+        assert img.do_transform(api.Transform(tid, par))
+        got = gpu_plane_image(po, img)
+        if k == len(steps) - 1:
+            img.recompute_minmax()
+            got = gpu_plane_image(po, img)
+        po.compare_plane_images(got, steps[k], f"{name} f{k}", check_meta=(k == len(steps) - 1))
+        k += 1
