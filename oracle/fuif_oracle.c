@@ -889,6 +889,74 @@ static int inv_permute(fo_image *img, const int *p, int np) {
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* 2DMatch, transform/2dmatch.h: inverse and meta (the forward is a search heuristic, not restated).  */
+/* Single-frame images only: the "corresponding pixel of the previous frame" mode needs nb_frames > 1. */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* compute_offset, 2dmatch.h:52-77: offset code -> (dx, dy) of an earlier sample, spiralling outwards in "onion layers" */
+static void match_offset(int code, int *xoffset, int *yoffset) {
+    int layer = 0, size = 4;
+    while (code > size) { code -= size; layer++; size += 4; }
+    if (layer & 1) {
+        if (code <= layer) { *xoffset = 1 + layer; *yoffset = -code; }
+        else if (code <= 3 + 3 * layer) { *xoffset = 2 + 2 * layer - code; *yoffset = -1 - layer; }
+        else { *xoffset = -1 - layer; *yoffset = -4 - 4 * layer + code; }
+    } else {
+        if (code <= 1 + layer) { *xoffset = -1 - layer; *yoffset = 1 - code; }
+        else if (code <= 4 + 3 * layer) { *xoffset = -3 - 2 * layer + code; *yoffset = -1 - layer; }
+        else { *xoffset = 1 + layer; *yoffset = -5 - 4 * layer + code; }
+    }
+}
+static int match_parameters(const fo_image *img, const int *p, int np, int *out) {     /* default_match_parameters, :89-95 */
+    if (!np) { out[0] = 0; out[1] = img->nb_channels - 1; out[2] = 0; out[3] = 1000000; return 4; }
+    for (int i = 0; i < np && i < 8; i++) out[i] = p[i];
+    return np < 8 ? np : 8;
+}
+/* meta_match, 2dmatch.h:179-194: a match channel of the size of the first matched channel leads the list */
+static int meta_match(fo_image *img, const int *p0, int np0) {
+    int p[8];
+    const int np = match_parameters(img, p0, np0, p);
+    if (np < 3) return 0;
+    const int begin_c = img->nb_meta_channels + p[0], end_c = img->nb_meta_channels + p[1];
+    if (p[0] < 0 || begin_c > end_c || end_c >= img->nch) return 0;
+    img->nb_meta_channels++;
+    fo_channel mch;
+    ch_make(&mch, img->ch[begin_c].w, img->ch[begin_c].h, 0, 1, 1, 0, 0, 0, 0);
+    img_insert(img, 0, &mch);
+    return 1;
+}
+/* inv_match, 2dmatch.h:97-177, for m.q == 1: in scanline order every sample with a non-zero code takes (or, for soft
+ * matches, adds) the already reconstructed sample at the coded offset.  Channel::value is flat-indexed: an offset that
+ * leaves the row lands in the neighbouring row, one that leaves the plane reads `zero` (image.h:82). */
+static int inv_match(fo_image *img, const int *p0, int np0) {
+    if (img->nb_meta_channels < 1) return 0;
+    int p[8];
+    const int np = match_parameters(img, p0, np0, p);
+    if (np < 3) return 0;
+    const fo_channel *m = &img->ch[0];
+    const int c0 = img->nb_meta_channels + p[0], cn = img->nb_meta_channels + p[1];
+    if (p[0] < 0 || p[1] < 0 || c0 >= img->nch || cn >= img->nch) return 0;
+    const int softmatch = p[2];
+    const int w = img->ch[c0].w, h = img->ch[c0].h;
+    if (m->q != 1) return 0;            /* previous-frame mode (animations) or "unexpected quantization factor" */
+    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+        const int z = ch_get(m, y, x);
+        if (!z) continue;
+        if (z < 0 || z > m->maxval) return 0;       /* the reference indexes its offsets table out of bounds here */
+        int dx, dy;
+        match_offset(z, &dx, &dy);
+        for (int c = c0; c <= cn; c++) {
+            fo_channel *ch = &img->ch[c];
+            const int src = ch_get(ch, y + dy, x + dx);
+            ch_set(ch, y, x, softmatch ? S16(ch_get(ch, y, x) + src) : src);
+        }
+    }
+    img->nb_meta_channels--;
+    img_erase(img, 0, 1);
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* Approximate, transform/approximate.h: channel = quotient, extra channel at the end = remainder    */
 /* ------------------------------------------------------------------------------------------------ */
 
@@ -988,8 +1056,9 @@ static int transform_apply(fo_image *img, fo_transform *t, int inverse) {
         return inv_subsample(img, t->p, t->np);
     case FO_PALETTE: return inverse ? inv_palette(img, t->p, t->np) : fwd_palette(img, t->p, t->np);
     case 9: return inverse ? inv_permute(img, t->p, t->np) : fwd_permute(img, t);
+    case 8: return inverse ? inv_match(img, t->p, t->np) : 0;       /* fwd_match: a search heuristic, not restated */
     case 10: return inverse ? inv_approximate(img, t->p, t->np) : fwd_approximate(img, t->p, t->np);
-    default: return 0;       /* 2dmatch: out of scope */
+    default: return 0;
     }
 }
 
@@ -1011,6 +1080,7 @@ static int transform_meta_apply(fo_image *img, fo_transform *t) {
     case 10: return meta_approximate(img, t->p, t->np);
     case FO_PALETTE: return meta_palette(img, t->p, t->np);
     case 9: return meta_permute(img, t->p, t->np);
+    case 8: return meta_match(img, t->p, t->np);
     default: return 0;
     }
 }

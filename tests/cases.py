@@ -66,3 +66,12 @@ PERMUTE_CASES = [
     ("perm_nosq", 33, 21, 4, 255, 62, ["-S", "0", "-M", "1,0,3,2"]),
     ("perm2", 36, 28, 3, 255, 63, ["-C", "0", "-M", "1,0"]),
 ]
+
+# 2DMatch (reference transform/2dmatch.h; ref_driver option -D n = exact matches over all channels within offset codes 1..n,
+# applied before the colour transform as fuif.cpp:440-447 does).  The input of these cases is a noisy patch repeated
+# horizontally and vertically (tests/golden/make_golden.py), so that the reference's heuristic finds matches.
+MATCH_CASES = [
+    ("match", 60, 44, 3, 255, 71, ["-D", "1500"]),
+    ("match_nosq", 52, 40, 3, 255, 72, ["-S", "0", "-D", "1200"]),
+    ("match_gray", 64, 36, 1, 255, 73, ["-C", "0", "-D", "900"]),
+]

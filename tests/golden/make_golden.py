@@ -16,14 +16,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from fuif_b200.synth import synth_image, write_pnm  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402
-from tests.cases import APPROX_CASES, CASES, PALETTE_CASES, PERMUTE_CASES  # noqa: E402
+from tests.cases import APPROX_CASES, CASES, MATCH_CASES, PALETTE_CASES, PERMUTE_CASES  # noqa: E402
 
 
 def main():
     po.build()
     assert po.have_ref(), "oracle/_ref/ref_driver missing (needs /root/reference)"
     out_dir = os.path.dirname(os.path.abspath(__file__))
-    which = APPROX_CASES if "approx" in sys.argv[1:] else PALETTE_CASES if "palette" in sys.argv[1:] else PERMUTE_CASES if "permute" in sys.argv[1:] else CASES    # python make_golden.py [approx|palette|permute]
+    which = APPROX_CASES if "approx" in sys.argv[1:] else PALETTE_CASES if "palette" in sys.argv[1:] else PERMUTE_CASES if "permute" in sys.argv[1:] else MATCH_CASES if "match" in sys.argv[1:] else CASES    # python make_golden.py [approx|palette|permute|match]
     for name, w, h, c, maxval, seed, opts in which:
         with tempfile.TemporaryDirectory() as td:
             pnm = os.path.join(td, "in.pnm")
@@ -31,6 +31,10 @@ def main():
             pix = synth_image(w, h, c, maxval, seed)
             if name.startswith("pal"):
                 pix = (pix // 64) * 64 + 17         # four levels per channel: few colours
+            if name.startswith("match"):            # a noisy patch, repeated: something for the matching heuristic to find
+                rng = np.random.default_rng(seed)
+                patch = rng.integers(0, maxval + 1, size=(h // 2 + 3, w // 3 + 2, c)).astype(np.int32)
+                pix = np.tile(patch, (2, 3, 1))[:h, :w, :]
             write_pnm(pnm, pix, maxval)
             po.ref_run("encode", pnm, fuif, *opts)
             po.ref_run("dump", fuif, os.path.join(td, "d"))

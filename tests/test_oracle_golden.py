@@ -2,14 +2,14 @@
 import numpy as np
 import pytest
 
-from tests.cases import APPROX_CASES, CASES, PALETTE_CASES, PERMUTE_CASES
+from tests.cases import APPROX_CASES, CASES, MATCH_CASES, PALETTE_CASES, PERMUTE_CASES
 
 ALL_CASES = CASES + APPROX_CASES + PALETTE_CASES + PERMUTE_CASES
 from tests.util import load_golden, ordered
 from fuif_b200.synth import read_pnm  # noqa: F401
 
 
-@pytest.mark.parametrize("case", ALL_CASES, ids=[c[0] for c in ALL_CASES])
+@pytest.mark.parametrize("case", ALL_CASES + MATCH_CASES, ids=[c[0] for c in ALL_CASES + MATCH_CASES])
 def test_decode_and_undo(oracle, case):
     po = oracle
     blob = load_golden(case[0])
@@ -48,7 +48,7 @@ def test_forward_chain(oracle, case):
         k += 1
 
 
-@pytest.mark.parametrize("case", [c for c in ALL_CASES if c[0] in ("odd", "sq128", "rgba14", "dct", "gray", "approx", "approx_q", "approx14", "pal", "pal4")], ids=lambda c: c[0])
+@pytest.mark.parametrize("case", [c for c in ALL_CASES + MATCH_CASES if c[0] in ("match", "odd", "sq128", "rgba14", "dct", "gray", "approx", "approx_q", "approx14", "pal", "pal4")], ids=lambda c: c[0])
 @pytest.mark.parametrize("preview", [0, 1, 2, 3, 4])
 def test_responsive_decode(oracle, case, preview):
     """-R k partial decodes (encoding.cpp:704-716, squeeze.h:379-383)."""
