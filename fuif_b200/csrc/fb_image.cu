@@ -774,6 +774,67 @@ static int inv_permute(fb_image *img, const std::vector<int> &p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// 2DMatch (reference transform/2dmatch.h): inverse for exact matches + decode-time meta step, single-frame images.  The
+// forward (a search heuristic, :196-385) and soft matches (never produced by the reference CLI, fuif.cpp:445) are not offered.
+// ---------------------------------------------------------------------------------------------------------
+
+static std::vector<int> match_parameters(const fb_image *img, const std::vector<int> &p) {     // default_match_parameters, :89-95
+    if (p.empty()) return {0, img->info.nb_channels - 1, 0, 1000000};
+    return p;
+}
+// meta_match, 2dmatch.h:179-194
+static int meta_match(fb_image *img, const std::vector<int> &p0) {
+    const std::vector<int> p = match_parameters(img, p0);
+    if (p.size() < 3) { img->ctx->err = "2DMatch: incorrect parameters"; return FB_ERR_INVALID; }
+    const int begin_c = img->info.nb_meta_channels + p[0], end_c = img->info.nb_meta_channels + p[1];
+    if (p[0] < 0 || begin_c > end_c || end_c >= (int)img->ch.size()) { img->ctx->err = "2DMatch: incorrect parameters"; return FB_ERR_INVALID; }
+    img->info.nb_meta_channels++;
+    FbChan mch;
+    chan_defaults(mch.d);
+    mch.d.w = img->ch[begin_c].d.w; mch.d.h = img->ch[begin_c].d.h; mch.d.minval = 0; mch.d.maxval = 1;
+    chan_setzero(mch.d);
+    img->ch.insert(img->ch.begin(), mch);
+    return FB_OK;
+}
+// inv_match, 2dmatch.h:97-177
+static int inv_match(fb_image *img, const std::vector<int> &p0) {
+    fb_ctx *ctx = img->ctx;
+    if (img->info.nb_meta_channels < 1) { ctx->err = "2DMatch transform without match channel"; return FB_ERR_INVALID; }
+    const std::vector<int> p = match_parameters(img, p0);
+    if (p.size() < 3) { ctx->err = "2DMatch: incorrect parameters"; return FB_ERR_INVALID; }
+    const int c0 = img->info.nb_meta_channels + p[0], cn = img->info.nb_meta_channels + p[1], nch = (int)img->ch.size();
+    if (p[0] < 0 || p[1] < p[0] || c0 >= nch || cn >= nch) { ctx->err = "2DMatch: incorrect parameters"; return FB_ERR_INVALID; }
+    if (p[2]) { ctx->err = "2DMatch with soft matches is not supported"; return FB_ERR_UNSUPPORTED; }
+    FbChan &m = img->ch[0];
+    if (m.d.q != 1) { ctx->err = "2DMatch against previous frames (animations) is not supported"; return FB_ERR_UNSUPPORTED; }
+    const int w = img->ch[c0].d.w, h = img->ch[c0].d.h;
+    if (m.dev && chan_samples(m.d)) {           // an undecoded match channel reads as zero everywhere: nothing is matched
+        if (m.d.w != w || m.d.h != h || (long long)w * h > 0x7fffffffLL) { ctx->err = "2DMatch: match channel of a different size"; return FB_ERR_UNSUPPORTED; }
+        for (int c = c0; c <= cn; c++)
+            if (!img->ch[c].dev || img->ch[c].d.w != w || img->ch[c].d.h != h) { ctx->err = "2DMatch over undecoded channels or channels of different sizes"; return FB_ERR_UNSUPPORTED; }
+        const int n = w * h;
+        int *parent = nullptr, bad = 0;
+        int rc = fb_match_resolve(ctx, m.dev, n, w, m.d.maxval, &parent, &bad);
+        if (rc) return rc;
+        if (bad) { cudaFreeAsync(parent, ctx->stream); ctx->err = "2DMatch: match code out of range"; return FB_ERR_INVALID; }
+        for (int c = c0; c <= cn && !rc; c++) {
+            FbChan &ch = img->ch[c];
+            int16_t *out = nullptr;
+            if ((rc = fb_plane_alloc(ctx, (size_t)n, &out))) break;
+            rc = fb_launch_match_gather(ctx, ch.dev, out, parent, n, ch.d.zero);
+            fb_plane_free(ctx, ch.dev);
+            ch.dev = out;
+        }
+        if (parent) cudaFreeAsync(parent, ctx->stream);
+        if (rc) return rc;
+    }
+    img->info.nb_meta_channels--;
+    if (m.dev) fb_plane_free(ctx, m.dev);
+    img->ch.erase(img->ch.begin());
+    return FB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Approximate (reference transform/approximate.h): parameters = first channel, last channel, divisor - 1 per channel (the
 // last one repeats; 0 = leave the channel alone).  Channel numbers are absolute (meta channels included), as in the reference.
 // ---------------------------------------------------------------------------------------------------------
@@ -871,6 +932,7 @@ static int transform_meta_apply(fb_image *img, FbXform &t) {
     case FB_TRANSFORM_APPROXIMATE: return meta_approximate(img, t.p);
     case FB_TRANSFORM_PALETTE: return meta_palette(img, t.p);
     case FB_TRANSFORM_PERMUTE: return meta_permute(img, t.p);
+    case FB_TRANSFORM_2DMATCH: return meta_match(img, t.p);
     default:
         img->ctx->err = "transform " + std::to_string(t.id) + " is outside the hot path (SURVEY.md 8: out of scope)";
         return FB_ERR_UNSUPPORTED;
@@ -922,6 +984,7 @@ extern "C" int fb_image_undo_transforms(fb_image *img, int keep) {
         case FB_TRANSFORM_APPROXIMATE: rc = inv_approximate(img, t.p); break;
         case FB_TRANSFORM_PALETTE: rc = inv_palette(img, t.p); break;
         case FB_TRANSFORM_PERMUTE: rc = inv_permute(img, t.p); break;
+        case FB_TRANSFORM_2DMATCH: rc = inv_match(img, t.p); break;
         default:
             ctx->err = "cannot undo transform " + std::to_string(t.id) + " (outside the hot path)";
             rc = FB_ERR_UNSUPPORTED;

@@ -10,6 +10,7 @@
 #include "fb_subsample.cuh"
 #include "fb_approx.cuh"
 #include "fb_palette.cuh"
+#include "fb_match.cuh"
 
 #include <stdlib.h>
 
@@ -1213,6 +1214,43 @@ int fb_launch_palette_index(fb_ctx *ctx, int16_t *const *planes, int nb, size_t 
     pl::k_palette_index<<<nblocks(n, 256), 256, 0, ctx->stream>>>(P, n, nb, sorted_dev, count);
     ctx->launches++;
     ctx->mark("k_palette_index", 2.0 * (double)n * (nb + 1));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e); return FB_ERR_CUDA; }
+    return FB_OK;
+}
+// inv_match (2dmatch.h:97-177, exact matches): resolves every sample's root; parent_out is a device array of n ints the
+// caller frees with cudaFreeAsync.  *bad = 1: a match code outside [0, maxcode].
+int fb_match_resolve(fb_ctx *ctx, const int16_t *m, int n, int w, int maxcode, int **parent_out, int *bad) {
+    *parent_out = nullptr; *bad = 0;
+    if (n <= 0) return FB_OK;
+    int *a = nullptr, *b = nullptr, *flag = nullptr;
+    FB_CUDA(ctx, cudaMallocAsync((void **)&a, (size_t)n * sizeof(int), ctx->stream));
+    FB_CUDA(ctx, cudaMallocAsync((void **)&b, (size_t)n * sizeof(int), ctx->stream));
+    FB_CUDA(ctx, cudaMallocAsync((void **)&flag, sizeof(int), ctx->stream));
+    FB_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    mt::k_match_parent<<<nblocks((size_t)n, 256), 256, 0, ctx->stream>>>(m, a, n, w, maxcode, flag);
+    ctx->launches++;
+    int rounds = 1;
+    while ((1ll << rounds) < n) rounds++;           // a chain is at most n samples long
+    for (int r = 0; r < rounds; r++) {
+        mt::k_match_jump<<<nblocks((size_t)n, 256), 256, 0, ctx->stream>>>(a, b, n);
+        ctx->launches++;
+        std::swap(a, b);
+    }
+    ctx->mark("k_match_parent+jump", (double)n * (2.0 + 8.0 * rounds));
+    FB_CUDA(ctx, cudaGetLastError());
+    FB_CUDA(ctx, cudaMemcpyAsync(bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(b, ctx->stream);
+    cudaFreeAsync(flag, ctx->stream);
+    *parent_out = a;
+    return FB_OK;
+}
+int fb_launch_match_gather(fb_ctx *ctx, const int16_t *src, int16_t *dst, const int *parent, int n, int zero) {
+    if (n <= 0) return FB_OK;
+    mt::k_match_gather<<<nblocks((size_t)n, 256), 256, 0, ctx->stream>>>(src, dst, parent, n, zero);
+    ctx->launches++;
+    ctx->mark("k_match_gather", 8.0 * n);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e); return FB_ERR_CUDA; }
     return FB_OK;

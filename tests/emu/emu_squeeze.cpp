@@ -11,6 +11,7 @@
 #include "fb_subsample.cuh"
 #include "fb_approx.cuh"
 #include "fb_palette.cuh"
+#include "fb_match.cuh"
 
 extern "C" {
 
@@ -43,6 +44,30 @@ int emu_palette_fwd(int16_t **planes, int nb, long long n, int limit, int16_t *p
     for (int k = 0; k < count; k++) for (int c = 0; c < nb; c++) palette[(size_t)c * count + k] = (int16_t)pl::unpack_colour(sorted[(size_t)k], c);
     if (n > 0) cuemu::launch(nblk, 256, 0, false, [&]() { pl::k_palette_index(P, (size_t)n, nb, sorted.data(), count); });
     return count;
+}
+
+// inv_match as the library runs it: parents, log2(n) rounds of pointer jumping (double-buffered), one out-of-place gather per
+// channel.  planes[c] are overwritten with the result.  Returns 1 when a match code is out of range.
+int emu_match_inv(const int16_t *m, int16_t **planes, int nc, int w, int h, int maxcode, const int *zero) {
+    const int n = w * h;
+    if (n <= 0) return 0;
+    std::vector<int> a((size_t)n), b((size_t)n);
+    int bad = 0;
+    const unsigned nblk = (unsigned)((n + 255) / 256);
+    cuemu::launch(nblk, 256, 0, false, [&]() { mt::k_match_parent(m, a.data(), n, w, maxcode, &bad); });
+    int rounds = 1;
+    while ((1ll << rounds) < n) rounds++;
+    for (int r = 0; r < rounds; r++) {
+        cuemu::launch(nblk, 256, 0, false, [&]() { mt::k_match_jump(a.data(), b.data(), n); });
+        a.swap(b);
+    }
+    if (bad) return 1;
+    for (int c = 0; c < nc; c++) {
+        std::vector<int16_t> out((size_t)n);
+        cuemu::launch(nblk, 256, 0, false, [&]() { mt::k_match_gather(planes[c], out.data(), a.data(), n, zero[c]); });
+        memcpy(planes[c], out.data(), (size_t)n * sizeof(int16_t));
+    }
+    return 0;
 }
 
 // the Approximate kernels on one channel (+ its remainder channel; chr may be NULL for the inverse)

@@ -15,7 +15,8 @@ SRCS = [os.path.join(EMU_DIR, "emu_squeeze.cpp"), os.path.join(EMU_DIR, "cuemu.h
         os.path.join(ROOT, "fuif_b200", "csrc", "fb_fused_squeeze.cuh"), os.path.join(ROOT, "fuif_b200", "csrc", "fb_fused_plan.h"),
         os.path.join(ROOT, "fuif_b200", "csrc", "fb_port.h"), os.path.join(ROOT, "fuif_b200", "csrc", "fb_direct_squeeze.cuh"),
         os.path.join(ROOT, "fuif_b200", "csrc", "fb_direct_plan.h"), os.path.join(ROOT, "fuif_b200", "csrc", "fb_subsample.cuh"),
-        os.path.join(ROOT, "fuif_b200", "csrc", "fb_approx.cuh"), os.path.join(ROOT, "fuif_b200", "csrc", "fb_palette.cuh")]
+        os.path.join(ROOT, "fuif_b200", "csrc", "fb_approx.cuh"), os.path.join(ROOT, "fuif_b200", "csrc", "fb_palette.cuh"),
+        os.path.join(ROOT, "fuif_b200", "csrc", "fb_match.cuh")]
 _lib = None
 
 
@@ -35,6 +36,7 @@ def lib():
         L.emu_approximate.restype = None
         L.emu_palette_inv.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_longlong]
         L.emu_palette_inv.restype = None
+        L.emu_match_inv.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.emu_palette_fwd.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_int]
         _lib = L
     return _lib
