@@ -103,11 +103,11 @@ def test_kernel_source_decodes_golden_indexed(oracle, name):
     _check(oracle, bytes(load_golden(name)["fuif"]), indexed=True)
 
 
-@pytest.mark.parametrize("name", ["approx", "approx_nosq", "approx14", "pal", "pal_nosq", "pal4", "pal_c0"])
-@pytest.mark.parametrize("indexed", [True, False], ids=["indexed", "sequential"])
+@pytest.mark.parametrize("name,indexed", [("approx", True), ("approx_nosq", False), ("approx14", True), ("pal", True), ("pal", False), ("pal_nosq", True),
+                                          ("pal4", False), ("pal_c0", True), ("match_gray", True), ("match_gray", False), ("match_nosq", True), ("perm", True)])
 def test_kernel_source_decodes_meta_and_remainder_channels(oracle, name, indexed):
-    """files whose channel list starts with a palette meta-channel (hshift -1: never a back-reference, context_predict.h:73)
-    or ends with Approximate's remainder channels"""
+    """files whose channel list starts with a meta-channel -- a palette (hshift -1: never a back-reference,
+    context_predict.h:73) or a 2DMatch code plane (hshift 0: it IS one) -- or ends with Approximate's remainder channels"""
     _check(oracle, bytes(load_golden(name)["fuif"]), indexed=indexed)
 
 
