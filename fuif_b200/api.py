@@ -20,6 +20,8 @@ LIB_PATH = os.path.join(_HERE, "libfuif_b200.so")
 TRANSFORM_YCbCr = 0
 TRANSFORM_YCoCg = 1
 TRANSFORM_ChromaSubsample = 3
+TRANSFORM_2DMATCH = 8
+TRANSFORM_PERMUTE = 9
 TRANSFORM_APPROXIMATE = 10
 TRANSFORM_DCT = 4
 TRANSFORM_QUANTIZE = 5

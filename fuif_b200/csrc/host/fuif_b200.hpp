@@ -35,6 +35,8 @@ typedef int16_t pixel_type;     // reference image/image.h:35
 #define TRANSFORM_QUANTIZE 5
 #define TRANSFORM_PALETTE 6
 #define TRANSFORM_SQUEEZE 7
+#define TRANSFORM_2DMATCH 8
+#define TRANSFORM_PERMUTE 9
 #define TRANSFORM_APPROXIMATE 10
 
 inline fb_ctx *default_context() {
