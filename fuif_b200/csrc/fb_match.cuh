@@ -2,7 +2,7 @@
 // zero takes the already reconstructed sample at the 2D offset that z encodes -- a serial chain in the reference, because
 // the source may itself be a matched sample.  On the GPU it is pointer jumping: every sample points at its source
 // (k_match_parent), path doubling replaces "my source" by "my source's source" until everything points at a sample that is
-// not matched (k_match_jump, log2(longest chain) rounds, double-buffered), and one gather per channel copies the roots'
+// not matched (k_match_jump, log2(longest chain) rounds, double-buffered, stopped once nothing moves), and one gather per channel copies the roots'
 // values (k_match_gather, out of place).
 //
 // parent[i] >= 0   : index of the sample this one copies (itself: not matched)
@@ -48,13 +48,16 @@ FB_KERNEL(256) k_match_parent(const int16_t *m, int *parent, int n, int w, int m
     else parent[i] = (int)src;
 }
 
-FB_KERNEL(256) k_match_jump(const int *in, int *out, int n) {
+// *changed is set when some sample moved: the host stops the rounds as soon as a whole batch of them changed nothing
+FB_KERNEL(256) k_match_jump(const int *in, int *out, int n, int *changed) {
     const int i = (int)((size_t)blockIdx.x * blockDim.x + threadIdx.x);
     if (i >= n) return;
     const int p = in[i];
     if (p < 0 || p == i) { out[i] = p; return; }
     const int g = in[p];
-    out[i] = (g == p) ? p : g;          // my source is a root: done; otherwise adopt what my source points at (an index or a terminal code)
+    const int q = (g == p) ? p : g;     // my source is a root: done; otherwise adopt what my source points at (an index or a terminal code)
+    out[i] = q;
+    if (q != p) *changed = 1;
 }
 
 FB_KERNEL(256) k_match_gather(const int16_t *src, int16_t *dst, const int *parent, int n, int zero) {

@@ -1226,18 +1226,26 @@ int fb_match_resolve(fb_ctx *ctx, const int16_t *m, int n, int w, int maxcode, i
     int *a = nullptr, *b = nullptr, *flag = nullptr;
     FB_CUDA(ctx, cudaMallocAsync((void **)&a, (size_t)n * sizeof(int), ctx->stream));
     FB_CUDA(ctx, cudaMallocAsync((void **)&b, (size_t)n * sizeof(int), ctx->stream));
-    FB_CUDA(ctx, cudaMallocAsync((void **)&flag, sizeof(int), ctx->stream));
-    FB_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    FB_CUDA(ctx, cudaMallocAsync((void **)&flag, 2 * sizeof(int), ctx->stream));       // [0] bad code, [1] something moved in this batch
+    FB_CUDA(ctx, cudaMemsetAsync(flag, 0, 2 * sizeof(int), ctx->stream));
     mt::k_match_parent<<<nblocks((size_t)n, 256), 256, 0, ctx->stream>>>(m, a, n, w, maxcode, flag);
     ctx->launches++;
     int rounds = 1;
     while ((1ll << rounds) < n) rounds++;           // a chain is at most n samples long
-    for (int r = 0; r < rounds; r++) {
-        mt::k_match_jump<<<nblocks((size_t)n, 256), 256, 0, ctx->stream>>>(a, b, n);
-        ctx->launches++;
-        std::swap(a, b);
+    // chains in real files are a few samples long: the rounds run in batches of three, and a batch in which nothing moved ends them
+    int done = 0, hflag[2] = {0, 0};
+    while (done < rounds) {
+        FB_CUDA(ctx, cudaMemsetAsync(flag + 1, 0, sizeof(int), ctx->stream));
+        for (int r = 0; r < 3 && done < rounds; r++, done++) {
+            mt::k_match_jump<<<nblocks((size_t)n, 256), 256, 0, ctx->stream>>>(a, b, n, flag + 1);
+            ctx->launches++;
+            std::swap(a, b);
+        }
+        FB_CUDA(ctx, cudaMemcpyAsync(hflag, flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!hflag[1]) break;
     }
-    ctx->mark("k_match_parent+jump", (double)n * (2.0 + 8.0 * rounds));
+    ctx->mark("k_match_parent+jump", (double)n * (2.0 + 8.0 * done));
     FB_CUDA(ctx, cudaGetLastError());
     FB_CUDA(ctx, cudaMemcpyAsync(bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -57,9 +57,13 @@ int emu_match_inv(const int16_t *m, int16_t **planes, int nc, int w, int h, int 
     cuemu::launch(nblk, 256, 0, false, [&]() { mt::k_match_parent(m, a.data(), n, w, maxcode, &bad); });
     int rounds = 1;
     while ((1ll << rounds) < n) rounds++;
-    for (int r = 0; r < rounds; r++) {
-        cuemu::launch(nblk, 256, 0, false, [&]() { mt::k_match_jump(a.data(), b.data(), n); });
-        a.swap(b);
+    for (int done = 0; done < rounds;) {            // batches of three rounds, as fb_match_resolve runs them
+        int changed = 0;
+        for (int r = 0; r < 3 && done < rounds; r++, done++) {
+            cuemu::launch(nblk, 256, 0, false, [&]() { mt::k_match_jump(a.data(), b.data(), n, &changed); });
+            a.swap(b);
+        }
+        if (!changed) break;
     }
     if (bad) return 1;
     for (int c = 0; c < nc; c++) {
