@@ -119,6 +119,7 @@ int fb_palette_collect(fb_ctx *ctx, int16_t *const *planes, int nb, size_t n, in
 int fb_launch_palette_index(fb_ctx *ctx, int16_t *const *planes, int nb, size_t n, const unsigned long long *sorted_dev, int count);
 // inv_match (2dmatch.h:97-177, exact matches): roots of all samples by pointer jumping, then one gather per channel
 int fb_match_resolve(fb_ctx *ctx, const int16_t *m, int n, int w, int maxcode, int **parent_out, int *bad);
+int fb_match_soft(fb_ctx *ctx, const int16_t *m, const int16_t *orig, int16_t *out, int n, int w, int maxcode, int zero, int *bad);
 int fb_launch_match_gather(fb_ctx *ctx, const int16_t *src, int16_t *dst, const int *parent, int n, int zero);
 // Approximate (approximate.h:32-113): inverse ch = ch*q + chr (chr may be nullptr), forward ch, chr = floor-div / remainder
 int fb_launch_approximate(fb_ctx *ctx, int16_t *ch, int16_t *chr, size_t n, int q, int inverse);

@@ -774,8 +774,8 @@ static int inv_permute(fb_image *img, const std::vector<int> &p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// 2DMatch (reference transform/2dmatch.h): inverse for exact matches + decode-time meta step, single-frame images.  The
-// forward (a search heuristic, :196-385) and soft matches (never produced by the reference CLI, fuif.cpp:445) are not offered.
+// 2DMatch (reference transform/2dmatch.h): inverse (exact and soft matches) + decode-time meta step, single-frame images.  The
+// forward (a search heuristic, :196-385) is not offered.
 // ---------------------------------------------------------------------------------------------------------
 
 static std::vector<int> match_parameters(const fb_image *img, const std::vector<int> &p) {     // default_match_parameters, :89-95
@@ -804,7 +804,7 @@ static int inv_match(fb_image *img, const std::vector<int> &p0) {
     if (p.size() < 3) { ctx->err = "2DMatch: incorrect parameters"; return FB_ERR_INVALID; }
     const int c0 = img->info.nb_meta_channels + p[0], cn = img->info.nb_meta_channels + p[1], nch = (int)img->ch.size();
     if (p[0] < 0 || p[1] < p[0] || c0 >= nch || cn >= nch) { ctx->err = "2DMatch: incorrect parameters"; return FB_ERR_INVALID; }
-    if (p[2]) { ctx->err = "2DMatch with soft matches is not supported"; return FB_ERR_UNSUPPORTED; }
+    const bool softmatch = p[2] != 0;
     FbChan &m = img->ch[0];
     if (m.d.q != 1) { ctx->err = "2DMatch against previous frames (animations) is not supported"; return FB_ERR_UNSUPPORTED; }
     const int w = img->ch[c0].d.w, h = img->ch[c0].d.h;
@@ -814,7 +814,19 @@ static int inv_match(fb_image *img, const std::vector<int> &p0) {
             if (!img->ch[c].dev || img->ch[c].d.w != w || img->ch[c].d.h != h) { ctx->err = "2DMatch over undecoded channels or channels of different sizes"; return FB_ERR_UNSUPPORTED; }
         const int n = w * h;
         int *parent = nullptr, bad = 0;
-        int rc = fb_match_resolve(ctx, m.dev, n, w, m.d.maxval, &parent, &bad);
+        int rc = FB_OK;
+        if (softmatch) {        // sums along the chains, one channel at a time
+            for (int c = c0; c <= cn; c++) {
+                FbChan &ch = img->ch[c];
+                int16_t *out = nullptr;
+                if ((rc = fb_plane_alloc(ctx, (size_t)n, &out))) return rc;
+                rc = fb_match_soft(ctx, m.dev, ch.dev, out, n, w, m.d.maxval, ch.d.zero, &bad);
+                if (rc || bad) { fb_plane_free(ctx, out); if (rc) return rc; ctx->err = "2DMatch: match code out of range"; return FB_ERR_INVALID; }
+                fb_plane_free(ctx, ch.dev);
+                ch.dev = out;
+            }
+        } else {
+        rc = fb_match_resolve(ctx, m.dev, n, w, m.d.maxval, &parent, &bad);
         if (rc) return rc;
         if (bad) { cudaFreeAsync(parent, ctx->stream); ctx->err = "2DMatch: match code out of range"; return FB_ERR_INVALID; }
         for (int c = c0; c <= cn && !rc; c++) {
@@ -827,6 +839,7 @@ static int inv_match(fb_image *img, const std::vector<int> &p0) {
         }
         if (parent) cudaFreeAsync(parent, ctx->stream);
         if (rc) return rc;
+        }
     }
     img->info.nb_meta_channels--;
     if (m.dev) fb_plane_free(ctx, m.dev);

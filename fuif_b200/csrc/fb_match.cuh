@@ -1,4 +1,4 @@
-// inv_match (reference transform/2dmatch.h:97-177), exact matches: in scanline order every sample whose match code z is not
+// inv_match (reference transform/2dmatch.h:97-177).  Exact matches: in scanline order every sample whose match code z is not
 // zero takes the already reconstructed sample at the 2D offset that z encodes -- a serial chain in the reference, because
 // the source may itself be a matched sample.  On the GPU it is pointer jumping: every sample points at its source
 // (k_match_parent), path doubling replaces "my source" by "my source's source" until everything points at a sample that is
@@ -65,6 +65,44 @@ FB_KERNEL(256) k_match_gather(const int16_t *src, int16_t *dst, const int *paren
     if (i >= n) return;
     const int p = parent[i];
     dst[i] = p >= 0 ? src[p] : (p == -1 ? (int16_t)zero : src[-2 - p]);
+}
+
+// ---- soft matches (2dmatch.h:119-129): value[i] += value[source] instead of a copy ------------------------------------------
+// The same chains, but what travels along them is a sum: acc[i] starts as the sample's own (residual) value, a round adds
+// the source's acc and adopts the source's parent -- int16 wrap-around addition is associative, so the order of the
+// additions does not matter.  Samples whose source is a terminal (outside the plane: `zero`; a forward reference: that
+// sample's original content) are roots whose value already includes the terminal.  One channel at a time.
+FB_KERNEL(256) k_match_soft_init(const int16_t *m, const int16_t *orig, int *parent, int16_t *acc, int n, int w, int maxcode, int zero, int *bad) {
+    const int i = (int)((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= n) return;
+    const int z = m[i];
+    const int own = orig[i];
+    if (z == 0) { parent[i] = i; acc[i] = (int16_t)own; return; }
+    if (z < 0 || z > maxcode) { *bad = 1; parent[i] = i; acc[i] = (int16_t)own; return; }
+    int dx, dy;
+    match_offset(z, dx, dy);
+    const long long src = (long long)i + (long long)dy * w + dx;
+    if (src < 0 || src >= n) { parent[i] = i; acc[i] = (int16_t)(own + zero); }
+    else if (src >= i) { parent[i] = i; acc[i] = (int16_t)(own + orig[src]); }
+    else { parent[i] = (int)src; acc[i] = (int16_t)own; }
+}
+FB_KERNEL(256) k_match_soft_jump(const int *pin, const int16_t *ain, int *pout, int16_t *aout, int n, int *changed) {
+    const int i = (int)((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= n) return;
+    const int p = pin[i];
+    const int a = ain[i];
+    if (p == i) { pout[i] = p; aout[i] = (int16_t)a; return; }
+    const int g = pin[p];
+    if (g == p) { pout[i] = p; aout[i] = (int16_t)a; return; }         // my source is a root: its value is added at the end
+    pout[i] = g;
+    aout[i] = (int16_t)(a + ain[p]);
+    *changed = 1;
+}
+FB_KERNEL(256) k_match_soft_finish(const int *parent, const int16_t *acc, int16_t *dst, int n) {
+    const int i = (int)((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= n) return;
+    const int p = parent[i];
+    dst[i] = p == i ? acc[i] : (int16_t)(acc[i] + acc[p]);
 }
 
 }  // namespace mt

@@ -1254,6 +1254,43 @@ int fb_match_resolve(fb_ctx *ctx, const int16_t *m, int n, int w, int maxcode, i
     *parent_out = a;
     return FB_OK;
 }
+// inv_match with soft matches on ONE channel: out = reconstructed plane (caller-allocated, n samples)
+int fb_match_soft(fb_ctx *ctx, const int16_t *m, const int16_t *orig, int16_t *out, int n, int w, int maxcode, int zero, int *bad) {
+    *bad = 0;
+    if (n <= 0) return FB_OK;
+    int *pa = nullptr, *pb = nullptr, *flag = nullptr;
+    int16_t *aa = nullptr, *ab = nullptr;
+    FB_CUDA(ctx, cudaMallocAsync((void **)&pa, (size_t)n * sizeof(int), ctx->stream));
+    FB_CUDA(ctx, cudaMallocAsync((void **)&pb, (size_t)n * sizeof(int), ctx->stream));
+    FB_CUDA(ctx, cudaMallocAsync((void **)&aa, (size_t)n * sizeof(int16_t), ctx->stream));
+    FB_CUDA(ctx, cudaMallocAsync((void **)&ab, (size_t)n * sizeof(int16_t), ctx->stream));
+    FB_CUDA(ctx, cudaMallocAsync((void **)&flag, 2 * sizeof(int), ctx->stream));
+    FB_CUDA(ctx, cudaMemsetAsync(flag, 0, 2 * sizeof(int), ctx->stream));
+    mt::k_match_soft_init<<<nblocks((size_t)n, 256), 256, 0, ctx->stream>>>(m, orig, pa, aa, n, w, maxcode, zero, flag);
+    ctx->launches++;
+    int rounds = 1;
+    while ((1ll << rounds) < n) rounds++;
+    int done = 0, hflag[2] = {0, 0};
+    while (done < rounds) {
+        FB_CUDA(ctx, cudaMemsetAsync(flag + 1, 0, sizeof(int), ctx->stream));
+        for (int r = 0; r < 3 && done < rounds; r++, done++) {
+            mt::k_match_soft_jump<<<nblocks((size_t)n, 256), 256, 0, ctx->stream>>>(pa, aa, pb, ab, n, flag + 1);
+            ctx->launches++;
+            std::swap(pa, pb);
+            std::swap(aa, ab);
+        }
+        FB_CUDA(ctx, cudaMemcpyAsync(hflag, flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!hflag[1]) break;
+    }
+    mt::k_match_soft_finish<<<nblocks((size_t)n, 256), 256, 0, ctx->stream>>>(pa, aa, out, n);
+    ctx->launches++;
+    ctx->mark("k_match_soft", (double)n * (8.0 + 12.0 * done));
+    FB_CUDA(ctx, cudaGetLastError());
+    *bad = hflag[0];
+    cudaFreeAsync(pa, ctx->stream); cudaFreeAsync(pb, ctx->stream); cudaFreeAsync(aa, ctx->stream); cudaFreeAsync(ab, ctx->stream); cudaFreeAsync(flag, ctx->stream);
+    return FB_OK;
+}
 int fb_launch_match_gather(fb_ctx *ctx, const int16_t *src, int16_t *dst, const int *parent, int n, int zero) {
     if (n <= 0) return FB_OK;
     mt::k_match_gather<<<nblocks((size_t)n, 256), 256, 0, ctx->stream>>>(src, dst, parent, n, zero);

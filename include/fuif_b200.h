@@ -29,7 +29,7 @@ extern "C" {
 #define FB_OK 0
 #define FB_ERR_INVALID 1      /* bad argument / malformed stream ("return false" in the reference)            */
 #define FB_ERR_CUDA 2         /* CUDA runtime error; fb_last_error() has the text                            */
-#define FB_ERR_UNSUPPORTED 3  /* not offered: forward 2dmatch, soft matches, permute via a meta-channel, palettes over > 4 channels */
+#define FB_ERR_UNSUPPORTED 3  /* not offered: forward 2dmatch, permute via a meta-channel, palettes over > 4 channels */
 #define FB_ERR_NOMEM 4
 
 /* transform ids, reference transform/transform.h:30-70 */
@@ -160,7 +160,7 @@ FB_API int fb_image_download_interleaved(fb_image *img, int n_channels, int byte
  * `keep` are left, then (keep == 0) clamps every sample to [minval, maxval].  Runs entirely on the GPU:
  * Squeeze (transform/squeeze.h:363-388), Quantize (quantize.h:32-49), DCT (dct.h:249-296),
  * YCbCr (ycbcr.h:33-63), YCoCg (ycocg.h:33-63), ChromaSubsample (subsample.h:73-128), Approximate (approximate.h:32-62),
- * Palette (palette.h:32-68), Permute with explicit parameters (permute.h:31-55), 2DMatch with exact matches (2dmatch.h:97-177). */
+ * Palette (palette.h:32-68), Permute with explicit parameters (permute.h:31-55), 2DMatch (2dmatch.h:97-177). */
 FB_API int fb_image_undo_transforms(fb_image *img, int keep);
 
 /* Replaces Image::do_transform (reference image/image.cpp:117-122; forward direction of the same transforms).

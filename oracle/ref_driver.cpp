@@ -18,7 +18,7 @@
 //   fuif_decode_file           encoding/encoding.cpp:745
 //
 // Sub-commands:
-//   encode <in.pam> <out.fuif> [-C 0|1|2] [-J] [-S 0|1] [-q luma,chroma] [-E n] [-I f] [-G n] [-P digits] [-A k,q] [-L colours] [-M perm] [-D dist]
+//   encode <in.pam> <out.fuif> [-C 0|1|2] [-J] [-S 0|1] [-q luma,chroma] [-E n] [-I f] [-G n] [-P digits] [-A k,q] [-L colours] [-M perm] [-D dist [-W]]
 //   decode <in.fuif> <out.pam> [-R k]
 //   dump   <in.fuif> <prefix>  [-R k]     planes after decode and after each inverse transform
 //   fwd    <in.pam>  <prefix>  [same options as encode]   planes after each forward transform
@@ -73,6 +73,7 @@ struct EncOpts {
     bool squeeze = true;
     int qluma = 0, qchroma = 0;  // 0 = lossless
     std::vector<int> permutation;   // -M a,b,c: TRANSFORM_PERMUTE with explicit parameters (-1 is prepended: fwd_permute's "no meta-channel" mode, permute.h:90-93)
+    int match_soft = 0;      // -W: soft matches (the matched samples keep a residual that is added back, 2dmatch.h:119-129)
     int match_dist = 0;      // -D n: TRANSFORM_2DMATCH over all channels, exact matches, search distance n (fuif.cpp:440-447), before the colour transform
     int palette_colors = 0;  // -L n: all-channel TRANSFORM_PALETTE with at most n colours after the colour transform (fuif.cpp:398-407)
     int approx_k = 0, approx_q = 0;     // -A k,q: TRANSFORM_APPROXIMATE on the last k channels with divisor q+1 (fuif.cpp:504-510)
@@ -92,6 +93,7 @@ static bool parse_enc_opts(int argc, char **argv, int start, EncOpts &o) {
         else if (a == "-G") o.options.max_group = atoi(need());
         else if (a == "-U") o.options.compress = false;
         else if (a == "-D") o.match_dist = atoi(need());
+        else if (a == "-W") o.match_soft = 1;
         else if (a == "-L") o.palette_colors = atoi(need());
         else if (a == "-M") { const char *v = need(); char *dup = strdup(v); for (char *tok = strtok(dup, ","); tok; tok = strtok(nullptr, ",")) o.permutation.push_back(atoi(tok)); free(dup); }
         else if (a == "-A") { if (sscanf(need(), "%d,%d", &o.approx_k, &o.approx_q) != 2) return false; }
@@ -115,7 +117,7 @@ static bool build_chain(Image &img, EncOpts &o, const std::string *dump_prefix) 
         Transform match(TRANSFORM_2DMATCH);
         match.parameters.push_back(0);
         match.parameters.push_back(img.nb_channels - 1);
-        match.parameters.push_back(0);
+        match.parameters.push_back(o.match_soft);
         match.parameters.push_back(o.match_dist);
         if (img.do_transform(match)) dump();
     }

@@ -74,4 +74,5 @@ MATCH_CASES = [
     ("match", 60, 44, 3, 255, 71, ["-D", "1500"]),
     ("match_nosq", 52, 40, 3, 255, 72, ["-S", "0", "-D", "1200"]),
     ("match_gray", 64, 36, 1, 255, 73, ["-C", "0", "-D", "900"]),
+    ("match_soft", 48, 34, 3, 255, 74, ["-S", "0", "-D", "900", "-W"]),
 ]

@@ -74,6 +74,30 @@ int emu_match_inv(const int16_t *m, int16_t **planes, int nc, int w, int h, int 
     return 0;
 }
 
+// inv_match with soft matches on one channel, as fb_match_soft runs it; plane is overwritten.  Returns 1 on a bad code.
+int emu_match_soft(const int16_t *m, int16_t *plane, int w, int h, int maxcode, int zero) {
+    const int n = w * h;
+    if (n <= 0) return 0;
+    std::vector<int> pa((size_t)n), pb((size_t)n);
+    std::vector<int16_t> aa((size_t)n), ab((size_t)n), out((size_t)n);
+    int bad = 0;
+    const unsigned nblk = (unsigned)((n + 255) / 256);
+    cuemu::launch(nblk, 256, 0, false, [&]() { mt::k_match_soft_init(m, plane, pa.data(), aa.data(), n, w, maxcode, zero, &bad); });
+    int rounds = 1;
+    while ((1ll << rounds) < n) rounds++;
+    for (int done = 0; done < rounds;) {
+        int changed = 0;
+        for (int r = 0; r < 3 && done < rounds; r++, done++) {
+            cuemu::launch(nblk, 256, 0, false, [&]() { mt::k_match_soft_jump(pa.data(), aa.data(), pb.data(), ab.data(), n, &changed); });
+            pa.swap(pb); aa.swap(ab);
+        }
+        if (!changed) break;
+    }
+    cuemu::launch(nblk, 256, 0, false, [&]() { mt::k_match_soft_finish(pa.data(), aa.data(), out.data(), n); });
+    memcpy(plane, out.data(), (size_t)n * sizeof(int16_t));
+    return bad;
+}
+
 // the Approximate kernels on one channel (+ its remainder channel; chr may be NULL for the inverse)
 void emu_approximate(int16_t *ch, int16_t *chr, long long n, int q, int inverse) {
     if (n <= 0) return;

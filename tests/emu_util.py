@@ -37,6 +37,7 @@ def lib():
         L.emu_palette_inv.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_longlong]
         L.emu_palette_inv.restype = None
         L.emu_match_inv.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.emu_match_soft.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.emu_palette_fwd.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_int]
         _lib = L
     return _lib

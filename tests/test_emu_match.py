@@ -35,8 +35,8 @@ def _offset(code):
     return 1 + layer, -5 - 4 * layer + code
 
 
-def _sequential(m, chan, zero):
-    """the loop of inv_match (2dmatch.h:131-141) with Channel::value's flat indexing (image.h:82-85)"""
+def _sequential(m, chan, zero, soft=False):
+    """the loops of inv_match (2dmatch.h:119-141) with Channel::value's flat indexing (image.h:82-85)"""
     h, w = m.shape
     flat = chan.astype(np.int16).reshape(-1).copy()
     n = flat.size
@@ -46,7 +46,8 @@ def _sequential(m, chan, zero):
             if z:
                 dx, dy = _offset(z)
                 src = (y + dy) * w + (x + dx)
-                flat[y * w + x] = flat[src] if 0 <= src < n else zero
+                v = int(flat[src]) if 0 <= src < n else zero
+                flat[y * w + x] = np.int16(((int(flat[y * w + x]) + v + 32768) % 65536) - 32768) if soft else v
     return flat.reshape(h, w)
 
 
@@ -60,8 +61,17 @@ def test_match_kernels_vs_reference(oracle, case):
     m = before.planes[0]
     assert int((m.data != 0).sum()) > 100
     chans = [p.data for p in before.planes[1:]]
-    bad, got = _run(m.data, chans, m.maxval, [p.zero for p in before.planes[1:]])
-    assert bad == 0
+    params = before.transforms[-1][1]
+    if params and params[2]:            # soft matches: the summing kernels, one channel at a time
+        got = []
+        mm = np.ascontiguousarray(m.data.astype(np.int16))
+        for pl_ in before.planes[1:]:
+            g = np.ascontiguousarray(pl_.data.astype(np.int16))
+            assert emu_util.lib().emu_match_soft(mm.ctypes.data, g.ctypes.data, g.shape[1], g.shape[0], m.maxval, pl_.zero) == 0
+            got.append(g)
+    else:
+        bad, got = _run(m.data, chans, m.maxval, [p.zero for p in before.planes[1:]])
+        assert bad == 0
     for c, g in enumerate(got):
         assert np.array_equal(g, after.planes[c].data), f"{case[0]} channel {c}"
 
@@ -84,3 +94,19 @@ def test_match_code_out_of_range_is_reported():
     m = np.zeros((4, 4), dtype=np.int16)
     m[2, 2] = 50
     assert _run(m, [np.zeros((4, 4), dtype=np.int16)], 10, [0])[0] == 1
+
+
+@pytest.mark.parametrize("shape", [(23, 31), (40, 3), (64, 1), (5, 200)])
+def test_soft_match_kernels_vs_sequential_model(shape):
+    """soft matches add the source instead of copying it (2dmatch.h:119-129): sums along the chains with int16 wrap-around"""
+    h, w = shape
+    rng = np.random.default_rng(h * 7 + w)
+    maxcode = 400
+    m = np.where(rng.random((h, w)) < 0.7, rng.integers(1, maxcode + 1, size=(h, w)), 0).astype(np.int16)
+    m[:, : w // 2] = np.where(rng.random((h, w // 2)) < 0.9, 1, m[:, : w // 2])
+    for zero, scale in ((0, 3000), (-11, 32767)):       # the second one wraps many times along a chain
+        chan = rng.integers(-scale, scale + 1, size=(h, w)).astype(np.int16)
+        got = np.ascontiguousarray(chan.copy())
+        mm = np.ascontiguousarray(m)
+        assert emu_util.lib().emu_match_soft(mm.ctypes.data, got.ctypes.data, w, h, maxcode, zero) == 0
+        assert np.array_equal(got, _sequential(m, chan, zero, soft=True))
