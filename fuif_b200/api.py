@@ -31,6 +31,7 @@ TRANSFORM_SQUEEZE = 7
 FB_OK = 0
 FB_OPT_SQUEEZE_MODE = 1
 FB_OPT_KERNEL_TIMING = 2
+FB_OPT_SQUEEZE_PACKED = 3
 
 
 class FuifError(RuntimeError):
@@ -63,7 +64,7 @@ ABI_SYMBOLS = [
     "fb_image_plane_device_ptr", "fb_image_download_plane", "fb_image_download_interleaved",
     "fb_image_undo_transforms", "fb_image_do_transform", "fb_image_recompute_minmax",
     "fb_decode_to_pixels", "fb_peek_header", "fb_ctx_set_option", "fb_ctx_counter", "fb_ctx_timing_report",
-    "fb_encode", "fb_free",
+    "fb_encode", "fb_free", "fb_selftest_packed",
 ]
 
 _lib = None
@@ -90,6 +91,7 @@ def load_library():
     L.fb_ctx_set_option.argtypes = [vp, C.c_int, C.c_int]
     L.fb_ctx_counter.argtypes = [vp, C.c_int]
     L.fb_ctx_counter.restype = C.c_longlong
+    L.fb_selftest_packed.argtypes = [vp, C.c_int, C.c_uint, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
     L.fb_ctx_timing_report.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.fb_ctx_timing_report.restype = C.c_longlong
     L.fb_decode.argtypes = [vp, vp, C.c_size_t, C.POINTER(DecodeOptions), i64p, i32p, C.c_int, C.POINTER(vp)]
@@ -216,6 +218,26 @@ class Context:
     def repaired_tiles(self) -> int:
         """Tiles of last launches whose speculative start failed verification (recomputed from exact states)."""
         return int(self.lib.fb_ctx_counter(self.h, 1))
+
+    def set_squeeze_packed(self, on: bool) -> None:
+        """Packed int16x2 unsqueeze kernels (TMA-fed; default on for images with maxval <= 1023); off = the 32-bit kernels."""
+        self.check(self.lib.fb_ctx_set_option(self.h, FB_OPT_SQUEEZE_PACKED, 1 if on else 0), "fb_ctx_set_option")
+
+    @property
+    def pk_repaired(self) -> int:
+        """Segments the packed unsqueeze kernels recomputed with the exact routine (speculation miss or range flag)."""
+        return int(self.lib.fb_ctx_counter(self.h, 2))
+
+    @property
+    def pk_range_flagged(self) -> int:
+        """Segments in which the packed unsqueeze kernels met a value outside the packed range."""
+        return int(self.lib.fb_ctx_counter(self.h, 3))
+
+    def selftest_packed(self, which: int, seed: int = 1, scale: int = 64, maxval: int = 255) -> int:
+        """Mismatches of the packed 16x2 primitives against their exact forms on the device (0 = correct)."""
+        n = C.c_longlong(-1)
+        self.check(self.lib.fb_selftest_packed(self.h, which, seed, scale, maxval, C.byref(n)), "fb_selftest_packed")
+        return int(n.value)
 
     def enable_kernel_timing(self, on: bool = True) -> None:
         self.check(self.lib.fb_ctx_set_option(self.h, FB_OPT_KERNEL_TIMING, 1 if on else 0), "fb_ctx_set_option")

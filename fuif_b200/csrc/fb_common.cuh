@@ -26,6 +26,15 @@ struct fb_ctx {
     // kernels + forced serial fallback, 3 fused + forced repair of every tile of the last launch, 4 fused
     int *fq_counters = nullptr;
     int fq_mode = 0;
+    // packed unsqueeze kernels (fb_pk_squeeze.cuh): scratch for est / act / bad, arrival counters (kept at zero by the
+    // kernels), [0] repaired segments [1] range-flagged segments; pk_mode: 1 = use them where eligible (default), 0 = off
+    unsigned char *pk_scratch = nullptr;
+    size_t pk_scratch_bytes = 0;
+    int *pk_counters = nullptr;
+    int pk_counters_n = 0;
+    int *pk_stats = nullptr;
+    int pk_mode = 1;
+    int sq_maxval = -1;         // maxval of the image whose Squeeze is being undone (packed kernels: 0 .. 1023 only)
     // FB_KERNEL_TIMING=1: a CUDA event after every launch, dumped by fb_ctx_synchronize (development aid)
     bool timing = false, timing_stderr = false;
     struct Mark { std::string name; cudaEvent_t ev; double bytes; };

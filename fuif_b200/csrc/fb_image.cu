@@ -52,6 +52,9 @@ extern "C" void fb_ctx_destroy(fb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     fb_maniac_release(ctx);
     if (ctx->fq_counters) cudaFree(ctx->fq_counters);
+    if (ctx->pk_scratch) cudaFree(ctx->pk_scratch);
+    if (ctx->pk_counters) cudaFree(ctx->pk_counters);
+    if (ctx->pk_stats) cudaFree(ctx->pk_stats);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -77,11 +80,20 @@ extern "C" long long fb_ctx_launch_count(fb_ctx *ctx) { return ctx ? ctx->launch
 extern "C" int fb_ctx_set_option(fb_ctx *ctx, int option, int value) {
     if (!ctx) return FB_ERR_INVALID;
     if (option == FB_OPT_SQUEEZE_MODE && value >= 0 && value <= 4) { ctx->fq_mode = value; return FB_OK; }
+    if (option == FB_OPT_SQUEEZE_PACKED && value >= 0 && value <= 1) { ctx->pk_mode = value; return FB_OK; }
     if (option == FB_OPT_KERNEL_TIMING) { ctx->timing = value != 0 || ctx->timing_stderr; return FB_OK; }
     return FB_ERR_INVALID;
 }
 
 extern "C" long long fb_ctx_counter(fb_ctx *ctx, int which) {
+    if (ctx && (which == FB_COUNTER_PK_REPAIRED || which == FB_COUNTER_PK_RANGE_FLAGGED)) {
+        if (!ctx->pk_stats) return 0;
+        int v[2] = {0, 0};
+        cudaSetDevice(ctx->device);
+        if (cudaMemcpyAsync(v, ctx->pk_stats, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+        return v[which - FB_COUNTER_PK_REPAIRED];
+    }
     if (!ctx || which < 0 || which > 1) return -1;
     if (!ctx->fq_counters) return 0;
     int v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -295,6 +307,7 @@ static int inv_squeeze(fb_image *img, const std::vector<int> &params, int ep_kin
         if (rc0) return rc0;
     }
     int done = 0;
+    ctx->sq_maxval = img->info.maxval;
     int rc = fb_run_inv_squeeze_plan(ctx, ops, ep.kind ? &ep : nullptr, &done);
     if (ep.rout) {
         if (!rc && done == 2) { to_free.push_back(img->ch[m].dev); img->ch[m].dev = ep.rout; }

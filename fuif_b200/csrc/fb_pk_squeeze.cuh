@@ -1,0 +1,673 @@
+// Packed (int16x2) inverse Squeeze steps for sm_100a: TMA-fed horizontal step with the colour epilogue, coalesced
+// vertical step.  These are the launches that move almost all the bytes of an inverse transform chain.
+//
+// Reference semantics: transform/squeeze.h:61-77 (smooth_tendency), :81-132 (inv_hsqueeze), :173-224 (inv_vsqueeze),
+// transform/ycocg.h:51-56 (inv_YCoCg), image/image.cpp:107-113 (final clamp).
+//
+// Why packed: the unsqueeze recurrence is integer-issue-bound on B200, not HBM-bound (measured, tools/ubench_pipes.cu:
+// LOP3 / SHF / PRMT / VIMNMX* issue every 2 cycles per SM sub-partition on the ALU pipe, VIADD.16x2 / IMAD every 2 cycles
+// on the FMA pipe, a balanced mix ~1.45 cycles per instruction).  sm_100a has native 16x2 add (VIADD.16x2), min / max /
+// min3 / add-min-relu (VIMNMX(3).S16x2, VIADDMNMX.S16x2.RELU): one instruction handles two chains.  A pair step costs ~38
+// instructions for two chains where the 32-bit formulation needs ~28 per chain.
+//
+// Exactness: the 16x2 arithmetic is exact (no wrap inside smooth_tendency) while every average is within +-kMaxAvg and
+// every residual within +-kMaxRes (8- and 10-bit images); the reference's own int16 wraps of diff / A / B are what VIADD.16x2
+// does anyway.  Every loaded word is range-checked on the fly (one VIADDMNMX.U16x2 per word); a segment that saw a value
+// outside the range is flagged and recomputed by the 32-bit routine (h_repair / v_repair), which is exact for all int16.
+//
+// Parallelism: a chain (row / column) is cut into segments that start kWarm pairs early from a guessed state (the
+// recurrence forgets its start within <= 7 pairs in practice).  Every segment records the state it assumed at
+// its first owned pair (est) and its final state (act).  Work items are independent warps; the warp that finishes LAST for
+// a group of chains (atomic counter) walks the segments of those chains in order, and recomputes any segment whose est
+// differs from the true state before it (or that was range-flagged) with the exact routine.  By induction over the segments
+// the output is bit-exact whatever the guesses were.
+//
+//   horizontal (k_pk_hsq): warp = 64 rows x one segment; lane = two rows (l, l+32) packed in the two halves of a word;
+//       planes Co and Cg side by side in one lane (ILP 2).  Input tiles (16 pairs x 64 rows of averages, residuals, Y)
+//       arrive through TMA (cp.async.bulk.tensor.2d + mbarrier, 3-stage ring per warp), output tiles leave through TMA
+//       stores: no address arithmetic, no uncoalesced LSU traffic.  Optional epilogue: inverse YCoCg + final clamp, so the
+//       last launch of a 4096^2 RGB image reads 100 MB and writes 100 MB once.
+//   vertical (k_pk_vsq): lane = 8 adjacent columns (4 packed words, ILP 4), 16-byte coalesced loads / stores straight
+//       from / to HBM with a register prefetch pipeline.
+//
+// Compiled by nvcc (product) and by g++ -DFB_EMULATE (tests/emu: CPU execution-model emulator vs the oracle; TMA and
+// mbarrier are replaced by synchronous copies there).
+#pragma once
+#include "fb_fused_squeeze.cuh"     // fq::unsqueeze_pair (exact 32-bit pair), FB_* macros
+
+#if !defined(FB_EMULATE)
+#include <cuda.h>
+#endif
+
+namespace ps {
+
+constexpr int kMaxAvg = 2047;       // packed arithmetic is exact while |average| <= kMaxAvg and |residual| <= kMaxRes:
+constexpr int kMaxRes = 4095;       // |B| <= 3*kMaxAvg + kMaxRes/2 + 1 = 8189, 4|P-a| + 3|a-n| + 6 <= 53232 < 65536
+constexpr int kHChunk = 16;         // pairs per TMA tile (32-byte rows)
+constexpr int kHRows = 64;          // rows per warp tile
+constexpr int kHStages = 3;
+constexpr int kHWarm = kHChunk;     // warm-up pairs of a horizontal segment (one whole tile, nothing stored)
+constexpr int kVWarm = 8;           // warm-up pairs of a vertical segment
+constexpr int kVDepth = 4;          // rows of register prefetch in the vertical kernel
+constexpr int kMaxHJobs = 8;
+constexpr int kMaxVJobs = 24;
+
+// ---------------------------------------------------------------------------------------------------------
+// 16x2 primitives
+// ---------------------------------------------------------------------------------------------------------
+#if defined(FB_EMULATE)
+inline uint32_t e_h(int lo, int hi) { return (uint32_t)(uint16_t)lo | ((uint32_t)(uint16_t)hi << 16); }
+inline int e_lo(uint32_t w) { return (int)(short)(w & 0xffffu); }
+inline int e_hi(uint32_t w) { return (int)(short)(w >> 16); }
+inline uint32_t __vadd2(uint32_t a, uint32_t b) { return e_h(e_lo(a) + e_lo(b), e_hi(a) + e_hi(b)); }
+inline uint32_t __vmins2(uint32_t a, uint32_t b) { return e_h(std::min(e_lo(a), e_lo(b)), std::min(e_hi(a), e_hi(b))); }
+inline uint32_t __vmaxs2(uint32_t a, uint32_t b) { return e_h(std::max(e_lo(a), e_lo(b)), std::max(e_hi(a), e_hi(b))); }
+inline uint32_t __viaddmin_s16x2_relu(uint32_t a, uint32_t b, uint32_t c) {
+    const int l = std::max(std::min((int)(short)(e_lo(a) + e_lo(b)), e_lo(c)), 0), h = std::max(std::min((int)(short)(e_hi(a) + e_hi(b)), e_hi(c)), 0);
+    return e_h(l, h);
+}
+inline uint32_t __vimin3_s16x2_relu(uint32_t a, uint32_t b, uint32_t c) {
+    return e_h(std::max(std::min(std::min(e_lo(a), e_lo(b)), e_lo(c)), 0), std::max(std::min(std::min(e_hi(a), e_hi(b)), e_hi(c)), 0));
+}
+inline uint32_t __viaddmax_u16x2(uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t l = std::max((uint32_t)(uint16_t)((a & 0xffff) + (b & 0xffff)), c & 0xffff), h = std::max((uint32_t)(uint16_t)((a >> 16) + (b >> 16)), c >> 16);
+    return l | (h << 16);
+}
+inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+    const uint64_t v = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        const uint32_t sel = (s >> (4 * i)) & 0xf;
+        const uint32_t b = (uint32_t)(v >> (8 * (sel & 7))) & 0xff;      // the CUDA intrinsic ignores bit 3 of a selector nibble
+        r |= b << (8 * i);
+    }
+    return r;
+}
+#endif
+
+FB_DEV uint32_t padd(uint32_t a, uint32_t b) { return __vadd2(a, b); }                  // VIADD.16x2 (wraps per half)
+FB_DEV uint32_t pneg(uint32_t a) { return __vadd2(~a, 0x00010001u); }
+// 0xffff where the half is negative: PRMT with the sign-replicate bit of the selector nibbles, which only PTX exposes
+// (__byte_perm masks the selector to 3 bits per nibble)
+#if defined(FB_EMULATE)
+inline uint32_t psign(uint32_t a) { return ((a & 0x8000u) ? 0xffffu : 0u) | ((a & 0x80000000u) ? 0xffff0000u : 0u); }
+#else
+FB_DEV uint32_t psign(uint32_t a) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0, 0xbb99;" : "=r"(r) : "r"(a));
+    return r;
+}
+#endif
+FB_DEV uint32_t pasr1(uint32_t a) { return ((a >> 1) & 0x7fff7fffu) | (a & 0x80008000u); }     // arithmetic >> 1 per half
+FB_DEV uint32_t plo(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5410); }       // (a.lo, b.lo)
+FB_DEV uint32_t phi(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }       // (a.hi, b.hi)
+
+// floor(t / 12) per unsigned half: (t * 43691) >> 19 is exact for t < 2^16 (43691 * 12 = 2^19 + 4)
+FB_DEV uint32_t pdiv12(uint32_t t) {
+    const uint32_t ql = ((t & 0xffffu) * 43691u) >> 19, qh = ((t >> 16) * 43691u) >> 19;
+    return ql | (qh << 16);
+}
+
+// One unsqueeze pair on two chains at once (squeeze.h:97-108 with smooth_tendency :61-77 in the closed form of
+// fq::unsqueeze_pair).  P = previous reconstructed B, a = average, nega = -a, negn = -(next average), r = residual.
+// With sigma = sign(P - n): a monotone triple has sigma*(P-a) >= 0 and sigma*(a-n) >= 0 and
+//   tendency = sigma * min((4 s(P-a) + 3 s(a-n) + 6) / 12, 2 s(P-a) + 1, 2 s(a-n));
+// otherwise one of 2 s(P-a) + 1, 2 s(a-n) is negative and the RELU of the min gives the reference's 0.
+FB_DEV void pk_step(uint32_t P, uint32_t a, uint32_t nega, uint32_t negn, uint32_t r, uint32_t &A, uint32_t &B) {
+    const uint32_t t1 = padd(P, nega), t2 = padd(a, negn), u = padd(P, negn);
+    const uint32_t s = psign(u), s1 = s & 0x00010001u;
+    const uint32_t a1 = padd(t1 ^ s, s1), a2 = padd(t2 ^ s, s1);
+    const uint32_t m1 = padd(a1, a1), m2 = padd(a2, a2);
+    const uint32_t t = padd(padd(padd(m1, m1), padd(m2, a2)), 0x00060006u);
+    const uint32_t q = pdiv12(t);
+    const uint32_t d = __viaddmin_s16x2_relu(m1, 0x00010001u, __vmins2(q, m2));
+    const uint32_t diff = padd(r, padd(d ^ s, s1));
+    const uint32_t dd = padd(diff, (diff >> 15) & 0x00010001u);      // + 1 where negative: >> 1 then truncates toward zero
+    A = padd(a, pasr1(dd));
+    B = padd(padd(A, ~diff), 0x00010001u);
+}
+
+// inverse YCoCg on two pixels at once (ycocg.h:51-56): G = clamp(Y + ((Cg+1)>>1)), B = clamp(Y - (Cg>>1) - (Co>>1)), R = clamp(Co + B),
+// all clamps to [0, maxval]; exact while |Co|, |Cg| <= 8189 (outputs of a range-checked step) and maxval >= 0
+FB_DEV void pk_ycocg(uint32_t y, uint32_t co, uint32_t cg, uint32_t mv, uint32_t &R, uint32_t &G, uint32_t &B) {
+    const uint32_t yc = __vimin3_s16x2_relu(y, mv, mv);
+    G = __viaddmin_s16x2_relu(yc, pasr1(padd(cg, 0x00010001u)), mv);
+    const uint32_t nsum = padd(padd(pasr1(~cg), pasr1(~co)), 0x00020002u);       // -(cg>>1) - (co>>1): ~(x>>1) = -(x>>1) - 1
+    B = __viaddmin_s16x2_relu(yc, nsum, mv);
+    R = __viaddmin_s16x2_relu(co, B, mv);
+}
+FB_DEV uint32_t pk_clamp(uint32_t x, uint32_t lo, uint32_t hi) { return __vmins2(__vmaxs2(x, lo), hi); }
+
+// range accumulators: every half of `acc` stays <= 2*bound while all checked values are within +-bound
+FB_DEV uint32_t pk_chk(uint32_t acc, uint32_t w, uint32_t bound2) { return __viaddmax_u16x2(w, bound2, acc); }
+FB_DEV bool pk_chk_bad(uint32_t acc, int bound) { return (int)(acc & 0xffffu) > 2 * bound || (int)(acc >> 16) > 2 * bound; }
+
+// ---------------------------------------------------------------------------------------------------------
+// tile movement: TMA + mbarrier on the GPU, synchronous copies under the emulator
+// ---------------------------------------------------------------------------------------------------------
+#if defined(FB_EMULATE)
+struct TileMap { int16_t *base; int w, h, box_w, box_h; };
+inline void fb_syncwarp() { cuemu::bar_sync(1 + (int)(threadIdx.x >> 5), 32); }
+inline void fb_threadfence() {}
+inline void tile_load(void *dst, const TileMap *m, int x, int y, uint64_t *, int) {
+    int16_t *d = (int16_t *)dst;
+    for (int r = 0; r < m->box_h; r++)
+        for (int c = 0; c < m->box_w; c++) {
+            const int gx = x + c, gy = y + r;
+            d[r * m->box_w + c] = (gx >= 0 && gx < m->w && gy >= 0 && gy < m->h) ? m->base[(size_t)gy * m->w + gx] : (int16_t)0;
+        }
+}
+inline void tile_store(const TileMap *m, int x, int y, const void *src) {
+    const int16_t *s = (const int16_t *)src;
+    for (int r = 0; r < m->box_h; r++)
+        for (int c = 0; c < m->box_w; c++) {
+            const int gx = x + c, gy = y + r;
+            if (gx >= 0 && gx < m->w && gy >= 0 && gy < m->h) m->base[(size_t)gy * m->w + gx] = s[r * m->box_w + c];
+        }
+}
+inline void mbar_init(uint64_t *, int) {}
+inline void mbar_expect(uint64_t *, int) {}
+inline void mbar_wait(uint64_t *, int) {}
+inline void fence_async_smem() {}
+inline void store_commit() {}
+inline void store_wait_read() {}
+inline void store_wait_all() {}
+inline void fence_mbar_init() {}
+#else
+typedef CUtensorMap TileMap;
+FB_DEV void fb_syncwarp() { __syncwarp(); }
+FB_DEV void fb_threadfence() { __threadfence(); }
+FB_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+FB_DEV void mbar_init(uint64_t *bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+FB_DEV void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+FB_DEV void mbar_expect(uint64_t *bar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+FB_DEV void mbar_wait(uint64_t *bar, int parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one 2-D tile global -> shared; out-of-range elements arrive as zero; completion is counted in bytes on `bar`
+FB_DEV void tile_load(void *dst, const TileMap *m, int x, int y, uint64_t *bar, int) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+                 "l"(m), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
+// one 2-D tile shared -> global (clipped at the plane border), bulk-group completion
+FB_DEV void tile_store(const TileMap *m, int x, int y, const void *src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(m), "r"(x), "r"(y), "r"(smem_u32(src)) : "memory");
+}
+FB_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+FB_DEV void store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+FB_DEV void store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+FB_DEV void store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+#endif
+
+// value of lane 0 for the whole warp
+#if defined(FB_EMULATE)
+inline int warp_bcast0(int v, int lane) {
+    static int slot[64];
+    const int w = (int)(threadIdx.x >> 5);
+    fb_syncwarp();
+    if (lane == 0) slot[w] = v;
+    fb_syncwarp();
+    return slot[w];
+}
+#else
+FB_DEV int warp_bcast0(int v, int) { return __shfl_sync(0xffffffffu, v, 0); }
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
+// horizontal step
+// ---------------------------------------------------------------------------------------------------------
+struct HJob {                   // one horizontal step on np planes of identical geometry
+    TileMap tm_a[2], tm_r[2];   // averages / residuals: wa x h, box kHChunk x kHRows
+    TileMap tm_o[3];            // outputs 2*wa x h, box 2*kHChunk x kHRows: planes [0..np), or R, G, B with the YCoCg epilogue
+    TileMap tm_y;               // epilogue: the final Y plane
+    const int16_t *avg[2], *res[2];     // the same planes for the exact repair routine
+    int16_t *out[3];
+    const int16_t *yin;
+    int16_t *est[2], *act[2];   // [nseg][h] per plane: state assumed at the first owned pair / final state of the segment
+    unsigned char *bad;         // [nseg][h]: segment saw a value outside the packed range (or is otherwise to be recomputed)
+    int *counter;               // [nrb] arrivals per row block (left at zero by the last arriver)
+    int *stats;                 // [0] repaired segments, [1] range-flagged segments (diagnostics)
+    int np, wa, h;
+    int S, nseg, nrb;           // pairs per segment (multiple of kHChunk), segments per row, row blocks of kHRows
+    int item0;                  // first work item of this job
+    int epilogue;               // fq::kEpNone / kEpClamp / kEpYCoCg
+    int maxval, lo, hi, do_clamp;
+};
+struct HJobs { HJob j[kMaxHJobs]; int n, items; };
+
+FB_HD size_t h_smem_per_warp(int np, int epilogue) {
+    const size_t in = (size_t)np * 2 * kHRows * kHChunk * 2 + (epilogue == fq::kEpYCoCg ? (size_t)kHRows * 2 * kHChunk * 2 : 0);
+    const size_t nout = epilogue == fq::kEpYCoCg ? 3 : np;
+    return kHStages * in + nout * kHRows * 2 * kHChunk * 2 + 128;     // + mbarriers (slices stay 128-byte aligned)
+}
+
+// exact inverse YCoCg + final clamp of one pixel
+FB_DEV void ycocg_exact(int Yr, int Co, int Cg, int maxval, int lo, int hi, int do_clamp, int &R, int &G, int &B) {
+    const int Y = fq::clampi(Yr, 0, maxval);
+    G = fq::clampi(Y - ((-Cg) >> 1), 0, maxval);
+    B = fq::clampi(Y + ((1 - Cg) >> 1) - (Co >> 1), 0, maxval);
+    R = fq::clampi(Co + B, 0, maxval);
+    if (do_clamp) { R = fq::clampi(R, lo, hi); G = fq::clampi(G, lo, hi); B = fq::clampi(B, lo, hi); }
+}
+
+// Exact recomputation of segment g of one row from the true state before it (prev[]); plain global accesses.
+FB_DEV void h_repair(const HJob &J, int row, int g, int *prev) {
+    const int x0 = g * J.S, x1 = fq::imin(x0 + J.S, J.wa), wo = 2 * J.wa;
+    for (int x = x0; x < x1; x++) {
+        int A[2], B[2];
+        for (int p = 0; p < J.np; p++) {
+            const int16_t *ar = J.avg[p] + (size_t)row * J.wa;
+            const int av = ar[x], nx = x + 1 < J.wa ? ar[x + 1] : av, rs = J.res[p][(size_t)row * J.wa + x];
+            fq::unsqueeze_pair(x == 0 ? av : prev[p], av, nx, rs, A[p], B[p]);
+            prev[p] = B[p];
+        }
+        const size_t o = (size_t)row * wo + 2 * x;
+        if (J.epilogue == fq::kEpYCoCg) {
+            for (int k = 0; k < 2; k++) {
+                int R, G, Bl;
+                ycocg_exact(J.yin[o + k], k ? B[0] : A[0], k ? B[1] : A[1], J.maxval, J.lo, J.hi, J.do_clamp, R, G, Bl);
+                J.out[0][o + k] = (int16_t)R; J.out[1][o + k] = (int16_t)G; J.out[2][o + k] = (int16_t)Bl;
+            }
+        } else {
+            for (int p = 0; p < J.np; p++) {
+                if (J.epilogue == fq::kEpClamp && J.do_clamp) { A[p] = fq::clampi(A[p], J.lo, J.hi); B[p] = fq::clampi(B[p], J.lo, J.hi); }
+                J.out[p][o] = (int16_t)A[p]; J.out[p][o + 1] = (int16_t)B[p];
+            }
+        }
+    }
+}
+
+// the last arriver of a row block: walk the segments of every row in order, repair what does not join
+FB_DEV void h_verify(const HJob &J, int rb, int lane) {
+    for (int half = 0; half < 2; half++) {
+        const int row = rb * kHRows + lane + 32 * half;
+        if (row >= J.h) continue;
+        int cur[2] = {0, 0};
+        for (int g = 0; g < J.nseg; g++) {
+            const size_t e = (size_t)g * J.h + row;
+            bool need = J.bad[e] != 0;
+            if (g > 0)
+                for (int p = 0; p < J.np; p++) need = need || (J.est[p][e] != (int16_t)cur[p]);
+            if (need) {
+                h_repair(J, row, g, cur);
+                for (int p = 0; p < J.np; p++) J.act[p][e] = (int16_t)cur[p];
+                atomicAdd(J.stats, 1);
+            } else {
+                for (int p = 0; p < J.np; p++) cur[p] = J.act[p][e];
+            }
+        }
+    }
+}
+
+// One work item: rows [64 rb, 64 rb + 64) x segment g of job J, by one warp.  sm = this warp's shared memory.
+template <int NP, int EP>
+FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane, int &par) {
+    constexpr bool kCol = EP == fq::kEpYCoCg;
+    constexpr int kTileA = kHRows * kHChunk * 2;                // bytes of an average / residual tile
+    constexpr int kTileO = kHRows * 2 * kHChunk * 2;            // bytes of an output / Y tile
+    constexpr int kStage = NP * 2 * kTileA + (kCol ? kTileO : 0);
+    constexpr int kNOut = kCol ? 3 : NP;
+    unsigned char *sm_out = sm + kHStages * kStage;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm_out + kNOut * kTileO);
+    const int wa = J.wa, row0 = rb * kHRows;
+    const int x_own = g * J.S, x_end = fq::imin(x_own + J.S, wa);
+    const int x_first = g ? x_own - kHWarm : 0;
+    const int nchunks = (x_end - x_first + kHChunk - 1) / kHChunk;
+
+    auto issue = [&](int c) {       // lane 0: loads of chunk c into its ring slot
+        const int st = c % kHStages, xc = x_first + c * kHChunk;
+        unsigned char *base = sm + st * kStage;
+        const bool with_y = kCol && !(g && c == 0);
+        mbar_expect(&bars[st], NP * 2 * kTileA + (with_y ? kTileO : 0));
+        for (int p = 0; p < NP; p++) {
+            tile_load(base + p * 2 * kTileA, &J.tm_a[p], xc, row0, &bars[st], 0);
+            tile_load(base + p * 2 * kTileA + kTileA, &J.tm_r[p], xc, row0, &bars[st], 0);
+        }
+        if (with_y) tile_load(base + NP * 2 * kTileA, &J.tm_y, 2 * xc, row0, &bars[st], 0);
+    };
+    if (lane == 0)
+        for (int c = 0; c < kHStages - 1 && c < nchunks; c++) issue(c);
+
+    uint32_t P[NP], a_end[NP], chk_a = 0, chk_r = 0;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {      // the average right after the segment (the last owned pair's "next"): one direct load per row
+        a_end[p] = 0;
+        if (x_end < wa) {
+            const int rA = fq::imin(row0 + lane, J.h - 1), rB = fq::imin(row0 + lane + 32, J.h - 1);
+            a_end[p] = (uint32_t)(uint16_t)J.avg[p][(size_t)rA * wa + x_end] | ((uint32_t)(uint16_t)J.avg[p][(size_t)rB * wa + x_end] << 16);
+            chk_a = pk_chk(chk_a, a_end[p], kMaxAvg * 0x00010001u);
+        }
+    }
+    const bool do_clamp = J.do_clamp != 0;
+    const uint32_t mv = (uint32_t)(uint16_t)J.maxval * 0x00010001u, clo = (uint32_t)(uint16_t)J.lo * 0x00010001u, chi = (uint32_t)(uint16_t)J.hi * 0x00010001u;
+    // par: bit st = parity the next wait on ring slot st must see (persists across the items of this warp)
+    for (int c = 0; c < nchunks; c++) {
+        const int st = c % kHStages, xc = x_first + c * kHChunk;
+        fb_syncwarp();                                          // every lane is done with chunk c-1: its slot may be refilled
+        if (lane == 0 && c + kHStages - 1 < nchunks) issue(c + kHStages - 1);
+        mbar_wait(&bars[st], (par >> st) & 1);
+        par ^= 1 << st;
+        const bool have_next = c + 1 < nchunks;
+        if (have_next) mbar_wait(&bars[(c + 1) % kHStages], (par >> ((c + 1) % kHStages)) & 1);      // its first average is this chunk's last "next"
+        const unsigned char *base = sm + st * kStage, *nbase = sm + ((c + 1) % kHStages) * kStage;
+        const bool warm = g && c == 0;
+        const int nsteps = fq::imin(kHChunk, x_end - xc);
+        if (c == 0) {
+#pragma unroll
+            for (int p = 0; p < NP; p++) {       // chain start: "left" = own average (squeeze.h:84-89); a segment start guesses the same
+                const uint32_t wA = *reinterpret_cast<const uint32_t *>(base + p * 2 * kTileA + lane * (kHChunk * 2));
+                const uint32_t wB = *reinterpret_cast<const uint32_t *>(base + p * 2 * kTileA + (lane + 32) * (kHChunk * 2));
+                P[p] = plo(wA, wB);
+            }
+        }
+        if (c == 1 && g) {          // first owned pair: remember the state the warm-up reached
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                if (row0 + lane < J.h) J.est[p][(size_t)g * J.h + row0 + lane] = (int16_t)(P[p] & 0xffffu);
+                if (row0 + lane + 32 < J.h) J.est[p][(size_t)g * J.h + row0 + lane + 32] = (int16_t)(P[p] >> 16);
+            }
+        }
+        if (!warm) {
+            if (lane == 0) store_wait_read();                   // the previous output tile has left shared memory
+            fb_syncwarp();
+        }
+        // half a tile (8 pairs) at a time, fully unrolled: 16-byte shared loads, everything else in registers
+        for (int hf = 0; hf < 2 && 8 * hf < nsteps; hf++) {
+            const int xh = xc + 8 * hf;
+            uint32_t aw[NP][2][4], rw[NP][2][4], a_last[NP];
+            // what the last pair of this half sees as its next average: own (row end, squeeze.h:93), the average after the
+            // segment (direct load above), or the next word in shared memory
+            const bool own_last = xh + 8 >= wa;
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                const unsigned char *ta = base + p * 2 * kTileA, *tr = ta + kTileA;
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const uint4 va = *reinterpret_cast<const uint4 *>(ta + (lane + 32 * r) * (kHChunk * 2) + 16 * hf);
+                    const uint4 vr = *reinterpret_cast<const uint4 *>(tr + (lane + 32 * r) * (kHChunk * 2) + 16 * hf);
+                    aw[p][r][0] = va.x; aw[p][r][1] = va.y; aw[p][r][2] = va.z; aw[p][r][3] = va.w;
+                    rw[p][r][0] = vr.x; rw[p][r][1] = vr.y; rw[p][r][2] = vr.z; rw[p][r][3] = vr.w;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        chk_a = pk_chk(chk_a, aw[p][r][i], kMaxAvg * 0x00010001u);
+                        chk_r = pk_chk(chk_r, rw[p][r][i], kMaxRes * 0x00010001u);
+                    }
+                }
+                if (hf == 0) {
+                    a_last[p] = plo(*reinterpret_cast<const uint32_t *>(ta + lane * (kHChunk * 2) + 16),
+                                    *reinterpret_cast<const uint32_t *>(ta + (lane + 32) * (kHChunk * 2) + 16));
+                } else if (have_next) {
+                    const unsigned char *na = nbase + p * 2 * kTileA;
+                    a_last[p] = plo(*reinterpret_cast<const uint32_t *>(na + lane * (kHChunk * 2)), *reinterpret_cast<const uint32_t *>(na + (lane + 32) * (kHChunk * 2)));
+                } else {
+                    a_last[p] = a_end[p];
+                }
+            }
+            uint32_t yw[2][8];
+            if (kCol && !warm) {
+                const unsigned char *ty = base + NP * 2 * kTileA;
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const uint4 y0 = *reinterpret_cast<const uint4 *>(ty + (lane + 32 * r) * (4 * kHChunk) + 32 * hf);
+                    const uint4 y1 = *reinterpret_cast<const uint4 *>(ty + (lane + 32 * r) * (4 * kHChunk) + 32 * hf + 16);
+                    yw[r][0] = y0.x; yw[r][1] = y0.y; yw[r][2] = y0.z; yw[r][3] = y0.w; yw[r][4] = y1.x; yw[r][5] = y1.y; yw[r][6] = y1.z; yw[r][7] = y1.w;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {                       // two pairs per iteration: one word of averages per row
+                uint32_t oA[NP][2], oB[NP][2];                  // [plane][pair]: packed (row l, row l+32)
+#pragma unroll
+                for (int p = 0; p < NP; p++) {
+                    const uint32_t a0 = plo(aw[p][0][k], aw[p][1][k]), a1 = phi(aw[p][0][k], aw[p][1][k]);
+                    uint32_t a2;
+                    if (k < 3) a2 = plo(aw[p][0][k + 1], aw[p][1][k + 1]);
+                    else a2 = own_last ? a1 : a_last[p];
+                    const uint32_t r0 = plo(rw[p][0][k], rw[p][1][k]), r1 = phi(rw[p][0][k], rw[p][1][k]);
+                    const uint32_t n1 = pneg(a1);
+                    pk_step(P[p], a0, pneg(a0), n1, r0, oA[p][0], oB[p][0]);
+                    pk_step(oB[p][0], a1, n1, pneg(a2), r1, oA[p][1], oB[p][1]);
+                    P[p] = oB[p][1];
+                }
+                if (!warm) {
+                    const int ob = 32 * hf + 8 * k;             // byte offset of output columns 4k .. 4k+3 of this half in a 64-byte output row
+                    if (kCol) {
+                        uint32_t R[4], G[4], Bc[4];
+                        const uint32_t y4[4] = {plo(yw[0][2 * k], yw[1][2 * k]), phi(yw[0][2 * k], yw[1][2 * k]), plo(yw[0][2 * k + 1], yw[1][2 * k + 1]),
+                                                phi(yw[0][2 * k + 1], yw[1][2 * k + 1])};
+                        const uint32_t co4[4] = {oA[0][0], oB[0][0], oA[0][1], oB[0][1]}, cg4[4] = {oA[NP - 1][0], oB[NP - 1][0], oA[NP - 1][1], oB[NP - 1][1]};
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            pk_ycocg(y4[i], co4[i], cg4[i], mv, R[i], G[i], Bc[i]);
+                            if (do_clamp) { R[i] = pk_clamp(R[i], clo, chi); G[i] = pk_clamp(G[i], clo, chi); Bc[i] = pk_clamp(Bc[i], clo, chi); }
+                        }
+                        uint2 v;
+                        v.x = plo(R[0], R[1]); v.y = plo(R[2], R[3]); *reinterpret_cast<uint2 *>(sm_out + lane * (4 * kHChunk) + ob) = v;
+                        v.x = phi(R[0], R[1]); v.y = phi(R[2], R[3]); *reinterpret_cast<uint2 *>(sm_out + (lane + 32) * (4 * kHChunk) + ob) = v;
+                        v.x = plo(G[0], G[1]); v.y = plo(G[2], G[3]); *reinterpret_cast<uint2 *>(sm_out + kTileO + lane * (4 * kHChunk) + ob) = v;
+                        v.x = phi(G[0], G[1]); v.y = phi(G[2], G[3]); *reinterpret_cast<uint2 *>(sm_out + kTileO + (lane + 32) * (4 * kHChunk) + ob) = v;
+                        v.x = plo(Bc[0], Bc[1]); v.y = plo(Bc[2], Bc[3]); *reinterpret_cast<uint2 *>(sm_out + 2 * kTileO + lane * (4 * kHChunk) + ob) = v;
+                        v.x = phi(Bc[0], Bc[1]); v.y = phi(Bc[2], Bc[3]); *reinterpret_cast<uint2 *>(sm_out + 2 * kTileO + (lane + 32) * (4 * kHChunk) + ob) = v;
+                    } else {
+#pragma unroll
+                        for (int p = 0; p < NP; p++) {
+                            uint32_t o4[4] = {oA[p][0], oB[p][0], oA[p][1], oB[p][1]};
+                            if (EP == fq::kEpClamp && do_clamp) {
+#pragma unroll
+                                for (int i = 0; i < 4; i++) o4[i] = pk_clamp(o4[i], clo, chi);
+                            }
+                            uint2 v;
+                            v.x = plo(o4[0], o4[1]); v.y = plo(o4[2], o4[3]); *reinterpret_cast<uint2 *>(sm_out + p * kTileO + lane * (4 * kHChunk) + ob) = v;
+                            v.x = phi(o4[0], o4[1]); v.y = phi(o4[2], o4[3]); *reinterpret_cast<uint2 *>(sm_out + p * kTileO + (lane + 32) * (4 * kHChunk) + ob) = v;
+                        }
+                    }
+                }
+            }
+        }
+        if (!warm) {
+            fence_async_smem();
+            fb_syncwarp();
+            if (lane == 0) {
+                for (int p = 0; p < kNOut; p++) tile_store(&J.tm_o[p], 2 * xc, row0, sm_out + p * kTileO);
+                store_commit();
+            }
+        }
+    }
+    // final state + range flag of this segment
+    const bool bad = pk_chk_bad(chk_a, kMaxAvg) || pk_chk_bad(chk_r, kMaxRes);
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        if (row0 + lane < J.h) J.act[p][(size_t)g * J.h + row0 + lane] = (int16_t)(P[p] & 0xffffu);
+        if (row0 + lane + 32 < J.h) J.act[p][(size_t)g * J.h + row0 + lane + 32] = (int16_t)(P[p] >> 16);
+    }
+    if (row0 + lane < J.h) J.bad[(size_t)g * J.h + row0 + lane] = bad ? 1 : 0;
+    if (row0 + lane + 32 < J.h) J.bad[(size_t)g * J.h + row0 + lane + 32] = bad ? 1 : 0;
+    if (bad) atomicAdd(J.stats + 1, 1);
+    if (lane == 0) store_wait_all();                            // this segment's tiles are in global memory
+    fb_threadfence();
+    fb_syncwarp();
+    int last = 0;
+    if (lane == 0) {
+        const int seen = atomicAdd(J.counter + rb, 1);
+        last = seen == J.nseg - 1;
+        if (last) J.counter[rb] = 0;                            // ready for the next launch
+    }
+    last = warp_bcast0(last, lane);
+    if (last) {
+        fb_threadfence();
+        h_verify(J, rb, lane);
+    }
+}
+
+// All jobs of a launch have the same (NP, EP).  A warp's slice of shared memory: kHStages input stages, the output tiles, the mbarriers.
+template <int NP, int EP>
+FB_KERNEL(384) k_pk_hsq(const FB_GRID_CONSTANT HJobs jobs, int warps_per_block, int smem_per_warp) {
+    FB_DYN_SMEM(smraw);
+    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+    unsigned char *sm = smraw + ((128 - (int)(reinterpret_cast<uintptr_t>(smraw) & 127)) & 127) + (size_t)warp * smem_per_warp;
+    const int item = (int)blockIdx.x * warps_per_block + warp;
+    if (item >= jobs.items) return;
+    int ji = 0;
+    while (ji < jobs.n - 1 && item >= jobs.j[ji + 1].item0) ji++;
+    const HJob &J = jobs.j[ji];
+    const int local = item - J.item0, rb = local / J.nseg, g = local - rb * J.nseg;
+    constexpr int kStage = NP * 2 * kHRows * kHChunk * 2 + (EP == fq::kEpYCoCg ? kHRows * 2 * kHChunk * 2 : 0);
+    constexpr int kNOut = EP == fq::kEpYCoCg ? 3 : NP;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + kHStages * kStage + kNOut * kHRows * 2 * kHChunk * 2);
+    if (lane == 0) {
+        for (int s = 0; s < kHStages; s++) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    fb_syncwarp();
+    int par = 0;
+    h_item<NP, EP>(J, rb, g, sm, lane, par);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// vertical step
+// ---------------------------------------------------------------------------------------------------------
+struct VJob {                   // one vertical step on one plane
+    const int16_t *avg, *res;
+    int16_t *out;
+    int16_t *est, *act;         // [nseg][w]
+    unsigned char *bad;         // [nseg][w / 8]
+    int *counter;               // [ncg] arrivals per group of 256 columns
+    int *stats;
+    int w, ha;                  // averages w x ha, residuals w x ha, output w x 2*ha;  w % 8 == 0
+    int S, nseg, ncg;           // pairs per segment, segments per column, column groups of 256
+    int item0;
+    int do_clamp, lo, hi;
+};
+struct VJobs { VJob j[kMaxVJobs]; int n, items; };
+
+FB_DEV uint4 ld16(const int16_t *p) { return *reinterpret_cast<const uint4 *>(p); }
+FB_DEV void st16(int16_t *p, const uint4 &v) { *reinterpret_cast<uint4 *>(p) = v; }
+
+// exact recomputation of segment g of the 8 columns at x from the true state before it
+FB_DEV void v_repair(const VJob &J, int x, int g, int *prev) {
+    const int q0 = g * J.S, q1 = fq::imin(q0 + J.S, J.ha);
+    for (int q = q0; q < q1; q++)
+        for (int k = 0; k < 8; k++) {
+            const int av = J.avg[(size_t)q * J.w + x + k], nx = q + 1 < J.ha ? J.avg[(size_t)(q + 1) * J.w + x + k] : av;
+            int A, B;
+            fq::unsqueeze_pair(q == 0 ? av : prev[k], av, nx, J.res[(size_t)q * J.w + x + k], A, B);
+            prev[k] = B;
+            if (J.do_clamp) { A = fq::clampi(A, J.lo, J.hi); B = fq::clampi(B, J.lo, J.hi); }
+            J.out[(size_t)(2 * q) * J.w + x + k] = (int16_t)A;
+            J.out[(size_t)(2 * q + 1) * J.w + x + k] = (int16_t)B;
+        }
+}
+
+FB_DEV void v_verify(const VJob &J, int x) {
+    int cur[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int g = 0; g < J.nseg; g++) {
+        bool need = J.bad[(size_t)g * (J.w >> 3) + (x >> 3)] != 0;
+        if (g > 0)
+            for (int k = 0; k < 8; k++) need = need || (J.est[(size_t)g * J.w + x + k] != (int16_t)cur[k]);
+        if (need) {
+            v_repair(J, x, g, cur);
+            for (int k = 0; k < 8; k++) J.act[(size_t)g * J.w + x + k] = (int16_t)cur[k];
+            atomicAdd(J.stats, 1);
+        } else {
+            for (int k = 0; k < 8; k++) cur[k] = J.act[(size_t)g * J.w + x + k];
+        }
+    }
+}
+
+FB_DEV void v_item(const VJob &J, int cg, int g, int lane) {
+    const int x = (cg * 32 + lane) * 8, w = J.w, last_row = J.ha - 1;
+    const bool active = x < w;
+    const int q_own = g * J.S, q_end = fq::imin(q_own + J.S, J.ha);
+    const int q_first = g ? q_own - kVWarm : 0;
+    const uint32_t clo = (uint32_t)(uint16_t)J.lo * 0x00010001u, chi = (uint32_t)(uint16_t)J.hi * 0x00010001u;
+    if (active) {
+        uint32_t P[4], chk_a = 0, chk_r = 0;
+        uint4 A[kVDepth + 1], R[kVDepth];
+#pragma unroll
+        for (int i = 0; i <= kVDepth; i++) A[i] = ld16(J.avg + (size_t)fq::imin(q_first + i, last_row) * w + x);
+#pragma unroll
+        for (int i = 0; i < kVDepth; i++) R[i] = ld16(J.res + (size_t)fq::imin(q_first + i, last_row) * w + x);
+        P[0] = A[0].x; P[1] = A[0].y; P[2] = A[0].z; P[3] = A[0].w;         // chain start: "top" = own average; a segment start guesses the same
+        for (int q0 = q_first; q0 < q_end; q0 += kVDepth) {
+            uint4 An[kVDepth], Rn[kVDepth];
+#pragma unroll
+            for (int i = 0; i < kVDepth; i++) {             // rows of the next round (clamped into the plane: unused rows are harmless)
+                An[i] = ld16(J.avg + (size_t)fq::imin(q0 + kVDepth + 1 + i, last_row) * w + x);
+                Rn[i] = ld16(J.res + (size_t)fq::imin(q0 + kVDepth + i, last_row) * w + x);
+            }
+#pragma unroll
+            for (int i = 0; i < kVDepth; i++) {
+                const int q = q0 + i;
+                if (q < q_end) {
+                    if (q == q_own && g) {
+                        uint4 e; e.x = P[0]; e.y = P[1]; e.z = P[2]; e.w = P[3];
+                        st16(J.est + (size_t)g * w + x, e);
+                    }
+                    // last pair of the column: next average = own (squeeze.h:201); A[i+1] is then a clamped re-read of row ha-1 = A[i]
+                    const uint32_t aw[4] = {A[i].x, A[i].y, A[i].z, A[i].w}, nw[4] = {A[i + 1].x, A[i + 1].y, A[i + 1].z, A[i + 1].w};
+                    const uint32_t rw[4] = {R[i].x, R[i].y, R[i].z, R[i].w};
+                    uint32_t oa[4], ob[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        chk_a = pk_chk(chk_a, aw[k], kMaxAvg * 0x00010001u);
+                        if (q == q_end - 1) chk_a = pk_chk(chk_a, nw[k], kMaxAvg * 0x00010001u);     // a row the next segment owns
+                        chk_r = pk_chk(chk_r, rw[k], kMaxRes * 0x00010001u);
+                        pk_step(P[k], aw[k], pneg(aw[k]), pneg(nw[k]), rw[k], oa[k], ob[k]);
+                        P[k] = ob[k];
+                        if (J.do_clamp) { oa[k] = pk_clamp(oa[k], clo, chi); ob[k] = pk_clamp(ob[k], clo, chi); }
+                    }
+                    if (q >= q_own) {
+                        uint4 v;
+                        v.x = oa[0]; v.y = oa[1]; v.z = oa[2]; v.w = oa[3]; st16(J.out + (size_t)(2 * q) * w + x, v);
+                        v.x = ob[0]; v.y = ob[1]; v.z = ob[2]; v.w = ob[3]; st16(J.out + (size_t)(2 * q + 1) * w + x, v);
+                    }
+                }
+            }
+            A[0] = A[kVDepth];
+#pragma unroll
+            for (int i = 0; i < kVDepth; i++) { A[i + 1] = An[i]; R[i] = Rn[i]; }
+        }
+        const bool bad = pk_chk_bad(chk_a, kMaxAvg) || pk_chk_bad(chk_r, kMaxRes);
+        uint4 e; e.x = P[0]; e.y = P[1]; e.z = P[2]; e.w = P[3];
+        st16(J.act + (size_t)g * w + x, e);
+        J.bad[(size_t)g * (w >> 3) + (x >> 3)] = bad ? 1 : 0;
+        if (bad) atomicAdd(J.stats + 1, 1);
+    }
+    fb_threadfence();
+    fb_syncwarp();
+    int last = 0;
+    if (lane == 0) {
+        const int seen = atomicAdd(J.counter + cg, 1);
+        last = seen == J.nseg - 1;
+        if (last) J.counter[cg] = 0;
+    }
+    last = warp_bcast0(last, lane);
+    if (last && active) {
+        fb_threadfence();
+        v_verify(J, x);
+    }
+}
+
+FB_KERNEL(256) k_pk_vsq(const FB_GRID_CONSTANT VJobs jobs, int warps_per_block) {
+    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+    const int item = (int)blockIdx.x * warps_per_block + warp;
+    if (item >= jobs.items) return;
+    int ji = 0;
+    while (ji < jobs.n - 1 && item >= jobs.j[ji + 1].item0) ji++;
+    const VJob &J = jobs.j[ji];
+    // consecutive items = consecutive column groups of the same segment (neighbouring warps touch neighbouring lines)
+    const int local = item - J.item0, g = local / J.ncg, cg = local - g * J.ncg;
+    v_item(J, cg, g, lane);
+}
+
+}  // namespace ps

@@ -7,6 +7,8 @@
 #include "fb_common.cuh"
 #include "fb_fused_plan.h"
 #include "fb_direct_plan.h"
+#include <type_traits>
+#include "fb_pk_plan.h"
 #include "fb_subsample.cuh"
 #include "fb_approx.cuh"
 #include "fb_palette.cuh"
@@ -839,6 +841,176 @@ int fb_launch_inv_squeeze_batch(fb_ctx *ctx, int horizontal, int n, const int16_
 // batched launch per step.
 // use_direct: steps whose planes are eligible run on the direct kernels (fb_direct_squeeze.cuh), which can also carry
 // the epilogue (inverse YCoCg on the step that produces Co and Cg, final clamp on every plane's last step).
+// ---------------------------------------------------------------------------------------------------------
+// packed unsqueeze kernels (fb_pk_squeeze.cuh): TMA descriptors + launches of one squeeze step
+// ---------------------------------------------------------------------------------------------------------
+namespace ps {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// box_w x box_h tiles of a row-major w x h int16 plane without padding: out-of-range elements load as zero, stores are clipped
+bool ps_make_tilemap(TileMap *m, const void *base, int w, int h, int box_w, int box_h) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn || (reinterpret_cast<uintptr_t>(base) & 15) || (w & 7) || box_w > 256 || box_h > 256) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)h};
+    const cuuint64_t strides[1] = {(cuuint64_t)w * sizeof(int16_t)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace ps
+
+template <int NP, int EP>
+static cudaError_t pk_launch_h(fb_ctx *ctx, const ps::HLaunch &L) {
+    // per device, not per process: a context on a second GPU needs the opt-in too
+    cudaError_t e = cudaFuncSetAttribute(ps::k_pk_hsq<NP, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (e != cudaSuccess) return e;
+    ps::k_pk_hsq<NP, EP><<<L.grid, 32 * L.warps_per_block, L.smem, ctx->stream>>>(L.jobs, L.warps_per_block, L.smem_per_warp);
+    return cudaGetLastError();
+}
+
+// Runs the planes of one squeeze step that the packed kernels take; `rest` receives the indices (into ops) they left.
+static int pk_run_step(fb_ctx *ctx, const std::vector<ps::StepOp> &ops, bool horizontal, const ps::StepEpilogue &E, int lo, int hi,
+                       std::vector<int> &rest, bool *epilogue_done) {
+    if (!ctx->pk_stats) {
+        FB_CUDA(ctx, cudaMalloc((void **)&ctx->pk_stats, 2 * sizeof(int)));
+        FB_CUDA(ctx, cudaMemsetAsync(ctx->pk_stats, 0, 2 * sizeof(int), ctx->stream));
+    }
+    ps::StepPlan P = ps::plan_step(ops, horizontal, E, lo, hi, ctx->sm_count, ctx->pk_stats);
+    rest = P.leftover;
+    *epilogue_done = P.epilogue_done;
+    if (P.h.empty() && P.v.empty()) return FB_OK;
+    if (P.scratch_bytes > ctx->pk_scratch_bytes) {      // grown rarely: the largest step of an image comes last
+        if (ctx->pk_scratch) { FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->pk_scratch); ctx->pk_scratch = nullptr; }
+        const size_t want = P.scratch_bytes + P.scratch_bytes / 2;
+        FB_CUDA(ctx, cudaMalloc((void **)&ctx->pk_scratch, want));
+        ctx->pk_scratch_bytes = want;
+    }
+    if (P.counters > ctx->pk_counters_n) {
+        if (ctx->pk_counters) { FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->pk_counters); ctx->pk_counters = nullptr; }
+        const int want = P.counters * 2 + 64;
+        FB_CUDA(ctx, cudaMalloc((void **)&ctx->pk_counters, want * sizeof(int)));
+        FB_CUDA(ctx, cudaMemsetAsync(ctx->pk_counters, 0, want * sizeof(int), ctx->stream));
+        ctx->pk_counters_n = want;
+    }
+    ps::relocate(P, ctx->pk_scratch, ctx->pk_counters);
+    for (auto &L : P.h) {
+        cudaError_t e;
+        if (L.ep == fq::kEpYCoCg) e = pk_launch_h<2, fq::kEpYCoCg>(ctx, L);
+        else if (L.np == 2 && L.ep == fq::kEpClamp) e = pk_launch_h<2, fq::kEpClamp>(ctx, L);
+        else if (L.np == 2) e = pk_launch_h<2, fq::kEpNone>(ctx, L);
+        else if (L.ep == fq::kEpClamp) e = pk_launch_h<1, fq::kEpClamp>(ctx, L);
+        else e = pk_launch_h<1, fq::kEpNone>(ctx, L);
+        if (e != cudaSuccess) { ctx->err = std::string("k_pk_hsq launch: ") + cudaGetErrorString(e); return FB_ERR_CUDA; }
+        ctx->launches++;
+        ctx->mark(L.ep == fq::kEpYCoCg ? "k_pk_hsq(ycocg)" : "k_pk_hsq", L.bytes);
+    }
+    for (auto &L : P.v) {
+        ps::k_pk_vsq<<<L.grid, 32 * L.warps_per_block, 0, ctx->stream>>>(L.jobs, L.warps_per_block);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { ctx->err = std::string("k_pk_vsq launch: ") + cudaGetErrorString(e); return FB_ERR_CUDA; }
+        ctx->launches++;
+        ctx->mark("k_pk_vsq", L.bytes);
+    }
+    static const bool pk_debug = getenv("FB_PK_DEBUG") != nullptr;
+    if (pk_debug) {        // development aid: repairs / range flags so far, after every step
+        int v[2] = {0, 0};
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(v, ctx->pk_stats, sizeof(v), cudaMemcpyDeviceToHost);
+        for (auto &L : P.h) for (int j = 0; j < L.jobs.n; j++)
+            fprintf(stderr, "[pk] h np=%d ep=%d wa=%d h=%d S=%d nseg=%d nrb=%d\n", L.np, L.ep, L.jobs.j[j].wa, L.jobs.j[j].h, L.jobs.j[j].S, L.jobs.j[j].nseg, L.jobs.j[j].nrb);
+        for (auto &L : P.v) for (int j = 0; j < L.jobs.n; j++)
+            fprintf(stderr, "[pk] v w=%d ha=%d S=%d nseg=%d ncg=%d\n", L.jobs.j[j].w, L.jobs.j[j].ha, L.jobs.j[j].S, L.jobs.j[j].nseg, L.jobs.j[j].ncg);
+        fprintf(stderr, "[pk]   -> repaired %d, range-flagged %d (cumulative)\n", v[0], v[1]);
+    }
+    return FB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// self-test of the packed primitives on the device (tests/test_gpu_pk_squeeze.py): the 16x2 pair and the 16x2 inverse
+// YCoCg against their exact 32-bit forms on pseudo-random inputs inside the admitted range; counts mismatches
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ unsigned st_rng(unsigned &s) { s = s * 1664525u + 1013904223u; return s >> 8; }
+__global__ void k_pk_selftest(int which, unsigned seed, int scale, int maxval, int iters, int *mism) {
+    unsigned s = seed ^ (blockIdx.x * 9781u + threadIdx.x * 6271u + 1u);
+    int bad = 0;
+    for (int it = 0; it < iters; it++) {
+        int v[2][4];
+        for (int k = 0; k < 2; k++) {
+            const int amax = min(4 * scale, ps::kMaxAvg), rmax = min(4 * scale, ps::kMaxRes);
+            const int av = (int)(st_rng(s) % (2 * amax + 1)) - amax;
+            int nx = av + (int)(st_rng(s) % (2 * scale + 1)) - scale;
+            nx = max(-ps::kMaxAvg, min(ps::kMaxAvg, nx));
+            int pv = av + (int)(st_rng(s) % (4 * scale + 1)) - 2 * scale;
+            pv = max(-8189, min(8189, pv));
+            const int rs = (int)(st_rng(s) % (2 * rmax + 1)) - rmax;
+            v[k][0] = pv; v[k][1] = av; v[k][2] = nx; v[k][3] = rs;
+        }
+        auto pk = [&](int i) { return (uint32_t)(uint16_t)v[0][i] | ((uint32_t)(uint16_t)v[1][i] << 16); };
+        if (which == 0) {
+            uint32_t A, B;
+            ps::pk_step(pk(0), pk(1), ps::pneg(pk(1)), ps::pneg(pk(2)), pk(3), A, B);
+            for (int k = 0; k < 2; k++) {
+                int A2, B2;
+                fq::unsqueeze_pair(v[k][0], v[k][1], v[k][2], v[k][3], A2, B2);
+                const int Ag = (int)(short)(k ? A >> 16 : A & 0xffff), Bg = (int)(short)(k ? B >> 16 : B & 0xffff);
+                if (Ag != A2 || Bg != B2) bad++;
+            }
+        } else {
+            // Y anywhere in int16, Co / Cg anywhere a checked step can leave them
+            int y[2], co[2], cg[2];
+            for (int k = 0; k < 2; k++) { y[k] = (int)(short)st_rng(s); co[k] = (int)(st_rng(s) % 16379) - 8189; cg[k] = (int)(st_rng(s) % 16379) - 8189; }
+            uint32_t R, G, B;
+            const uint32_t mv = (uint32_t)(uint16_t)maxval * 0x00010001u;
+            ps::pk_ycocg((uint32_t)(uint16_t)y[0] | ((uint32_t)(uint16_t)y[1] << 16), (uint32_t)(uint16_t)co[0] | ((uint32_t)(uint16_t)co[1] << 16),
+                         (uint32_t)(uint16_t)cg[0] | ((uint32_t)(uint16_t)cg[1] << 16), mv, R, G, B);
+            for (int k = 0; k < 2; k++) {
+                int R2, G2, B2;
+                ps::ycocg_exact(y[k], co[k], cg[k], maxval, 0, 0, 0, R2, G2, B2);
+                const int Rg = (int)(short)(k ? R >> 16 : R & 0xffff), Gg = (int)(short)(k ? G >> 16 : G & 0xffff), Bg = (int)(short)(k ? B >> 16 : B & 0xffff);
+                if (Rg != R2 || Gg != G2 || Bg != B2) bad++;
+            }
+        }
+        // the range accumulator: inside the range it must stay quiet, one value outside must trip it
+        if (which == 0) {
+            uint32_t acc = 0;
+            acc = ps::pk_chk(acc, pk(1), ps::kMaxAvg * 0x00010001u);
+            acc = ps::pk_chk(acc, pk(2), ps::kMaxAvg * 0x00010001u);
+            if (ps::pk_chk_bad(acc, ps::kMaxAvg)) bad++;
+            const int out = (it & 1) ? ps::kMaxAvg + 1 + (int)(st_rng(s) % 30000) : -ps::kMaxAvg - 1 - (int)(st_rng(s) % 30000);
+            acc = ps::pk_chk(acc, (uint32_t)(uint16_t)out << ((it & 2) ? 16 : 0), ps::kMaxAvg * 0x00010001u);
+            if (!ps::pk_chk_bad(acc, ps::kMaxAvg)) bad++;
+        }
+    }
+    if (bad) atomicAdd(mism, bad);
+}
+}  // namespace
+
+extern "C" FB_API int fb_selftest_packed(fb_ctx *ctx, int which, unsigned seed, int scale, int maxval, long long *mismatches) {
+    if (!ctx || !mismatches || which < 0 || which > 1 || scale < 1) return FB_ERR_INVALID;
+    int *d = nullptr;
+    FB_CUDA(ctx, cudaMalloc((void **)&d, sizeof(int)));
+    FB_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(int), ctx->stream));
+    k_pk_selftest<<<296, 256, 0, ctx->stream>>>(which, seed, scale, maxval, 64, d);
+    ctx->launches++;
+    int h = 0;
+    FB_CUDA(ctx, cudaMemcpyAsync(&h, d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    *mismatches = h;
+    return FB_OK;
+}
+
 static int run_inv_squeeze_plan_per_level(fb_ctx *ctx, const std::vector<FbSqOp> &ops, bool use_direct, const FbSqEpilogue *ep, int *epilogue_done) {
     const int n = (int)ops.size();
     if (epilogue_done) *epilogue_done = 0;
@@ -936,11 +1108,39 @@ static int run_inv_squeeze_plan_per_level(fb_ctx *ctx, const std::vector<FbSqOp>
         int q = k;
         while (q < n && ops[q].step == step) { if (!fused[q]) idx.push_back(q); q++; }
         std::vector<int> rest = idx;
+        static const bool pk_env_off = getenv("FB_SQUEEZE_PK") && atoi(getenv("FB_SQUEEZE_PK")) == 0;
+        const bool last_step = step == ops[n - 1].step;
+        bool pk_took_epilogue = false;
+        if (use_direct && ctx->pk_mode && !pk_env_off && ctx->sq_maxval >= 0 && ctx->sq_maxval <= 1023) {
+            // packed int16x2 kernels first (fb_pk_squeeze.cuh); what they refuse falls through to the older kernels
+            std::vector<ps::StepOp> sops;
+            for (int i : idx) {
+                ps::StepOp so;
+                so.avg = ops[i].avg; so.res = ops[i].res; so.out = ops[i].out; so.wa = ops[i].wa; so.wr = ops[i].wr; so.ha = ops[i].ha; so.hr = ops[i].hr;
+                so.clamp = clamp_op[i];
+                sops.push_back(so);
+            }
+            ps::StepEpilogue E;
+            if (ep_ok && ep->kind == 2 && last_step && horizontal) {
+                E.enabled = 1; E.yin = ep->ycc[0]; E.rout = ep->rout; E.co_out = ep->ycc[1]; E.cg_out = ep->ycc[2];
+                E.maxval = ep->maxval; E.lo = ep->lo; E.hi = ep->hi;
+                E.do_clamp = (ep->do_clamp && !(ep->lo <= 0 && ep->hi >= ep->maxval)) ? 1 : 0;
+            }
+            std::vector<int> left;
+            int rc = pk_run_step(ctx, sops, horizontal != 0, E, ep ? ep->lo : 0, ep ? ep->hi : 0, left, &pk_took_epilogue);
+            if (rc) return rc;
+            std::vector<int> nidx;
+            for (int i : left) nidx.push_back(idx[i]);
+            idx = nidx;
+            rest = idx;
+            if (pk_took_epilogue) ep_applied = true;
+        }
+        if (idx.empty()) { k = q; continue; }
         if (use_direct && (horizontal || direct_v)) {
             std::vector<dq::StepOp> sops;
             for (int i : idx) { dq::StepOp so = as_step_op(ops[i]); so.clamp = clamp_op[i]; sops.push_back(so); }
             dq::StepEpilogue E;
-            if (ep_ok && ep->kind == 2 && step == ops[n - 1].step) {
+            if (ep_ok && ep->kind == 2 && step == ops[n - 1].step && !pk_took_epilogue) {
                 E.enabled = 1; E.yin = ep->ycc[0]; E.rout = ep->rout; E.co_out = ep->ycc[1]; E.cg_out = ep->ycc[2];
                 E.maxval = ep->maxval; E.lo = ep->lo; E.hi = ep->hi;
                 // inv_YCoCg leaves R, G, B in [0, maxval] (ycocg.h:51-56): a final clamp to a range that contains it is the identity

@@ -97,6 +97,10 @@ FB_API long long fb_ctx_launch_count(fb_ctx *ctx);
  * FB_OPT_KERNEL_TIMING: 1 = record a CUDA event after every launch (fb_ctx_timing_report). */
 #define FB_OPT_SQUEEZE_MODE 1
 #define FB_OPT_KERNEL_TIMING 2
+/* FB_OPT_SQUEEZE_PACKED: 1 (default) = squeeze steps of images with maxval <= 1023 whose planes qualify (width a multiple
+ *   of 8, at least 64 x 32) run on the packed int16x2 kernels (TMA-fed horizontal step with the inverse YCoCg / clamp
+ *   epilogue, coalesced vertical step); 0 = never.  Results are bit-exact either way. */
+#define FB_OPT_SQUEEZE_PACKED 3
 FB_API int fb_ctx_set_option(fb_ctx *ctx, int option, int value);
 /* The fused Squeeze inverse (mode >= 2) starts tiles speculatively and verifies them (results are bit-exact either way).
  * which = 0: Squeeze inverses so far that failed verification in an early launch and were recomputed serially;
@@ -104,7 +108,14 @@ FB_API int fb_ctx_set_option(fb_ctx *ctx, int option, int value);
  * Synchronises the stream. */
 #define FB_COUNTER_SERIAL_FALLBACKS 0
 #define FB_COUNTER_REPAIRED_TILES 1
+/* packed kernels: segments recomputed by the exact routine so far / segments that saw a value outside the packed range */
+#define FB_COUNTER_PK_REPAIRED 2
+#define FB_COUNTER_PK_RANGE_FLAGGED 3
 FB_API long long fb_ctx_counter(fb_ctx *ctx, int which);
+/* Device self-test of the packed 16x2 primitives against their exact 32-bit forms on pseudo-random inputs inside the
+ * admitted range: which = 0 the unsqueeze pair (+ the range accumulator), 1 the inverse YCoCg.  scale = typical distance
+ * between neighbouring values.  *mismatches = 0 on a correct device / build.  (No reference counterpart: a test hook.) */
+FB_API int fb_selftest_packed(fb_ctx *ctx, int which, unsigned seed, int scale, int maxval, long long *mismatches);
 /* With FB_OPT_KERNEL_TIMING: synchronises, then writes one line "name<TAB>microseconds<TAB>algorithmic bytes" per
  * launch recorded since the last report (NUL-terminated, truncated to cap) and returns the untruncated length. */
 FB_API long long fb_ctx_timing_report(fb_ctx *ctx, char *buf, size_t cap);

@@ -248,3 +248,122 @@ int emu_run_direct(int nplanes, int16_t **planes, int nops, const int *opdesc, c
     return 0;
 }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// packed per-step kernels (fb_pk_squeeze.cuh + fb_pk_plan.h): TMA / mbarrier replaced by synchronous copies
+// ---------------------------------------------------------------------------------------------------------
+#include <type_traits>
+#include "fb_pk_plan.h"
+
+namespace ps {
+bool ps_make_tilemap(TileMap *m, const void *base, int w, int h, int box_w, int box_h) {
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (w & 7)) return false;
+    m->base = (int16_t *)base; m->w = w; m->h = h; m->box_w = box_w; m->box_h = box_h;
+    return true;
+}
+}  // namespace ps
+
+extern "C" {
+// same descriptors as emu_run_direct.  sm_count shapes the segment lengths.
+// stats[6] (out) = packed launches, ops handled by the packed kernels, ops left to the serial code, epilogue done, repaired segments, range-flagged segments
+int emu_run_pk(int nplanes, int16_t **planes, int nops, const int *opdesc, const int *ep, int lo, int hi, int sm_count, int *stats) {
+    (void)nplanes;
+    memset(stats, 0, 6 * sizeof(int));
+    int dev_stats[2] = {0, 0};
+    int i0 = 0;
+    while (i0 < nops) {
+        int i1 = i0;
+        while (i1 < nops && opdesc[10 * i1] == opdesc[10 * i0]) i1++;
+        const bool horizontal = opdesc[10 * i0 + 1] != 0;
+        std::vector<ps::StepOp> ops;
+        for (int i = i0; i < i1; i++) {
+            const int *d = opdesc + 10 * i;
+            ps::StepOp o;
+            o.avg = planes[d[2]]; o.res = d[3] >= 0 ? planes[d[3]] : nullptr; o.out = planes[d[4]];
+            o.wa = d[5]; o.wr = d[6]; o.ha = d[7]; o.hr = d[8]; o.clamp = d[9];
+            ops.push_back(o);
+        }
+        ps::StepEpilogue E;
+        if (ep[0] && i1 == nops) {
+            E.enabled = 1; E.yin = planes[ep[1]]; E.rout = planes[ep[2]]; E.co_out = planes[ep[3]]; E.cg_out = planes[ep[4]];
+            E.maxval = ep[5]; E.lo = ep[6]; E.hi = ep[7]; E.do_clamp = ep[8];
+        }
+        ps::StepPlan P = ps::plan_step(ops, horizontal, E, lo, hi, sm_count, dev_stats);
+        std::vector<unsigned char> scratch(P.scratch_bytes + 64, 0xEE);
+        std::vector<int> counters((size_t)P.counters + 1, 0);
+        ps::relocate(P, scratch.data(), counters.data());
+        for (auto &L : P.h) {
+            const ps::HJobs J = L.jobs;
+            const int wpb = L.warps_per_block, spw = L.smem_per_warp;
+            auto run = [&](auto kern) { cuemu::launch((unsigned)L.grid, (unsigned)(32 * wpb), L.smem, false, kern); };
+            if (L.ep == fq::kEpYCoCg) run([&]() { ps::k_pk_hsq<2, fq::kEpYCoCg>(J, wpb, spw); });
+            else if (L.np == 2 && L.ep == fq::kEpClamp) run([&]() { ps::k_pk_hsq<2, fq::kEpClamp>(J, wpb, spw); });
+            else if (L.np == 2) run([&]() { ps::k_pk_hsq<2, fq::kEpNone>(J, wpb, spw); });
+            else if (L.ep == fq::kEpClamp) run([&]() { ps::k_pk_hsq<1, fq::kEpClamp>(J, wpb, spw); });
+            else run([&]() { ps::k_pk_hsq<1, fq::kEpNone>(J, wpb, spw); });
+            stats[0]++;
+            for (int j = 0; j < J.n; j++) stats[1] += J.j[j].np;
+        }
+        for (auto &L : P.v) {
+            const ps::VJobs J = L.jobs;
+            const int wpb = L.warps_per_block;
+            cuemu::launch((unsigned)L.grid, (unsigned)(32 * wpb), 0, false, [&]() { ps::k_pk_vsq(J, wpb); });
+            stats[0]++;
+            stats[1] += J.n;
+        }
+        for (int c : counters) if (c != 0) return 2;        // every arrival counter must be back at zero
+        for (int k : P.leftover) {
+            const ps::StepOp &o = ops[k];
+            fq::SerialOp so;
+            so.avg = o.avg; so.res = o.res; so.out = o.out; so.wa = o.wa; so.wr = o.wr; so.ha = o.ha; so.hr = o.hr;
+            so.horizontal = horizontal; so.step = 0;
+            const int nchain = horizontal ? o.ha : o.wa;
+            for (int c = 0; c < nchain; c++) fq::serial_chain(so, c);
+            if (o.clamp) {
+                const size_t nn = (size_t)(horizontal ? o.wa + o.wr : o.wa) * (horizontal ? o.ha : o.ha + o.hr);
+                for (size_t q = 0; q < nn; q++) o.out[q] = (int16_t)fq::clampi(o.out[q], lo, hi);
+            }
+            stats[2]++;
+        }
+        if (P.epilogue_done) stats[3] = 1;
+        i0 = i1;
+    }
+    stats[4] = dev_stats[0];
+    stats[5] = dev_stats[1];
+    return 0;
+}
+
+// the packed pair against the exact 32-bit pair on n inputs; returns mismatches
+int emu_check_pk_pair(const int16_t *prev, const int16_t *av, const int16_t *nx, const int16_t *rs, int n) {
+    int bad = 0;
+    for (int i = 0; i + 1 < n; i += 2) {
+        const uint32_t P = ps::e_h(prev[i], prev[i + 1]), a = ps::e_h(av[i], av[i + 1]), nn = ps::e_h(nx[i], nx[i + 1]), r = ps::e_h(rs[i], rs[i + 1]);
+        uint32_t A, B;
+        ps::pk_step(P, a, ps::pneg(a), ps::pneg(nn), r, A, B);
+        for (int k = 0; k < 2; k++) {
+            int A2, B2;
+            fq::unsqueeze_pair(prev[i + k], av[i + k], nx[i + k], rs[i + k], A2, B2);
+            const int Ag = k ? ps::e_hi(A) : ps::e_lo(A), Bg = k ? ps::e_hi(B) : ps::e_lo(B);
+            if (Ag != A2 || Bg != B2) bad++;
+        }
+    }
+    return bad;
+}
+
+// packed inverse YCoCg against the exact one; returns mismatches
+int emu_check_pk_ycocg(const int16_t *y, const int16_t *co, const int16_t *cg, int n, int maxval) {
+    int bad = 0;
+    const uint32_t mv = (uint32_t)(uint16_t)maxval * 0x00010001u;
+    for (int i = 0; i + 1 < n; i += 2) {
+        uint32_t R, G, B;
+        ps::pk_ycocg(ps::e_h(y[i], y[i + 1]), ps::e_h(co[i], co[i + 1]), ps::e_h(cg[i], cg[i + 1]), mv, R, G, B);
+        for (int k = 0; k < 2; k++) {
+            int R2, G2, B2;
+            ps::ycocg_exact(y[i + k], co[i + k], cg[i + k], maxval, 0, 0, 0, R2, G2, B2);
+            const int Rg = k ? ps::e_hi(R) : ps::e_lo(R), Gg = k ? ps::e_hi(G) : ps::e_lo(G), Bg = k ? ps::e_hi(B) : ps::e_lo(B);
+            if (Rg != R2 || Gg != G2 || Bg != B2) bad++;
+        }
+    }
+    return bad;
+}
+}

@@ -16,7 +16,8 @@ SRCS = [os.path.join(EMU_DIR, "emu_squeeze.cpp"), os.path.join(EMU_DIR, "cuemu.h
         os.path.join(ROOT, "fuif_b200", "csrc", "fb_port.h"), os.path.join(ROOT, "fuif_b200", "csrc", "fb_direct_squeeze.cuh"),
         os.path.join(ROOT, "fuif_b200", "csrc", "fb_direct_plan.h"), os.path.join(ROOT, "fuif_b200", "csrc", "fb_subsample.cuh"),
         os.path.join(ROOT, "fuif_b200", "csrc", "fb_approx.cuh"), os.path.join(ROOT, "fuif_b200", "csrc", "fb_palette.cuh"),
-        os.path.join(ROOT, "fuif_b200", "csrc", "fb_match.cuh")]
+        os.path.join(ROOT, "fuif_b200", "csrc", "fb_match.cuh"), os.path.join(ROOT, "fuif_b200", "csrc", "fb_pk_squeeze.cuh"),
+        os.path.join(ROOT, "fuif_b200", "csrc", "fb_pk_plan.h")]
 _lib = None
 
 
@@ -39,6 +40,9 @@ def lib():
         L.emu_match_inv.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.emu_match_soft.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.emu_palette_fwd.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_int]
+        L.emu_run_pk.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.emu_check_pk_pair.argtypes = [C.c_void_p] * 4 + [C.c_int]
+        L.emu_check_pk_ycocg.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -89,4 +93,17 @@ def run_direct(planes, ops10, ep9, lo, hi):
     e = (C.c_int * 9)(*ep9)
     st = (C.c_int * 4)()
     L.emu_run_direct(len(planes), ptrs, len(ops10), od, e, lo, hi, st)
+    return list(st)
+
+
+def run_pk(planes, ops10, ep9, lo, hi, sm_count=4):
+    """The packed per-step kernels (fb_pk_squeeze.cuh) under the emulator; same descriptors as run_direct.
+    Returns [launches, packed ops, serial ops, epilogue done, repaired segments, range-flagged segments]."""
+    L = lib()
+    ptrs = (C.c_void_p * len(planes))(*[p.ctypes.data for p in planes])
+    od = (C.c_int * (10 * len(ops10)))(*[int(v) for o in ops10 for v in o])
+    e = (C.c_int * 9)(*ep9)
+    st = (C.c_int * 6)()
+    rc = L.emu_run_pk(len(planes), ptrs, len(ops10), od, e, lo, hi, sm_count, st)
+    assert rc == 0, f"emu_run_pk rc={rc}"
     return list(st)
