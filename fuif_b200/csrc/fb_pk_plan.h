@@ -59,8 +59,8 @@ struct ScratchCursor {
 
 // warps of the packed horizontal kernel that fit one SM (shared memory is the limit)
 inline int h_warps_per_sm(int np, int ep) {
-    int w = (int)((220 * 1024) / h_smem_per_warp(np, ep));
-    return w > 12 ? 12 : w;
+    int w = (int)((226 * 1024) / (h_smem_per_warp(np, ep) + 128 + 1024));      // + alignment slack + the per-block reservation
+    return w > 16 ? 16 : w;
 }
 
 inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const StepEpilogue &ep, int lo, int hi, int sm_count, int *stats_dev) {
@@ -114,7 +114,9 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
                     S = (S + kHChunk - 1) / kHChunk * kHChunk;
                     if (S < 2 * kHChunk) S = 2 * kHChunk;
                     J.np = np; J.wa = a.wa; J.h = a.ha; J.S = S; J.nseg = (a.wa + S - 1) / S; J.nrb = (a.ha + kHRows - 1) / kHRows;
+                    J.nsegp = (J.nseg + 7) / 8 * 8;
                     J.item0 = items;
+                    J.k1 = 0x00010001u;
                     items += J.nrb * J.nseg;
                     J.epilogue = epk; J.maxval = ep.maxval; J.lo = lo; J.hi = hi; J.do_clamp = epk == fq::kEpClamp ? 1 : 0;
                     const StepOp *pl[2] = {&a, i1 >= 0 ? &ops[i1] : nullptr};
@@ -122,10 +124,10 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
                         J.avg[p] = pl[p]->avg; J.res[p] = pl[p]->res;
                         ok = ok && ps_make_tilemap(&J.tm_a[p], pl[p]->avg, a.wa, a.ha, kHChunk, kHRows);
                         ok = ok && ps_make_tilemap(&J.tm_r[p], pl[p]->res, a.wa, a.ha, kHChunk, kHRows);
-                        J.est[p] = cur.take<int16_t>((size_t)J.nseg * a.ha);
-                        J.act[p] = cur.take<int16_t>((size_t)J.nseg * a.ha);
+                        J.est[p] = cur.take<int16_t>((size_t)J.nsegp * a.ha);
+                        J.act[p] = cur.take<int16_t>((size_t)J.nsegp * a.ha);
                     }
-                    J.bad = cur.take<unsigned char>((size_t)J.nseg * a.ha);
+                    J.bad = cur.take<int16_t>((size_t)J.nsegp * a.ha);
                     J.counter = reinterpret_cast<int *>((size_t)P.counters * sizeof(int));
                     P.counters += J.nrb;
                     J.stats = stats_dev;
@@ -166,7 +168,7 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
             L.bytes = 0;
             long long total_cg = 0;
             for (size_t j = j0; j < j1; j++) total_cg += (ops[mine[j]].wa + 255) / 256;
-            long long nseg_want = ((long long)sm_count * 8) / (total_cg > 0 ? total_cg : 1);       // ~8 warps per SM
+            long long nseg_want = ((long long)sm_count * 6) / (total_cg > 0 ? total_cg : 1);       // ~6 warps per SM, 4 chains each
             if (nseg_want < 1) nseg_want = 1;
             int items = 0;
             for (size_t j = j0; j < j1; j++) {
@@ -175,8 +177,10 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
                 int S = (int)((a.ha + nseg_want - 1) / nseg_want);
                 S = (S + 7) / 8 * 8;
                 if (S < 32) S = 32;
+                while ((a.ha + S - 1) / S > 32) S += 8;        // the verification pass reads two 16-byte words per segment and lane
                 J.avg = a.avg; J.res = a.res; J.out = a.out; J.w = a.wa; J.ha = a.ha; J.S = S; J.nseg = (a.ha + S - 1) / S; J.ncg = (a.wa + 255) / 256;
                 J.item0 = items;
+                J.k1 = 0x00010001u;
                 items += J.ncg * J.nseg;
                 J.do_clamp = a.clamp; J.lo = lo; J.hi = hi;
                 J.est = cur.take<int16_t>((size_t)J.nseg * a.wa);

@@ -45,7 +45,6 @@ constexpr int kMaxAvg = 2047;       // packed arithmetic is exact while |average
 constexpr int kMaxRes = 4095;       // |B| <= 3*kMaxAvg + kMaxRes/2 + 1 = 8189, 4|P-a| + 3|a-n| + 6 <= 53232 < 65536
 constexpr int kHChunk = 16;         // pairs per TMA tile (32-byte rows)
 constexpr int kHRows = 64;          // rows per warp tile
-constexpr int kHStages = 3;
 constexpr int kHWarm = kHChunk;     // warm-up pairs of a horizontal segment (one whole tile, nothing stored)
 constexpr int kVWarm = 8;           // warm-up pairs of a vertical segment
 constexpr int kVDepth = 4;          // rows of register prefetch in the vertical kernel
@@ -86,7 +85,13 @@ inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
 #endif
 
 FB_DEV uint32_t padd(uint32_t a, uint32_t b) { return __vadd2(a, b); }                  // VIADD.16x2 (wraps per half)
-FB_DEV uint32_t pneg(uint32_t a) { return __vadd2(~a, 0x00010001u); }
+// Packed constants come in through a register the compiler cannot see through (PK::k1 = 0x00010001 read from the job
+// descriptor): ptxas 12.9 was caught splitting `add.u16x2 x, 0x00010001` into per-half pieces and dropping the +1 of the low
+// half in one unrolled instance (VIADD.16x2 R, R, 0x0 + PRMT 0x7610; wrong low halves on the hardware, tests/test_sass_checks.py
+// looks for the pattern).  With a register operand there is no immediate to split.
+struct PK { uint32_t k1, k2, k6; };
+FB_DEV PK pk_consts(uint32_t one) { PK k; k.k1 = one; k.k2 = __vadd2(one, one); k.k6 = __vadd2(__vadd2(k.k2, k.k2), k.k2); return k; }
+FB_DEV uint32_t pneg(uint32_t a, const PK &K) { return __vadd2(~a, K.k1); }
 // 0xffff where the half is negative: PRMT with the sign-replicate bit of the selector nibbles, which only PTX exposes
 // (__byte_perm masks the selector to 3 bits per nibble)
 #if defined(FB_EMULATE)
@@ -113,26 +118,26 @@ FB_DEV uint32_t pdiv12(uint32_t t) {
 // With sigma = sign(P - n): a monotone triple has sigma*(P-a) >= 0 and sigma*(a-n) >= 0 and
 //   tendency = sigma * min((4 s(P-a) + 3 s(a-n) + 6) / 12, 2 s(P-a) + 1, 2 s(a-n));
 // otherwise one of 2 s(P-a) + 1, 2 s(a-n) is negative and the RELU of the min gives the reference's 0.
-FB_DEV void pk_step(uint32_t P, uint32_t a, uint32_t nega, uint32_t negn, uint32_t r, uint32_t &A, uint32_t &B) {
+FB_DEV void pk_step(const PK &K, uint32_t P, uint32_t a, uint32_t nega, uint32_t negn, uint32_t r, uint32_t &A, uint32_t &B) {
     const uint32_t t1 = padd(P, nega), t2 = padd(a, negn), u = padd(P, negn);
-    const uint32_t s = psign(u), s1 = s & 0x00010001u;
+    const uint32_t s = psign(u), s1 = s & K.k1;
     const uint32_t a1 = padd(t1 ^ s, s1), a2 = padd(t2 ^ s, s1);
     const uint32_t m1 = padd(a1, a1), m2 = padd(a2, a2);
-    const uint32_t t = padd(padd(padd(m1, m1), padd(m2, a2)), 0x00060006u);
+    const uint32_t t = padd(padd(padd(m1, m1), padd(m2, a2)), K.k6);
     const uint32_t q = pdiv12(t);
-    const uint32_t d = __viaddmin_s16x2_relu(m1, 0x00010001u, __vmins2(q, m2));
+    const uint32_t d = __viaddmin_s16x2_relu(m1, K.k1, __vmins2(q, m2));
     const uint32_t diff = padd(r, padd(d ^ s, s1));
-    const uint32_t dd = padd(diff, (diff >> 15) & 0x00010001u);      // + 1 where negative: >> 1 then truncates toward zero
+    const uint32_t dd = padd(diff, (diff >> 15) & K.k1);             // + 1 where negative: >> 1 then truncates toward zero
     A = padd(a, pasr1(dd));
-    B = padd(padd(A, ~diff), 0x00010001u);
+    B = padd(padd(A, ~diff), K.k1);
 }
 
 // inverse YCoCg on two pixels at once (ycocg.h:51-56): G = clamp(Y + ((Cg+1)>>1)), B = clamp(Y - (Cg>>1) - (Co>>1)), R = clamp(Co + B),
 // all clamps to [0, maxval]; exact while |Co|, |Cg| <= 8189 (outputs of a range-checked step) and maxval >= 0
-FB_DEV void pk_ycocg(uint32_t y, uint32_t co, uint32_t cg, uint32_t mv, uint32_t &R, uint32_t &G, uint32_t &B) {
+FB_DEV void pk_ycocg(const PK &K, uint32_t y, uint32_t co, uint32_t cg, uint32_t mv, uint32_t &R, uint32_t &G, uint32_t &B) {
     const uint32_t yc = __vimin3_s16x2_relu(y, mv, mv);
-    G = __viaddmin_s16x2_relu(yc, pasr1(padd(cg, 0x00010001u)), mv);
-    const uint32_t nsum = padd(padd(pasr1(~cg), pasr1(~co)), 0x00020002u);       // -(cg>>1) - (co>>1): ~(x>>1) = -(x>>1) - 1
+    G = __viaddmin_s16x2_relu(yc, pasr1(padd(cg, K.k1)), mv);
+    const uint32_t nsum = padd(padd(pasr1(~cg), pasr1(~co)), K.k2);       // -(cg>>1) - (co>>1): ~(x>>1) = -(x>>1) - 1
     B = __viaddmin_s16x2_relu(yc, nsum, mv);
     R = __viaddmin_s16x2_relu(co, B, mv);
 }
@@ -165,6 +170,9 @@ inline void tile_store(const TileMap *m, int x, int y, const void *src) {
             if (gx >= 0 && gx < m->w && gy >= 0 && gy < m->h) m->base[(size_t)gy * m->w + gx] = s[r * m->box_w + c];
         }
 }
+// the copies above are synchronous, so "the tile has landed" only needs lane 0 to have reached its issue point: a warp
+// rendezvous stands in for the mbarrier wait (emu_issue_point is empty in the product)
+inline void emu_issue_point() { fb_syncwarp(); }
 inline void mbar_init(uint64_t *, int) {}
 inline void mbar_expect(uint64_t *, int) {}
 inline void mbar_wait(uint64_t *, int) {}
@@ -175,8 +183,9 @@ inline void store_wait_all() {}
 inline void fence_mbar_init() {}
 #else
 typedef CUtensorMap TileMap;
+FB_DEV void emu_issue_point() {}
 FB_DEV void fb_syncwarp() { __syncwarp(); }
-FB_DEV void fb_threadfence() { __threadfence(); }
+FB_DEV void fb_threadfence() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }     // release before / acquire after the arrival counter
 FB_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 FB_DEV void mbar_init(uint64_t *bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
 FB_DEV void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -234,22 +243,24 @@ struct HJob {                   // one horizontal step on np planes of identical
     const int16_t *avg[2], *res[2];     // the same planes for the exact repair routine
     int16_t *out[3];
     const int16_t *yin;
-    int16_t *est[2], *act[2];   // [nseg][h] per plane: state assumed at the first owned pair / final state of the segment
-    unsigned char *bad;         // [nseg][h]: segment saw a value outside the packed range (or is otherwise to be recomputed)
+    int16_t *est[2], *act[2];   // [h][nsegp] per plane: act[row][g] = final state of segment g, est[row][g-1] = state segment g assumed at its
+                                // first owned pair (so a row joins everywhere iff est[row][j] == act[row][j] for j < nseg-1: vector compares)
+    int16_t *bad;               // [h][nsegp]: segment saw a value outside the packed range (it is recomputed by the exact routine)
     int *counter;               // [nrb] arrivals per row block (left at zero by the last arriver)
     int *stats;                 // [0] repaired segments, [1] range-flagged segments (diagnostics)
     int np, wa, h;
     int S, nseg, nrb;           // pairs per segment (multiple of kHChunk), segments per row, row blocks of kHRows
+    int nsegp;                  // nseg rounded up to a multiple of 8 (16-byte rows of est / act / bad)
     int item0;                  // first work item of this job
     int epilogue;               // fq::kEpNone / kEpClamp / kEpYCoCg
     int maxval, lo, hi, do_clamp;
+    uint32_t k1;                // 0x00010001 (see PK)
 };
 struct HJobs { HJob j[kMaxHJobs]; int n, items; };
 
 FB_HD size_t h_smem_per_warp(int np, int epilogue) {
-    const size_t in = (size_t)np * 2 * kHRows * kHChunk * 2 + (epilogue == fq::kEpYCoCg ? (size_t)kHRows * 2 * kHChunk * 2 : 0);
-    const size_t nout = epilogue == fq::kEpYCoCg ? 3 : np;
-    return kHStages * in + nout * kHRows * 2 * kHChunk * 2 + 128;     // + mbarriers (slices stay 128-byte aligned)
+    const size_t stage = (size_t)np * 2 * kHRows * kHChunk * 2 + (epilogue == fq::kEpYCoCg ? (size_t)kHRows * 2 * kHChunk * 2 : 0);
+    return 2 * stage + 128;         // two slots (inputs, then the outputs in place) + mbarriers; slices stay 128-byte aligned
 }
 
 // exact inverse YCoCg + final clamp of one pixel
@@ -288,56 +299,80 @@ FB_DEV void h_repair(const HJob &J, int row, int g, int *prev) {
     }
 }
 
-// the last arriver of a row block: walk the segments of every row in order, repair what does not join
+// halves [0, valid) of the four words starting at halfword 8*i of a row are meaningful
+FB_DEV uint32_t tail_mask(int valid, int word) {
+    const int v = valid - 2 * word;
+    return v >= 2 ? 0xffffffffu : (v == 1 ? 0x0000ffffu : 0u);
+}
+// the last arriver of a row block: does every segment of its rows join its predecessor?  First with a handful of independent
+// 16-byte loads per row (the common case: one memory round trip); only a row that does not is walked in order and repaired.
 FB_DEV void h_verify(const HJob &J, int rb, int lane) {
     for (int half = 0; half < 2; half++) {
         const int row = rb * kHRows + lane + 32 * half;
         if (row >= J.h) continue;
+        const size_t ro = (size_t)row * J.nsegp;
+        uint32_t dirty = 0;
+        for (int i = 0; i < J.nsegp / 8; i++) {
+            const uint4 b = *reinterpret_cast<const uint4 *>(J.bad + ro + 8 * i);
+            const int vb = J.nseg - 8 * i, ve = J.nseg - 1 - 8 * i;
+            dirty |= (b.x & tail_mask(vb, 0)) | (b.y & tail_mask(vb, 1)) | (b.z & tail_mask(vb, 2)) | (b.w & tail_mask(vb, 3));
+            for (int p = 0; p < J.np; p++) {
+                const uint4 e = *reinterpret_cast<const uint4 *>(J.est[p] + ro + 8 * i), a = *reinterpret_cast<const uint4 *>(J.act[p] + ro + 8 * i);
+                dirty |= ((e.x ^ a.x) & tail_mask(ve, 0)) | ((e.y ^ a.y) & tail_mask(ve, 1)) | ((e.z ^ a.z) & tail_mask(ve, 2)) | ((e.w ^ a.w) & tail_mask(ve, 3));
+            }
+        }
+        if (!dirty) continue;
         int cur[2] = {0, 0};
         for (int g = 0; g < J.nseg; g++) {
-            const size_t e = (size_t)g * J.h + row;
-            bool need = J.bad[e] != 0;
+            bool need = J.bad[ro + g] != 0;
             if (g > 0)
-                for (int p = 0; p < J.np; p++) need = need || (J.est[p][e] != (int16_t)cur[p]);
+                for (int p = 0; p < J.np; p++) need = need || (J.est[p][ro + g - 1] != (int16_t)cur[p]);
             if (need) {
                 h_repair(J, row, g, cur);
-                for (int p = 0; p < J.np; p++) J.act[p][e] = (int16_t)cur[p];
+                for (int p = 0; p < J.np; p++) J.act[p][ro + g] = (int16_t)cur[p];
                 atomicAdd(J.stats, 1);
             } else {
-                for (int p = 0; p < J.np; p++) cur[p] = J.act[p][e];
+                for (int p = 0; p < J.np; p++) cur[p] = J.act[p][ro + g];
             }
         }
     }
 }
 
-// One work item: rows [64 rb, 64 rb + 64) x segment g of job J, by one warp.  sm = this warp's shared memory.
+// One work item: rows [64 rb, 64 rb + 64) x segment g of job J, by one warp.  sm = this warp's shared memory: two slots of
+// kStage bytes + two mbarriers.  A slot receives the input tiles of a chunk (16 pairs x 64 rows of every plane); the lanes pull
+// their two rows into registers, and the slot then becomes the staging area of the chunk's OUTPUT tiles (same size: a pair of
+// averages + residuals makes a pair of samples), which a TMA store writes out while the other slot is being worked on.
 template <int NP, int EP>
-FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane, int &par) {
+FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane) {
     constexpr bool kCol = EP == fq::kEpYCoCg;
-    constexpr int kTileA = kHRows * kHChunk * 2;                // bytes of an average / residual tile
-    constexpr int kTileO = kHRows * 2 * kHChunk * 2;            // bytes of an output / Y tile
+    constexpr int kTileA = kHRows * kHChunk * 2;                // bytes of an average / residual tile (32-byte rows)
+    constexpr int kTileO = kHRows * 2 * kHChunk * 2;            // bytes of an output / Y tile (64-byte rows)
     constexpr int kStage = NP * 2 * kTileA + (kCol ? kTileO : 0);
     constexpr int kNOut = kCol ? 3 : NP;
-    unsigned char *sm_out = sm + kHStages * kStage;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm_out + kNOut * kTileO);
+    static_assert(kNOut * kTileO == kStage, "output tiles reuse the input slot");
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + 2 * kStage);
     const int wa = J.wa, row0 = rb * kHRows;
     const int x_own = g * J.S, x_end = fq::imin(x_own + J.S, wa);
     const int x_first = g ? x_own - kHWarm : 0;
     const int nchunks = (x_end - x_first + kHChunk - 1) / kHChunk;
+    const int rowA = lane * (kHChunk * 2), rowB = (lane + 32) * (kHChunk * 2);         // byte offsets of this lane's rows in a 32-byte-row tile
 
-    auto issue = [&](int c) {       // lane 0: loads of chunk c into its ring slot
-        const int st = c % kHStages, xc = x_first + c * kHChunk;
-        unsigned char *base = sm + st * kStage;
+    auto issue = [&](int c) {       // lane 0: the input tiles of chunk c into slot c & 1
+        const int xc = x_first + c * kHChunk;
+        unsigned char *base = sm + (c & 1) * kStage;
         const bool with_y = kCol && !(g && c == 0);
-        mbar_expect(&bars[st], NP * 2 * kTileA + (with_y ? kTileO : 0));
+        mbar_expect(&bars[c & 1], NP * 2 * kTileA + (with_y ? kTileO : 0));
         for (int p = 0; p < NP; p++) {
-            tile_load(base + p * 2 * kTileA, &J.tm_a[p], xc, row0, &bars[st], 0);
-            tile_load(base + p * 2 * kTileA + kTileA, &J.tm_r[p], xc, row0, &bars[st], 0);
+            tile_load(base + p * 2 * kTileA, &J.tm_a[p], xc, row0, &bars[c & 1], 0);
+            tile_load(base + p * 2 * kTileA + kTileA, &J.tm_r[p], xc, row0, &bars[c & 1], 0);
         }
-        if (with_y) tile_load(base + NP * 2 * kTileA, &J.tm_y, 2 * xc, row0, &bars[st], 0);
+        if (with_y) tile_load(base + NP * 2 * kTileA, &J.tm_y, 2 * xc, row0, &bars[c & 1], 0);
     };
-    if (lane == 0)
-        for (int c = 0; c < kHStages - 1 && c < nchunks; c++) issue(c);
+    if (lane == 0) {
+        issue(0);
+        if (nchunks > 1) issue(1);
+    }
+    emu_issue_point();
 
     uint32_t P[NP], a_end[NP], chk_a = 0, chk_r = 0;
 #pragma unroll
@@ -350,97 +385,95 @@ FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane, in
         }
     }
     const bool do_clamp = J.do_clamp != 0;
+    const PK K = pk_consts(J.k1);
     const uint32_t mv = (uint32_t)(uint16_t)J.maxval * 0x00010001u, clo = (uint32_t)(uint16_t)J.lo * 0x00010001u, chi = (uint32_t)(uint16_t)J.hi * 0x00010001u;
-    // par: bit st = parity the next wait on ring slot st must see (persists across the items of this warp)
     for (int c = 0; c < nchunks; c++) {
-        const int st = c % kHStages, xc = x_first + c * kHChunk;
-        fb_syncwarp();                                          // every lane is done with chunk c-1: its slot may be refilled
-        if (lane == 0 && c + kHStages - 1 < nchunks) issue(c + kHStages - 1);
-        mbar_wait(&bars[st], (par >> st) & 1);
-        par ^= 1 << st;
-        const bool have_next = c + 1 < nchunks;
-        if (have_next) mbar_wait(&bars[(c + 1) % kHStages], (par >> ((c + 1) % kHStages)) & 1);      // its first average is this chunk's last "next"
-        const unsigned char *base = sm + st * kStage, *nbase = sm + ((c + 1) % kHStages) * kStage;
-        const bool warm = g && c == 0;
-        const int nsteps = fq::imin(kHChunk, x_end - xc);
+        const int xc = x_first + c * kHChunk;
+        unsigned char *slot = sm + (c & 1) * kStage;
+        const unsigned char *nslot = sm + ((c + 1) & 1) * kStage;
+        const bool warm = g && c == 0, have_next = c + 1 < nchunks;
+        const int nsteps = fq::imin(kHChunk, x_end - xc);       // 16, or 8 at the end of a row whose width is 8 mod 16
+        if (c >= 1 && have_next) {
+            // the other slot held chunk c-1: once its output tiles have been read by the store engine it takes chunk c+1,
+            // which then has this chunk's whole computation to arrive
+            if (lane == 0) { store_wait_read(); issue(c + 1); }
+            emu_issue_point();
+        }
+        mbar_wait(&bars[c & 1], (c >> 1) & 1);
+        // ---- the lane's two rows of every input tile into registers
+        uint32_t aw[NP][2][8], rw[NP][2][8], yw[2][16];
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            const unsigned char *ta = slot + p * 2 * kTileA, *tr = ta + kTileA;
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int ro = r ? rowB : rowA;
+#pragma unroll
+                for (int v = 0; v < 2; v++) {
+                    const uint4 va = *reinterpret_cast<const uint4 *>(ta + ro + 16 * v), vr = *reinterpret_cast<const uint4 *>(tr + ro + 16 * v);
+                    aw[p][r][4 * v] = va.x; aw[p][r][4 * v + 1] = va.y; aw[p][r][4 * v + 2] = va.z; aw[p][r][4 * v + 3] = va.w;
+                    rw[p][r][4 * v] = vr.x; rw[p][r][4 * v + 1] = vr.y; rw[p][r][4 * v + 2] = vr.z; rw[p][r][4 * v + 3] = vr.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    chk_a = pk_chk(chk_a, aw[p][r][i], kMaxAvg * 0x00010001u);
+                    chk_r = pk_chk(chk_r, rw[p][r][i], kMaxRes * 0x00010001u);
+                }
+            }
+        }
+        if (kCol && !warm) {
+            const unsigned char *ty = slot + NP * 2 * kTileA;
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    const uint4 y = *reinterpret_cast<const uint4 *>(ty + 2 * (r ? rowB : rowA) + 16 * v);
+                    yw[r][4 * v] = y.x; yw[r][4 * v + 1] = y.y; yw[r][4 * v + 2] = y.z; yw[r][4 * v + 3] = y.w;
+                }
+        }
         if (c == 0) {
 #pragma unroll
-            for (int p = 0; p < NP; p++) {       // chain start: "left" = own average (squeeze.h:84-89); a segment start guesses the same
-                const uint32_t wA = *reinterpret_cast<const uint32_t *>(base + p * 2 * kTileA + lane * (kHChunk * 2));
-                const uint32_t wB = *reinterpret_cast<const uint32_t *>(base + p * 2 * kTileA + (lane + 32) * (kHChunk * 2));
-                P[p] = plo(wA, wB);
-            }
+            for (int p = 0; p < NP; p++) P[p] = plo(aw[p][0][0], aw[p][1][0]);      // chain start: "left" = own average (squeeze.h:84-89); a segment start guesses the same
         }
         if (c == 1 && g) {          // first owned pair: remember the state the warm-up reached
 #pragma unroll
             for (int p = 0; p < NP; p++) {
-                if (row0 + lane < J.h) J.est[p][(size_t)g * J.h + row0 + lane] = (int16_t)(P[p] & 0xffffu);
-                if (row0 + lane + 32 < J.h) J.est[p][(size_t)g * J.h + row0 + lane + 32] = (int16_t)(P[p] >> 16);
+                if (row0 + lane < J.h) J.est[p][(size_t)(row0 + lane) * J.nsegp + g - 1] = (int16_t)(P[p] & 0xffffu);
+                if (row0 + lane + 32 < J.h) J.est[p][(size_t)(row0 + lane + 32) * J.nsegp + g - 1] = (int16_t)(P[p] >> 16);
             }
         }
-        if (!warm) {
-            if (lane == 0) store_wait_read();                   // the previous output tile has left shared memory
-            fb_syncwarp();
+        // what the last pair of the chunk sees as its next average: own (row end, squeeze.h:93), the first average of the next
+        // chunk (already in the other slot), or the average after the segment (direct load above)
+        uint32_t a_last[NP];
+        if (have_next) {
+            mbar_wait(&bars[(c + 1) & 1], ((c + 1) >> 1) & 1);
+#pragma unroll
+            for (int p = 0; p < NP; p++)
+                a_last[p] = plo(*reinterpret_cast<const uint32_t *>(nslot + p * 2 * kTileA + rowA), *reinterpret_cast<const uint32_t *>(nslot + p * 2 * kTileA + rowB));
+        } else {
+#pragma unroll
+            for (int p = 0; p < NP; p++) a_last[p] = a_end[p];
         }
-        // half a tile (8 pairs) at a time, fully unrolled: 16-byte shared loads, everything else in registers
-        for (int hf = 0; hf < 2 && 8 * hf < nsteps; hf++) {
-            const int xh = xc + 8 * hf;
-            uint32_t aw[NP][2][4], rw[NP][2][4], a_last[NP];
-            // what the last pair of this half sees as its next average: own (row end, squeeze.h:93), the average after the
-            // segment (direct load above), or the next word in shared memory
-            const bool own_last = xh + 8 >= wa;
+        fb_syncwarp();              // every lane holds its inputs: the slot may now receive the outputs
 #pragma unroll
-            for (int p = 0; p < NP; p++) {
-                const unsigned char *ta = base + p * 2 * kTileA, *tr = ta + kTileA;
-#pragma unroll
-                for (int r = 0; r < 2; r++) {
-                    const uint4 va = *reinterpret_cast<const uint4 *>(ta + (lane + 32 * r) * (kHChunk * 2) + 16 * hf);
-                    const uint4 vr = *reinterpret_cast<const uint4 *>(tr + (lane + 32 * r) * (kHChunk * 2) + 16 * hf);
-                    aw[p][r][0] = va.x; aw[p][r][1] = va.y; aw[p][r][2] = va.z; aw[p][r][3] = va.w;
-                    rw[p][r][0] = vr.x; rw[p][r][1] = vr.y; rw[p][r][2] = vr.z; rw[p][r][3] = vr.w;
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        chk_a = pk_chk(chk_a, aw[p][r][i], kMaxAvg * 0x00010001u);
-                        chk_r = pk_chk(chk_r, rw[p][r][i], kMaxRes * 0x00010001u);
-                    }
-                }
-                if (hf == 0) {
-                    a_last[p] = plo(*reinterpret_cast<const uint32_t *>(ta + lane * (kHChunk * 2) + 16),
-                                    *reinterpret_cast<const uint32_t *>(ta + (lane + 32) * (kHChunk * 2) + 16));
-                } else if (have_next) {
-                    const unsigned char *na = nbase + p * 2 * kTileA;
-                    a_last[p] = plo(*reinterpret_cast<const uint32_t *>(na + lane * (kHChunk * 2)), *reinterpret_cast<const uint32_t *>(na + (lane + 32) * (kHChunk * 2)));
-                } else {
-                    a_last[p] = a_end[p];
-                }
-            }
-            uint32_t yw[2][8];
-            if (kCol && !warm) {
-                const unsigned char *ty = base + NP * 2 * kTileA;
-#pragma unroll
-                for (int r = 0; r < 2; r++) {
-                    const uint4 y0 = *reinterpret_cast<const uint4 *>(ty + (lane + 32 * r) * (4 * kHChunk) + 32 * hf);
-                    const uint4 y1 = *reinterpret_cast<const uint4 *>(ty + (lane + 32 * r) * (4 * kHChunk) + 32 * hf + 16);
-                    yw[r][0] = y0.x; yw[r][1] = y0.y; yw[r][2] = y0.z; yw[r][3] = y0.w; yw[r][4] = y1.x; yw[r][5] = y1.y; yw[r][6] = y1.z; yw[r][7] = y1.w;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++) {                       // two pairs per iteration: one word of averages per row
+        for (int k = 0; k < 8; k++) {                           // two pairs per iteration: one word of averages per row
+            if (2 * k < nsteps) {
                 uint32_t oA[NP][2], oB[NP][2];                  // [plane][pair]: packed (row l, row l+32)
 #pragma unroll
                 for (int p = 0; p < NP; p++) {
                     const uint32_t a0 = plo(aw[p][0][k], aw[p][1][k]), a1 = phi(aw[p][0][k], aw[p][1][k]);
                     uint32_t a2;
-                    if (k < 3) a2 = plo(aw[p][0][k + 1], aw[p][1][k + 1]);
-                    else a2 = own_last ? a1 : a_last[p];
+                    if (k < 7) a2 = plo(aw[p][0][k + 1], aw[p][1][k + 1]);
+                    else a2 = a_last[p];
+                    if (xc + 2 * k + 2 >= wa) a2 = a1;          // last pair of the row
                     const uint32_t r0 = plo(rw[p][0][k], rw[p][1][k]), r1 = phi(rw[p][0][k], rw[p][1][k]);
-                    const uint32_t n1 = pneg(a1);
-                    pk_step(P[p], a0, pneg(a0), n1, r0, oA[p][0], oB[p][0]);
-                    pk_step(oB[p][0], a1, n1, pneg(a2), r1, oA[p][1], oB[p][1]);
+                    const uint32_t n1 = pneg(a1, K);
+                    pk_step(K, P[p], a0, pneg(a0, K), n1, r0, oA[p][0], oB[p][0]);
+                    pk_step(K, oB[p][0], a1, n1, pneg(a2, K), r1, oA[p][1], oB[p][1]);
                     P[p] = oB[p][1];
                 }
                 if (!warm) {
-                    const int ob = 32 * hf + 8 * k;             // byte offset of output columns 4k .. 4k+3 of this half in a 64-byte output row
+                    const int ob = 8 * k;                       // byte offset of output columns 4k .. 4k+3 in a 64-byte output row
                     if (kCol) {
                         uint32_t R[4], G[4], Bc[4];
                         const uint32_t y4[4] = {plo(yw[0][2 * k], yw[1][2 * k]), phi(yw[0][2 * k], yw[1][2 * k]), plo(yw[0][2 * k + 1], yw[1][2 * k + 1]),
@@ -448,16 +481,16 @@ FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane, in
                         const uint32_t co4[4] = {oA[0][0], oB[0][0], oA[0][1], oB[0][1]}, cg4[4] = {oA[NP - 1][0], oB[NP - 1][0], oA[NP - 1][1], oB[NP - 1][1]};
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
-                            pk_ycocg(y4[i], co4[i], cg4[i], mv, R[i], G[i], Bc[i]);
+                            pk_ycocg(K, y4[i], co4[i], cg4[i], mv, R[i], G[i], Bc[i]);
                             if (do_clamp) { R[i] = pk_clamp(R[i], clo, chi); G[i] = pk_clamp(G[i], clo, chi); Bc[i] = pk_clamp(Bc[i], clo, chi); }
                         }
                         uint2 v;
-                        v.x = plo(R[0], R[1]); v.y = plo(R[2], R[3]); *reinterpret_cast<uint2 *>(sm_out + lane * (4 * kHChunk) + ob) = v;
-                        v.x = phi(R[0], R[1]); v.y = phi(R[2], R[3]); *reinterpret_cast<uint2 *>(sm_out + (lane + 32) * (4 * kHChunk) + ob) = v;
-                        v.x = plo(G[0], G[1]); v.y = plo(G[2], G[3]); *reinterpret_cast<uint2 *>(sm_out + kTileO + lane * (4 * kHChunk) + ob) = v;
-                        v.x = phi(G[0], G[1]); v.y = phi(G[2], G[3]); *reinterpret_cast<uint2 *>(sm_out + kTileO + (lane + 32) * (4 * kHChunk) + ob) = v;
-                        v.x = plo(Bc[0], Bc[1]); v.y = plo(Bc[2], Bc[3]); *reinterpret_cast<uint2 *>(sm_out + 2 * kTileO + lane * (4 * kHChunk) + ob) = v;
-                        v.x = phi(Bc[0], Bc[1]); v.y = phi(Bc[2], Bc[3]); *reinterpret_cast<uint2 *>(sm_out + 2 * kTileO + (lane + 32) * (4 * kHChunk) + ob) = v;
+                        v.x = plo(R[0], R[1]); v.y = plo(R[2], R[3]); *reinterpret_cast<uint2 *>(slot + 2 * rowA + ob) = v;
+                        v.x = phi(R[0], R[1]); v.y = phi(R[2], R[3]); *reinterpret_cast<uint2 *>(slot + 2 * rowB + ob) = v;
+                        v.x = plo(G[0], G[1]); v.y = plo(G[2], G[3]); *reinterpret_cast<uint2 *>(slot + kTileO + 2 * rowA + ob) = v;
+                        v.x = phi(G[0], G[1]); v.y = phi(G[2], G[3]); *reinterpret_cast<uint2 *>(slot + kTileO + 2 * rowB + ob) = v;
+                        v.x = plo(Bc[0], Bc[1]); v.y = plo(Bc[2], Bc[3]); *reinterpret_cast<uint2 *>(slot + 2 * kTileO + 2 * rowA + ob) = v;
+                        v.x = phi(Bc[0], Bc[1]); v.y = phi(Bc[2], Bc[3]); *reinterpret_cast<uint2 *>(slot + 2 * kTileO + 2 * rowB + ob) = v;
                     } else {
 #pragma unroll
                         for (int p = 0; p < NP; p++) {
@@ -467,8 +500,8 @@ FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane, in
                                 for (int i = 0; i < 4; i++) o4[i] = pk_clamp(o4[i], clo, chi);
                             }
                             uint2 v;
-                            v.x = plo(o4[0], o4[1]); v.y = plo(o4[2], o4[3]); *reinterpret_cast<uint2 *>(sm_out + p * kTileO + lane * (4 * kHChunk) + ob) = v;
-                            v.x = phi(o4[0], o4[1]); v.y = phi(o4[2], o4[3]); *reinterpret_cast<uint2 *>(sm_out + p * kTileO + (lane + 32) * (4 * kHChunk) + ob) = v;
+                            v.x = plo(o4[0], o4[1]); v.y = plo(o4[2], o4[3]); *reinterpret_cast<uint2 *>(slot + p * kTileO + 2 * rowA + ob) = v;
+                            v.x = phi(o4[0], o4[1]); v.y = phi(o4[2], o4[3]); *reinterpret_cast<uint2 *>(slot + p * kTileO + 2 * rowB + ob) = v;
                         }
                     }
                 }
@@ -478,20 +511,22 @@ FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane, in
             fence_async_smem();
             fb_syncwarp();
             if (lane == 0) {
-                for (int p = 0; p < kNOut; p++) tile_store(&J.tm_o[p], 2 * xc, row0, sm_out + p * kTileO);
+                for (int p = 0; p < kNOut; p++) tile_store(&J.tm_o[p], 2 * xc, row0, slot + p * kTileO);
                 store_commit();
             }
+        } else {
+            fb_syncwarp();          // the warm-up chunk stores nothing, but its slot is refilled by lane 0 next
         }
     }
     // final state + range flag of this segment
     const bool bad = pk_chk_bad(chk_a, kMaxAvg) || pk_chk_bad(chk_r, kMaxRes);
 #pragma unroll
     for (int p = 0; p < NP; p++) {
-        if (row0 + lane < J.h) J.act[p][(size_t)g * J.h + row0 + lane] = (int16_t)(P[p] & 0xffffu);
-        if (row0 + lane + 32 < J.h) J.act[p][(size_t)g * J.h + row0 + lane + 32] = (int16_t)(P[p] >> 16);
+        if (row0 + lane < J.h) J.act[p][(size_t)(row0 + lane) * J.nsegp + g] = (int16_t)(P[p] & 0xffffu);
+        if (row0 + lane + 32 < J.h) J.act[p][(size_t)(row0 + lane + 32) * J.nsegp + g] = (int16_t)(P[p] >> 16);
     }
-    if (row0 + lane < J.h) J.bad[(size_t)g * J.h + row0 + lane] = bad ? 1 : 0;
-    if (row0 + lane + 32 < J.h) J.bad[(size_t)g * J.h + row0 + lane + 32] = bad ? 1 : 0;
+    if (row0 + lane < J.h) J.bad[(size_t)(row0 + lane) * J.nsegp + g] = bad ? 1 : 0;
+    if (row0 + lane + 32 < J.h) J.bad[(size_t)(row0 + lane + 32) * J.nsegp + g] = bad ? 1 : 0;
     if (bad) atomicAdd(J.stats + 1, 1);
     if (lane == 0) store_wait_all();                            // this segment's tiles are in global memory
     fb_threadfence();
@@ -509,9 +544,10 @@ FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane, in
     }
 }
 
-// All jobs of a launch have the same (NP, EP).  A warp's slice of shared memory: kHStages input stages, the output tiles, the mbarriers.
+// All jobs of a launch have the same (NP, EP).  One warp per block (the blocks of an SM are independent pipelines that the
+// block scheduler keeps refilling); its shared memory: two slots + the mbarriers.
 template <int NP, int EP>
-FB_KERNEL(384) k_pk_hsq(const FB_GRID_CONSTANT HJobs jobs, int warps_per_block, int smem_per_warp) {
+FB_KERNEL(32) k_pk_hsq(const FB_GRID_CONSTANT HJobs jobs, int warps_per_block, int smem_per_warp) {
     FB_DYN_SMEM(smraw);
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
     unsigned char *sm = smraw + ((128 - (int)(reinterpret_cast<uintptr_t>(smraw) & 127)) & 127) + (size_t)warp * smem_per_warp;
@@ -522,15 +558,14 @@ FB_KERNEL(384) k_pk_hsq(const FB_GRID_CONSTANT HJobs jobs, int warps_per_block, 
     const HJob &J = jobs.j[ji];
     const int local = item - J.item0, rb = local / J.nseg, g = local - rb * J.nseg;
     constexpr int kStage = NP * 2 * kHRows * kHChunk * 2 + (EP == fq::kEpYCoCg ? kHRows * 2 * kHChunk * 2 : 0);
-    constexpr int kNOut = EP == fq::kEpYCoCg ? 3 : NP;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + kHStages * kStage + kNOut * kHRows * 2 * kHChunk * 2);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + 2 * kStage);
     if (lane == 0) {
-        for (int s = 0; s < kHStages; s++) mbar_init(&bars[s], 1);
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
         fence_mbar_init();
     }
     fb_syncwarp();
-    int par = 0;
-    h_item<NP, EP>(J, rb, g, sm, lane, par);
+    h_item<NP, EP>(J, rb, g, sm, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -547,6 +582,7 @@ struct VJob {                   // one vertical step on one plane
     int S, nseg, ncg;           // pairs per segment, segments per column, column groups of 256
     int item0;
     int do_clamp, lo, hi;
+    uint32_t k1;                // 0x00010001 (see PK)
 };
 struct VJobs { VJob j[kMaxVJobs]; int n, items; };
 
@@ -569,6 +605,16 @@ FB_DEV void v_repair(const VJob &J, int x, int g, int *prev) {
 }
 
 FB_DEV void v_verify(const VJob &J, int x) {
+    int dirty = 0;
+#pragma unroll 8
+    for (int g = 0; g < J.nseg; g++) {          // independent loads: a few round trips when everything joins
+        dirty |= J.bad[(size_t)g * (J.w >> 3) + (x >> 3)];
+        if (g > 0) {
+            const uint4 e = *reinterpret_cast<const uint4 *>(J.est + (size_t)g * J.w + x), a = *reinterpret_cast<const uint4 *>(J.act + (size_t)(g - 1) * J.w + x);
+            dirty |= (int)((e.x ^ a.x) | (e.y ^ a.y) | (e.z ^ a.z) | (e.w ^ a.w));
+        }
+    }
+    if (!dirty) return;
     int cur[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int g = 0; g < J.nseg; g++) {
         bool need = J.bad[(size_t)g * (J.w >> 3) + (x >> 3)] != 0;
@@ -590,6 +636,7 @@ FB_DEV void v_item(const VJob &J, int cg, int g, int lane) {
     const int q_own = g * J.S, q_end = fq::imin(q_own + J.S, J.ha);
     const int q_first = g ? q_own - kVWarm : 0;
     const uint32_t clo = (uint32_t)(uint16_t)J.lo * 0x00010001u, chi = (uint32_t)(uint16_t)J.hi * 0x00010001u;
+    const PK K = pk_consts(J.k1);
     if (active) {
         uint32_t P[4], chk_a = 0, chk_r = 0;
         uint4 A[kVDepth + 1], R[kVDepth];
@@ -622,7 +669,7 @@ FB_DEV void v_item(const VJob &J, int cg, int g, int lane) {
                         chk_a = pk_chk(chk_a, aw[k], kMaxAvg * 0x00010001u);
                         if (q == q_end - 1) chk_a = pk_chk(chk_a, nw[k], kMaxAvg * 0x00010001u);     // a row the next segment owns
                         chk_r = pk_chk(chk_r, rw[k], kMaxRes * 0x00010001u);
-                        pk_step(P[k], aw[k], pneg(aw[k]), pneg(nw[k]), rw[k], oa[k], ob[k]);
+                        pk_step(K, P[k], aw[k], pneg(aw[k], K), pneg(nw[k], K), rw[k], oa[k], ob[k]);
                         P[k] = ob[k];
                         if (J.do_clamp) { oa[k] = pk_clamp(oa[k], clo, chi); ob[k] = pk_clamp(ob[k], clo, chi); }
                     }

@@ -941,7 +941,8 @@ static int pk_run_step(fb_ctx *ctx, const std::vector<ps::StepOp> &ops, bool hor
 // ---------------------------------------------------------------------------------------------------------
 namespace {
 __device__ __forceinline__ unsigned st_rng(unsigned &s) { s = s * 1664525u + 1013904223u; return s >> 8; }
-__global__ void k_pk_selftest(int which, unsigned seed, int scale, int maxval, int iters, int *mism) {
+__global__ void k_pk_selftest(int which, unsigned seed, int scale, int maxval, int iters, unsigned one, int *mism) {
+    const ps::PK K = ps::pk_consts(one);
     unsigned s = seed ^ (blockIdx.x * 9781u + threadIdx.x * 6271u + 1u);
     int bad = 0;
     for (int it = 0; it < iters; it++) {
@@ -959,7 +960,7 @@ __global__ void k_pk_selftest(int which, unsigned seed, int scale, int maxval, i
         auto pk = [&](int i) { return (uint32_t)(uint16_t)v[0][i] | ((uint32_t)(uint16_t)v[1][i] << 16); };
         if (which == 0) {
             uint32_t A, B;
-            ps::pk_step(pk(0), pk(1), ps::pneg(pk(1)), ps::pneg(pk(2)), pk(3), A, B);
+            ps::pk_step(K, pk(0), pk(1), ps::pneg(pk(1), K), ps::pneg(pk(2), K), pk(3), A, B);
             for (int k = 0; k < 2; k++) {
                 int A2, B2;
                 fq::unsqueeze_pair(v[k][0], v[k][1], v[k][2], v[k][3], A2, B2);
@@ -972,7 +973,7 @@ __global__ void k_pk_selftest(int which, unsigned seed, int scale, int maxval, i
             for (int k = 0; k < 2; k++) { y[k] = (int)(short)st_rng(s); co[k] = (int)(st_rng(s) % 16379) - 8189; cg[k] = (int)(st_rng(s) % 16379) - 8189; }
             uint32_t R, G, B;
             const uint32_t mv = (uint32_t)(uint16_t)maxval * 0x00010001u;
-            ps::pk_ycocg((uint32_t)(uint16_t)y[0] | ((uint32_t)(uint16_t)y[1] << 16), (uint32_t)(uint16_t)co[0] | ((uint32_t)(uint16_t)co[1] << 16),
+            ps::pk_ycocg(K, (uint32_t)(uint16_t)y[0] | ((uint32_t)(uint16_t)y[1] << 16), (uint32_t)(uint16_t)co[0] | ((uint32_t)(uint16_t)co[1] << 16),
                          (uint32_t)(uint16_t)cg[0] | ((uint32_t)(uint16_t)cg[1] << 16), mv, R, G, B);
             for (int k = 0; k < 2; k++) {
                 int R2, G2, B2;
@@ -1001,7 +1002,7 @@ extern "C" FB_API int fb_selftest_packed(fb_ctx *ctx, int which, unsigned seed, 
     int *d = nullptr;
     FB_CUDA(ctx, cudaMalloc((void **)&d, sizeof(int)));
     FB_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(int), ctx->stream));
-    k_pk_selftest<<<296, 256, 0, ctx->stream>>>(which, seed, scale, maxval, 64, d);
+    k_pk_selftest<<<296, 256, 0, ctx->stream>>>(which, seed, scale, maxval, 64, 0x00010001u, d);
     ctx->launches++;
     int h = 0;
     FB_CUDA(ctx, cudaMemcpyAsync(&h, d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -339,7 +339,8 @@ int emu_check_pk_pair(const int16_t *prev, const int16_t *av, const int16_t *nx,
     for (int i = 0; i + 1 < n; i += 2) {
         const uint32_t P = ps::e_h(prev[i], prev[i + 1]), a = ps::e_h(av[i], av[i + 1]), nn = ps::e_h(nx[i], nx[i + 1]), r = ps::e_h(rs[i], rs[i + 1]);
         uint32_t A, B;
-        ps::pk_step(P, a, ps::pneg(a), ps::pneg(nn), r, A, B);
+        const ps::PK K = ps::pk_consts(0x00010001u);
+        ps::pk_step(K, P, a, ps::pneg(a, K), ps::pneg(nn, K), r, A, B);
         for (int k = 0; k < 2; k++) {
             int A2, B2;
             fq::unsqueeze_pair(prev[i + k], av[i + k], nx[i + k], rs[i + k], A2, B2);
@@ -356,7 +357,7 @@ int emu_check_pk_ycocg(const int16_t *y, const int16_t *co, const int16_t *cg, i
     const uint32_t mv = (uint32_t)(uint16_t)maxval * 0x00010001u;
     for (int i = 0; i + 1 < n; i += 2) {
         uint32_t R, G, B;
-        ps::pk_ycocg(ps::e_h(y[i], y[i + 1]), ps::e_h(co[i], co[i + 1]), ps::e_h(cg[i], cg[i + 1]), mv, R, G, B);
+        ps::pk_ycocg(ps::pk_consts(0x00010001u), ps::e_h(y[i], y[i + 1]), ps::e_h(co[i], co[i + 1]), ps::e_h(cg[i], cg[i + 1]), mv, R, G, B);
         for (int k = 0; k < 2; k++) {
             int R2, G2, B2;
             ps::ycocg_exact(y[i + k], co[i + k], cg[i + k], maxval, 0, 0, 0, R2, G2, B2);
