@@ -41,6 +41,10 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-index", action="store_true", help="decode without the group-offset sidecar (one stream per image)")
+    ap.add_argument("--no-index-steps", type=int, default=1,
+                    help="besides the main (indexed) measurement, time this many steps WITHOUT the sidecar and report value_no_index / e2e_no_index (0 = skip)")
+    ap.add_argument("--distinct-images", action="store_true", help="weak scaling with a different image (seed) on every rank instead of replicas of the same one")
+    ap.add_argument("--strong", action="store_true", help="multi-image workloads (cfg4): split the fixed batch over the ranks (strong scaling)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -101,8 +105,12 @@ def run_reference(args, rank, world):
     import bench_workloads as wl
     if rank != 0:
         return
-    n_img = max(1, args.gpus) * wl.WORKLOADS[args.workload][5]
-    imgs = wl.prepare_images(args.workload, range(n_img), want_index=False)
+    per = wl.WORKLOADS[args.workload][5]
+    n_img = per if args.strong else max(1, args.gpus) * per
+    seeds = range(n_img) if (args.distinct_images or args.strong) else [u % per for u in range(n_img)]     # replicas: the same image(s) for every GPU
+    imgs = wl.prepare_images(args.workload, sorted(set(seeds)), want_index=False)
+    by_seed = {u: im for u, im in zip(sorted(set(seeds)), imgs)}
+    imgs = [by_seed[u] for u in seeds]
     mpix = sum(im["w"] * im["h"] for im in imgs) / 1e6
     use_ref = wl.have_ref_driver()
 
@@ -164,8 +172,16 @@ def main():
 
     # ---- workload: one image per GPU (weak scaling, no data-path collective: files are independent units)
     spec = wl.WORKLOADS[args.workload]
-    n_per_gpu = spec[5]
-    units = shard.units_for_rank(n_per_gpu, rank)
+    if args.strong:                 # a fixed batch split over the ranks (BASELINE config 4: 64 images over 8 GPUs)
+        units = shard.split_batch(spec[5], rank, world)
+        scaling = "strong"
+    elif args.distinct_images:      # weak scaling, a different image on every rank
+        units = shard.units_for_rank(spec[5], rank)
+        scaling = "weak"
+    else:                           # weak scaling, every rank decodes its own copy of the same image(s): the per-GPU work is identical
+        units = shard.replica_units(spec[5])
+        scaling = "weak"
+    n_per_gpu = len(units)
     imgs = wl.prepare_images(args.workload, units, want_index=not args.no_index)
     w, h, c, maxval = spec[0], spec[1], spec[2], spec[3]
     mpix_rank = n_per_gpu * w * h / 1e6
@@ -183,15 +199,16 @@ def main():
     pin_out = [torch.empty((h, w, c), dtype=(torch.int16 if bps == 2 else torch.uint8)).pin_memory() for _ in imgs]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
-    def step_value(ev=None):
+    def step_value(ev=None, indexed=True):
         """decode + undo_transforms, inputs and outputs in HBM. ev: optional (start, mid, end) CUDA events."""
+        use_idx = indexed and not args.no_index
         if ev:
             ev[0].record(stream)
         if len(imgs) == 1:
-            out = [api.fuif_decode((dev_bytes[0].data_ptr(), dev_bytes[0].numel()), ctx=ctx, group_index=imgs[0]["index"])]
+            out = [api.fuif_decode((dev_bytes[0].data_ptr(), dev_bytes[0].numel()), ctx=ctx, group_index=imgs[0]["index"] if use_idx else None)]
         else:       # a batch: every (image, group) is a stream of ONE launch
             out = api.fuif_decode_batch([(db.data_ptr(), db.numel()) for db in dev_bytes], ctx=ctx,
-                                        group_indexes=None if args.no_index else [im["index"] for im in imgs])
+                                        group_indexes=[im["index"] for im in imgs] if use_idx else None)
         if ev:
             ev[1].record(stream)
         for o in out:
@@ -200,13 +217,14 @@ def main():
             ev[2].record(stream)
         return out
 
-    def step_e2e():
+    def step_e2e(indexed=True):
+        use_idx = indexed and not args.no_index
         if len(imgs) == 1:
             arr = np.frombuffer(memoryview(pin_bytes[0].numpy()), dtype=np.uint8)
-            api.decode_to_pixels(arr, ctx=ctx, group_index=imgs[0]["index"], out=pin_out[0].numpy())
+            api.decode_to_pixels(arr, ctx=ctx, group_index=imgs[0]["index"] if use_idx else None, out=pin_out[0].numpy())
             return
         res_ = api.fuif_decode_batch([np.frombuffer(memoryview(pb.numpy()), dtype=np.uint8) for pb in pin_bytes], ctx=ctx,
-                                     group_indexes=None if args.no_index else [im["index"] for im in imgs])
+                                     group_indexes=[im["index"] for im in imgs] if use_idx else None)
         for o in res_:
             o.undo_transforms(0)
         for o, po_ in zip(res_, pin_out):
@@ -244,12 +262,15 @@ def main():
     ctx.enable_kernel_timing(True)      # one CUDA event after every launch of the library (on its stream)
     ctx.timing_report()
     kernel_us = {}
+    launch_seq = []         # per step: [(name, us, bytes)] in launch order
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()
         r = step_value(evs[k])
         del r
-        for name, us, nbytes in ctx.timing_report():       # synchronises the stream
+        rep = ctx.timing_report()                           # synchronises the stream
+        launch_seq.append(rep)
+        for name, us, nbytes in rep:
             kernel_us.setdefault(name, []).append((us, nbytes))
     ctx.enable_kernel_timing(False)
     torch.cuda.synchronize()
@@ -263,6 +284,14 @@ def main():
     total_ms, total_units = shard.reduce_step_time(sum(step_ms), len(units), device="cuda")
     ms_per_step = total_ms / args.steps
     value = total_units * (w * h / 1e6) / (ms_per_step / 1e3)
+    # every rank's own stage times (the max over ranks above hides which rank / stage is the slow one)
+    mine = torch.tensor([sum(dec_ms) / len(dec_ms), sum(chain_ms) / len(chain_ms), sum(step_ms) / len(step_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+    else:
+        allr = [mine]
+    per_rank = [{"rank": i, "entropy_ms": float(t[0]), "transform_chain_ms": float(t[1]), "step_ms": float(t[2])} for i, t in enumerate(allr)]
 
     # ---- e2e: host buffers through the C-ABI convenience call
     for _ in range(min(args.warmup, 1)):
@@ -282,6 +311,33 @@ def main():
             got = got.view(">u2")
         assert np.array_equal(got.astype(np.int32), synth_image(w, h, c, maxval, spec_seed0)), "e2e pixels differ"
 
+    # ---- the same workload WITHOUT the group-offset sidecar (one stream per file, as the bare format dictates): a bounded sample
+    no_index = None
+    if not args.no_index and args.no_index_steps > 0:
+        ev_n = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.no_index_steps)]
+        barrier()
+        for k in range(args.no_index_steps):
+            flush.zero_()
+            r = step_value(ev_n[k], indexed=False)
+            del r
+        torch.cuda.synchronize()
+        ni_ms, _ = shard.reduce_step_time(sum(e[0].elapsed_time(e[2]) for e in ev_n), len(units), device="cuda")
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.no_index_steps):
+            step_e2e(indexed=False)
+        torch.cuda.synchronize()
+        ni_e2e, _ = shard.reduce_step_time((time.perf_counter() - t0) * 1e3, len(units), device="cuda")
+        if lossless:
+            got = pin_out[0].numpy()
+            if bps == 2:
+                got = got.view(">u2")
+            assert np.array_equal(got.astype(np.int32), synth_image(w, h, c, maxval, spec_seed0)), "un-indexed e2e pixels differ"
+        no_index = {"value": total_units * (w * h / 1e6) / (ni_ms / 1e3 / args.no_index_steps),
+                    "e2e": total_units * (w * h / 1e6) / (ni_e2e / 1e3 / args.no_index_steps), "unit": "Mpx/s", "steps": args.no_index_steps,
+                    "ms_per_step": ni_ms / args.no_index_steps,
+                    "what": "same workload, no sidecar: the channel groups of a file decode back to back on one SM (group offsets are not in the bitstream)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -298,37 +354,44 @@ def main():
     chain_gbs = alg_bytes / (chain_mean_ms / 1e3) / 1e9
     per_kernel = {name: {"launches_per_step": len(v) / args.steps, "mean_us": sum(u for u, _ in v) / len(v),
                          "us_per_step": sum(u for u, _ in v) / args.steps, "algorithmic_bytes": v[0][1]} for name, v in kernel_us.items()}
-    # dominant kernel of the chain = the launch of the library with the largest time per step among those whose
-    # algorithmic bytes the library accounts (the MANIAC launch is not on a bandwidth roofline)
+    # dominant kernel of the chain = the single launch of the inverse transform chain with the largest mean duration (position by
+    # position in the launch sequence of a step; the MANIAC launch is not on a bandwidth roofline)
     KERNEL_DOC = {
-        "k_inv_hsq_direct(ycocg)": "final horizontal unsqueeze step of Co and Cg fused with inverse YCoCg + clamp (reads Co/Cg averages and "
-                                   "residuals + Y, writes R, G, B): its algorithmic bytes equal the image's 4*W*H*C",
-        "k_inv_hsq_direct": "one horizontal unsqueeze step, all planes of the step in one launch",
-        "k_inv_vsq_direct": "one vertical unsqueeze step, all planes of the step in one launch",
+        "k_pk_hsq(ycocg)": "final horizontal unsqueeze step of Co and Cg fused with inverse YCoCg + clamp, packed int16x2, TMA-fed tiles (reads the "
+                           "Co/Cg averages and residuals + Y, writes R, G, B): its algorithmic bytes equal the image's 4*W*H*C",
+        "k_pk_hsq": "one horizontal unsqueeze step (packed int16x2, TMA-fed tiles), all planes of the step in one launch",
+        "k_pk_vsq": "one vertical unsqueeze step (packed int16x2, 16-byte coalesced accesses), all planes of the step in one launch",
+        "k_inv_hsq_direct(ycocg)": "final horizontal unsqueeze step of Co and Cg fused with inverse YCoCg + clamp (32-bit kernel)",
+        "k_inv_hsq_direct": "one horizontal unsqueeze step, all planes of the step in one launch (32-bit kernel)",
+        "k_inv_vsq_direct": "one vertical unsqueeze step, all planes of the step in one launch (32-bit kernel)",
         "k_fq_tiles(last)": "final unsqueeze steps of every plane + inverse YCoCg + clamp, one fused tile kernel",
+        "k_idct_ycbcr": "dequantise + 8x8 inverse DCT + inverse YCbCr + clamp of all three components in one launch",
     }
-    cand = [(sum(u for u, _ in v) / args.steps, name) for name, v in kernel_us.items() if v[0][1] and v[0][1] > 0 and "maniac" not in name]
-    dom_name = max(cand)[1] if cand else None
+    nl = min(len(r) for r in launch_seq) if launch_seq else 0
+    same_seq = nl > 0 and all(len(r) == nl and [x[0] for x in r] == [x[0] for x in launch_seq[0]] for r in launch_seq)
+    launches_ranked = []
+    if same_seq:
+        for pos in range(nl):
+            name = launch_seq[0][pos][0]
+            us = sum(r[pos][1] for r in launch_seq) / len(launch_seq)
+            launches_ranked.append({"pos": pos, "name": name, "us": us, "algorithmic_bytes": launch_seq[0][pos][2]})
+    chain_launches = [x for x in launches_ranked if "maniac" not in x["name"]]
+    cand = [x for x in chain_launches if x["algorithmic_bytes"] > 0]
+    dom = max(cand, key=lambda x: x["us"]) if cand else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath) and dom_name:
-        traffic = json.load(open(tpath)).get(args.workload, {}).get(dom_name)
-    dom = kernel_us.get(dom_name) if dom_name else None
-    if dom and dom[0][1] > 0:
-        # several launches of that name per step (one per squeeze step): the roofline is quoted for the largest one
-        per_step = len(dom) // args.steps
-        big = max(range(per_step), key=lambda i: dom[i][1]) if per_step > 1 else 0
-        sel = [dom[k * per_step + big] for k in range(args.steps)] if per_step >= 1 else dom
-        us = sum(u for u, _ in sel) / len(sel)
-        kbytes = sel[0][1]
-        achieved = kbytes / (us * 1e-6) / 1e9
-        roofline = {"bound": "hbm", "kernel": f"{dom_name}: {KERNEL_DOC.get(dom_name, '')}",
+    if os.path.exists(tpath) and dom:
+        traffic = json.load(open(tpath)).get(args.workload, {}).get(dom["name"])
+    if dom:
+        achieved = dom["algorithmic_bytes"] / (dom["us"] * 1e-6) / 1e9
+        roofline = {"bound": "hbm", "kernel": f"{dom['name']}: {KERNEL_DOC.get(dom['name'], '')}",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "algorithmic_bytes": kbytes, "us": us, "share_of_chain": us / (chain_mean_ms * 1e3),
+                    "algorithmic_bytes": dom["algorithmic_bytes"], "us": dom["us"], "share_of_chain": dom["us"] / (chain_mean_ms * 1e3),
                     "peak_source": peak_src,
                     "chain": {"what": "whole Image::undo_transforms (all launches), 4*W*H*C algorithmic bytes", "ms": chain_mean_ms,
-                              "achieved": chain_gbs, "frac": chain_gbs / peak}}
-    else:       # chains without an accounted Squeeze launch (e.g. the DCT chain): the whole chain
+                              "achieved": chain_gbs, "frac": chain_gbs / peak, "launches": len(chain_launches)},
+                    "chain_launches": [{"name": x["name"], "us": round(x["us"], 2), "MB": round(x["algorithmic_bytes"] / 1e6, 2)} for x in chain_launches]}
+    else:       # no accounted launch: the whole chain
         roofline = {"bound": "hbm", "kernel": "inverse transform chain (Image::undo_transforms, all launches)",
                     "achieved": chain_gbs, "peak": peak, "unit": "GB/s", "frac": chain_gbs / peak, "traffic": None,
                     "algorithmic_bytes": alg_bytes, "ms": chain_mean_ms, "peak_source": peak_src}
@@ -362,19 +425,25 @@ def main():
 
     line = {
         "metric": "decode Mpixels/s (bit-exact)", "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {spec[7]}", "images_per_gpu": n_per_gpu, "width": w, "height": h, "channels": c,
-                   "group_index_sidecar": not args.no_index, "l2": "256 MiB buffer written between timed steps", "parallelism": f"one image per GPU x{world}",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {spec[7]}", "images": n_per_gpu if scaling == "weak" else spec[5], "images_per_gpu": n_per_gpu,
+                   "width": w, "height": h, "channels": c,
+                   "group_index_sidecar": not args.no_index, "group_index_source": None if args.no_index else imgs[0].get("index_source"),
+                   "l2": "256 MiB buffer written between timed steps",
+                   "parallelism": (f"fixed batch of {spec[5]} images split over {world} GPU(s)" if scaling == "strong" else
+                                   f"{n_per_gpu} image(s) per GPU x{world}" + ("" if args.distinct_images else " (replicas of the same image(s))")),
                    "bit_exact_checked": exact},
+        "value_no_index": no_index["value"] if no_index else None, "e2e_no_index": no_index["e2e"] if no_index else None, "no_index": no_index,
         "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": int(sum(len(im["fuif"]) for im in imgs)),
                 "d2h_bytes_per_step": int(n_per_gpu * w * h * c * bps)},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "per_rank": per_rank,
         "stages": {"entropy_ms": sum(dec_ms) / len(dec_ms), "transform_chain_ms": chain_mean_ms, "wall_s_timed_region": t_wall,
                    "transform_chain_mpx_s": mpix_rank / (chain_mean_ms / 1e3), "kernels": per_kernel,
-                   "unsqueeze_repaired_tiles": ctx.repaired_tiles, "unsqueeze_serial_fallbacks": ctx.fallbacks},
+                   "unsqueeze_repaired_segments": ctx.pk_repaired, "unsqueeze_range_flagged_segments": ctx.pk_range_flagged},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -5,9 +5,9 @@ Benchmark infrastructure, not product code (it lives outside the fuif_b200 packa
 of the decode hot path that is being measured: files are produced by the reference's own encoder (the prebuilt
 oracle/_ref/ref_driver travels with the repository to the GPU box), which also makes the inputs independent of this
 repository's code.  The "group index" sidecar (byte offset of every channel group, 61 integers for a 4096x4096 image) is
-what an encoder knows for free when it writes the file; for reference-encoded files it is recovered ONCE by a sequential
-decode on the GPU (fb_image_group_index) -- or, in the GPU-less build container, by the CPU oracle -- and cached next to
-the file.
+what an encoder knows for free when it writes the file.  It always comes out of the PRODUCT: fb_encode on the same pixels (which writes the very file the reference
+encoder wrote, byte for byte, and returns the offsets) or one sequential decode + fb_image_group_index, once, outside
+the timed region, cached next to the file with its source and cost.  bench.py reports the un-indexed decode as well.
 """
 from __future__ import annotations
 
@@ -65,32 +65,51 @@ def prepare_image(name: str, seed_offset: int = 0, want_index: bool = True) -> d
         os.remove(pnm)      # the pixels are regenerated from the seed when a check needs them
     with open(fuif, "rb") as f:
         data = f.read()
-    out = {"fuif": data, "w": w, "h": h, "c": c, "maxval": maxval, "pnm": pnm, "fuif_path": fuif, "index": None}
+    out = {"fuif": data, "w": w, "h": h, "c": c, "maxval": maxval, "pnm": pnm, "fuif_path": fuif, "index": None, "index_source": None}
     if want_index:
+        j = None
         if os.path.exists(idx):
             with open(idx) as f:
                 j = json.load(f)
-        else:
-            t0 = time.perf_counter()
-            import torch
-            if torch.cuda.is_available():       # one sequential decode by the library itself
-                from fuif_b200 import api
-                ictx = api.Context(torch.cuda.current_device())      # this rank's GPU (N ranks must not all queue on device 0)
-                seq = api.fuif_decode(data, ctx=ictx)
-                offs_, first_ = seq.group_index()
-                del seq
-                ictx.close()
-                j = {"offsets": [int(a) for a in offs_], "first": [int(b) for b in first_], "source": "fb_image_group_index", "decode_s": time.perf_counter() - t0}
-            else:                               # build container without a GPU
-                from oracle import pyoracle as po
-                _img, offs = po.OracleImage.decode(data, want_offsets=True)
-                del _img
-                j = {"offsets": [int(a) for a, _ in offs], "first": [int(b) for _, b in offs], "source": "oracle", "decode_s": time.perf_counter() - t0}
+            if not str(j.get("source", "")).startswith("fb_"):     # an index that did not come out of the product is not used
+                j = None
+        if j is None:
+            j = product_index(data, w, h, c, maxval, seed, opts)
             with open(idx + f".tmp{os.getpid()}", "w") as f:
                 json.dump(j, f)
             os.replace(idx + f".tmp{os.getpid()}", idx)
         out["index"] = (j["offsets"], j["first"])
+        out["index_source"] = f"{j['source']} ({j.get('cost_s', 0):.1f} s, once, outside the timed region)"
     return out
+
+
+def product_index(data: bytes, w: int, h: int, c: int, maxval: int, seed: int, opts) -> dict:
+    """The group-offset sidecar, made by the PRODUCT (never by the oracle): either by its encoder -- fb_encode on the same pixels
+    writes the very file the reference encoder wrote and knows where every group starts -- or, for chains fb_encode is not
+    asked to build here, by one sequential decode + fb_image_group_index.  FUIF_B200_INDEX=decode forces the second way."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("the group index is produced by the library on a GPU (fb_encode / fb_image_group_index); no CUDA device here")
+    from fuif_b200 import api
+    ictx = api.Context(torch.cuda.current_device())      # this rank's GPU (N ranks must not all queue on device 0)
+    try:
+        t0 = time.perf_counter()
+        how = os.environ.get("FUIF_B200_INDEX", "encode" if (not opts and w * h <= 2048 * 2048) else "decode")
+        if how == "encode":
+            img = api.Image.from_pixels(synth_image(w, h, c, maxval, seed), maxval, ictx)
+            img.recompute_minmax()
+            for tid in ((1, 7) if c >= 3 else (7,)):
+                assert img.do_transform(api.Transform(tid, []))
+            mine, index = api.fuif_encode(img, api.fuif_options(max_group=1, predictor=[2, 2, 2, 0]), want_index=True)
+            if mine == data:        # byte-identical to the reference encoder's file: its offsets are this file's offsets
+                return {"offsets": [int(a) for a in index[0]], "first": [int(b) for b in index[1]], "source": "fb_encode", "cost_s": time.perf_counter() - t0}
+        seq = api.fuif_decode(data, ctx=ictx)
+        offs_, first_ = seq.group_index()
+        del seq
+        return {"offsets": [int(a) for a in offs_], "first": [int(b) for b in first_], "source": "fb_image_group_index after one sequential decode",
+                "cost_s": time.perf_counter() - t0}
+    finally:
+        ictx.close()
 
 
 def prepare_images(name: str, seed_offsets, want_index: bool = True, workers: int = 32) -> list:
@@ -114,8 +133,8 @@ def prepare_images(name: str, seed_offsets, want_index: bool = True, workers: in
                 offs_, first_ = im.group_index()
                 idx = _paths(name, WORKLOADS[name][4] + u)[2]
                 with open(idx, "w") as f:
-                    json.dump({"offsets": [int(a) for a in offs_], "first": [int(b) for b in first_], "source": "fb_image_group_index (batch)",
-                               "decode_s": time.perf_counter() - t0}, f)
+                    json.dump({"offsets": [int(a) for a in offs_], "first": [int(b) for b in first_], "source": "fb_image_group_index after one batched sequential decode",
+                               "cost_s": time.perf_counter() - t0}, f)
     return [prepare_image(name, seed_offset=u, want_index=want_index) for u in seed_offsets]
 
 

@@ -81,13 +81,12 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
             taken[ico] = taken[icg] = 1;
             P.epilogue_done = true;
         }
+        // every other plane is a job of its own in ONE launch (one chain per lane, but twice the warps of a paired job fit an SM,
+        // and luma and chroma of a step run side by side instead of one launch after the other)
         for (int i = 0; i < n; i++) {
             if (taken[i] || !h_eligible(ops[i])) continue;
-            int mate = -1;
-            for (int k = i + 1; k < n; k++) if (!taken[k] && h_eligible(ops[k]) && same(ops[i], ops[k])) { mate = k; break; }
-            pend.push_back(Pend{i, mate, ops[i].clamp ? fq::kEpClamp : fq::kEpNone});
+            pend.push_back(Pend{i, -1, ops[i].clamp ? fq::kEpClamp : fq::kEpNone});
             taken[i] = 1;
-            if (mate >= 0) taken[mate] = 1;
         }
         // one launch per (np, epilogue) class
         for (int cls = 0; cls < 6; cls++) {
@@ -102,7 +101,9 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
                 const int wps = h_warps_per_sm(np, epk);
                 long long total_rb = 0;
                 for (size_t j = j0; j < j1; j++) total_rb += (ops[mine[j].i0].ha + kHRows - 1) / kHRows;
-                long long nseg_want = ((long long)sm_count * wps) / (total_rb > 0 ? total_rb : 1);
+                // one round of items: at most wps warps per SM fit, 8 (two per scheduler, each with its planes as independent
+                // chains) are enough to keep the integer pipes busy -- beyond that shorter segments only add warm-up work
+                long long nseg_want = ((long long)sm_count * (wps < 8 ? wps : 8)) / (total_rb > 0 ? total_rb : 1);
                 if (nseg_want < 1) nseg_want = 1;
                 int items = 0;
                 bool ok = true;
@@ -112,7 +113,7 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
                     const int i1 = mine[j].i1;
                     int S = (int)((a.wa + nseg_want - 1) / nseg_want);
                     S = (S + kHChunk - 1) / kHChunk * kHChunk;
-                    if (S < 2 * kHChunk) S = 2 * kHChunk;
+                    if (S < kHChunk) S = kHChunk;
                     J.np = np; J.wa = a.wa; J.h = a.ha; J.S = S; J.nseg = (a.wa + S - 1) / S; J.nrb = (a.ha + kHRows - 1) / kHRows;
                     J.nsegp = (J.nseg + 7) / 8 * 8;
                     J.item0 = items;
@@ -168,7 +169,7 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
             L.bytes = 0;
             long long total_cg = 0;
             for (size_t j = j0; j < j1; j++) total_cg += (ops[mine[j]].wa + 255) / 256;
-            long long nseg_want = ((long long)sm_count * 6) / (total_cg > 0 ? total_cg : 1);       // ~6 warps per SM, 4 chains each
+            long long nseg_want = ((long long)sm_count * 8) / (total_cg > 0 ? total_cg : 1);       // ~8 warps per SM, 4 chains each
             if (nseg_want < 1) nseg_want = 1;
             int items = 0;
             for (size_t j = j0; j < j1; j++) {
@@ -176,7 +177,7 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
                 VJob &J = L.jobs.j[L.jobs.n++];
                 int S = (int)((a.ha + nseg_want - 1) / nseg_want);
                 S = (S + 7) / 8 * 8;
-                if (S < 32) S = 32;
+                if (S < 16) S = 16;
                 while ((a.ha + S - 1) / S > 32) S += 8;        // the verification pass reads two 16-byte words per segment and lane
                 J.avg = a.avg; J.res = a.res; J.out = a.out; J.w = a.wa; J.ha = a.ha; J.S = S; J.nseg = (a.ha + S - 1) / S; J.ncg = (a.wa + 255) / 256;
                 J.item0 = items;

@@ -46,7 +46,7 @@ constexpr int kMaxRes = 4095;       // |B| <= 3*kMaxAvg + kMaxRes/2 + 1 = 8189, 
 constexpr int kHChunk = 16;         // pairs per TMA tile (32-byte rows)
 constexpr int kHRows = 64;          // rows per warp tile
 constexpr int kHWarm = kHChunk;     // warm-up pairs of a horizontal segment (one whole tile, nothing stored)
-constexpr int kVWarm = 8;           // warm-up pairs of a vertical segment
+constexpr int kVWarm = 12;          // warm-up pairs of a vertical segment (8 missed about once per 4096^2 image: a repair costs tens of microseconds)
 constexpr int kVDepth = 4;          // rows of register prefetch in the vertical kernel
 constexpr int kMaxHJobs = 8;
 constexpr int kMaxVJobs = 24;
@@ -381,8 +381,7 @@ FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane) {
         if (x_end < wa) {
             const int rA = fq::imin(row0 + lane, J.h - 1), rB = fq::imin(row0 + lane + 32, J.h - 1);
             a_end[p] = (uint32_t)(uint16_t)J.avg[p][(size_t)rA * wa + x_end] | ((uint32_t)(uint16_t)J.avg[p][(size_t)rB * wa + x_end] << 16);
-            chk_a = pk_chk(chk_a, a_end[p], kMaxAvg * 0x00010001u);
-        }
+        }                               // (range-checked where it is used, so that nothing waits for these loads here)
     }
     const bool do_clamp = J.do_clamp != 0;
     const PK K = pk_consts(J.k1);
@@ -442,21 +441,23 @@ FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane) {
                 if (row0 + lane + 32 < J.h) J.est[p][(size_t)(row0 + lane + 32) * J.nsegp + g - 1] = (int16_t)(P[p] >> 16);
             }
         }
-        // what the last pair of the chunk sees as its next average: own (row end, squeeze.h:93), the first average of the next
-        // chunk (already in the other slot), or the average after the segment (direct load above)
         uint32_t a_last[NP];
-        if (have_next) {
-            mbar_wait(&bars[(c + 1) & 1], ((c + 1) >> 1) & 1);
-#pragma unroll
-            for (int p = 0; p < NP; p++)
-                a_last[p] = plo(*reinterpret_cast<const uint32_t *>(nslot + p * 2 * kTileA + rowA), *reinterpret_cast<const uint32_t *>(nslot + p * 2 * kTileA + rowB));
-        } else {
-#pragma unroll
-            for (int p = 0; p < NP; p++) a_last[p] = a_end[p];
-        }
         fb_syncwarp();              // every lane holds its inputs: the slot may now receive the outputs
 #pragma unroll
         for (int k = 0; k < 8; k++) {                           // two pairs per iteration: one word of averages per row
+            if (k == 7) {
+                // what the last pair of the chunk sees as its next average: the first average of the next chunk (its tiles have had
+                // this chunk's computation to arrive in the other slot), or the average after the segment (direct load at the start)
+                if (have_next) {
+                    mbar_wait(&bars[(c + 1) & 1], ((c + 1) >> 1) & 1);
+#pragma unroll
+                    for (int p = 0; p < NP; p++)
+                        a_last[p] = plo(*reinterpret_cast<const uint32_t *>(nslot + p * 2 * kTileA + rowA), *reinterpret_cast<const uint32_t *>(nslot + p * 2 * kTileA + rowB));
+                } else {
+#pragma unroll
+                    for (int p = 0; p < NP; p++) { a_last[p] = a_end[p]; chk_a = pk_chk(chk_a, a_end[p], kMaxAvg * 0x00010001u); }
+                }
+            }
             if (2 * k < nsteps) {
                 uint32_t oA[NP][2], oB[NP][2];                  // [plane][pair]: packed (row l, row l+32)
 #pragma unroll
@@ -589,19 +590,38 @@ struct VJobs { VJob j[kMaxVJobs]; int n, items; };
 FB_DEV uint4 ld16(const int16_t *p) { return *reinterpret_cast<const uint4 *>(p); }
 FB_DEV void st16(int16_t *p, const uint4 &v) { *reinterpret_cast<uint4 *>(p) = v; }
 
-// exact recomputation of segment g of the 8 columns at x from the true state before it
+// exact recomputation of segment g of the 8 columns at x from the true state before it (16-byte accesses, the rows of the
+// next four pairs requested before the current four are computed)
 FB_DEV void v_repair(const VJob &J, int x, int g, int *prev) {
-    const int q0 = g * J.S, q1 = fq::imin(q0 + J.S, J.ha);
-    for (int q = q0; q < q1; q++)
-        for (int k = 0; k < 8; k++) {
-            const int av = J.avg[(size_t)q * J.w + x + k], nx = q + 1 < J.ha ? J.avg[(size_t)(q + 1) * J.w + x + k] : av;
-            int A, B;
-            fq::unsqueeze_pair(q == 0 ? av : prev[k], av, nx, J.res[(size_t)q * J.w + x + k], A, B);
-            prev[k] = B;
-            if (J.do_clamp) { A = fq::clampi(A, J.lo, J.hi); B = fq::clampi(B, J.lo, J.hi); }
-            J.out[(size_t)(2 * q) * J.w + x + k] = (int16_t)A;
-            J.out[(size_t)(2 * q + 1) * J.w + x + k] = (int16_t)B;
+    const int q0 = g * J.S, q1 = fq::imin(q0 + J.S, J.ha), last = J.ha - 1, w = J.w;
+    for (int qb = q0; qb < q1; qb += 4) {
+        uint4 A[5], R[4];
+#pragma unroll
+        for (int i = 0; i < 5; i++) A[i] = ld16(J.avg + (size_t)fq::imin(qb + i, last) * w + x);
+#pragma unroll
+        for (int i = 0; i < 4; i++) R[i] = ld16(J.res + (size_t)fq::imin(qb + i, last) * w + x);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int q = qb + i;
+            if (q >= q1) break;
+            const uint32_t aw[4] = {A[i].x, A[i].y, A[i].z, A[i].w}, nw[4] = {A[i + 1].x, A[i + 1].y, A[i + 1].z, A[i + 1].w}, rw[4] = {R[i].x, R[i].y, R[i].z, R[i].w};
+            uint32_t oa[4], ob[4];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int sh = 16 * (k & 1);
+                const int av = (int)(short)(aw[k >> 1] >> sh), nx = (int)(short)(nw[k >> 1] >> sh), rs = (int)(short)(rw[k >> 1] >> sh);     // row ha-1: A[i+1] re-reads it, next = own
+                int Av, Bv;
+                fq::unsqueeze_pair(q == 0 ? av : prev[k], av, nx, rs, Av, Bv);
+                prev[k] = Bv;
+                if (J.do_clamp) { Av = fq::clampi(Av, J.lo, J.hi); Bv = fq::clampi(Bv, J.lo, J.hi); }
+                if (k & 1) { oa[k >> 1] |= (uint32_t)(uint16_t)Av << 16; ob[k >> 1] |= (uint32_t)(uint16_t)Bv << 16; }
+                else { oa[k >> 1] = (uint32_t)(uint16_t)Av; ob[k >> 1] = (uint32_t)(uint16_t)Bv; }
+            }
+            uint4 v;
+            v.x = oa[0]; v.y = oa[1]; v.z = oa[2]; v.w = oa[3]; st16(J.out + (size_t)(2 * q) * w + x, v);
+            v.x = ob[0]; v.y = ob[1]; v.z = ob[2]; v.w = ob[3]; st16(J.out + (size_t)(2 * q + 1) * w + x, v);
         }
+    }
 }
 
 FB_DEV void v_verify(const VJob &J, int x) {

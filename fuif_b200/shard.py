@@ -9,6 +9,12 @@ def units_for_rank(n_units_per_rank: int, rank: int) -> list:
     return [rank * n_units_per_rank + i for i in range(n_units_per_rank)]
 
 
+def replica_units(n_units_per_rank: int) -> list:
+    """Weak scaling with replicas: every rank decodes its own copy of the same n_units_per_rank images, so the per-GPU work is
+    identical and the max over ranks measures the machine, not which image happened to land where."""
+    return list(range(n_units_per_rank))
+
+
 def split_batch(n_units: int, rank: int, world: int) -> list:
     """Strong scaling of a fixed batch: round-robin, the layout BASELINE config 4 (64 images over 8 GPUs) uses."""
     return list(range(rank, n_units, world))
