@@ -35,6 +35,10 @@ struct fb_ctx {
     int *pk_stats = nullptr;
     int pk_mode = 1;
     int sq_maxval = -1;         // maxval of the image whose Squeeze is being undone (packed kernels: 0 .. 1023 only)
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: the opt-ins are remembered per context (= per
+    // device), not per process, so that a context on a second GPU of the same process gets them too
+    unsigned smem_optin = 0;
+    enum { kOptHsqTiled = 1, kOptPyramid = 2, kOptDirect = 4, kOptFq = 8 };
     // FB_KERNEL_TIMING=1: a CUDA event after every launch, dumped by fb_ctx_synchronize (development aid)
     bool timing = false, timing_stderr = false;
     struct Mark { std::string name; cudaEvent_t ev; double bytes; };

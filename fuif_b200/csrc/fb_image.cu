@@ -7,7 +7,23 @@
 #include <string.h>
 
 #include <algorithm>
+#include <exception>
 #include <new>
+
+// Nothing may propagate through the C ABI: an exception inside an entry point (a failed host allocation while parsing an
+// untrusted file, ...) becomes an error code.
+template <class F>
+static int abi_guard(fb_ctx *ctx, F &&f) {
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        if (ctx) ctx->err = "out of host memory";
+        return FB_ERR_NOMEM;
+    } catch (const std::exception &e) {
+        if (ctx) ctx->err = std::string("internal error: ") + e.what();
+        return FB_ERR_INVALID;
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // context + plane memory
@@ -780,7 +796,11 @@ static int inv_permute(fb_image *img, const std::vector<int> &p) {
     const int m = img->info.nb_meta_channels, np = (int)p.size();
     if (np == 0) { img->ctx->err = "Permute through a meta-channel is not supported"; return FB_ERR_UNSUPPORTED; }
     if (np > (int)img->ch.size() - m) { img->ctx->err = "Permute: incorrect number of parameters"; return FB_ERR_INVALID; }
-    for (int i = 0; i < np; i++) if (p[i] < 0 || p[i] >= np) { img->ctx->err = "Permute: invalid permutation"; return FB_ERR_INVALID; }
+    std::vector<char> seen((size_t)np, 0);          // a repeated index would alias one plane twice (and free it twice later)
+    for (int i = 0; i < np; i++) {
+        if (p[i] < 0 || p[i] >= np || seen[p[i]]) { img->ctx->err = "Permute: invalid permutation"; return FB_ERR_INVALID; }
+        seen[p[i]] = 1;
+    }
     const std::vector<FbChan> old(img->ch.begin() + m, img->ch.begin() + m + np);
     for (int i = 0; i < np; i++) img->ch[m + i] = old[p[i]];
     return FB_OK;
@@ -965,7 +985,7 @@ static int transform_meta_apply(fb_image *img, FbXform &t) {
     }
 }
 
-extern "C" int fb_image_undo_transforms(fb_image *img, int keep) {
+static int fb_image_undo_transforms_impl(fb_image *img, int keep) {
     if (!img || keep < 0) return FB_ERR_INVALID;
     fb_ctx *ctx = img->ctx;
     cudaSetDevice(ctx->device);
@@ -1030,7 +1050,11 @@ extern "C" int fb_image_undo_transforms(fb_image *img, int keep) {
     return FB_OK;
 }
 
-extern "C" int fb_image_do_transform(fb_image *img, int32_t id, const int32_t *params, int nparams, int *applied_out) {
+extern "C" int fb_image_undo_transforms(fb_image *img, int keep) {
+    return abi_guard(img ? img->ctx : nullptr, [&]() { return fb_image_undo_transforms_impl(img, keep); });
+}
+
+static int fb_image_do_transform_impl(fb_image *img, int32_t id, const int32_t *params, int nparams, int *applied_out) {
     if (!img || nparams < 0 || (nparams && !params)) return FB_ERR_INVALID;
     cudaSetDevice(img->ctx->device);
     FbXform t;
@@ -1060,6 +1084,10 @@ extern "C" int fb_image_do_transform(fb_image *img, int32_t id, const int32_t *p
     img->info.nb_transforms = (int)img->tr.size();
     if (applied_out) *applied_out = applied;
     return FB_OK;
+}
+
+extern "C" int fb_image_do_transform(fb_image *img, int32_t id, const int32_t *params, int nparams, int *applied_out) {
+    return abi_guard(img ? img->ctx : nullptr, [&]() { return fb_image_do_transform_impl(img, id, params, nparams, applied_out); });
 }
 
 extern "C" int fb_image_recompute_minmax(fb_image *img) {
@@ -1214,6 +1242,10 @@ int read_varint(ByteReader &io) {        // read_big_endian_varint, encoding.cpp
 bool transform_has_parameters(int id) {  // Transform::has_parameters, transform/transform.h:85-102
     return id == 3 || id == 4 || id == 6 || id == 7 || id == 8 || id == 9 || id == 10;
 }
+// bounds on what an (untrusted) header may ask for; far above every configuration this library is meant for
+constexpr int kMaxHeaderChannels = 4096;
+constexpr long long kMaxHeaderPixels = 1ll << 31;
+constexpr int kMaxHeaderTransforms = 4096;
 struct Header {
     int w, h, bit_depth, nb_channels, colormodel, max_properties;
     int responsive_offsets[5];
@@ -1233,7 +1265,7 @@ int parse_header(ByteReader &io, Header &hd) {
         int nb_frames = read_varint(io) + 2;
         (void)read_varint(io);
         int numerator = read_varint(io);
-        if (numerator) for (int i = 1; i < nb_frames; i++) (void)read_varint(io);
+        if (numerator) for (int i = 1; i < nb_frames && !io.eof; i++) (void)read_varint(io);
         (void)read_varint(io);
     }
     hd.colormodel = read_varint(io);
@@ -1277,6 +1309,12 @@ static int parse_container(fb_ctx *ctx, const uint8_t *bytes_in, size_t nbytes, 
     Header hd;
     int rc = parse_header(io, hd);
     if (rc) { ctx->err = "not a FUIF file or corrupt header"; return rc; }
+    // an untrusted header must not size allocations: the reference's Image would try to allocate w*h*nb_channels samples here;
+    // this library bounds what it accepts (documented in include/fuif_b200.h)
+    if (hd.nb_channels > kMaxHeaderChannels || hd.w < 1 || hd.h < 1 || (long long)hd.w * hd.h > kMaxHeaderPixels) {
+        ctx->err = "header asks for more channels / pixels than this library accepts";
+        return FB_ERR_UNSUPPORTED;
+    }
     fb_image *img = new (std::nothrow) fb_image();
     if (!img) return FB_ERR_NOMEM;
     img->ctx = ctx;
@@ -1302,6 +1340,7 @@ static int parse_container(fb_ctx *ctx, const uint8_t *bytes_in, size_t nbytes, 
     for (int s = 0; s < 5; s++) hd.responsive_offsets[s] += rel;
 
     const int nb_transforms = read_varint(io);
+    if (nb_transforms < 0 || nb_transforms > kMaxHeaderTransforms) { ctx->err = "corrupt transform list"; return FB_ERR_INVALID; }
     for (int i = 0; i < nb_transforms; i++) {
         const int idp = read_varint(io);
         if (idp < 0 || io.eof) { ctx->err = "truncated transform list (or header larger than 4 KiB in a device buffer)"; return FB_ERR_INVALID; }
@@ -1309,7 +1348,12 @@ static int parse_container(fb_ctx *ctx, const uint8_t *bytes_in, size_t nbytes, 
         t.id = idp & 0xf;
         if (transform_has_parameters(t.id)) {
             const int np = idp >> 4;
-            for (int j = 0; j < np; j++) t.p.push_back(read_varint(io));
+            if ((size_t)np > io.n - io.pos) { ctx->err = "transform with more parameters than the file has bytes"; return FB_ERR_INVALID; }
+            for (int j = 0; j < np; j++) {
+                const int v = read_varint(io);
+                if (io.eof) { ctx->err = "truncated transform parameters (or header larger than 4 KiB in a device buffer)"; return FB_ERR_INVALID; }
+                t.p.push_back(v);
+            }
         }
         if ((rc = transform_meta_apply(img, t))) return rc;
         img->tr.push_back(t);
@@ -1327,14 +1371,17 @@ extern "C" int fb_decode_batch(fb_ctx *ctx, int n_images, const uint8_t *const *
                                const int64_t *const *group_index, const int32_t *const *group_first, const int *n_groups, fb_image **out) {
     if (!ctx || n_images < 0 || !bytes || !nbytes || !out) return FB_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    std::vector<FbManiacJob> jobs(n_images);
-    std::vector<std::vector<uint8_t>> headers(n_images);
     for (int i = 0; i < n_images; i++) out[i] = nullptr;
-    int rc = FB_OK;
-    for (int i = 0; i < n_images && !rc; i++)
-        rc = parse_container(ctx, bytes[i], nbytes[i], opts, group_index ? group_index[i] : nullptr, group_first ? group_first[i] : nullptr,
-                             n_groups ? n_groups[i] : 0, &out[i], jobs[i], headers[i]);
-    if (!rc) rc = fb_maniac_decode(ctx, jobs);
+    int rc = abi_guard(ctx, [&]() {
+        std::vector<FbManiacJob> jobs(n_images);
+        std::vector<std::vector<uint8_t>> headers(n_images);
+        int r = FB_OK;
+        for (int i = 0; i < n_images && !r; i++)
+            r = parse_container(ctx, bytes[i], nbytes[i], opts, group_index ? group_index[i] : nullptr, group_first ? group_first[i] : nullptr,
+                                n_groups ? n_groups[i] : 0, &out[i], jobs[i], headers[i]);
+        if (!r) r = fb_maniac_decode(ctx, jobs);
+        return r;
+    });
     if (rc) {
         for (int i = 0; i < n_images; i++) { fb_image_destroy(out[i]); out[i] = nullptr; }
         return rc;

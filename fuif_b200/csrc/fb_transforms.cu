@@ -800,10 +800,9 @@ int fb_launch_inv_squeeze_batch(fb_ctx *ctx, int horizontal, int n, const int16_
         }
         if (!jobs.n) return FB_OK;
         const size_t smem = smem_for(R);
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
+        if (smem > 48 * 1024 && !(ctx->smem_optin & fb_ctx::kOptHsqTiled)) {
             FB_CUDA(ctx, cudaFuncSetAttribute(k_inv_hsqueeze_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            configured = 200 * 1024;
+            ctx->smem_optin |= fb_ctx::kOptHsqTiled;
         }
         int threads = R * tpr;
         threads = (threads + 31) / 32 * 32;
@@ -1053,10 +1052,9 @@ static int run_inv_squeeze_plan_per_level(fb_ctx *ctx, const std::vector<FbSqOp>
     }
     if (P.nchains > 0) {
         const size_t smem = 2 * 4096 * sizeof(int) + 150 * 1024 + 64;
-        static bool configured = false;
-        if (!configured) {
+        if (!(ctx->smem_optin & fb_ctx::kOptPyramid)) {
             FB_CUDA(ctx, cudaFuncSetAttribute(k_inv_squeeze_pyramid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
+            ctx->smem_optin |= fb_ctx::kOptPyramid;
         }
         k_inv_squeeze_pyramid<<<P.nchains, 1024, smem, ctx->stream>>>(P);
         FB_LAUNCH_CHECK(ctx);
@@ -1098,7 +1096,6 @@ static int run_inv_squeeze_plan_per_level(fb_ctx *ctx, const std::vector<FbSqOp>
         }
     }
     if (!ep_ok) std::fill(clamp_op.begin(), clamp_op.end(), 0);
-    static bool direct_configured = false;
     // ---- the remaining ops, step by step: direct kernels where eligible, the tiled kernels for the rest
     int k = 0;
     bool ep_applied = false;
@@ -1149,10 +1146,10 @@ static int run_inv_squeeze_plan_per_level(fb_ctx *ctx, const std::vector<FbSqOp>
             }
             dq::StepPlan SP = dq::plan_step(sops, horizontal != 0, E, ep ? ep->lo : 0, ep ? ep->hi : 0, ctx->sm_count);
             if (E.enabled && !SP.epilogue_done) { ctx->err = "internal: YCoCg epilogue planned but not placed"; return FB_ERR_INVALID; }
-            if (!direct_configured) {
+            if (!(ctx->smem_optin & fb_ctx::kOptDirect)) {
                 FB_CUDA(ctx, cudaFuncSetAttribute(dq::k_inv_hsq_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
                 FB_CUDA(ctx, cudaFuncSetAttribute(dq::k_inv_vsq_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-                direct_configured = true;
+                ctx->smem_optin |= fb_ctx::kOptDirect;
             }
             if (SP.hj.n) {
                 dq::k_inv_hsq_direct<<<SP.h_grid, SP.h_threads, SP.h_smem, ctx->stream>>>(SP.hj);
@@ -1242,11 +1239,10 @@ int fb_run_inv_squeeze_plan(fb_ctx *ctx, const std::vector<FbSqOp> &ops, const F
     }
     if (!P.ok) return run_inv_squeeze_plan_per_level(ctx, ops, mode != 1, mode != 1 ? ep : nullptr, epilogue_done);
 
-    static bool configured = false;
-    if (!configured) {
+    if (!(ctx->smem_optin & fb_ctx::kOptFq)) {
         FB_CUDA(ctx, cudaFuncSetAttribute(fq::k_fq_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         FB_CUDA(ctx, cudaFuncSetAttribute(fq::k_fq_verify_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
+        ctx->smem_optin |= fb_ctx::kOptFq;
     }
     if (!ctx->fq_counters) {
         FB_CUDA(ctx, cudaMalloc((void **)&ctx->fq_counters, 8 * sizeof(int)));

@@ -38,8 +38,6 @@ def results():
     return _results
 
 
-# Not strict: a pass is reported as XPASS.  The marker goes away once the kernel has a recorded hardware run.
-@pytest.mark.xfail(strict=False, reason="fb_encode has been verified under the CPU emulator only; this is its first run on hardware")
 @pytest.mark.parametrize("name", NAMES)
 def test_encode_matches_oracle_encoder(name):
     res = results()

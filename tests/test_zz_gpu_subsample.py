@@ -6,9 +6,7 @@ import pytest
 from tests.cases import SUBSAMPLE_CASES
 from tests.util import gpu_plane_image, load_golden, upload_plane_image
 
-pytestmark = [pytest.mark.gpu,
-              # Not strict: a pass is reported as XPASS.  Written after the round's GPU budget was spent; the marker goes away with the first recorded hardware run.
-              pytest.mark.xfail(strict=False, reason="inv_subsample has been verified under the CPU emulator only; this is its first run on hardware")]
+pytestmark = pytest.mark.gpu      # hardware runs on record: GPUTEST_r01.json (XPASS), round 2 calls (passed)
 
 
 @pytest.mark.parametrize("case", SUBSAMPLE_CASES, ids=lambda c: c[0])
