@@ -123,6 +123,10 @@ int fb_launch_clamp(fb_ctx *ctx, int16_t *p, size_t n, int lo, int hi);
 // 8x8 inverse DCT of one component: 64 coefficient planes (bw x bh each, planes[k] for coefficient k in the
 // reference's block order, nullptr = absent) -> (8bw x 8bh) samples (dct.h:249-296)
 int fb_launch_inv_dct(fb_ctx *ctx, const int16_t *const *planes64_dev, int16_t *out, int bw, int bh, float dc_offset);
+// dequantise (quantize.h:32-49) + inverse DCT (+ inverse YCbCr, ycbcr.h:49-58, + clamp) of ncomp <= 3 components in one launch;
+// planes[c][k] = coefficient k (block order) of component c (nullptr = zero), q[c][k] its quantisation factor, out[c] = 8bw x 8bh samples
+int fb_launch_idct_fused(fb_ctx *ctx, const int16_t *const (*planes)[64], const int (*q)[64], int16_t *const *out, int ncomp, int bw, int bh,
+                         float dc_offset, int ycbcr, int minval, int maxval);
 // forward: samples (w x h, edge replicated) -> 64 planes (dct.h:298-336)
 int fb_launch_fwd_dct(fb_ctx *ctx, const int16_t *in, int w, int h, int16_t *const *planes64_dev, int bw, int bh, float dc_offset);
 // inv_palette (palette.h:32-68): out_planes[0] holds the indices and receives row 0 of the palette, planes 1..nb-1 the other rows

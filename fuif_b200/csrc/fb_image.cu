@@ -480,6 +480,71 @@ static int inv_dct(fb_image *img, std::vector<int> &p) {
     return FB_OK;
 }
 
+// Quantize -> DCT (-> YCbCr) undone together: the tail of a JPEG-transcode chain in one launch (fb_idct_fused.cuh) instead of
+// one launch per coefficient plane, one per component and one for the colour inverse.  *fused = how many transforms were
+// undone (0: the shape is not one the fused kernel takes, the caller goes on transform by transform).
+static int try_fused_dct_tail(fb_image *img, int keep, int *fused, bool *clamped) {
+    fb_ctx *ctx = img->ctx;
+    *fused = 0;
+    static const bool off = getenv("FB_DCT_FUSED") && atoi(getenv("FB_DCT_FUSED")) == 0;
+    const int nt = (int)img->tr.size();
+    if (off || nt < 2 || nt - 2 < keep || img->tr[nt - 1].id != FB_TRANSFORM_QUANTIZE || img->tr[nt - 2].id != FB_TRANSFORM_DCT) return FB_OK;
+    if (img->info.nb_meta_channels != 0) return FB_OK;
+    std::vector<int> p = img->tr[nt - 2].p;
+    if (p.size() < 2) default_dct_parameters(p, img);
+    const int beginc = p[0], endc = p[1], nb = endc - beginc + 1;
+    const int offset = (int)img->ch.size() - 63 * nb;
+    if (nb < 1 || nb > 3 || beginc < 0 || offset <= endc) return FB_OK;
+    const int *zz = scan_of_block_index();
+    const int16_t *planes[3][64];
+    int q[3][64];
+    int bw = 0, bh = 0;
+    for (int c = 0; c < nb; c++)
+        for (int i = 0; i < 64; i++) {
+            const FbChan &s = i == 0 ? img->ch[beginc + c] : img->ch[offset - nb + zz[i] * nb + c];
+            planes[c][i] = s.dev;
+            q[c][i] = s.d.q;
+            if (c == 0 && i == 0) { bw = s.d.w; bh = s.d.h; }
+            if (s.d.w != bw || s.d.h != bh) return FB_OK;       // planes of unequal size: the generic path reports it
+        }
+    if (bw < 1 || bh < 1 || bh > 65535) return FB_OK;
+    const bool with_ycbcr = nt >= 3 && nt - 3 >= keep && img->tr[nt - 3].id == FB_TRANSFORM_YCBCR && nb == 3 && beginc == 0;
+    // channels outside the DCT set are only dequantised (inv_quantize touches every non-meta channel)
+    for (int c = 0; c < offset; c++) {
+        if (c >= beginc && c <= endc) continue;
+        FbChan &ch = img->ch[c];
+        if (!ch.dev || ch.d.q == 1) continue;
+        const int qq = ch.d.q;
+        int rc = fb_launch_quantize(ctx, ch.dev, chan_samples(ch.d), qq, 1);
+        if (rc) return rc;
+        ch.d.minval = s16(ch.d.minval * qq); ch.d.maxval = s16(ch.d.maxval * qq); ch.d.q = 1;
+    }
+    FbChan out[3];
+    int16_t *outp[3] = {nullptr, nullptr, nullptr};
+    for (int c = 0; c < nb; c++) {
+        const FbChan &dc = img->ch[beginc + c];
+        chan_defaults(out[c].d);
+        out[c].d.w = bw * 8; out[c].d.h = bh * 8;
+        out[c].d.component = dc.d.component;
+        out[c].d.hshift = dc.d.hshift - 3; out[c].d.vshift = dc.d.vshift - 3;
+        out[c].d.hcshift = dc.d.hcshift - 3; out[c].d.vcshift = dc.d.hcshift - 3;      // sic, dct.h:280
+        out[c].d.decoded = 1;
+        int rc = fb_plane_alloc(ctx, chan_samples(out[c].d), &out[c].dev);
+        if (rc) return rc;
+        outp[c] = out[c].dev;
+    }
+    const float dc_offset = (float)((img->info.maxval + 1.0) * 4.0);
+    int rc = fb_launch_idct_fused(ctx, planes, q, outp, nb, bw, bh, dc_offset, with_ycbcr ? 1 : 0, img->info.minval, img->info.maxval);
+    if (rc) return rc;
+    for (int c = 0; c < nb; c++) { fb_plane_free(ctx, img->ch[beginc + c].dev); img->ch[beginc + c] = out[c]; }
+    for (int c = offset; c < offset + nb * 63; c++) fb_plane_free(ctx, img->ch[c].dev);
+    img->ch.erase(img->ch.begin() + offset, img->ch.begin() + offset + nb * 63);
+    *fused = with_ycbcr ? 3 : 2;
+    // after the YCbCr clamp the final clamp of undo_transforms is the identity for these planes
+    if (with_ycbcr && nt == 3 && keep == 0 && (int)img->ch.size() == 3) *clamped = true;
+    return FB_OK;
+}
+
 // fwd_DCT, dct.h:298-336 (explicit parameters only: the reference dereferences an empty vector otherwise)
 static int fwd_dct(fb_image *img, std::vector<int> &p, int *applied) {
     fb_ctx *ctx = img->ctx;
@@ -1005,7 +1070,16 @@ static int fb_image_undo_transforms_impl(fb_image *img, int keep) {
             if (!rc && fuse) clamped = true;
             break;
         }
-        case FB_TRANSFORM_QUANTIZE: rc = do_quantize(img, true, t.p); break;
+        case FB_TRANSFORM_QUANTIZE: {
+            int fused = 0;
+            rc = try_fused_dct_tail(img, keep, &fused, &clamped);
+            if (!rc && fused) {
+                for (int k = 0; k < fused - 1; k++) img->tr.pop_back();        // the last one is popped below
+                break;
+            }
+            if (!rc) rc = do_quantize(img, true, t.p);
+            break;
+        }
         case FB_TRANSFORM_SQUEEZE: {
             // look ahead: an inverse YCoCg and / or the final clamp right after the Squeeze ride on its last launch
             const int nt = (int)img->tr.size();

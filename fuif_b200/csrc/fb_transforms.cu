@@ -9,6 +9,7 @@
 #include "fb_direct_plan.h"
 #include <type_traits>
 #include "fb_pk_plan.h"
+#include "fb_idct_fused.cuh"
 #include "fb_subsample.cuh"
 #include "fb_approx.cuh"
 #include "fb_palette.cuh"
@@ -1329,6 +1330,25 @@ int fb_launch_inv_dct(fb_ctx *ctx, const int16_t *const *planes64, int16_t *out,
     for (int i = 0; i < 64; i++) pl.p[i] = planes64[i];
     k_inv_dct<<<nblocks(n, 64), 64, 0, ctx->stream>>>(pl, out, bw, bh, dc_offset);
     FB_LAUNCH_CHECK(ctx);
+    return FB_OK;
+}
+// dequantise + inverse DCT (+ inverse YCbCr + clamp) of up to three components in one launch (fb_idct_fused.cuh)
+int fb_launch_idct_fused(fb_ctx *ctx, const int16_t *const (*planes)[64], const int (*q)[64], int16_t *const *out, int ncomp, int bw, int bh,
+                         float dc_offset, int ycbcr, int minval, int maxval) {
+    if (ncomp < 1 || ncomp > 3 || bw < 1 || bh < 1 || bh > 65535) { ctx->err = "fused inverse DCT: bad geometry"; return FB_ERR_INVALID; }
+    idf::Job J;
+    memset(&J, 0, sizeof(J));
+    for (int c = 0; c < ncomp; c++) {
+        for (int k = 0; k < 64; k++) { J.pl[c][k] = planes[c][k]; J.q[c][k] = q[c][k]; }
+        J.out[c] = out[c];
+    }
+    J.ncomp = ncomp; J.bw = bw; J.bh = bh; J.dc_offset = dc_offset; J.ycbcr = ycbcr; J.minval = minval; J.maxval = maxval;
+    const dim3 grid((unsigned)((bw + idf::kBlocksPerCta - 1) / idf::kBlocksPerCta), (unsigned)bh);
+    idf::k_idct_ycbcr<<<grid, 256, 0, ctx->stream>>>(J);
+    ctx->launches++;
+    ctx->mark("k_idct_ycbcr", 4.0 * 64.0 * bw * bh * ncomp);      // every coefficient read once, every sample written once
+    cudaError_t e__ = cudaGetLastError();
+    if (e__ != cudaSuccess) { ctx->err = std::string("k_idct_ycbcr launch: ") + cudaGetErrorString(e__); return FB_ERR_CUDA; }
     return FB_OK;
 }
 int fb_launch_fwd_dct(fb_ctx *ctx, const int16_t *in, int w, int h, int16_t *const *planes64, int bw, int bh, float dc_offset) {

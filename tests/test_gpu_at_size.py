@@ -53,3 +53,28 @@ def test_decode_and_chain_vs_reference_at_size(oracle, ctx, case, tmp_path):
     seq.undo_transforms(0)
     po.compare_plane_images(gpu_plane_image(po, seq), last, name + " final planes (sequential)", check_meta=False)
     assert ctx.pk_range_flagged == 0 or maxval > 1023
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 3, 255), (203, 117, 3, 255), (64, 64, 3, 1023), (1024, 520, 3, 255), (320, 200, 1, 255)])
+@pytest.mark.parametrize("keep", [0, 1])
+def test_fused_dct_tail_vs_oracle(oracle, ctx, shape, keep):
+    """Quantize -> DCT (-> YCbCr) undone in ONE call = one fused launch (fb_idct_fused.cuh); keep = 1 leaves the colour transform
+    in place (two transforms fused).  Against the oracle's transform-by-transform result, bit for bit."""
+    from fuif_b200 import api
+    from tests.util import default_squeeze_parameters
+    po = oracle
+    w, h, c, maxval = shape
+    pix = synth_image(w, h, c, maxval, seed=3 * w + h)
+    oi = po.OracleImage.from_pixels(pix, maxval)
+    gi = api.Image.from_pixels(pix, maxval, ctx)
+    q = ([8, 12, 12] if c == 3 else [8]) * 64
+    sq = default_squeeze_parameters((w + 7) // 8, (h + 7) // 8, c)
+    chain = ([(0, [])] if c == 3 else []) + [(4, [0, c - 1]), (5, q), (7, sq)]
+    for tid, params in chain:
+        assert oi.do_transform(tid, params) and gi.do_transform(api.Transform(tid, params))
+    k = keep if c == 3 else 0
+    n0 = ctx.launches
+    gi.undo_transforms(k)
+    oi.undo_transforms(k)
+    po.compare_plane_images(gpu_plane_image(po, gi), oi.to_plane_image(), f"fused dct tail keep={k} {shape}")
+    assert ctx.launches - n0 < 40, "the fused kernel did not take the chain (one launch per coefficient plane again?)"
