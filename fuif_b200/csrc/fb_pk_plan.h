@@ -13,7 +13,7 @@
 namespace ps {
 
 // box_w x box_h tiles of a w x h int16 plane; false = the plane cannot be described (unaligned base / pitch)
-bool ps_make_tilemap(TileMap *m, const void *base, int w, int h, int box_w, int box_h);
+bool ps_make_tilemap(TileMap *m, const void *base, int w, int h, int box_w, int box_h, int swizzle_bytes);
 
 struct StepOp {                 // one plane of one squeeze step
     const int16_t *avg, *res;
@@ -59,7 +59,7 @@ struct ScratchCursor {
 
 // warps of the packed horizontal kernel that fit one SM (shared memory is the limit)
 inline int h_warps_per_sm(int np, int ep) {
-    int w = (int)((226 * 1024) / (h_smem_per_warp(np, ep) + 128 + 1024));      // + alignment slack + the per-block reservation
+    int w = (int)((226 * 1024) / (h_smem_per_warp(np, ep) + 1024 + 1024));     // + alignment slack + the per-block reservation
     return w > 16 ? 16 : w;
 }
 
@@ -101,9 +101,9 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
                 const int wps = h_warps_per_sm(np, epk);
                 long long total_rb = 0;
                 for (size_t j = j0; j < j1; j++) total_rb += (ops[mine[j].i0].ha + kHRows - 1) / kHRows;
-                // one round of items: at most wps warps per SM fit, 8 (two per scheduler, each with its planes as independent
-                // chains) are enough to keep the integer pipes busy -- beyond that shorter segments only add warm-up work
-                long long nseg_want = ((long long)sm_count * (wps < 8 ? wps : 8)) / (total_rb > 0 ? total_rb : 1);
+                // one round of items: at most wps warps per SM fit, 12 (three per scheduler) keep the integer pipes busy through
+                // the dependent-issue latency of the chains -- beyond that shorter segments only add warm-up work
+                long long nseg_want = ((long long)sm_count * (wps < 12 ? wps : 12)) / (total_rb > 0 ? total_rb : 1);
                 if (nseg_want < 1) nseg_want = 1;
                 int items = 0;
                 bool ok = true;
@@ -112,8 +112,8 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
                     HJob &J = L.jobs.j[L.jobs.n];
                     const int i1 = mine[j].i1;
                     int S = (int)((a.wa + nseg_want - 1) / nseg_want);
-                    S = (S + kHChunk - 1) / kHChunk * kHChunk;
-                    if (S < kHChunk) S = kHChunk;
+                    S = (S + 15) / 16 * 16;         // (a multiple of 16 whatever the tile width: only the last segment of a row may end on 8)
+                    if (S < 16) S = 16;
                     J.np = np; J.wa = a.wa; J.h = a.ha; J.S = S; J.nseg = (a.wa + S - 1) / S; J.nrb = (a.ha + kHRows - 1) / kHRows;
                     J.nsegp = (J.nseg + 7) / 8 * 8;
                     J.item0 = items;
@@ -123,8 +123,8 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
                     const StepOp *pl[2] = {&a, i1 >= 0 ? &ops[i1] : nullptr};
                     for (int p = 0; p < np; p++) {
                         J.avg[p] = pl[p]->avg; J.res[p] = pl[p]->res;
-                        ok = ok && ps_make_tilemap(&J.tm_a[p], pl[p]->avg, a.wa, a.ha, kHChunk, kHRows);
-                        ok = ok && ps_make_tilemap(&J.tm_r[p], pl[p]->res, a.wa, a.ha, kHChunk, kHRows);
+                        ok = ok && ps_make_tilemap(&J.tm_a[p], pl[p]->avg, a.wa, a.ha, kHChunk, kHRows, kSwzA);
+                        ok = ok && ps_make_tilemap(&J.tm_r[p], pl[p]->res, a.wa, a.ha, kHChunk, kHRows, kSwzA);
                         J.est[p] = cur.take<int16_t>((size_t)J.nsegp * a.ha);
                         J.act[p] = cur.take<int16_t>((size_t)J.nsegp * a.ha);
                     }
@@ -135,12 +135,12 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
                     if (epk == fq::kEpYCoCg) {
                         J.yin = ep.yin; J.out[0] = ep.rout; J.out[1] = a.out; J.out[2] = ops[i1].out;
                         J.do_clamp = ep.do_clamp; J.lo = ep.lo; J.hi = ep.hi;
-                        ok = ok && ps_make_tilemap(&J.tm_y, ep.yin, 2 * a.wa, a.ha, 2 * kHChunk, kHRows);
-                        for (int k = 0; k < 3; k++) ok = ok && ps_make_tilemap(&J.tm_o[k], J.out[k], 2 * a.wa, a.ha, 2 * kHChunk, kHRows);
+                        ok = ok && ps_make_tilemap(&J.tm_y, ep.yin, 2 * a.wa, a.ha, 2 * kHChunk, kHRows, kSwzO);
+                        for (int k = 0; k < 3; k++) ok = ok && ps_make_tilemap(&J.tm_o[k], J.out[k], 2 * a.wa, a.ha, 2 * kHChunk, kHRows, kSwzO);
                     } else {
                         for (int p = 0; p < np; p++) {
                             J.out[p] = pl[p]->out;
-                            ok = ok && ps_make_tilemap(&J.tm_o[p], pl[p]->out, 2 * a.wa, a.ha, 2 * kHChunk, kHRows);
+                            ok = ok && ps_make_tilemap(&J.tm_o[p], pl[p]->out, 2 * a.wa, a.ha, 2 * kHChunk, kHRows, kSwzO);
                         }
                     }
                     L.bytes += (double)np * 8.0 * a.wa * a.ha + (epk == fq::kEpYCoCg ? 8.0 * a.wa * a.ha : 0.0);
@@ -154,7 +154,7 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
                 L.jobs.items = items;
                 L.warps_per_block = 1;
                 L.smem_per_warp = (int)h_smem_per_warp(np, epk);
-                L.smem = (size_t)L.warps_per_block * L.smem_per_warp + 128;
+                L.smem = (size_t)L.warps_per_block * L.smem_per_warp + 1024;
                 L.grid = (items + L.warps_per_block - 1) / L.warps_per_block;
                 P.h.push_back(L);
             }

@@ -43,9 +43,21 @@ namespace ps {
 
 constexpr int kMaxAvg = 2047;       // packed arithmetic is exact while |average| <= kMaxAvg and |residual| <= kMaxRes:
 constexpr int kMaxRes = 4095;       // |B| <= 3*kMaxAvg + kMaxRes/2 + 1 = 8189, 4|P-a| + 3|a-n| + 6 <= 53232 < 65536
-constexpr int kHChunk = 16;         // pairs per TMA tile (32-byte rows)
+#ifndef PS_HCHUNK
+#define PS_HCHUNK 16
+#endif
+constexpr int kHChunk = PS_HCHUNK;  // pairs per TMA tile (8: 16-byte average / residual rows, 32-byte output rows; 16: twice that)
+constexpr int kHW = kHChunk / 2;    // 32-bit words of averages per tile row
 constexpr int kHRows = 64;          // rows per warp tile
-constexpr int kHWarm = kHChunk;     // warm-up pairs of a horizontal segment (one whole tile, nothing stored)
+constexpr int kHWarm = 16;          // warm-up pairs of a horizontal segment (whole tiles, nothing stored)
+constexpr int kHWarmChunks = kHWarm / kHChunk;
+static_assert(kHChunk == 8 || kHChunk == 16, "tile widths the register staging is written for");
+// Shared-memory swizzle of the tiles (TMA swizzle modes): a lane owns ROWS, so with dense tiles the 32 lanes of a 16-byte access
+// would sit 32 / 64 bytes apart and hit the same few banks (measured: 16-way conflicts on the output stores, ~800 conflict cycles
+// per tile).  With the 16-byte chunk index XORed with the row bits (address bits 7.. of 1024-byte aligned tiles) they spread out.
+constexpr int kSwzA = kHChunk * 2 >= 32 ? kHChunk * 2 : 0;          // average / residual tiles: 32-byte rows -> SWIZZLE_32B
+constexpr int kSwzO = 2 * kHChunk * 2 >= 32 ? 2 * kHChunk * 2 : 0;  // Y / output tiles: 64-byte rows -> SWIZZLE_64B
+static_assert(kSwzA <= 64 && kSwzO <= 64, "swizzle spans");
 constexpr int kVWarm = 12;          // warm-up pairs of a vertical segment (8 missed about once per 4096^2 image: a repair costs tens of microseconds)
 constexpr int kVDepth = 4;          // rows of register prefetch in the vertical kernel
 constexpr int kMaxHJobs = 8;
@@ -151,7 +163,9 @@ FB_DEV bool pk_chk_bad(uint32_t acc, int bound) { return (int)(acc & 0xffffu) > 
 // tile movement: TMA + mbarrier on the GPU, synchronous copies under the emulator
 // ---------------------------------------------------------------------------------------------------------
 #if defined(FB_EMULATE)
-struct TileMap { int16_t *base; int w, h, box_w, box_h; };
+struct TileMap { int16_t *base; int w, h, box_w, box_h, swz; };      // swz: 0, 32 or 64 = the TMA shared-memory swizzle span in bytes
+// 16-byte chunk index bits [4, 4+B) of a shared-memory offset XORed with bits [7, 7+B): CU_TENSOR_MAP_SWIZZLE_32B (B = 1) / _64B (B = 2)
+inline int emu_swz(int off, int swz) { const int m = swz == 64 ? 3 : (swz == 32 ? 1 : 0); return off ^ (((off >> 7) & m) << 4); }
 inline void fb_syncwarp() { cuemu::bar_sync(1 + (int)(threadIdx.x >> 5), 32); }
 inline void fb_threadfence() {}
 inline void tile_load(void *dst, const TileMap *m, int x, int y, uint64_t *, int) {
@@ -159,7 +173,7 @@ inline void tile_load(void *dst, const TileMap *m, int x, int y, uint64_t *, int
     for (int r = 0; r < m->box_h; r++)
         for (int c = 0; c < m->box_w; c++) {
             const int gx = x + c, gy = y + r;
-            d[r * m->box_w + c] = (gx >= 0 && gx < m->w && gy >= 0 && gy < m->h) ? m->base[(size_t)gy * m->w + gx] : (int16_t)0;
+            d[emu_swz((r * m->box_w + c) * 2, m->swz) / 2] = (gx >= 0 && gx < m->w && gy >= 0 && gy < m->h) ? m->base[(size_t)gy * m->w + gx] : (int16_t)0;
         }
 }
 inline void tile_store(const TileMap *m, int x, int y, const void *src) {
@@ -167,7 +181,7 @@ inline void tile_store(const TileMap *m, int x, int y, const void *src) {
     for (int r = 0; r < m->box_h; r++)
         for (int c = 0; c < m->box_w; c++) {
             const int gx = x + c, gy = y + r;
-            if (gx >= 0 && gx < m->w && gy >= 0 && gy < m->h) m->base[(size_t)gy * m->w + gx] = s[r * m->box_w + c];
+            if (gx >= 0 && gx < m->w && gy >= 0 && gy < m->h) m->base[(size_t)gy * m->w + gx] = s[emu_swz((r * m->box_w + c) * 2, m->swz) / 2];
         }
 }
 // the copies above are synchronous, so "the tile has landed" only needs lane 0 to have reached its issue point: a warp
@@ -260,7 +274,7 @@ struct HJobs { HJob j[kMaxHJobs]; int n, items; };
 
 FB_HD size_t h_smem_per_warp(int np, int epilogue) {
     const size_t stage = (size_t)np * 2 * kHRows * kHChunk * 2 + (epilogue == fq::kEpYCoCg ? (size_t)kHRows * 2 * kHChunk * 2 : 0);
-    return 2 * stage + 128;         // two slots (inputs, then the outputs in place) + mbarriers; slices stay 128-byte aligned
+    return 2 * stage + 1024;        // two slots (inputs, then the outputs in place) + mbarriers; slices stay 1024-byte aligned
 }
 
 // exact inverse YCoCg + final clamp of one pixel
@@ -356,11 +370,14 @@ FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane) {
     const int x_first = g ? x_own - kHWarm : 0;
     const int nchunks = (x_end - x_first + kHChunk - 1) / kHChunk;
     const int rowA = lane * (kHChunk * 2), rowB = (lane + 32) * (kHChunk * 2);         // byte offsets of this lane's rows in a 32-byte-row tile
+    // swizzle terms of this lane's rows (the same for row l and row l + 32): XOR them into the 16-byte chunk offset
+    const int sA = kSwzA == 32 ? ((lane >> 2) & 1) << 4 : (kSwzA == 64 ? ((lane >> 1) & 3) << 4 : 0);
+    const int sO = kSwzO == 64 ? ((lane >> 1) & 3) << 4 : (kSwzO == 32 ? ((lane >> 2) & 1) << 4 : 0);
 
     auto issue = [&](int c) {       // lane 0: the input tiles of chunk c into slot c & 1
         const int xc = x_first + c * kHChunk;
         unsigned char *base = sm + (c & 1) * kStage;
-        const bool with_y = kCol && !(g && c == 0);
+        const bool with_y = kCol && !(g && c < kHWarmChunks);
         mbar_expect(&bars[c & 1], NP * 2 * kTileA + (with_y ? kTileO : 0));
         for (int p = 0; p < NP; p++) {
             tile_load(base + p * 2 * kTileA, &J.tm_a[p], xc, row0, &bars[c & 1], 0);
@@ -374,14 +391,16 @@ FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane) {
     }
     emu_issue_point();
 
-    uint32_t P[NP], a_end[NP], chk_a = 0, chk_r = 0;
-#pragma unroll
-    for (int p = 0; p < NP; p++) {      // the average right after the segment (the last owned pair's "next"): one direct load per row
-        a_end[p] = 0;
+    uint32_t P[NP], chk_a = 0, chk_r = 0;
+    int ae_lo[NP], ae_hi[NP];           // the average right after the segment (the last owned pair's "next"): one direct load per row,
+#pragma unroll                          // packed and range-checked only where it is used, so that nothing waits for these loads here
+    for (int p = 0; p < NP; p++) {
+        ae_lo[p] = 0; ae_hi[p] = 0;
         if (x_end < wa) {
             const int rA = fq::imin(row0 + lane, J.h - 1), rB = fq::imin(row0 + lane + 32, J.h - 1);
-            a_end[p] = (uint32_t)(uint16_t)J.avg[p][(size_t)rA * wa + x_end] | ((uint32_t)(uint16_t)J.avg[p][(size_t)rB * wa + x_end] << 16);
-        }                               // (range-checked where it is used, so that nothing waits for these loads here)
+            ae_lo[p] = J.avg[p][(size_t)rA * wa + x_end];
+            ae_hi[p] = J.avg[p][(size_t)rB * wa + x_end];
+        }
     }
     const bool do_clamp = J.do_clamp != 0;
     const PK K = pk_consts(J.k1);
@@ -390,17 +409,11 @@ FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane) {
         const int xc = x_first + c * kHChunk;
         unsigned char *slot = sm + (c & 1) * kStage;
         const unsigned char *nslot = sm + ((c + 1) & 1) * kStage;
-        const bool warm = g && c == 0, have_next = c + 1 < nchunks;
-        const int nsteps = fq::imin(kHChunk, x_end - xc);       // 16, or 8 at the end of a row whose width is 8 mod 16
-        if (c >= 1 && have_next) {
-            // the other slot held chunk c-1: once its output tiles have been read by the store engine it takes chunk c+1,
-            // which then has this chunk's whole computation to arrive
-            if (lane == 0) { store_wait_read(); issue(c + 1); }
-            emu_issue_point();
-        }
+        const bool warm = g && c < kHWarmChunks, have_next = c + 1 < nchunks;
+        const int nsteps = fq::imin(kHChunk, x_end - xc);       // a whole tile, or 8 at the end of a row whose width is 8 mod 16
         mbar_wait(&bars[c & 1], (c >> 1) & 1);
         // ---- the lane's two rows of every input tile into registers
-        uint32_t aw[NP][2][8], rw[NP][2][8], yw[2][16];
+        uint32_t aw[NP][2][kHW], rw[NP][2][kHW], yw[2][2 * kHW];
 #pragma unroll
         for (int p = 0; p < NP; p++) {
             const unsigned char *ta = slot + p * 2 * kTileA, *tr = ta + kTileA;
@@ -408,13 +421,13 @@ FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane) {
             for (int r = 0; r < 2; r++) {
                 const int ro = r ? rowB : rowA;
 #pragma unroll
-                for (int v = 0; v < 2; v++) {
-                    const uint4 va = *reinterpret_cast<const uint4 *>(ta + ro + 16 * v), vr = *reinterpret_cast<const uint4 *>(tr + ro + 16 * v);
+                for (int v = 0; v < kHW / 4; v++) {
+                    const uint4 va = *reinterpret_cast<const uint4 *>(ta + ro + ((16 * v) ^ sA)), vr = *reinterpret_cast<const uint4 *>(tr + ro + ((16 * v) ^ sA));
                     aw[p][r][4 * v] = va.x; aw[p][r][4 * v + 1] = va.y; aw[p][r][4 * v + 2] = va.z; aw[p][r][4 * v + 3] = va.w;
                     rw[p][r][4 * v] = vr.x; rw[p][r][4 * v + 1] = vr.y; rw[p][r][4 * v + 2] = vr.z; rw[p][r][4 * v + 3] = vr.w;
                 }
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
+                for (int i = 0; i < kHW; i++) {
                     chk_a = pk_chk(chk_a, aw[p][r][i], kMaxAvg * 0x00010001u);
                     chk_r = pk_chk(chk_r, rw[p][r][i], kMaxRes * 0x00010001u);
                 }
@@ -425,8 +438,8 @@ FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane) {
 #pragma unroll
             for (int r = 0; r < 2; r++)
 #pragma unroll
-                for (int v = 0; v < 4; v++) {
-                    const uint4 y = *reinterpret_cast<const uint4 *>(ty + 2 * (r ? rowB : rowA) + 16 * v);
+                for (int v = 0; v < kHW / 2; v++) {
+                    const uint4 y = *reinterpret_cast<const uint4 *>(ty + 2 * (r ? rowB : rowA) + ((16 * v) ^ sO));
                     yw[r][4 * v] = y.x; yw[r][4 * v + 1] = y.y; yw[r][4 * v + 2] = y.z; yw[r][4 * v + 3] = y.w;
                 }
         }
@@ -434,7 +447,7 @@ FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane) {
 #pragma unroll
             for (int p = 0; p < NP; p++) P[p] = plo(aw[p][0][0], aw[p][1][0]);      // chain start: "left" = own average (squeeze.h:84-89); a segment start guesses the same
         }
-        if (c == 1 && g) {          // first owned pair: remember the state the warm-up reached
+        if (c == kHWarmChunks && g) {       // first owned pair: remember the state the warm-up reached
 #pragma unroll
             for (int p = 0; p < NP; p++) {
                 if (row0 + lane < J.h) J.est[p][(size_t)(row0 + lane) * J.nsegp + g - 1] = (int16_t)(P[p] & 0xffffu);
@@ -444,18 +457,27 @@ FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane) {
         uint32_t a_last[NP];
         fb_syncwarp();              // every lane holds its inputs: the slot may now receive the outputs
 #pragma unroll
-        for (int k = 0; k < 8; k++) {                           // two pairs per iteration: one word of averages per row
-            if (k == 7) {
+        for (int k = 0; k < kHW; k++) {                         // two pairs per iteration: one word of averages per row
+            if (k == kHW / 4 && c >= 1 && have_next) {
+                // the other slot held chunk c-1: its output tiles have had a quarter of this chunk's computation to be read by the
+                // store engine; now it takes chunk c+1, which has the remaining three quarters to arrive
+                if (lane == 0) { store_wait_read(); issue(c + 1); }
+                emu_issue_point();
+            }
+            if (k == kHW - 1) {
                 // what the last pair of the chunk sees as its next average: the first average of the next chunk (its tiles have had
                 // this chunk's computation to arrive in the other slot), or the average after the segment (direct load at the start)
                 if (have_next) {
                     mbar_wait(&bars[(c + 1) & 1], ((c + 1) >> 1) & 1);
 #pragma unroll
                     for (int p = 0; p < NP; p++)
-                        a_last[p] = plo(*reinterpret_cast<const uint32_t *>(nslot + p * 2 * kTileA + rowA), *reinterpret_cast<const uint32_t *>(nslot + p * 2 * kTileA + rowB));
+                        a_last[p] = plo(*reinterpret_cast<const uint32_t *>(nslot + p * 2 * kTileA + rowA + sA), *reinterpret_cast<const uint32_t *>(nslot + p * 2 * kTileA + rowB + sA));
                 } else {
 #pragma unroll
-                    for (int p = 0; p < NP; p++) { a_last[p] = a_end[p]; chk_a = pk_chk(chk_a, a_end[p], kMaxAvg * 0x00010001u); }
+                    for (int p = 0; p < NP; p++) {
+                        a_last[p] = (uint32_t)(uint16_t)ae_lo[p] | ((uint32_t)(uint16_t)ae_hi[p] << 16);
+                        chk_a = pk_chk(chk_a, a_last[p], kMaxAvg * 0x00010001u);
+                    }
                 }
             }
             if (2 * k < nsteps) {
@@ -464,7 +486,7 @@ FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane) {
                 for (int p = 0; p < NP; p++) {
                     const uint32_t a0 = plo(aw[p][0][k], aw[p][1][k]), a1 = phi(aw[p][0][k], aw[p][1][k]);
                     uint32_t a2;
-                    if (k < 7) a2 = plo(aw[p][0][k + 1], aw[p][1][k + 1]);
+                    if (k < kHW - 1) a2 = plo(aw[p][0][k + 1], aw[p][1][k + 1]);
                     else a2 = a_last[p];
                     if (xc + 2 * k + 2 >= wa) a2 = a1;          // last pair of the row
                     const uint32_t r0 = plo(rw[p][0][k], rw[p][1][k]), r1 = phi(rw[p][0][k], rw[p][1][k]);
@@ -474,7 +496,7 @@ FB_DEV void h_item(const HJob &J, int rb, int g, unsigned char *sm, int lane) {
                     P[p] = oB[p][1];
                 }
                 if (!warm) {
-                    const int ob = 8 * k;                       // byte offset of output columns 4k .. 4k+3 in a 64-byte output row
+                    const int ob = ((16 * (k >> 1)) ^ sO) + 8 * (k & 1);      // byte offset of output columns 4k .. 4k+3 in a (swizzled) output row
                     if (kCol) {
                         uint32_t R[4], G[4], Bc[4];
                         const uint32_t y4[4] = {plo(yw[0][2 * k], yw[1][2 * k]), phi(yw[0][2 * k], yw[1][2 * k]), plo(yw[0][2 * k + 1], yw[1][2 * k + 1]),
@@ -551,7 +573,7 @@ template <int NP, int EP>
 FB_KERNEL(32) k_pk_hsq(const FB_GRID_CONSTANT HJobs jobs, int warps_per_block, int smem_per_warp) {
     FB_DYN_SMEM(smraw);
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
-    unsigned char *sm = smraw + ((128 - (int)(reinterpret_cast<uintptr_t>(smraw) & 127)) & 127) + (size_t)warp * smem_per_warp;
+    unsigned char *sm = smraw + ((1024 - (int)(reinterpret_cast<uintptr_t>(smraw) & 1023)) & 1023) + (size_t)warp * smem_per_warp;     // swizzled tiles: 1024-byte aligned
     const int item = (int)blockIdx.x * warps_per_block + warp;
     if (item >= jobs.items) return;
     int ji = 0;

@@ -857,15 +857,17 @@ static EncodeTiledFn encode_tiled() {
     return fn;
 }
 // box_w x box_h tiles of a row-major w x h int16 plane without padding: out-of-range elements load as zero, stores are clipped
-bool ps_make_tilemap(TileMap *m, const void *base, int w, int h, int box_w, int box_h) {
+bool ps_make_tilemap(TileMap *m, const void *base, int w, int h, int box_w, int box_h, int swizzle_bytes) {
     EncodeTiledFn fn = encode_tiled();
     if (!fn || (reinterpret_cast<uintptr_t>(base) & 15) || (w & 7) || box_w > 256 || box_h > 256) return false;
+    if (swizzle_bytes && swizzle_bytes != box_w * 2) return false;        // the swizzle span is the tile row
+    const CUtensorMapSwizzle swz = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
     const cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)h};
     const cuuint64_t strides[1] = {(cuuint64_t)w * sizeof(int16_t)};
     const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
     const cuuint32_t estr[2] = {1, 1};
-    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 }  // namespace ps
 

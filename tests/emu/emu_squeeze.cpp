@@ -256,9 +256,9 @@ int emu_run_direct(int nplanes, int16_t **planes, int nops, const int *opdesc, c
 #include "fb_pk_plan.h"
 
 namespace ps {
-bool ps_make_tilemap(TileMap *m, const void *base, int w, int h, int box_w, int box_h) {
+bool ps_make_tilemap(TileMap *m, const void *base, int w, int h, int box_w, int box_h, int swizzle_bytes) {
     if ((reinterpret_cast<uintptr_t>(base) & 15) || (w & 7)) return false;
-    m->base = (int16_t *)base; m->w = w; m->h = h; m->box_w = box_w; m->box_h = box_h;
+    m->base = (int16_t *)base; m->w = w; m->h = h; m->box_w = box_w; m->box_h = box_h; m->swz = swizzle_bytes;
     return true;
 }
 }  // namespace ps
