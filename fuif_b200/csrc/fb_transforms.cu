@@ -370,9 +370,19 @@ struct PyrParams {
     int nchains;
 };
 constexpr int kPyrSeg = 8, kPyrWarm = 8;
-constexpr int kPyrMaxOut = 4096;           // samples of a level's output plane (one block = one SM works on it)
+constexpr int kPyrMaxOut = 16384;          // samples of a level's output plane (one block = one SM works on it)
+constexpr int kPyrBufHalfwords = 20480;    // each of the two ping-pong plane buffers in shared memory (output of a level incl. pitch padding)
+constexpr int kPyrResHalfwords = 12288;    // the residual staging buffer
+constexpr int kPyrMaxItems = 4096;         // (chain, segment) items of a level
+// halfword pitch of a plane of width w in shared memory: for a plane that a HORIZONTAL level reads (lanes = rows) the word
+// pitch is made odd so that the rows fall into different banks
+__host__ __device__ __forceinline__ int pyr_pitch(int w, bool read_by_horizontal) {
+    int P = (w + 1) & ~1;
+    if (read_by_horizontal && ((P >> 1) & 1) == 0) P += 2;
+    return P;
+}
 
-// One segment of one chain, inputs staged in shared memory, outputs to global memory.
+// One segment of one chain, inputs and outputs in shared memory.
 // ch_stride / step strides let the same code run along x (horizontal) or y (vertical).
 __device__ __forceinline__ int pyr_segment(const int16_t *a, const int16_t *rr, int a_step, int r_step, int16_t *o, int o_step, int n_avg,
                                            int from, int xs, int xe, int prev, bool chain_start, int &bw) {
@@ -390,24 +400,27 @@ __device__ __forceinline__ int pyr_segment(const int16_t *a, const int16_t *rr, 
     return prev;
 }
 
+// The coarse levels of one plane's chain, level after level in ONE block: the plane stays in shared memory between the levels
+// (two ping-pong buffers), only the residuals come from HBM and only the last level's output goes back.
 __global__ void __launch_bounds__(1024) k_inv_squeeze_pyramid(PyrParams P) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int c = blockIdx.x;
     const int l0 = P.chain_start[c], l1 = P.chain_start[c + 1];
     int *bwS = reinterpret_cast<int *>(smraw);                  // [items] state assumed at the segment start
-    int *bfS = bwS + 4096;                                      // [items] state after the segment
-    int16_t *data = reinterpret_cast<int16_t *>(bfS + 4096);
+    int *bfS = bwS + kPyrMaxItems;                              // [items] state after the segment
+    int16_t *bufA = reinterpret_cast<int16_t *>(bfS + kPyrMaxItems), *bufB = bufA + kPyrBufHalfwords, *resS = bufB + kPyrBufHalfwords;
+    int16_t *avgS = bufA, *outS = bufB;
     for (int l = l0; l < l1; l++) {
         const PyrLevel L = P.lv[l];
         const bool H = L.horizontal != 0;
         const int wa = L.wa, ha = L.ha;
         const int wr = H ? L.wr : wa, hr = H ? ha : L.hr;           // residual plane dims
         const int wo = H ? wa + wr : wa, ho = H ? ha : ha + hr;
-        // pitches in halfwords: for horizontal levels lanes are rows, so make the word pitch odd
-        int PA = (wa + 1) & ~1, PR = (wr + 1) & ~1;
-        if (H) { if (((PA >> 1) & 1) == 0) PA += 2; if (((PR >> 1) & 1) == 0) PR += 2; }
-        int16_t *avgS = data, *resS = data + (size_t)ha * PA;
-        for (int i = threadIdx.x; i < wa * ha; i += blockDim.x) { const int r = i / wa, q = i - r * wa; avgS[r * PA + q] = L.avg[i]; }
+        const int PA = pyr_pitch(wa, H), PR = pyr_pitch(wr, H);
+        const bool last = l + 1 == l1;
+        const int PO = pyr_pitch(wo, !last && P.lv[l + 1].horizontal != 0);
+        if (l == l0)
+            for (int i = threadIdx.x; i < wa * ha; i += blockDim.x) { const int r = i / wa, q = i - r * wa; avgS[r * PA + q] = L.avg[i]; }
         for (int i = threadIdx.x; i < wr * hr; i += blockDim.x) { const int r = i / wr, q = i - r * wr; resS[r * PR + q] = L.res ? L.res[i] : (int16_t)0; }
         __syncthreads();
         const int nchain = H ? ha : wa;                 // independent chains
@@ -420,8 +433,8 @@ __global__ void __launch_bounds__(1024) k_inv_squeeze_pyramid(PyrParams P) {
             const int xs = seg * kPyrSeg, xe = min(xs + kPyrSeg, npair);
             const int16_t *a = H ? avgS + chain * PA : avgS + chain;
             const int16_t *rr = H ? resS + chain * PR : resS + chain;
-            int16_t *o = H ? L.out + (size_t)chain * wo : L.out + chain;
-            const int a_step = H ? 1 : PA, r_step = H ? 1 : PR, o_step = H ? 1 : wo;
+            int16_t *o = H ? outS + chain * PO : outS + chain;
+            const int a_step = H ? 1 : PA, r_step = H ? 1 : PR, o_step = H ? 1 : PO;
             int bw = 0x7fffffff, bf;
             if (repair) bf = pyr_segment(a, rr, a_step, r_step, o, o_step, navg, xs, xs, xe, state, false, bw);
             else if (xs < kPyrWarm + 1) { bf = pyr_segment(a, rr, a_step, r_step, o, o_step, navg, 0, xs, xe, 0, true, bw); if (xs == 0) bw = 0x7fffffff; else bw = 0x7ffffffe; }
@@ -432,7 +445,7 @@ __global__ void __launch_bounds__(1024) k_inv_squeeze_pyramid(PyrParams P) {
             if (!repair) bwS[item] = bw;
             bfS[item] = bf;
         };
-        if (items <= 4096) {
+        if (items <= kPyrMaxItems) {
             for (int item = threadIdx.x; item < items; item += blockDim.x) run_item(item, false, 0);
             __syncthreads();
             for (;;) {
@@ -454,19 +467,23 @@ __global__ void __launch_bounds__(1024) k_inv_squeeze_pyramid(PyrParams P) {
                 }
                 __syncthreads();
             }
-        } else {        // cannot happen for planes within kPyrMaxOut, kept as a safe serial path
+        } else {        // cannot happen for planes the planner admits, kept as a safe serial path
             for (int chain = threadIdx.x; chain < nchain; chain += blockDim.x) {
                 const int16_t *a = H ? avgS + chain * PA : avgS + chain;
                 const int16_t *rr = H ? resS + chain * PR : resS + chain;
-                int16_t *o = H ? L.out + (size_t)chain * wo : L.out + chain;
+                int16_t *o = H ? outS + chain * PO : outS + chain;
                 int bw;
-                pyr_segment(a, rr, H ? 1 : PA, H ? 1 : PR, o, H ? 1 : wo, navg, 0, 0, npair, 0, true, bw);
+                pyr_segment(a, rr, H ? 1 : PA, H ? 1 : PR, o, H ? 1 : PO, navg, 0, 0, npair, 0, true, bw);
             }
         }
         // odd tail: copy of the last average column / row (squeeze.h:129, :217-222)
-        if (H) { if (wo & 1) for (int r = threadIdx.x; r < ha; r += blockDim.x) L.out[(size_t)r * wo + wo - 1] = avgS[r * PA + wa - 1]; }
-        else { if (ho & 1) for (int q = threadIdx.x; q < wa; q += blockDim.x) L.out[(size_t)(ho - 1) * wo + q] = avgS[(ha - 1) * PA + q]; }
-        __syncthreads();        // the level's output (global memory) is complete and visible to the whole block
+        if (H) { if (wo & 1) for (int r = threadIdx.x; r < ha; r += blockDim.x) outS[r * PO + wo - 1] = avgS[r * PA + wa - 1]; }
+        else { if (ho & 1) for (int q = threadIdx.x; q < wa; q += blockDim.x) outS[(ho - 1) * PO + q] = avgS[(ha - 1) * PA + q]; }
+        __syncthreads();
+        // the output of the last level of this launch is what the rest of the chain reads; the levels in between never leave the SM
+        if (last)
+            for (int i = threadIdx.x; i < wo * ho; i += blockDim.x) { const int r = i / wo, q = i - r * wo; L.out[i] = outS[r * PO + q]; }
+        int16_t *t = avgS; avgS = outS; outS = t;
     }
 }
 
@@ -1031,9 +1048,11 @@ static int run_inv_squeeze_plan_per_level(fb_ctx *ctx, const std::vector<FbSqOp>
     auto level_fits = [&](const FbSqOp &o) {
         const long long wo = o.horizontal ? o.wa + o.wr : o.wa, ho = o.horizontal ? o.ha : o.ha + o.hr;
         const long long npair = o.horizontal ? o.wr : o.hr, nchain = o.horizontal ? o.ha : o.wa;
+        const long long wres = o.horizontal ? o.wr : o.wa, hres = o.horizontal ? o.ha : o.hr;
         if (npair <= 0 || wo * ho > kPyrMaxOut) return false;
-        if (nchain * ((npair + kPyrSeg - 1) / kPyrSeg) > 4096) return false;
-        return ((long long)(o.wa + 3) * o.ha + (long long)((o.horizontal ? o.wr : o.wa) + 3) * (o.horizontal ? o.ha : o.hr)) * 2 <= 150 * 1024;
+        if (nchain * ((npair + kPyrSeg - 1) / kPyrSeg) > kPyrMaxItems) return false;
+        // the planes with their shared-memory pitches (at most 3 halfwords of padding per row) must fit the buffers
+        return (wo + 3) * ho <= kPyrBufHalfwords && (long long)(o.wa + 3) * o.ha <= kPyrBufHalfwords && (wres + 3) * hres <= kPyrResHalfwords;
     };
     PyrParams P;
     P.nchains = 0;
@@ -1054,7 +1073,7 @@ static int run_inv_squeeze_plan_per_level(fb_ctx *ctx, const std::vector<FbSqOp>
         P.chain_start[P.nchains] = nlv;
     }
     if (P.nchains > 0) {
-        const size_t smem = 2 * 4096 * sizeof(int) + 150 * 1024 + 64;
+        const size_t smem = 2 * kPyrMaxItems * sizeof(int) + (2 * (size_t)kPyrBufHalfwords + kPyrResHalfwords) * sizeof(int16_t) + 64;
         if (!(ctx->smem_optin & fb_ctx::kOptPyramid)) {
             FB_CUDA(ctx, cudaFuncSetAttribute(k_inv_squeeze_pyramid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ctx->smem_optin |= fb_ctx::kOptPyramid;
