@@ -144,8 +144,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "decode Mpixels/s (bit-exact)", "value": value, "unit": "Mpx/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
         "data": "synthetic", "config": {"workload": f"{args.workload}: {wl.WORKLOADS[args.workload][7]}", "images": n_img},
-        "cpu_baseline": {"value": value, "unit": "Mpx/s", "cores": n_img, "kind": "reference" if use_ref else "port",
-                         "sample": f"{n_img} full decode(s) of the workload image per step, one single-threaded process per image"},
+        "cpu_baseline": {"value": value, "unit": "Mpx/s", "cores": min(n_img, os.cpu_count() or 1), "kind": "reference" if use_ref else "port",
+                         "host_cores": os.cpu_count(),
+                         "sample": f"{n_img} full decode(s) of the workload image per step, one single-threaded process per image, all started together"},
         "e2e": {"value": value, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -426,7 +427,7 @@ def main():
     line = {
         "metric": "decode Mpixels/s (bit-exact)", "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {spec[7]}", "images": n_per_gpu if scaling == "weak" else spec[5], "images_per_gpu": n_per_gpu,
+        "config": {"workload": f"{args.workload}: {spec[7]}", "images": int(total_units), "images_per_gpu": n_per_gpu,
                    "width": w, "height": h, "channels": c,
                    "group_index_sidecar": not args.no_index, "group_index_source": None if args.no_index else imgs[0].get("index_source"),
                    "l2": "256 MiB buffer written between timed steps",

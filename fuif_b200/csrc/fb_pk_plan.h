@@ -4,6 +4,7 @@
 // provides ps_make_tilemap (driver cuTensorMapEncodeTiled in the product, a plain descriptor under the emulator).
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -169,7 +170,8 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
             L.bytes = 0;
             long long total_cg = 0;
             for (size_t j = j0; j < j1; j++) total_cg += (ops[mine[j]].wa + 255) / 256;
-            long long nseg_want = ((long long)sm_count * 8) / (total_cg > 0 ? total_cg : 1);       // ~8 warps per SM, 4 chains each
+            static const int v_warps = getenv("FB_PK_VWARPS") ? atoi(getenv("FB_PK_VWARPS")) : 8;    // resident warps per SM aimed at (4 chains each)
+            long long nseg_want = ((long long)sm_count * v_warps) / (total_cg > 0 ? total_cg : 1);
             if (nseg_want < 1) nseg_want = 1;
             int items = 0;
             for (size_t j = j0; j < j1; j++) {

@@ -627,6 +627,32 @@ __global__ void k_quantize(int16_t *__restrict__ p, size_t n, int q, int inverse
     p[i] = (int16_t)(inverse ? v * q : v / q);      // quantize.h:42 / 63 (rounded_div == n/d, :54)
 }
 
+// 8 samples per thread, 16-byte accesses (planes are 256-byte aligned allocations); the last n % 8 samples by the scalar kernels
+__global__ void k_clamp_vec8(int16_t *__restrict__ p, size_t n8, int lo, int hi) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    uint4 v = reinterpret_cast<uint4 *>(p)[i];
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int a = clampi((int)(short)(w[k] & 0xffffu), lo, hi), b = clampi((int)(short)(w[k] >> 16), lo, hi);
+        w[k] = (uint32_t)(uint16_t)a | ((uint32_t)(uint16_t)b << 16);
+    }
+    reinterpret_cast<uint4 *>(p)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+__global__ void k_quantize_vec8(int16_t *__restrict__ p, size_t n8, int q, int inverse) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    uint4 v = reinterpret_cast<uint4 *>(p)[i];
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int a = (int)(short)(w[k] & 0xffffu), b = (int)(short)(w[k] >> 16);
+        const int ra = inverse ? a * q : a / q, rb = inverse ? b * q : b / q;      // quantize.h:42 / 63, int16 wrap on the store
+        w[k] = (uint32_t)(uint16_t)ra | ((uint32_t)(uint16_t)rb << 16);
+    }
+    reinterpret_cast<uint4 *>(p)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
 __global__ void k_clamp(int16_t *__restrict__ p, size_t n, int lo, int hi) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1334,14 +1360,28 @@ int fb_launch_ycbcr(fb_ctx *ctx, int16_t *c0, int16_t *c1, int16_t *c2, size_t n
 }
 int fb_launch_quantize(fb_ctx *ctx, int16_t *p, size_t n, int q, int inverse) {
     if (!n) return FB_OK;
-    k_quantize<<<nblocks(n, 256), 256, 0, ctx->stream>>>(p, n, q, inverse);
-    FB_LAUNCH_CHECK(ctx);
+    const size_t n8 = (reinterpret_cast<uintptr_t>(p) & 15) == 0 ? n / 8 : 0;
+    if (n8) {
+        k_quantize_vec8<<<nblocks(n8, 256), 256, 0, ctx->stream>>>(p, n8, q, inverse);
+        FB_LAUNCH_CHECK(ctx);
+    }
+    if (n > 8 * n8) {
+        k_quantize<<<nblocks(n - 8 * n8, 256), 256, 0, ctx->stream>>>(p + 8 * n8, n - 8 * n8, q, inverse);
+        FB_LAUNCH_CHECK(ctx);
+    }
     return FB_OK;
 }
 int fb_launch_clamp(fb_ctx *ctx, int16_t *p, size_t n, int lo, int hi) {
     if (!n) return FB_OK;
-    k_clamp<<<nblocks(n, 256), 256, 0, ctx->stream>>>(p, n, lo, hi);
-    FB_LAUNCH_CHECK(ctx);
+    const size_t n8 = (reinterpret_cast<uintptr_t>(p) & 15) == 0 ? n / 8 : 0;
+    if (n8) {
+        k_clamp_vec8<<<nblocks(n8, 256), 256, 0, ctx->stream>>>(p, n8, lo, hi);
+        FB_LAUNCH_CHECK(ctx);
+    }
+    if (n > 8 * n8) {
+        k_clamp<<<nblocks(n - 8 * n8, 256), 256, 0, ctx->stream>>>(p + 8 * n8, n - 8 * n8, lo, hi);
+        FB_LAUNCH_CHECK(ctx);
+    }
     return FB_OK;
 }
 int fb_launch_inv_dct(fb_ctx *ctx, const int16_t *const *planes64, int16_t *out, int bw, int bh, float dc_offset) {
