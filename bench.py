@@ -183,6 +183,12 @@ def main():
         units = shard.replica_units(spec[5])
         scaling = "weak"
     n_per_gpu = len(units)
+    if world > 1:           # rank 0 encodes / indexes whatever is missing for EVERY rank first (one set of host processes, one GPU decode); the others then find the cache
+        all_units = sorted(set(u for r in range(world) for u in (shard.split_batch(spec[5], r, world) if args.strong else
+                                                                  shard.units_for_rank(spec[5], r) if args.distinct_images else shard.replica_units(spec[5]))))
+        if rank == 0:
+            wl.prepare_images(args.workload, all_units, want_index=not args.no_index)
+        dist.barrier()
     imgs = wl.prepare_images(args.workload, units, want_index=not args.no_index)
     w, h, c, maxval = spec[0], spec[1], spec[2], spec[3]
     mpix_rank = n_per_gpu * w * h / 1e6

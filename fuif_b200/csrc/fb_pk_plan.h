@@ -180,7 +180,8 @@ inline StepPlan plan_step(const std::vector<StepOp> &ops, bool horizontal, const
                 int S = (int)((a.ha + nseg_want - 1) / nseg_want);
                 S = (S + 7) / 8 * 8;
                 if (S < 16) S = 16;
-                while ((a.ha + S - 1) / S > 32) S += 8;        // the verification pass reads two 16-byte words per segment and lane
+                static const int v_maxseg = getenv("FB_PK_VMAXSEG") ? atoi(getenv("FB_PK_VMAXSEG")) : 32;
+                while ((a.ha + S - 1) / S > v_maxseg) S += 8;  // the verification pass reads two 16-byte words per segment and lane
                 J.avg = a.avg; J.res = a.res; J.out = a.out; J.w = a.wa; J.ha = a.ha; J.S = S; J.nseg = (a.ha + S - 1) / S; J.ncg = (a.wa + 255) / 256;
                 J.item0 = items;
                 J.k1 = 0x00010001u;

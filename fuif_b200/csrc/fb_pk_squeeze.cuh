@@ -59,7 +59,7 @@ constexpr int kSwzA = kHChunk * 2 >= 32 ? kHChunk * 2 : 0;          // average /
 constexpr int kSwzO = 2 * kHChunk * 2 >= 32 ? 2 * kHChunk * 2 : 0;  // Y / output tiles: 64-byte rows -> SWIZZLE_64B
 static_assert(kSwzA <= 64 && kSwzO <= 64, "swizzle spans");
 constexpr int kVWarm = 12;          // warm-up pairs of a vertical segment (8 missed about once per 4096^2 image: a repair costs tens of microseconds)
-constexpr int kVDepth = 4;          // rows of register prefetch in the vertical kernel
+constexpr int kVDepthDefault = 6;   // rows of register prefetch in the vertical kernel (template parameter of k_pk_vsq)
 constexpr int kMaxHJobs = 8;
 constexpr int kMaxVJobs = 24;
 
@@ -672,6 +672,7 @@ FB_DEV void v_verify(const VJob &J, int x) {
     }
 }
 
+template <int kVDepth>
 FB_DEV void v_item(const VJob &J, int cg, int g, int lane) {
     const int x = (cg * 32 + lane) * 8, w = J.w, last_row = J.ha - 1;
     const bool active = x < w;
@@ -747,6 +748,7 @@ FB_DEV void v_item(const VJob &J, int cg, int g, int lane) {
     }
 }
 
+template <int kVDepth>
 FB_KERNEL(256) k_pk_vsq(const FB_GRID_CONSTANT VJobs jobs, int warps_per_block) {
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
     const int item = (int)blockIdx.x * warps_per_block + warp;
@@ -756,7 +758,7 @@ FB_KERNEL(256) k_pk_vsq(const FB_GRID_CONSTANT VJobs jobs, int warps_per_block) 
     const VJob &J = jobs.j[ji];
     // consecutive items = consecutive column groups of the same segment (neighbouring warps touch neighbouring lines)
     const int local = item - J.item0, g = local / J.ncg, cg = local - g * J.ncg;
-    v_item(J, cg, g, lane);
+    v_item<kVDepth>(J, cg, g, lane);
 }
 
 }  // namespace ps

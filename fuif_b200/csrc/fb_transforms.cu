@@ -960,7 +960,10 @@ static int pk_run_step(fb_ctx *ctx, const std::vector<ps::StepOp> &ops, bool hor
         ctx->mark(L.ep == fq::kEpYCoCg ? "k_pk_hsq(ycocg)" : "k_pk_hsq", L.bytes);
     }
     for (auto &L : P.v) {
-        ps::k_pk_vsq<<<L.grid, 32 * L.warps_per_block, 0, ctx->stream>>>(L.jobs, L.warps_per_block);
+        static const int vdepth = getenv("FB_PK_VDEPTH") ? atoi(getenv("FB_PK_VDEPTH")) : ps::kVDepthDefault;
+        if (vdepth == 8) ps::k_pk_vsq<8><<<L.grid, 32 * L.warps_per_block, 0, ctx->stream>>>(L.jobs, L.warps_per_block);
+        else if (vdepth == 4) ps::k_pk_vsq<4><<<L.grid, 32 * L.warps_per_block, 0, ctx->stream>>>(L.jobs, L.warps_per_block);
+        else ps::k_pk_vsq<ps::kVDepthDefault><<<L.grid, 32 * L.warps_per_block, 0, ctx->stream>>>(L.jobs, L.warps_per_block);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { ctx->err = std::string("k_pk_vsq launch: ") + cudaGetErrorString(e); return FB_ERR_CUDA; }
         ctx->launches++;

@@ -307,7 +307,7 @@ int emu_run_pk(int nplanes, int16_t **planes, int nops, const int *opdesc, const
         for (auto &L : P.v) {
             const ps::VJobs J = L.jobs;
             const int wpb = L.warps_per_block;
-            cuemu::launch((unsigned)L.grid, (unsigned)(32 * wpb), 0, false, [&]() { ps::k_pk_vsq(J, wpb); });
+            cuemu::launch((unsigned)L.grid, (unsigned)(32 * wpb), 0, false, [&]() { ps::k_pk_vsq<ps::kVDepthDefault>(J, wpb); });
             stats[0]++;
             stats[1] += J.n;
         }
