@@ -6,6 +6,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/fuif_b200.h"
@@ -35,10 +36,16 @@ struct fb_ctx {
     int *pk_stats = nullptr;
     int pk_mode = 1;
     int sq_maxval = -1;         // maxval of the image whose Squeeze is being undone (packed kernels: 0 .. 1023 only)
+    // Plane memory recycled on the host side: every plane is used on this context's ONE stream, so a freed plane can be handed out
+    // again without a driver call (60 cudaMallocAsync + 60 cudaFreeAsync per 4096^2 undo_transforms cost more host time than the
+    // whole chain takes on the GPU).  Keyed by the rounded byte size; emptied by fb_ctx_destroy or when it holds more than 16 GiB.
+    std::unordered_map<size_t, std::vector<void *>> plane_pool;
+    size_t plane_pool_bytes = 0;
+    std::unordered_map<void *, size_t> plane_sizes;       // every live plane allocation of this context -> its rounded size
     // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: the opt-ins are remembered per context (= per
     // device), not per process, so that a context on a second GPU of the same process gets them too
     unsigned smem_optin = 0;
-    enum { kOptHsqTiled = 1, kOptPyramid = 2, kOptDirect = 4, kOptFq = 8 };
+    enum { kOptHsqTiled = 1, kOptPyramid = 2, kOptDirect = 4, kOptFq = 8, kOptPkH = 16 /* << variant, 5 bits */ };
     // FB_KERNEL_TIMING=1: a CUDA event after every launch, dumped by fb_ctx_synchronize (development aid)
     bool timing = false, timing_stderr = false;
     struct Mark { std::string name; cudaEvent_t ev; double bytes; };
@@ -84,6 +91,7 @@ struct fb_image {
 // plane memory (stream-ordered pool)
 int fb_plane_alloc(fb_ctx *ctx, size_t nsamples, int16_t **out);
 void fb_plane_free(fb_ctx *ctx, int16_t *p);
+void fb_plane_pool_release(fb_ctx *ctx);
 
 // ---- transform launchers (fb_transforms.cu).  All enqueue on ctx->stream and bump ctx->launches. -------------
 

@@ -67,6 +67,8 @@ extern "C" void fb_ctx_destroy(fb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     fb_maniac_release(ctx);
+    fb_plane_pool_release(ctx);
+    cudaStreamSynchronize(ctx->stream);
     if (ctx->fq_counters) cudaFree(ctx->fq_counters);
     if (ctx->pk_scratch) cudaFree(ctx->pk_scratch);
     if (ctx->pk_counters) cudaFree(ctx->pk_counters);
@@ -145,14 +147,36 @@ int fb_plane_alloc(fb_ctx *ctx, size_t nsamples, int16_t **out) {
     *out = nullptr;
     size_t bytes = std::max<size_t>(nsamples * sizeof(int16_t), 16);
     bytes = (bytes + 255) & ~(size_t)255;
+    auto it = ctx->plane_pool.find(bytes);
+    if (it != ctx->plane_pool.end() && !it->second.empty()) {
+        *out = (int16_t *)it->second.back();
+        it->second.pop_back();
+        ctx->plane_pool_bytes -= bytes;
+        return FB_OK;
+    }
     void *p = nullptr;
     FB_CUDA(ctx, cudaMallocAsync(&p, bytes, ctx->stream));
+    ctx->plane_sizes[p] = bytes;
     *out = (int16_t *)p;
     return FB_OK;
 }
 
 void fb_plane_free(fb_ctx *ctx, int16_t *p) {
-    if (p) cudaFreeAsync(p, ctx->stream);
+    if (!p) return;
+    auto it = ctx->plane_sizes.find(p);
+    if (it == ctx->plane_sizes.end() || ctx->plane_pool_bytes > ((size_t)16 << 30)) {
+        if (it != ctx->plane_sizes.end()) ctx->plane_sizes.erase(it);
+        cudaFreeAsync(p, ctx->stream);
+        return;
+    }
+    ctx->plane_pool[it->second].push_back(p);
+    ctx->plane_pool_bytes += it->second;
+}
+void fb_plane_pool_release(fb_ctx *ctx) {
+    for (auto &kv : ctx->plane_pool)
+        for (void *q : kv.second) { ctx->plane_sizes.erase(q); cudaFreeAsync(q, ctx->stream); }
+    ctx->plane_pool.clear();
+    ctx->plane_pool_bytes = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------

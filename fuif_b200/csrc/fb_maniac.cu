@@ -38,6 +38,7 @@
 namespace {
 
 constexpr int kMaxNodes = 65536;
+constexpr int kStatusTreeTooLarge = 100;   // internal image status: a MANIAC tree with more than 65535 nodes (the reference has no limit: std::vector)
 constexpr int kMaxProps = 64;
 constexpr int NB_NONREF = 13;           // context_predict.h:210
 constexpr int MAX_BIT_DEPTH = 15;       // config.h:5
@@ -361,7 +362,7 @@ __device__ bool read_tree(Rac &rac, const uint16_t *__restrict__ mtable, int (*r
             if (oldmin >= oldmax) return false;                                     // "Invalid tree", compound.h:285-288
             int splitval = read_int2(rac, mtable, coder[2], oldmin, oldmax - 1);
             nodes[pos].splitval = splitval;
-            if (nnodes + 2 > 65535) return false;
+            if (nnodes + 2 > 65535) { nnodes = -1; return false; }       // a valid but larger tree than this decoder holds (child ids are 16 bit): reported as unsupported, not as corrupt
             int child = nnodes;
             nodes[pos].child = (unsigned short)child;
             nodes[child].property = -1; nodes[child].child = 0; nodes[child].splitval = 0;
@@ -1178,7 +1179,10 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
     }
 
     int nnodes = 0, tree_ok = 1;
-    if (lane == 0) tree_ok = read_tree(rac, P.meta_table, pr, nprops, ws.nodes, nnodes, ws.stack, sm.coder) ? 1 : 0;
+    if (lane == 0) {
+        tree_ok = read_tree(rac, P.meta_table, pr, nprops, ws.nodes, nnodes, ws.stack, sm.coder) ? 1 : 0;
+        if (!tree_ok && nnodes < 0) img.status = kStatusTreeTooLarge;
+    }
     tree_ok = __shfl_sync(0xffffffffu, tree_ok, 0);
     nnodes = __shfl_sync(0xffffffffu, nnodes, 0);
     if (!tree_ok) { const bool st = STOPPED(); SYNC_IO(); return corrupt_or_truncated(st, img.ch[beginc], lane); }
@@ -1704,6 +1708,7 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
             if (d.group_off >= 0) { img->group_off.push_back(d.group_off); img->group_first.push_back((int32_t)i); }
         }
         if (himg[b].status == FB_ERR_UNSUPPORTED) { ctx->err = "max_properties > 18 is not supported by the GPU context model"; rc = FB_ERR_UNSUPPORTED; }
+        else if (himg[b].status == kStatusTreeTooLarge) { ctx->err = "a MANIAC tree of this file has more than 65535 nodes: not supported by this decoder (image " + std::to_string(b) + ")"; rc = FB_ERR_UNSUPPORTED; }
         else if (himg[b].status) { ctx->err = "corrupt FUIF stream (image " + std::to_string(b) + ")"; rc = FB_ERR_INVALID; }
         coff += img->ch.size();
     }

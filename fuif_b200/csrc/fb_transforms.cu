@@ -18,6 +18,8 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
+#include <unordered_map>
 
 namespace {
 
@@ -904,21 +906,41 @@ bool ps_make_tilemap(TileMap *m, const void *base, int w, int h, int box_w, int 
     EncodeTiledFn fn = encode_tiled();
     if (!fn || (reinterpret_cast<uintptr_t>(base) & 15) || (w & 7) || box_w > 256 || box_h > 256) return false;
     if (swizzle_bytes && swizzle_bytes != box_w * 2) return false;        // the swizzle span is the tile row
+    // Planes come out of a per-context pool, so the same (address, shape, box) recurs with every image: the encoded
+    // descriptor (a pure function of these values) is kept instead of calling into the driver again.
+    struct Key { const void *b; int w, h, bw, bh, s; bool operator==(const Key &o) const { return b == o.b && w == o.w && h == o.h && bw == o.bw && bh == o.bh && s == o.s; } };
+    struct KeyHash { size_t operator()(const Key &k) const { return std::hash<const void *>()(k.b) ^ ((size_t)k.w * 1000003u) ^ ((size_t)k.h * 10007u) ^ ((size_t)k.bw << 20) ^ ((size_t)k.bh << 28) ^ (size_t)k.s; } };
+    static std::mutex mu;
+    static std::unordered_map<Key, CUtensorMap, KeyHash> cache;
+    const Key key{base, w, h, box_w, box_h, swizzle_bytes};
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *m = it->second; return true; }
+        if (cache.size() > 65536) cache.clear();
+    }
     const CUtensorMapSwizzle swz = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
     const cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)h};
     const cuuint64_t strides[1] = {(cuuint64_t)w * sizeof(int16_t)};
     const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
     const cuuint32_t estr[2] = {1, 1};
-    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    std::lock_guard<std::mutex> lk(mu);
+    cache.emplace(key, *m);
+    return true;
 }
 }  // namespace ps
 
 template <int NP, int EP>
 static cudaError_t pk_launch_h(fb_ctx *ctx, const ps::HLaunch &L) {
-    // per device, not per process: a context on a second GPU needs the opt-in too
-    cudaError_t e = cudaFuncSetAttribute(ps::k_pk_hsq<NP, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
-    if (e != cudaSuccess) return e;
+    // per device, not per process: a context on a second GPU needs the opt-in too (remembered per context, one bit per variant)
+    const unsigned bit = (unsigned)fb_ctx::kOptPkH << ((NP - 1) * 3 + EP);
+    if (!(ctx->smem_optin & bit)) {
+        cudaError_t e = cudaFuncSetAttribute(ps::k_pk_hsq<NP, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+        if (e != cudaSuccess) return e;
+        ctx->smem_optin |= bit;
+    }
     ps::k_pk_hsq<NP, EP><<<L.grid, 32 * L.warps_per_block, L.smem, ctx->stream>>>(L.jobs, L.warps_per_block, L.smem_per_warp);
     return cudaGetLastError();
 }
