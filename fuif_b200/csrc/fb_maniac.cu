@@ -1655,7 +1655,15 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         // streams are ordered image-major, groups ascending: dependencies always point to lower stream ids
         FB_CUDA(ctx, cudaMallocAsync((void **)&streams_dev, nstreams * sizeof(DStream), ctx->stream));
         FB_CUDA(ctx, cudaMemcpyAsync(streams_dev, streams.data(), nstreams * sizeof(DStream), cudaMemcpyHostToDevice, ctx->stream));
-        const int nslots = std::min((nstreams + 1) / 2 * 2, ctx->sm_count * 2);        // scratch slots: one per stream in flight
+        // Throughput shape for big batches: 8 streams per block, each ONE warp on the one-warp decode path (no walkers).  A stream is
+        // slower (no run-ahead) but four times as many are in flight; measured on 64 x 1080p (3520 streams): 41.5 -> 71.1 Mpx/s
+        // (4 per block: 61.4, 16 per block: 47.3 -- 13 KB of shared memory per stream is too little for the leaf cache).  Taken when
+        // the batch has at least 16 streams per SM; FB_MANIAC_SPB=n forces n (3..16) from sm_count * n streams on, 0 / 1 disables.
+        static const int env_spb = getenv("FB_MANIAC_SPB") ? atoi(getenv("FB_MANIAC_SPB")) : -1;
+        int spb_many = 0;
+        if (env_spb > 2 && env_spb <= 16) { if (nstreams >= ctx->sm_count * env_spb) spb_many = env_spb; }
+        else if (env_spb < 0 && nstreams >= ctx->sm_count * 16) spb_many = 8;
+        const int nslots = spb_many ? ctx->sm_count * spb_many : std::min((nstreams + 1) / 2 * 2, ctx->sm_count * 2);        // scratch slots: one per stream in flight
         int rc = ensure_state(ctx, cutoff, alpha, nslots, maxw);
         if (rc) return rc;
         ManiacState *st = (ManiacState *)ctx->maniac_state;
@@ -1675,8 +1683,8 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         // property rows).  Few streams (one image) => one stream per SM with 8 walkers (value ranges up to 256); batches =>
         // two streams per SM with 6 walkers each (ranges up to 192; wider ranges fall back to the decoder's own walk).
         const int per_sm = (nstreams + ctx->sm_count - 1) / ctx->sm_count;
-        const int wpb = std::max(1, std::min(2, per_sm));          // streams per block
-        P.helpers = getenv("FB_MANIAC_NO_WALKERS") ? 0 : (wpb == 1 ? 15 : 7);     // 16 / 8 warps per stream: decoder, 12 / 6 walkers, idle warps
+        const int wpb = spb_many ? spb_many : std::max(1, std::min(2, per_sm));          // streams per block
+        P.helpers = (getenv("FB_MANIAC_NO_WALKERS") || spb_many) ? 0 : (wpb == 1 ? 15 : 7);     // 16 / 8 warps per stream: decoder, 12 / 6 walkers, idle warps
         const int nblocks = std::min((nstreams + wpb - 1) / wpb, ctx->sm_count);
         const size_t block_smem = 226 * 1024;
         const size_t warp_smem = ((block_smem - 16384) / wpb) & ~(size_t)15;
