@@ -32,6 +32,9 @@ FB_OK = 0
 FB_OPT_SQUEEZE_MODE = 1
 FB_OPT_KERNEL_TIMING = 2
 FB_OPT_SQUEEZE_PACKED = 3
+FB_OPT_ENTROPY_BACKEND = 4
+FB_OPT_HOST_THREADS = 5
+FB_ENTROPY_GPU, FB_ENTROPY_HOST = 0, 1
 
 
 class FuifError(RuntimeError):
@@ -64,7 +67,7 @@ ABI_SYMBOLS = [
     "fb_image_plane_device_ptr", "fb_image_download_plane", "fb_image_download_interleaved",
     "fb_image_undo_transforms", "fb_image_do_transform", "fb_image_recompute_minmax",
     "fb_decode_to_pixels", "fb_peek_header", "fb_ctx_set_option", "fb_ctx_counter", "fb_ctx_timing_report",
-    "fb_encode", "fb_free", "fb_selftest_packed",
+    "fb_encode", "fb_free", "fb_selftest_packed", "fb_host_decode", "fb_host_last_error", "fb_image_upload",
 ]
 
 _lib = None
@@ -116,6 +119,10 @@ def load_library():
     L.fb_encode.argtypes = [vp, vp, C.POINTER(EncodeOptions), C.POINTER(vp), C.POINTER(C.c_size_t), i64p, i32p, C.c_int, C.POINTER(C.c_int)]
     L.fb_free.argtypes = [vp]
     L.fb_free.restype = None
+    L.fb_host_decode.argtypes = [vp, C.c_size_t, C.POINTER(DecodeOptions), i64p, i32p, C.c_int, C.c_int, C.POINTER(vp)]
+    L.fb_host_last_error.argtypes = []
+    L.fb_host_last_error.restype = C.c_char_p
+    L.fb_image_upload.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -239,6 +246,17 @@ class Context:
         self.check(self.lib.fb_selftest_packed(self.h, which, seed, scale, maxval, C.byref(n)), "fb_selftest_packed")
         return int(n.value)
 
+    def set_entropy_backend(self, backend: str, threads: int = 0) -> None:
+        """'gpu' (default): k_maniac_decode; 'host': fuif_decode_channel on CPU threads (0 = one per hardware thread), planes uploaded
+        afterwards -- the faster backend for ONE large image with a group index.  Identical planes and errors."""
+        self.check(self.lib.fb_ctx_set_option(self.h, FB_OPT_ENTROPY_BACKEND, {"gpu": FB_ENTROPY_GPU, "host": FB_ENTROPY_HOST}[backend]), "fb_ctx_set_option")
+        self.check(self.lib.fb_ctx_set_option(self.h, FB_OPT_HOST_THREADS, threads), "fb_ctx_set_option")
+
+    @property
+    def host_threads_used(self) -> int:
+        """Threads the host entropy backend used in its last call."""
+        return int(self.lib.fb_ctx_counter(self.h, 4))
+
     def enable_kernel_timing(self, on: bool = True) -> None:
         self.check(self.lib.fb_ctx_set_option(self.h, FB_OPT_KERNEL_TIMING, 1 if on else 0), "fb_ctx_set_option")
 
@@ -251,6 +269,19 @@ class Context:
             name, us, b = ln.split("\t")
             out.append((name, float(us), float(b)))
         return out
+
+
+class HostContext:
+    """What stands behind a host-only Image (fuif_host_decode): the library without a GPU."""
+
+    def __init__(self):
+        self.lib = load_library()
+        self.h = True       # "open"; never handed to the library
+        self.device = -1
+
+    def check(self, rc: int, what: str):
+        if rc != FB_OK:
+            raise FuifError(f"{what} failed ({rc}): {self.lib.fb_host_last_error().decode()}")
 
 
 _default_ctx = None
@@ -281,6 +312,12 @@ class Image:
             if self.ctx.h:      # a closed context has already released the device
                 self.ctx.lib.fb_image_destroy(self._handle)
             self._handle = None
+
+    def upload(self, ctx: "Context") -> "Image":
+        """Moves a host-only image (fuif_host_decode) into ctx's HBM."""
+        ctx.check(ctx.lib.fb_image_upload(ctx.h, self._handle), "fb_image_upload")
+        self.ctx = ctx
+        return self
 
     # ---- construction ----------------------------------------------------------------------------------------
     @staticmethod
@@ -416,6 +453,18 @@ def fuif_decode(data: bytes, options: fuif_options = default_fuif_options, ctx: 
         ptr, size = buf.ctypes.data, buf.size
     ctx.check(ctx.lib.fb_decode(ctx.h, ptr, size, C.byref(opts), arr, farr, n, C.byref(h)), "fb_decode")
     return Image(ctx, h)
+
+
+def fuif_host_decode(data: bytes, options: fuif_options = default_fuif_options, group_index=None, threads: int = 0) -> Image:
+    """fuif_decode on CPU threads only (fb_host_decode): no GPU, no Context.  The Image lives in host memory: planes, ranges, the
+    transform list and the group index can be read; Image.upload(ctx) moves it to a GPU for everything else."""
+    hc = HostContext()
+    arr, farr, n = _index_args(group_index)
+    h = C.c_void_p()
+    opts = options._c()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    hc.check(hc.lib.fb_host_decode(buf.ctypes.data, buf.size, C.byref(opts), arr, farr, n, threads, C.byref(h)), "fb_host_decode")
+    return Image(hc, h)
 
 
 def fuif_encode(image: "Image", options: fuif_options = default_fuif_options, want_index: bool = False):

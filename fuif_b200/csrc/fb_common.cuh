@@ -45,6 +45,12 @@ struct fb_ctx {
     // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: the opt-ins are remembered per context (= per
     // device), not per process, so that a context on a second GPU of the same process gets them too
     unsigned smem_optin = 0;
+    // Entropy backend (FB_OPT_ENTROPY_BACKEND): 0 = k_maniac_decode on the GPU (default), 1 = host threads (fb_host_entropy.cpp),
+    // planes uploaded afterwards.  host_threads 0 = one per hardware thread.  host_stage: pinned staging the host backend decodes
+    // into (grow-only, reused from call to call).  device < 0 marks the context of a host-only image (fb_host_decode): no CUDA at all.
+    int entropy_backend = 0, host_threads = 0, host_threads_used = 0;
+    void *host_stage = nullptr;
+    size_t host_stage_bytes = 0;
     enum { kOptHsqTiled = 1, kOptPyramid = 2, kOptDirect = 4, kOptFq = 8, kOptPkH = 16 /* << variant, 5 bits */ };
     // FB_KERNEL_TIMING=1: a CUDA event after every launch, dumped by fb_ctx_synchronize (development aid)
     bool timing = false, timing_stderr = false;
@@ -63,6 +69,7 @@ struct fb_ctx {
 struct FbChan {
     fb_plane_desc d;          // mirrors Channel (reference image/image.h:54-91)
     int16_t *dev = nullptr;   // w*h samples in HBM, row-major, no padding; nullptr = not decoded (data.size()==0)
+    int16_t *host = nullptr;  // host-only images (fb_host_decode): the samples in host memory (inside fb_image::host_block)
 };
 
 struct FbXform {
@@ -77,6 +84,9 @@ struct fb_image {
     std::vector<FbXform> tr;
     std::vector<int64_t> group_off;
     std::vector<int32_t> group_first;
+    // host-only image (made by fb_host_decode, no GPU involved): planes live in host_block until fb_image_upload moves them
+    bool on_host = false, owns_ctx = false;
+    std::vector<int16_t> host_block;
 };
 
 #define FB_CUDA(ctx, call)                                                                          \

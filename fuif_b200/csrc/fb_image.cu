@@ -52,6 +52,8 @@ extern "C" int fb_ctx_create(int device, void *stream, fb_ctx **out) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     ctx->timing_stderr = getenv("FB_KERNEL_TIMING") != nullptr;
     ctx->timing = ctx->timing_stderr;
+    // FUIF_B200_ENTROPY=host|gpu presets FB_OPT_ENTROPY_BACKEND (fb_ctx_set_option still overrides it)
+    if (const char *e = getenv("FUIF_B200_ENTROPY")) ctx->entropy_backend = (strcmp(e, "host") == 0) ? FB_ENTROPY_HOST : FB_ENTROPY_GPU;
     // keep freed plane memory in the stream-ordered pool instead of returning it to the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -73,6 +75,7 @@ extern "C" void fb_ctx_destroy(fb_ctx *ctx) {
     if (ctx->pk_scratch) cudaFree(ctx->pk_scratch);
     if (ctx->pk_counters) cudaFree(ctx->pk_counters);
     if (ctx->pk_stats) cudaFree(ctx->pk_stats);
+    if (ctx->host_stage) cudaFreeHost(ctx->host_stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -99,11 +102,14 @@ extern "C" int fb_ctx_set_option(fb_ctx *ctx, int option, int value) {
     if (!ctx) return FB_ERR_INVALID;
     if (option == FB_OPT_SQUEEZE_MODE && value >= 0 && value <= 4) { ctx->fq_mode = value; return FB_OK; }
     if (option == FB_OPT_SQUEEZE_PACKED && value >= 0 && value <= 1) { ctx->pk_mode = value; return FB_OK; }
+    if (option == FB_OPT_ENTROPY_BACKEND && (value == FB_ENTROPY_GPU || value == FB_ENTROPY_HOST)) { ctx->entropy_backend = value; return FB_OK; }
+    if (option == FB_OPT_HOST_THREADS && value >= 0 && value <= 4096) { ctx->host_threads = value; return FB_OK; }
     if (option == FB_OPT_KERNEL_TIMING) { ctx->timing = value != 0 || ctx->timing_stderr; return FB_OK; }
     return FB_ERR_INVALID;
 }
 
 extern "C" long long fb_ctx_counter(fb_ctx *ctx, int which) {
+    if (ctx && which == FB_COUNTER_HOST_THREADS) return ctx->host_threads_used;
     if (ctx && (which == FB_COUNTER_PK_REPAIRED || which == FB_COUNTER_PK_RANGE_FLAGGED)) {
         if (!ctx->pk_stats) return 0;
         int v[2] = {0, 0};
@@ -220,10 +226,19 @@ static int chan_materialize(fb_ctx *ctx, FbChan &c) {
 
 extern "C" void fb_image_destroy(fb_image *img) {
     if (!img) return;
-    cudaSetDevice(img->ctx->device);
-    for (auto &c : img->ch) fb_plane_free(img->ctx, c.dev);
+    if (img->ctx->device >= 0) {
+        cudaSetDevice(img->ctx->device);
+        for (auto &c : img->ch) fb_plane_free(img->ctx, c.dev);
+    }
+    if (img->owns_ctx) delete img->ctx;     // the CUDA-free context of a host-only image (fb_host_decode)
     delete img;
 }
+
+// entry points that compute on the planes need them in HBM
+#define FB_NEEDS_DEVICE(img)                                                                                              \
+    do {                                                                                                                  \
+        if ((img) && (img)->on_host) { (img)->ctx->err = "this image lives in host memory (fb_host_decode): fb_image_upload() it first"; return FB_ERR_INVALID; } \
+    } while (0)
 
 // ---------------------------------------------------------------------------------------------------------
 // Squeeze bookkeeping (reference transform/squeeze.h:266-408)
@@ -1149,6 +1164,7 @@ static int fb_image_undo_transforms_impl(fb_image *img, int keep) {
 }
 
 extern "C" int fb_image_undo_transforms(fb_image *img, int keep) {
+    FB_NEEDS_DEVICE(img);
     return abi_guard(img ? img->ctx : nullptr, [&]() { return fb_image_undo_transforms_impl(img, keep); });
 }
 
@@ -1185,11 +1201,13 @@ static int fb_image_do_transform_impl(fb_image *img, int32_t id, const int32_t *
 }
 
 extern "C" int fb_image_do_transform(fb_image *img, int32_t id, const int32_t *params, int nparams, int *applied_out) {
+    FB_NEEDS_DEVICE(img);
     return abi_guard(img ? img->ctx : nullptr, [&]() { return fb_image_do_transform_impl(img, id, params, nparams, applied_out); });
 }
 
 extern "C" int fb_image_recompute_minmax(fb_image *img) {
     if (!img) return FB_ERR_INVALID;
+    FB_NEEDS_DEVICE(img);
     fb_ctx *ctx = img->ctx;
     cudaSetDevice(ctx->device);
     const size_t n = img->ch.size();
@@ -1259,7 +1277,7 @@ extern "C" int fb_image_get_info(fb_image *img, fb_image_info *info) {
 extern "C" int fb_image_get_plane(fb_image *img, int i, fb_plane_desc *desc) {
     if (!img || !desc || i < 0 || i >= (int)img->ch.size()) return FB_ERR_INVALID;
     *desc = img->ch[i].d;
-    desc->decoded = img->ch[i].dev ? 1 : 0;
+    desc->decoded = (img->ch[i].dev || img->ch[i].host) ? 1 : 0;
     return FB_OK;
 }
 
@@ -1276,6 +1294,10 @@ extern "C" void *fb_image_plane_device_ptr(fb_image *img, int i) {
 }
 
 extern "C" int fb_image_download_plane(fb_image *img, int i, int16_t *dst) {
+    if (img && dst && img->on_host && i >= 0 && i < (int)img->ch.size() && img->ch[i].host) {
+        memcpy(dst, img->ch[i].host, chan_samples(img->ch[i].d) * sizeof(int16_t));
+        return FB_OK;
+    }
     if (!img || !dst || i < 0 || i >= (int)img->ch.size() || !img->ch[i].dev) return FB_ERR_INVALID;
     fb_ctx *ctx = img->ctx;
     cudaSetDevice(ctx->device);
@@ -1286,6 +1308,7 @@ extern "C" int fb_image_download_plane(fb_image *img, int i, int16_t *dst) {
 }
 
 extern "C" int fb_image_download_interleaved(fb_image *img, int nch, int bps, void *dst) {
+    FB_NEEDS_DEVICE(img);
     if (!img || !dst || nch < 1 || nch > 8 || nch > (int)img->ch.size() || (bps != 1 && bps != 2)) return FB_ERR_INVALID;
     fb_ctx *ctx = img->ctx;
     cudaSetDevice(ctx->device);
@@ -1394,7 +1417,9 @@ static int parse_container(fb_ctx *ctx, const uint8_t *bytes_in, size_t nbytes, 
     const uint8_t *bytes = bytes_in;
     const uint8_t *bytes_dev = nullptr;
     cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, bytes_in) == cudaSuccess && attr.type == cudaMemoryTypeDevice) {
+    if (ctx->device < 0) {
+        // host-only decode (fb_host_decode): the bytes are host memory by contract, no CUDA call is made
+    } else if (cudaPointerGetAttributes(&attr, bytes_in) == cudaSuccess && attr.type == cudaMemoryTypeDevice) {
         header_copy.resize(std::min<size_t>(nbytes, 4096));
         FB_CUDA(ctx, cudaMemcpyAsync(header_copy.data(), bytes_in, header_copy.size(), cudaMemcpyDeviceToHost, ctx->stream));
         FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1484,6 +1509,59 @@ extern "C" int fb_decode_batch(fb_ctx *ctx, int n_images, const uint8_t *const *
         for (int i = 0; i < n_images; i++) { fb_image_destroy(out[i]); out[i] = nullptr; }
         return rc;
     }
+    return FB_OK;
+}
+
+static thread_local std::string g_host_err;
+extern "C" const char *fb_host_last_error(void) { return g_host_err.c_str(); }
+
+extern "C" int fb_host_decode(const uint8_t *bytes, size_t nbytes, const fb_decode_options *opts, const int64_t *group_index,
+                              const int32_t *group_first, int n_groups, int threads, fb_image **out) {
+    if (!bytes || !out || threads < 0) return FB_ERR_INVALID;
+    *out = nullptr;
+    fb_ctx *hctx = new (std::nothrow) fb_ctx();      // a context without a device: no CUDA call is made on this path
+    if (!hctx) return FB_ERR_NOMEM;
+    hctx->device = -1;
+    hctx->entropy_backend = FB_ENTROPY_HOST;
+    hctx->host_threads = threads;
+    fb_image *img = nullptr;
+    int rc = abi_guard(hctx, [&]() {
+        std::vector<FbManiacJob> jobs(1);
+        std::vector<uint8_t> header;
+        int r = parse_container(hctx, bytes, nbytes, opts, group_index, group_first, n_groups, &img, jobs[0], header);
+        if (!r) r = fb_maniac_decode(hctx, jobs);
+        return r;
+    });
+    if (rc) {
+        g_host_err = hctx->err;
+        if (img) { img->owns_ctx = false; fb_image_destroy(img); }
+        delete hctx;
+        return rc;
+    }
+    img->on_host = true;
+    img->owns_ctx = true;
+    *out = img;
+    return FB_OK;
+}
+
+extern "C" int fb_image_upload(fb_ctx *ctx, fb_image *img) {
+    if (!ctx || !img || ctx->device < 0) return FB_ERR_INVALID;
+    if (!img->on_host) return img->ctx == ctx ? FB_OK : FB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    for (auto &c : img->ch) {
+        if (!c.host) continue;
+        const size_t n = chan_samples(c.d);
+        int rc = fb_plane_alloc(ctx, n, &c.dev);
+        if (rc) return rc;
+        if (n) FB_CUDA(ctx, cudaMemcpyAsync(c.dev, c.host, n * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &c : img->ch) c.host = nullptr;
+    std::vector<int16_t>().swap(img->host_block);
+    if (img->owns_ctx) delete img->ctx;
+    img->ctx = ctx;
+    img->owns_ctx = false;
+    img->on_host = false;
     return FB_OK;
 }
 

@@ -25,6 +25,7 @@
 #define FB_SPIN() fb_emu_yield()
 #else
 #include "fb_common.cuh"
+#include "fb_host_entropy.h"
 #define FB_SPIN()
 #define FB_DYN_SMEM_DECL(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
@@ -1540,6 +1541,172 @@ int host_varint(const uint8_t *p, size_t n, size_t &pos) {
     return -1;
 }
 
+
+// The streams of one file: one per channel group when the caller supplied the groups' byte offsets (the group index), walking
+// the channel list exactly like the loop of fuif_decode (encoding.cpp:708-718); otherwise the whole file as one stream.
+// S = DStream (GPU backend) or fbh::Stream (host-threads backend): same fields.
+template <class S>
+void build_streams(const FbManiacJob &job, int b, std::vector<S> &streams) {
+    const fb_image *img = job.img;
+    const int nch = (int)img->ch.size();
+    if (nch <= 0) return;
+    bool indexed = job.group_index && job.n_groups > 0;
+    if (indexed) {
+        int i = 0;
+        std::vector<S> mine;
+        for (int g = 0; g < job.n_groups && indexed; g++) {
+            while (i < nch && (!img->ch[i].d.w || !img->ch[i].d.h)) i++;
+            size_t pos = (size_t)job.group_index[g];
+            if (i >= nch || job.group_index[g] < (int64_t)job.body_pos || pos >= job.nbytes) { indexed = false; break; }
+            if (job.bytes_to_load && pos >= job.bytes_to_load) break;
+            if (job.group_first) {
+                i = job.group_first[g];
+                if (i < 0 || i >= nch || (!mine.empty() && i <= mine.back().first_channel)) { indexed = false; break; }
+            } else {
+                if (job.bytes_dev) { indexed = false; break; }      // cannot read group headers of a device buffer on the host
+                int fb = host_varint(job.bytes_host, job.nbytes, pos);
+                if (fb < 0) { indexed = false; break; }
+            }
+            if (!mine.empty()) mine.back().end_channel = i;
+            mine.push_back(S{b, i, nch, 1, (unsigned long long)job.group_index[g]});
+            if (!job.group_first) { size_t p2 = (size_t)job.group_index[g]; int fb = host_varint(job.bytes_host, job.nbytes, p2); i += (fb >> 4) + 1; }
+        }
+        if (indexed && !mine.empty()) streams.insert(streams.end(), mine.begin(), mine.end());
+        else indexed = false;
+    }
+    if (!indexed) streams.push_back(S{b, 0, nch, -1, (unsigned long long)job.body_pos});
+}
+
+// group-major ticket order for batches: the k-th stream of every image before any (k+1)-th stream.  A stream still only depends
+// on lower tickets (earlier groups of its own image), and the large late groups of all images end up running together instead
+// of trailing image by image.
+template <class S>
+void group_major_order(std::vector<S> &streams, int nimg) {
+    if (nimg <= 1) return;
+    std::vector<int> ord(streams.size());
+    std::vector<int> seen(nimg, 0);
+    for (size_t k = 0; k < streams.size(); k++) ord[k] = seen[streams[k].image]++;
+    std::vector<size_t> idx(streams.size());
+    for (size_t k = 0; k < idx.size(); k++) idx[k] = k;
+    std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return ord[a] < ord[b]; });
+    std::vector<S> sorted(streams.size());
+    for (size_t k = 0; k < idx.size(); k++) sorted[k] = streams[idx[k]];
+    streams.swap(sorted);
+}
+
+// what every backend leaves in the image: ranges / q / zero of the planes, which planes hold data, where the groups start
+template <class C>
+int finish_images(fb_ctx *ctx, std::vector<FbManiacJob> &jobs, const std::vector<C> &back, const std::vector<int> &status) {
+    size_t coff = 0;
+    int rc = FB_OK;
+    for (size_t b = 0; b < jobs.size(); b++) {
+        fb_image *img = jobs[b].img;
+        for (size_t i = 0; i < img->ch.size(); i++) {
+            const C &d = back[coff + i];
+            FbChan &c = img->ch[i];
+            c.d.minval = d.minval; c.d.maxval = d.maxval; c.d.zero = d.zero; c.d.q = d.q;
+            if (d.state) c.d.decoded = 1;
+            else { fb_plane_free(ctx, c.dev); c.dev = nullptr; c.host = nullptr; c.d.decoded = 0; }
+            if (d.group_off >= 0) { img->group_off.push_back(d.group_off); img->group_first.push_back((int32_t)i); }
+        }
+        if (status[b] == FB_ERR_UNSUPPORTED) { ctx->err = "max_properties > 18 is not supported by the GPU context model"; rc = FB_ERR_UNSUPPORTED; }
+        else if (status[b] == kStatusTreeTooLarge) { ctx->err = "a MANIAC tree of this file has more than 65535 nodes: not supported by this decoder (image " + std::to_string(b) + ")"; rc = FB_ERR_UNSUPPORTED; }
+        else if (status[b]) { ctx->err = "corrupt FUIF stream (image " + std::to_string(b) + ")"; rc = FB_ERR_INVALID; }
+        coff += img->ch.size();
+    }
+    return rc;
+}
+
+// ---- host-threads backend (FB_OPT_ENTROPY_BACKEND = FB_ENTROPY_HOST) ---------------------------------------
+// fb_host_entropy.cpp decodes into host memory -- pinned staging of the context, or the image's own block for a host-only image --
+// one thread per channel group (with the group index) or per image; the planes are then copied to HBM, where the transform
+// chain runs as with the GPU backend.  100 MB of planes of a 4096^2 image cross PCIe in a few ms against >= 1 s of decoding.
+int maniac_decode_host(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
+    const int nimg = (int)jobs.size();
+    const bool gpu = ctx->device >= 0;
+    std::vector<std::vector<uint8_t>> file_copy(nimg);
+    std::vector<fbh::Image> himg(nimg);
+    std::vector<fbh::Stream> streams;
+    std::vector<size_t> plane_off;      // per plane: offset (in samples) into its block
+    size_t total_ch = 0, total_samples = 0;
+    for (int b = 0; b < nimg; b++) {
+        FbManiacJob &job = jobs[b];
+        if (job.cutoff != jobs[0].cutoff || job.alpha != jobs[0].alpha) { ctx->err = "batch with mixed maniac options"; return FB_ERR_INVALID; }
+        if (job.bytes_dev) {        // the file lives in HBM: this backend reads it on the host
+            file_copy[b].resize(job.nbytes);
+            FB_CUDA(ctx, cudaMemcpyAsync(file_copy[b].data(), job.bytes_dev, job.nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+            FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            job.bytes_host = file_copy[b].data();
+            job.bytes_dev = nullptr;
+        }
+        if (!gpu) total_samples = 0;     // host-only images own their block: offsets restart per image
+        for (auto &c : job.img->ch) {
+            const size_t n = (c.d.w > 0 && c.d.h > 0) ? (size_t)c.d.w * c.d.h : 0;
+            plane_off.push_back(total_samples);
+            total_samples += (n + 31) & ~(size_t)31;
+        }
+        if (!gpu) { job.img->host_block.assign(total_samples + 32, 0); job.img->on_host = true; }
+        total_ch += job.img->ch.size();
+    }
+    int16_t *stage = nullptr;
+    if (gpu) {
+        const size_t need = std::max<size_t>(total_samples * sizeof(int16_t), 4096);
+        if (need > ctx->host_stage_bytes) {
+            FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (ctx->host_stage) cudaFreeHost(ctx->host_stage);
+            ctx->host_stage = nullptr; ctx->host_stage_bytes = 0;
+            FB_CUDA(ctx, cudaHostAlloc(&ctx->host_stage, need, cudaHostAllocDefault));
+            ctx->host_stage_bytes = need;
+        }
+        stage = (int16_t *)ctx->host_stage;
+    }
+    std::vector<fbh::Chan> hch(total_ch);
+    size_t coff = 0;
+    for (int b = 0; b < nimg; b++) {
+        FbManiacJob &job = jobs[b];
+        fb_image *img = job.img;
+        himg[b].bytes = job.bytes_host; himg[b].nbytes = job.nbytes; himg[b].bytes_to_load = job.bytes_to_load;
+        himg[b].ch = hch.data() + coff; himg[b].nch = (int)img->ch.size(); himg[b].max_properties = job.max_properties;
+        himg[b].n_orig = img->info.real_nb_channels; himg[b].status = 0;
+        int16_t *base = gpu ? stage : img->host_block.data();
+        for (size_t i = 0; i < img->ch.size(); i++) {
+            FbChan &c = img->ch[i];
+            fbh::Chan &d = hch[coff + i];
+            memset(&d, 0, sizeof(d));
+            d.w = c.d.w; d.h = c.d.h; d.minval = c.d.minval; d.maxval = c.d.maxval; d.zero = c.d.zero; d.q = c.d.q;
+            d.hshift = c.d.hshift; d.vshift = c.d.vshift; d.group_off = -1;
+            d.data = base + plane_off[coff + i];
+            if (!(c.d.w > 0 && c.d.h > 0)) { d.hdr_done = 1; d.rows_done = 0x7fffffff; }     // empty planes are skipped by the channel loop
+        }
+        build_streams(job, b, streams);
+        coff += img->ch.size();
+    }
+    group_major_order(streams, nimg);
+    ctx->host_threads_used = fbh::decode(himg.data(), nimg, streams.data(), (int)streams.size(), jobs[0].cutoff, (uint32_t)jobs[0].alpha, ctx->host_threads);
+    // ---- planes to HBM (or stay where they are, for a host-only image)
+    coff = 0;
+    for (int b = 0; b < nimg; b++) {
+        fb_image *img = jobs[b].img;
+        for (size_t i = 0; i < img->ch.size(); i++) {
+            FbChan &c = img->ch[i];
+            const fbh::Chan &d = hch[coff + i];
+            if (!d.state) continue;
+            if (!gpu) { c.host = d.data; continue; }
+            const size_t n = (size_t)d.w * d.h;
+            int rc = fb_plane_alloc(ctx, n, &c.dev);
+            if (rc) return rc;
+            FB_CUDA(ctx, cudaMemcpyAsync(c.dev, d.data, n * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        coff += img->ch.size();
+    }
+    if (gpu) FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the staging is free for the next call
+    std::vector<int> status(nimg);
+    for (int b = 0; b < nimg; b++) status[b] = himg[b].status;
+    int rc = finish_images(ctx, jobs, hch, status);
+    if (rc == FB_ERR_UNSUPPORTED) ctx->err = "more properties than the host context model holds (max_properties > 100)";
+    return rc;
+}
+
 }  // namespace
 
 void fb_maniac_release(fb_ctx *ctx) {
@@ -1553,6 +1720,7 @@ void fb_maniac_release(fb_ctx *ctx) {
 int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
     const int nimg = (int)jobs.size();
     if (!nimg) return FB_OK;
+    if (ctx->entropy_backend == FB_ENTROPY_HOST || ctx->device < 0) return maniac_decode_host(ctx, jobs);
     int cutoff = jobs[0].cutoff, alpha = jobs[0].alpha;
     // ---- plane allocation + descriptors
     std::vector<DImage> himg(nimg);
@@ -1603,53 +1771,12 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         }
         if (!hch[b].empty())
             FB_CUDA(ctx, cudaMemcpyAsync(ch_dev + coff, hch[b].data(), hch[b].size() * sizeof(DChan), cudaMemcpyHostToDevice, ctx->stream));
-        // ---- streams
-        if (himg[b].nch > 0) {
-            bool indexed = job.group_index && job.n_groups > 0;
-            if (indexed) {
-                // one stream per group: walk the channel list exactly like the loop of fuif_decode (encoding.cpp:708-718)
-                int i = 0;
-                std::vector<DStream> mine;
-                for (int g = 0; g < job.n_groups && indexed; g++) {
-                    while (i < himg[b].nch && (!img->ch[i].d.w || !img->ch[i].d.h)) i++;
-                    size_t pos = (size_t)job.group_index[g];
-                    if (i >= himg[b].nch || job.group_index[g] < (int64_t)job.body_pos || pos >= job.nbytes) { indexed = false; break; }
-                    if (job.bytes_to_load && pos >= job.bytes_to_load) break;
-                    if (job.group_first) {
-                        i = job.group_first[g];
-                        if (i < 0 || i >= himg[b].nch || (!mine.empty() && i <= mine.back().first_channel)) { indexed = false; break; }
-                    } else {
-                        if (job.bytes_dev) { indexed = false; break; }      // cannot read group headers of a device buffer on the host
-                        int fb = host_varint(job.bytes_host, job.nbytes, pos);
-                        if (fb < 0) { indexed = false; break; }
-                    }
-                    if (!mine.empty()) mine.back().end_channel = i;
-                    mine.push_back(DStream{b, i, himg[b].nch, 1, (unsigned long long)job.group_index[g]});
-                    if (!job.group_first) { size_t p2 = (size_t)job.group_index[g]; int fb = host_varint(job.bytes_host, job.nbytes, p2); i += (fb >> 4) + 1; }
-                }
-                if (indexed && !mine.empty()) streams.insert(streams.end(), mine.begin(), mine.end());
-                else indexed = false;
-            }
-            if (!indexed) streams.push_back(DStream{b, 0, himg[b].nch, -1, (unsigned long long)job.body_pos});
-        }
+        build_streams(job, b, streams);
         if (!job.bytes_dev) boff += (job.nbytes + 255) & ~(size_t)255;
         coff += img->ch.size();
     }
     FB_CUDA(ctx, cudaMemcpyAsync(img_dev, himg.data(), nimg * sizeof(DImage), cudaMemcpyHostToDevice, ctx->stream));
-    if (nimg > 1) {
-        // group-major ticket order: the k-th stream of every image before any (k+1)-th stream.  A stream still only depends on
-        // lower tickets (earlier groups of its own image), and the large late groups of all images end up running together
-        // instead of trailing image by image.
-        std::vector<int> ord(streams.size());
-        std::vector<int> seen(nimg, 0);
-        for (size_t k = 0; k < streams.size(); k++) ord[k] = seen[streams[k].image]++;
-        std::vector<size_t> idx(streams.size());
-        for (size_t k = 0; k < idx.size(); k++) idx[k] = k;
-        std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return ord[a] < ord[b]; });
-        std::vector<DStream> sorted(streams.size());
-        for (size_t k = 0; k < idx.size(); k++) sorted[k] = streams[idx[k]];
-        streams.swap(sorted);
-    }
+    group_major_order(streams, nimg);
     const int nstreams = (int)streams.size();
     if (nstreams) {
         // streams are ordered image-major, groups ascending: dependencies always point to lower stream ids
@@ -1703,23 +1830,8 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFreeAsync(bytes_dev, ctx->stream); cudaFreeAsync(ch_dev, ctx->stream); cudaFreeAsync(img_dev, ctx->stream);
     if (streams_dev) cudaFreeAsync(streams_dev, ctx->stream);
-    coff = 0;
-    int rc = FB_OK;
-    for (int b = 0; b < nimg; b++) {
-        fb_image *img = jobs[b].img;
-        for (size_t i = 0; i < img->ch.size(); i++) {
-            const DChan &d = back[coff + i];
-            FbChan &c = img->ch[i];
-            c.d.minval = d.minval; c.d.maxval = d.maxval; c.d.zero = d.zero; c.d.q = d.q;
-            if (d.state) c.d.decoded = 1;
-            else { fb_plane_free(ctx, c.dev); c.dev = nullptr; c.d.decoded = 0; }
-            if (d.group_off >= 0) { img->group_off.push_back(d.group_off); img->group_first.push_back((int32_t)i); }
-        }
-        if (himg[b].status == FB_ERR_UNSUPPORTED) { ctx->err = "max_properties > 18 is not supported by the GPU context model"; rc = FB_ERR_UNSUPPORTED; }
-        else if (himg[b].status == kStatusTreeTooLarge) { ctx->err = "a MANIAC tree of this file has more than 65535 nodes: not supported by this decoder (image " + std::to_string(b) + ")"; rc = FB_ERR_UNSUPPORTED; }
-        else if (himg[b].status) { ctx->err = "corrupt FUIF stream (image " + std::to_string(b) + ")"; rc = FB_ERR_INVALID; }
-        coff += img->ch.size();
-    }
-    return rc;
+    std::vector<int> status(nimg);
+    for (int b = 0; b < nimg; b++) status[b] = himg[b].status;
+    return finish_images(ctx, jobs, back, status);
 }
 #endif  // FB_EMULATE

@@ -101,6 +101,16 @@ FB_API long long fb_ctx_launch_count(fb_ctx *ctx);
  *   of 8, at least 64 x 32) run on the packed int16x2 kernels (TMA-fed horizontal step with the inverse YCoCg / clamp
  *   epilogue, coalesced vertical step); 0 = never.  Results are bit-exact either way. */
 #define FB_OPT_SQUEEZE_PACKED 3
+/* FB_OPT_ENTROPY_BACKEND: where fuif_decode_channel (encoding.cpp:259-429) runs.  FB_ENTROPY_GPU (default): k_maniac_decode,
+ *   one stream per SM-resident warp team.  FB_ENTROPY_HOST: CPU threads (one channel group per thread with the group index,
+ *   one image per thread without), planes copied to HBM afterwards; the transform chain stays on the GPU either way.  The
+ *   serial coder of ONE group runs ~6x faster on a CPU core than on a GPU warp, so this is the backend for a single large
+ *   image with a group index; batches that fill the GPU (hundreds of groups) are faster on the GPU backend.  Planes and
+ *   errors are identical.  FB_OPT_HOST_THREADS: threads of the host backend, 0 (default) = one per hardware thread. */
+#define FB_OPT_ENTROPY_BACKEND 4
+#define FB_OPT_HOST_THREADS 5
+#define FB_ENTROPY_GPU 0
+#define FB_ENTROPY_HOST 1
 FB_API int fb_ctx_set_option(fb_ctx *ctx, int option, int value);
 /* The fused Squeeze inverse (mode >= 2) starts tiles speculatively and verifies them (results are bit-exact either way).
  * which = 0: Squeeze inverses so far that failed verification in an early launch and were recomputed serially;
@@ -111,6 +121,8 @@ FB_API int fb_ctx_set_option(fb_ctx *ctx, int option, int value);
 /* packed kernels: segments recomputed by the exact routine so far / segments that saw a value outside the packed range */
 #define FB_COUNTER_PK_REPAIRED 2
 #define FB_COUNTER_PK_RANGE_FLAGGED 3
+/* threads the host entropy backend used in its last call */
+#define FB_COUNTER_HOST_THREADS 4
 FB_API long long fb_ctx_counter(fb_ctx *ctx, int which);
 /* Device self-test of the packed 16x2 primitives against their exact 32-bit forms on pseudo-random inputs inside the
  * admitted range: which = 0 the unsqueeze pair (+ the range accumulator), 1 the inverse YCoCg.  scale = typical distance
@@ -137,6 +149,17 @@ FB_API long long fb_ctx_timing_report(fb_ctx *ctx, char *buf, size_t cap);
  * max_properties <= 18.  A damaged stream decodes to garbage planes or FB_ERR_INVALID; the call always returns. */
 FB_API int fb_decode(fb_ctx *ctx, const uint8_t *bytes, size_t nbytes, const fb_decode_options *opts,
               const int64_t *group_index, const int32_t *group_first, int n_groups, fb_image **out);
+
+/* The host-threads entropy backend on its own, without any GPU (no fb_ctx): container parse + fuif_decode_channel on `threads`
+ * CPU threads (0 = one per hardware thread).  The image it returns lives in HOST memory: fb_image_get_info / get_plane /
+ * get_transform / download_plane / group_index / destroy work on it, everything that computes returns FB_ERR_INVALID until
+ * fb_image_upload() has moved it to a context's GPU.  fb_decode() with FB_OPT_ENTROPY_BACKEND = FB_ENTROPY_HOST is this plus the
+ * upload (through pinned staging).  On failure *out is NULL and fb_host_last_error() (thread-local) has the message. */
+FB_API int fb_host_decode(const uint8_t *bytes, size_t nbytes, const fb_decode_options *opts, const int64_t *group_index,
+                          const int32_t *group_first, int n_groups, int threads, fb_image **out);
+FB_API const char *fb_host_last_error(void);
+/* Moves a host-only image into ctx's HBM (one H2D copy per plane); the image belongs to ctx afterwards. */
+FB_API int fb_image_upload(fb_ctx *ctx, fb_image *img);
 
 /* Same for a batch: every (image, group) is an independent stream of one kernel launch. */
 FB_API int fb_decode_batch(fb_ctx *ctx, int n_images, const uint8_t *const *bytes, const size_t *nbytes,

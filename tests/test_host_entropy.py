@@ -1,0 +1,87 @@
+"""The host-threads entropy backend (fb_host_decode) against the golden vectors of the unmodified
+reference: no GPU involved, so these run in the CPU tier.  The same planes must come out with and without the group
+index, for any thread count."""
+import numpy as np
+import pytest
+
+from tests.cases import CASES
+from tests.util import gpu_plane_image, load_golden
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_host_decode_vs_golden(oracle, case):
+    from fuif_b200 import api
+    po = oracle
+    blob = load_golden(case[0])
+    ref = po.parse_fbpd(blob["s0"])
+    img = api.fuif_host_decode(blob["fuif"], threads=1)
+    po.compare_plane_images(gpu_plane_image(po, img), ref, case[0] + " host s0")
+    offs, first = img.group_index()
+    _, ooffs = po.OracleImage.decode(blob["fuif"], want_offsets=True)
+    assert list(zip(offs, first)) == [(int(a), int(b)) for a, b in ooffs]
+    for threads, gi in ((4, (offs, first)), (3, offs), (0, (offs, first))):
+        par = api.fuif_host_decode(blob["fuif"], group_index=gi, threads=threads)
+        po.compare_plane_images(gpu_plane_image(po, par), ref, f"{case[0]} host indexed t{threads}")
+
+
+ALL_WITH_FUIF = ["approx", "approx14", "approx_noop", "approx_nosq", "approx_q", "match", "match_gray", "match_nosq", "match_soft", "pal", "pal4",
+                 "pal_c0", "pal_nosq", "perm", "perm2", "perm_nosq", "sub_420", "sub_420odd", "sub_422", "sub_440", "sub_one_chan", "sub_tiny"]
+
+
+@pytest.mark.parametrize("name", ALL_WITH_FUIF)
+def test_host_decode_vs_oracle_other_chains(oracle, name):
+    """Files of the other transform chains (palette and match meta-channels, permutations, subsampled chroma): same planes as
+    the C restatement of fuif_decode, sequentially and one thread per group."""
+    from fuif_b200 import api
+    po = oracle
+    data = bytes(load_golden(name)["fuif"])
+    ref = po.OracleImage.decode(data).to_plane_image()
+    img = api.fuif_host_decode(data, threads=1)
+    po.compare_plane_images(gpu_plane_image(po, img), ref, name + " host")
+    par = api.fuif_host_decode(data, group_index=img.group_index(), threads=8)
+    po.compare_plane_images(gpu_plane_image(po, par), ref, name + " host indexed")
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("odd", "sq128", "rgba14", "dct", "gray")], ids=lambda c: c[0])
+@pytest.mark.parametrize("preview", [0, 1, 2, 3, 4])
+def test_host_responsive_decode(oracle, case, preview):
+    from fuif_b200 import api
+    po = oracle
+    blob = load_golden(case[0])
+    img = api.fuif_host_decode(blob["fuif"], api.fuif_options(preview=preview))
+    po.compare_plane_images(gpu_plane_image(po, img), po.parse_fbpd(blob[f"r{preview}s0"]), f"{case[0]} host R{preview} s0", check_meta=False)
+
+
+@pytest.mark.parametrize("name", ["sq128", "rgba14", "dct", "unc", "pred"])
+def test_host_truncated_and_damaged_like_oracle(oracle, name):
+    """Truncation is tolerated the way the reference tolerates it (zero fill, encoding.cpp:209-219); a damaged stream gives the
+    oracle's planes or an error where the oracle fails -- and always returns."""
+    from fuif_b200 import api
+    po = oracle
+    data = bytes(load_golden(name)["fuif"])
+    rng = np.random.default_rng(len(data))
+    variants = [data[:cut] for cut in (len(data) - 1, len(data) * 3 // 4, len(data) // 2, len(data) // 7, 64)]
+    for k in range(8):
+        d = bytearray(data)
+        for _ in range(1 + 2 * k):
+            d[int(rng.integers(40, len(d)))] ^= 1 << int(rng.integers(0, 8))
+        variants.append(bytes(d))
+    for k, d in enumerate(variants):
+        try:
+            ref = po.OracleImage.decode(d).to_plane_image()
+        except RuntimeError:
+            ref = None
+        try:
+            got = gpu_plane_image(po, api.fuif_host_decode(d, threads=2))
+        except api.FuifError:
+            got = None
+        assert (ref is None) == (got is None), f"{name} variant {k}: oracle {'fails' if ref is None else 'decodes'}, host backend {'fails' if got is None else 'decodes'}"
+        if ref is not None:
+            po.compare_plane_images(got, ref, f"{name} damaged {k}", check_meta=False)
+
+
+def test_host_image_needs_upload_before_computing():
+    from fuif_b200 import api
+    img = api.fuif_host_decode(bytes(load_golden("sq128")["fuif"]))
+    with pytest.raises(api.FuifError):
+        img.undo_transforms(0)
