@@ -45,6 +45,9 @@ def parse_args():
                     help="besides the main (indexed) measurement, time this many steps WITHOUT the sidecar and report value_no_index / e2e_no_index (0 = skip)")
     ap.add_argument("--distinct-images", action="store_true", help="weak scaling with a different image (seed) on every rank instead of replicas of the same one")
     ap.add_argument("--strong", action="store_true", help="multi-image workloads (cfg4): split the fixed batch over the ranks (strong scaling)")
+    ap.add_argument("--host-entropy-steps", type=int, default=1,
+                    help="also time this many e2e steps with the host-threads entropy backend and report e2e_host_entropy (0 = skip)")
+    ap.add_argument("--host-threads", type=int, default=0, help="threads of the host entropy backend per GPU (0 = host cores / GPUs)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -318,6 +321,32 @@ def main():
             got = got.view(">u2")
         assert np.array_equal(got.astype(np.int32), synth_image(w, h, c, maxval, spec_seed0)), "e2e pixels differ"
 
+    # ---- the same e2e call with the HOST-THREADS entropy backend (FB_OPT_ENTROPY_BACKEND = FB_ENTROPY_HOST): the serial
+    # MANIAC coder of each channel group runs on a CPU thread, the planes go to HBM through pinned staging and the transform chain
+    # runs on the GPU as before.  A second number next to `e2e`, not a replacement: `value` / `e2e` stay the all-GPU path.
+    host_entropy = None
+    if args.host_entropy_steps > 0:
+        nthreads = args.host_threads or max(1, (os.cpu_count() or 1) // world)
+        ctx.set_entropy_backend("host", nthreads)
+        step_e2e()          # warm-up: the pinned staging is allocated once per context
+        launches0 = ctx.launches
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.host_entropy_steps):
+            step_e2e()
+        torch.cuda.synchronize()
+        he_ms, _ = shard.reduce_step_time((time.perf_counter() - t0) * 1e3, len(units), device="cuda")
+        if lossless:
+            got = pin_out[0].numpy()
+            if bps == 2:
+                got = got.view(">u2")
+            assert np.array_equal(got.astype(np.int32), synth_image(w, h, c, maxval, spec_seed0)), "host-entropy e2e pixels differ"
+        host_entropy = {"value": total_units * (w * h / 1e6) / (he_ms / 1e3 / args.host_entropy_steps), "unit": "Mpx/s",
+                        "ms_per_step": he_ms / args.host_entropy_steps, "steps": args.host_entropy_steps, "threads_per_gpu": ctx.host_threads_used,
+                        "host_cores": os.cpu_count(), "gpu_launches_per_step": (ctx.launches - launches0) // args.host_entropy_steps,
+                        "what": "same call as e2e with the entropy stage on host threads (one channel group per thread), transform chain on the GPU"}
+        ctx.set_entropy_backend("gpu")
+
     # ---- the same workload WITHOUT the group-offset sidecar (one stream per file, as the bare format dictates): a bounded sample
     no_index = None
     if not args.no_index and args.no_index_steps > 0:
@@ -443,6 +472,7 @@ def main():
         "value_no_index": no_index["value"] if no_index else None, "e2e_no_index": no_index["e2e"] if no_index else None, "no_index": no_index,
         "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": int(sum(len(im["fuif"]) for im in imgs)),
                 "d2h_bytes_per_step": int(n_per_gpu * w * h * c * bps)},
+        "e2e_host_entropy": host_entropy,
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline,
