@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--strong", action="store_true", help="multi-image workloads (cfg4): split the fixed batch over the ranks (strong scaling)")
     ap.add_argument("--host-entropy-steps", type=int, default=1,
                     help="also time this many e2e steps with the host-threads entropy backend and report e2e_host_entropy (0 = skip)")
+    ap.add_argument("--hybrid-gpu-percent", type=int, default=55, help="hybrid entropy backend: share of a batch's images that go to the GPU")
     ap.add_argument("--host-threads", type=int, default=0, help="threads of the host entropy backend per GPU (0 = host cores / GPUs)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -324,28 +325,34 @@ def main():
     # ---- the same e2e call with the HOST-THREADS entropy backend (FB_OPT_ENTROPY_BACKEND = FB_ENTROPY_HOST): the serial
     # MANIAC coder of each channel group runs on a CPU thread, the planes go to HBM through pinned staging and the transform chain
     # runs on the GPU as before.  A second number next to `e2e`, not a replacement: `value` / `e2e` stay the all-GPU path.
-    host_entropy = None
+    alt_entropy = {}
     if args.host_entropy_steps > 0:
         nthreads = args.host_threads or max(1, (os.cpu_count() or 1) // world)
-        ctx.set_entropy_backend("host", nthreads)
-        step_e2e()          # warm-up: the pinned staging is allocated once per context
-        launches0 = ctx.launches
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.host_entropy_steps):
-            step_e2e()
-        torch.cuda.synchronize()
-        he_ms, _ = shard.reduce_step_time((time.perf_counter() - t0) * 1e3, len(units), device="cuda")
-        if lossless:
-            got = pin_out[0].numpy()
-            if bps == 2:
-                got = got.view(">u2")
-            assert np.array_equal(got.astype(np.int32), synth_image(w, h, c, maxval, spec_seed0)), "host-entropy e2e pixels differ"
-        host_entropy = {"value": total_units * (w * h / 1e6) / (he_ms / 1e3 / args.host_entropy_steps), "unit": "Mpx/s",
-                        "ms_per_step": he_ms / args.host_entropy_steps, "steps": args.host_entropy_steps, "threads_per_gpu": ctx.host_threads_used,
-                        "host_cores": os.cpu_count(), "gpu_launches_per_step": (ctx.launches - launches0) // args.host_entropy_steps,
-                        "what": "same call as e2e with the entropy stage on host threads (one channel group per thread), transform chain on the GPU"}
+        # hybrid (batches only): gpu_percent % of the images on k_maniac_decode, the others on the host threads at the same time
+        for backend in ["host"] + (["hybrid"] if len(imgs) > 1 else []):
+            ctx.set_entropy_backend(backend, nthreads, args.hybrid_gpu_percent)
+            step_e2e()          # warm-up: the pinned staging is allocated once per context
+            launches0 = ctx.launches
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.host_entropy_steps):
+                step_e2e()
+            torch.cuda.synchronize()
+            he_ms, _ = shard.reduce_step_time((time.perf_counter() - t0) * 1e3, len(units), device="cuda")
+            if lossless:
+                for k_img, po_ in enumerate(pin_out):
+                    got = po_.numpy()
+                    if bps == 2:
+                        got = got.view(">u2")
+                    assert np.array_equal(got.astype(np.int32), synth_image(w, h, c, maxval, spec[4] + units[k_img])), f"{backend}-entropy e2e pixels differ (image {k_img})"
+            alt_entropy[backend] = {
+                "value": total_units * (w * h / 1e6) / (he_ms / 1e3 / args.host_entropy_steps), "unit": "Mpx/s",
+                "ms_per_step": he_ms / args.host_entropy_steps, "steps": args.host_entropy_steps, "threads_per_gpu": ctx.host_threads_used,
+                "host_cores": os.cpu_count(), "gpu_launches_per_step": (ctx.launches - launches0) // args.host_entropy_steps,
+                "what": ("same call as e2e with the entropy stage on host threads (one channel group per thread), transform chain on the GPU" if backend == "host" else
+                         f"same call as e2e with {args.hybrid_gpu_percent} % of the images entropy-decoded by k_maniac_decode and the others by the host threads at the same time")}
         ctx.set_entropy_backend("gpu")
+    host_entropy = alt_entropy.get("host")
 
     # ---- the same workload WITHOUT the group-offset sidecar (one stream per file, as the bare format dictates): a bounded sample
     no_index = None
@@ -472,7 +479,7 @@ def main():
         "value_no_index": no_index["value"] if no_index else None, "e2e_no_index": no_index["e2e"] if no_index else None, "no_index": no_index,
         "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": int(sum(len(im["fuif"]) for im in imgs)),
                 "d2h_bytes_per_step": int(n_per_gpu * w * h * c * bps)},
-        "e2e_host_entropy": host_entropy,
+        "e2e_host_entropy": host_entropy, "e2e_hybrid_entropy": alt_entropy.get("hybrid"),
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline,

@@ -178,8 +178,9 @@ FBH_INLINE int read_ctx(Rac &rac, const uint16_t *table, uint16_t *leaf, int idx
     return bit;
 }
 
-// reader<15>(coder, min, max), symbol.h:154-185
-FBH_INLINE int read_int(Rac &rac, const uint16_t *table, uint16_t *leaf, int mn, int mx) {
+// reader<15>(coder, min, max), symbol.h:154-185.  mant_base: index of bit_mant[0] in the leaf (16 in the full layout, 9 in the
+// compact one: zero, sign, exp[7], mant[7] -- enough while no value of the group needs more than 7 exponent / mantissa bits)
+FBH_INLINE int read_int(Rac &rac, const uint16_t *table, uint16_t *leaf, int mn, int mx, int mant_base = SC_MANT) {
     if (mn == mx) return mn;
     if (read_ctx(rac, table, leaf, SC_ZERO)) return 0;
     int sign;
@@ -193,7 +194,7 @@ FBH_INLINE int read_int(Rac &rac, const uint16_t *table, uint16_t *leaf, int mn,
         pos--;
         const int minabs1 = have | (1 << pos);
         if (minabs1 > amax) continue;
-        if (read_ctx(rac, table, leaf, SC_MANT + pos)) have = minabs1;
+        if (read_ctx(rac, table, leaf, mant_base + pos)) have = minabs1;
     }
     return sign ? have : -have;
 }
@@ -384,7 +385,7 @@ void reference_row(const Chan &ch, const Chan &cj, int y, int16_t *out) {
 // pixel to the left and nearly everything depends on it.
 template <bool PRED0>
 FBH_INLINE void decode_row(const Chan &ch, int y, int predictor, int nused, const int *used_ref, int nref, const int16_t *refrow, Rac &rac,
-                           const uint16_t *table, const Node *nodes, uint16_t *leaves) {
+                           const uint16_t *table, const Node *nodes, uint16_t *leaves, int leaf_shift, int mant_base) {
     const int w = ch.w, zero = ch.zero, cmin = ch.minval, cmax = ch.maxval;
     int16_t *row = ch.data + (size_t)y * w;
     const int16_t *row1 = row - w, *row2 = row1 - w;
@@ -424,7 +425,7 @@ FBH_INLINE void decode_row(const Chan &ch, int y, int predictor, int nused, cons
         int diff = mn;
         if (mn != mx) {
             const Node n = walk(nodes, props, nodes[1]);
-            diff = read_int(rac, table, leaves + ((size_t)node_ref(n) << 5), mn, mx);
+            diff = read_int(rac, table, leaves + ((size_t)node_ref(n) << leaf_shift), mn, mx, mant_base);
         }
         const int val = s16(s16(diff) + guess);
         row[x] = (int16_t)val;
@@ -444,7 +445,8 @@ FBH_INLINE void decode_row(const Chan &ch, int y, int predictor, int nused, cons
 constexpr int kChunk = 64;
 template <bool PRED0>
 FBH_INLINE void decode_row_chunked(const Chan &ch, int y, int predictor, int nused, const int *used_ref, int nref, int stride, int *pc,
-                                   const int16_t *refrow, Rac &rac, const uint16_t *table, const Node *nodes, uint16_t *leaves) {
+                                   const int16_t *refrow, Rac &rac, const uint16_t *table, const Node *nodes, uint16_t *leaves, int leaf_shift,
+                                   int mant_base) {
     const int w = ch.w, zero = ch.zero, cmin = ch.minval, cmax = ch.maxval;
     int16_t *row = ch.data + (size_t)y * w;
     const int16_t *row1 = row - w, *row2 = (y > 1) ? row1 - w : row1;       // toptop = top on row 1
@@ -490,7 +492,7 @@ FBH_INLINE void decode_row_chunked(const Chan &ch, int y, int predictor, int nus
             int diff = mn;
             if (mn != mx) {
                 const Node n = walk(nodes, p, nodes[1]);
-                diff = read_int(rac, table, leaves + ((size_t)node_ref(n) << 5), mn, mx);
+                diff = read_int(rac, table, leaves + ((size_t)node_ref(n) << leaf_shift), mn, mx, mant_base);
             }
             const int val = s16(s16(diff) + guess);
             row[x] = (int16_t)val;
@@ -605,10 +607,24 @@ bool decode_group(Image &img, Reader &io, int &beginc, const Tables &T, Scratch 
         for (int i = 0; i < nnodes; i++) if (S.prop_of[i] >= 0) used[S.prop_of[i]] = true;
         for (int r = 0; r < nrefchan; r++) if (used[2 * r] || used[2 * r + 1]) used_ref[nused++] = r;
     }
+    // leaf layout: 32 chances (64 bytes), or 16 (32 bytes: twice as many leaves per cache level) when every |residual| of the group
+    // fits 8 bits.  With a predictor the residual range is up to twice the value range.
+    int group_abs = 0;
+    for (int i = beginc; i <= endc; i++) {
+        const Chan &c = img.ch[i];
+        if (c.minval == c.maxval) continue;
+        const int span = predictor ? (c.maxval - c.minval) : std::max(std::abs(c.minval - c.zero), std::abs(c.maxval - c.zero));
+        group_abs = std::max(group_abs, span);
+    }
+    const bool compact = group_abs <= 255;
+    const int leaf_shift = compact ? 4 : 5, mant_base = compact ? 9 : SC_MANT;
     uint16_t proto[32];
     for (int e = 0; e < 32; e++) proto[e] = initial_chance(e, predictability);
-    S.leaves.resize((size_t)nleaves * 32);
-    for (int l = 0; l < nleaves; l++) memcpy(&S.leaves[(size_t)l * 32], proto, sizeof(proto));
+    if (compact) for (int e = 0; e < 7; e++) proto[9 + e] = proto[SC_MANT + e];       // zero, sign, exp[0..6] stay where they are
+    const size_t lstride = (size_t)1 << leaf_shift;
+    S.leaves.resize((size_t)nleaves * lstride + 32);
+    uint16_t *leaves = (uint16_t *)(((uintptr_t)S.leaves.data() + 63) & ~(uintptr_t)63);
+    for (int l = 0; l < nleaves; l++) memcpy(leaves + (size_t)l * lstride, proto, lstride * sizeof(uint16_t));
 
     for (int i = beginc; i <= endc; i++) {
         Chan &ch = img.ch[i];
@@ -619,7 +635,7 @@ bool decode_group(Image &img, Reader &io, int &beginc, const Tables &T, Scratch 
             for (int y = 0; y < ch.h; y++) {
                 if (rac.io.stop()) break;
                 int16_t *row = ch.data + (size_t)y * ch.w;
-                for (int x = 0; x < ch.w; x++) row[x] = (int16_t)read_int(rac, T.table, S.leaves.data(), ch.minval, ch.maxval);
+                for (int x = 0; x < ch.w; x++) row[x] = (int16_t)read_int(rac, T.table, leaves, ch.minval, ch.maxval, mant_base);
                 st_release(&ch.rows_done, y + 1);
             }
         } else {
@@ -637,10 +653,10 @@ bool decode_group(Image &img, Reader &io, int &beginc, const Tables &T, Scratch 
                     reference_row(ch, cj, y, S.refrow.data() + (size_t)r * ch.w);
                 }
                 if (y) {
-                    if (predictor == 0) decode_row_chunked<true>(ch, y, predictor, nused, used_ref, nref, stride, S.chunk.data(), S.refrow.data(), rac, T.table, nodes, S.leaves.data());
-                    else decode_row_chunked<false>(ch, y, predictor, nused, used_ref, nref, stride, S.chunk.data(), S.refrow.data(), rac, T.table, nodes, S.leaves.data());
-                } else if (predictor == 0) decode_row<true>(ch, y, predictor, nused, used_ref, nref, S.refrow.data(), rac, T.table, nodes, S.leaves.data());
-                else decode_row<false>(ch, y, predictor, nused, used_ref, nref, S.refrow.data(), rac, T.table, nodes, S.leaves.data());
+                    if (predictor == 0) decode_row_chunked<true>(ch, y, predictor, nused, used_ref, nref, stride, S.chunk.data(), S.refrow.data(), rac, T.table, nodes, leaves, leaf_shift, mant_base);
+                    else decode_row_chunked<false>(ch, y, predictor, nused, used_ref, nref, stride, S.chunk.data(), S.refrow.data(), rac, T.table, nodes, leaves, leaf_shift, mant_base);
+                } else if (predictor == 0) decode_row<true>(ch, y, predictor, nused, used_ref, nref, S.refrow.data(), rac, T.table, nodes, leaves, leaf_shift, mant_base);
+                else decode_row<false>(ch, y, predictor, nused, used_ref, nref, S.refrow.data(), rac, T.table, nodes, leaves, leaf_shift, mant_base);
                 st_release(&ch.rows_done, y + 1);
             }
         }

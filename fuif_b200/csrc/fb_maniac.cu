@@ -26,6 +26,7 @@
 #else
 #include "fb_common.cuh"
 #include "fb_host_entropy.h"
+#include <thread>
 #define FB_SPIN()
 #define FB_DYN_SMEM_DECL(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
@@ -1621,35 +1622,46 @@ int finish_images(fb_ctx *ctx, std::vector<FbManiacJob> &jobs, const std::vector
 // fb_host_entropy.cpp decodes into host memory -- pinned staging of the context, or the image's own block for a host-only image --
 // one thread per channel group (with the group index) or per image; the planes are then copied to HBM, where the transform
 // chain runs as with the GPU backend.  100 MB of planes of a 4096^2 image cross PCIe in a few ms against >= 1 s of decoding.
-int maniac_decode_host(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
-    const int nimg = (int)jobs.size();
-    const bool gpu = ctx->device >= 0;
-    std::vector<std::vector<uint8_t>> file_copy(nimg);
-    std::vector<fbh::Image> himg(nimg);
+// Three phases, so that the middle one (pure CPU work, touches nothing of the context) can run beside the GPU backend.
+struct HostRun {
+    std::vector<std::vector<uint8_t>> file_copy;
+    std::vector<fbh::Image> himg;
+    std::vector<fbh::Chan> hch;
     std::vector<fbh::Stream> streams;
+    int cutoff = 0, threads_used = 0;
+    uint32_t alpha = 0;
+    bool gpu = true;
+};
+
+int host_prepare(fb_ctx *ctx, std::vector<FbManiacJob> &jobs, HostRun &R) {
+    const int nimg = (int)jobs.size();
+    R.gpu = ctx->device >= 0;
+    R.file_copy.resize(nimg);
+    R.himg.resize(nimg);
+    R.cutoff = jobs[0].cutoff; R.alpha = (uint32_t)jobs[0].alpha;
     std::vector<size_t> plane_off;      // per plane: offset (in samples) into its block
     size_t total_ch = 0, total_samples = 0;
     for (int b = 0; b < nimg; b++) {
         FbManiacJob &job = jobs[b];
         if (job.cutoff != jobs[0].cutoff || job.alpha != jobs[0].alpha) { ctx->err = "batch with mixed maniac options"; return FB_ERR_INVALID; }
         if (job.bytes_dev) {        // the file lives in HBM: this backend reads it on the host
-            file_copy[b].resize(job.nbytes);
-            FB_CUDA(ctx, cudaMemcpyAsync(file_copy[b].data(), job.bytes_dev, job.nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+            R.file_copy[b].resize(job.nbytes);
+            FB_CUDA(ctx, cudaMemcpyAsync(R.file_copy[b].data(), job.bytes_dev, job.nbytes, cudaMemcpyDeviceToHost, ctx->stream));
             FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            job.bytes_host = file_copy[b].data();
+            job.bytes_host = R.file_copy[b].data();
             job.bytes_dev = nullptr;
         }
-        if (!gpu) total_samples = 0;     // host-only images own their block: offsets restart per image
+        if (!R.gpu) total_samples = 0;     // host-only images own their block: offsets restart per image
         for (auto &c : job.img->ch) {
             const size_t n = (c.d.w > 0 && c.d.h > 0) ? (size_t)c.d.w * c.d.h : 0;
             plane_off.push_back(total_samples);
             total_samples += (n + 31) & ~(size_t)31;
         }
-        if (!gpu) { job.img->host_block.assign(total_samples + 32, 0); job.img->on_host = true; }
+        if (!R.gpu) { job.img->host_block.assign(total_samples + 32, 0); job.img->on_host = true; }
         total_ch += job.img->ch.size();
     }
     int16_t *stage = nullptr;
-    if (gpu) {
+    if (R.gpu) {
         const size_t need = std::max<size_t>(total_samples * sizeof(int16_t), 4096);
         if (need > ctx->host_stage_bytes) {
             FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1660,38 +1672,48 @@ int maniac_decode_host(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         }
         stage = (int16_t *)ctx->host_stage;
     }
-    std::vector<fbh::Chan> hch(total_ch);
+    R.hch.resize(total_ch);
     size_t coff = 0;
     for (int b = 0; b < nimg; b++) {
         FbManiacJob &job = jobs[b];
         fb_image *img = job.img;
-        himg[b].bytes = job.bytes_host; himg[b].nbytes = job.nbytes; himg[b].bytes_to_load = job.bytes_to_load;
-        himg[b].ch = hch.data() + coff; himg[b].nch = (int)img->ch.size(); himg[b].max_properties = job.max_properties;
-        himg[b].n_orig = img->info.real_nb_channels; himg[b].status = 0;
-        int16_t *base = gpu ? stage : img->host_block.data();
+        fbh::Image &hi = R.himg[b];
+        hi.bytes = job.bytes_host; hi.nbytes = job.nbytes; hi.bytes_to_load = job.bytes_to_load;
+        hi.ch = R.hch.data() + coff; hi.nch = (int)img->ch.size(); hi.max_properties = job.max_properties;
+        hi.n_orig = img->info.real_nb_channels; hi.status = 0;
+        int16_t *base = R.gpu ? stage : img->host_block.data();
         for (size_t i = 0; i < img->ch.size(); i++) {
             FbChan &c = img->ch[i];
-            fbh::Chan &d = hch[coff + i];
+            fbh::Chan &d = R.hch[coff + i];
             memset(&d, 0, sizeof(d));
             d.w = c.d.w; d.h = c.d.h; d.minval = c.d.minval; d.maxval = c.d.maxval; d.zero = c.d.zero; d.q = c.d.q;
             d.hshift = c.d.hshift; d.vshift = c.d.vshift; d.group_off = -1;
             d.data = base + plane_off[coff + i];
             if (!(c.d.w > 0 && c.d.h > 0)) { d.hdr_done = 1; d.rows_done = 0x7fffffff; }     // empty planes are skipped by the channel loop
         }
-        build_streams(job, b, streams);
+        build_streams(job, b, R.streams);
         coff += img->ch.size();
     }
-    group_major_order(streams, nimg);
-    ctx->host_threads_used = fbh::decode(himg.data(), nimg, streams.data(), (int)streams.size(), jobs[0].cutoff, (uint32_t)jobs[0].alpha, ctx->host_threads);
-    // ---- planes to HBM (or stay where they are, for a host-only image)
-    coff = 0;
+    group_major_order(R.streams, nimg);
+    return FB_OK;
+}
+
+void host_run(HostRun &R, int threads) {
+    R.threads_used = fbh::decode(R.himg.data(), (int)R.himg.size(), R.streams.data(), (int)R.streams.size(), R.cutoff, R.alpha, threads);
+}
+
+// planes to HBM (or they stay where they are, for a host-only image), then what every backend leaves in the image
+int host_finish(fb_ctx *ctx, std::vector<FbManiacJob> &jobs, HostRun &R) {
+    const int nimg = (int)jobs.size();
+    ctx->host_threads_used = R.threads_used;
+    size_t coff = 0;
     for (int b = 0; b < nimg; b++) {
         fb_image *img = jobs[b].img;
         for (size_t i = 0; i < img->ch.size(); i++) {
             FbChan &c = img->ch[i];
-            const fbh::Chan &d = hch[coff + i];
+            const fbh::Chan &d = R.hch[coff + i];
             if (!d.state) continue;
-            if (!gpu) { c.host = d.data; continue; }
+            if (!R.gpu) { c.host = d.data; continue; }
             const size_t n = (size_t)d.w * d.h;
             int rc = fb_plane_alloc(ctx, n, &c.dev);
             if (rc) return rc;
@@ -1699,12 +1721,42 @@ int maniac_decode_host(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         }
         coff += img->ch.size();
     }
-    if (gpu) FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the staging is free for the next call
+    if (R.gpu) FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the staging is free for the next call
     std::vector<int> status(nimg);
-    for (int b = 0; b < nimg; b++) status[b] = himg[b].status;
-    int rc = finish_images(ctx, jobs, hch, status);
+    for (int b = 0; b < nimg; b++) status[b] = R.himg[b].status;
+    int rc = finish_images(ctx, jobs, R.hch, status);
     if (rc == FB_ERR_UNSUPPORTED) ctx->err = "more properties than the host context model holds (max_properties > 100)";
     return rc;
+}
+
+int maniac_decode_host(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
+    HostRun R;
+    int rc = host_prepare(ctx, jobs, R);
+    if (rc) return rc;
+    host_run(R, ctx->host_threads);
+    return host_finish(ctx, jobs, R);
+}
+
+int maniac_decode_gpu(fb_ctx *ctx, std::vector<FbManiacJob> &jobs);
+
+// FB_ENTROPY_HYBRID: both engines at once on a batch.  The first hybrid_gpu_percent % of the images go to k_maniac_decode, the
+// rest to the host threads, which run while this thread sits in the GPU backend; their planes are uploaded when both are done.
+int maniac_decode_hybrid(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
+    const int nimg = (int)jobs.size();
+    int n_gpu = (nimg * ctx->hybrid_gpu_percent + 50) / 100;
+    n_gpu = std::max(1, std::min(nimg - 1, n_gpu));
+    std::vector<FbManiacJob> gj(jobs.begin(), jobs.begin() + n_gpu), hj(jobs.begin() + n_gpu, jobs.end());
+    HostRun R;
+    int rc = host_prepare(ctx, hj, R);
+    if (rc) return rc;
+    std::thread host([&]() { host_run(R, ctx->host_threads); });
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{host};     // also when the GPU part throws
+    const int rc_gpu = maniac_decode_gpu(ctx, gj);
+    host.join();
+    const std::string gpu_err = ctx->err;
+    const int rc_host = host_finish(ctx, hj, R);
+    if (rc_gpu) { ctx->err = gpu_err; return rc_gpu; }
+    return rc_host;
 }
 
 }  // namespace
@@ -1718,9 +1770,15 @@ void fb_maniac_release(fb_ctx *ctx) {
 }
 
 int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
-    const int nimg = (int)jobs.size();
-    if (!nimg) return FB_OK;
+    if (jobs.empty()) return FB_OK;
     if (ctx->entropy_backend == FB_ENTROPY_HOST || ctx->device < 0) return maniac_decode_host(ctx, jobs);
+    if (ctx->entropy_backend == FB_ENTROPY_HYBRID && jobs.size() >= 2) return maniac_decode_hybrid(ctx, jobs);
+    return maniac_decode_gpu(ctx, jobs);
+}
+
+namespace {
+int maniac_decode_gpu(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
+    const int nimg = (int)jobs.size();
     int cutoff = jobs[0].cutoff, alpha = jobs[0].alpha;
     // ---- plane allocation + descriptors
     std::vector<DImage> himg(nimg);
@@ -1785,11 +1843,11 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
         // Throughput shape for big batches: 8 streams per block, each ONE warp on the one-warp decode path (no walkers).  A stream is
         // slower (no run-ahead) but four times as many are in flight; measured on 64 x 1080p (3520 streams): 41.5 -> 71.1 Mpx/s
         // (4 per block: 61.4, 16 per block: 47.3 -- 13 KB of shared memory per stream is too little for the leaf cache).  Taken when
-        // the batch has at least 16 streams per SM; FB_MANIAC_SPB=n forces n (3..16) from sm_count * n streams on, 0 / 1 disables.
+        // the batch has at least 12 streams per SM; FB_MANIAC_SPB=n forces n (3..16) from sm_count * n streams on, 0 / 1 disables.
         static const int env_spb = getenv("FB_MANIAC_SPB") ? atoi(getenv("FB_MANIAC_SPB")) : -1;
         int spb_many = 0;
         if (env_spb > 2 && env_spb <= 16) { if (nstreams >= ctx->sm_count * env_spb) spb_many = env_spb; }
-        else if (env_spb < 0 && nstreams >= ctx->sm_count * 16) spb_many = 8;
+        else if (env_spb < 0 && nstreams >= ctx->sm_count * 12) spb_many = 8;
         const int nslots = spb_many ? ctx->sm_count * spb_many : std::min((nstreams + 1) / 2 * 2, ctx->sm_count * 2);        // scratch slots: one per stream in flight
         int rc = ensure_state(ctx, cutoff, alpha, nslots, maxw);
         if (rc) return rc;
@@ -1834,4 +1892,5 @@ int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
     for (int b = 0; b < nimg; b++) status[b] = himg[b].status;
     return finish_images(ctx, jobs, back, status);
 }
+}  // namespace
 #endif  // FB_EMULATE
