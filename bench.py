@@ -47,7 +47,6 @@ def parse_args():
     ap.add_argument("--strong", action="store_true", help="multi-image workloads (cfg4): split the fixed batch over the ranks (strong scaling)")
     ap.add_argument("--host-entropy-steps", type=int, default=1,
                     help="also time this many e2e steps with the host-threads entropy backend and report e2e_host_entropy (0 = skip)")
-    ap.add_argument("--hybrid-gpu-percent", type=int, default=55, help="hybrid entropy backend: share of a batch's images that go to the GPU")
     ap.add_argument("--host-threads", type=int, default=0, help="threads of the host entropy backend per GPU (0 = host cores / GPUs)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -328,9 +327,8 @@ def main():
     alt_entropy = {}
     if args.host_entropy_steps > 0:
         nthreads = args.host_threads or max(1, (os.cpu_count() or 1) // world)
-        # hybrid (batches only): gpu_percent % of the images on k_maniac_decode, the others on the host threads at the same time
-        for backend in ["host"] + (["hybrid"] if len(imgs) > 1 else []):
-            ctx.set_entropy_backend(backend, nthreads, args.hybrid_gpu_percent)
+        for backend in ["host"]:
+            ctx.set_entropy_backend(backend, nthreads)
             step_e2e()          # warm-up: the pinned staging is allocated once per context
             launches0 = ctx.launches
             barrier()
@@ -349,8 +347,7 @@ def main():
                 "value": total_units * (w * h / 1e6) / (he_ms / 1e3 / args.host_entropy_steps), "unit": "Mpx/s",
                 "ms_per_step": he_ms / args.host_entropy_steps, "steps": args.host_entropy_steps, "threads_per_gpu": ctx.host_threads_used,
                 "host_cores": os.cpu_count(), "gpu_launches_per_step": (ctx.launches - launches0) // args.host_entropy_steps,
-                "what": ("same call as e2e with the entropy stage on host threads (one channel group per thread), transform chain on the GPU" if backend == "host" else
-                         f"same call as e2e with {args.hybrid_gpu_percent} % of the images entropy-decoded by k_maniac_decode and the others by the host threads at the same time")}
+                "what": "same call as e2e with the entropy stage on host threads (one channel group per thread), transform chain on the GPU"}
         ctx.set_entropy_backend("gpu")
     host_entropy = alt_entropy.get("host")
 
@@ -479,7 +476,7 @@ def main():
         "value_no_index": no_index["value"] if no_index else None, "e2e_no_index": no_index["e2e"] if no_index else None, "no_index": no_index,
         "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": int(sum(len(im["fuif"]) for im in imgs)),
                 "d2h_bytes_per_step": int(n_per_gpu * w * h * c * bps)},
-        "e2e_host_entropy": host_entropy, "e2e_hybrid_entropy": alt_entropy.get("hybrid"),
+        "e2e_host_entropy": host_entropy,
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline,

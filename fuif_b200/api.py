@@ -34,8 +34,7 @@ FB_OPT_KERNEL_TIMING = 2
 FB_OPT_SQUEEZE_PACKED = 3
 FB_OPT_ENTROPY_BACKEND = 4
 FB_OPT_HOST_THREADS = 5
-FB_ENTROPY_GPU, FB_ENTROPY_HOST, FB_ENTROPY_HYBRID = 0, 1, 2
-FB_OPT_HYBRID_GPU_PERCENT = 6
+FB_ENTROPY_GPU, FB_ENTROPY_HOST = 0, 1
 
 
 class FuifError(RuntimeError):
@@ -247,14 +246,11 @@ class Context:
         self.check(self.lib.fb_selftest_packed(self.h, which, seed, scale, maxval, C.byref(n)), "fb_selftest_packed")
         return int(n.value)
 
-    def set_entropy_backend(self, backend: str, threads: int = 0, gpu_percent: int = 55) -> None:
+    def set_entropy_backend(self, backend: str, threads: int = 0) -> None:
         """'gpu' (default): k_maniac_decode; 'host': fuif_decode_channel on CPU threads (0 = one per hardware thread), planes uploaded
-        afterwards -- the faster backend for ONE large image with a group index; 'hybrid': batches split between the two
-        (gpu_percent % of the images on the GPU).  Identical planes and errors."""
-        self.check(self.lib.fb_ctx_set_option(self.h, FB_OPT_ENTROPY_BACKEND, {"gpu": FB_ENTROPY_GPU, "host": FB_ENTROPY_HOST, "hybrid": FB_ENTROPY_HYBRID}[backend]),
-                   "fb_ctx_set_option")
+        afterwards -- the faster backend for ONE large image with a group index.  Identical planes and errors."""
+        self.check(self.lib.fb_ctx_set_option(self.h, FB_OPT_ENTROPY_BACKEND, {"gpu": FB_ENTROPY_GPU, "host": FB_ENTROPY_HOST}[backend]), "fb_ctx_set_option")
         self.check(self.lib.fb_ctx_set_option(self.h, FB_OPT_HOST_THREADS, threads), "fb_ctx_set_option")
-        self.check(self.lib.fb_ctx_set_option(self.h, FB_OPT_HYBRID_GPU_PERCENT, gpu_percent), "fb_ctx_set_option")
 
     @property
     def host_threads_used(self) -> int:

@@ -48,7 +48,7 @@ struct fb_ctx {
     // Entropy backend (FB_OPT_ENTROPY_BACKEND): 0 = k_maniac_decode on the GPU (default), 1 = host threads (fb_host_entropy.cpp),
     // planes uploaded afterwards.  host_threads 0 = one per hardware thread.  host_stage: pinned staging the host backend decodes
     // into (grow-only, reused from call to call).  device < 0 marks the context of a host-only image (fb_host_decode): no CUDA at all.
-    int entropy_backend = 0, host_threads = 0, host_threads_used = 0, hybrid_gpu_percent = 55;
+    int entropy_backend = 0, host_threads = 0, host_threads_used = 0;
     void *host_stage = nullptr;
     size_t host_stage_bytes = 0;
     enum { kOptHsqTiled = 1, kOptPyramid = 2, kOptDirect = 4, kOptFq = 8, kOptPkH = 16 /* << variant, 5 bits */ };

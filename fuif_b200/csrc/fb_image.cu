@@ -52,8 +52,8 @@ extern "C" int fb_ctx_create(int device, void *stream, fb_ctx **out) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     ctx->timing_stderr = getenv("FB_KERNEL_TIMING") != nullptr;
     ctx->timing = ctx->timing_stderr;
-    // FUIF_B200_ENTROPY=host|hybrid|gpu presets FB_OPT_ENTROPY_BACKEND (fb_ctx_set_option still overrides it)
-    if (const char *e = getenv("FUIF_B200_ENTROPY")) ctx->entropy_backend = !strcmp(e, "host") ? FB_ENTROPY_HOST : (!strcmp(e, "hybrid") ? FB_ENTROPY_HYBRID : FB_ENTROPY_GPU);
+    // FUIF_B200_ENTROPY=host|gpu presets FB_OPT_ENTROPY_BACKEND (fb_ctx_set_option still overrides it)
+    if (const char *e = getenv("FUIF_B200_ENTROPY")) ctx->entropy_backend = !strcmp(e, "host") ? FB_ENTROPY_HOST : FB_ENTROPY_GPU;
     // keep freed plane memory in the stream-ordered pool instead of returning it to the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -102,8 +102,7 @@ extern "C" int fb_ctx_set_option(fb_ctx *ctx, int option, int value) {
     if (!ctx) return FB_ERR_INVALID;
     if (option == FB_OPT_SQUEEZE_MODE && value >= 0 && value <= 4) { ctx->fq_mode = value; return FB_OK; }
     if (option == FB_OPT_SQUEEZE_PACKED && value >= 0 && value <= 1) { ctx->pk_mode = value; return FB_OK; }
-    if (option == FB_OPT_ENTROPY_BACKEND && value >= FB_ENTROPY_GPU && value <= FB_ENTROPY_HYBRID) { ctx->entropy_backend = value; return FB_OK; }
-    if (option == FB_OPT_HYBRID_GPU_PERCENT && value >= 1 && value <= 99) { ctx->hybrid_gpu_percent = value; return FB_OK; }
+    if (option == FB_OPT_ENTROPY_BACKEND && (value == FB_ENTROPY_GPU || value == FB_ENTROPY_HOST)) { ctx->entropy_backend = value; return FB_OK; }
     if (option == FB_OPT_HOST_THREADS && value >= 0 && value <= 4096) { ctx->host_threads = value; return FB_OK; }
     if (option == FB_OPT_KERNEL_TIMING) { ctx->timing = value != 0 || ctx->timing_stderr; return FB_OK; }
     return FB_ERR_INVALID;

@@ -26,7 +26,6 @@
 #else
 #include "fb_common.cuh"
 #include "fb_host_entropy.h"
-#include <thread>
 #define FB_SPIN()
 #define FB_DYN_SMEM_DECL(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
@@ -1622,7 +1621,10 @@ int finish_images(fb_ctx *ctx, std::vector<FbManiacJob> &jobs, const std::vector
 // fb_host_entropy.cpp decodes into host memory -- pinned staging of the context, or the image's own block for a host-only image --
 // one thread per channel group (with the group index) or per image; the planes are then copied to HBM, where the transform
 // chain runs as with the GPU backend.  100 MB of planes of a 4096^2 image cross PCIe in a few ms against >= 1 s of decoding.
-// Three phases, so that the middle one (pure CPU work, touches nothing of the context) can run beside the GPU backend.
+// Three phases; the middle one is pure CPU work and touches nothing of the context.  (Tried on top of this split: a hybrid
+// backend that gave part of a batch's images to k_maniac_decode and the rest to the host threads at the same time.  No gain on
+// 64 x 1080p -- the GPU side takes 1.8 s for 35 images as for 64, its time is the longest single stream -- so it was dropped:
+// profiles/r02_hybrid_sweep_cfg4_experiment.txt.)
 struct HostRun {
     std::vector<std::vector<uint8_t>> file_copy;
     std::vector<fbh::Image> himg;
@@ -1739,26 +1741,6 @@ int maniac_decode_host(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
 
 int maniac_decode_gpu(fb_ctx *ctx, std::vector<FbManiacJob> &jobs);
 
-// FB_ENTROPY_HYBRID: both engines at once on a batch.  The first hybrid_gpu_percent % of the images go to k_maniac_decode, the
-// rest to the host threads, which run while this thread sits in the GPU backend; their planes are uploaded when both are done.
-int maniac_decode_hybrid(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
-    const int nimg = (int)jobs.size();
-    int n_gpu = (nimg * ctx->hybrid_gpu_percent + 50) / 100;
-    n_gpu = std::max(1, std::min(nimg - 1, n_gpu));
-    std::vector<FbManiacJob> gj(jobs.begin(), jobs.begin() + n_gpu), hj(jobs.begin() + n_gpu, jobs.end());
-    HostRun R;
-    int rc = host_prepare(ctx, hj, R);
-    if (rc) return rc;
-    std::thread host([&]() { host_run(R, ctx->host_threads); });
-    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{host};     // also when the GPU part throws
-    const int rc_gpu = maniac_decode_gpu(ctx, gj);
-    host.join();
-    const std::string gpu_err = ctx->err;
-    const int rc_host = host_finish(ctx, hj, R);
-    if (rc_gpu) { ctx->err = gpu_err; return rc_gpu; }
-    return rc_host;
-}
-
 }  // namespace
 
 void fb_maniac_release(fb_ctx *ctx) {
@@ -1772,7 +1754,6 @@ void fb_maniac_release(fb_ctx *ctx) {
 int fb_maniac_decode(fb_ctx *ctx, std::vector<FbManiacJob> &jobs) {
     if (jobs.empty()) return FB_OK;
     if (ctx->entropy_backend == FB_ENTROPY_HOST || ctx->device < 0) return maniac_decode_host(ctx, jobs);
-    if (ctx->entropy_backend == FB_ENTROPY_HYBRID && jobs.size() >= 2) return maniac_decode_hybrid(ctx, jobs);
     return maniac_decode_gpu(ctx, jobs);
 }
 

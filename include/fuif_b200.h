@@ -111,10 +111,6 @@ FB_API long long fb_ctx_launch_count(fb_ctx *ctx);
 #define FB_OPT_HOST_THREADS 5
 #define FB_ENTROPY_GPU 0
 #define FB_ENTROPY_HOST 1
-/* FB_ENTROPY_HYBRID: batches (fb_decode_batch with >= 2 images) use both engines at once -- the first FB_OPT_HYBRID_GPU_PERCENT %
- *   (default 55) of the images on the GPU backend, the others on the host threads meanwhile; single images as FB_ENTROPY_GPU. */
-#define FB_ENTROPY_HYBRID 2
-#define FB_OPT_HYBRID_GPU_PERCENT 6
 FB_API int fb_ctx_set_option(fb_ctx *ctx, int option, int value);
 /* The fused Squeeze inverse (mode >= 2) starts tiles speculatively and verifies them (results are bit-exact either way).
  * which = 0: Squeeze inverses so far that failed verification in an early launch and were recomputed serially;

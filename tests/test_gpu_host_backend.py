@@ -79,26 +79,3 @@ def test_backends_agree_on_a_1080p_image(ctx, hctx):
     assert hctx.host_threads_used == 4
     assert np.array_equal(a, b) and np.array_equal(np.asarray(a).reshape(pix.shape).astype(np.int32), pix)
 
-
-@pytest.mark.parametrize("percent", [20, 55, 80])
-def test_hybrid_backend_batch(oracle, percent):
-    """A batch split between k_maniac_decode and the host threads, both running at once: every image as the golden planes say."""
-    from fuif_b200 import api
-    po = oracle
-    c = api.Context(0)
-    try:
-        c.set_entropy_backend("hybrid", 3, percent)
-        names = ["sq128", "rgba14", "dct", "odd", "gray", "pred", "unc", "tall"]
-        datas = [bytes(load_golden(n)["fuif"]) for n in names]
-        idx = [api.fuif_host_decode(d).group_index() for d in datas]
-        for gi in (None, idx):
-            outs = api.fuif_decode_batch(datas, ctx=c, group_indexes=gi)
-            for n, o in zip(names, outs):
-                po.compare_plane_images(gpu_plane_image(po, o), po.parse_fbpd(load_golden(n)["s0"]), f"{n} hybrid {percent}%")
-            for n, o in zip(names[:3], outs[:3]):
-                o.undo_transforms(0)
-                po.compare_plane_images(gpu_plane_image(po, o), po.parse_fbpd(ordered(load_golden(n), "s")[-1]), f"{n} hybrid {percent}% undone")
-        single = api.fuif_decode(datas[0], ctx=c)          # a single image: the GPU backend
-        po.compare_plane_images(gpu_plane_image(po, single), po.parse_fbpd(load_golden("sq128")["s0"]), "hybrid, single image")
-    finally:
-        c.close()
