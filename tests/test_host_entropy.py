@@ -85,3 +85,42 @@ def test_host_image_needs_upload_before_computing():
     img = api.fuif_host_decode(bytes(load_golden("sq128")["fuif"]))
     with pytest.raises(api.FuifError):
         img.undo_transforms(0)
+
+
+import os  # noqa: E402
+import subprocess  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+
+AT_SIZE = [
+    # name, w, h, channels, maxval, seed, ref_driver encode options: trees of thousands of nodes, 14-bit planes (full leaf layout),
+    # multi-plane groups of the DCT chain, a non-zero predictor through the chunked row decoder
+    ("rgb_512", 512, 512, 3, 255, 1234, []),
+    ("raw14_640", 640, 480, 4, 16383, 9, ["-q", "12,64"]),
+    ("dct_odd_grouped", 600, 328, 3, 255, 11, ["-C", "1", "-J", "-q", "8,12"]),
+    ("pred6_gray", 700, 300, 1, 255, 5, ["-P", "6"]),
+]
+
+
+@pytest.mark.parametrize("case", AT_SIZE, ids=[c[0] for c in AT_SIZE])
+def test_host_decode_vs_reference_at_size(oracle, case, tmp_path):
+    """Against the UNMODIFIED reference run on the spot (ref_driver encodes a synthetic image and dumps its decoded planes)."""
+    from fuif_b200 import api
+    from fuif_b200.synth import synth_image, write_pnm
+    if not os.access(REF, os.X_OK):
+        pytest.skip("oracle/_ref/ref_driver is not built (needs /root/reference at build time)")
+    po = oracle
+    name, w, h, c, maxval, seed, opts = case
+    pnm, fuif, pre = str(tmp_path / "in.pnm"), str(tmp_path / "x.fuif"), str(tmp_path / "d")
+    write_pnm(pnm, synth_image(w, h, c, maxval, seed), maxval)
+    subprocess.run([REF, "encode", pnm, fuif, *opts], check=True, capture_output=True)
+    subprocess.run([REF, "dump", fuif, pre], check=True, capture_output=True)
+    dumps = sorted((f for f in os.listdir(tmp_path) if f.startswith("d.s") and f.endswith(".fbpd")), key=lambda f: int(f[3:-5]))
+    first = po.parse_fbpd(open(tmp_path / dumps[0], "rb").read())
+    data = open(fuif, "rb").read()
+    seq = api.fuif_host_decode(data, threads=1)
+    po.compare_plane_images(gpu_plane_image(po, seq), first, name + " host decode")
+    for rep in range(3):        # several runs with more threads than cores: the row wavefront between dependent groups under preemption
+        par = api.fuif_host_decode(data, group_index=seq.group_index(), threads=12)
+        po.compare_plane_images(gpu_plane_image(po, par), first, f"{name} host decode indexed, run {rep}")
