@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--strong", action="store_true", help="multi-image workloads (cfg4): split the fixed batch over the ranks (strong scaling)")
     ap.add_argument("--host-entropy-steps", type=int, default=1,
                     help="also time this many e2e steps with the host-threads entropy backend and report e2e_host_entropy (0 = skip)")
-    ap.add_argument("--host-threads", type=int, default=0, help="threads of the host entropy backend per GPU (0 = host cores / GPUs)")
+    ap.add_argument("--host-threads", type=int, default=0, help="threads of the host entropy backend per GPU (0 = 4 x host cores / GPUs)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -326,7 +326,7 @@ def main():
     # runs on the GPU as before.  A second number next to `e2e`, not a replacement: `value` / `e2e` stay the all-GPU path.
     alt_entropy = {}
     if args.host_entropy_steps > 0:
-        nthreads = args.host_threads or max(1, (os.cpu_count() or 1) // world)
+        nthreads = args.host_threads or max(1, 4 * (os.cpu_count() or 1) // world)      # the library's default, shared out over the ranks
         for backend in ["host"]:
             ctx.set_entropy_backend(backend, nthreads)
             step_e2e()          # warm-up: the pinned staging is allocated once per context

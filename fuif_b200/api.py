@@ -247,7 +247,7 @@ class Context:
         return int(n.value)
 
     def set_entropy_backend(self, backend: str, threads: int = 0) -> None:
-        """'gpu' (default): k_maniac_decode; 'host': fuif_decode_channel on CPU threads (0 = one per hardware thread), planes uploaded
+        """'gpu' (default): k_maniac_decode; 'host': fuif_decode_channel on CPU threads (0 = four per hardware thread, at most one per stream), planes uploaded
         afterwards -- the faster backend for ONE large image with a group index.  Identical planes and errors."""
         self.check(self.lib.fb_ctx_set_option(self.h, FB_OPT_ENTROPY_BACKEND, {"gpu": FB_ENTROPY_GPU, "host": FB_ENTROPY_HOST}[backend]), "fb_ctx_set_option")
         self.check(self.lib.fb_ctx_set_option(self.h, FB_OPT_HOST_THREADS, threads), "fb_ctx_set_option")

@@ -46,7 +46,7 @@ struct fb_ctx {
     // device), not per process, so that a context on a second GPU of the same process gets them too
     unsigned smem_optin = 0;
     // Entropy backend (FB_OPT_ENTROPY_BACKEND): 0 = k_maniac_decode on the GPU (default), 1 = host threads (fb_host_entropy.cpp),
-    // planes uploaded afterwards.  host_threads 0 = one per hardware thread.  host_stage: pinned staging the host backend decodes
+    // planes uploaded afterwards.  host_threads 0 = four per hardware thread, at most one per stream.  host_stage: pinned staging the host backend decodes
     // into (grow-only, reused from call to call).  device < 0 marks the context of a host-only image (fb_host_decode): no CUDA at all.
     int entropy_backend = 0, host_threads = 0, host_threads_used = 0;
     void *host_stage = nullptr;

@@ -444,7 +444,7 @@ FBH_INLINE void decode_row(const Chan &ch, int y, int predictor, int nused, cons
 // loop exits than it saved.)
 constexpr int kChunk = 64;
 template <bool PRED0>
-FBH_INLINE void decode_row_chunked(const Chan &ch, int y, int predictor, int nused, const int *used_ref, int nref, int stride, int *pc,
+__attribute__((noinline)) void decode_row_chunked(const Chan &ch, int y, int predictor, int nused, const int *used_ref, int nref, int stride, int *pc,
                                    const int16_t *refrow, Rac &rac, const uint16_t *table, const Node *nodes, uint16_t *leaves, int leaf_shift,
                                    int mant_base) {
     const int w = ch.w, zero = ch.zero, cmin = ch.minval, cmax = ch.maxval;
@@ -700,7 +700,10 @@ int decode(Image *images, int nimages, const Stream *streams, int nstreams, int 
     std::vector<Tables> tables(1);
     build_table(tables[0].table, alpha, (unsigned)(4096 - cutoff));
     build_table(tables[0].meta, 0xFFFFFFFFu / 19, 4096 - 2);
-    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    // Default: up to four threads per hardware thread.  Streams are claimed in index order (the dependency rule), which puts the
+    // largest groups of a file last; with more threads than cores they are all claimed at once and the OS shares the cores out
+    // until the small ones are gone (4096^2, 61 groups, 8 cores: 2.7 s with 8 threads, 2.1 s with 16 or 61).  Waiting threads yield.
+    if (threads <= 0) threads = 4 * std::max(1, (int)std::thread::hardware_concurrency());
     threads = std::max(1, std::min(threads, nstreams));
     std::atomic<int> ticket{0};
     auto worker = [&]() {

@@ -106,7 +106,8 @@ FB_API long long fb_ctx_launch_count(fb_ctx *ctx);
  *   one image per thread without), planes copied to HBM afterwards; the transform chain stays on the GPU either way.  The
  *   serial coder of ONE group runs ~6x faster on a CPU core than on a GPU warp, so this is the backend for a single large
  *   image with a group index; batches that fill the GPU (hundreds of groups) are faster on the GPU backend.  Planes and
- *   errors are identical.  FB_OPT_HOST_THREADS: threads of the host backend, 0 (default) = one per hardware thread. */
+ *   errors are identical.  FB_OPT_HOST_THREADS: threads of the host backend, 0 (default) = four per hardware thread, at most one per
+ *   stream (the large groups of a file come last in the claim order; oversubscribing starts them at once). */
 #define FB_OPT_ENTROPY_BACKEND 4
 #define FB_OPT_HOST_THREADS 5
 #define FB_ENTROPY_GPU 0
@@ -151,7 +152,7 @@ FB_API int fb_decode(fb_ctx *ctx, const uint8_t *bytes, size_t nbytes, const fb_
               const int64_t *group_index, const int32_t *group_first, int n_groups, fb_image **out);
 
 /* The host-threads entropy backend on its own, without any GPU (no fb_ctx): container parse + fuif_decode_channel on `threads`
- * CPU threads (0 = one per hardware thread).  The image it returns lives in HOST memory: fb_image_get_info / get_plane /
+ * CPU threads (0 = four per hardware thread, at most one per stream).  The image it returns lives in HOST memory: fb_image_get_info / get_plane /
  * get_transform / download_plane / group_index / destroy work on it, everything that computes returns FB_ERR_INVALID until
  * fb_image_upload() has moved it to a context's GPU.  fb_decode() with FB_OPT_ENTROPY_BACKEND = FB_ENTROPY_HOST is this plus the
  * upload (through pinned staging).  On failure *out is NULL and fb_host_last_error() (thread-local) has the message. */
