@@ -672,20 +672,24 @@ void run_stream(Image *images, const Stream &st, const Tables &T, Scratch &S) {
     Image &img = images[st.image];
     Reader io{img.bytes, img.nbytes, st.offset, img.bytes_to_load, false};
     int groups = 0;
-    for (int i = st.first_channel; i < img.nch; i++) {
-        if (st.max_groups >= 0 && groups >= st.max_groups) break;
-        if ((img.bytes_to_load == 0 || io.pos < img.bytes_to_load) && !io.eof) {
-            if (!img.ch[i].w || !img.ch[i].h) continue;
-            const bool ok = decode_group(img, io, i, T, S);
-            groups++;
-            if (!ok) {
-                int expected = 0;
-                __atomic_compare_exchange_n(&img.status, &expected, (int)FB_ERR_INVALID, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
-                break;
-            }
-        } else break;
+    try {
+        for (int i = st.first_channel; i < img.nch; i++) {
+            if (st.max_groups >= 0 && groups >= st.max_groups) break;
+            if ((img.bytes_to_load == 0 || io.pos < img.bytes_to_load) && !io.eof) {
+                if (!img.ch[i].w || !img.ch[i].h) continue;
+                const bool ok = decode_group(img, io, i, T, S);
+                groups++;
+                if (!ok) {
+                    int expected = 0;
+                    __atomic_compare_exchange_n(&img.status, &expected, (int)FB_ERR_INVALID, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
+                    break;
+                }
+            } else break;
+        }
+    } catch (...) {     // out of memory for a tree of a damaged file: an exception must not leave a worker thread
+        __atomic_store_n(&img.status, (int)FB_ERR_NOMEM, __ATOMIC_RELAXED);
     }
-    // whatever happened (truncation, corruption), nobody may wait forever on this stream's planes
+    // whatever happened (truncation, corruption, an exception), nobody may wait forever on this stream's planes
     for (int c = st.first_channel; c < st.end_channel && c < img.nch; c++) {
         st_release(&img.ch[c].hdr_done, 1);
         st_release(&img.ch[c].rows_done, 0x7fffffff);

@@ -1611,6 +1611,7 @@ int finish_images(fb_ctx *ctx, std::vector<FbManiacJob> &jobs, const std::vector
         }
         if (status[b] == FB_ERR_UNSUPPORTED) { ctx->err = "max_properties > 18 is not supported by the GPU context model"; rc = FB_ERR_UNSUPPORTED; }
         else if (status[b] == kStatusTreeTooLarge) { ctx->err = "a MANIAC tree of this file has more than 65535 nodes: not supported by this decoder (image " + std::to_string(b) + ")"; rc = FB_ERR_UNSUPPORTED; }
+        else if (status[b] == FB_ERR_NOMEM) { ctx->err = "out of memory while decoding image " + std::to_string(b); rc = FB_ERR_NOMEM; }
         else if (status[b]) { ctx->err = "corrupt FUIF stream (image " + std::to_string(b) + ")"; rc = FB_ERR_INVALID; }
         coff += img->ch.size();
     }
