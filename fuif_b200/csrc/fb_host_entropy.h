@@ -33,7 +33,8 @@ struct Stream {         // planes [first_channel, end_channel) starting at byte 
 
 // Decodes every stream.  A stream only ever waits for planes of streams with a lower index (its back-references), and
 // streams are claimed in index order, so any thread count >= 1 makes progress.  threads <= 0: four per hardware thread (at most one per stream).
-// Returns the number of threads used.
+// Large planes may add a look-ahead helper thread each while hardware threads are free (never when threads == 1).
+// Returns the number of worker threads used.
 int decode(Image *images, int nimages, const Stream *streams, int nstreams, int cutoff, uint32_t alpha, int threads);
 
 }  // namespace fbh
