@@ -365,6 +365,10 @@ FBH_INLINE int predict(int predictor, int left, int top, int topleft, int toprig
 
 // precompute_references, context_predict.h:233-289: for every x of row y the co-located sample of a referenced plane
 void reference_row(const Chan &ch, const Chan &cj, int y, int16_t *out) {
+    if (cj.w <= 0 || cj.h <= 0) {       // an empty plane can be "referenced" (its default range is not a constant); the reference reads
+        memset(out, 0, (size_t)ch.w * sizeof(int16_t));     // out of bounds there -- nothing to be exact about, so: zeros
+        return;
+    }
     int ry = shr(shl(y, ch.vshift), cj.vshift);
     if (ry >= cj.h) ry = cj.h - 1;
     const int16_t *src = cj.data + (size_t)ry * cj.w;
