@@ -204,7 +204,7 @@ int read_int2(Rac &rac, const uint16_t *table, uint16_t *leaf, int mn, int mx) {
     return read_int(rac, table, leaf, mn, mx);
 }
 FBH_INLINE int uniform_read(Rac &rac, int mn, int len) {    // UniformSymbolCoder::read_int, symbol.h:44-56
-    while (len != 0) {
+    while (len > 0) {       // len < 0 only comes out of a damaged header (the reference asserts); it must not loop forever
         const int med = len / 2;
         if (rac.read_bit()) { mn = mn + med + 1; len = len - (med + 1); }
         else len = med;
@@ -703,7 +703,7 @@ bool corrupt_or_truncated(bool stopped, Chan &c) {      // encoding.cpp:209-219:
 }
 
 // fuif_decode_channel, encoding.cpp:259-429.  Returns false on a hard error; `beginc` is advanced to the group's last plane.
-bool decode_group(Image &img, Reader &io, int &beginc, const Tables &T, Scratch &S) {
+bool decode_group(Image &img, Reader &io, int &beginc, int limit, const Tables &T, Scratch &S) {
     if (io.stop()) return true;
     const long long header_pos = (long long)io.pos;
     const int firstbyte = io.varint();
@@ -718,7 +718,10 @@ bool decode_group(Image &img, Reader &io, int &beginc, const Tables &T, Scratch 
     if (io.stop()) return true;
     const int global_maxv = s16(global_minv + io.varint());
     if (io.stop()) return true;
-    if (endc >= img.nch || endc < beginc) return false;
+    // `limit`: the planes of this stream end there.  A group that reaches beyond them (a group index that does not belong to the file, a
+    // damaged header) would write planes another stream owns -- and could lower their `rows_done` after the owner released it, which
+    // leaves every stream that waits for those rows spinning forever.  Corrupt, not garbage.
+    if (endc >= img.nch || endc < beginc || endc >= limit) return false;
     img.ch[b0].group_off = header_pos;
 
     int firstrealc = beginc;
@@ -735,7 +738,8 @@ bool decode_group(Image &img, Reader &io, int &beginc, const Tables &T, Scratch 
         if (ch.minval == 0 && ch.maxval == 0) continue;
         ch.q = io.varint();
         if (io.stop()) { early = true; early_result = corrupt_or_truncated(true, ch); break; }
-        if (compress && !check_bit_depth(ch.minval, ch.maxval, predictor)) { early = true; early_result = false; break; }
+        // an inverted range only comes out of a damaged header (the reference runs into its asserts there): corrupt, like a failed depth check
+        if (ch.maxval < ch.minval || (compress && !check_bit_depth(ch.minval, ch.maxval, predictor))) { early = true; early_result = false; break; }
     }
     for (int i = beginc; i <= endc; i++) {
         Chan &ch = img.ch[i];
@@ -788,6 +792,7 @@ bool decode_group(Image &img, Reader &io, int &beginc, const Tables &T, Scratch 
     }
     // FinalPropertySymbolCoder ctor, compound.h:213-225: leaf numbering in node order, all leaves start from zero_chance
     const int nnodes = (int)S.prop_of.size();
+    if (T.debug) fprintf(stderr, "[host entropy] group at %lld: planes %d-%d, predictor %d, %d properties, tree of %d nodes\n", header_pos, beginc, endc, predictor, nprops, nnodes);
     S.nodes.resize((size_t)nnodes + 2);
     Node *nodes = (Node *)(((uintptr_t)S.nodes.data() + 15) & ~(uintptr_t)15);     // slot 0 unused; slots 2k, 2k + 1 share 16 bytes
     int nleaves = 0;
@@ -876,7 +881,7 @@ void run_stream(Image *images, const Stream &st, const Tables &T, Scratch &S) {
             if (st.max_groups >= 0 && groups >= st.max_groups) break;
             if ((img.bytes_to_load == 0 || io.pos < img.bytes_to_load) && !io.eof) {
                 if (!img.ch[i].w || !img.ch[i].h) continue;
-                const bool ok = decode_group(img, io, i, T, S);
+                const bool ok = decode_group(img, io, i, st.end_channel, T, S);
                 groups++;
                 if (!ok) {
                     int expected = 0;

@@ -255,7 +255,7 @@ __device__ int read_int2(Rac &rac, const uint16_t *table, uint16_t *leaf, int mn
     return read_int(rac, table, leaf, mn, mx);
 }
 __device__ int uniform_read(Rac &rac, int mn, int len) {    // UniformSymbolCoder::read_int, symbol.h:44-56
-    while (len != 0) {
+    while (len > 0) {       // len < 0 only comes out of a damaged header (the reference asserts); it must not loop forever
         int med = len / 2;
         if (rac.read_bit()) { mn = mn + med + 1; len = len - (med + 1); }
         else len = med;
@@ -1087,7 +1087,7 @@ __device__ __forceinline__ void decode_row(DImage &img, DChan &ch, int y, int pr
 
 // fuif_decode_channel, encoding.cpp:259-429.  Returns false on a hard error. `beginc` is advanced to the group's last channel.
 // `io` is kept identical in all lanes on entry and on exit; in between only lane 0's copy (inside `rac`) advances.
-__device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params &P, WarpScratch &ws, int lane, const Smem &sm) {
+__device__ bool decode_group(DImage &img, Reader &io, int &beginc, int limit, const Params &P, WarpScratch &ws, int lane, const Smem &sm) {
     if (io.stop()) return true;
     const long long header_pos = (long long)io.pos;
     const int firstbyte = io.varint();
@@ -1103,7 +1103,10 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
     const int global_maxv = s16(global_minv + io.varint());
     if (io.stop()) return true;
     if (P.debug && lane == 0) printf("[maniac] group at %lld: ch %d-%d compress %d pred %d range %d..%d\n", header_pos, beginc, endc, (int)compress, predictor, global_minv, global_maxv);
-    if (endc >= img.nch || endc < beginc) return false;
+    // `limit`: the planes of this stream end there.  A group that reaches beyond them (a group index that does not belong to the file, a
+    // damaged header) would write planes another stream owns -- and could lower their `rows_done` after the owner released it, which
+    // leaves every stream that waits for those rows spinning forever.  Corrupt, not garbage.
+    if (endc >= img.nch || endc < beginc || endc >= limit) return false;
     img.ch[b0].group_off = header_pos;
 
     int firstrealc = beginc;
@@ -1120,7 +1123,8 @@ __device__ bool decode_group(DImage &img, Reader &io, int &beginc, const Params 
         if (ch.minval == 0 && ch.maxval == 0) continue;
         ch.q = io.varint();
         if (io.stop()) { early = true; early_result = corrupt_or_truncated(true, ch, lane); break; }
-        if (compress && !check_bit_depth(ch.minval, ch.maxval, predictor)) { early = true; early_result = false; break; }
+        // an inverted range only comes out of a damaged header (the reference runs into its asserts there): corrupt, like a failed depth check
+        if (ch.maxval < ch.minval || (compress && !check_bit_depth(ch.minval, ch.maxval, predictor))) { early = true; early_result = false; break; }
     }
     for (int i = beginc; i <= endc; i++) {
         DChan &ch = img.ch[i];
@@ -1422,7 +1426,7 @@ __global__ void __launch_bounds__(512, 1) k_maniac_decode(Params P) {
             if (st.max_groups >= 0 && groups >= st.max_groups) break;
             if ((img.bytes_to_load == 0 || io.pos < img.bytes_to_load) && !io.eof) {
                 if (!img.ch[i].w || !img.ch[i].h) continue;
-                bool ok = decode_group(img, io, i, P, ws, lane, sm);
+                bool ok = decode_group(img, io, i, st.end_channel, P, ws, lane, sm);
                 groups++;
                 if (!ok) { if (!img.status) img.status = FB_ERR_INVALID; break; }
             } else break;
@@ -1560,6 +1564,9 @@ void build_streams(const FbManiacJob &job, int b, std::vector<S> &streams) {
             if (i >= nch || job.group_index[g] < (int64_t)job.body_pos || pos >= job.nbytes) { indexed = false; break; }
             if (job.bytes_to_load && pos >= job.bytes_to_load) break;
             if (job.group_first) {
+                // the first stream must start at the first plane there is: planes before it would belong to no stream, nobody would
+                // ever release them, and a stream that references them would wait forever
+                if (mine.empty() && job.group_first[g] != i) { indexed = false; break; }
                 i = job.group_first[g];
                 if (i < 0 || i >= nch || (!mine.empty() && i <= mine.back().first_channel)) { indexed = false; break; }
             } else {
