@@ -16,6 +16,9 @@
 
 #include <stdio.h>
 #include <string.h>
+#ifdef __linux__
+#include <sched.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
@@ -900,22 +903,32 @@ void run_stream(Image *images, const Stream &st, const Tables &T, Scratch &S) {
     }
 }
 
+// hardware threads this process may run on (its affinity mask: a cpuset-restricted container has fewer than the machine)
+int hardware_threads() {
+#ifdef __linux__
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) return CPU_COUNT(&set);
+#endif
+    return std::max(1, (int)std::thread::hardware_concurrency());
+}
+
 }  // namespace
 
 int decode(Image *images, int nimages, const Stream *streams, int nstreams, int cutoff, uint32_t alpha, int threads) {
     (void)nimages;
     if (nstreams <= 0) return 0;
+    const int hw = hardware_threads();
     std::vector<Tables> tables(1);
     build_table(tables[0].table, alpha, (unsigned)(4096 - cutoff));
     build_table(tables[0].meta, 0xFFFFFFFFu / 19, 4096 - 2);
     tables[0].helpers = threads != 1;
     tables[0].debug = getenv("FB_HOST_DEBUG") != nullptr;
-    tables[0].hw_threads = std::max(1, (int)std::thread::hardware_concurrency());
+    tables[0].hw_threads = hw;
     tables[0].busy.store(0);
     // Default: up to four threads per hardware thread.  Streams are claimed in index order (the dependency rule), which puts the
     // largest groups of a file last; with more threads than cores they are all claimed at once and the OS shares the cores out
     // until the small ones are gone (4096^2, 61 groups, 8 cores: 2.7 s with 8 threads, 2.1 s with 16 or 61).  Waiting threads yield.
-    if (threads <= 0) threads = 4 * std::max(1, (int)std::thread::hardware_concurrency());
+    if (threads <= 0) threads = 4 * hw;
     threads = std::max(1, std::min(threads, nstreams));
     std::atomic<int> ticket{0};
     auto worker = [&]() {
