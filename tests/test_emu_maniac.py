@@ -134,3 +134,15 @@ def test_responsive_truncation(oracle, name, preview, indexed):
     """-R k: the stream stops at a responsive offset (encoding.cpp:704-716): planes beyond it stay undecoded, a plane cut in
     the middle keeps its initial fill"""
     _check(oracle, bytes(load_golden(name)["fuif"]), meta=False, indexed=indexed, preview=preview)
+
+
+@pytest.mark.parametrize("shape", [0, 1], ids=["one_stream_per_block", "two_streams_two_blocks"])
+def test_kernel_source_survives_damaged_input(shape):
+    """120 damaged files / bogus group offsets per launch shape through the emulated kernel in a child process: every launch ends
+    (no spin-wait on rows nobody will publish, no endless coder loop).  The same inputs hang a GPU if they hang here."""
+    import sys
+    child = os.path.join(HERE, "emu_maniac_fuzz_child.py")
+    lib()       # build the emulator library here, not under the child's timeout
+    r = subprocess.run([sys.executable, child, str(21 + shape), "120", str(shape)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-800:]
+    assert "returned 120 times" in r.stdout
