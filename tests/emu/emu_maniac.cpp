@@ -48,10 +48,10 @@ int emu_maniac_decode(const uint8_t *bytes, size_t nbytes, size_t body_pos, int 
     std::vector<uint16_t> table(4096 * 2), meta(4096 * 2);
     build_table(meta.data(), 0xFFFFFFFFu / 19, 4096 - 2);
     build_table(table.data(), (uint32_t)alpha, (unsigned)(4096 - cutoff));
-    const int wpb = shape == 1 ? 2 : 1;
+    const int wpb = shape == 1 ? 2 : (shape == 3 ? 8 : 1);     // shape 3: the throughput shape of big batches, 8 one-warp streams per block
     Params P;
     memset(&P, 0, sizeof(P));
-    P.helpers = shape == 2 ? 0 : (shape ? 7 : 15);      // shape 2: no walkers at all (the one-warp path for every group)
+    P.helpers = (shape == 2 || shape == 3) ? 0 : (shape ? 7 : 15);      // shapes 2, 3: no walkers at all (the one-warp path for every group)
     const int nslots = nblocks * wpb;
     std::vector<WarpScratch> ws((size_t)nslots);
     std::vector<std::vector<unsigned char>> arena((size_t)nslots);

@@ -136,7 +136,14 @@ def test_responsive_truncation(oracle, name, preview, indexed):
     _check(oracle, bytes(load_golden(name)["fuif"]), meta=False, indexed=indexed, preview=preview)
 
 
-@pytest.mark.parametrize("shape", [0, 1], ids=["one_stream_per_block", "two_streams_two_blocks"])
+@pytest.mark.parametrize("name", ["odd", "dct", "sq128", "rgba14", "pred", "unc"])
+def test_throughput_shape_eight_one_warp_streams_per_block(oracle, name):
+    """the launch shape of big batches (fb_maniac.cu: from 12 streams per SM on): 8 streams per block, one warp each, no walkers; two
+    blocks, so streams also wait for planes decoded in the other block"""
+    _check(oracle, bytes(load_golden(name)["fuif"]), indexed=True, shape=3, nblocks=2)
+
+
+@pytest.mark.parametrize("shape", [0, 1, 3], ids=["one_stream_per_block", "two_streams_two_blocks", "eight_one_warp_streams"])
 def test_kernel_source_survives_damaged_input(shape):
     """120 damaged files / bogus group offsets per launch shape through the emulated kernel in a child process: every launch ends
     (no spin-wait on rows nobody will publish, no endless coder loop).  The same inputs hang a GPU if they hang here."""
