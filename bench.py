@@ -348,6 +348,21 @@ def main():
                 "ms_per_step": he_ms / args.host_entropy_steps, "steps": args.host_entropy_steps, "threads_per_gpu": ctx.host_threads_used,
                 "host_cores": os.cpu_count(), "gpu_launches_per_step": (ctx.launches - launches0) // args.host_entropy_steps,
                 "what": "same call as e2e with the entropy stage on host threads (one channel group per thread), transform chain on the GPU"}
+            if not args.no_index and args.no_index_steps > 0:
+                # ... and without the sidecar: what the reference arm gets too (one stream per file; a large plane may add a look-ahead
+                # helper thread)
+                barrier()
+                t0 = time.perf_counter()
+                step_e2e(indexed=False)
+                torch.cuda.synchronize()
+                hn_ms, _ = shard.reduce_step_time((time.perf_counter() - t0) * 1e3, len(units), device="cuda")
+                if lossless:
+                    got = pin_out[0].numpy()
+                    if bps == 2:
+                        got = got.view(">u2")
+                    assert np.array_equal(got.astype(np.int32), synth_image(w, h, c, maxval, spec_seed0)), "un-indexed host-entropy e2e pixels differ"
+                alt_entropy[backend]["no_index"] = {"value": total_units * (w * h / 1e6) / (hn_ms / 1e3), "unit": "Mpx/s", "ms_per_step": hn_ms, "steps": 1,
+                                                    "worker_threads_per_gpu": ctx.host_threads_used}
         ctx.set_entropy_backend("gpu")
     host_entropy = alt_entropy.get("host")
 
@@ -482,7 +497,7 @@ def main():
         "value_no_index": no_index["value"] if no_index else None, "e2e_no_index": no_index["e2e"] if no_index else None, "no_index": no_index,
         "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": int(sum(len(im["fuif"]) for im in imgs)),
                 "d2h_bytes_per_step": int(n_per_gpu * w * h * c * bps)},
-        "e2e_host_entropy": host_entropy,
+        "e2e_host_entropy": host_entropy, "e2e_host_entropy_no_index": (host_entropy or {}).get("no_index", {}).get("value"),
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline,
