@@ -147,7 +147,9 @@ FB_API long long fb_ctx_timing_report(fb_ctx *ctx, char *buf, size_t cap);
  * End-of-stream follows FileIO (reference fileio.h:33-81).
  * Limits (the reference has none; exceeding one returns FB_ERR_UNSUPPORTED with a message, never a crash): at most 4096
  * channels and 2^31 pixels per channel in the header, 4096 transforms, MANIAC trees of at most 65535 nodes,
- * max_properties <= 18.  A damaged stream decodes to garbage planes or FB_ERR_INVALID; the call always returns. */
+ * max_properties <= 18.  A damaged stream, or a group index that does not belong to the file, decodes to garbage planes or
+ * FB_ERR_INVALID; the call always returns (a group header with an inverted value range, and a group that reaches beyond the planes
+ * the index gives its stream, are FB_ERR_INVALID: the reference asserts / overruns there). */
 FB_API int fb_decode(fb_ctx *ctx, const uint8_t *bytes, size_t nbytes, const fb_decode_options *opts,
               const int64_t *group_index, const int32_t *group_first, int n_groups, fb_image **out);
 
